@@ -1,0 +1,51 @@
+import os
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
+
+
+def pytest_collection_modifyitems(config, items):
+    try:
+        import torch
+
+        has_gpu = torch.cuda.is_available()
+    except Exception:  # pragma: no cover
+        has_gpu = False
+    if has_gpu:
+        return
+    skip = pytest.mark.skip(reason="no CUDA device")
+    for item in items:
+        if "gpu" in item.keywords:
+            item.add_marker(skip)
+
+
+@pytest.fixture(scope="session")
+def port():
+    from oracle import cpu
+
+    if not cpu.available("port"):
+        cpu.build("port")
+    return cpu.CpuLib("port")
+
+
+@pytest.fixture(scope="session")
+def ref():
+    """The unmodified reference CPU library (prebuilt oracle/_ref travels to the GPU box)."""
+    from oracle import cpu
+
+    if not cpu.available("reference"):
+        try:
+            cpu.build("reference")
+        except Exception:
+            pass
+    if not cpu.available("reference"):
+        pytest.skip("oracle/_ref/libdeepmd_ref.so not built (needs /root/reference)")
+    return cpu.CpuLib("reference")
