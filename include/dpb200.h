@@ -1,0 +1,184 @@
+/* dpb200 — C ABI of the B200-native compressed se_e2_a / se_atten force-evaluation hot path.
+ *
+ * This is the drop-in boundary: plain device pointers, sizes and a CUDA
+ * stream; no torch / TF types.  Every entry point names the reference interface it
+ * replaces (paths relative to /root/reference).  The reference-side bindings (C++
+ * `deepmd::*_gpu` shim, torch ops) that a maintainer adds on top are shown in
+ * INTEGRATION.md and live in deepmd-kit_b200/csrc/deepmd_gpu_shim.cc and
+ * deepmd-kit_b200/ops.py.
+ *
+ * Conventions
+ *  - `_f64` / `_f32` suffix = FPTYPE of the reference template instantiation.
+ *  - All array arguments are DEVICE pointers unless marked [host].
+ *  - Outputs need not be pre-zeroed (the reference wrappers memset them; so do we).
+ *  - Work is enqueued on `stream` and NOT synchronised (the reference synchronises the whole
+ *    device around every kernel; callers that rely on that must synchronise the stream).
+ *  - Return value: DPB200_OK or a negative DPB200_ERR_*; dpb200_last_error() gives the
+ *    thread-local message.  There is no CPU fallback: without a CUDA device every compute
+ *    entry point returns DPB200_ERR_CUDA.
+ */
+#ifndef DPB200_H_
+#define DPB200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DPB200_OK 0
+#define DPB200_ERR_INVALID (-1)        /* bad argument (maps to deepmd::deepmd_exception) */
+#define DPB200_ERR_CUDA (-2)           /* CUDA runtime error */
+#define DPB200_ERR_OOM (-3)            /* maps to deepmd::deepmd_exception_oom (errors.h:17-22) */
+#define DPB200_ERR_NLIST_CAPACITY (-4) /* maps to deepmd_exception_nlist_capacity (errors.h:30-33) */
+
+#define DPB200_MAX_NBOR_SIZE 4096 /* GPU_MAX_NBOR_SIZE, source/lib/include/gpu_cuda.h:20 */
+#define DPB200_MAX_TYPES 128      /* 7 type bits in the sort key (same limit as prod_env_mat.cu:83-104) */
+#define DPB200_MAX_NALL (1 << 26) /* 26 index bits in the sort key (reference: 1<<24) */
+
+typedef struct CUstream_st* dpb200_stream_t; /* == cudaStream_t */
+
+const char* dpb200_last_error(void);
+int dpb200_abi_version(void);
+
+/* ---------------------------------------------------------------------------------------
+ * prod_env_mat_a : neighbour formatting + environment matrix + normalisation, one launch.
+ * Replaces deepmd::prod_env_mat_a_gpu  (source/lib/include/prod_env_mat.h:91-110,
+ * source/lib/src/gpu/prod_env_mat.cu:681-726); results follow the CPU semantics of
+ * prod_env_mat_a_cpu (source/lib/src/prod_env_mat.cc:14-132): nlist bit-exact with
+ * format_nlist_i_cpu (source/lib/src/fmt_nlist.cc:98-143).
+ *
+ * Raw neighbour rows: row r (r < nframes*nloc) holds numneigh[r] indices of centre atom
+ * ilist[r] (ilist==NULL: centre r).  Either `firstneigh` (device array of device row
+ * pointers, the InputNlist layout of neighbor_list.h:20-57 after convert_nlist_gpu_device)
+ * or, when firstneigh==NULL, a dense block `rows` with `row_stride` ints per row.
+ * max_nbor_size: upper bound of numneigh (row capacity), <= DPB200_MAX_NBOR_SIZE.
+ * f_type may be NULL (= type).  sec [host] has nsec = ntypes+1 entries.
+ * workspace: >= dpb200_prod_env_mat_a_workspace_bytes(...) bytes, 256-byte aligned.
+ * ------------------------------------------------------------------------------------- */
+size_t dpb200_prod_env_mat_a_workspace_bytes(int ntypes, int nnei, int nall, int nframes, int fp_bytes);
+
+#define DPB200_DECL_ENV(SUF, FP)                                                                  \
+  int dpb200_prod_env_mat_a_##SUF(FP* em, FP* em_deriv, FP* rij, int* nlist, const FP* coord,     \
+                                  const int* type, const int* f_type, const int* ilist,           \
+                                  const int* numneigh, const int* const* firstneigh,              \
+                                  const int* rows, int row_stride, int max_nbor_size,             \
+                                  const FP* avg, const FP* std, int nloc, int nall, int nframes,  \
+                                  float rcut, float rcut_smth, const int* sec, int nsec,          \
+                                  void* workspace, size_t workspace_bytes, dpb200_stream_t stream); \
+  /* format only: replaces deepmd::format_nbor_list_gpu (source/lib/include/fmt_nlist.h:22-34) */ \
+  int dpb200_format_nlist_##SUF(int* nlist, const FP* coord, const int* type, const int* ilist,   \
+                                const int* numneigh, const int* const* firstneigh,                \
+                                const int* rows, int row_stride, int max_nbor_size, int nloc,     \
+                                int nall, int nframes, float rcut, const int* sec, int nsec,      \
+                                void* workspace, size_t workspace_bytes, dpb200_stream_t stream);
+DPB200_DECL_ENV(f64, double)
+DPB200_DECL_ENV(f32, float)
+#undef DPB200_DECL_ENV
+
+/* ---------------------------------------------------------------------------------------
+ * tabulate_fusion_se_a (+ se_atten when two_embed != NULL) forward / backward / 2nd order.
+ * Replace deepmd::tabulate_fusion_se_a_gpu, _grad_gpu, _grad_grad_gpu
+ * (source/lib/include/tabulate.h:175-218; source/lib/src/gpu/tabulate.cu:1219-1370), CPU
+ * semantics source/lib/src/tabulate.cc:162-447.  table: [nspline][M][6] (coefficients
+ * innermost); table_info [host]: lower, upper, max, stride0, stride1, (check_freq).
+ * em_x [nloc*nnei], em [nloc*nnei*4], two_embed [nloc*nnei*M] or NULL, out/dy [nloc*4*M].
+ *
+ * The `_ex` forms take element strides so a caller can pass one type-section of the full
+ * env-mat without copying (deepmd/pt/model/descriptor/se_a.py:810-831 slices and copies):
+ *   em_x[i,j]   at em_x + i*ldx_i + j*ldx_j ;  em[i,j,0:4] at em + i*ldem_i + j*4
+ *   dy_dem_x / dy_dem use the same strides as em_x / em;
+ *   accumulate!=0 adds into `out` instead of overwriting it (sum over type sections).
+ * ------------------------------------------------------------------------------------- */
+#define DPB200_DECL_TAB(SUF, FP)                                                                   \
+  int dpb200_tabulate_fusion_se_a_##SUF(FP* out, const FP* table, const FP* table_info,            \
+                                        const FP* em_x, const FP* em, const FP* two_embed,         \
+                                        int nloc, int nnei, int last_layer_size, int is_sorted,    \
+                                        dpb200_stream_t stream);                                   \
+  int dpb200_tabulate_fusion_se_a_grad_##SUF(FP* dy_dem_x, FP* dy_dem, FP* dy_dtwo,                \
+                                             const FP* table, const FP* table_info,                \
+                                             const FP* em_x, const FP* em, const FP* two_embed,    \
+                                             const FP* dy, int nloc, int nnei,                     \
+                                             int last_layer_size, int is_sorted,                   \
+                                             dpb200_stream_t stream);                              \
+  int dpb200_tabulate_fusion_se_a_grad_grad_##SUF(                                                 \
+      FP* dz_dy, const FP* table, const FP* table_info, const FP* em_x, const FP* em,              \
+      const FP* two_embed, const FP* dz_dy_dem_x, const FP* dz_dy_dem, const FP* dz_dy_dtwo,       \
+      int nloc, int nnei, int last_layer_size, int is_sorted, dpb200_stream_t stream);             \
+  int dpb200_tabulate_fusion_se_a_ex_##SUF(FP* out, const FP* table, const FP* table_info,         \
+                                           const FP* em_x, long long ldx_i, int ldx_j,             \
+                                           const FP* em, long long ldem_i, const FP* two_embed,    \
+                                           int nloc, int nnei, int last_layer_size,                \
+                                           int is_sorted, int accumulate, dpb200_stream_t stream); \
+  int dpb200_tabulate_fusion_se_a_grad_ex_##SUF(                                                   \
+      FP* dy_dem_x, FP* dy_dem, FP* dy_dtwo, const FP* table, const FP* table_info,                \
+      const FP* em_x, long long ldx_i, int ldx_j, const FP* em, long long ldem_i,                  \
+      const FP* two_embed, const FP* dy, int nloc, int nnei, int last_layer_size, int is_sorted,   \
+      dpb200_stream_t stream);
+DPB200_DECL_TAB(f64, double)
+DPB200_DECL_TAB(f32, float)
+#undef DPB200_DECL_TAB
+
+/* ---------------------------------------------------------------------------------------
+ * prod_force_a / prod_virial_a : reverse scatter of dE/d(env-mat) to forces and virial.
+ * Replace deepmd::prod_force_a_gpu (source/lib/include/prod_force.h:71-79,
+ * source/lib/src/gpu/prod_force.cu:104-131) and deepmd::prod_virial_a_gpu
+ * (source/lib/include/prod_virial.h:30-39, source/lib/src/gpu/prod_virial.cu:106-134);
+ * CPU semantics source/lib/src/prod_force.cc:23-87, prod_virial.cc:22-69.
+ * force [nframes*nall*3], virial [9], atom_virial [nall*9] (may be NULL in the fused form).
+ * dpb200_prod_force_virial_a does both in one pass over net_deriv / in_deriv.
+ * ------------------------------------------------------------------------------------- */
+#define DPB200_DECL_FV(SUF, FP)                                                                    \
+  int dpb200_prod_force_a_##SUF(FP* force, const FP* net_deriv, const FP* in_deriv,                \
+                                const int* nlist, int nloc, int nall, int nnei, int nframes,       \
+                                dpb200_stream_t stream);                                           \
+  int dpb200_prod_virial_a_##SUF(FP* virial, FP* atom_virial, const FP* net_deriv,                 \
+                                 const FP* in_deriv, const FP* rij, const int* nlist, int nloc,    \
+                                 int nall, int nnei, dpb200_stream_t stream);                      \
+  int dpb200_prod_force_virial_a_##SUF(FP* force, FP* virial, FP* atom_virial,                     \
+                                       const FP* net_deriv, const FP* in_deriv, const FP* rij,     \
+                                       const int* nlist, int nloc, int nall, int nnei,             \
+                                       dpb200_stream_t stream);
+DPB200_DECL_FV(f64, double)
+DPB200_DECL_FV(f32, float)
+#undef DPB200_DECL_FV
+
+/* ---------------------------------------------------------------------------------------
+ * Neighbour-list front end (cell list; the reference GPU path is O(nloc*nall)).
+ *  normalize_coord : deepmd::normalize_coord_gpu (source/lib/include/coord.h:47-55)
+ *  copy_coord      : deepmd::copy_coord_gpu      (coord.h:57-85): periodic ghost images within
+ *                    rcut; local atoms first; returns 1 and the needed *nall when nall>mem_nall.
+ *                    Ghost ORDER is unspecified (the reference tests sort before comparing,
+ *                    source/lib/tests/test_coord.cc:137-165); we emit (owner cell, image) order.
+ *  build_nlist     : deepmd::build_nlist_gpu     (source/lib/include/neighbor_list.h:256-266):
+ *                    all j != i with |ri-rj|^2 < rcut^2 (strict, FPTYPE), type<0 excluded; rows
+ *                    written to a dense [nloc][mem_size] block in ascending j (the order of
+ *                    build_nlist_cpu, neighbor_list.cc:875-928); returns 1 and *max_list_size
+ *                    when a row needs more than mem_size.
+ * boxt [host] is the 3x3 row-major cell.  workspace sizes via the *_workspace_bytes calls.
+ * ------------------------------------------------------------------------------------- */
+size_t dpb200_copy_coord_workspace_bytes(int nloc);
+size_t dpb200_build_nlist_workspace_bytes(int nall);
+
+#define DPB200_DECL_NL(SUF, FP)                                                                    \
+  int dpb200_normalize_coord_##SUF(FP* coord, int natom, const FP* boxt, dpb200_stream_t stream);  \
+  int dpb200_copy_coord_##SUF(FP* out_c, int* out_t, int* mapping, int* nall /*host out*/,         \
+                              const FP* in_c, const int* in_t, int nloc, int mem_nall,             \
+                              float rcut, const FP* boxt, void* workspace,                         \
+                              size_t workspace_bytes, dpb200_stream_t stream);                     \
+  int dpb200_build_nlist_##SUF(int* numneigh, int* rows, int* max_list_size /*host out*/,          \
+                               const FP* coord, int nloc, int nall, int mem_size, float rcut,      \
+                               const int* type, void* workspace, size_t workspace_bytes,           \
+                               dpb200_stream_t stream);
+DPB200_DECL_NL(f64, double)
+DPB200_DECL_NL(f32, float)
+#undef DPB200_DECL_NL
+
+/* use_nlist_map (neighbor_list.h:219-222): nlist[k] = map[nlist[k]] for entries >= 0. */
+int dpb200_use_nlist_map(int* nlist, const int* nlist_map, int nloc, int nnei, dpb200_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DPB200_H_ */
