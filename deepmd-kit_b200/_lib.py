@@ -1,0 +1,106 @@
+"""ctypes binding of the dpb200 C ABI (include/dpb200.h).
+
+This is the only place where Python touches the native library.  There is no CPU fallback: if
+``lib/libdpb200.so`` is missing the import fails, and every compute entry point needs a CUDA device.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "lib", "libdpb200.so")
+
+OK = 0
+ERR_INVALID = -1
+ERR_CUDA = -2
+ERR_OOM = -3
+ERR_NLIST_CAPACITY = -4
+MAX_NBOR_SIZE = 4096
+
+_T = {"p": C.c_void_p, "i": C.c_int, "l": C.c_longlong, "f": C.c_float, "z": C.c_size_t}
+
+# name -> argument codes (p pointer, i int, l long long, f float, z size_t); `{s}` = f32 | f64
+_SIGS = {
+    "prod_env_mat_a_{s}": "pppp ppppppp ii pp iii ff pi pz p",
+    "format_nlist_{s}": "p pp pppp ii iii f pi pz p",
+    "tabulate_fusion_se_a_{s}": "pppppp iiii p",
+    "tabulate_fusion_se_a_grad_{s}": "ppp pp ppp p iiii p",
+    "tabulate_fusion_se_a_grad_grad_{s}": "p pp ppp ppp iiii p",
+    "tabulate_fusion_se_a_ex_{s}": "ppp pli pl p iiiii p",
+    "tabulate_fusion_se_a_grad_ex_{s}": "ppp pp pli pl p p iiii p",
+    "prod_force_a_{s}": "pppp iiii p",
+    "prod_virial_a_{s}": "pppppp iii p",
+    "prod_force_virial_a_{s}": "ppppppp iii p",
+    "normalize_coord_{s}": "pip p",
+    "copy_coord_{s}": "pppp pp ii f p pz p",
+    "build_nlist_{s}": "ppp p iii f p pz p",
+}
+
+
+class DPB200Error(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__(f"dpb200 error {code}: {msg}")
+        self.code = code
+
+
+class NlistCapacityError(DPB200Error):
+    pass
+
+
+class _Lib:
+    def __init__(self):
+        if not os.path.exists(LIB_PATH):
+            raise ImportError(
+                f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                "(nvcc, sm_100a).  There is no CPU fallback for the dpb200 hot path.")
+        self.cdll = C.CDLL(LIB_PATH)
+        self.cdll.dpb200_last_error.restype = C.c_char_p
+        self.cdll.dpb200_abi_version.restype = C.c_int
+        for fn, res in (("dpb200_prod_env_mat_a_workspace_bytes", "iiiii"), ("dpb200_copy_coord_workspace_bytes", "i"),
+                        ("dpb200_build_nlist_workspace_bytes", "i")):
+            f = getattr(self.cdll, fn)
+            f.restype = C.c_size_t
+            f.argtypes = [_T[c] for c in res]
+        self.cdll.dpb200_use_nlist_map.restype = C.c_int
+        self.cdll.dpb200_use_nlist_map.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p]
+        for pat, sig in _SIGS.items():
+            for s in ("f32", "f64"):
+                f = getattr(self.cdll, "dpb200_" + pat.format(s=s))
+                f.restype = C.c_int
+                f.argtypes = [_T[c] for c in sig.replace(" ", "")]
+
+    def exported(self):
+        names = ["dpb200_last_error", "dpb200_abi_version", "dpb200_prod_env_mat_a_workspace_bytes",
+                 "dpb200_copy_coord_workspace_bytes", "dpb200_build_nlist_workspace_bytes", "dpb200_use_nlist_map"]
+        for pat in _SIGS:
+            for s in ("f32", "f64"):
+                names.append("dpb200_" + pat.format(s=s))
+        return names
+
+    def last_error(self) -> str:
+        return (self.cdll.dpb200_last_error() or b"").decode()
+
+    def call(self, name, *args):
+        """Call dpb200_<name>; returns the (non-negative) status, raises on a negative one."""
+        rc = getattr(self.cdll, "dpb200_" + name)(*args)
+        if rc < 0:
+            msg = self.last_error()
+            if rc == ERR_NLIST_CAPACITY:
+                raise NlistCapacityError(rc, msg)
+            if rc == ERR_INVALID:
+                raise ValueError(f"dpb200_{name}: {msg}")
+            if rc == ERR_OOM:
+                raise MemoryError(f"dpb200_{name}: {msg}")
+            raise DPB200Error(rc, f"dpb200_{name}: {msg}")
+        return rc
+
+
+_lib = None
+
+
+def lib() -> _Lib:
+    global _lib
+    if _lib is None:
+        _lib = _Lib()
+    return _lib

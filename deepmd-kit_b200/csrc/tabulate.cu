@@ -1,0 +1,668 @@
+// tabulate_fusion_se_a / se_atten (forward, first- and second-order backward) for sm_100a.
+//
+// Semantics: source/lib/src/tabulate.cc:162-447 (CPU), i.e. for every centre atom i
+//   out[i,m,k] = sum_j em[i,j,m] * g_k(em_x[i,j]),  g_k = quintic of table row locate_xx(em_x)
+// with linear extrapolation outside [lower,max) (tabulate.cc:45-73,122-158), the optional
+// se_atten gate g <- g*t + g, and the `is_sorted` fold of the trailing padding (":197-201").
+//
+// Design (not a port of source/lib/src/gpu/tabulate.cu, which runs one thread per output
+// channel with stride-6 coefficient loads and, in the backward, five full warp reductions per
+// neighbour):
+//   * the table is re-laid out once per call as T[row][6][Mpad] so that one coefficient of 32
+//     channels is ONE coalesced 128/256-byte request (the reference layout [row][M][6] costs 3x
+//     the L1 wavefronts); rows are L1/L2 resident, the op is bound by L1 bandwidth + FP pipe;
+//   * one WARP per centre atom, lanes over channels (NC channels per lane, M <= 32*NC per
+//     block of channels), persistent grid-stride loop over atoms: no block barrier anywhere;
+//   * neighbours are "located" 32 at a time in parallel (exact FP division as the reference),
+//     records {dx, delta, em[4], row, multiplicity} are staged in per-warp shared memory and
+//     read back as broadcast LDS.128 by the channel loop;
+//   * consecutive neighbours are distance-sorted, so they frequently share a table row: the
+//     coefficients stay in registers until the row changes;
+//   * backward: 8 neighbours x 4 components = 32 partial sums per lane are reduced with ONE
+//     butterfly reduce-scatter (31 shuffles) whose result is exactly the 32 contiguous dy_dem
+//     values of those neighbours -> one coalesced store; dy_dem_x needs 9 more shuffles.
+#include <cmath>
+
+#include "common.cuh"
+
+namespace dpb200 {
+namespace {
+
+template <typename FP>
+struct TabParams {
+  const FP* T;  // [nrow][6][Mpad]
+  FP lower, upper, vmax, s0, s1;
+  int first;     // int((upper-lower)/s0)
+  int tail_idx;  // row of x >= max
+  FP tail_xx;    // max - start of that row
+  const FP* em_x;
+  long long ldx_i;
+  int ldx_j;
+  const FP* em;
+  long long ldem_i;
+  const FP* two;  // [nloc][nnei][M] or null
+  int nloc, nnei, M, Mpad, is_sorted, accumulate, vec_ok;
+  // forward / second order
+  FP* out;  // [nloc][4][M]
+  const FP* dz_x;
+  const FP* dz_em;
+  const FP* dz_two;
+  // first-order backward
+  const FP* dy;  // [nloc][4][M]
+  FP* dy_dem_x;
+  FP* dy_dem;
+  FP* dy_dtwo;
+};
+
+template <typename FP>
+struct alignas(16) Rec {
+  FP xx, delta;
+  FP e[4];
+  int idx;
+  int mult;
+};
+template <typename FP>
+struct alignas(16) RecGG {  // second order only: dz_dy_dem[4], dz_dy_dem_x of this neighbour
+  FP h[4];
+  FP zx;
+  FP pad_;
+};
+
+// [row][M][6] -> [row][6][Mpad]
+template <typename FP>
+__global__ void k_table_relayout(FP* __restrict__ T, const FP* __restrict__ table, long long nrow,
+                                 int M, int Mpad) {
+  const long long n = nrow * 6 * (long long)Mpad;
+  for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < n;
+       e += (long long)gridDim.x * blockDim.x) {
+    const int k = (int)(e % Mpad);
+    const long long rp = e / Mpad;
+    const int pp = (int)(rp % 6);
+    const long long r = rp / 6;
+    T[e] = k < M ? table[(r * M + k) * 6 + pp] : (FP)0.;
+  }
+}
+
+template <typename FP>
+__global__ void k_zero(FP* __restrict__ p, long long n) {
+  for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < n;
+       e += (long long)gridDim.x * blockDim.x)
+    p[e] = (FP)0.;
+}
+
+// tabulate.cc:45-73
+template <typename FP>
+__device__ __forceinline__ void locate(const TabParams<FP>& p, FP x0, FP& xx, int& idx, FP& delta) {
+  delta = (FP)0.;
+  if (x0 < p.lower) {
+    idx = 0;
+    xx = (FP)0.;
+    delta = x0 - p.lower;
+  } else if (x0 < p.upper) {
+    idx = (int)((x0 - p.lower) / p.s0);
+    xx = x0 - ((FP)idx * p.s0 + p.lower);
+  } else if (x0 < p.vmax) {
+    idx = p.first + (int)((x0 - p.upper) / p.s1);
+    xx = x0 - ((FP)(idx - p.first) * p.s1 + p.upper);
+  } else {
+    idx = p.tail_idx;
+    xx = p.tail_xx;
+    delta = x0 - p.vmax;
+  }
+}
+
+__device__ __forceinline__ void load4(const float* q, bool vec, float (&e)[4]) {
+  if (vec) {
+    const float4 v = *reinterpret_cast<const float4*>(q);
+    e[0] = v.x, e[1] = v.y, e[2] = v.z, e[3] = v.w;
+  } else {
+    e[0] = q[0], e[1] = q[1], e[2] = q[2], e[3] = q[3];
+  }
+}
+__device__ __forceinline__ void load4(const double* q, bool vec, double (&e)[4]) {
+  if (vec) {
+    const double2 a = *reinterpret_cast<const double2*>(q);
+    const double2 b = *reinterpret_cast<const double2*>(q + 2);
+    e[0] = a.x, e[1] = a.y, e[2] = b.x, e[3] = b.y;
+  } else {
+    e[0] = q[0], e[1] = q[1], e[2] = q[2], e[3] = q[3];
+  }
+}
+
+// Locate up to 32 neighbours [j0, j0+32) of atom i in parallel and stage their records.
+// Returns how many of them must be processed (the fold entry, if any, is the last one).
+template <typename FP, bool GG>
+__device__ __forceinline__ int stage_chunk(const TabParams<FP>& p, long long i, int j0, FP last,
+                                           Rec<FP>* __restrict__ rec, RecGG<FP>* __restrict__ rgg,
+                                           int lane, bool& done) {
+  const int j = j0 + lane;
+  const bool valid = j < p.nnei;
+  FP x = (FP)0.;
+  FP e[4] = {(FP)0., (FP)0., (FP)0., (FP)0.};
+  if (valid) {
+    x = p.em_x[i * p.ldx_i + (long long)j * p.ldx_j];
+    load4(p.em + i * p.ldem_i + (long long)j * 4, p.vec_ok != 0, e);
+  }
+  const bool fold = valid && p.is_sorted && (x == last) && e[1] == (FP)0. && e[2] == (FP)0. && e[3] == (FP)0.;
+  const unsigned fm = __ballot_sync(kFull, fold);
+  const int nvalid = (p.nnei - j0) < 32 ? (p.nnei - j0) : 32;
+  const int nproc = fm ? __ffs(fm) : nvalid;
+  done = fm != 0u;
+  Rec<FP> r;
+  locate(p, x, r.xx, r.idx, r.delta);
+  r.e[0] = e[0], r.e[1] = e[1], r.e[2] = e[2], r.e[3] = e[3];
+  r.mult = (fm && lane == nproc - 1) ? (p.nnei - j) : 1;
+  RecGG<FP> g2;
+  if (GG) {
+    FP h[4] = {(FP)0., (FP)0., (FP)0., (FP)0.};
+    g2.zx = (FP)0.;
+    g2.pad_ = (FP)0.;
+    if (valid) {
+      load4(p.dz_em + (i * p.nnei + j) * 4, true, h);
+      g2.zx = p.dz_x[i * p.nnei + j];
+    }
+    g2.h[0] = h[0], g2.h[1] = h[1], g2.h[2] = h[2], g2.h[3] = h[3];
+  }
+  __syncwarp();  // previous chunk's readers are done
+  rec[lane] = r;
+  if (GG) rgg[lane] = g2;
+  __syncwarp();
+  return nproc;
+}
+
+// ------------------------------------------------------------------------------------------
+// forward (GG=false) and second-order backward (GG=true): both accumulate a [4][M] tile.
+// ------------------------------------------------------------------------------------------
+template <typename FP, int NC, bool TWO, bool GG>
+__global__ void __launch_bounds__(128) k_tab_fwd(const __grid_constant__ TabParams<FP> p) {
+  __shared__ Rec<FP> rec_all[4][32];
+  __shared__ RecGG<FP> rgg_all[GG ? 4 : 1][GG ? 32 : 1];
+  const int lane = threadIdx.x & 31;
+  const int warp = threadIdx.x >> 5;
+  Rec<FP>* rec = rec_all[warp];
+  RecGG<FP>* rgg = rgg_all[GG ? warp : 0];
+  const int nkb = (p.M + 32 * NC - 1) / (32 * NC);
+  const long long nwork = (long long)p.nloc * nkb;
+  const int Mpad = p.Mpad;
+  for (long long w = (long long)blockIdx.x * 4 + warp; w < nwork; w += (long long)gridDim.x * 4) {
+    const long long i = w / nkb;
+    const int kb = (int)(w - i * nkb) * 32 * NC;
+    FP acc[4][NC];
+#pragma unroll
+    for (int m = 0; m < 4; ++m)
+#pragma unroll
+      for (int c = 0; c < NC; ++c) acc[m][c] = (FP)0.;
+    FP a[NC][6];
+#pragma unroll
+    for (int c = 0; c < NC; ++c)
+#pragma unroll
+      for (int q = 0; q < 6; ++q) a[c][q] = (FP)0.;
+    int cur_row = -1;
+    const FP last = p.em_x[i * p.ldx_i + (long long)(p.nnei - 1) * p.ldx_j];
+    bool done = false;
+    for (int j0 = 0; j0 < p.nnei && !done; j0 += 32) {
+      const int nproc = stage_chunk<FP, GG>(p, i, j0, last, rec, rgg, lane, done);
+      for (int jj = 0; jj < nproc; ++jj) {
+        const Rec<FP>& r = rec[jj];
+        const int row = r.idx;
+        if (row != cur_row) {  // warp-uniform
+          cur_row = row;
+          const FP* __restrict__ tr = p.T + (long long)row * 6 * Mpad + kb + lane;
+#pragma unroll
+          for (int c = 0; c < NC; ++c) {
+            if (kb + lane + 32 * c < p.M) {
+#pragma unroll
+              for (int q = 0; q < 6; ++q) a[c][q] = __ldg(tr + q * Mpad + 32 * c);
+            }
+          }
+        }
+        const FP xx = r.xx;
+        const FP dl = r.delta;
+        const FP mult = (FP)r.mult;
+        FP e[4];
+#pragma unroll
+        for (int m = 0; m < 4; ++m) e[m] = r.e[m] * mult;
+        FP h[4];
+        FP zx = (FP)0.;
+        if (GG) {
+#pragma unroll
+          for (int m = 0; m < 4; ++m) h[m] = rgg[jj].h[m] * mult;
+          zx = rgg[jj].zx;
+        }
+        const long long two_off = ((i * p.nnei + j0 + jj) * (long long)p.M) + kb + lane;
+#pragma unroll
+        for (int c = 0; c < NC; ++c) {
+          FP g = a[c][0] + (a[c][1] + (a[c][2] + (a[c][3] + (a[c][4] + a[c][5] * xx) * xx) * xx) * xx) * xx;
+          FP gd = (FP)0.;
+          if (GG || dl != (FP)0.) {
+            gd = a[c][1] + ((FP)2. * a[c][2] + ((FP)3. * a[c][3] + ((FP)4. * a[c][4] + (FP)5. * a[c][5] * xx) * xx) * xx) * xx;
+            g += gd * dl;
+          }
+          const bool kin = kb + lane + 32 * c < p.M;
+          if (GG) {
+            FP two_grad = (FP)0.;
+            if (TWO && kin) {
+              const FP t = p.two[two_off + 32 * c];
+              two_grad = p.dz_two[two_off + 32 * c] * g;
+              g += g * t;
+              gd += gd * t;
+            }
+            const FP s = zx * gd + two_grad;
+#pragma unroll
+            for (int m = 0; m < 4; ++m) acc[m][c] += g * h[m] + s * e[m];
+          } else {
+            if (TWO && kin) {
+              const FP t = p.two[two_off + 32 * c];
+              g = g * t + g;
+            }
+#pragma unroll
+            for (int m = 0; m < 4; ++m) acc[m][c] += e[m] * g;
+          }
+        }
+      }
+    }
+    FP* __restrict__ o = p.out + i * 4 * (long long)p.M + kb + lane;
+#pragma unroll
+    for (int c = 0; c < NC; ++c) {
+      if (kb + lane + 32 * c < p.M) {
+#pragma unroll
+        for (int m = 0; m < 4; ++m) {
+          FP* q = o + (long long)m * p.M + 32 * c;
+          *q = p.accumulate ? (*q + acc[m][c]) : acc[m][c];
+        }
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// first-order backward
+// ------------------------------------------------------------------------------------------
+// v[0..31] per lane -> lane l returns the warp-wide sum of v[l].
+template <typename FP>
+__device__ __forceinline__ FP reduce_scatter32(FP (&v)[32], int lane) {
+#pragma unroll
+  for (int s = 16, n = 32; s >= 1; s >>= 1, n >>= 1) {
+    const bool up = (lane & s) != 0;
+#pragma unroll
+    for (int t = 0; t < n / 2; ++t) {
+      const FP send = up ? v[t] : v[t + n / 2];
+      const FP keep = up ? v[t + n / 2] : v[t];
+      v[t] = keep + __shfl_xor_sync(kFull, send, s);
+    }
+  }
+  return v[0];
+}
+// v[0..7] per lane -> lane l returns the warp-wide sum of v[l >> 2].
+template <typename FP>
+__device__ __forceinline__ FP reduce_scatter8(FP (&v)[8], int lane) {
+#pragma unroll
+  for (int s = 16, n = 8; s >= 4; s >>= 1, n >>= 1) {
+    const bool up = (lane & s) != 0;
+#pragma unroll
+    for (int t = 0; t < n / 2; ++t) {
+      const FP send = up ? v[t] : v[t + n / 2];
+      const FP keep = up ? v[t + n / 2] : v[t];
+      v[t] = keep + __shfl_xor_sync(kFull, send, s);
+    }
+  }
+  FP r = v[0];
+  r += __shfl_xor_sync(kFull, r, 2);
+  r += __shfl_xor_sync(kFull, r, 1);
+  return r;
+}
+
+template <typename FP, int NC, bool TWO>
+__global__ void __launch_bounds__(128, 3) k_tab_grad(const __grid_constant__ TabParams<FP> p) {
+  __shared__ Rec<FP> rec_all[4][32];
+  const int lane = threadIdx.x & 31;
+  const int warp = threadIdx.x >> 5;
+  Rec<FP>* rec = rec_all[warp];
+  const int Mpad = p.Mpad;
+  const int M = p.M;
+  const bool single = M <= 32 * NC;
+  for (long long i = (long long)blockIdx.x * 4 + warp; i < p.nloc; i += (long long)gridDim.x * 4) {
+    const FP* __restrict__ dyi = p.dy + i * 4 * (long long)M;
+    FP dyr[4][NC];
+    if (single) {
+#pragma unroll
+      for (int c = 0; c < NC; ++c)
+#pragma unroll
+        for (int m = 0; m < 4; ++m) dyr[m][c] = (lane + 32 * c < M) ? dyi[(long long)m * M + lane + 32 * c] : (FP)0.;
+    }
+    const FP last = p.em_x[i * p.ldx_i + (long long)(p.nnei - 1) * p.ldx_j];
+    // dy_dem_x == nullptr: em_x IS component 0 of em, its gradient is added into dy_dem[j][0]
+    const bool fuse_x = p.dy_dem_x == nullptr;
+    FP* __restrict__ gx = fuse_x ? nullptr : p.dy_dem_x + i * p.ldx_i;
+    FP* __restrict__ gem = p.dy_dem + i * p.ldem_i;
+    bool done = false;
+    int jend = 0;  // neighbours [0, jend) have been written
+    for (int j0 = 0; j0 < p.nnei && !done; j0 += 32) {
+      const int nproc = stage_chunk<FP, false>(p, i, j0, last, rec, nullptr, lane, done);
+      for (int b = 0; b < nproc; b += 8) {
+        FP v[32];
+        FP vx[8];
+#pragma unroll
+        for (int t = 0; t < 32; ++t) v[t] = (FP)0.;
+#pragma unroll
+        for (int t = 0; t < 8; ++t) vx[t] = (FP)0.;
+        for (int kb = 0; kb < M; kb += 32 * NC) {
+#pragma unroll
+          for (int c = 0; c < NC; ++c) {
+            const int k = kb + lane + 32 * c;
+            const bool kin = k < M;
+            FP d0, d1, d2, d3;
+            if (single) {
+              d0 = dyr[0][c], d1 = dyr[1][c], d2 = dyr[2][c], d3 = dyr[3][c];
+            } else {
+              d0 = kin ? dyi[k] : (FP)0.;
+              d1 = kin ? dyi[(long long)M + k] : (FP)0.;
+              d2 = kin ? dyi[2ll * M + k] : (FP)0.;
+              d3 = kin ? dyi[3ll * M + k] : (FP)0.;
+            }
+            FP a0 = 0, a1 = 0, a2 = 0, a3 = 0, a4 = 0, a5 = 0;
+            int cur_row = -1;
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+              if (b + u < nproc) {  // warp-uniform
+                const Rec<FP>& r = rec[b + u];
+                if (r.idx != cur_row) {
+                  cur_row = r.idx;
+                  if (kin) {
+                    const FP* __restrict__ tr = p.T + (long long)cur_row * 6 * Mpad + k;
+                    a0 = __ldg(tr);
+                    a1 = __ldg(tr + Mpad);
+                    a2 = __ldg(tr + 2 * Mpad);
+                    a3 = __ldg(tr + 3 * Mpad);
+                    a4 = __ldg(tr + 4 * Mpad);
+                    a5 = __ldg(tr + 5 * Mpad);
+                  }
+                }
+                const FP xx = r.xx;
+                FP gd = a1 + ((FP)2. * a2 + ((FP)3. * a3 + ((FP)4. * a4 + (FP)5. * a5 * xx) * xx) * xx) * xx;
+                FP g = a0 + (a1 + (a2 + (a3 + (a4 + a5 * xx) * xx) * xx) * xx) * xx + gd * r.delta;
+                const FP dot = r.e[0] * d0 + r.e[1] * d1 + r.e[2] * d2 + r.e[3] * d3;
+                if (TWO) {
+                  if (kin) {
+                    const long long to = (i * p.nnei + j0 + b + u) * (long long)M + k;
+                    const FP t = p.two[to];
+                    p.dy_dtwo[to] = (FP)r.mult * g * dot;
+                    g = g * t + g;
+                    gd += t * gd;
+                  }
+                }
+                vx[u] += gd * dot;
+                v[4 * u + 0] += g * d0;
+                v[4 * u + 1] += g * d1;
+                v[4 * u + 2] += g * d2;
+                v[4 * u + 3] += g * d3;
+              }
+            }
+          }
+        }
+        const FP tot = reduce_scatter32(v, lane);
+        const FP totx = reduce_scatter8(vx, lane);
+        const int u = lane >> 2;
+        if (b + u < nproc) {
+          const FP mult = (FP)rec[b + u].mult;
+          const int j = j0 + b + u;
+          if (fuse_x) {
+            gem[(long long)j * 4 + (lane & 3)] = ((lane & 3) == 0 ? tot + totx : tot) * mult;
+          } else {
+            gem[(long long)j * 4 + (lane & 3)] = tot * mult;
+            if ((lane & 3) == 0) gx[(long long)j * p.ldx_j] = totx * mult;
+          }
+        }
+      }
+      jend = j0 + nproc;
+    }
+    // everything behind the fold (or nothing) is zero (tabulate.cc zero-fills the outputs first)
+    for (int j = jend + lane; j < p.nnei; j += 32) {
+      if (!fuse_x) gx[(long long)j * p.ldx_j] = (FP)0.;
+#pragma unroll
+      for (int m = 0; m < 4; ++m) gem[(long long)j * 4 + m] = (FP)0.;
+    }
+    if (TWO) {
+      for (long long e = (long long)jend * M + lane; e < (long long)p.nnei * M; e += 32)
+        p.dy_dtwo[i * p.nnei * (long long)M + e] = (FP)0.;
+    }
+    __syncwarp();
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------
+template <typename FP>
+struct TabHost {
+  long long nrow;
+  int Mpad;
+};
+
+template <typename FP>
+int fill_info(TabParams<FP>& p, const FP* info, int M, long long& nrow) {
+  DPB_REQUIRE(info != nullptr, "tabulate: table_info is null (it must be a HOST pointer)");
+  p.lower = info[0];
+  p.upper = info[1];
+  p.vmax = info[2];
+  p.s0 = info[3];
+  p.s1 = info[4];
+  DPB_REQUIRE(p.s0 > (FP)0. && p.s1 > (FP)0. && p.upper >= p.lower && p.vmax >= p.upper,
+              "tabulate: table_info must satisfy lower <= upper <= max and positive strides");
+  // tabulate.cc:21-30
+  p.first = (int)((p.upper - p.lower) / p.s0);
+  const FP edge = std::nextafter(p.vmax, p.lower);
+  p.tail_idx = p.first + (int)((edge - p.upper) / p.s1);
+  p.tail_xx = p.vmax - ((FP)(p.tail_idx - p.first) * p.s1 + p.upper);
+  nrow = (long long)p.tail_idx + 1;
+  p.M = M;
+  p.Mpad = (M + 31) / 32 * 32;
+  return DPB200_OK;
+}
+
+template <typename FP>
+int prepare_table(TabParams<FP>& p, const FP* table, long long nrow, FP** scratch, cudaStream_t st) {
+  const size_t bytes = (size_t)nrow * 6 * p.Mpad * sizeof(FP);
+  DPB_CUDA(cudaMallocAsync((void**)scratch, bytes, st));
+  const long long n = nrow * 6 * (long long)p.Mpad;
+  int grid = ceil_div(n, 256);
+  const int cap = sm_count() * 8;
+  if (grid > cap) grid = cap;
+  k_table_relayout<FP><<<grid, 256, 0, st>>>(*scratch, table, nrow, p.M, p.Mpad);
+  p.T = *scratch;
+  return DPB200_OK;
+}
+
+inline bool aligned16(const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15) == 0; }
+
+template <typename FP>
+int common_args(TabParams<FP>& p, const FP* em_x, long long ldx_i, int ldx_j, const FP* em,
+                long long ldem_i, const FP* two, int nloc, int nnei, int is_sorted) {
+  DPB_REQUIRE(em_x != nullptr && em != nullptr, "tabulate: em_x / em are null");
+  p.em_x = em_x;
+  p.ldx_i = ldx_i;
+  p.ldx_j = ldx_j;
+  p.em = em;
+  p.ldem_i = ldem_i;
+  p.two = two;
+  p.nloc = nloc;
+  p.nnei = nnei;
+  p.is_sorted = is_sorted ? 1 : 0;
+  p.vec_ok = aligned16(em) && ((ldem_i * sizeof(FP)) % 16 == 0) ? 1 : 0;
+  return DPB200_OK;
+}
+
+// Persistent launch shape: min(work, SMs x resident CTAs) CTAs of 4 warps; L1-heavy carve-out.
+template <typename K>
+int persistent_grid(K kern, long long nwarps_needed) {
+  cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxL1);
+  int occ = 0;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, 128, 0) != cudaSuccess || occ < 1) occ = 1;
+  long long want = (nwarps_needed + 3) / 4;
+  long long cap = (long long)sm_count() * occ;
+  if (want < 1) want = 1;
+  return (int)(want < cap ? want : cap);
+}
+
+template <typename FP, bool GG>
+int launch_fwd(FP* out, const FP* table, const FP* info, const FP* em_x, long long ldx_i, int ldx_j,
+               const FP* em, long long ldem_i, const FP* two, const FP* dz_x, const FP* dz_em,
+               const FP* dz_two, int nloc, int nnei, int M, int is_sorted, int accumulate,
+               cudaStream_t st) {
+  DPB_REQUIRE(nloc >= 0 && nnei >= 0 && M >= 0, "tabulate: negative size");
+  if (nloc == 0 || M == 0) return DPB200_OK;
+  DPB_REQUIRE(out != nullptr, "tabulate: out is null");
+  if (nnei == 0) {  // an empty neighbour axis is a valid empty reduction (tabulate.cc:176-181)
+    if (!accumulate) DPB_CUDA(cudaMemsetAsync(out, 0, sizeof(FP) * (size_t)nloc * 4 * M, st));
+    return DPB200_OK;
+  }
+  DPB_REQUIRE(table != nullptr, "tabulate: table is null");
+  TabParams<FP> p = {};
+  long long nrow = 0;
+  int rc = fill_info(p, info, M, nrow);
+  if (rc) return rc;
+  rc = common_args(p, em_x, ldx_i, ldx_j, em, ldem_i, two, nloc, nnei, is_sorted);
+  if (rc) return rc;
+  p.out = out;
+  p.accumulate = accumulate;
+  p.dz_x = dz_x;
+  p.dz_em = dz_em;
+  p.dz_two = dz_two;
+  if (GG) {
+    DPB_REQUIRE(dz_x != nullptr && dz_em != nullptr, "tabulate grad_grad: dz_dy_dem_x / dz_dy_dem are null");
+    DPB_REQUIRE(aligned16(dz_em), "tabulate grad_grad: dz_dy_dem must be 16-byte aligned");
+    DPB_REQUIRE(two == nullptr || dz_two != nullptr, "tabulate grad_grad: dz_dy_dtwo is null");
+  }
+  FP* scratch = nullptr;
+  rc = prepare_table(p, table, nrow, &scratch, st);
+  if (rc) return rc;
+  const bool tw = two != nullptr;
+#define DPB_LAUNCH_FWD(NC)                                                                       \
+  do {                                                                                           \
+    const int nkb = (M + 32 * NC - 1) / (32 * NC);                                               \
+    if (tw) {                                                                                    \
+      auto kern = k_tab_fwd<FP, NC, true, GG>;                                                   \
+      kern<<<persistent_grid(kern, (long long)nloc * nkb), 128, 0, st>>>(p);                     \
+    } else {                                                                                     \
+      auto kern = k_tab_fwd<FP, NC, false, GG>;                                                  \
+      kern<<<persistent_grid(kern, (long long)nloc * nkb), 128, 0, st>>>(p);                     \
+    }                                                                                            \
+  } while (0)
+  if (M <= 32)
+    DPB_LAUNCH_FWD(1);
+  else if (M <= 64)
+    DPB_LAUNCH_FWD(2);
+  else
+    DPB_LAUNCH_FWD(4);
+#undef DPB_LAUNCH_FWD
+  cudaError_t e = cudaGetLastError();
+  cudaFreeAsync(scratch, st);
+  DPB_CUDA(e);
+  return DPB200_OK;
+}
+
+template <typename FP>
+int launch_grad(FP* dy_dem_x, FP* dy_dem, FP* dy_dtwo, const FP* table, const FP* info,
+                const FP* em_x, long long ldx_i, int ldx_j, const FP* em, long long ldem_i,
+                const FP* two, const FP* dy, int nloc, int nnei, int M, int is_sorted,
+                cudaStream_t st) {
+  DPB_REQUIRE(nloc >= 0 && nnei >= 0 && M >= 0, "tabulate grad: negative size");
+  if (nloc == 0 || nnei == 0) return DPB200_OK;  // tabulate.cc: nothing to write
+  DPB_REQUIRE(dy_dem != nullptr && dy != nullptr && table != nullptr, "tabulate grad: null pointer");
+  DPB_REQUIRE(two == nullptr || dy_dtwo != nullptr, "tabulate grad: dy_dtwo is null");
+  TabParams<FP> p = {};
+  long long nrow = 0;
+  int rc = fill_info(p, info, M, nrow);
+  if (rc) return rc;
+  rc = common_args(p, em_x, ldx_i, ldx_j, em, ldem_i, two, nloc, nnei, is_sorted);
+  if (rc) return rc;
+  p.dy = dy;
+  p.dy_dem_x = dy_dem_x;
+  p.dy_dem = dy_dem;
+  p.dy_dtwo = dy_dtwo;
+  FP* scratch = nullptr;
+  rc = prepare_table(p, table, nrow, &scratch, st);
+  if (rc) return rc;
+  const bool tw = two != nullptr;
+#define DPB_LAUNCH_GRAD(NC)                                           \
+  do {                                                                \
+    if (tw) {                                                         \
+      auto kern = k_tab_grad<FP, NC, true>;                           \
+      kern<<<persistent_grid(kern, nloc), 128, 0, st>>>(p);           \
+    } else {                                                          \
+      auto kern = k_tab_grad<FP, NC, false>;                          \
+      kern<<<persistent_grid(kern, nloc), 128, 0, st>>>(p);           \
+    }                                                                 \
+  } while (0)
+  if (M <= 32)
+    DPB_LAUNCH_GRAD(1);
+  else if (M <= 64)
+    DPB_LAUNCH_GRAD(2);
+  else
+    DPB_LAUNCH_GRAD(4);
+#undef DPB_LAUNCH_GRAD
+  cudaError_t e = cudaGetLastError();
+  cudaFreeAsync(scratch, st);
+  DPB_CUDA(e);
+  return DPB200_OK;
+}
+
+}  // namespace
+}  // namespace dpb200
+
+extern "C" {
+
+#define DPB200_DEF_TAB(SUF, FP)                                                                    \
+  int dpb200_tabulate_fusion_se_a_##SUF(FP* out, const FP* table, const FP* table_info,            \
+                                        const FP* em_x, const FP* em, const FP* two_embed,         \
+                                        int nloc, int nnei, int last_layer_size, int is_sorted,    \
+                                        dpb200_stream_t stream) {                                  \
+    return dpb200::launch_fwd<FP, false>(out, table, table_info, em_x, nnei, 1, em,                \
+                                         (long long)nnei * 4, two_embed, nullptr, nullptr,         \
+                                         nullptr, nloc, nnei, last_layer_size, is_sorted, 0,       \
+                                         (cudaStream_t)stream);                                    \
+  }                                                                                                \
+  int dpb200_tabulate_fusion_se_a_ex_##SUF(FP* out, const FP* table, const FP* table_info,         \
+                                           const FP* em_x, long long ldx_i, int ldx_j,             \
+                                           const FP* em, long long ldem_i, const FP* two_embed,    \
+                                           int nloc, int nnei, int last_layer_size,                \
+                                           int is_sorted, int accumulate,                          \
+                                           dpb200_stream_t stream) {                               \
+    return dpb200::launch_fwd<FP, false>(out, table, table_info, em_x, ldx_i, ldx_j, em, ldem_i,   \
+                                         two_embed, nullptr, nullptr, nullptr, nloc, nnei,         \
+                                         last_layer_size, is_sorted, accumulate,                   \
+                                         (cudaStream_t)stream);                                    \
+  }                                                                                                \
+  int dpb200_tabulate_fusion_se_a_grad_##SUF(FP* dy_dem_x, FP* dy_dem, FP* dy_dtwo,                \
+                                             const FP* table, const FP* table_info,                \
+                                             const FP* em_x, const FP* em, const FP* two_embed,    \
+                                             const FP* dy, int nloc, int nnei,                     \
+                                             int last_layer_size, int is_sorted,                   \
+                                             dpb200_stream_t stream) {                             \
+    return dpb200::launch_grad<FP>(dy_dem_x, dy_dem, dy_dtwo, table, table_info, em_x, nnei, 1,    \
+                                   em, (long long)nnei * 4, two_embed, dy, nloc, nnei,             \
+                                   last_layer_size, is_sorted, (cudaStream_t)stream);              \
+  }                                                                                                \
+  int dpb200_tabulate_fusion_se_a_grad_ex_##SUF(                                                   \
+      FP* dy_dem_x, FP* dy_dem, FP* dy_dtwo, const FP* table, const FP* table_info,                \
+      const FP* em_x, long long ldx_i, int ldx_j, const FP* em, long long ldem_i,                  \
+      const FP* two_embed, const FP* dy, int nloc, int nnei, int last_layer_size, int is_sorted,   \
+      dpb200_stream_t stream) {                                                                    \
+    return dpb200::launch_grad<FP>(dy_dem_x, dy_dem, dy_dtwo, table, table_info, em_x, ldx_i,      \
+                                   ldx_j, em, ldem_i, two_embed, dy, nloc, nnei, last_layer_size,  \
+                                   is_sorted, (cudaStream_t)stream);                               \
+  }                                                                                                \
+  int dpb200_tabulate_fusion_se_a_grad_grad_##SUF(                                                 \
+      FP* dz_dy, const FP* table, const FP* table_info, const FP* em_x, const FP* em,              \
+      const FP* two_embed, const FP* dz_dy_dem_x, const FP* dz_dy_dem, const FP* dz_dy_dtwo,       \
+      int nloc, int nnei, int last_layer_size, int is_sorted, dpb200_stream_t stream) {            \
+    return dpb200::launch_fwd<FP, true>(dz_dy, table, table_info, em_x, nnei, 1, em,               \
+                                        (long long)nnei * 4, two_embed, dz_dy_dem_x, dz_dy_dem,    \
+                                        dz_dy_dtwo, nloc, nnei, last_layer_size, is_sorted, 0,     \
+                                        (cudaStream_t)stream);                                     \
+  }
+DPB200_DEF_TAB(f64, double)
+DPB200_DEF_TAB(f32, float)
+#undef DPB200_DEF_TAB
+
+}  // extern "C"

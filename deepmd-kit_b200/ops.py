@@ -1,0 +1,653 @@
+"""Host side of the hot path: tensor-level wrappers over the C ABI and the ``torch.ops.deepmd.*``
+operator surface.
+
+Two layers, both thin:
+
+* ``raw`` functions (``prod_env_mat_a``, ``format_nlist``, ``tabulate_fusion_se_a`` ...): take CUDA
+  tensors, check shapes/devices, allocate outputs and the workspace and call ``dpb200_*`` on the
+  current torch stream.  Argument meaning follows the reference library functions they replace
+  (``deepmd::prod_env_mat_a_gpu`` etc., source/lib/include/*.h).
+* ``torch.ops.deepmd.*``: the reference's PyTorch operator schemas
+  (source/op/pt/tabulate_multi_device.cc:1630-1696) for ``tabulate_fusion_se_a`` /
+  ``tabulate_fusion_se_atten`` -- differentiable twice, like the reference -- plus
+  ``prod_env_mat_a`` / ``prod_force_se_a`` / ``prod_virial_se_a`` whose argument lists mirror the
+  TensorFlow op schemas (source/op/tf/prod_env_mat_multi_device.cc:13-30,
+  prod_force_multi_device.cc:6-14, prod_virial_multi_device.cc:5-15).
+
+No CPU implementation exists here: CPU tensors are rejected.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import List, Optional, Sequence
+
+import numpy as np
+import torch
+
+from ._lib import MAX_NBOR_SIZE, lib
+
+__all__ = [
+    "prod_env_mat_a", "format_nlist", "tabulate_fusion_se_a", "tabulate_fusion_se_a_grad",
+    "tabulate_fusion_se_a_grad_grad", "prod_force_a", "prod_virial_a", "prod_force_virial_a",
+    "normalize_coord", "copy_coord", "build_nlist", "use_nlist_map", "csr_row_pointers",
+]
+
+
+# ------------------------------------------------------------------------------------------------
+# helpers
+# ------------------------------------------------------------------------------------------------
+def _suffix(t: torch.Tensor) -> str:
+    if t.dtype == torch.float64:
+        return "f64"
+    if t.dtype == torch.float32:
+        return "f32"
+    raise TypeError(f"dpb200: unsupported floating type {t.dtype} (float32 / float64 only)")
+
+
+def _p(t: Optional[torch.Tensor]):
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+def _stream(dev) -> C.c_void_p:
+    return C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+
+
+def _need_cuda(*named):
+    dev = None
+    for name, t in named:
+        if t is None:
+            continue
+        if not t.is_cuda:
+            raise RuntimeError(f"dpb200: `{name}` is on {t.device}; the hot path has no CPU implementation "
+                               "(CUDA tensors required)")
+        if dev is None:
+            dev = t.device
+        elif t.device != dev:
+            raise RuntimeError(f"dpb200: `{name}` is on {t.device} but other arguments are on {dev}")
+    return dev
+
+
+def _c(t: torch.Tensor, dtype=None) -> torch.Tensor:
+    if dtype is not None and t.dtype != dtype:
+        t = t.to(dtype)
+    return t if t.is_contiguous() else t.contiguous()
+
+
+def _sec_arr(sec: Sequence[int]):
+    sec = [int(s) for s in sec]
+    return (C.c_int * len(sec))(*sec), len(sec), sec[-1]
+
+
+def _workspace(nbytes: int, dev) -> torch.Tensor:
+    return torch.empty(max(int(nbytes), 256), dtype=torch.uint8, device=dev)
+
+
+def csr_row_pointers(neigh: torch.Tensor, numneigh: torch.Tensor) -> torch.Tensor:
+    """Device array of device row pointers (the `firstneigh` of a converted InputNlist,
+    source/lib/include/neighbor_list.h:20-57) for rows stored back to back in `neigh`."""
+    off = torch.cumsum(numneigh.to(torch.int64), 0) - numneigh.to(torch.int64)
+    return off * 4 + neigh.data_ptr()
+
+
+# ------------------------------------------------------------------------------------------------
+# a5-a7: neighbour formatting + environment matrix
+# ------------------------------------------------------------------------------------------------
+def _rows_args(numneigh, rows, firstneigh, max_nbor_size):
+    if firstneigh is not None:
+        if max_nbor_size is None:
+            max_nbor_size = int(numneigh.max().item()) if numneigh.numel() else 0
+        return None, 0, firstneigh, int(max_nbor_size)
+    if rows.dim() != 2:
+        raise ValueError("dpb200: `rows` must be a dense [nrows, capacity] int32 block")
+    cap = rows.shape[1]
+    if max_nbor_size is None:
+        max_nbor_size = cap
+    return rows, cap, None, int(min(max_nbor_size, cap))
+
+
+def prod_env_mat_a(coord, atype, numneigh, rows, avg, std, nloc, nall, rcut, rcut_smth, sec, *, ilist=None,
+                   f_type=None, firstneigh=None, nframes=1, max_nbor_size=None):
+    """deepmd::prod_env_mat_a_gpu (source/lib/include/prod_env_mat.h:91-110): returns
+    (em[nf*nloc, nnei*4], em_deriv[nf*nloc, nnei*12], rij[nf*nloc, nnei*3], nlist[nf*nloc, nnei])."""
+    dev = _need_cuda(("coord", coord), ("type", atype), ("numneigh", numneigh), ("rows", rows), ("avg", avg),
+                     ("std", std), ("ilist", ilist), ("f_type", f_type), ("firstneigh", firstneigh))
+    s = _suffix(coord)
+    coord = _c(coord)
+    atype = _c(atype, torch.int32)
+    numneigh = _c(numneigh, torch.int32)
+    avg = _c(avg, coord.dtype)
+    std = _c(std, coord.dtype)
+    if rows is not None:
+        rows = _c(rows, torch.int32)
+    if ilist is not None:
+        ilist = _c(ilist, torch.int32)
+    if f_type is not None:
+        f_type = _c(f_type, torch.int32)
+    sec_c, nsec, nnei = _sec_arr(sec)
+    ntypes = nsec - 1
+    if avg.numel() != ntypes * nnei * 4 or std.numel() != ntypes * nnei * 4:
+        raise ValueError("dpb200: avg/std must have ntypes*nnei*4 elements")
+    if coord.numel() != nframes * nall * 3 or atype.numel() != nframes * nall:
+        raise ValueError("dpb200: coord/type do not match nframes*nall")
+    rows_t, stride, fn, mx = _rows_args(numneigh, rows, firstneigh, max_nbor_size)
+    if mx > MAX_NBOR_SIZE:
+        raise ValueError(f"dpb200: neighbour rows wider than {MAX_NBOR_SIZE} are not supported")
+    n = nframes * nloc
+    em = torch.empty((n, nnei * 4), dtype=coord.dtype, device=dev)
+    dv = torch.empty((n, nnei * 12), dtype=coord.dtype, device=dev)
+    rij = torch.empty((n, nnei * 3), dtype=coord.dtype, device=dev)
+    nlist = torch.empty((n, nnei), dtype=torch.int32, device=dev)
+    L = lib()
+    wsb = L.cdll.dpb200_prod_env_mat_a_workspace_bytes(ntypes, nnei, nall, nframes, coord.element_size())
+    ws = _workspace(wsb, dev)
+    L.call("prod_env_mat_a_" + s, _p(em), _p(dv), _p(rij), _p(nlist), _p(coord), _p(atype), _p(f_type), _p(ilist),
+           _p(numneigh), _p(fn), _p(rows_t), stride, mx, _p(avg), _p(std), nloc, nall, nframes, float(rcut),
+           float(rcut_smth), sec_c, nsec, _p(ws), ws.numel(), _stream(dev))
+    return em, dv, rij, nlist
+
+
+def format_nlist(coord, atype, numneigh, rows, nloc, nall, rcut, sec, *, ilist=None, firstneigh=None, nframes=1,
+                 max_nbor_size=None):
+    """deepmd::format_nbor_list_gpu (source/lib/include/fmt_nlist.h:22-34) with the CPU semantics of
+    format_nlist_i_cpu (source/lib/src/fmt_nlist.cc:98-143): nlist[nf*nloc, nnei] int32."""
+    dev = _need_cuda(("coord", coord), ("type", atype), ("numneigh", numneigh), ("rows", rows), ("ilist", ilist),
+                     ("firstneigh", firstneigh))
+    s = _suffix(coord)
+    coord = _c(coord)
+    atype = _c(atype, torch.int32)
+    numneigh = _c(numneigh, torch.int32)
+    if rows is not None:
+        rows = _c(rows, torch.int32)
+    if ilist is not None:
+        ilist = _c(ilist, torch.int32)
+    sec_c, nsec, nnei = _sec_arr(sec)
+    rows_t, stride, fn, mx = _rows_args(numneigh, rows, firstneigh, max_nbor_size)
+    if mx > MAX_NBOR_SIZE:
+        raise ValueError(f"dpb200: neighbour rows wider than {MAX_NBOR_SIZE} are not supported")
+    nlist = torch.empty((nframes * nloc, nnei), dtype=torch.int32, device=dev)
+    L = lib()
+    wsb = L.cdll.dpb200_prod_env_mat_a_workspace_bytes(nsec - 1, nnei, nall, nframes, coord.element_size())
+    ws = _workspace(wsb, dev)
+    L.call("format_nlist_" + s, _p(nlist), _p(coord), _p(atype), _p(ilist), _p(numneigh), _p(fn), _p(rows_t), stride,
+           mx, nloc, nall, nframes, float(rcut), sec_c, nsec, _p(ws), ws.numel(), _stream(dev))
+    return nlist
+
+
+# ------------------------------------------------------------------------------------------------
+# a8-a10: compressed embedding table
+# ------------------------------------------------------------------------------------------------
+def _info_host(table_info: torch.Tensor, dtype) -> torch.Tensor:
+    if table_info.device.type != "cpu":
+        raise RuntimeError("table_info must be on the CPU")
+    ti = table_info.detach().reshape(-1).to(dtype).contiguous()
+    if ti.numel() < 5:
+        raise ValueError("table_info needs at least 5 entries (lower, upper, max, stride0, stride1)")
+    return ti
+
+
+def _check_tab(table, em_x, em, two_embed):
+    if table.dim() != 2:
+        raise ValueError("Dim of table should be 2")
+    if em_x.dim() != 2:
+        raise ValueError("Dim of input should be 2")
+    if em.dim() != 3:
+        raise ValueError("Dim of input should be 3")
+    if two_embed is not None and two_embed.dim() != 2:
+        raise ValueError("Dim of input should be 2")
+    if em.shape[2] != 4:
+        raise NotImplementedError(
+            f"The environment basis dimension must be 4 for the se_a / se_atten path, got {em.shape[2]}")
+    for name, t in (("em_x", em_x), ("em", em), ("two_embed", two_embed)):
+        if t is not None and t.device != table.device:
+            raise RuntimeError(f"{name} must be on the same device as table; table is on {table.device} but "
+                               f"{name} is on {t.device}")
+
+
+def tabulate_fusion_se_a(table, table_info, em_x, em, last_layer_size, two_embed=None, is_sorted=True):
+    """deepmd::tabulate_fusion_se_a_gpu (source/lib/include/tabulate.h:175-186): descriptor [nloc,4,M]."""
+    _check_tab(table, em_x, em, two_embed)
+    dev = _need_cuda(("table", table), ("em_x", em_x), ("em", em), ("two_embed", two_embed))
+    s = _suffix(table)
+    ti = _info_host(table_info, table.dtype)
+    table, em_x, em = _c(table), _c(em_x, table.dtype), _c(em, table.dtype)
+    if two_embed is not None:
+        two_embed = _c(two_embed, table.dtype)
+    nloc, nnei = em.shape[0], em.shape[1]
+    M = int(last_layer_size)
+    out = torch.empty((nloc, 4, M), dtype=table.dtype, device=dev)
+    lib().call("tabulate_fusion_se_a_" + s, _p(out), _p(table), C.c_void_p(ti.data_ptr()), _p(em_x), _p(em),
+               _p(two_embed), nloc, nnei, M, int(bool(is_sorted)), _stream(dev))
+    return out
+
+
+def tabulate_fusion_se_a_grad(table, table_info, em_x, em, dy, last_layer_size, two_embed=None, is_sorted=True):
+    """deepmd::tabulate_fusion_se_a_grad_gpu (tabulate.h:188-202): (dy_dem_x, dy_dem, dy_dtwo|None)."""
+    _check_tab(table, em_x, em, two_embed)
+    dev = _need_cuda(("table", table), ("em_x", em_x), ("em", em), ("two_embed", two_embed), ("dy", dy))
+    s = _suffix(table)
+    ti = _info_host(table_info, table.dtype)
+    table, em_x, em, dy = _c(table), _c(em_x, table.dtype), _c(em, table.dtype), _c(dy, table.dtype)
+    if two_embed is not None:
+        two_embed = _c(two_embed, table.dtype)
+    nloc, nnei = em.shape[0], em.shape[1]
+    M = int(last_layer_size)
+    g_x = torch.zeros_like(em_x) if nnei == 0 else torch.empty_like(em_x)
+    g_em = torch.zeros_like(em) if nnei == 0 else torch.empty_like(em)
+    g_two = None if two_embed is None else torch.empty_like(two_embed)
+    lib().call("tabulate_fusion_se_a_grad_" + s, _p(g_x), _p(g_em), _p(g_two), _p(table), C.c_void_p(ti.data_ptr()),
+               _p(em_x), _p(em), _p(two_embed), _p(dy), nloc, nnei, M, int(bool(is_sorted)), _stream(dev))
+    return g_x, g_em, g_two
+
+
+def tabulate_fusion_se_a_grad_grad(table, table_info, em_x, em, dz_dy_dem_x, dz_dy_dem, last_layer_size,
+                                   two_embed=None, dz_dy_dtwo=None, is_sorted=True):
+    """deepmd::tabulate_fusion_se_a_grad_grad_gpu (tabulate.h:204-218): dz_dy [nloc,4,M]."""
+    _check_tab(table, em_x, em, two_embed)
+    dev = _need_cuda(("table", table), ("em_x", em_x), ("em", em), ("two_embed", two_embed),
+                     ("dz_dy_dem_x", dz_dy_dem_x), ("dz_dy_dem", dz_dy_dem), ("dz_dy_dtwo", dz_dy_dtwo))
+    s = _suffix(table)
+    ti = _info_host(table_info, table.dtype)
+    table, em_x, em = _c(table), _c(em_x, table.dtype), _c(em, table.dtype)
+    dz_x, dz_em = _c(dz_dy_dem_x, table.dtype), _c(dz_dy_dem, table.dtype)
+    if two_embed is not None:
+        two_embed = _c(two_embed, table.dtype)
+        dz_dy_dtwo = torch.zeros_like(two_embed) if dz_dy_dtwo is None else _c(dz_dy_dtwo, table.dtype)
+    nloc, nnei = em.shape[0], em.shape[1]
+    M = int(last_layer_size)
+    out = torch.empty((nloc, 4, M), dtype=table.dtype, device=dev)
+    lib().call("tabulate_fusion_se_a_grad_grad_" + s, _p(out), _p(table), C.c_void_p(ti.data_ptr()), _p(em_x), _p(em),
+               _p(two_embed), _p(dz_x), _p(dz_em), _p(dz_dy_dtwo if two_embed is not None else None), nloc, nnei, M,
+               int(bool(is_sorted)), _stream(dev))
+    return out
+
+
+def tabulate_sections_fwd(tables, infos, em, sec, last_layer_size, is_sorted=True):
+    """All type sections of one env-mat in place (no slicing copies): sum_t tabulate(em[:, sec_t]) ->
+    [nloc,4,M].  `em` is the full [nloc, nnei*4] matrix of prod_env_mat_a; em_x is its component 0.
+    Mirrors the loop of deepmd/pt/model/descriptor/se_a.py:810-841 (type_one_side)."""
+    dev = _need_cuda(("em", em))
+    s = _suffix(em)
+    em = _c(em)
+    nloc = em.shape[0]
+    nnei = int(sec[-1])
+    M = int(last_layer_size)
+    out = torch.empty((nloc, 4, M), dtype=em.dtype, device=dev)
+    esz = em.element_size()
+    first = True
+    for t, (table, info) in enumerate(zip(tables, infos)):
+        n_t = int(sec[t + 1] - sec[t])
+        if n_t == 0:
+            continue
+        ti = _info_host(info, em.dtype)
+        base = em.data_ptr() + int(sec[t]) * 4 * esz
+        lib().call("tabulate_fusion_se_a_ex_" + s, _p(out), _p(_c(table)), C.c_void_p(ti.data_ptr()),
+                   C.c_void_p(base), nnei * 4, 4, C.c_void_p(base), nnei * 4, None, nloc, n_t, M,
+                   int(bool(is_sorted)), 0 if first else 1, _stream(dev))
+        first = False
+    if first:
+        out.zero_()
+    return out
+
+
+def tabulate_sections_grad(tables, infos, em, dy, sec, last_layer_size, is_sorted=True):
+    """Backward of tabulate_sections_fwd: d/d(em) as one [nloc, nnei*4] matrix (the em_x gradient is
+    added into component 0 inside the kernel, which is what autograd does with the
+    `ss = rr[..., :1]` slice of deepmd/pt/model/descriptor/se_a.py:818-820)."""
+    dev = _need_cuda(("em", em), ("dy", dy))
+    s = _suffix(em)
+    em, dy = _c(em), _c(dy, em.dtype)
+    nloc = em.shape[0]
+    nnei = int(sec[-1])
+    M = int(last_layer_size)
+    g_em = torch.empty_like(em)
+    esz = em.element_size()
+    for t, (table, info) in enumerate(zip(tables, infos)):
+        n_t = int(sec[t + 1] - sec[t])
+        if n_t == 0:
+            continue
+        ti = _info_host(info, em.dtype)
+        off = int(sec[t])
+        base = em.data_ptr() + off * 4 * esz
+        lib().call("tabulate_fusion_se_a_grad_ex_" + s, None,
+                   C.c_void_p(g_em.data_ptr() + off * 4 * esz), None, _p(_c(table)), C.c_void_p(ti.data_ptr()),
+                   C.c_void_p(base), nnei * 4, 4, C.c_void_p(base), nnei * 4, None, _p(dy), nloc, n_t, M,
+                   int(bool(is_sorted)), _stream(dev))
+    return g_em
+
+
+# ------------------------------------------------------------------------------------------------
+# a11-a12: force / virial
+# ------------------------------------------------------------------------------------------------
+def prod_force_a(net_deriv, in_deriv, nlist, nloc, nall, nnei, nframes=1):
+    """deepmd::prod_force_a_gpu (source/lib/include/prod_force.h:71-79): force [nframes, nall*3]."""
+    dev = _need_cuda(("net_deriv", net_deriv), ("in_deriv", in_deriv), ("nlist", nlist))
+    s = _suffix(net_deriv)
+    net_deriv, in_deriv, nlist = _c(net_deriv), _c(in_deriv, net_deriv.dtype), _c(nlist, torch.int32)
+    if net_deriv.numel() != nframes * nloc * nnei * 4 or in_deriv.numel() != nframes * nloc * nnei * 12:
+        raise ValueError("dpb200: net_deriv / in_deriv do not match nframes*nloc*nnei")
+    force = torch.empty((nframes, nall * 3), dtype=net_deriv.dtype, device=dev)
+    lib().call("prod_force_a_" + s, _p(force), _p(net_deriv), _p(in_deriv), _p(nlist), nloc, nall, nnei, nframes,
+               _stream(dev))
+    return force
+
+
+def prod_virial_a(net_deriv, in_deriv, rij, nlist, nloc, nall, nnei):
+    """deepmd::prod_virial_a_gpu (source/lib/include/prod_virial.h:30-39): (virial[9], atom_virial[nall*9])."""
+    dev = _need_cuda(("net_deriv", net_deriv), ("in_deriv", in_deriv), ("rij", rij), ("nlist", nlist))
+    s = _suffix(net_deriv)
+    dt = net_deriv.dtype
+    net_deriv, in_deriv, rij, nlist = _c(net_deriv), _c(in_deriv, dt), _c(rij, dt), _c(nlist, torch.int32)
+    virial = torch.empty(9, dtype=dt, device=dev)
+    atom_virial = torch.empty(nall * 9, dtype=dt, device=dev)
+    lib().call("prod_virial_a_" + s, _p(virial), _p(atom_virial), _p(net_deriv), _p(in_deriv), _p(rij), _p(nlist),
+               nloc, nall, nnei, _stream(dev))
+    return virial, atom_virial
+
+
+def prod_force_virial_a(net_deriv, in_deriv, rij, nlist, nloc, nall, nnei, atom_virial=False):
+    """Fused single pass over net_deriv / in_deriv: (force[nall*3], virial[9], atom_virial|None)."""
+    dev = _need_cuda(("net_deriv", net_deriv), ("in_deriv", in_deriv), ("rij", rij), ("nlist", nlist))
+    s = _suffix(net_deriv)
+    dt = net_deriv.dtype
+    net_deriv, in_deriv, rij, nlist = _c(net_deriv), _c(in_deriv, dt), _c(rij, dt), _c(nlist, torch.int32)
+    force = torch.empty(nall * 3, dtype=dt, device=dev)
+    virial = torch.empty(9, dtype=dt, device=dev)
+    av = torch.empty(nall * 9, dtype=dt, device=dev) if atom_virial else None
+    lib().call("prod_force_virial_a_" + s, _p(force), _p(virial), _p(av), _p(net_deriv), _p(in_deriv), _p(rij),
+               _p(nlist), nloc, nall, nnei, _stream(dev))
+    return force, virial, av
+
+
+# ------------------------------------------------------------------------------------------------
+# a2-a4: neighbour-list front end
+# ------------------------------------------------------------------------------------------------
+def _box_host(box, dtype):
+    b = torch.as_tensor(box).detach().to("cpu").reshape(9).to(dtype).contiguous()
+    return b
+
+
+def normalize_coord(coord, box):
+    """deepmd::normalize_coord_gpu (source/lib/include/coord.h:47-55), in place; returns coord."""
+    dev = _need_cuda(("coord", coord))
+    s = _suffix(coord)
+    if not coord.is_contiguous():
+        raise ValueError("dpb200: normalize_coord works in place and needs a contiguous tensor")
+    b = _box_host(box, coord.dtype)
+    lib().call("normalize_coord_" + s, _p(coord), coord.numel() // 3, C.c_void_p(b.data_ptr()), _stream(dev))
+    return coord
+
+
+def copy_coord(coord, atype, box, rcut, mem_nall=None):
+    """deepmd::copy_coord_gpu (coord.h:57-85) with the caller-side retry folded in:
+    returns (ext_coord[nall,3], ext_type[nall], mapping[nall])."""
+    dev = _need_cuda(("coord", coord), ("type", atype))
+    s = _suffix(coord)
+    coord = _c(coord).reshape(-1, 3)
+    atype = _c(atype, torch.int32).reshape(-1)
+    nloc = atype.numel()
+    b = _box_host(box, coord.dtype)
+    L = lib()
+    ws = _workspace(L.cdll.dpb200_copy_coord_workspace_bytes(nloc), dev)
+    mem = int(mem_nall) if mem_nall is not None else max(64, 2 * nloc)
+    for _ in range(8):
+        out_c = torch.empty((mem, 3), dtype=coord.dtype, device=dev)
+        out_t = torch.empty(mem, dtype=torch.int32, device=dev)
+        mapping = torch.empty(mem, dtype=torch.int32, device=dev)
+        nall = C.c_int(0)
+        rc = L.call("copy_coord_" + s, _p(out_c), _p(out_t), _p(mapping), C.byref(nall), _p(coord), _p(atype), nloc,
+                    mem, float(rcut), C.c_void_p(b.data_ptr()), _p(ws), ws.numel(), _stream(dev))
+        if rc == 0:
+            n = nall.value
+            return out_c[:n], out_t[:n], mapping[:n]
+        if mem_nall is not None:
+            raise MemoryError(f"copy_coord: nall={nall.value} exceeds mem_nall={mem_nall}")
+        mem = nall.value
+    raise RuntimeError("copy_coord: retry limit reached")
+
+
+def build_nlist(coord, nloc, rcut, atype=None, mem_size=None):
+    """deepmd::build_nlist_gpu (source/lib/include/neighbor_list.h:256-266), cell list, with the
+    caller-side doubling retry folded in: returns (numneigh[nloc], rows[nloc, mem_size])."""
+    dev = _need_cuda(("coord", coord), ("type", atype))
+    s = _suffix(coord)
+    coord = _c(coord).reshape(-1, 3)
+    nall = coord.shape[0]
+    if atype is not None:
+        atype = _c(atype, torch.int32)
+    L = lib()
+    ws = _workspace(L.cdll.dpb200_build_nlist_workspace_bytes(nall), dev)
+    mem = int(mem_size) if mem_size is not None else 256
+    for _ in range(8):
+        numneigh = torch.empty(nloc, dtype=torch.int32, device=dev)
+        rows = torch.empty((nloc, mem), dtype=torch.int32, device=dev)
+        mx = C.c_int(0)
+        rc = L.call("build_nlist_" + s, _p(numneigh), _p(rows), C.byref(mx), _p(coord), nloc, nall, mem, float(rcut),
+                    _p(atype), _p(ws), ws.numel(), _stream(dev))
+        if rc == 0:
+            return numneigh, rows
+        if mem_size is not None:
+            raise MemoryError(f"build_nlist: a row needs {mx.value} entries, mem_size={mem_size}")
+        mem = (mx.value + 31) // 32 * 32
+    raise RuntimeError("build_nlist: retry limit reached")
+
+
+def use_nlist_map(nlist, mapping):
+    """deepmd::use_nlist_map (neighbor_list.h:219-222), in place."""
+    dev = _need_cuda(("nlist", nlist), ("mapping", mapping))
+    if nlist.dtype != torch.int32 or not nlist.is_contiguous():
+        raise ValueError("dpb200: nlist must be a contiguous int32 tensor")
+    mapping = _c(mapping, torch.int32)
+    nnei = nlist.shape[-1]
+    lib().cdll.dpb200_use_nlist_map(_p(nlist), _p(mapping), nlist.numel() // max(nnei, 1), nnei, _stream(dev))
+    return nlist
+
+
+# ------------------------------------------------------------------------------------------------
+# torch.ops.deepmd.*  (reference operator surface)
+# ------------------------------------------------------------------------------------------------
+class _TabGradOp(torch.autograd.Function):
+    """TabulateFusionSeAGradOp / TabulateFusionSeAttenGradOp
+    (source/op/pt/tabulate_multi_device.cc:731-831, 964-1061): differentiable w.r.t. dy only."""
+
+    @staticmethod
+    def forward(ctx, table, table_info, em_x, em, two_embed, dy, M, is_sorted):
+        ctx.save_for_backward(table, table_info, em_x, em, two_embed)
+        ctx.M, ctx.is_sorted = M, is_sorted
+        gx, gem, gtwo = tabulate_fusion_se_a_grad(table, table_info, em_x, em, dy, M, two_embed, is_sorted)
+        if gtwo is None:
+            return gx, gem
+        return gx, gem, gtwo
+
+    @staticmethod
+    def backward(ctx, *dz):
+        table, table_info, em_x, em, two_embed = ctx.saved_tensors
+        dz_x = dz[0] if dz[0] is not None else torch.zeros_like(em_x)
+        dz_em = dz[1] if dz[1] is not None else torch.zeros_like(em)
+        dz_two = dz[2] if len(dz) > 2 else None
+        dz_dy = tabulate_fusion_se_a_grad_grad(table, table_info, em_x, em, dz_x, dz_em, ctx.M, two_embed, dz_two,
+                                               ctx.is_sorted)
+        return None, None, None, None, None, dz_dy, None, None
+
+
+class _TabOp(torch.autograd.Function):
+    """TabulateFusionSeAOp / TabulateFusionSeAttenOp (tabulate_multi_device.cc:881-962, 1063-1151)."""
+
+    @staticmethod
+    def forward(ctx, table, table_info, em_x, em, two_embed, M, is_sorted):
+        ctx.save_for_backward(table, table_info, em_x, em, two_embed)
+        ctx.M, ctx.is_sorted = M, is_sorted
+        return tabulate_fusion_se_a(table, table_info, em_x, em, M, two_embed, is_sorted)
+
+    @staticmethod
+    def backward(ctx, dy):
+        table, table_info, em_x, em, two_embed = ctx.saved_tensors
+        res = _TabGradOp.apply(table, table_info, em_x, em, two_embed, dy.contiguous(), ctx.M, ctx.is_sorted)
+        gtwo = res[2] if len(res) > 2 else None
+        return None, None, res[0], res[1], gtwo, None, None
+
+
+def _op_tabulate_fusion_se_a(table, table_info, em_x, em, last_layer_size):
+    return [_TabOp.apply(table, table_info, em_x, em, None, int(last_layer_size), True)]
+
+
+def _op_tabulate_fusion_se_atten(table, table_info, em_x, em, two_embed, last_layer_size, is_sorted):
+    return [_TabOp.apply(table, table_info, em_x, em, two_embed, int(last_layer_size), bool(is_sorted))]
+
+
+def decode_mesh(mesh: torch.Tensor, nloc: int):
+    """Neighbour-list hand-off encodings of the `mesh` argument (SURVEY.md 8b;
+    source/lib/src/prod_env_mat.cc:327-332, source/op/tf/prod_env_mat_multi_device.cc:2813-2828).
+    Returns (mode, ilist, numneigh, neigh) with CSR rows, tensors on the CPU or on mesh.device."""
+    n = mesh.numel()
+    if n == 0:
+        return "nopbc", None, None, None
+    if n == 6:
+        return "pbc", None, None, None
+    if n == 16:
+        m = mesh.detach().to("cpu", torch.int32).contiguous().numpy()
+        inum = int(m[1])
+        as_ptr = lambda k: int(np.frombuffer(m[k:k + 2].tobytes(), dtype=np.uint64)[0])
+        ilist = np.ctypeslib.as_array(C.cast(as_ptr(4), C.POINTER(C.c_int)), shape=(inum,)).copy()
+        numneigh = np.ctypeslib.as_array(C.cast(as_ptr(8), C.POINTER(C.c_int)), shape=(inum,)).copy()
+        first = C.cast(as_ptr(12), C.POINTER(C.POINTER(C.c_int)))
+        rows = [np.ctypeslib.as_array(first[r], shape=(int(numneigh[r]),)).copy() if numneigh[r] > 0
+                else np.zeros(0, np.int32) for r in range(inum)]
+        neigh = np.concatenate(rows) if rows else np.zeros(0, np.int32)
+        return ("list", torch.from_numpy(ilist.astype(np.int32)), torch.from_numpy(numneigh.astype(np.int32)),
+                torch.from_numpy(neigh.astype(np.int32)))
+    if n > 16:
+        m = mesh.reshape(-1)
+        inum = int(m[1].item())
+        ilist = m[16:16 + inum]
+        numneigh = m[16 + inum:16 + 2 * inum]
+        neigh = m[16 + 2 * inum:]
+        return "list", ilist, numneigh, neigh
+    raise ValueError(f"invalid mesh tensor of length {n} (mixed-type meshes of length 1/7 are not supported)")
+
+
+def _op_prod_env_mat_a(coord, type, natoms, box, mesh, davg, dstd, rcut_a: float, rcut_r: float, rcut_r_smth: float,
+                       sel_a: List[int], sel_r: List[int]):
+    """ProdEnvMatA (source/op/tf/prod_env_mat_multi_device.cc:13-30, host logic :451-905)."""
+    dev = _need_cuda(("coord", coord), ("type", type), ("davg", davg), ("dstd", dstd))
+    if coord.dim() != 2 or type.dim() != 2:
+        raise ValueError("Dim of coord and type should be 2")
+    nat = natoms.detach().to("cpu").reshape(-1).tolist()
+    if len(nat) < 3:
+        raise ValueError("number of atoms should be larger than (or equal to) 3")
+    nloc, nall = int(nat[0]), int(nat[1])
+    ntypes = len(nat) - 2
+    if len(sel_a) != ntypes:
+        raise ValueError("number of types should match the length of sel array")
+    if any(int(s) != 0 for s in sel_r):
+        raise NotImplementedError("prod_env_mat_a: radial-only selections (sel_r) are outside the se_a hot path")
+    nf = coord.shape[0]
+    if coord.shape[1] != nall * 3 or type.shape[1] != nall or type.shape[0] != nf:
+        raise ValueError("number of atoms should match")
+    sec = [0]
+    for s_ in sel_a:
+        sec.append(sec[-1] + int(s_))
+    nnei = sec[-1]
+    if davg.numel() != ntypes * nnei * 4 or dstd.numel() != ntypes * nnei * 4:
+        raise ValueError("number of avg / std should be ntype * ndescrpt")
+    mode, ilist, numneigh, neigh = decode_mesh(mesh, nloc)
+    dt = coord.dtype
+    if mode == "list":
+        if nf != 1:
+            raise ValueError("a neighbour list passed through mesh implies a single frame")
+        ilist, numneigh, neigh = (t.to(dev, torch.int32).contiguous() for t in (ilist, numneigh, neigh))
+        if ilist.numel() != nloc:
+            raise ValueError(f"neighbour list has {ilist.numel()} centre atoms but natoms[0] = {nloc}")
+        if neigh.numel() == 0:
+            neigh = torch.zeros(1, dtype=torch.int32, device=dev)
+        fn = csr_row_pointers(neigh, numneigh)
+        mx = int(numneigh.max().item()) if numneigh.numel() else 0
+        if mx > MAX_NBOR_SIZE:
+            raise ValueError(f"Neighbor row is larger than the maximum supported size {MAX_NBOR_SIZE}")
+        em, dv, rij, nl = prod_env_mat_a(coord.reshape(-1), type.reshape(-1), numneigh, None, davg, dstd, nloc, nall,
+                                         rcut_r, rcut_r_smth, sec, ilist=ilist, firstneigh=fn, max_nbor_size=mx)
+        return (em.reshape(1, -1), dv.reshape(1, -1), rij.reshape(1, -1), nl.reshape(1, -1))
+    outs = ([], [], [], [])
+    for f in range(nf):
+        c = coord[f].reshape(-1, 3).to(dt).contiguous().clone()
+        t = type[f].to(torch.int32).contiguous()
+        if mode == "pbc":
+            if nall != nloc:
+                raise ValueError("PBC mesh (length 6) expects nall == nloc; ghosts are generated by the op")
+            normalize_coord(c, box[f])
+            ext_c, ext_t, mapping = copy_coord(c, t, box[f], rcut_r)
+        else:
+            ext_c, ext_t, mapping = c, t, None
+        n_ext = ext_t.numel()
+        numneigh_f, rows_f = build_nlist(ext_c, nloc, rcut_r, ext_t)
+        em, dv, rij, nl = prod_env_mat_a(ext_c.reshape(-1), ext_t, numneigh_f, rows_f, davg, dstd, nloc, n_ext, rcut_r,
+                                         rcut_r_smth, sec)
+        if mapping is not None:
+            use_nlist_map(nl, mapping)
+        for o, v in zip(outs, (em, dv, rij, nl)):
+            o.append(v.reshape(1, -1))
+    return tuple(torch.cat(o, 0) for o in outs)
+
+
+def _op_prod_force_se_a(net_deriv, in_deriv, nlist, natoms, n_a_sel: int, n_r_sel: int):
+    """ProdForceSeA (source/op/tf/prod_force_multi_device.cc:6-14, 50-167)."""
+    nat = natoms.detach().to("cpu").reshape(-1).tolist()
+    nloc, nall = int(nat[0]), int(nat[1])
+    nnei = int(n_a_sel) + int(n_r_sel)
+    if net_deriv.dim() != 2 or in_deriv.dim() != 2 or nlist.dim() != 2:
+        raise ValueError("Dim of net deriv, input deriv and nlist should be 2")
+    nf = net_deriv.shape[0]
+    if in_deriv.shape[0] != nf or nlist.shape[0] != nf:
+        raise ValueError("number of samples should match")
+    if nloc * nnei * 4 != net_deriv.shape[1] or nloc * nnei * 12 != in_deriv.shape[1] or nloc * nnei != nlist.shape[1]:
+        raise ValueError("number of descriptors should match")
+    return prod_force_a(net_deriv, in_deriv, nlist, nloc, nall, nnei, nf)
+
+
+def _op_prod_virial_se_a(net_deriv, in_deriv, rij, nlist, natoms, n_a_sel: int, n_r_sel: int):
+    """ProdVirialSeA (source/op/tf/prod_virial_multi_device.cc:5-15, 40-140)."""
+    nat = natoms.detach().to("cpu").reshape(-1).tolist()
+    nloc, nall = int(nat[0]), int(nat[1])
+    nnei = int(n_a_sel) + int(n_r_sel)
+    if net_deriv.dim() != 2 or in_deriv.dim() != 2 or rij.dim() != 2 or nlist.dim() != 2:
+        raise ValueError("Dim of net deriv, input deriv, rij and nlist should be 2")
+    nf = net_deriv.shape[0]
+    if nloc * nnei * 4 != net_deriv.shape[1] or nloc * nnei * 12 != in_deriv.shape[1] or \
+            nloc * nnei * 3 != rij.shape[1] or nloc * nnei != nlist.shape[1]:
+        raise ValueError("number of descriptors should match")
+    vs, avs = [], []
+    for f in range(nf):
+        v, av = prod_virial_a(net_deriv[f], in_deriv[f], rij[f], nlist[f], nloc, nall, nnei)
+        vs.append(v.reshape(1, 9))
+        avs.append(av.reshape(1, -1))
+    return torch.cat(vs, 0), torch.cat(avs, 0)
+
+
+_REGISTERED = False
+_LIBRARY = None
+
+
+def register_torch_ops():
+    """Define torch.ops.deepmd.* once per process (TORCH_LIBRARY_FRAGMENT(deepmd, m) in the
+    reference, tabulate_multi_device.cc:1682-1696)."""
+    global _REGISTERED, _LIBRARY
+    if _REGISTERED:
+        return
+    L = torch.library.Library("deepmd", "FRAGMENT")
+    L.define("tabulate_fusion_se_a(Tensor table, Tensor table_info, Tensor em_x, Tensor em, int last_layer_size) "
+             "-> Tensor[]")
+    L.define("tabulate_fusion_se_atten(Tensor table, Tensor table_info, Tensor em_x, Tensor em, Tensor two_embed, "
+             "int last_layer_size, bool is_sorted) -> Tensor[]")
+    L.define("prod_env_mat_a(Tensor coord, Tensor type, Tensor natoms, Tensor box, Tensor mesh, Tensor davg, "
+             "Tensor dstd, float rcut_a, float rcut_r, float rcut_r_smth, int[] sel_a, int[] sel_r) "
+             "-> (Tensor, Tensor, Tensor, Tensor)")
+    L.define("prod_force_se_a(Tensor net_deriv, Tensor in_deriv, Tensor nlist, Tensor natoms, int n_a_sel, "
+             "int n_r_sel) -> Tensor")
+    L.define("prod_virial_se_a(Tensor net_deriv, Tensor in_deriv, Tensor rij, Tensor nlist, Tensor natoms, "
+             "int n_a_sel, int n_r_sel) -> (Tensor, Tensor)")
+    L.impl("tabulate_fusion_se_a", _op_tabulate_fusion_se_a, "CompositeImplicitAutograd")
+    L.impl("tabulate_fusion_se_atten", _op_tabulate_fusion_se_atten, "CompositeImplicitAutograd")
+    L.impl("prod_env_mat_a", _op_prod_env_mat_a, "CompositeExplicitAutograd")
+    L.impl("prod_force_se_a", _op_prod_force_se_a, "CompositeExplicitAutograd")
+    L.impl("prod_virial_se_a", _op_prod_virial_se_a, "CompositeExplicitAutograd")
+    _LIBRARY = L
+    _REGISTERED = True

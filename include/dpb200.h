@@ -26,6 +26,9 @@
 #ifdef __cplusplus
 extern "C" {
 #endif
+#if defined(__GNUC__)
+#pragma GCC visibility push(default) /* the library is built with -fvisibility=hidden */
+#endif
 
 #define DPB200_OK 0
 #define DPB200_ERR_INVALID (-1)        /* bad argument (maps to deepmd::deepmd_exception) */
@@ -88,7 +91,8 @@ DPB200_DECL_ENV(f32, float)
  * The `_ex` forms take element strides so a caller can pass one type-section of the full
  * env-mat without copying (deepmd/pt/model/descriptor/se_a.py:810-831 slices and copies):
  *   em_x[i,j]   at em_x + i*ldx_i + j*ldx_j ;  em[i,j,0:4] at em + i*ldem_i + j*4
- *   dy_dem_x / dy_dem use the same strides as em_x / em;
+ *   dy_dem_x / dy_dem use the same strides as em_x / em;  grad_ex with dy_dem_x == NULL adds
+ *   the em_x gradient into dy_dem[i,j,0] (em_x being component 0 of em, as in se_a.py:818-820);
  *   accumulate!=0 adds into `out` instead of overwriting it (sum over type sections).
  * ------------------------------------------------------------------------------------- */
 #define DPB200_DECL_TAB(SUF, FP)                                                                   \
@@ -178,6 +182,9 @@ DPB200_DECL_NL(f32, float)
 /* use_nlist_map (neighbor_list.h:219-222): nlist[k] = map[nlist[k]] for entries >= 0. */
 int dpb200_use_nlist_map(int* nlist, const int* nlist_map, int nloc, int nnei, dpb200_stream_t stream);
 
+#if defined(__GNUC__)
+#pragma GCC visibility pop
+#endif
 #ifdef __cplusplus
 }
 #endif

@@ -88,6 +88,22 @@ def main():
             json.dump(data, f, separators=(",", ":"))
         sizes = {c: {k: (len(v) if isinstance(v, list) else v) for k, v in data[c].items()} for c in classes if c in data}
         print(f"{fname}: {sizes} missing={missing}")
+    water192(args.ref)
+
+
+def water192(ref):
+    """BASELINE config 1: frame 0 of examples/water/data/data_0 (192 atoms, cubic box)."""
+    import numpy as np
+
+    d = os.path.join(ref, "examples", "water", "data", "data_0")
+    coord = np.load(os.path.join(d, "set.000", "coord.npy"))[0].astype(np.float64)
+    box = np.load(os.path.join(d, "set.000", "box.npy"))[0].astype(np.float64)
+    atype = [int(x) for x in open(os.path.join(d, "type.raw")).read().split()]
+    out = {"_source": "examples/water/data/data_0/set.000 frame 0 (float32 data cast to float64)",
+           "coord": coord.tolist(), "box": box.tolist(), "atype": atype}
+    with open(os.path.join(HERE, "water192.json"), "w") as f:
+        json.dump(out, f)
+    print(f"water192.json: {len(atype)} atoms, box {box.reshape(3, 3).diagonal()}")
 
 
 if __name__ == "__main__":

@@ -1,0 +1,518 @@
+"""GPU parity tests: the CUDA path (through the C ABI / torch ops) against the CPU oracle and the
+reference's golden vectors.  Integer outputs must be bit-exact; floating point within the
+north_star tolerances: 1e-10 relative (fp64), 1e-5 (fp32), relative to the largest reference
+magnitude of the compared array (sums with cancellation have no meaningful per-element ratio).
+"""
+import numpy as np
+import pytest
+import torch
+
+from oracle import cpu as ocpu
+from _systems import extended_system, golden, random_table, six_atom_system, water_like_box
+
+pytestmark = pytest.mark.gpu
+
+TOL = {np.float64: 1e-10, np.float32: 1e-5}
+DEV = "cuda:0"
+
+
+@pytest.fixture(scope="module")
+def ops():
+    import __graft_entry__ as g
+
+    return g.load_package().ops
+
+
+def T(a, dtype=None):
+    t = torch.as_tensor(np.ascontiguousarray(a))
+    if dtype is not None:
+        t = t.to(dtype)
+    return t.to(DEV)
+
+
+def N(t):
+    return t.detach().cpu().numpy()
+
+
+def close(got, want, dtype, scale=None, fac=1.0):
+    got = np.asarray(got, dtype=np.float64).reshape(-1)
+    want = np.asarray(want, dtype=np.float64).reshape(-1)
+    assert got.shape == want.shape
+    s = scale if scale is not None else max(np.abs(want).max() if want.size else 0.0, 1e-300)
+    tol = TOL[dtype] * fac
+    err = np.abs(got - want).max() if want.size else 0.0
+    assert err <= tol * s, f"max abs err {err:.3e} > {tol:.1e} * {s:.3e}"
+
+
+def avg_std(ntypes, nnei, dtype, seed=3):
+    rng = np.random.default_rng(seed)
+    avg = rng.normal(scale=0.05, size=(ntypes, nnei * 4)).astype(dtype)
+    avg[:, 1::4] = 0
+    avg[:, 2::4] = 0
+    avg[:, 3::4] = 0
+    std = (0.08 + 0.1 * rng.random(size=(ntypes, nnei * 4))).astype(dtype)
+    return avg, std
+
+
+# ------------------------------------------------------------------ a5: format_nlist ---------
+@pytest.mark.parametrize("cls", ["TestFormatNlist", "TestFormatNlistShortSel"])
+def test_format_nlist_golden(ops, port, cls):
+    g = golden("fmt_nlist.json")[cls]
+    s = six_atom_system(port, rc=g["rc"])
+    nl = ops.format_nlist(T(s["coord"]), T(s["atype"]), T(s["numneigh"]), T(s["rows"]), s["nloc"], len(s["atype"]),
+                          g["rc"], g["sec_a"])
+    assert N(nl).reshape(-1).tolist() == g["expect_nlist_cpy"]
+
+
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+@pytest.mark.parametrize("jitter", [0.0, 0.05])
+@pytest.mark.parametrize("sel", [(46, 92), (6, 11)])
+def test_format_nlist_bit_exact(ops, port, dtype, jitter, sel):
+    """Replicated boxes (exact distance ties when jitter == 0) and overflowing selections."""
+    coord, atype, box = water_like_box(ncopy=2, seed=1, jitter=jitter, dtype=dtype)
+    s = extended_system(port, coord, atype, box, 6.5, dtype=dtype)
+    sec = [0, sel[0], sel[0] + sel[1]]
+    off, neigh = ocpu.dense_to_csr(s["rows"], s["numneigh"])
+    want, _ = port.format_nlist(s["coord"], s["atype"], off, neigh, 6.0, sec)
+    got = ops.format_nlist(T(s["coord"]), T(s["atype"]), T(s["numneigh"]), T(s["rows"]), s["nloc"], len(s["atype"]),
+                           6.0, sec)
+    assert np.array_equal(N(got), want)
+    # CSR rows through device row pointers (InputNlist layout) + a shuffled raw order
+    rng = np.random.default_rng(0)
+    rows = s["rows"].copy()
+    for i in range(rows.shape[0]):
+        n = s["numneigh"][i]
+        rows[i, :n] = rng.permutation(rows[i, :n])
+    off2, neigh2 = ocpu.dense_to_csr(rows, s["numneigh"])
+    neigh_t = T(neigh2)
+    nn_t = T(s["numneigh"])
+    fn = ops.csr_row_pointers(neigh_t, nn_t)
+    got2 = ops.format_nlist(T(s["coord"]), T(s["atype"]), nn_t, None, s["nloc"], len(s["atype"]), 6.0, sec,
+                            firstneigh=fn)
+    assert np.array_equal(N(got2), want)
+
+
+def test_format_nlist_virtual_atoms_and_empty(ops, port):
+    coord, atype, box = water_like_box(ncopy=1, seed=2, jitter=0.05)
+    atype = atype.copy()
+    atype[::7] = -1  # virtual atoms are never neighbours
+    s = extended_system(port, coord, atype, box, 6.0)
+    sec = [0, 20, 60]
+    off, neigh = ocpu.dense_to_csr(s["rows"], s["numneigh"])
+    want, _ = port.format_nlist(s["coord"], s["atype"], off, neigh, 6.0, sec)
+    got = ops.format_nlist(T(s["coord"]), T(s["atype"]), T(s["numneigh"]), T(s["rows"]), s["nloc"], len(s["atype"]),
+                           6.0, sec)
+    assert np.array_equal(N(got), want)
+    # rows with zero neighbours
+    nn0 = np.zeros_like(s["numneigh"])
+    got0 = ops.format_nlist(T(s["coord"]), T(s["atype"]), T(nn0), T(s["rows"]), s["nloc"], len(s["atype"]), 6.0, sec)
+    assert (N(got0) == -1).all()
+    # nloc == 0
+    e = ops.format_nlist(T(s["coord"]), T(s["atype"]), T(nn0[:0]), T(s["rows"][:0]), 0, len(s["atype"]), 6.0, sec)
+    assert e.shape == (0, 60)
+
+
+# ------------------------------------------------------------------ a6/a7: env mat -----------
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+def test_prod_env_mat_a_golden(ops, port, dtype):
+    g = golden("env_mat_a.json")["TestEnvMatA"]
+    s = six_atom_system(port, rc=g["rc"], dtype=dtype)
+    sec = g["sec_a"]
+    nnei = sec[-1]
+    avg = np.zeros((2, nnei * 4), dtype)
+    std = np.ones((2, nnei * 4), dtype)
+    em, dv, rij, nl = ops.prod_env_mat_a(T(s["coord"]), T(s["atype"]), T(s["numneigh"]), T(s["rows"]), T(avg), T(std),
+                                         s["nloc"], len(s["atype"]), g["rc"], g["rc_smth"], sec)
+    np.testing.assert_allclose(N(em).reshape(-1), np.array(g["expected_env"]), atol=1e-5)
+    off, neigh = ocpu.dense_to_csr(s["rows"], s["numneigh"])
+    w_em, w_dv, w_rij, w_nl = port.prod_env_mat_a(s["coord"], s["atype"], off, neigh, avg, std, s["nloc"], g["rc"],
+                                                  g["rc_smth"], sec)
+    assert np.array_equal(N(nl), w_nl)
+    close(N(em), w_em, dtype)
+    close(N(dv), w_dv, dtype)
+    close(N(rij), w_rij, dtype)
+
+
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+@pytest.mark.parametrize("jitter", [0.0, 0.05])
+def test_prod_env_mat_a_water(ops, port, dtype, jitter):
+    coord, atype, box = water_like_box(ncopy=2, seed=5, jitter=jitter, dtype=dtype)
+    atype = atype.copy()
+    atype[5] = -1  # one virtual centre atom: zero rows
+    s = extended_system(port, coord, atype, box, 6.8, dtype=dtype)
+    sec = [0, 46, 138]
+    avg, std = avg_std(2, 138, dtype)
+    off, neigh = ocpu.dense_to_csr(s["rows"], s["numneigh"])
+    w = port.prod_env_mat_a(s["coord"], s["atype"], off, neigh, avg, std, s["nloc"], 6.0, 0.5, sec)
+    got = ops.prod_env_mat_a(T(s["coord"]), T(s["atype"]), T(s["numneigh"]), T(s["rows"]), T(avg), T(std), s["nloc"],
+                             len(s["atype"]), 6.0, 0.5, sec)
+    assert np.array_equal(N(got[3]), w[3])
+    for a, b in zip(got[:3], w[:3]):
+        close(N(a), b, dtype)
+
+
+def test_prod_env_mat_a_ilist_permutation(ops, port):
+    """ilist in arbitrary order writes row ilist[r] (prod_env_mat.cc:43-46)."""
+    coord, atype, box = water_like_box(ncopy=1, seed=6, jitter=0.05)
+    s = extended_system(port, coord, atype, box, 6.0)
+    sec = [0, 20, 50]
+    avg, std = avg_std(2, 50, np.float64)
+    rng = np.random.default_rng(1)
+    perm = rng.permutation(s["nloc"]).astype(np.int32)
+    off, neigh = ocpu.dense_to_csr(s["rows"][perm], s["numneigh"][perm])
+    w = port.prod_env_mat_a(s["coord"], s["atype"], off, neigh, avg, std, s["nloc"], 6.0, 1.0, sec, ilist=perm)
+    got = ops.prod_env_mat_a(T(s["coord"]), T(s["atype"]), T(s["numneigh"][perm]), T(s["rows"][perm]), T(avg), T(std),
+                             s["nloc"], len(s["atype"]), 6.0, 1.0, sec, ilist=T(perm))
+    assert np.array_equal(N(got[3]), w[3])
+    close(N(got[0]), w[0], np.float64)
+    close(N(got[1]), w[1], np.float64)
+
+
+# ------------------------------------------------------------------ a8-a10: tabulate ---------
+def _tab_golden(dtype):
+    g = golden("tabulate_se_a.json")["TestTabulateSeA"]
+    nloc, nnei, M = g["nloc"], g["nnei"], g["last_layer_size"]
+    return (g, np.array(g["table"], dtype).reshape(-1, M * 6), np.array(g["info"], dtype),
+            np.array(g["em_x"], dtype).reshape(nloc * nnei, 1), np.array(g["em"], dtype).reshape(nloc, nnei, 4), M)
+
+
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+def test_tabulate_golden(ops, dtype):
+    """source/lib/tests/test_tabulate_se_a.cc + source/tests/pt/test_tabulate_fusion_se_a.py literals."""
+    g, table, info, em_x, em, M = _tab_golden(dtype)
+    nloc, nnei = em.shape[:2]
+    out = ops.tabulate_fusion_se_a(T(table), torch.as_tensor(info), T(em_x), T(em), M)
+    close(N(out), g["expected_xyz_scatter"], dtype, fac=10)
+    dy = np.ones((nloc, 4, M), dtype)
+    gx, gem, _ = ops.tabulate_fusion_se_a_grad(T(table), torch.as_tensor(info), T(em_x), T(em), T(dy), M)
+    close(N(gx), g["expected_dy_dem_x"], dtype, fac=10)
+    close(N(gem), g["expected_dy_dem"], dtype, fac=10)
+    two = np.array(g["two_embed"], dtype).reshape(nloc * nnei, M)
+    out2 = ops.tabulate_fusion_se_a(T(table), torch.as_tensor(info), T(em_x), T(em), M, two_embed=T(two))
+    close(N(out2), g["expected_xyz_scatter_with_two_embed"], dtype, fac=10)
+    gx2, gem2, gtwo = ops.tabulate_fusion_se_a_grad(T(table), torch.as_tensor(info), T(em_x), T(em), T(dy), M,
+                                                    two_embed=T(two))
+    close(N(gx2), g["expected_dy_dem_x_with_two_embed"], dtype, fac=10)
+    close(N(gem2), g["expected_dy_dem_with_two_embed"], dtype, fac=10)
+    assert gtwo.shape == two.shape
+
+
+def _random_tab_case(rng, dtype, nloc, nnei, M, nreal_max=None, unsorted=False):
+    """Env-mat-like inputs: descending em_x, trailing padding (em_x = pad value, angular part 0),
+    values reaching below `lower` and above `max` (extrapolation branches)."""
+    info = np.array([-0.4, 2.0, 6.0, 0.05, 0.5, -1.0], dtype)
+    nspline = int((info[1] - info[0]) / info[3]) + int((info[2] - info[1]) / info[4]) + 1
+    table = random_table(nspline, M, rng, dtype)
+    em = rng.normal(size=(nloc, nnei, 4)).astype(dtype)
+    em_x = np.sort(rng.uniform(-0.8, 7.5, size=(nloc, nnei)), axis=1)[:, ::-1].astype(dtype)
+    pad = dtype(-0.37)
+    for i in range(nloc):
+        nreal = rng.integers(0, (nreal_max or nnei) + 1)
+        em_x[i, nreal:] = pad
+        em[i, nreal:, 0] = pad
+        em[i, nreal:, 1:] = 0
+    if unsorted:
+        for i in range(nloc):
+            p = rng.permutation(nnei)
+            em_x[i] = em_x[i, p]
+            em[i] = em[i, p]
+    em[:, :, 0] = em_x
+    return table, info, np.ascontiguousarray(em_x.reshape(-1, 1)), np.ascontiguousarray(em)
+
+
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+@pytest.mark.parametrize("nnei,M", [(46, 100), (92, 100), (7, 8), (33, 32), (64, 40), (20, 160), (138, 128)])
+@pytest.mark.parametrize("is_sorted", [True, False])
+def test_tabulate_vs_oracle(ops, port, dtype, nnei, M, is_sorted):
+    rng = np.random.default_rng(nnei * 1000 + M)
+    nloc = 37
+    table, info, em_x, em = _random_tab_case(rng, dtype, nloc, nnei, M, unsorted=not is_sorted)
+    want = port.tabulate_fusion_se_a(table, info, em_x, em, M, is_sorted=is_sorted)
+    got = ops.tabulate_fusion_se_a(T(table), torch.as_tensor(info), T(em_x), T(em), M, is_sorted=is_sorted)
+    close(N(got), want, dtype, fac=4)
+    dy = rng.normal(size=(nloc, 4, M)).astype(dtype)
+    wx, wem, _ = port.tabulate_fusion_se_a_grad(table, info, em_x, em, dy, M, is_sorted=is_sorted)
+    gx, gem, _ = ops.tabulate_fusion_se_a_grad(T(table), torch.as_tensor(info), T(em_x), T(em), T(dy), M,
+                                               is_sorted=is_sorted)
+    close(N(gx), wx, dtype, fac=4)
+    close(N(gem), wem, dtype, fac=4)
+    dzx = rng.normal(size=em_x.shape).astype(dtype)
+    dzem = rng.normal(size=em.shape).astype(dtype)
+    wgg = port.tabulate_fusion_se_a_grad_grad(table, info, em_x, em, dzx, dzem, M, is_sorted=is_sorted)
+    ggg = ops.tabulate_fusion_se_a_grad_grad(T(table), torch.as_tensor(info), T(em_x), T(em), T(dzx), T(dzem), M,
+                                             is_sorted=is_sorted)
+    close(N(ggg), wgg, dtype, fac=4)
+
+
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+@pytest.mark.parametrize("is_sorted", [True, False])
+def test_tabulate_atten_vs_oracle(ops, port, dtype, is_sorted):
+    rng = np.random.default_rng(11)
+    nloc, nnei, M = 19, 120, 100
+    table, info, em_x, em = _random_tab_case(rng, dtype, nloc, nnei, M, unsorted=not is_sorted)
+    two = rng.normal(size=(nloc * nnei, M)).astype(dtype)
+    want = port.tabulate_fusion_se_a(table, info, em_x, em, M, two_embed=two, is_sorted=is_sorted)
+    got = ops.tabulate_fusion_se_a(T(table), torch.as_tensor(info), T(em_x), T(em), M, two_embed=T(two),
+                                   is_sorted=is_sorted)
+    close(N(got), want, dtype, fac=4)
+    dy = rng.normal(size=(nloc, 4, M)).astype(dtype)
+    wx, wem, wtwo = port.tabulate_fusion_se_a_grad(table, info, em_x, em, dy, M, two_embed=two, is_sorted=is_sorted)
+    gx, gem, gtwo = ops.tabulate_fusion_se_a_grad(T(table), torch.as_tensor(info), T(em_x), T(em), T(dy), M,
+                                                  two_embed=T(two), is_sorted=is_sorted)
+    close(N(gx), wx, dtype, fac=4)
+    close(N(gem), wem, dtype, fac=4)
+    close(N(gtwo), wtwo.reshape(nloc * nnei, M), dtype, fac=4)
+    dzx = rng.normal(size=em_x.shape).astype(dtype)
+    dzem = rng.normal(size=em.shape).astype(dtype)
+    dztwo = rng.normal(size=two.shape).astype(dtype)
+    wgg = port.tabulate_fusion_se_a_grad_grad(table, info, em_x, em, dzx, dzem, M, two_embed=two, dz_dtwo=dztwo,
+                                              is_sorted=is_sorted)
+    ggg = ops.tabulate_fusion_se_a_grad_grad(T(table), torch.as_tensor(info), T(em_x), T(em), T(dzx), T(dzem), M,
+                                             two_embed=T(two), dz_dy_dtwo=T(dztwo), is_sorted=is_sorted)
+    close(N(ggg), wgg, dtype, fac=4)
+
+
+def test_tabulate_empty_neighbors(ops):
+    """test_tabulate_se_a.cc:761-786: nnei == 0 gives a zero descriptor and empty gradients."""
+    table = torch.zeros(4, 48, dtype=torch.float64, device=DEV)
+    info = torch.tensor([0, 0.2, 0.4, 0.01, 0.1, -1], dtype=torch.float64)
+    em_x = torch.zeros(0, 1, dtype=torch.float64, device=DEV)
+    em = torch.zeros(3, 0, 4, dtype=torch.float64, device=DEV)
+    out = ops.tabulate_fusion_se_a(table, info, em_x, em, 8)
+    assert out.shape == (3, 4, 8) and float(out.abs().sum()) == 0.0
+    gx, gem, _ = ops.tabulate_fusion_se_a_grad(table, info, em_x, em, torch.ones(3, 4, 8, dtype=torch.float64,
+                                                                               device=DEV), 8)
+    assert gx.numel() == 0 and gem.numel() == 0
+
+
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+def test_tabulate_sections(ops, port, dtype):
+    """Strided per-type sections over the full env-mat == per-section calls on copies, summed."""
+    rng = np.random.default_rng(21)
+    nloc, M = 23, 100
+    sec = [0, 46, 138]
+    ems, tabs, infos = [], [], []
+    want = 0
+    dy = rng.normal(size=(nloc, 4, M)).astype(dtype)
+    wg = []
+    for t in range(2):
+        table, info, em_x, em = _random_tab_case(rng, dtype, nloc, sec[t + 1] - sec[t], M)
+        ems.append(em)
+        tabs.append(table)
+        infos.append(info)
+        want = want + port.tabulate_fusion_se_a(table, info, em_x, em, M)
+        gx, gem, _ = port.tabulate_fusion_se_a_grad(table, info, em_x, em, dy, M)
+        gem = gem.copy()
+        gem[:, :, 0] += gx
+        wg.append(gem)
+    em_full = np.concatenate(ems, axis=1).reshape(nloc, -1)
+    got = ops.tabulate_sections_fwd([T(t) for t in tabs], [torch.as_tensor(i) for i in infos], T(em_full), sec, M)
+    close(N(got), want, dtype, fac=4)
+    gg = ops.tabulate_sections_grad([T(t) for t in tabs], [torch.as_tensor(i) for i in infos], T(em_full), T(dy), sec,
+                                    M)
+    close(N(gg), np.concatenate(wg, axis=1), dtype, fac=4)
+
+
+def test_torch_ops_autograd(ops, port):
+    """torch.ops.deepmd.tabulate_fusion_se_a/_se_atten: forward, backward, double backward
+    (source/tests/pt/test_tabulate_fusion_se_a.py:1424-1511)."""
+    dtype = np.float64
+    g, table, info, em_x, em, M = _tab_golden(dtype)
+    nloc, nnei = em.shape[:2]
+    tt, ti = T(table), torch.as_tensor(info)
+    ex = T(em_x).requires_grad_(True)
+    ee = T(em).requires_grad_(True)
+    out = torch.ops.deepmd.tabulate_fusion_se_a(tt, ti, ex, ee, M)[0]
+    close(N(out), g["expected_xyz_scatter"], dtype, fac=10)
+    gx, gem = torch.autograd.grad(out, [ex, ee], torch.ones_like(out), create_graph=True)
+    close(N(gx), g["expected_dy_dem_x"], dtype, fac=10)
+    close(N(gem), g["expected_dy_dem"], dtype, fac=10)
+    # double backward == oracle grad_grad contracted with the same cotangents
+    rng = np.random.default_rng(0)
+    cx = rng.normal(size=em_x.shape)
+    cem = rng.normal(size=em.shape)
+    dy0 = torch.ones_like(out).requires_grad_(True)
+    out = torch.ops.deepmd.tabulate_fusion_se_a(tt, ti, ex, ee, M)[0]
+    gx, gem = torch.autograd.grad(out, [ex, ee], dy0, create_graph=True)
+    (gdy,) = torch.autograd.grad([gx, gem], [dy0], [T(cx), T(cem)])
+    want = port.tabulate_fusion_se_a_grad_grad(table, info, em_x, em, cx, cem, M)
+    close(N(gdy), want, dtype, fac=10)
+    # se_atten schema
+    two = np.array(g["two_embed"], dtype).reshape(nloc * nnei, M)
+    tw = T(two).requires_grad_(True)
+    out2 = torch.ops.deepmd.tabulate_fusion_se_atten(tt, ti, ex, ee, tw, M, True)[0]
+    close(N(out2), g["expected_xyz_scatter_with_two_embed"], dtype, fac=10)
+    g2 = torch.autograd.grad(out2, [ex, ee, tw], torch.ones_like(out2))
+    close(N(g2[0]), g["expected_dy_dem_x_with_two_embed"], dtype, fac=10)
+    close(N(g2[1]), g["expected_dy_dem_with_two_embed"], dtype, fac=10)
+    # device validation (source/tests/pt/test_tabulate_device_validation.py)
+    with pytest.raises(RuntimeError):
+        torch.ops.deepmd.tabulate_fusion_se_a(tt, ti.to(DEV), ex, ee, M)
+    with pytest.raises(RuntimeError):
+        torch.ops.deepmd.tabulate_fusion_se_a(tt, ti, ex.cpu(), ee, M)
+
+
+# ------------------------------------------------------------------ a11/a12: force, virial ----
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+def test_prod_force_virial_golden(ops, port, dtype):
+    gf = golden("prod_force_a.json")["TestProdForceA"]
+    gv = golden("prod_virial_a.json")["TestProdVirialA"]
+    s = six_atom_system(port, rc=gf["rc"], dtype=dtype)
+    sec = gf["sec_a"]
+    nnei = sec[-1]
+    nloc, nall = s["nloc"], len(s["atype"])
+    off, neigh = ocpu.dense_to_csr(s["rows"], s["numneigh"])
+    nl, _ = port.format_nlist(s["coord"], s["atype"], off, neigh, gf["rc"], sec)
+    em, dv, rij = port.env_mat_a(s["coord"], s["atype"], nl, gf["rc_smth"], gf["rc"], sec)
+    nd = (np.arange(nloc * nnei * 4, dtype=dtype) * dtype(0.1)).reshape(nloc, nnei * 4)
+    # test_prod_force_a.cc:95-118: 2 identical frames
+    nf = gf["nframes"]
+    f = ops.prod_force_a(T(np.tile(nd, (nf, 1))), T(np.tile(dv, (nf, 1))), T(np.tile(nl, (nf, 1))), nloc, nall, nnei,
+                         nframes=nf)
+    np.testing.assert_allclose(N(f).reshape(-1), np.array(gf["expected_force"]), atol=1e-5 * 50)
+    close(N(f)[0], port.prod_force_a(nd, dv, nl, nall), dtype, fac=4)
+    v, av = ops.prod_virial_a(T(nd), T(dv), T(rij), T(nl), nloc, nall, nnei)
+    np.testing.assert_allclose(N(v), np.array(gv["expected_virial"]), rtol=1e-5, atol=1e-3)
+    np.testing.assert_allclose(N(av), np.array(gv["expected_atom_virial"]), rtol=1e-5, atol=1e-3)
+    wv, wav = port.prod_virial_a(nd, dv, rij, nl, nall)
+    close(N(v), wv, dtype, fac=4)
+    close(N(av), wav, dtype, fac=4)
+
+
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+def test_prod_force_virial_water(ops, port, dtype):
+    coord, atype, box = water_like_box(ncopy=2, seed=8, jitter=0.05, dtype=dtype)
+    s = extended_system(port, coord, atype, box, 6.0, dtype=dtype)
+    sec = [0, 46, 138]
+    nnei = 138
+    nloc, nall = s["nloc"], len(s["atype"])
+    avg, std = avg_std(2, nnei, dtype)
+    off, neigh = ocpu.dense_to_csr(s["rows"], s["numneigh"])
+    em, dv, rij, nl = port.prod_env_mat_a(s["coord"], s["atype"], off, neigh, avg, std, nloc, 6.0, 0.5, sec)
+    rng = np.random.default_rng(4)
+    nd = rng.normal(size=(nloc, nnei * 4)).astype(dtype)
+    wf = port.prod_force_a(nd, dv, nl, nall)
+    wv, wav = port.prod_virial_a(nd, dv, rij, nl, nall)
+    f = ops.prod_force_a(T(nd), T(dv), T(nl), nloc, nall, nnei)
+    close(N(f), wf, dtype, fac=4)
+    v, av = ops.prod_virial_a(T(nd), T(dv), T(rij), T(nl), nloc, nall, nnei)
+    close(N(v), wv, dtype, fac=20)
+    close(N(av), wav, dtype, fac=4)
+    f2, v2, av2 = ops.prod_force_virial_a(T(nd), T(dv), T(rij), T(nl), nloc, nall, nnei, atom_virial=True)
+    close(N(f2), wf, dtype, fac=4)
+    close(N(v2), wv, dtype, fac=20)
+    close(N(av2), wav, dtype, fac=4)
+    f3, v3, av3 = ops.prod_force_virial_a(T(nd), T(dv), T(rij), T(nl), nloc, nall, nnei)
+    assert av3 is None
+    close(N(v3), wv, dtype, fac=20)
+    # size-independent property: translation invariance => net force vanishes after folding ghosts
+    fold = np.zeros((nloc, 3))
+    np.add.at(fold, s["mapping"], N(f).reshape(-1, 3).astype(np.float64))
+    assert np.abs(fold.sum(0)).max() <= 1e3 * TOL[dtype] * np.abs(wf).max()
+    # torch op schemas (TF-style)
+    nat = torch.tensor([nloc, nall, 0, 0], dtype=torch.int32)
+    fo = torch.ops.deepmd.prod_force_se_a(T(nd).reshape(1, -1), T(dv).reshape(1, -1), T(nl).reshape(1, -1), nat, nnei, 0)
+    close(N(fo), wf, dtype, fac=4)
+    vo, avo = torch.ops.deepmd.prod_virial_se_a(T(nd).reshape(1, -1), T(dv).reshape(1, -1), T(rij).reshape(1, -1),
+                                                T(nl).reshape(1, -1), nat, nnei, 0)
+    close(N(vo), wv, dtype, fac=20)
+    close(N(avo), wav, dtype, fac=4)
+
+
+# ------------------------------------------------------------------ a2-a4: list front end ----
+def _ghost_key(c, t, m, nloc):
+    c = np.asarray(c, np.float64)
+    rows = [(int(m[i]), int(t[i])) + tuple(np.round(c[i], 6)) for i in range(nloc, len(t))]
+    return sorted(rows)
+
+
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+def test_normalize_copy_build(ops, port, dtype):
+    coord, atype, box = water_like_box(ncopy=2, seed=9, jitter=0.3, dtype=dtype)
+    coord = coord + dtype(7.3)  # push atoms outside the cell
+    w = port.normalize_coord(coord, box)
+    gc = ops.normalize_coord(T(coord).clone(), box)
+    assert np.array_equal(N(gc), w)  # same operation order, no contraction: bitwise
+    for rc in (6.0, 4.0, 10.5):
+        wc, wt, wm = port.copy_coord(w, atype, box, rc)
+        c, t, m = ops.copy_coord(T(w), T(atype), box, rc)
+        nloc = len(atype)
+        assert len(wt) == t.numel()
+        assert np.array_equal(N(c)[:nloc], w) and np.array_equal(N(m)[:nloc], np.arange(nloc))
+        assert _ghost_key(N(c), N(t), N(m), nloc) == _ghost_key(wc, wt, wm, nloc)
+    # raw list on the oracle's extended system: rows identical element by element
+    ext_c, ext_t, ext_m = port.copy_coord(w, atype, box, 6.0)
+    nloc = len(atype)
+    wn, wr = port.build_nlist(ext_c, nloc, 6.0)
+    nn, rows = ops.build_nlist(T(ext_c), nloc, 6.0)
+    assert np.array_equal(N(nn), wn)
+    rows = N(rows)
+    for i in range(nloc):
+        assert np.array_equal(rows[i, : wn[i]], wr[i, : wn[i]])
+    # virtual atoms + capacity error path
+    ty = ext_t.copy()
+    ty[::5] = -1
+    wn2, wr2 = port.build_nlist(ext_c, nloc, 6.0, atype=ty)
+    nn2, rows2 = ops.build_nlist(T(ext_c), nloc, 6.0, atype=T(ty))
+    assert np.array_equal(N(nn2), wn2)
+    with pytest.raises(MemoryError):
+        ops.build_nlist(T(ext_c), nloc, 6.0, mem_size=8)
+
+
+def test_copy_coord_golden(ops):
+    for cls in ("TestCopyCoord", "TestCopyCoordMoreCell"):
+        g = golden("coord.json")[cls]
+        posi = np.array(g["posi"]).reshape(-1, 3)
+        atype = np.array(g["atype"], np.int32)
+        box = np.array(g["boxt"]).reshape(3, 3)
+        c, t, m = ops.copy_coord(T(posi), T(atype), box, g["rc"])
+        want_c = np.array(g["_expected_posi_cpy"]).reshape(-1, 3)
+        want_t = np.array(g["_expected_atype_cpy"])
+        want_m = np.array(g["_expected_mapping"])
+        nloc = len(atype)
+        assert t.numel() == len(want_t)
+        assert _ghost_key(N(c), N(t), N(m), nloc) == _ghost_key(want_c, want_t, want_m, nloc)
+        with pytest.raises(MemoryError):
+            ops.copy_coord(T(posi), T(atype), box, g["rc"], mem_nall=40)
+
+
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+def test_op_prod_env_mat_a_modes(ops, port, dtype):
+    """torch.ops.deepmd.prod_env_mat_a with the mesh encodings: PBC self-built list
+    (len 6) and pointer-free inline list (len > 16), against the oracle pipeline."""
+    coord, atype, box = water_like_box(ncopy=2, seed=12, jitter=0.1, dtype=dtype)
+    nloc = len(atype)
+    sec = [0, 46, 138]
+    avg, std = avg_std(2, 138, dtype)
+    cn = port.normalize_coord(coord, box)
+    ext_c, ext_t, mapping = port.copy_coord(cn, atype, box, 6.0)
+    nn, rows = port.build_nlist(ext_c, nloc, 6.0)
+    off, neigh = ocpu.dense_to_csr(rows, nn)
+    w = port.prod_env_mat_a(ext_c, ext_t, off, neigh, avg, std, nloc, 6.0, 0.5, sec)
+    nat = torch.tensor([nloc, nloc, (atype == 0).sum(), (atype == 1).sum()], dtype=torch.int32)
+    mesh6 = torch.zeros(6, dtype=torch.int32)
+    em, dv, rij, nl = torch.ops.deepmd.prod_env_mat_a(T(coord).reshape(1, -1), T(atype).reshape(1, -1), nat,
+                                                      T(box).reshape(1, 9), mesh6, T(avg), T(std), 0.0, 6.0, 0.5,
+                                                      [46, 92], [0, 0])
+    # ghost numbering differs from the oracle's copy_coord; compare per slot after mapping to owners
+    want_nl = np.where(w[3] >= 0, mapping[np.maximum(w[3], 0)], -1)
+    got_nl = N(nl).reshape(nloc, -1)
+    # equal distances between different images of one owner can swap slots: compare em instead of
+    # requiring identical owner ids slot by slot, then check the owner multiset per type section
+    close(N(em), w[0], dtype)
+    for i in range(nloc):
+        for a, b in ((0, 46), (46, 138)):
+            assert sorted(got_nl[i, a:b].tolist()) == sorted(want_nl[i, a:b].tolist())
+    # inline list: extended system and raw rows handed over explicitly
+    nall = len(ext_t)
+    nat2 = torch.tensor([nloc, nall, 0, 0], dtype=torch.int32)
+    head = np.zeros(16, np.int32)
+    head[1] = nloc
+    mesh = np.concatenate([head, np.arange(nloc, dtype=np.int32), nn.astype(np.int32), neigh[: off[-1]]])
+    em2, dv2, rij2, nl2 = torch.ops.deepmd.prod_env_mat_a(T(ext_c).reshape(1, -1), T(ext_t).reshape(1, -1), nat2,
+                                                          T(box).reshape(1, 9), T(mesh), T(avg), T(std), 0.0, 6.0,
+                                                          0.5, [46, 92], [0, 0])
+    assert np.array_equal(N(nl2).reshape(nloc, -1), w[3])
+    close(N(em2), w[0], dtype)
+    close(N(dv2), w[1], dtype)
+    close(N(rij2), w[2], dtype)
