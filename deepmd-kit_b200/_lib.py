@@ -57,6 +57,11 @@ class _Lib:
         self.cdll = C.CDLL(LIB_PATH)
         self.cdll.dpb200_last_error.restype = C.c_char_p
         self.cdll.dpb200_abi_version.restype = C.c_int
+        self.cdll.dpb200_launch_count.restype = C.c_longlong
+        for s_ in ("f32", "f64"):
+            f = getattr(self.cdll, "dpb200_fma_peak_" + s_)
+            f.restype = C.c_int
+            f.argtypes = [C.POINTER(C.c_double), C.c_void_p]
         for fn, res in (("dpb200_prod_env_mat_a_workspace_bytes", "iiiii"), ("dpb200_copy_coord_workspace_bytes", "i"),
                         ("dpb200_build_nlist_workspace_bytes", "i")):
             f = getattr(self.cdll, fn)
@@ -71,12 +76,21 @@ class _Lib:
                 f.argtypes = [_T[c] for c in sig.replace(" ", "")]
 
     def exported(self):
-        names = ["dpb200_last_error", "dpb200_abi_version", "dpb200_prod_env_mat_a_workspace_bytes",
+        names = ["dpb200_last_error", "dpb200_abi_version", "dpb200_launch_count", "dpb200_fma_peak_f32",
+                 "dpb200_fma_peak_f64", "dpb200_prod_env_mat_a_workspace_bytes",
                  "dpb200_copy_coord_workspace_bytes", "dpb200_build_nlist_workspace_bytes", "dpb200_use_nlist_map"]
         for pat in _SIGS:
             for s in ("f32", "f64"):
                 names.append("dpb200_" + pat.format(s=s))
         return names
+
+    def launch_count(self) -> int:
+        return int(self.cdll.dpb200_launch_count())
+
+    def fma_peak(self, suffix: str, stream) -> float:
+        v = C.c_double(0.0)
+        self.call("fma_peak_" + suffix, C.byref(v), stream)
+        return v.value
 
     def last_error(self) -> str:
         return (self.cdll.dpb200_last_error() or b"").decode()

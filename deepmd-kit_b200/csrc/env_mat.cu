@@ -471,6 +471,7 @@ int launch_env(FP* em, FP* em_deriv, FP* rij, int* nlist, const FP* coord, const
   int grid = (int)(want < cap ? want : cap);
   kern<<<grid, wpb * 32, smem, stream>>>(p);
   DPB_CUDA(cudaGetLastError());
+  note_launches(kEnv ? 3 : 2);
   return DPB200_OK;
 }
 

@@ -192,6 +192,7 @@ int launch_fv(FP* force, FP* virial, FP* atom_virial, const FP* net_deriv, const
   const int grid = (int)(want < cap ? want : cap);
   kern<<<grid, 128, 0, st>>>(p);
   DPB_CUDA(cudaGetLastError());
+  note_launches(1);
   return DPB200_OK;
 }
 
@@ -245,6 +246,7 @@ int dpb200_use_nlist_map(int* nlist, const int* nlist_map, int nloc, int nnei, d
   if (grid > cap) grid = cap;
   k_nlist_map<<<grid, 256, 0, (cudaStream_t)stream>>>(nlist, nlist_map, n);
   DPB_CUDA(cudaGetLastError());
+  note_launches(1);
   return DPB200_OK;
 }
 

@@ -90,6 +90,7 @@ int exclusive_scan(int* out, const int* in, long long n, int* tmp, cudaStream_t 
   if (n <= 0) return DPB200_OK;
   const long long nt = (n + kScanTile - 1) / kScanTile;
   k_scan_tiles<<<(unsigned)nt, 256, 0, st>>>(out, in, tmp, n);
+  note_launches(nt > 1 ? 2 : 1);
   if (nt > 1) {
     int* next = tmp + nt;
     int rc = exclusive_scan(tmp, tmp, nt, next, st);
@@ -517,6 +518,7 @@ int do_normalize(FP* coord, int natom, const FP* boxt, cudaStream_t st) {
   make_rec(bx.rec, boxt);
   k_normalize<FP><<<ceil_div(natom, 256), 256, 0, st>>>(coord, natom, bx);
   DPB_CUDA(cudaGetLastError());
+  note_launches(1);
   return DPB200_OK;
 }
 
@@ -540,6 +542,7 @@ int do_copy_coord(FP* out_c, int* out_t, int* mapping, int* nall_out, const FP* 
   int* off = cnt + align_up((size_t)nloc + 1, 64);
   int* tmp = off + align_up((size_t)nloc + 1, 64);
   k_ghost_count<FP><<<ceil_div((long long)nloc + 1, 256), 256, 0, st>>>(cnt, in_c, nloc, ci);
+  note_launches(1);
   int rc = exclusive_scan(off, cnt, (long long)nloc + 1, tmp, st);
   if (rc) return rc;
   int total = 0;
@@ -551,6 +554,7 @@ int do_copy_coord(FP* out_c, int* out_t, int* mapping, int* nall_out, const FP* 
   if (nall > mem_nall) return 1;
   k_ghost_fill<FP><<<ceil_div(nloc, 128), 128, 0, st>>>(out_c, out_t, mapping, off, in_c, in_t, nloc, ci);
   DPB_CUDA(cudaGetLastError());
+  note_launches(1);
   return DPB200_OK;
 }
 
@@ -614,6 +618,7 @@ int do_build_nlist(int* numneigh, int* rows, int* max_list_size, const FP* coord
   long long capb = (long long)sm_count() * occ;
   kern<<<(int)(want < capb ? want : capb), 128, smem, st>>>(p);
   DPB_CUDA(cudaGetLastError());
+  note_launches(6);  // bbox_init, bbox, grid_setup, cell_count, cell_fill, build_rows (+ scans above)
   int mx = 0;
   DPB_CUDA(cudaMemcpyAsync(&mx, maxl, sizeof(int), cudaMemcpyDeviceToHost, st));
   DPB_CUDA(cudaStreamSynchronize(st));

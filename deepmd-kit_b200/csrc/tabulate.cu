@@ -558,6 +558,7 @@ int launch_fwd(FP* out, const FP* table, const FP* info, const FP* em_x, long lo
   cudaError_t e = cudaGetLastError();
   cudaFreeAsync(scratch, st);
   DPB_CUDA(e);
+  note_launches(2);
   return DPB200_OK;
 }
 
@@ -604,6 +605,7 @@ int launch_grad(FP* dy_dem_x, FP* dy_dem, FP* dy_dtwo, const FP* table, const FP
   cudaError_t e = cudaGetLastError();
   cudaFreeAsync(scratch, st);
   DPB_CUDA(e);
+  note_launches(2);
   return DPB200_OK;
 }
 

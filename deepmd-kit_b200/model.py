@@ -1,0 +1,274 @@
+"""Compressed se_e2_a energy / force / virial evaluation — the per-step hot path, driven from
+PyTorch host code through the dpb200 operators.
+
+Pipeline per step (the decomposed graph of deepmd/tf/descriptor/se_a.py:665-681,753-783 with the
+descriptor algebra of deepmd/pt/model/descriptor/se_a.py:838-850):
+
+    [every `nlist_every` steps] normalize_coord -> copy_coord (ghost images) -> build_nlist(rcut+skin)
+    prod_env_mat_a (format with the true rcut + env-mat)      -> em, em_deriv, rij, nlist
+    tabulate_fusion_se_a over the type sections               -> xyz_scatter [nloc,4,M]
+    /nnei, GR^T GR[:, :axis], fitting net, dE/d(xyz_scatter)  (torch GEMMs; SURVEY 8f-1 "next")
+    tabulate_fusion_se_a_grad over the type sections          -> net_deriv = dE/d(em)
+    use_nlist_map (ghost -> owner)                            -> prod_force_a + prod_virial_a
+
+``DeepPotB200.eval`` is the public call (argument meaning of deepmd.infer.DeepPot.eval): host
+coordinates in, host energy / force / virial out.
+"""
+from __future__ import annotations
+
+import math
+from dataclasses import dataclass, field
+from typing import List, Optional, Sequence
+
+import numpy as np
+import torch
+
+from . import ops
+from .compress import EmbeddingNet, compress_se_a
+
+# davg / dstd of the reference's se_e2_a water model (source/tests/infer/deeppot_sea.yaml), per
+# centre type: (davg of component 0, dstd of component 0, dstd of components 1..3)
+WATER_STATS = [(0.05033, 0.13984, 0.08580), (0.04810, 0.12388, 0.07672)]
+
+
+@dataclass
+class SeAConfig:
+    """examples/water/se_e2_a/input.json by default."""
+    ntypes: int = 2
+    sel: Sequence[int] = (46, 92)
+    rcut: float = 6.0
+    rcut_smth: float = 0.5
+    neuron: Sequence[int] = (25, 50, 100)
+    axis_neuron: int = 16
+    fitting_neuron: Sequence[int] = (240, 240, 240)
+    fitting_resnet_dt: bool = True
+    stats: Sequence[Sequence[float]] = field(default_factory=lambda: list(WATER_STATS))
+    seed: int = 1
+    stride0: float = 0.01
+    stride1: float = 0.1
+    extrapolate: float = 5.0
+    min_nbor_dist: float = 0.9
+
+    @property
+    def nnei(self) -> int:
+        return int(sum(self.sel))
+
+    @property
+    def sec(self) -> List[int]:
+        s = [0]
+        for v in self.sel:
+            s.append(s[-1] + int(v))
+        return s
+
+
+COPPER_CONFIG = dict(ntypes=1, sel=(512,), rcut=8.0, rcut_smth=2.0, stats=[(0.06, 0.12, 0.07)], min_nbor_dist=2.0)
+
+
+class FittingNet:
+    """Energy fitting net of one atom type: D -> neuron... -> 1, tanh, `resnet_dt` skip connections
+    on equal-width layers (deepmd/pt/model/network/mlp.py), default normal init, bias_atom_e = 0."""
+
+    def __init__(self, dim_in: int, neuron: Sequence[int], resnet_dt: bool, seed: int, dtype, device):
+        g = torch.Generator().manual_seed(seed)
+        self.layers = []
+        n_in = dim_in
+        for n_out in neuron:
+            w = torch.empty(n_in, n_out, dtype=torch.float64).normal_(0.0, 1.0 / math.sqrt(n_in + n_out), generator=g)
+            b = torch.empty(n_out, dtype=torch.float64).normal_(0.0, 1.0, generator=g)
+            idt = torch.empty(n_out, dtype=torch.float64).normal_(0.1, 0.001, generator=g) if resnet_dt else None
+            self.layers.append((w.to(device, dtype), b.to(device, dtype), None if idt is None else idt.to(device, dtype)))
+            n_in = n_out
+        w = torch.empty(n_in, 1, dtype=torch.float64).normal_(0.0, 1.0 / math.sqrt(n_in + 1), generator=g)
+        b = torch.empty(1, dtype=torch.float64).normal_(0.0, 1.0, generator=g)
+        self.head = (w.to(device, dtype), b.to(device, dtype))
+
+    def to(self, device, dtype):
+        self.layers = [(w.to(device, dtype), b.to(device, dtype), None if i is None else i.to(device, dtype))
+                       for w, b, i in self.layers]
+        self.head = (self.head[0].to(device, dtype), self.head[1].to(device, dtype))
+        return self
+
+    def __call__(self, x: torch.Tensor) -> torch.Tensor:
+        for w, b, idt in self.layers:
+            y = torch.tanh(torch.addmm(b, x, w))
+            if idt is not None:
+                y = y * idt
+            if w.shape[0] == w.shape[1]:
+                y = y + x
+            elif w.shape[1] == 2 * w.shape[0]:
+                y = y + torch.cat([x, x], 1)
+            x = y
+        return torch.addmm(self.head[1], x, self.head[0]).reshape(-1)
+
+
+class SeAModel:
+    """Random-init compressed se_e2_a model (weights of the named architecture, tabulated with the
+    restated `dp compress`)."""
+
+    def __init__(self, cfg: SeAConfig, dtype=torch.float64, device="cuda"):
+        self.cfg = cfg
+        self.dtype = dtype
+        self.device = torch.device(device)
+        nnei = cfg.nnei
+        davg = np.zeros((cfg.ntypes, nnei, 4))
+        dstd = np.ones((cfg.ntypes, nnei, 4))
+        for t, (a0, s0, s1) in enumerate(cfg.stats):
+            davg[t, :, 0] = a0
+            dstd[t, :, 0] = s0
+            dstd[t, :, 1:] = s1
+        self.davg_np, self.dstd_np = davg, dstd
+        self.davg = torch.as_tensor(davg.reshape(cfg.ntypes, -1), dtype=dtype, device=self.device)
+        self.dstd = torch.as_tensor(dstd.reshape(cfg.ntypes, -1), dtype=dtype, device=self.device)
+        self.embed = [EmbeddingNet(cfg.neuron, cfg.seed + 17 * t) for t in range(cfg.ntypes)]
+        tables, infos = compress_se_a(self.embed, davg[:, 0, :], dstd[:, 0, :], cfg.sel, cfg.min_nbor_dist,
+                                      cfg.rcut_smth, cfg.rcut, cfg.stride0, cfg.stride1, cfg.extrapolate)
+        self.tables64 = tables
+        self.tables = [t.to(self.device, dtype).contiguous() for t in tables]
+        self.infos = [i.to(dtype) for i in infos]  # host
+        self.M = int(cfg.neuron[-1])
+        dim_d = self.M * cfg.axis_neuron
+        self.fit = [FittingNet(dim_d, cfg.fitting_neuron, cfg.fitting_resnet_dt, cfg.seed + 101 * t, dtype, self.device)
+                    for t in range(cfg.ntypes)]
+        self.fit_chunk = 1 << 17
+
+    # -- descriptor algebra + fitting net: torch GEMMs (library code; not one of the named kernels)
+    def energy_and_dy(self, xyz: torch.Tensor, type_perm: torch.Tensor, type_ranges):
+        """xyz: [nloc,4,M] raw tabulate output. Returns (E_total, atom_energy[nloc], dE/d(xyz))."""
+        cfg = self.cfg
+        nloc = xyz.shape[0]
+        dy = torch.empty_like(xyz)
+        e_atom = torch.empty(nloc, dtype=self.dtype, device=xyz.device)
+        inv = 1.0 / cfg.nnei
+        for t, (a, b) in enumerate(type_ranges):
+            for c0 in range(a, b, self.fit_chunk):
+                c1 = min(b, c0 + self.fit_chunk)
+                idx = type_perm[c0:c1]
+                with torch.enable_grad():
+                    x = xyz.index_select(0, idx).requires_grad_(True)
+                    xs = x * inv
+                    d = torch.matmul(xs.permute(0, 2, 1), xs[:, :, :cfg.axis_neuron]).reshape(c1 - c0, -1)
+                    e = self.fit[t](d)
+                    (g,) = torch.autograd.grad(e.sum(), x)
+                dy.index_copy_(0, idx, g)
+                e_atom.index_copy_(0, idx, e.detach())
+        return e_atom.sum(), e_atom, dy
+
+    def evaluate(self, ext_coord, ext_type, numneigh, rows, mapping, nloc, type_perm, type_ranges, atom_virial=False,
+                 fused=True):
+        """One force evaluation on an extended system. Returns (E, force[nloc,3], virial[9], extras)."""
+        cfg = self.cfg
+        nall = ext_type.numel()
+        em, dv, rij, nlist = ops.prod_env_mat_a(ext_coord.reshape(-1), ext_type, numneigh, rows, self.davg, self.dstd,
+                                                nloc, nall, cfg.rcut, cfg.rcut_smth, cfg.sec)
+        xyz = ops.tabulate_sections_fwd(self.tables, self.infos, em, cfg.sec, self.M)
+        energy, e_atom, dy = self.energy_and_dy(xyz, type_perm, type_ranges)
+        net_deriv = ops.tabulate_sections_grad(self.tables, self.infos, em, dy, cfg.sec, self.M)
+        if mapping is not None:
+            ops.use_nlist_map(nlist, mapping)
+            n_out = nloc
+        else:
+            n_out = nall
+        if fused:
+            force, virial, av = ops.prod_force_virial_a(net_deriv, dv, rij, nlist, nloc, n_out, cfg.nnei,
+                                                        atom_virial=atom_virial)
+        else:
+            force = ops.prod_force_a(net_deriv, dv, nlist, nloc, n_out, cfg.nnei)
+            virial, av = ops.prod_virial_a(net_deriv, dv, rij, nlist, nloc, n_out, cfg.nnei)
+        return energy, force.reshape(-1, 3), virial, dict(atom_energy=e_atom, atom_virial=av, nlist=nlist)
+
+
+@dataclass
+class NeighborState:
+    nloc: int
+    ext_type: torch.Tensor
+    mapping: torch.Tensor
+    shift: torch.Tensor  # ext_coord - coord[mapping] at build time
+    numneigh: torch.Tensor
+    rows: torch.Tensor
+    type_perm: torch.Tensor
+    type_ranges: list
+    ago: int = 0
+
+
+def type_partition(atype: torch.Tensor, ntypes: int):
+    perm = torch.argsort(atype.to(torch.int64), stable=True)
+    counts = torch.bincount(atype.to(torch.int64), minlength=ntypes).tolist()
+    ranges, a = [], 0
+    for c in counts[:ntypes]:
+        ranges.append((a, a + int(c)))
+        a += int(c)
+    return perm, ranges
+
+
+class DeepPotB200:
+    """Inference facade with the calling convention of deepmd.infer.DeepPot.eval: periodic cell,
+    host arrays in and out.  The raw neighbour list is rebuilt every `nlist_every` evaluations with a
+    `skin` (the reference MD set-up examples/water/lmp/in.lammps:7-8: neighbor 2.0 bin, every 10)."""
+
+    def __init__(self, model: SeAModel, skin: float = 2.0, nlist_every: int = 10):
+        self.model = model
+        self.skin = float(skin)
+        self.nlist_every = int(nlist_every)
+        self.state: Optional[NeighborState] = None
+        self._pin_in = None
+        self._pin_out = None
+
+    def reset(self):
+        self.state = None
+
+    def build_neighbors(self, coord: torch.Tensor, atype: torch.Tensor, box) -> NeighborState:
+        m = self.model
+        rc = m.cfg.rcut + self.skin
+        c = coord.reshape(-1, 3).clone()
+        ops.normalize_coord(c, box)
+        ext_c, ext_t, mapping = ops.copy_coord(c, atype, box, rc)
+        nloc = atype.numel()
+        numneigh, rows = ops.build_nlist(ext_c, nloc, rc, ext_t)
+        shift = ext_c - coord.reshape(-1, 3).index_select(0, mapping.long())
+        perm, ranges = type_partition(atype, m.cfg.ntypes)
+        self.state = NeighborState(nloc, ext_t.contiguous(), mapping.contiguous(), shift, numneigh, rows, perm, ranges)
+        return self.state
+
+    def eval_device(self, coord: torch.Tensor, atype: torch.Tensor, box, atom_virial=False, fused=True):
+        """Device tensors in, device tensors out (no host copies)."""
+        st = self.state
+        if st is None or st.ago >= self.nlist_every or st.nloc != atype.numel():
+            st = self.build_neighbors(coord, atype, box)
+        ext_c = coord.reshape(-1, 3).index_select(0, st.mapping.long()) + st.shift
+        st.ago += 1
+        return self.model.evaluate(ext_c, st.ext_type, st.numneigh, st.rows, st.mapping, st.nloc, st.type_perm,
+                                   st.type_ranges, atom_virial=atom_virial, fused=fused)
+
+    def eval(self, coords, cells, atom_types, atomic: bool = False):
+        """coords [nframes, natoms*3], cells [nframes, 9], atom_types [natoms] (host arrays).
+        Returns (energy [nframes,1], force [nframes,natoms,3], virial [nframes,9]) as numpy arrays
+        (+ atom_energy, atom_virial when atomic)."""
+        m = self.model
+        dev = m.device
+        coords = np.asarray(coords).reshape(-1, len(atom_types) * 3)
+        cells = np.asarray(cells, dtype=np.float64).reshape(-1, 9)
+        nf, nat = coords.shape[0], len(atom_types)
+        np_dt = np.float64 if m.dtype == torch.float64 else np.float32
+        if self._pin_in is None or self._pin_in.numel() != nat * 3:
+            self._pin_in = torch.empty(nat * 3, dtype=m.dtype).pin_memory()
+            self._pin_out = torch.empty(nat * 3 + 10, dtype=m.dtype).pin_memory()
+            self._atype = torch.as_tensor(np.asarray(atom_types, np.int32)).to(dev)
+        es, fs, vs, aes, avs = [], [], [], [], []
+        for f in range(nf):
+            self._pin_in.copy_(torch.as_tensor(coords[f].astype(np_dt, copy=False)))
+            c = self._pin_in.to(dev, non_blocking=True)
+            e, force, virial, ex = self.eval_device(c, self._atype, cells[f], atom_virial=atomic)
+            out = torch.cat([force.reshape(-1), virial.reshape(-1), e.reshape(1)])
+            self._pin_out.copy_(out, non_blocking=True)
+            torch.cuda.current_stream(dev).synchronize()
+            o = self._pin_out.numpy()
+            fs.append(o[: nat * 3].reshape(nat, 3).copy())
+            vs.append(o[nat * 3: nat * 3 + 9].copy())
+            es.append(o[nat * 3 + 9: nat * 3 + 10].copy())
+            if atomic:
+                aes.append(ex["atom_energy"].cpu().numpy())
+                avs.append(ex["atom_virial"].cpu().numpy().reshape(nat, 9))
+        res = (np.stack(es), np.stack(fs), np.stack(vs))
+        if atomic:
+            res = res + (np.stack(aes)[..., None], np.stack(avs))
+        return res

@@ -44,6 +44,12 @@ typedef struct CUstream_st* dpb200_stream_t; /* == cudaStream_t */
 
 const char* dpb200_last_error(void);
 int dpb200_abi_version(void);
+/* Number of dpb200 kernels enqueued by this process so far (all threads). */
+long long dpb200_launch_count(void);
+/* Measured peak FMA rate (TFLOP/s, 2 flops per FMA) of the FP64 / FP32 pipe of the current device:
+ * the roofline denominator of the tabulate kernels (MEASURED_PEAKS.json has no such entry). */
+int dpb200_fma_peak_f64(double* tflops /*host out*/, dpb200_stream_t stream);
+int dpb200_fma_peak_f32(double* tflops /*host out*/, dpb200_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------
  * prod_env_mat_a : neighbour formatting + environment matrix + normalisation, one launch.

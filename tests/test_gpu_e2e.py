@@ -1,0 +1,88 @@
+"""End-to-end parity on the GPU: DeepPotB200.eval (public API, host arrays in/out) against the CPU
+pipeline of the reference library on the same boxes, plus size-independent physical properties."""
+import numpy as np
+import pytest
+import torch
+
+import __graft_entry__ as g
+from oracle import cpu as ocpu
+from oracle import pipeline
+
+pytestmark = pytest.mark.gpu
+TOL = {torch.float64: 1e-10, torch.float32: 1e-5}
+
+
+@pytest.fixture(scope="module")
+def pkg():
+    return g.load_package()
+
+
+def _cpu_lib():
+    return ocpu.CpuLib("reference" if ocpu.available("reference") else "port")
+
+
+def rel(a, b):
+    return float(np.abs(np.asarray(a, np.float64) - np.asarray(b, np.float64)).max() / max(np.abs(b).max(), 1e-300))
+
+
+@pytest.mark.parametrize("dtype", [torch.float64, torch.float32])
+@pytest.mark.parametrize("ncopy,jitter", [(1, 0.0), (2, 0.0), (2, 0.01)])
+def test_water_e2e_matches_reference_cpu(pkg, dtype, ncopy, jitter):
+    from deepmd_kit_b200.model import DeepPotB200, SeAConfig, SeAModel
+
+    coord, atype, box = g.water_box(ncopy, jitter)
+    cfg = SeAConfig()
+    dp = DeepPotB200(SeAModel(cfg, dtype, "cuda:0"), skin=2.0)
+    e, f, v = dp.eval(coord.reshape(1, -1), box.reshape(1, 9), atype)
+    lib = _cpu_lib()
+    np_dt = np.float64 if dtype == torch.float64 else np.float32
+    lists = pipeline.build_lists(lib, coord.astype(np_dt), atype, box.astype(np_dt), cfg.rcut + 2.0)
+    we, wf, wv, _ = pipeline.evaluate(lib, SeAModel(cfg, dtype, "cpu"), lists)
+    tol = TOL[dtype]
+    assert abs(e[0, 0] - we) <= tol * abs(we) * (1 if dtype == torch.float64 else 10)
+    assert rel(f[0], wf) <= tol * (1 if dtype == torch.float64 else 10)
+    assert rel(v[0], wv) <= tol * (1 if dtype == torch.float64 else 10)
+    # second call reuses the raw list (ago > 0) and must give the same answer
+    e2, f2, v2 = dp.eval(coord.reshape(1, -1), box.reshape(1, 9), atype)
+    assert rel(f2[0], f[0]) <= tol
+    # unfused prod_force_a + prod_virial_a path and atomic outputs
+    ea, fa, va, ae, av = dp.eval(coord.reshape(1, -1), box.reshape(1, 9), atype, atomic=True)
+    assert rel(fa[0], wf) <= tol * 10
+    assert abs(ae.sum() - we) <= 10 * tol * abs(we)
+    assert rel(av[0].sum(0), wv) <= tol * 100
+
+
+def test_properties_at_scale(pkg):
+    """4x4x4 replica (12288 atoms, exact replication => ties): net force zero, symmetric virial,
+    replicas equivalent, energy extensive."""
+    from deepmd_kit_b200.model import DeepPotB200, SeAConfig, SeAModel
+
+    cfg = SeAConfig()
+    model = SeAModel(cfg, torch.float64, "cuda:0")
+    c1, t1, b1 = g.water_box(1)
+    e1, f1, v1 = DeepPotB200(model).eval(c1.reshape(1, -1), b1.reshape(1, 9), t1)
+    c4, t4, b4 = g.water_box(4)
+    e4, f4, v4 = DeepPotB200(model).eval(c4.reshape(1, -1), b4.reshape(1, 9), t4)
+    assert abs(e4[0, 0] - 64 * e1[0, 0]) < 1e-9 * abs(e4[0, 0])
+    assert np.abs(f4[0].sum(0)).max() < 1e-9
+    assert np.abs(f4[0].reshape(64, 192, 3) - f1[0][None]).max() < 1e-10
+    assert np.abs(v4[0] - 64 * v1[0]).max() < 1e-9 * np.abs(v4[0]).max()
+    vm = v4[0].reshape(3, 3)
+    assert np.abs(vm - vm.T).max() < 1e-9 * np.abs(vm).max()
+
+
+def test_force_is_energy_gradient(pkg):
+    from deepmd_kit_b200.model import DeepPotB200, SeAConfig, SeAModel
+
+    model = SeAModel(SeAConfig(), torch.float64, "cuda:0")
+    coord, atype, box = g.water_box(1)
+    dp = DeepPotB200(model, nlist_every=1)
+    e0, f0, _ = dp.eval(coord.reshape(1, -1), box.reshape(1, 9), atype)
+    h = 1e-5
+    for i, d in ((3, 0), (150, 1)):
+        es = []
+        for sgn in (1, -1):
+            c = coord.copy()
+            c[i, d] += sgn * h
+            es.append(dp.eval(c.reshape(1, -1), box.reshape(1, 9), atype)[0][0, 0])
+        assert abs(-(es[0] - es[1]) / (2 * h) - f0[0, i, d]) < 1e-7
