@@ -1,0 +1,413 @@
+#!/usr/bin/env python
+"""bench.py — us/step/atom of one compressed se_e2_a energy+force+virial evaluation.
+
+    python bench.py --gpus N --steps K --warmup W            # this repository (CUDA, sm_100a)
+    python bench.py --impl reference --gpus N --steps K ...  # reference CPU ops on the host cores
+
+N = 1: BASELINE.json configs[1] — the 192-atom water frame replicated 20x20x20 (1 536 000 atoms),
+fp64, raw neighbour list with a 2 A skin rebuilt every 10 steps (reference MD set-up), formatted
+every step.  N > 1: weak scaling, one 20x20x20 brick per GPU, spatial decomposition with a ghost
+halo exchange over NCCL (one rank per GPU, launched by torchrun).
+
+One JSON line on stdout (rank 0).  `value` = device-resident step, `e2e` = the same step through the
+public host API (DeepPotB200.eval: pinned host coordinates in, host forces out).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "us/step/atom (energy+force+virial) compressed se_e2_a water"
+UNIT = "us/step/atom"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--dtype", default="f64", choices=["f64", "f32"])
+    ap.add_argument("--ncopy", type=int, default=20, help="replicas of the 192-atom frame per axis and per GPU")
+    ap.add_argument("--jitter", type=float, default=0.01)
+    ap.add_argument("--cpu-ncopy", type=int, default=4, help="replicas per axis of the bounded CPU sample")
+    ap.add_argument("--cpu-seconds", type=float, default=12.0)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--atom-virial", action="store_true")
+    return ap.parse_args()
+
+
+# ------------------------------------------------------------------------------------------------
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index=0):
+        self.index = index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms",
+                                          "200", "-i", str(self.index)], stdout=subprocess.PIPE, text=True)
+            self.thread = threading.Thread(target=self._pump, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, pw, reasons = [], [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            p = [x.strip() for x in ln.split(",")]
+            if len(p) < 9:
+                continue
+            try:
+                sm.append(float(p[1]))
+                mx.append(float(p[2]))
+                pw.append(float(p[3]))
+            except ValueError:
+                continue
+            for n, v in zip(names, p[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "power_w_max": max(pw) if pw else None, "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            d = json.load(f)
+        return float(d["hbm_gbs"]), "MEASURED_PEAKS.json"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+# ------------------------------------------------------------------------------------------------
+def cpu_pipeline_timing(args, steps, warmup, seconds=None):
+    """The reference's CPU ops (OpenMP, all host cores) on a bounded sample of the workload."""
+    import torch
+
+    import __graft_entry__ as g
+    from oracle import cpu as ocpu
+    from oracle import pipeline
+
+    g.load_package()
+    from deepmd_kit_b200.model import SeAConfig, SeAModel
+
+    kind = "reference" if ocpu.available("reference") else "port"
+    lib = ocpu.CpuLib(kind)
+    dtype = torch.float64 if args.dtype == "f64" else torch.float32
+    np_dt = np.float64 if args.dtype == "f64" else np.float32
+    cfg = SeAConfig()
+    model = SeAModel(cfg, dtype, "cpu")
+    coord, atype, box = g.water_box(args.cpu_ncopy, args.jitter)
+    nat = len(atype)
+    t0 = time.perf_counter()
+    lists = pipeline.build_lists(ocpu.CpuLib("port"), coord.astype(np_dt), atype, box.astype(np_dt), cfg.rcut + 2.0)
+    t_build = time.perf_counter() - t0
+    for _ in range(warmup):
+        pipeline.evaluate(lib, model, lists)
+    stage = {}
+    t0 = time.perf_counter()
+    n = 0
+    while n < steps:
+        pipeline.evaluate(lib, model, lists, stage)
+        n += 1
+        if seconds is not None and time.perf_counter() - t0 > seconds and n >= 3:
+            break
+    dt = (time.perf_counter() - t0) / n
+    us = dt * 1e6 / nat
+    return dict(us_per_step_atom=us, ms_per_step=dt * 1e3, steps=n, natoms=nat, kind=kind,
+                cores=os.cpu_count(), build_s=t_build,
+                stages_us_per_atom={k: v / n * 1e6 / nat for k, v in stage.items()},
+                sample=f"{nat}-atom water box ({args.cpu_ncopy}^3 replicas of the 192-atom frame), {n} steps, "
+                       f"raw list (cell list, {t_build * 1e3:.0f} ms) excluded, {args.dtype}")
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    r = cpu_pipeline_timing(args, args.steps, args.warmup)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": r["us_per_step_atom"], "unit": UNIT, "n_gpus": args.gpus,
+        "steps": r["steps"], "warmup": args.warmup, "ms_per_step": r["ms_per_step"], "higher_is_better": False,
+        "scaling": "weak", "vs_baseline": None, "dtype": args.dtype, "data": "synthetic",
+        "config": {"workload": "se_e2_a compressed water (rcut 6.0, sel [46,92], neuron [25,50,100], axis 16, fitting "
+                               "[240,240,240]), reference CPU ops (libdeepmd *_cpu, OpenMP) + torch CPU fitting net; "
+                               "each step = one evaluation of a bounded sample", "sample_natoms": r["natoms"]},
+        "cpu_baseline": {"value": r["us_per_step_atom"], "unit": UNIT, "cores": r["cores"], "kind": r["kind"],
+                         "sample": r["sample"], "stages_us_per_atom": r["stages_us_per_atom"]},
+        "e2e": {"value": r["us_per_step_atom"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------------------------------
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+
+    import __graft_entry__ as g
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise RuntimeError("bench.py needs a CUDA device: the hot path has no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    pkg = g.load_package()
+    from deepmd_kit_b200 import ops
+    from deepmd_kit_b200.model import DeepPotB200, SeAConfig, SeAModel
+
+    L = pkg._lib.lib()
+    dtype = torch.float64 if args.dtype == "f64" else torch.float32
+    np_dt = np.float64 if args.dtype == "f64" else np.float32
+    cfg = SeAConfig()
+    model = SeAModel(cfg, dtype, dev)
+    esz = 8 if args.dtype == "f64" else 4
+
+    if world == 1:
+        coord, atype, box = g.water_box(args.ncopy, args.jitter)
+        natoms_total = len(atype)
+        dp = DeepPotB200(model, skin=2.0, nlist_every=10)
+        coord_d = torch.as_tensor(coord.astype(np_dt)).to(dev)
+        atype_d = torch.as_tensor(atype).to(dev)
+
+        def step():
+            return dp.eval_device(coord_d, atype_d, box, atom_virial=args.atom_virial)
+
+        parallelism = "1 GPU"
+    else:
+        from deepmd_kit_b200.domain import DomainDeepPot, proc_grid
+
+        grid = proc_grid(world)
+        dp = DomainDeepPot(model, grid, skin=2.0, nlist_every=10)
+        coord, atype, box = dp.make_local_water(g.water_box, args.ncopy, args.jitter)
+        natoms_total = len(atype) * world
+        coord_d = torch.as_tensor(coord.astype(np_dt)).to(dev)
+        atype_d = torch.as_tensor(atype).to(dev)
+
+        def step():
+            return dp.eval_device(coord_d, atype_d, box, atom_virial=args.atom_virial)
+
+        parallelism = f"spatial {grid[0]}x{grid[1]}x{grid[2]} bricks, NCCL halo"
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        out = step()
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    l0 = L.launch_count()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    ev0.record()
+    for _ in range(args.steps):
+        out = step()
+    ev1.record()
+    barrier()
+    ms = ev0.elapsed_time(ev1)
+    launches = L.launch_count() - l0
+    clocks = sampler.stop() if rank == 0 else None
+    if world > 1:
+        t = torch.tensor([ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    ms_per_step = ms / args.steps
+    value = ms_per_step * 1e3 / natoms_total
+    energy = float(out[0])
+
+    # ---- e2e through the public host API ---------------------------------------------------
+    e2e = None
+    if not args.no_e2e:
+        nat_local = len(atype)
+        k = max(3, min(args.steps, 10))
+        coords_h = coord.astype(np_dt).reshape(1, -1)
+        cells_h = np.asarray(box, np.float64).reshape(1, 9)
+        for _ in range(2):
+            dp.eval(coords_h, cells_h, atype)
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(k):
+            res = dp.eval(coords_h, cells_h, atype)
+        barrier()
+        dt = (time.perf_counter() - t0) / k
+        if world > 1:
+            t = torch.tensor([dt], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            dt = float(t.item())
+        e2e = {"value": dt * 1e6 / natoms_total, "unit": UNIT, "h2d_bytes_per_step": nat_local * 3 * esz * world,
+               "d2h_bytes_per_step": (nat_local * 3 + 10) * esz * world, "steps": k,
+               "api": "DeepPotB200.eval(coords, cells, atom_types) — pinned host buffers, H2D + D2H inside the timed region"}
+
+    # ---- per-kernel timing (instrumented pass, rank 0 reports) ---------------------------------
+    kernels, roofline = None, None
+    if rank == 0:
+        kernels, roofline = per_kernel(args, torch, ops, model, dp, step, L, dev, len(atype), esz)
+
+    cpu_base = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        try:
+            r = cpu_pipeline_timing(args, 10 ** 6, 1, seconds=args.cpu_seconds)
+            cpu_base = {"value": r["us_per_step_atom"], "unit": UNIT, "cores": r["cores"], "kind": r["kind"],
+                        "sample": r["sample"], "stages_us_per_atom": r["stages_us_per_atom"]}
+        except Exception as e:  # the checker libraries are test infrastructure; report, do not hide
+            cpu_base = {"value": None, "unit": UNIT, "error": repr(e)}
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": False, "scaling": "weak",
+            "vs_baseline": None, "dtype": args.dtype, "data": "synthetic",
+            "config": {
+                "workload": f"se_e2_a compressed water, {natoms_total}-atom box ({args.ncopy}^3 replicas of the 192-atom "
+                            f"frame per GPU, Gaussian jitter {args.jitter} A), {args.dtype}, {world}xB200",
+                "natoms": natoms_total, "rcut": cfg.rcut, "rcut_smth": cfg.rcut_smth, "sel": list(cfg.sel),
+                "neuron": list(cfg.neuron), "axis_neuron": cfg.axis_neuron, "fitting_neuron": list(cfg.fitting_neuron),
+                "table": "dp-compress restatement, stride 0.01/0.1, extrapolate 5, random-init weights (seed 1)",
+                "skin": 2.0, "nlist_every": 10, "parallelism": parallelism,
+                "atom_virial": bool(args.atom_virial),
+                "l2_policy": "per-step working set (tens of GB of env-mat intermediates) is far larger than the 126 MB L2",
+                "energy": energy,
+            },
+            "clocks": clocks, "gpu_launches": int(launches),
+        }
+        if e2e:
+            line["e2e"] = e2e
+        if roofline:
+            line["roofline"] = roofline
+        if kernels:
+            line["kernels"] = kernels
+        if cpu_base:
+            line["cpu_baseline"] = cpu_base
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def per_kernel(args, torch, ops, model, dp, step, L, dev, nloc, esz):
+    """CUDA-event time of every dpb200 operator inside the real step (events on the launching stream),
+    and the roofline of each against measured peaks."""
+    names = ["prod_env_mat_a", "tabulate_sections_fwd", "tabulate_sections_grad", "prod_force_virial_a", "use_nlist_map",
+             "normalize_coord", "copy_coord", "build_nlist"]
+    acc = {}
+    orig = {}
+
+    def wrap(name, fn):
+        def f(*a, **k):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            r = fn(*a, **k)
+            e1.record()
+            acc.setdefault(name, []).append((e0, e1))
+            return r
+        return f
+
+    for n in names:
+        orig[n] = getattr(ops, n)
+        setattr(ops, n, wrap(n, orig[n]))
+    orig_fit = model.energy_and_dy
+    model.energy_and_dy = wrap("fitting_net(torch)", orig_fit)
+    nsteps = 10
+    try:
+        for _ in range(nsteps):
+            out = step()
+        torch.cuda.synchronize()
+    finally:
+        for n in names:
+            setattr(ops, n, orig[n])
+        model.energy_and_dy = orig_fit
+    nlist = out[3]["nlist"]
+    nreal = float((nlist >= 0).sum().item()) / nloc
+    cfg = model.cfg
+    nnei, M, nt = cfg.nnei, model.M, cfg.ntypes
+    st = dp.state
+    nall = int(st.ext_type.numel())
+    raw = float(st.numneigh.sum().item()) / nloc
+    F = esz
+    hbm, hbm_src = measured_peaks()
+    fma = L.fma_peak(args.dtype, None)
+    npr = nreal + nt  # one folded padding entry per table
+    alg = {
+        "prod_env_mat_a": ("hbm", (19 * nnei * F + 4 * nnei) + 4 * raw + 3 * F * (1 + nall / nloc)),
+        "prod_force_virial_a": ("hbm", (19 * nnei * F + 4 * nnei) + 3 * F + (9 * F if args.atom_virial else 0)),
+        "tabulate_sections_fwd": ("fp", 18 * npr * M),
+        "tabulate_sections_grad": ("fp", 36 * npr * M),
+    }
+    table = {}
+    total = 0.0
+    for n, evs in acc.items():
+        ms = sum(a.elapsed_time(b) for a, b in evs) / nsteps
+        table[n] = {"ms_per_step": ms, "calls_per_step": len(evs) / nsteps}
+        total += ms
+    for n, row in table.items():
+        row["share"] = row["ms_per_step"] / total if total > 0 else None
+        if n in alg and row["ms_per_step"] > 0:
+            kind, per_atom = alg[n]
+            t = row["ms_per_step"] * 1e-3
+            if kind == "hbm":
+                a = per_atom * nloc / t / 1e9
+                row.update(bound="hbm", achieved=a, peak=hbm, unit="GB/s", frac=a / hbm, alg_bytes_per_atom=per_atom)
+            else:
+                a = per_atom * nloc / t / 1e12
+                row.update(bound="fp64-fma" if args.dtype == "f64" else "fp32-fma", achieved=a, peak=fma,
+                           unit="TFLOP/s", frac=a / fma, alg_flops_per_atom=per_atom)
+    ours = {n: r for n, r in table.items() if "bound" in r}
+    top = max(ours, key=lambda n: ours[n]["ms_per_step"]) if ours else None
+    roofline = None
+    if top:
+        r = ours[top]
+        roofline = {"kernel": top, "bound": r["bound"], "achieved": r["achieved"], "peak": r["peak"], "unit": r["unit"],
+                    "frac": r["frac"], "traffic": None,
+                    "peak_source": hbm_src if r["bound"] == "hbm" else "dpb200_fma_peak measured in this run (burst)",
+                    "mean_real_neighbours": nreal, "mean_raw_neighbours": raw}
+    return table, roofline
+
+
+def main():
+    args = parse()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -35,6 +35,8 @@ _SIGS = {
     "normalize_coord_{s}": "pip p",
     "copy_coord_{s}": "pppp pp ii f p pz p",
     "build_nlist_{s}": "ppp p iii f p pz p",
+    "halo_pack_{s}": "pppp i p",
+    "halo_unpack_add_{s}": "ppp i p",
 }
 
 

@@ -492,10 +492,9 @@ int common_args(TabParams<FP>& p, const FP* em_x, long long ldx_i, int ldx_j, co
   return DPB200_OK;
 }
 
-// Persistent launch shape: min(work, SMs x resident CTAs) CTAs of 4 warps; L1-heavy carve-out.
+// Persistent launch shape: min(work, SMs x resident CTAs) CTAs of 4 warps.
 template <typename K>
 int persistent_grid(K kern, long long nwarps_needed) {
-  cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxL1);
   int occ = 0;
   if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, 128, 0) != cudaSuccess || occ < 1) occ = 1;
   long long want = (nwarps_needed + 3) / 4;

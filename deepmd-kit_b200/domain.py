@@ -1,0 +1,211 @@
+"""Spatial domain decomposition for multi-GPU force evaluation: one rank per GPU, each owning a brick
+of the periodic box, ghost-atom coordinate halo forward and ghost-force halo back every step.
+
+This is the role LAMMPS' Comm plays around PairDeepMD::compute in the reference
+(source/lmp/pair_deepmd.cpp:217-229 swap plan hand-off, :482-488 reverse_comm of ghost forces;
+source/lib/include/neighbor_list.h:29-57 carries the plan in InputNlist), re-done for NVSwitch: all
+peers are one hop away at full bandwidth, so the 6 staged swaps collapse to ONE grouped NCCL
+send/recv over the 26 neighbour directions (<= 7 distinct peers on 2x2x2, self-images copied
+locally), bracketed by the dpb200 pack / unpack-accumulate kernels.  Energy and virial leave as
+one 10-scalar all-reduce.
+
+Atoms are not migrated between bricks here (the benchmark boxes are static); an atom that drifts
+out of its brick by less than the skin is still handled correctly because the ghost shell is
+selected with rcut + skin.
+"""
+from __future__ import annotations
+
+from typing import List, Sequence, Tuple
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+from . import ops
+from .model import DeepPotB200, NeighborState, SeAModel, type_partition
+
+DIRS: List[Tuple[int, int, int]] = [(a, b, c) for a in (-1, 0, 1) for b in (-1, 0, 1) for c in (-1, 0, 1)
+                                    if (a, b, c) != (0, 0, 0)]
+
+
+def proc_grid(world: int) -> Tuple[int, int, int]:
+    """Near-cubic factorisation, x fastest-growing: 1->(1,1,1) 2->(2,1,1) 4->(2,2,1) 8->(2,2,2)."""
+    g = [1, 1, 1]
+    n = world
+    d = 0
+    f = 2
+    while n > 1:
+        while n % f:
+            f += 1
+        g[d % 3] *= f
+        n //= f
+        d += 1
+    g.sort(reverse=True)
+    return tuple(g)
+
+
+def rank_to_coords(rank: int, grid: Sequence[int]) -> Tuple[int, int, int]:
+    gx, gy, gz = grid
+    return (rank // (gy * gz), (rank // gz) % gy, rank % gz)
+
+
+def coords_to_rank(c: Sequence[int], grid: Sequence[int]) -> int:
+    gx, gy, gz = grid
+    return ((c[0] % gx) * gy + (c[1] % gy)) * gz + (c[2] % gz)
+
+
+class HaloPlan:
+    """Send lists per direction, receive segments, peers.  Device-agnostic (torch ops only) so the
+    N>1 host logic is testable with the gloo backend on CPU."""
+
+    def __init__(self, coord: torch.Tensor, box, grid, rank, rc: float, group=None):
+        self.grid, self.rank, self.group = tuple(grid), rank, group
+        self.world = grid[0] * grid[1] * grid[2]
+        dev, dt = coord.device, coord.dtype
+        b = np.asarray(box, np.float64).reshape(3, 3)
+        vol = abs(np.linalg.det(b))
+        rec = np.linalg.inv(b)  # fractional s = r @ rec
+        face = np.array([vol / np.linalg.norm(np.cross(b[(d + 1) % 3], b[(d + 2) % 3])) for d in range(3)])
+        me = rank_to_coords(rank, grid)
+        lo = np.array([me[d] / grid[d] for d in range(3)])
+        hi = np.array([(me[d] + 1) / grid[d] for d in range(3)])
+        w = rc / face
+        for d in range(3):
+            if w[d] > 1.0 / grid[d] + 1e-12:
+                raise ValueError(f"halo width {rc} exceeds the brick width along axis {d}: use fewer ranks on that axis")
+        c = coord.reshape(-1, 3)
+        s = c.to(torch.float64) @ torch.as_tensor(rec, device=dev)
+        lists, shifts, dests, srcs = [], [], [], []
+        for (dx, dy, dz) in DIRS:
+            m = torch.ones(c.shape[0], dtype=torch.bool, device=dev)
+            wrap = [0, 0, 0]
+            for d, dd in enumerate((dx, dy, dz)):
+                if dd == 1:
+                    m &= s[:, d] >= hi[d] - w[d]
+                    wrap[d] = 1 if me[d] + 1 >= grid[d] else 0
+                elif dd == -1:
+                    m &= s[:, d] < lo[d] + w[d]
+                    wrap[d] = -1 if me[d] - 1 < 0 else 0
+            idx = torch.nonzero(m).reshape(-1).to(torch.int32)
+            sh = -(wrap[0] * b[0] + wrap[1] * b[1] + wrap[2] * b[2])
+            lists.append(idx)
+            shifts.append(torch.as_tensor(sh, dtype=dt, device=dev).expand(idx.numel(), 3))
+            dests.append(coords_to_rank((me[0] + dx, me[1] + dy, me[2] + dz), grid))
+            srcs.append(coords_to_rank((me[0] - dx, me[1] - dy, me[2] - dz), grid))
+        self.dests, self.srcs = dests, srcs
+        self.send_counts = [int(l.numel()) for l in lists]
+        self.sendlist = torch.cat(lists) if lists else torch.zeros(0, dtype=torch.int32, device=dev)
+        self.shift = torch.cat(shifts).contiguous()
+        cnt = torch.tensor(self.send_counts, dtype=torch.int64, device=dev)
+        if self.world > 1:
+            allc = torch.empty(self.world * len(DIRS), dtype=torch.int64, device=dev)
+            dist.all_gather_into_tensor(allc, cnt, group=group)
+            allc = allc.reshape(self.world, len(DIRS)).cpu()
+        else:
+            allc = cnt.reshape(1, -1).cpu()
+        # direction k arrives from srcs[k], which sent it as ITS direction k
+        self.recv_counts = [int(allc[srcs[k], k]) for k in range(len(DIRS))]
+        self.nsend = int(sum(self.send_counts))
+        self.nghost = int(sum(self.recv_counts))
+        self.send_off = np.concatenate([[0], np.cumsum(self.send_counts)]).astype(int)
+        self.recv_off = np.concatenate([[0], np.cumsum(self.recv_counts)]).astype(int)
+
+    # one grouped exchange: sendbuf segments -> dests, recvbuf segments <- srcs (reverse=True mirrors it)
+    def exchange(self, sendbuf: torch.Tensor, recvbuf: torch.Tensor, reverse: bool = False):
+        p2p = []
+        s_off, r_off = (self.recv_off, self.send_off) if reverse else (self.send_off, self.recv_off)
+        to, frm = (self.srcs, self.dests) if reverse else (self.dests, self.srcs)
+        for k in range(len(DIRS)):
+            a, bnd = s_off[k], s_off[k + 1]
+            ra, rb = r_off[k], r_off[k + 1]
+            if to[k] == self.rank and frm[k] == self.rank:
+                if rb > ra:
+                    recvbuf[ra:rb].copy_(sendbuf[a:bnd])
+                continue
+            if bnd > a:
+                p2p.append(dist.P2POp(dist.isend, sendbuf[a:bnd], to[k], group=self.group))
+            if rb > ra:
+                p2p.append(dist.P2POp(dist.irecv, recvbuf[ra:rb], frm[k], group=self.group))
+        if p2p:
+            for r in dist.batch_isend_irecv(p2p):
+                r.wait()
+
+
+class DomainDeepPot(DeepPotB200):
+    """DeepPotB200 over a brick decomposition: `eval_device(local coords)` returns the global energy
+    and virial (all-reduced) and the forces on this rank's own atoms."""
+
+    def __init__(self, model: SeAModel, grid, skin: float = 2.0, nlist_every: int = 10, group=None):
+        super().__init__(model, skin, nlist_every)
+        self.grid = tuple(grid)
+        self.group = group
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        self.plan = None
+
+    def make_local_water(self, water_box_fn, ncopy: int, jitter: float):
+        """This rank's brick of the weak-scaling benchmark box: ncopy^3 replicas of the 192-atom frame per
+        rank, global box = grid * brick."""
+        c, t, b = water_box_fn(ncopy, jitter, seed=20260101 + self.rank)
+        me = rank_to_coords(self.rank, self.grid)
+        L = np.diag(b)
+        c = c + np.array(me) * L
+        return c, t, b * np.array(self.grid)[:, None]
+
+    # -- host-side pieces (overridable for CPU tests) -----------------------------------------
+    def _pack(self, coord, plan):
+        return ops.halo_pack(coord, plan.sendlist, plan.shift)
+
+    def _unpack_add(self, force, buf, plan):
+        return ops.halo_unpack_add(force, buf, plan.sendlist)
+
+    def halo_forward(self, coord: torch.Tensor) -> torch.Tensor:
+        plan = self.plan
+        nloc = coord.shape[0]
+        ext = torch.empty((nloc + plan.nghost, 3), dtype=coord.dtype, device=coord.device)
+        ext[:nloc].copy_(coord)
+        plan.exchange(self._pack(coord, plan), ext[nloc:])
+        return ext
+
+    def halo_reverse(self, force_ext: torch.Tensor, nloc: int) -> torch.Tensor:
+        plan = self.plan
+        buf = torch.empty((plan.nsend, 3), dtype=force_ext.dtype, device=force_ext.device)
+        plan.exchange(force_ext[nloc:].contiguous(), buf, reverse=True)
+        f = force_ext[:nloc].contiguous()
+        return self._unpack_add(f, buf, plan)
+
+    def build_neighbors(self, coord, atype, box):
+        m = self.model
+        rc = m.cfg.rcut + self.skin
+        c = coord.reshape(-1, 3)
+        nloc = atype.numel()
+        self.plan = HaloPlan(c, box, self.grid, self.rank, rc, self.group)
+        ext_c = self.halo_forward(c)
+        gt = torch.empty(self.plan.nghost, dtype=torch.int32, device=c.device)
+        self.plan.exchange(atype.to(torch.int32).index_select(0, self.plan.sendlist.long()), gt)
+        ext_t = torch.cat([atype.to(torch.int32), gt]).contiguous()
+        numneigh, rows = ops.build_nlist(ext_c, nloc, rc, ext_t)
+        perm, ranges = type_partition(atype, m.cfg.ntypes)
+        self.state = NeighborState(nloc, ext_t, None, None, numneigh, rows, perm, ranges)
+        return self.state
+
+    def eval_device(self, coord, atype, box, atom_virial=False, fused=True):
+        st = self.state
+        if st is None or st.ago >= self.nlist_every or st.nloc != atype.numel():
+            st = self.build_neighbors(coord, atype, box)
+        c = coord.reshape(-1, 3)
+        ext_c = self.halo_forward(c)
+        st.ago += 1
+        e, f_ext, virial, ex = self.model.evaluate(ext_c, st.ext_type, st.numneigh, st.rows, None, st.nloc,
+                                                   st.type_perm, st.type_ranges, atom_virial=atom_virial, fused=fused)
+        force = self.halo_reverse(f_ext, st.nloc)
+        red = torch.cat([e.reshape(1), virial.reshape(9)])
+        if dist.is_initialized() and dist.get_world_size(self.group) > 1:
+            dist.all_reduce(red, group=self.group)
+        if atom_virial and ex.get("atom_virial") is not None:
+            av_ext = ex["atom_virial"].reshape(-1, 9)
+            av = av_ext[:st.nloc].contiguous()
+            for q in range(3):  # 9 components as three 3-vectors through the same reverse halo
+                part = self.halo_reverse(av_ext[:, 3 * q:3 * q + 3].contiguous(), st.nloc)
+                av[:, 3 * q:3 * q + 3] = part
+            ex["atom_virial"] = av.reshape(-1)
+        return red[0], force, red[1:], ex

@@ -442,6 +442,28 @@ def use_nlist_map(nlist, mapping):
     return nlist
 
 
+def halo_pack(coord, sendlist, shift):
+    """sendbuf[k] = coord[sendlist[k]] + shift[k] (dpb200_halo_pack)."""
+    dev = _need_cuda(("coord", coord), ("sendlist", sendlist), ("shift", shift))
+    s = _suffix(coord)
+    n = sendlist.numel()
+    out = torch.empty((n, 3), dtype=coord.dtype, device=dev)
+    lib().call("halo_pack_" + s, _p(out), _p(_c(coord)), _p(_c(sendlist, torch.int32)), _p(_c(shift, coord.dtype)), n,
+               _stream(dev))
+    return out
+
+
+def halo_unpack_add(force, recvbuf, sendlist):
+    """force[sendlist[k]] += recvbuf[k] in place (dpb200_halo_unpack_add)."""
+    dev = _need_cuda(("force", force), ("recvbuf", recvbuf), ("sendlist", sendlist))
+    s = _suffix(force)
+    if not force.is_contiguous():
+        raise ValueError("dpb200: halo_unpack_add works in place and needs a contiguous force tensor")
+    lib().call("halo_unpack_add_" + s, _p(force), _p(_c(recvbuf, force.dtype)), _p(_c(sendlist, torch.int32)),
+               sendlist.numel(), _stream(dev))
+    return force
+
+
 # ------------------------------------------------------------------------------------------------
 # torch.ops.deepmd.*  (reference operator surface)
 # ------------------------------------------------------------------------------------------------

@@ -185,6 +185,22 @@ DPB200_DECL_NL(f64, double)
 DPB200_DECL_NL(f32, float)
 #undef DPB200_DECL_NL
 
+/* ---------------------------------------------------------------------------------------
+ * Ghost halo for the spatially decomposed multi-GPU path.  Replaces what LAMMPS' Comm does around
+ * PairDeepMD::compute (source/lmp/pair_deepmd.cpp:482-488 reverse_comm, :1069-1093 pack/unpack):
+ *   halo_pack       sendbuf[k,:] = coord[sendlist[k],:] + shift[k,:]   (k < n; shift = image vector)
+ *   halo_unpack_add force[sendlist[k],:] += recvbuf[k,:]               (ghost forces to owners)
+ * The transfer itself is a grouped NCCL send/recv issued by the host side.
+ * ------------------------------------------------------------------------------------- */
+#define DPB200_DECL_HALO(SUF, FP)                                                                      \
+  int dpb200_halo_pack_##SUF(FP* sendbuf, const FP* coord, const int* sendlist, const FP* shift, int n, \
+                             dpb200_stream_t stream);                                                  \
+  int dpb200_halo_unpack_add_##SUF(FP* force, const FP* recvbuf, const int* sendlist, int n,           \
+                                   dpb200_stream_t stream);
+DPB200_DECL_HALO(f64, double)
+DPB200_DECL_HALO(f32, float)
+#undef DPB200_DECL_HALO
+
 /* use_nlist_map (neighbor_list.h:219-222): nlist[k] = map[nlist[k]] for entries >= 0. */
 int dpb200_use_nlist_map(int* nlist, const int* nlist_map, int nloc, int nnei, dpb200_stream_t stream);
 
