@@ -67,12 +67,27 @@ def build(force: bool = False, verbose: bool = False) -> str:
         list(ex.map(run, jobs))
     if force or jobs or _stale(LIB, objs):
         run([nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", LIB] + objs + ["-cudart", "static"])
-    shim_src = os.path.join(CSRC, "deepmd_gpu_shim.cc")
-    if os.path.exists(shim_src) and (force or _stale(SHIM, [shim_src, LIB] + headers)):
-        cxx = shutil.which("g++") or "g++"
-        run([cxx, "-O2", "-std=c++17", "-fPIC", "-shared", "-I", os.path.join(os.path.dirname(HERE), "include"),
-             shim_src, "-o", SHIM, "-L", LIBDIR, "-ldpb200", "-Wl,-rpath,$ORIGIN"])
+    build_shim(force, run)
     return LIB
+
+
+def build_shim(force=False, run=subprocess.check_call) -> str | None:
+    """lib/libdeepmd_op_cuda.so: the reference's C++ `deepmd::*_gpu` symbols on top of the C ABI.  It is
+    compiled against the REFERENCE'S OWN headers (never copied), so it is only (re)built where a
+    DeePMD-kit source tree is available ($DEEPMD_SOURCE_DIR or /root/reference)."""
+    ref = os.environ.get("DEEPMD_SOURCE_DIR", "/root/reference")
+    inc = os.path.join(ref, "source", "lib", "include")
+    shim_src = os.path.join(CSRC, "deepmd_gpu_shim.cc")
+    if not os.path.isdir(inc) or not os.path.exists(shim_src):
+        return SHIM if os.path.exists(SHIM) else None
+    if force or _stale(SHIM, [shim_src, LIB, os.path.join(os.path.dirname(HERE), "include", "dpb200.h")]):
+        cxx = shutil.which("g++") or "g++"
+        cuda_inc = os.path.join(os.path.dirname(os.path.dirname(_nvcc())), "include")
+        run([cxx, "-O2", "-std=c++17", "-fPIC", "-shared", "-DGOOGLE_CUDA=1", "-I", inc,
+             "-I", os.path.join(os.path.dirname(HERE), "include"), "-I", cuda_inc, shim_src, "-o", SHIM,
+             "-L", LIBDIR, "-ldpb200", "-L", os.path.join(os.path.dirname(cuda_inc), "lib64"), "-lcudart",
+             "-Wl,-rpath,$ORIGIN"])
+    return SHIM
 
 
 if __name__ == "__main__":

@@ -34,6 +34,7 @@ _SIGS = {
     "prod_force_virial_a_{s}": "ppppppp iii p",
     "normalize_coord_{s}": "pip p",
     "copy_coord_{s}": "pppp pp ii f p pz p",
+    "copy_coord_cells_{s}": "pppp pp ii pp p pz p",
     "build_nlist_{s}": "ppp p iii f p pz p",
     "halo_pack_{s}": "pppp i p",
     "halo_unpack_add_{s}": "ppp i p",

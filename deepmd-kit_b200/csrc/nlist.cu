@@ -524,10 +524,10 @@ int do_normalize(FP* coord, int natom, const FP* boxt, cudaStream_t st) {
 
 template <typename FP>
 int do_copy_coord(FP* out_c, int* out_t, int* mapping, int* nall_out, const FP* in_c, const int* in_t,
-                  int nloc, int mem_nall, float rcut, const FP* boxt, void* workspace, size_t ws_bytes,
-                  cudaStream_t st) {
+                  int nloc, int mem_nall, float rcut, const int* ncell, const int* ngcell, const FP* boxt,
+                  void* workspace, size_t ws_bytes, cudaStream_t st) {
   DPB_REQUIRE(nloc >= 0 && mem_nall >= 0 && nall_out, "copy_coord: bad size arguments");
-  DPB_REQUIRE(rcut > 0.f && boxt, "copy_coord: rcut must be positive and boxt non-null");
+  DPB_REQUIRE((rcut > 0.f || (ncell && ngcell)) && boxt, "copy_coord: rcut must be positive and boxt non-null");
   if (nloc == 0) {
     *nall_out = 0;
     return DPB200_OK;
@@ -537,7 +537,14 @@ int do_copy_coord(FP* out_c, int* out_t, int* mapping, int* nall_out, const FP* 
   CellInfo ci;
   double b[9];
   for (int k = 0; k < 9; ++k) b[k] = (double)boxt[k];
-  make_cell_info(ci, b, rcut);
+  make_cell_info(ci, b, rcut > 0.f ? rcut : 1.f);
+  if (ncell && ngcell) {  // cell grid handed over by the caller (compute_cell_info, coord.cc:68-108)
+    for (int d = 0; d < 3; ++d) {
+      DPB_REQUIRE(ncell[d] >= 1 && ngcell[d] >= 0, "copy_coord: invalid cell grid");
+      ci.ncell[d] = ncell[d];
+      ci.ng[d] = ngcell[d];
+    }
+  }
   int* cnt = static_cast<int*>(workspace);
   int* off = cnt + align_up((size_t)nloc + 1, 64);
   int* tmp = off + align_up((size_t)nloc + 1, 64);
@@ -647,7 +654,16 @@ size_t dpb200_build_nlist_workspace_bytes(int nall) { return dpb200::build_ws(na
                               const int* in_t, int nloc, int mem_nall, float rcut, const FP* boxt, \
                               void* workspace, size_t workspace_bytes, dpb200_stream_t stream) {   \
     return dpb200::do_copy_coord<FP>(out_c, out_t, mapping, nall, in_c, in_t, nloc, mem_nall,      \
-                                     rcut, boxt, workspace, workspace_bytes,                       \
+                                     rcut, nullptr, nullptr, boxt, workspace, workspace_bytes,     \
+                                     (cudaStream_t)stream);                                        \
+  }                                                                                                \
+  int dpb200_copy_coord_cells_##SUF(FP* out_c, int* out_t, int* mapping, int* nall,                \
+                                    const FP* in_c, const int* in_t, int nloc, int mem_nall,       \
+                                    const int* ncell, const int* ngcell, const FP* boxt,           \
+                                    void* workspace, size_t workspace_bytes,                       \
+                                    dpb200_stream_t stream) {                                      \
+    return dpb200::do_copy_coord<FP>(out_c, out_t, mapping, nall, in_c, in_t, nloc, mem_nall,      \
+                                     0.f, ncell, ngcell, boxt, workspace, workspace_bytes,         \
                                      (cudaStream_t)stream);                                        \
   }                                                                                                \
   int dpb200_build_nlist_##SUF(int* numneigh, int* rows, int* max_list_size, const FP* coord,      \

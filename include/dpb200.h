@@ -177,6 +177,13 @@ size_t dpb200_build_nlist_workspace_bytes(int nall);
                               const FP* in_c, const int* in_t, int nloc, int mem_nall,             \
                               float rcut, const FP* boxt, void* workspace,                         \
                               size_t workspace_bytes, dpb200_stream_t stream);                     \
+  /* same, with the cell grid of compute_cell_info (coord.cc:68-108) handed over: ncell[3] =        \
+   * cell_info[3..5], ngcell[3] = cell_info[12..14] -- the form copy_coord_gpu receives */          \
+  int dpb200_copy_coord_cells_##SUF(FP* out_c, int* out_t, int* mapping, int* nall /*host out*/,   \
+                                    const FP* in_c, const int* in_t, int nloc, int mem_nall,       \
+                                    const int* ncell, const int* ngcell, const FP* boxt,           \
+                                    void* workspace, size_t workspace_bytes,                       \
+                                    dpb200_stream_t stream);                                       \
   int dpb200_build_nlist_##SUF(int* numneigh, int* rows, int* max_list_size /*host out*/,          \
                                const FP* coord, int nloc, int nall, int mem_size, float rcut,      \
                                const int* type, void* workspace, size_t workspace_bytes,           \
