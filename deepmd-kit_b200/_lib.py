@@ -18,7 +18,7 @@ ERR_OOM = -3
 ERR_NLIST_CAPACITY = -4
 MAX_NBOR_SIZE = 4096
 
-_T = {"p": C.c_void_p, "i": C.c_int, "l": C.c_longlong, "f": C.c_float, "z": C.c_size_t}
+_T = {"p": C.c_void_p, "i": C.c_int, "l": C.c_longlong, "f": C.c_float, "z": C.c_size_t, "d": C.c_double}
 
 # name -> argument codes (p pointer, i int, l long long, f float, z size_t); `{s}` = f32 | f64
 _SIGS = {
@@ -36,6 +36,8 @@ _SIGS = {
     "copy_coord_{s}": "pppp pp ii f p pz p",
     "copy_coord_cells_{s}": "pppp pp ii pp p pz p",
     "build_nlist_{s}": "ppp p iii f p pz p",
+    "se_a_descriptor_{s}": "pp l ii d p",
+    "se_a_descriptor_grad_{s}": "ppp l ii d p",
     "halo_pack_{s}": "pppp i p",
     "halo_unpack_add_{s}": "ppp i p",
 }

@@ -5,22 +5,29 @@
 // with linear extrapolation outside [lower,max) (tabulate.cc:45-73,122-158), the optional
 // se_atten gate g <- g*t + g, and the `is_sorted` fold of the trailing padding (":197-201").
 //
-// Design (not a port of source/lib/src/gpu/tabulate.cu, which runs one thread per output
-// channel with stride-6 coefficient loads and, in the backward, five full warp reductions per
-// neighbour):
-//   * the table is re-laid out once per call as T[row][6][Mpad] so that one coefficient of 32
-//     channels is ONE coalesced 128/256-byte request (the reference layout [row][M][6] costs 3x
-//     the L1 wavefronts); rows are L1/L2 resident, the op is bound by L1 bandwidth + FP pipe;
-//   * one WARP per centre atom, lanes over channels (NC channels per lane, M <= 32*NC per
-//     block of channels), persistent grid-stride loop over atoms: no block barrier anywhere;
+// What bounds this op on B200 (measured, profiles/r01_*): not HBM and not yet the FP pipe but the
+// coefficient traffic -- every (neighbour, channel) needs 6 coefficients = 4.8 KB per neighbour in
+// fp64 for M=100 -- which a cache-oblivious kernel pulls from L2 (~90 neighbours/atom).  The row
+// distribution is extremely skewed (water: 50% of all look-ups fall into 16 rows, 90% into ~150,
+// because sw(r)/r flattens towards rcut), so the design keeps the hot rows ON CHIP:
+//   * forward: the channel axis is split over gridDim.y CTAs (slice of Mc channels each) so that a
+//     CTA's shared memory (~190 KB) holds H >= 150 hot rows of ITS slice; look-ups that hit the
+//     window are LDS.128, the rest fall back to the (L2-resident) table.  One WARP per (atom,
+//     slice), lanes over channels, persistent loop, no block barrier after the preload;
+//   * backward: all channels of an atom must meet in one reduction, so a CTA caches full-width
+//     rows (fewer of them) and 8 neighbours x 4 components = 32 partial sums per lane are reduced
+//     with ONE butterfly reduce-scatter (31 shuffles) whose result is exactly the 32 contiguous
+//     dy_dem values of those neighbours -> one coalesced store; dy_dem_x needs 9 more shuffles
+//     (the reference does five full warp reductions per neighbour);
 //   * neighbours are "located" 32 at a time in parallel (exact FP division as the reference),
-//     records {dx, delta, em[4], row, multiplicity} are staged in per-warp shared memory and
-//     read back as broadcast LDS.128 by the channel loop;
-//   * consecutive neighbours are distance-sorted, so they frequently share a table row: the
+//     records {dx, delta, em[4], row, multiplicity} are staged in per-warp shared memory and read
+//     back as broadcast LDS by the channel loop;
+//   * consecutive neighbours are distance-sorted, so ~35% of them share the previous row: the
 //     coefficients stay in registers until the row changes;
-//   * backward: 8 neighbours x 4 components = 32 partial sums per lane are reduced with ONE
-//     butterfly reduce-scatter (31 shuffles) whose result is exactly the 32 contiguous dy_dem
-//     values of those neighbours -> one coalesced store; dy_dem_x needs 9 more shuffles.
+//   * the table is read in the reference layout [row][M][6] (one 48-byte record per lane): no
+//     re-layout pass, no scratch allocation.
+// Not a port of source/lib/src/gpu/tabulate.cu (one thread per channel, stride-6 scalar loads, all
+// coefficients from global memory, serial padding search by thread 0).
 #include <cmath>
 
 #include "common.cuh"
@@ -30,18 +37,22 @@ namespace {
 
 template <typename FP>
 struct TabParams {
-  const FP* T;  // [nrow][6][Mpad]
+  const FP* table;  // [nrow][M][6], reference layout
   FP lower, upper, vmax, s0, s1;
   int first;     // int((upper-lower)/s0)
   int tail_idx;  // row of x >= max
   FP tail_xx;    // max - start of that row
+  int nrow;
   const FP* em_x;
   long long ldx_i;
   int ldx_j;
   const FP* em;
   long long ldem_i;
   const FP* two;  // [nloc][nnei][M] or null
-  int nloc, nnei, M, Mpad, is_sorted, accumulate, vec_ok;
+  int nloc, nnei, M, is_sorted, accumulate, vec_ok;
+  int Mc;  // channels per CTA slice (forward: gridDim.y slices; backward: Mc == M)
+  int H;   // hot rows kept in shared memory
+  int hot_elems;  // H*Mc*6 rounded up to a 16-byte boundary (start of the per-warp records)
   // forward / second order
   FP* out;  // [nloc][4][M]
   const FP* dz_x;
@@ -67,28 +78,6 @@ struct alignas(16) RecGG {  // second order only: dz_dy_dem[4], dz_dy_dem_x of t
   FP zx;
   FP pad_;
 };
-
-// [row][M][6] -> [row][6][Mpad]
-template <typename FP>
-__global__ void k_table_relayout(FP* __restrict__ T, const FP* __restrict__ table, long long nrow,
-                                 int M, int Mpad) {
-  const long long n = nrow * 6 * (long long)Mpad;
-  for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < n;
-       e += (long long)gridDim.x * blockDim.x) {
-    const int k = (int)(e % Mpad);
-    const long long rp = e / Mpad;
-    const int pp = (int)(rp % 6);
-    const long long r = rp / 6;
-    T[e] = k < M ? table[(r * M + k) * 6 + pp] : (FP)0.;
-  }
-}
-
-template <typename FP>
-__global__ void k_zero(FP* __restrict__ p, long long n) {
-  for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < n;
-       e += (long long)gridDim.x * blockDim.x)
-    p[e] = (FP)0.;
-}
 
 // tabulate.cc:45-73
 template <typename FP>
@@ -126,6 +115,69 @@ __device__ __forceinline__ void load4(const double* q, bool vec, double (&e)[4])
     e[0] = a.x, e[1] = a.y, e[2] = b.x, e[3] = b.y;
   } else {
     e[0] = q[0], e[1] = q[1], e[2] = q[2], e[3] = q[3];
+  }
+}
+
+// the 6 coefficients of one (row, channel): 48 B (3 x 16 B) in fp64, 24 B (3 x 8 B) in fp32
+__device__ __forceinline__ void load6(const double* q, double (&a)[6]) {
+  const double2 u = *reinterpret_cast<const double2*>(q);
+  const double2 v = *reinterpret_cast<const double2*>(q + 2);
+  const double2 w = *reinterpret_cast<const double2*>(q + 4);
+  a[0] = u.x, a[1] = u.y, a[2] = v.x, a[3] = v.y, a[4] = w.x, a[5] = w.y;
+}
+__device__ __forceinline__ void load6(const float* q, float (&a)[6]) {
+  const float2 u = *reinterpret_cast<const float2*>(q);
+  const float2 v = *reinterpret_cast<const float2*>(q + 2);
+  const float2 w = *reinterpret_cast<const float2*>(q + 4);
+  a[0] = u.x, a[1] = u.y, a[2] = v.x, a[3] = v.y, a[4] = w.x, a[5] = w.y;
+}
+__device__ __forceinline__ void load6_g(const double* q, double (&a)[6]) {
+  const double2 u = __ldg(reinterpret_cast<const double2*>(q));
+  const double2 v = __ldg(reinterpret_cast<const double2*>(q + 2));
+  const double2 w = __ldg(reinterpret_cast<const double2*>(q + 4));
+  a[0] = u.x, a[1] = u.y, a[2] = v.x, a[3] = v.y, a[4] = w.x, a[5] = w.y;
+}
+__device__ __forceinline__ void load6_g(const float* q, float (&a)[6]) {
+  const float2 u = __ldg(reinterpret_cast<const float2*>(q));
+  const float2 v = __ldg(reinterpret_cast<const float2*>(q + 2));
+  const float2 w = __ldg(reinterpret_cast<const float2*>(q + 4));
+  a[0] = u.x, a[1] = u.y, a[2] = v.x, a[3] = v.y, a[4] = w.x, a[5] = w.y;
+}
+
+// Coefficients of (row, slice channel kk): shared-memory window [r0, r0+H) or the global table.
+template <typename FP>
+__device__ __forceinline__ void fetch_coef(FP (&a)[6], const FP* __restrict__ hot, const FP* __restrict__ table,
+                                           int row, int r0, int H, int Mc, int M, int c0, int kk) {
+  const unsigned rel = (unsigned)(row - r0);
+  if (rel < (unsigned)H) {
+    load6(hot + ((size_t)rel * Mc + kk) * 6, a);
+  } else {
+    load6_g(table + ((long long)row * M + c0 + kk) * 6, a);
+  }
+}
+
+// First row of the hot window: the row of the last slot of atom 0 (padding or the farthest
+// neighbour: the crowded end of the table) minus a small margin; every CTA picks the same one.
+template <typename FP>
+__device__ __forceinline__ int hot_window_start(const TabParams<FP>& p) {
+  FP xx, dl;
+  int idx;
+  locate(p, p.em_x[(long long)(p.nnei - 1) * p.ldx_j], xx, idx, dl);
+  int r0 = idx - 8;
+  if (r0 > p.nrow - p.H) r0 = p.nrow - p.H;
+  if (r0 < 0) r0 = 0;
+  return r0;
+}
+
+// Cooperative preload of rows [r0, r0+H) x channels [c0, c0+mc) into hot[H][Mc][6].
+template <typename FP>
+__device__ __forceinline__ void preload_hot(FP* __restrict__ hot, const TabParams<FP>& p, int r0, int c0, int mc) {
+  const int per_row = mc * 6;
+  const long long n = (long long)p.H * per_row;
+  for (long long e = threadIdx.x; e < n; e += blockDim.x) {
+    const int r = (int)(e / per_row);
+    const int q = (int)(e - (long long)r * per_row);
+    hot[(size_t)r * p.Mc * 6 + q] = __ldg(p.table + ((long long)(r0 + r) * p.M + c0) * 6 + q);
   }
 }
 
@@ -170,23 +222,42 @@ __device__ __forceinline__ int stage_chunk(const TabParams<FP>& p, long long i, 
   return nproc;
 }
 
+template <typename FP>
+__device__ __forceinline__ FP poly(const FP (&a)[6], FP x) {
+  return a[0] + (a[1] + (a[2] + (a[3] + (a[4] + a[5] * x) * x) * x) * x) * x;
+}
+template <typename FP>
+__device__ __forceinline__ FP dpoly(const FP (&a)[6], FP x) {
+  return a[1] + ((FP)2. * a[2] + ((FP)3. * a[3] + ((FP)4. * a[4] + (FP)5. * a[5] * x) * x) * x) * x;
+}
+
+extern __shared__ __align__(16) unsigned char tab_smem[];
+
 // ------------------------------------------------------------------------------------------
 // forward (GG=false) and second-order backward (GG=true): both accumulate a [4][M] tile.
+// grid (x: persistent over atoms, y: channel slice); block = nw warps.
+// smem: hot[H][Mc][6] | Rec[nw][32] | RecGG[nw][32] (GG only)
 // ------------------------------------------------------------------------------------------
 template <typename FP, int NC, bool TWO, bool GG>
-__global__ void __launch_bounds__(128) k_tab_fwd(const __grid_constant__ TabParams<FP> p) {
-  __shared__ Rec<FP> rec_all[4][32];
-  __shared__ RecGG<FP> rgg_all[GG ? 4 : 1][GG ? 32 : 1];
+__global__ void __launch_bounds__(512) k_tab_fwd(const __grid_constant__ TabParams<FP> p) {
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
-  Rec<FP>* rec = rec_all[warp];
-  RecGG<FP>* rgg = rgg_all[GG ? warp : 0];
-  const int nkb = (p.M + 32 * NC - 1) / (32 * NC);
-  const long long nwork = (long long)p.nloc * nkb;
-  const int Mpad = p.Mpad;
-  for (long long w = (long long)blockIdx.x * 4 + warp; w < nwork; w += (long long)gridDim.x * 4) {
-    const long long i = w / nkb;
-    const int kb = (int)(w - i * nkb) * 32 * NC;
+  const int nw = blockDim.x >> 5;
+  FP* hot = reinterpret_cast<FP*>(tab_smem);
+  Rec<FP>* rec = reinterpret_cast<Rec<FP>*>(hot + p.hot_elems) + warp * 32;
+  RecGG<FP>* rgg = reinterpret_cast<RecGG<FP>*>(reinterpret_cast<Rec<FP>*>(hot + p.hot_elems) + nw * 32) +
+                   (GG ? warp * 32 : 0);
+  const int c0 = blockIdx.y * p.Mc;
+  const int mc = (p.M - c0) < p.Mc ? (p.M - c0) : p.Mc;
+  const int r0 = hot_window_start(p);
+  preload_hot(hot, p, r0, c0, mc);
+  __syncthreads();
+
+  bool act[NC];
+#pragma unroll
+  for (int c = 0; c < NC; ++c) act[c] = lane + 32 * c < mc;
+
+  for (long long i = (long long)blockIdx.x * nw + warp; i < p.nloc; i += (long long)gridDim.x * nw) {
     FP acc[4][NC];
 #pragma unroll
     for (int m = 0; m < 4; ++m)
@@ -207,14 +278,9 @@ __global__ void __launch_bounds__(128) k_tab_fwd(const __grid_constant__ TabPara
         const int row = r.idx;
         if (row != cur_row) {  // warp-uniform
           cur_row = row;
-          const FP* __restrict__ tr = p.T + (long long)row * 6 * Mpad + kb + lane;
 #pragma unroll
-          for (int c = 0; c < NC; ++c) {
-            if (kb + lane + 32 * c < p.M) {
-#pragma unroll
-              for (int q = 0; q < 6; ++q) a[c][q] = __ldg(tr + q * Mpad + 32 * c);
-            }
-          }
+          for (int c = 0; c < NC; ++c)
+            if (act[c]) fetch_coef(a[c], hot, p.table, row, r0, p.H, p.Mc, p.M, c0, lane + 32 * c);
         }
         const FP xx = r.xx;
         const FP dl = r.delta;
@@ -229,29 +295,28 @@ __global__ void __launch_bounds__(128) k_tab_fwd(const __grid_constant__ TabPara
           for (int m = 0; m < 4; ++m) h[m] = rgg[jj].h[m] * mult;
           zx = rgg[jj].zx;
         }
-        const long long two_off = ((i * p.nnei + j0 + jj) * (long long)p.M) + kb + lane;
+        const long long two_off = ((i * p.nnei + j0 + jj) * (long long)p.M) + c0 + lane;
 #pragma unroll
         for (int c = 0; c < NC; ++c) {
-          FP g = a[c][0] + (a[c][1] + (a[c][2] + (a[c][3] + (a[c][4] + a[c][5] * xx) * xx) * xx) * xx) * xx;
+          FP g = poly(a[c], xx);
           FP gd = (FP)0.;
           if (GG || dl != (FP)0.) {
-            gd = a[c][1] + ((FP)2. * a[c][2] + ((FP)3. * a[c][3] + ((FP)4. * a[c][4] + (FP)5. * a[c][5] * xx) * xx) * xx) * xx;
+            gd = dpoly(a[c], xx);
             g += gd * dl;
           }
-          const bool kin = kb + lane + 32 * c < p.M;
           if (GG) {
             FP two_grad = (FP)0.;
-            if (TWO && kin) {
+            if (TWO && act[c]) {
               const FP t = p.two[two_off + 32 * c];
               two_grad = p.dz_two[two_off + 32 * c] * g;
               g += g * t;
               gd += gd * t;
             }
-            const FP s = zx * gd + two_grad;
+            const FP sgl = zx * gd + two_grad;
 #pragma unroll
-            for (int m = 0; m < 4; ++m) acc[m][c] += g * h[m] + s * e[m];
+            for (int m = 0; m < 4; ++m) acc[m][c] += g * h[m] + sgl * e[m];
           } else {
-            if (TWO && kin) {
+            if (TWO && act[c]) {
               const FP t = p.two[two_off + 32 * c];
               g = g * t + g;
             }
@@ -261,10 +326,10 @@ __global__ void __launch_bounds__(128) k_tab_fwd(const __grid_constant__ TabPara
         }
       }
     }
-    FP* __restrict__ o = p.out + i * 4 * (long long)p.M + kb + lane;
+    FP* __restrict__ o = p.out + i * 4 * (long long)p.M + c0 + lane;
 #pragma unroll
     for (int c = 0; c < NC; ++c) {
-      if (kb + lane + 32 * c < p.M) {
+      if (act[c]) {
 #pragma unroll
         for (int m = 0; m < 4; ++m) {
           FP* q = o + (long long)m * p.M + 32 * c;
@@ -312,16 +377,20 @@ __device__ __forceinline__ FP reduce_scatter8(FP (&v)[8], int lane) {
   return r;
 }
 
+// block = nw warps, one warp per atom; smem: hot[H][M][6] | Rec[nw][32]
 template <typename FP, int NC, bool TWO>
-__global__ void __launch_bounds__(128, 3) k_tab_grad(const __grid_constant__ TabParams<FP> p) {
-  __shared__ Rec<FP> rec_all[4][32];
+__global__ void __launch_bounds__(384) k_tab_grad(const __grid_constant__ TabParams<FP> p) {
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
-  Rec<FP>* rec = rec_all[warp];
-  const int Mpad = p.Mpad;
+  const int nw = blockDim.x >> 5;
+  FP* hot = reinterpret_cast<FP*>(tab_smem);
+  Rec<FP>* rec = reinterpret_cast<Rec<FP>*>(hot + p.hot_elems) + warp * 32;
   const int M = p.M;
+  const int r0 = hot_window_start(p);
+  preload_hot(hot, p, r0, 0, M);
+  __syncthreads();
   const bool single = M <= 32 * NC;
-  for (long long i = (long long)blockIdx.x * 4 + warp; i < p.nloc; i += (long long)gridDim.x * 4) {
+  for (long long i = (long long)blockIdx.x * nw + warp; i < p.nloc; i += (long long)gridDim.x * nw) {
     const FP* __restrict__ dyi = p.dy + i * 4 * (long long)M;
     FP dyr[4][NC];
     if (single) {
@@ -360,7 +429,7 @@ __global__ void __launch_bounds__(128, 3) k_tab_grad(const __grid_constant__ Tab
               d2 = kin ? dyi[2ll * M + k] : (FP)0.;
               d3 = kin ? dyi[3ll * M + k] : (FP)0.;
             }
-            FP a0 = 0, a1 = 0, a2 = 0, a3 = 0, a4 = 0, a5 = 0;
+            FP a[6] = {(FP)0., (FP)0., (FP)0., (FP)0., (FP)0., (FP)0.};
             int cur_row = -1;
 #pragma unroll
             for (int u = 0; u < 8; ++u) {
@@ -368,19 +437,11 @@ __global__ void __launch_bounds__(128, 3) k_tab_grad(const __grid_constant__ Tab
                 const Rec<FP>& r = rec[b + u];
                 if (r.idx != cur_row) {
                   cur_row = r.idx;
-                  if (kin) {
-                    const FP* __restrict__ tr = p.T + (long long)cur_row * 6 * Mpad + k;
-                    a0 = __ldg(tr);
-                    a1 = __ldg(tr + Mpad);
-                    a2 = __ldg(tr + 2 * Mpad);
-                    a3 = __ldg(tr + 3 * Mpad);
-                    a4 = __ldg(tr + 4 * Mpad);
-                    a5 = __ldg(tr + 5 * Mpad);
-                  }
+                  if (kin) fetch_coef(a, hot, p.table, cur_row, r0, p.H, p.Mc, M, 0, k);
                 }
                 const FP xx = r.xx;
-                FP gd = a1 + ((FP)2. * a2 + ((FP)3. * a3 + ((FP)4. * a4 + (FP)5. * a5 * xx) * xx) * xx) * xx;
-                FP g = a0 + (a1 + (a2 + (a3 + (a4 + a5 * xx) * xx) * xx) * xx) * xx + gd * r.delta;
+                FP gd = dpoly(a, xx);
+                FP g = poly(a, xx) + gd * r.delta;
                 const FP dot = r.e[0] * d0 + r.e[1] * d1 + r.e[2] * d2 + r.e[3] * d3;
                 if (TWO) {
                   if (kin) {
@@ -433,14 +494,10 @@ __global__ void __launch_bounds__(128, 3) k_tab_grad(const __grid_constant__ Tab
 // ------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------
-template <typename FP>
-struct TabHost {
-  long long nrow;
-  int Mpad;
-};
+constexpr size_t kSmemBudget = 225 * 1024;
 
 template <typename FP>
-int fill_info(TabParams<FP>& p, const FP* info, int M, long long& nrow) {
+int fill_info(TabParams<FP>& p, const FP* info, int M) {
   DPB_REQUIRE(info != nullptr, "tabulate: table_info is null (it must be a HOST pointer)");
   p.lower = info[0];
   p.upper = info[1];
@@ -454,31 +511,19 @@ int fill_info(TabParams<FP>& p, const FP* info, int M, long long& nrow) {
   const FP edge = std::nextafter(p.vmax, p.lower);
   p.tail_idx = p.first + (int)((edge - p.upper) / p.s1);
   p.tail_xx = p.vmax - ((FP)(p.tail_idx - p.first) * p.s1 + p.upper);
-  nrow = (long long)p.tail_idx + 1;
+  p.nrow = p.tail_idx + 1;
   p.M = M;
-  p.Mpad = (M + 31) / 32 * 32;
-  return DPB200_OK;
-}
-
-template <typename FP>
-int prepare_table(TabParams<FP>& p, const FP* table, long long nrow, FP** scratch, cudaStream_t st) {
-  const size_t bytes = (size_t)nrow * 6 * p.Mpad * sizeof(FP);
-  DPB_CUDA(cudaMallocAsync((void**)scratch, bytes, st));
-  const long long n = nrow * 6 * (long long)p.Mpad;
-  int grid = ceil_div(n, 256);
-  const int cap = sm_count() * 8;
-  if (grid > cap) grid = cap;
-  k_table_relayout<FP><<<grid, 256, 0, st>>>(*scratch, table, nrow, p.M, p.Mpad);
-  p.T = *scratch;
   return DPB200_OK;
 }
 
 inline bool aligned16(const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15) == 0; }
 
 template <typename FP>
-int common_args(TabParams<FP>& p, const FP* em_x, long long ldx_i, int ldx_j, const FP* em,
+int common_args(TabParams<FP>& p, const FP* table, const FP* em_x, long long ldx_i, int ldx_j, const FP* em,
                 long long ldem_i, const FP* two, int nloc, int nnei, int is_sorted) {
-  DPB_REQUIRE(em_x != nullptr && em != nullptr, "tabulate: em_x / em are null");
+  DPB_REQUIRE(table != nullptr && em_x != nullptr && em != nullptr, "tabulate: table / em_x / em are null");
+  DPB_REQUIRE(aligned16(table), "tabulate: table must be 16-byte aligned");
+  p.table = table;
   p.em_x = em_x;
   p.ldx_i = ldx_i;
   p.ldx_j = ldx_j;
@@ -492,15 +537,20 @@ int common_args(TabParams<FP>& p, const FP* em_x, long long ldx_i, int ldx_j, co
   return DPB200_OK;
 }
 
-// Persistent launch shape: min(work, SMs x resident CTAs) CTAs of 4 warps.
-template <typename K>
-int persistent_grid(K kern, long long nwarps_needed) {
-  int occ = 0;
-  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, 128, 0) != cudaSuccess || occ < 1) occ = 1;
-  long long want = (nwarps_needed + 3) / 4;
-  long long cap = (long long)sm_count() * occ;
-  if (want < 1) want = 1;
-  return (int)(want < cap ? want : cap);
+// hot rows that fit beside the per-warp records
+template <typename FP>
+int hot_rows(int nrow, int Mc, size_t other_bytes) {
+  const size_t row_bytes = (size_t)Mc * 6 * sizeof(FP);
+  if (other_bytes + row_bytes > kSmemBudget) return 0;
+  long long h = (long long)((kSmemBudget - other_bytes) / row_bytes);
+  return (int)(h < nrow ? h : nrow);
+}
+
+template <typename FP>
+int hot_elems_aligned(int H, int Mc) {
+  const long long per16 = 16 / sizeof(FP);
+  const long long n = (long long)H * Mc * 6;
+  return (int)((n + per16 - 1) / per16 * per16);
 }
 
 template <typename FP, bool GG>
@@ -515,12 +565,10 @@ int launch_fwd(FP* out, const FP* table, const FP* info, const FP* em_x, long lo
     if (!accumulate) DPB_CUDA(cudaMemsetAsync(out, 0, sizeof(FP) * (size_t)nloc * 4 * M, st));
     return DPB200_OK;
   }
-  DPB_REQUIRE(table != nullptr, "tabulate: table is null");
   TabParams<FP> p = {};
-  long long nrow = 0;
-  int rc = fill_info(p, info, M, nrow);
+  int rc = fill_info(p, info, M);
   if (rc) return rc;
-  rc = common_args(p, em_x, ldx_i, ldx_j, em, ldem_i, two, nloc, nnei, is_sorted);
+  rc = common_args(p, table, em_x, ldx_i, ldx_j, em, ldem_i, two, nloc, nnei, is_sorted);
   if (rc) return rc;
   p.out = out;
   p.accumulate = accumulate;
@@ -532,32 +580,46 @@ int launch_fwd(FP* out, const FP* table, const FP* info, const FP* em_x, long lo
     DPB_REQUIRE(aligned16(dz_em), "tabulate grad_grad: dz_dy_dem must be 16-byte aligned");
     DPB_REQUIRE(two == nullptr || dz_two != nullptr, "tabulate grad_grad: dz_dy_dtwo is null");
   }
-  FP* scratch = nullptr;
-  rc = prepare_table(p, table, nrow, &scratch, st);
-  if (rc) return rc;
+  // channel slicing: the smallest number of slices whose shared-memory window reaches ~150 rows
+  const int nw = 16;
+  const size_t rec_bytes = (size_t)nw * 32 * (sizeof(Rec<FP>) + (GG ? sizeof(RecGG<FP>) : 0));
+  int S = (M + 127) / 128, Mc = 0, H = 0;
+  for (;; S *= 2) {
+    Mc = (M + S - 1) / S;
+    H = hot_rows<FP>(p.nrow, Mc, rec_bytes);
+    if (H >= (p.nrow < 150 ? p.nrow : 150) || Mc <= 32) break;
+  }
+  S = (M + Mc - 1) / Mc;
+  p.Mc = Mc;
+  p.H = H;
+  p.hot_elems = hot_elems_aligned<FP>(H, Mc);
+  const size_t smem = (size_t)p.hot_elems * sizeof(FP) + rec_bytes;
   const bool tw = two != nullptr;
-#define DPB_LAUNCH_FWD(NC)                                                                       \
-  do {                                                                                           \
-    const int nkb = (M + 32 * NC - 1) / (32 * NC);                                               \
-    if (tw) {                                                                                    \
-      auto kern = k_tab_fwd<FP, NC, true, GG>;                                                   \
-      kern<<<persistent_grid(kern, (long long)nloc * nkb), 128, 0, st>>>(p);                     \
-    } else {                                                                                     \
-      auto kern = k_tab_fwd<FP, NC, false, GG>;                                                  \
-      kern<<<persistent_grid(kern, (long long)nloc * nkb), 128, 0, st>>>(p);                     \
-    }                                                                                            \
+  const int nc = Mc <= 32 ? 1 : (Mc <= 64 ? 2 : 4);
+  long long want = ((long long)nloc + nw - 1) / nw;
+  const long long cap = (sm_count() + S - 1) / S > 0 ? (long long)((sm_count() + S - 1) / S) : 1;
+  dim3 grid((unsigned)(want < cap ? want : cap), (unsigned)S);
+#define DPB_LAUNCH_FWD(NC)                                                                          \
+  do {                                                                                              \
+    if (tw) {                                                                                       \
+      auto kern = k_tab_fwd<FP, NC, true, GG>;                                                      \
+      DPB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+      kern<<<grid, nw * 32, smem, st>>>(p);                                                         \
+    } else {                                                                                        \
+      auto kern = k_tab_fwd<FP, NC, false, GG>;                                                     \
+      DPB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+      kern<<<grid, nw * 32, smem, st>>>(p);                                                         \
+    }                                                                                               \
   } while (0)
-  if (M <= 32)
+  if (nc == 1)
     DPB_LAUNCH_FWD(1);
-  else if (M <= 64)
+  else if (nc == 2)
     DPB_LAUNCH_FWD(2);
   else
     DPB_LAUNCH_FWD(4);
 #undef DPB_LAUNCH_FWD
-  cudaError_t e = cudaGetLastError();
-  cudaFreeAsync(scratch, st);
-  DPB_CUDA(e);
-  note_launches(2);
+  DPB_CUDA(cudaGetLastError());
+  note_launches(1);
   return DPB200_OK;
 }
 
@@ -568,31 +630,38 @@ int launch_grad(FP* dy_dem_x, FP* dy_dem, FP* dy_dtwo, const FP* table, const FP
                 cudaStream_t st) {
   DPB_REQUIRE(nloc >= 0 && nnei >= 0 && M >= 0, "tabulate grad: negative size");
   if (nloc == 0 || nnei == 0) return DPB200_OK;  // tabulate.cc: nothing to write
-  DPB_REQUIRE(dy_dem != nullptr && dy != nullptr && table != nullptr, "tabulate grad: null pointer");
+  DPB_REQUIRE(dy_dem != nullptr && dy != nullptr, "tabulate grad: null pointer");
   DPB_REQUIRE(two == nullptr || dy_dtwo != nullptr, "tabulate grad: dy_dtwo is null");
   TabParams<FP> p = {};
-  long long nrow = 0;
-  int rc = fill_info(p, info, M, nrow);
+  int rc = fill_info(p, info, M);
   if (rc) return rc;
-  rc = common_args(p, em_x, ldx_i, ldx_j, em, ldem_i, two, nloc, nnei, is_sorted);
+  rc = common_args(p, table, em_x, ldx_i, ldx_j, em, ldem_i, two, nloc, nnei, is_sorted);
   if (rc) return rc;
   p.dy = dy;
   p.dy_dem_x = dy_dem_x;
   p.dy_dem = dy_dem;
   p.dy_dtwo = dy_dtwo;
-  FP* scratch = nullptr;
-  rc = prepare_table(p, table, nrow, &scratch, st);
-  if (rc) return rc;
+  const int nw = 12;
+  const size_t rec_bytes = (size_t)nw * 32 * sizeof(Rec<FP>);
+  p.Mc = M;
+  p.H = hot_rows<FP>(p.nrow, M, rec_bytes);
+  p.hot_elems = hot_elems_aligned<FP>(p.H, M);
+  const size_t smem = (size_t)p.hot_elems * sizeof(FP) + rec_bytes;
   const bool tw = two != nullptr;
-#define DPB_LAUNCH_GRAD(NC)                                           \
-  do {                                                                \
-    if (tw) {                                                         \
-      auto kern = k_tab_grad<FP, NC, true>;                           \
-      kern<<<persistent_grid(kern, nloc), 128, 0, st>>>(p);           \
-    } else {                                                          \
-      auto kern = k_tab_grad<FP, NC, false>;                          \
-      kern<<<persistent_grid(kern, nloc), 128, 0, st>>>(p);           \
-    }                                                                 \
+  long long want = ((long long)nloc + nw - 1) / nw;
+  const long long cap = sm_count();
+  const int grid = (int)(want < cap ? want : cap);
+#define DPB_LAUNCH_GRAD(NC)                                                                         \
+  do {                                                                                              \
+    if (tw) {                                                                                       \
+      auto kern = k_tab_grad<FP, NC, true>;                                                         \
+      DPB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+      kern<<<grid, nw * 32, smem, st>>>(p);                                                         \
+    } else {                                                                                        \
+      auto kern = k_tab_grad<FP, NC, false>;                                                        \
+      DPB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+      kern<<<grid, nw * 32, smem, st>>>(p);                                                         \
+    }                                                                                               \
   } while (0)
   if (M <= 32)
     DPB_LAUNCH_GRAD(1);
@@ -601,10 +670,8 @@ int launch_grad(FP* dy_dem_x, FP* dy_dem, FP* dy_dtwo, const FP* table, const FP
   else
     DPB_LAUNCH_GRAD(4);
 #undef DPB_LAUNCH_GRAD
-  cudaError_t e = cudaGetLastError();
-  cudaFreeAsync(scratch, st);
-  DPB_CUDA(e);
-  note_launches(2);
+  DPB_CUDA(cudaGetLastError());
+  note_launches(1);
   return DPB200_OK;
 }
 

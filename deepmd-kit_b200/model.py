@@ -7,7 +7,7 @@ descriptor algebra of deepmd/pt/model/descriptor/se_a.py:838-850):
     [every `nlist_every` steps] normalize_coord -> copy_coord (ghost images) -> build_nlist(rcut+skin)
     prod_env_mat_a (format with the true rcut + env-mat)      -> em, em_deriv, rij, nlist
     tabulate_fusion_se_a over the type sections               -> xyz_scatter [nloc,4,M]
-    /nnei, GR^T GR[:, :axis], fitting net, dE/d(xyz_scatter)  (torch GEMMs; SURVEY 8f-1 "next")
+    se_a_descriptor: (GR/nnei)^T (GR/nnei)[:, :axis]; fitting net fwd + hand-written bwd (cuBLAS GEMMs)
     tabulate_fusion_se_a_grad over the type sections          -> net_deriv = dE/d(em)
     use_nlist_map (ghost -> owner)                            -> prod_force_a + prod_virial_a
 
@@ -100,6 +100,36 @@ class FittingNet:
             x = y
         return torch.addmm(self.head[1], x, self.head[0]).reshape(-1)
 
+    @torch.no_grad()
+    def forward_backward(self, x: torch.Tensor):
+        """Atomic energies e[n] and dE/dx[n, dim_in] with a hand-written backward: six GEMMs and a few
+        in-place elementwise passes over [n, width] (no autograd graph, no saved [n, dim_in] copies)."""
+        acts = []
+        h = x
+        for w, b, idt in self.layers:
+            a = torch.addmm(b, h, w).tanh_()
+            y = a * idt if idt is not None else a.clone()
+            if w.shape[0] == w.shape[1]:
+                y.add_(h)
+            elif w.shape[1] == 2 * w.shape[0]:
+                y.add_(torch.cat([h, h], 1))
+            acts.append(a)
+            h = y
+        e = torch.addmv(self.head[1], h, self.head[0][:, 0])
+        g = self.head[0][:, 0].unsqueeze(0).expand(x.shape[0], -1)
+        for (w, b, idt), a in zip(reversed(self.layers), reversed(acts)):
+            t = a.mul(a).neg_().add_(1.0).mul_(g)  # g * (1 - tanh^2)
+            if idt is not None:
+                t.mul_(idt)
+            gin = t @ w.t()
+            if w.shape[0] == w.shape[1]:
+                gin.add_(g)
+            elif w.shape[1] == 2 * w.shape[0]:
+                n_in = w.shape[0]
+                gin.add_(g[:, :n_in]).add_(g[:, n_in:])
+            g = gin
+        return e, g
+
 
 class SeAModel:
     """Random-init compressed se_e2_a model (weights of the named architecture, tabulated with the
@@ -131,7 +161,8 @@ class SeAModel:
                     for t in range(cfg.ntypes)]
         self.fit_chunk = 1 << 17
 
-    # -- descriptor algebra + fitting net: torch GEMMs (library code; not one of the named kernels)
+    # -- descriptor contraction (dpb200 kernels) + fitting net (cuBLAS GEMMs through torch, hand-written
+    #    backward).  The fitting net is library code here; SURVEY 8f-1 lists its fusion as the next item.
     def energy_and_dy(self, xyz: torch.Tensor, type_perm: torch.Tensor, type_ranges):
         """xyz: [nloc,4,M] raw tabulate output. Returns (E_total, atom_energy[nloc], dE/d(xyz))."""
         cfg = self.cfg
@@ -143,14 +174,13 @@ class SeAModel:
             for c0 in range(a, b, self.fit_chunk):
                 c1 = min(b, c0 + self.fit_chunk)
                 idx = type_perm[c0:c1]
-                with torch.enable_grad():
-                    x = xyz.index_select(0, idx).requires_grad_(True)
-                    xs = x * inv
-                    d = torch.matmul(xs.permute(0, 2, 1), xs[:, :, :cfg.axis_neuron]).reshape(c1 - c0, -1)
-                    e = self.fit[t](d)
-                    (g,) = torch.autograd.grad(e.sum(), x)
+                x = xyz.index_select(0, idx)
+                d = ops.se_a_descriptor(x, cfg.axis_neuron, inv)
+                e, gd = self.fit[t].forward_backward(d)
+                del d
+                g = ops.se_a_descriptor_grad(gd, x, cfg.axis_neuron, inv)
                 dy.index_copy_(0, idx, g)
-                e_atom.index_copy_(0, idx, e.detach())
+                e_atom.index_copy_(0, idx, e)
         return e_atom.sum(), e_atom, dy
 
     def evaluate(self, ext_coord, ext_type, numneigh, rows, mapping, nloc, type_perm, type_ranges, atom_virial=False,

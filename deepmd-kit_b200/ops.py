@@ -442,6 +442,28 @@ def use_nlist_map(nlist, mapping):
     return nlist
 
 
+def se_a_descriptor(gr, axis, scale):
+    """D = (gr*scale)^T (gr*scale)[:, :axis] per atom: [n,4,M] -> [n, M*axis] (dpb200_se_a_descriptor)."""
+    dev = _need_cuda(("gr", gr))
+    s = _suffix(gr)
+    gr = _c(gr)
+    n, _, M = gr.shape
+    out = torch.empty((n, M * int(axis)), dtype=gr.dtype, device=dev)
+    lib().call("se_a_descriptor_" + s, _p(out), _p(gr), n, M, int(axis), float(scale), _stream(dev))
+    return out
+
+
+def se_a_descriptor_grad(dD, gr, axis, scale):
+    """dE/d(gr) [n,4,M] from dE/dD [n, M*axis] (dpb200_se_a_descriptor_grad)."""
+    dev = _need_cuda(("dD", dD), ("gr", gr))
+    s = _suffix(gr)
+    gr, dD = _c(gr), _c(dD, gr.dtype)
+    n, _, M = gr.shape
+    out = torch.empty_like(gr)
+    lib().call("se_a_descriptor_grad_" + s, _p(out), _p(dD), _p(gr), n, M, int(axis), float(scale), _stream(dev))
+    return out
+
+
 def halo_pack(coord, sendlist, shift):
     """sendbuf[k] = coord[sendlist[k]] + shift[k] (dpb200_halo_pack)."""
     dev = _need_cuda(("coord", coord), ("sendlist", sendlist), ("shift", shift))

@@ -208,6 +208,21 @@ DPB200_DECL_HALO(f64, double)
 DPB200_DECL_HALO(f32, float)
 #undef DPB200_DECL_HALO
 
+/* ---------------------------------------------------------------------------------------
+ * se_e2_a descriptor contraction  D[i] = (gr[i]*scale)^T (gr[i]*scale)[:, :axis]  and its backward
+ * (deepmd/pt/model/descriptor/se_a.py:843-850: xyz_scatter /= nnei; matmul(xyz_scatter_1,
+ * xyz_scatter_2)).  gr [nloc][4][M] = summed tabulate output, scale = 1/nnei, D [nloc][M*axis],
+ * dgr [nloc][4][M] = dE/d(gr) given dD = dE/dD.
+ * ------------------------------------------------------------------------------------- */
+#define DPB200_DECL_DESC(SUF, FP)                                                                       \
+  int dpb200_se_a_descriptor_##SUF(FP* D, const FP* gr, long long nloc, int M, int axis, double scale,  \
+                                   dpb200_stream_t stream);                                             \
+  int dpb200_se_a_descriptor_grad_##SUF(FP* dgr, const FP* dD, const FP* gr, long long nloc, int M,     \
+                                        int axis, double scale, dpb200_stream_t stream);
+DPB200_DECL_DESC(f64, double)
+DPB200_DECL_DESC(f32, float)
+#undef DPB200_DECL_DESC
+
 /* use_nlist_map (neighbor_list.h:219-222): nlist[k] = map[nlist[k]] for entries >= 0. */
 int dpb200_use_nlist_map(int* nlist, const int* nlist_map, int nloc, int nnei, dpb200_stream_t stream);
 

@@ -36,6 +36,26 @@ def _reference_lists(lib, ext_c, ext_t, nloc, rc_list):
     return lib.build_nlist(ext_c, nloc, rc_list, atype=ext_t)
 
 
+def reference_energy_and_dy(model, xyz, perm, ranges):
+    """Descriptor algebra + fitting net exactly as the reference's PyTorch backend writes them
+    (deepmd/pt/model/descriptor/se_a.py:843-850: xyz_scatter /= nnei; matmul(xyz_scatter_1,
+    xyz_scatter_2); per-type fitting MLP with resnet_dt, deepmd/pt/model/network/mlp.py), with
+    dE/d(xyz_scatter) from torch.autograd.  Plain torch on the CPU: the checker for the dpb200
+    descriptor kernels and the hand-written MLP backward."""
+    cfg = model.cfg
+    x = xyz.detach().clone().requires_grad_(True)
+    xs = x / cfg.nnei
+    d = torch.matmul(xs.permute(0, 2, 1), xs[:, :, :cfg.axis_neuron]).reshape(x.shape[0], -1)
+    e_atom = torch.zeros(x.shape[0], dtype=x.dtype)
+    for t, (a, b) in enumerate(ranges):
+        idx = perm[a:b]
+        if idx.numel():
+            e_atom = e_atom.index_add(0, idx, model.fit[t](d.index_select(0, idx)))
+    energy = e_atom.sum()
+    (dy,) = torch.autograd.grad(energy, x)
+    return energy.detach(), e_atom.detach(), dy
+
+
 def evaluate(lib, model, lists, timings=None):
     """One force evaluation. `model` is a deepmd_kit_b200.model.SeAModel living on the CPU (only its
     weights, tables and torch fitting net are used).  Returns (E, force[nloc,3], virial[9], extras)."""
@@ -76,7 +96,7 @@ def evaluate(lib, model, lists, timings=None):
     for c in cnt[:cfg.ntypes]:
         ranges.append((a0, a0 + int(c)))
         a0 += int(c)
-    energy, e_atom, dy = model.energy_and_dy(torch.as_tensor(xyz), perm, ranges)
+    energy, e_atom, dy = reference_energy_and_dy(model, torch.as_tensor(xyz), perm, ranges)
     dy = dy.numpy()
     tick("fitting_net", t0)
     t0 = time.perf_counter()

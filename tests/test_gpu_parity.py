@@ -529,3 +529,40 @@ def test_op_prod_env_mat_a_modes(ops, port, dtype):
     close(N(em2), w[0], dtype)
     close(N(dv2), w[1], dtype)
     close(N(rij2), w[2], dtype)
+
+
+# ------------------------------------------------------------------ descriptor contraction ----
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+@pytest.mark.parametrize("M,axis", [(100, 16), (8, 4), (33, 33)])
+def test_descriptor_contraction(ops, dtype, M, axis):
+    """dpb200_se_a_descriptor / _grad against the plain torch statement of
+    deepmd/pt/model/descriptor/se_a.py:843-850 (and autograd for the backward)."""
+    rng = np.random.default_rng(M)
+    n, nnei = 57, 138
+    tdt = torch.float64 if dtype == np.float64 else torch.float32
+    x = torch.as_tensor(rng.normal(size=(n, 4, M)).astype(dtype)).to(DEV).requires_grad_(True)
+    xs = x / nnei
+    want = torch.matmul(xs.permute(0, 2, 1), xs[:, :, :axis]).reshape(n, -1)
+    got = ops.se_a_descriptor(x.detach(), axis, 1.0 / nnei)
+    close(N(got), N(want), dtype, fac=4)
+    cot = torch.as_tensor(rng.normal(size=(n, M * axis)).astype(dtype)).to(DEV)
+    (wg,) = torch.autograd.grad(want, x, cot)
+    gg = ops.se_a_descriptor_grad(cot, x.detach(), axis, 1.0 / nnei)
+    close(N(gg), N(wg), dtype, fac=8)
+    assert got.dtype == tdt
+
+
+def test_fitting_forward_backward_matches_autograd():
+    import __graft_entry__ as g
+
+    g.load_package()
+    from deepmd_kit_b200.model import FittingNet
+
+    for dims, dt, tol in (((1600, (240, 240, 240)), torch.float64, 1e-12), ((64, (32, 64, 64)), torch.float32, 2e-5)):
+        f = FittingNet(dims[0], dims[1], True, 3, dt, DEV)
+        x = torch.randn(301, dims[0], dtype=dt, device=DEV, requires_grad=True)
+        e = f(x)
+        (ga,) = torch.autograd.grad(e.sum(), x)
+        e2, g2 = f.forward_backward(x.detach())
+        assert float((e - e2).abs().max()) <= tol * float(e.abs().max())
+        assert float((ga - g2).abs().max()) <= tol * float(ga.abs().max())
