@@ -124,6 +124,15 @@ def cpu_pipeline_timing(args, steps, warmup, seconds=None):
 
     kind = "reference" if ocpu.available("reference") else "port"
     lib = ocpu.CpuLib(kind)
+    # all host cores, also under torchrun (which exports OMP_NUM_THREADS=1 to its workers)
+    ncores = os.cpu_count() or 1
+    try:
+        import ctypes
+
+        ctypes.CDLL("libgomp.so.1").omp_set_num_threads(ncores)
+    except OSError:
+        pass
+    torch.set_num_threads(ncores)
     dtype = torch.float64 if args.dtype == "f64" else torch.float32
     np_dt = np.float64 if args.dtype == "f64" else np.float32
     cfg = SeAConfig()
@@ -186,7 +195,9 @@ def run_ours(args):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
+        import datetime
+
+        dist.init_process_group("nccl", device_id=dev, timeout=datetime.timedelta(seconds=180))
     pkg = g.load_package()
     from deepmd_kit_b200 import ops
     from deepmd_kit_b200.model import DeepPotB200, SeAConfig, SeAModel
@@ -278,9 +289,8 @@ def run_ours(args):
                "api": "DeepPotB200.eval(coords, cells, atom_types) — pinned host buffers, H2D + D2H inside the timed region"}
 
     # ---- per-kernel timing (instrumented pass, rank 0 reports) ---------------------------------
-    kernels, roofline = None, None
-    if rank == 0:
-        kernels, roofline = per_kernel(args, torch, ops, model, dp, step, L, dev, len(atype), esz)
+    # (every rank runs the instrumented steps -- they contain collectives -- rank 0 reports)
+    kernels, roofline = per_kernel(args, torch, ops, model, dp, step, L, dev, len(atype), esz)
 
     cpu_base = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -326,7 +336,8 @@ def per_kernel(args, torch, ops, model, dp, step, L, dev, nloc, esz):
     """CUDA-event time of every dpb200 operator inside the real step (events on the launching stream),
     and the roofline of each against measured peaks."""
     names = ["prod_env_mat_a", "tabulate_sections_fwd", "tabulate_sections_grad", "prod_force_virial_a", "use_nlist_map",
-             "normalize_coord", "copy_coord", "build_nlist"]
+             "normalize_coord", "copy_coord", "build_nlist", "se_a_descriptor", "se_a_descriptor_grad", "halo_pack",
+             "halo_unpack_add"]
     acc = {}
     orig = {}
 

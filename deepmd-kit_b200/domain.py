@@ -58,7 +58,8 @@ class HaloPlan:
     """Send lists per direction, receive segments, peers.  Device-agnostic (torch ops only) so the
     N>1 host logic is testable with the gloo backend on CPU."""
 
-    def __init__(self, coord: torch.Tensor, box, grid, rank, rc: float, group=None):
+    def __init__(self, coord: torch.Tensor, box, grid, rank, rc: float, group=None, slack: float = 0.0):
+        """`slack` (a length): how far outside its brick an owned atom may sit (half the skin)."""
         self.grid, self.rank, self.group = tuple(grid), rank, group
         self.world = grid[0] * grid[1] * grid[2]
         dev, dt = coord.device, coord.dtype
@@ -75,6 +76,12 @@ class HaloPlan:
                 raise ValueError(f"halo width {rc} exceeds the brick width along axis {d}: use fewer ranks on that axis")
         c = coord.reshape(-1, 3)
         s = c.to(torch.float64) @ torch.as_tensor(rec, device=dev)
+        if c.shape[0]:
+            tol = torch.as_tensor(slack / face + 1e-9, device=dev)
+            out = ((s < torch.as_tensor(lo, device=dev) - tol) | (s >= torch.as_tensor(hi, device=dev) + tol)).any()
+            if bool(out):
+                raise ValueError(f"rank {rank}: some atoms lie outside this rank's brick by more than {slack} "
+                                 "(atoms must be handed to the rank that owns them; there is no migration here)")
         lists, shifts, dests, srcs = [], [], [], []
         for (dx, dy, dz) in DIRS:
             m = torch.ones(c.shape[0], dtype=torch.bool, device=dev)
@@ -178,7 +185,7 @@ class DomainDeepPot(DeepPotB200):
         rc = m.cfg.rcut + self.skin
         c = coord.reshape(-1, 3)
         nloc = atype.numel()
-        self.plan = HaloPlan(c, box, self.grid, self.rank, rc, self.group)
+        self.plan = HaloPlan(c, box, self.grid, self.rank, rc, self.group, slack=0.5 * self.skin)
         ext_c = self.halo_forward(c)
         gt = torch.empty(self.plan.nghost, dtype=torch.int32, device=c.device)
         self.plan.exchange(atype.to(torch.int32).index_select(0, self.plan.sendlist.long()), gt)

@@ -14,13 +14,61 @@ sys.path.insert(0, ROOT)
 import __graft_entry__ as g  # noqa: E402
 
 
+def diagnose(dp, coord, atype, box, rank, world, cs, ts, rex, ref, off, dev):
+    """Where does the decomposed evaluation differ? ghost set vs brute force, per-atom energies."""
+    from deepmd_kit_b200.domain import rank_to_coords
+
+    nloc = len(atype)
+    c_d = torch.as_tensor(coord).to(dev)
+    ext = dp.halo_forward(c_d).cpu().numpy()
+    ext_t = dp.state.ext_type.cpu().numpy()
+    allc, allt = np.concatenate(cs), np.concatenate(ts)
+    L = np.diag(box)
+    me = np.array(rank_to_coords(rank, dp.grid))
+    lo, hi = me * L / np.array(dp.grid), (me + 1) * L / np.array(dp.grid)
+    rc = dp.model.cfg.rcut + dp.skin
+    want = []
+    for sx in (-1, 0, 1):
+        for sy in (-1, 0, 1):
+            for sz in (-1, 0, 1):
+                img = allc + np.array([sx, sy, sz]) * L
+                inside = np.all((img >= lo - rc) & (img < hi + rc), axis=1)
+                core = np.all((img >= lo) & (img < hi), axis=1)
+                sel = inside & ~core
+                want.append(np.concatenate([img[sel], allt[sel, None].astype(np.float64)], axis=1))
+    want = np.concatenate(want)
+    got = np.concatenate([ext[nloc:], ext_t[nloc:, None].astype(np.float64)], axis=1)
+    key = lambda a: sorted(map(tuple, np.round(a, 7)))
+    kg, kw = key(got), key(want)
+    print(f"[diag {rank}] ghosts got {len(kg)} want {len(kw)} equal {kg == kw}", flush=True)
+    if kg != kw:
+        sg, sw = set(kg), set(kw)
+        print(f"[diag {rank}] missing {len(sw - sg)} extra {len(sg - sw)} e.g. {list(sw - sg)[:3]} / {list(sg - sw)[:3]}",
+              flush=True)
+    e, f, v, ex = dp.eval_device(c_d, torch.as_tensor(atype).to(dev), box)
+    ea = ex["atom_energy"].cpu().numpy()
+    ea_ref = rex["atom_energy"].cpu().numpy()[off[rank]:off[rank + 1]]
+    bad = np.nonzero(np.abs(ea - ea_ref) > 1e-9)[0]
+    print(f"[diag {rank}] atoms with different energy: {len(bad)} of {nloc}; max diff {np.abs(ea - ea_ref).max():.3e}",
+          flush=True)
+    if len(bad):
+        print(f"[diag {rank}] positions (fraction of brick) {((coord[bad[:6]] - lo) / (hi - lo)).round(3).tolist()}", flush=True)
+    # neighbour counts
+    nl = ex["nlist"].cpu().numpy()
+    nl_ref = rex["nlist"].cpu().numpy()[off[rank]:off[rank + 1]]
+    cnt, cnt_ref = (nl >= 0).sum(1), (nl_ref >= 0).sum(1)
+    print(f"[diag {rank}] formatted neighbour counts differ for {int((cnt != cnt_ref).sum())} atoms", flush=True)
+
+
 def main():
     rank = int(os.environ["RANK"])
     world = int(os.environ["WORLD_SIZE"])
     local = int(os.environ.get("LOCAL_RANK", rank))
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
-    dist.init_process_group("nccl", device_id=dev)
+    import datetime
+
+    dist.init_process_group("nccl", device_id=dev, timeout=datetime.timedelta(seconds=120))
     g.load_package()
     from deepmd_kit_b200.domain import DomainDeepPot, proc_grid
     from deepmd_kit_b200.model import DeepPotB200, SeAConfig, SeAModel
@@ -44,8 +92,11 @@ def main():
     gc, gt = np.concatenate(cs), np.concatenate(ts)
     off = np.cumsum([0] + [len(x) for x in ts])
     ref = DeepPotB200(model, skin=2.0)
-    er, fr, vr, _ = ref.eval_device(torch.as_tensor(gc).to(dev), torch.as_tensor(gt).to(dev), box)
+    er, fr, vr, rex = ref.eval_device(torch.as_tensor(gc).to(dev), torch.as_tensor(gt).to(dev), box)
+    _ = rex
     fr_mine = fr[off[rank]:off[rank + 1]]
+    if os.environ.get("DPB_DIAG"):
+        diagnose(dp, coord, atype, box, rank, world, cs, ts, _, ref, off, dev)
     ferr = float((f - fr_mine).abs().max() / fr.abs().max())
     eerr = float(abs(e - er) / abs(er))
     verr = float((v - vr).abs().max() / vr.abs().max())
