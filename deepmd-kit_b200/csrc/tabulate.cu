@@ -28,9 +28,13 @@
 //     re-layout pass, no scratch allocation.
 // Not a port of source/lib/src/gpu/tabulate.cu (one thread per channel, stride-6 scalar loads, all
 // coefficients from global memory, serial padding search by thread 0).
+#include <cooperative_groups.h>
+
 #include <cmath>
 
 #include "common.cuh"
+
+namespace cg = cooperative_groups;
 
 namespace dpb200 {
 namespace {
@@ -181,39 +185,63 @@ __device__ __forceinline__ void preload_hot(FP* __restrict__ hot, const TabParam
   }
 }
 
-// Locate up to 32 neighbours [j0, j0+32) of atom i in parallel and stage their records.
-// Returns how many of them must be processed (the fold entry, if any, is the last one).
+// One lane's share of a 32-neighbour chunk, fetched one work item ahead of its use so that the
+// HBM/L2 latency of em_x / em overlaps the previous chunk's arithmetic.
 template <typename FP, bool GG>
-__device__ __forceinline__ int stage_chunk(const TabParams<FP>& p, long long i, int j0, FP last,
+struct Pre {
+  FP x;
+  FP e[4];
+  FP h[4];  // GG only
+  FP zx;    // GG only
+};
+
+template <typename FP, bool GG>
+__device__ __forceinline__ void load_pre(Pre<FP, GG>& q, const TabParams<FP>& p, long long i, int j0, int lane) {
+  const int j = j0 + lane;
+  q.x = (FP)0.;
+#pragma unroll
+  for (int m = 0; m < 4; ++m) q.e[m] = (FP)0.;
+  if (GG) {
+#pragma unroll
+    for (int m = 0; m < 4; ++m) q.h[m] = (FP)0.;
+    q.zx = (FP)0.;
+  }
+  if (i < p.nloc && j < p.nnei) {
+    q.x = p.em_x[i * p.ldx_i + (long long)j * p.ldx_j];
+    load4(p.em + i * p.ldem_i + (long long)j * 4, p.vec_ok != 0, q.e);
+    if (GG) {
+      load4(p.dz_em + (i * p.nnei + j) * 4, true, q.h);
+      q.zx = p.dz_x[i * p.nnei + j];
+    }
+  }
+}
+
+// Locate up to 32 neighbours [j0, j0+32) in parallel and stage their records (em and dz_dy_dem are
+// stored pre-multiplied by the fold multiplicity).  Returns how many of them must be processed
+// (the fold entry, if any, is the last one).
+template <typename FP, bool GG>
+__device__ __forceinline__ int stage_chunk(const TabParams<FP>& p, int j0, FP last, const Pre<FP, GG>& q,
                                            Rec<FP>* __restrict__ rec, RecGG<FP>* __restrict__ rgg,
                                            int lane, bool& done) {
   const int j = j0 + lane;
   const bool valid = j < p.nnei;
-  FP x = (FP)0.;
-  FP e[4] = {(FP)0., (FP)0., (FP)0., (FP)0.};
-  if (valid) {
-    x = p.em_x[i * p.ldx_i + (long long)j * p.ldx_j];
-    load4(p.em + i * p.ldem_i + (long long)j * 4, p.vec_ok != 0, e);
-  }
-  const bool fold = valid && p.is_sorted && (x == last) && e[1] == (FP)0. && e[2] == (FP)0. && e[3] == (FP)0.;
+  const bool fold = valid && p.is_sorted && (q.x == last) && q.e[1] == (FP)0. && q.e[2] == (FP)0. && q.e[3] == (FP)0.;
   const unsigned fm = __ballot_sync(kFull, fold);
   const int nvalid = (p.nnei - j0) < 32 ? (p.nnei - j0) : 32;
   const int nproc = fm ? __ffs(fm) : nvalid;
   done = fm != 0u;
   Rec<FP> r;
-  locate(p, x, r.xx, r.idx, r.delta);
-  r.e[0] = e[0], r.e[1] = e[1], r.e[2] = e[2], r.e[3] = e[3];
+  locate(p, q.x, r.xx, r.idx, r.delta);
   r.mult = (fm && lane == nproc - 1) ? (p.nnei - j) : 1;
+  const FP mult = (FP)r.mult;
+#pragma unroll
+  for (int m = 0; m < 4; ++m) r.e[m] = q.e[m] * mult;
   RecGG<FP> g2;
   if (GG) {
-    FP h[4] = {(FP)0., (FP)0., (FP)0., (FP)0.};
-    g2.zx = (FP)0.;
+#pragma unroll
+    for (int m = 0; m < 4; ++m) g2.h[m] = q.h[m] * mult;
+    g2.zx = q.zx;
     g2.pad_ = (FP)0.;
-    if (valid) {
-      load4(p.dz_em + (i * p.nnei + j) * 4, true, h);
-      g2.zx = p.dz_x[i * p.nnei + j];
-    }
-    g2.h[0] = h[0], g2.h[1] = h[1], g2.h[2] = h[2], g2.h[3] = h[3];
   }
   __syncwarp();  // previous chunk's readers are done
   rec[lane] = r;
@@ -239,7 +267,7 @@ extern __shared__ __align__(16) unsigned char tab_smem[];
 // smem: hot[H][Mc][6] | Rec[nw][32] | RecGG[nw][32] (GG only)
 // ------------------------------------------------------------------------------------------
 template <typename FP, int NC, bool TWO, bool GG>
-__global__ void __launch_bounds__(512) k_tab_fwd(const __grid_constant__ TabParams<FP> p) {
+__global__ void __launch_bounds__(NC == 1 ? 1024 : 512) k_tab_fwd(const __grid_constant__ TabParams<FP> p) {
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
   const int nw = blockDim.x >> 5;
@@ -257,86 +285,104 @@ __global__ void __launch_bounds__(512) k_tab_fwd(const __grid_constant__ TabPara
 #pragma unroll
   for (int c = 0; c < NC; ++c) act[c] = lane + 32 * c < mc;
 
-  for (long long i = (long long)blockIdx.x * nw + warp; i < p.nloc; i += (long long)gridDim.x * nw) {
-    FP acc[4][NC];
+  const long long stride = (long long)gridDim.x * nw;
+  long long i = (long long)blockIdx.x * nw + warp;
+  int j0 = 0;
+  Pre<FP, GG> pre;
+  load_pre(pre, p, i, 0, lane);
+  FP last = i < p.nloc ? p.em_x[i * p.ldx_i + (long long)(p.nnei - 1) * p.ldx_j] : (FP)0.;
+  FP acc[4][NC];
 #pragma unroll
-    for (int m = 0; m < 4; ++m)
+  for (int m = 0; m < 4; ++m)
 #pragma unroll
-      for (int c = 0; c < NC; ++c) acc[m][c] = (FP)0.;
-    FP a[NC][6];
+    for (int c = 0; c < NC; ++c) acc[m][c] = (FP)0.;
+  FP a[NC][6];
 #pragma unroll
-    for (int c = 0; c < NC; ++c)
+  for (int c = 0; c < NC; ++c)
 #pragma unroll
-      for (int q = 0; q < 6; ++q) a[c][q] = (FP)0.;
-    int cur_row = -1;
-    const FP last = p.em_x[i * p.ldx_i + (long long)(p.nnei - 1) * p.ldx_j];
-    bool done = false;
-    for (int j0 = 0; j0 < p.nnei && !done; j0 += 32) {
-      const int nproc = stage_chunk<FP, GG>(p, i, j0, last, rec, rgg, lane, done);
-      for (int jj = 0; jj < nproc; ++jj) {
-        const Rec<FP>& r = rec[jj];
-        const int row = r.idx;
-        if (row != cur_row) {  // warp-uniform
-          cur_row = row;
+    for (int q = 0; q < 6; ++q) a[c][q] = (FP)0.;
+  int cur_row = -1;  // the coefficient registers stay valid across atoms
+
+  while (i < p.nloc) {
+    bool done;
+    const int nproc = stage_chunk<FP, GG>(p, j0, last, pre, rec, rgg, lane, done);
+    // next work item, fetched now, consumed after this chunk's arithmetic
+    const bool atom_end = done || j0 + 32 >= p.nnei;
+    const long long ni = atom_end ? i + stride : i;
+    const int nj0 = atom_end ? 0 : j0 + 32;
+    load_pre(pre, p, ni, nj0, lane);
+    FP nlast = last;
+    if (atom_end && ni < p.nloc) nlast = p.em_x[ni * p.ldx_i + (long long)(p.nnei - 1) * p.ldx_j];
+
+    for (int jj = 0; jj < nproc; ++jj) {
+      const Rec<FP>& r = rec[jj];
+      const int row = r.idx;
+      if (row != cur_row) {  // warp-uniform
+        cur_row = row;
 #pragma unroll
-          for (int c = 0; c < NC; ++c)
-            if (act[c]) fetch_coef(a[c], hot, p.table, row, r0, p.H, p.Mc, p.M, c0, lane + 32 * c);
+        for (int c = 0; c < NC; ++c)
+          if (act[c]) fetch_coef(a[c], hot, p.table, row, r0, p.H, p.Mc, p.M, c0, lane + 32 * c);
+      }
+      const FP xx = r.xx;
+      const FP dl = r.delta;
+      FP e[4];
+#pragma unroll
+      for (int m = 0; m < 4; ++m) e[m] = r.e[m];
+      FP h[4];
+      FP zx = (FP)0.;
+      if (GG) {
+#pragma unroll
+        for (int m = 0; m < 4; ++m) h[m] = rgg[jj].h[m];
+        zx = rgg[jj].zx;
+      }
+      const long long two_off = ((i * p.nnei + j0 + jj) * (long long)p.M) + c0 + lane;
+#pragma unroll
+      for (int c = 0; c < NC; ++c) {
+        FP g = poly(a[c], xx);
+        FP gd = (FP)0.;
+        if (GG || dl != (FP)0.) {
+          gd = dpoly(a[c], xx);
+          g += gd * dl;
         }
-        const FP xx = r.xx;
-        const FP dl = r.delta;
-        const FP mult = (FP)r.mult;
-        FP e[4];
-#pragma unroll
-        for (int m = 0; m < 4; ++m) e[m] = r.e[m] * mult;
-        FP h[4];
-        FP zx = (FP)0.;
         if (GG) {
-#pragma unroll
-          for (int m = 0; m < 4; ++m) h[m] = rgg[jj].h[m] * mult;
-          zx = rgg[jj].zx;
-        }
-        const long long two_off = ((i * p.nnei + j0 + jj) * (long long)p.M) + c0 + lane;
-#pragma unroll
-        for (int c = 0; c < NC; ++c) {
-          FP g = poly(a[c], xx);
-          FP gd = (FP)0.;
-          if (GG || dl != (FP)0.) {
-            gd = dpoly(a[c], xx);
-            g += gd * dl;
+          FP two_grad = (FP)0.;
+          if (TWO && act[c]) {
+            const FP t = p.two[two_off + 32 * c];
+            two_grad = p.dz_two[two_off + 32 * c] * g;
+            g += g * t;
+            gd += gd * t;
           }
-          if (GG) {
-            FP two_grad = (FP)0.;
-            if (TWO && act[c]) {
-              const FP t = p.two[two_off + 32 * c];
-              two_grad = p.dz_two[two_off + 32 * c] * g;
-              g += g * t;
-              gd += gd * t;
-            }
-            const FP sgl = zx * gd + two_grad;
+          const FP sgl = zx * gd + two_grad;
 #pragma unroll
-            for (int m = 0; m < 4; ++m) acc[m][c] += g * h[m] + sgl * e[m];
-          } else {
-            if (TWO && act[c]) {
-              const FP t = p.two[two_off + 32 * c];
-              g = g * t + g;
-            }
-#pragma unroll
-            for (int m = 0; m < 4; ++m) acc[m][c] += e[m] * g;
+          for (int m = 0; m < 4; ++m) acc[m][c] += g * h[m] + sgl * e[m];
+        } else {
+          if (TWO && act[c]) {
+            const FP t = p.two[two_off + 32 * c];
+            g = g * t + g;
           }
+#pragma unroll
+          for (int m = 0; m < 4; ++m) acc[m][c] += e[m] * g;
         }
       }
     }
-    FP* __restrict__ o = p.out + i * 4 * (long long)p.M + c0 + lane;
+    if (atom_end) {
+      FP* __restrict__ o = p.out + i * 4 * (long long)p.M + c0 + lane;
 #pragma unroll
-    for (int c = 0; c < NC; ++c) {
-      if (act[c]) {
+      for (int c = 0; c < NC; ++c) {
+        if (act[c]) {
 #pragma unroll
-        for (int m = 0; m < 4; ++m) {
-          FP* q = o + (long long)m * p.M + 32 * c;
-          *q = p.accumulate ? (*q + acc[m][c]) : acc[m][c];
+          for (int m = 0; m < 4; ++m) {
+            FP* q = o + (long long)m * p.M + 32 * c;
+            *q = p.accumulate ? (*q + acc[m][c]) : acc[m][c];
+          }
         }
+#pragma unroll
+        for (int m = 0; m < 4; ++m) acc[m][c] = (FP)0.;
       }
     }
+    i = ni;
+    j0 = nj0;
+    last = nlast;
   }
 }
 
@@ -377,118 +423,163 @@ __device__ __forceinline__ FP reduce_scatter8(FP (&v)[8], int lane) {
   return r;
 }
 
-// block = nw warps, one warp per atom; smem: hot[H][M][6] | Rec[nw][32]
+// Backward.  grid (x: persistent over atoms, y: S channel slices), thread-block CLUSTER (1, S, 1):
+// the S CTAs of a cluster walk the same atoms in lockstep, each over its own Mc channels with its
+// own shared-memory window of hot rows; per 32-neighbour chunk every warp leaves its 160 partial
+// sums (32 x dy_dem[4] + 32 x dy_dem_x) in its CTA's shared memory, one cluster barrier, then CTA
+// s sums slice s of every buffer across the cluster through distributed shared memory and writes
+// it out (coalesced).  Work items are (atom, chunk) in a fixed order so that all CTAs execute the
+// same number of barriers; chunks behind the fold are empty rounds that write the zero fill.
+// smem: hot[H][Mc][6] | Rec[nw][32] | part[2][nw][160]
 template <typename FP, int NC, bool TWO>
 __global__ void __launch_bounds__(384) k_tab_grad(const __grid_constant__ TabParams<FP> p) {
+  cg::cluster_group cluster = cg::this_cluster();
+  const int S = (int)cluster.num_blocks();
+  const int srank = (int)cluster.block_rank();
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
   const int nw = blockDim.x >> 5;
   FP* hot = reinterpret_cast<FP*>(tab_smem);
   Rec<FP>* rec = reinterpret_cast<Rec<FP>*>(hot + p.hot_elems) + warp * 32;
+  FP* part_base = reinterpret_cast<FP*>(reinterpret_cast<Rec<FP>*>(hot + p.hot_elems) + nw * 32);
   const int M = p.M;
+  const int c0 = blockIdx.y * p.Mc;
+  const int mc = (M - c0) < p.Mc ? (M - c0) : p.Mc;
   const int r0 = hot_window_start(p);
-  preload_hot(hot, p, r0, 0, M);
+  preload_hot(hot, p, r0, c0, mc);
   __syncthreads();
-  const bool single = M <= 32 * NC;
-  for (long long i = (long long)blockIdx.x * nw + warp; i < p.nloc; i += (long long)gridDim.x * nw) {
-    const FP* __restrict__ dyi = p.dy + i * 4 * (long long)M;
-    FP dyr[4][NC];
-    if (single) {
+  cluster.sync();  // every CTA of the cluster is resident before any DSMEM access
+
+  bool act[NC];
 #pragma unroll
-      for (int c = 0; c < NC; ++c)
+  for (int c = 0; c < NC; ++c) act[c] = lane + 32 * c < mc;
+  const bool fuse_x = p.dy_dem_x == nullptr;  // em_x IS component 0 of em: add its gradient there
+  const int nchunk = (p.nnei + 31) / 32;
+  const long long nblk_atoms = (p.nloc + nw - 1) / nw;  // atom groups of nw
+  const long long T = nblk_atoms > blockIdx.x ? (nblk_atoms - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+  const long long R = T * nchunk;  // rounds: identical for all CTAs of the cluster
+  const int per = (160 + S - 1) / S;  // entries of every buffer reduced by one CTA
+
+  long long i = ((long long)blockIdx.x) * nw + warp;
+  Pre<FP, false> pre;
+  load_pre(pre, p, i, 0, lane);
+  FP last = i < p.nloc ? p.em_x[i * p.ldx_i + (long long)(p.nnei - 1) * p.ldx_j] : (FP)0.;
+  FP dyr[4][NC];
+  bool done = false;
+
+  for (long long r = 0; r < R; ++r) {
+    const int c = (int)(r % nchunk);
+    const int j0 = c * 32;
+    const bool have = i < p.nloc;
+    FP* part = part_base + ((size_t)(r & 1) * nw + warp) * 160;
+    if (c == 0) {
+      done = false;
+      if (have) {
+        const FP* __restrict__ dyi = p.dy + i * 4 * (long long)M + c0;
 #pragma unroll
-        for (int m = 0; m < 4; ++m) dyr[m][c] = (lane + 32 * c < M) ? dyi[(long long)m * M + lane + 32 * c] : (FP)0.;
+        for (int cc = 0; cc < NC; ++cc)
+#pragma unroll
+          for (int m = 0; m < 4; ++m) dyr[m][cc] = act[cc] ? dyi[(long long)m * M + lane + 32 * cc] : (FP)0.;
+      }
     }
-    const FP last = p.em_x[i * p.ldx_i + (long long)(p.nnei - 1) * p.ldx_j];
-    // dy_dem_x == nullptr: em_x IS component 0 of em, its gradient is added into dy_dem[j][0]
-    const bool fuse_x = p.dy_dem_x == nullptr;
-    FP* __restrict__ gx = fuse_x ? nullptr : p.dy_dem_x + i * p.ldx_i;
-    FP* __restrict__ gem = p.dy_dem + i * p.ldem_i;
-    bool done = false;
-    int jend = 0;  // neighbours [0, jend) have been written
-    for (int j0 = 0; j0 < p.nnei && !done; j0 += 32) {
-      const int nproc = stage_chunk<FP, false>(p, i, j0, last, rec, nullptr, lane, done);
-      for (int b = 0; b < nproc; b += 8) {
-        FP v[32];
-        FP vx[8];
+    int nproc = 0;
+    if (have && !done) nproc = stage_chunk<FP, false>(p, j0, last, pre, rec, nullptr, lane, done);
+    // next work item (fixed order: next chunk of this atom, then the next atom of this warp)
+    const bool atom_end = c + 1 == nchunk;
+    const long long ni = atom_end ? i + (long long)gridDim.x * nw : i;
+    const int nj0 = atom_end ? 0 : j0 + 32;
+    FP nlast = last;
+    if (!(done && !atom_end)) {  // chunks behind the fold are never staged: skip their loads
+      load_pre(pre, p, ni, nj0, lane);
+      if (atom_end && ni < p.nloc) nlast = p.em_x[ni * p.ldx_i + (long long)(p.nnei - 1) * p.ldx_j];
+    }
 #pragma unroll
-        for (int t = 0; t < 32; ++t) v[t] = (FP)0.;
+    for (int q = 0; q < 5; ++q) part[lane + 32 * q] = (FP)0.;
+    __syncwarp();
+
+    for (int b = 0; b < nproc; b += 8) {
+      FP v[32];
+      FP vx[8];
 #pragma unroll
-        for (int t = 0; t < 8; ++t) vx[t] = (FP)0.;
-        for (int kb = 0; kb < M; kb += 32 * NC) {
+      for (int t = 0; t < 32; ++t) v[t] = (FP)0.;
 #pragma unroll
-          for (int c = 0; c < NC; ++c) {
-            const int k = kb + lane + 32 * c;
-            const bool kin = k < M;
-            FP d0, d1, d2, d3;
-            if (single) {
-              d0 = dyr[0][c], d1 = dyr[1][c], d2 = dyr[2][c], d3 = dyr[3][c];
-            } else {
-              d0 = kin ? dyi[k] : (FP)0.;
-              d1 = kin ? dyi[(long long)M + k] : (FP)0.;
-              d2 = kin ? dyi[2ll * M + k] : (FP)0.;
-              d3 = kin ? dyi[3ll * M + k] : (FP)0.;
+      for (int t = 0; t < 8; ++t) vx[t] = (FP)0.;
+#pragma unroll
+      for (int cc = 0; cc < NC; ++cc) {
+        const int kk = lane + 32 * cc;
+        const FP d0 = dyr[0][cc], d1 = dyr[1][cc], d2 = dyr[2][cc], d3 = dyr[3][cc];
+        FP a[6] = {(FP)0., (FP)0., (FP)0., (FP)0., (FP)0., (FP)0.};
+        int cur_row = -1;
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          if (b + u < nproc) {  // warp-uniform
+            const Rec<FP>& rc = rec[b + u];
+            if (rc.idx != cur_row) {
+              cur_row = rc.idx;
+              if (act[cc]) fetch_coef(a, hot, p.table, cur_row, r0, p.H, p.Mc, M, c0, kk);
             }
-            FP a[6] = {(FP)0., (FP)0., (FP)0., (FP)0., (FP)0., (FP)0.};
-            int cur_row = -1;
-#pragma unroll
-            for (int u = 0; u < 8; ++u) {
-              if (b + u < nproc) {  // warp-uniform
-                const Rec<FP>& r = rec[b + u];
-                if (r.idx != cur_row) {
-                  cur_row = r.idx;
-                  if (kin) fetch_coef(a, hot, p.table, cur_row, r0, p.H, p.Mc, M, 0, k);
-                }
-                const FP xx = r.xx;
-                FP gd = dpoly(a, xx);
-                FP g = poly(a, xx) + gd * r.delta;
-                const FP dot = r.e[0] * d0 + r.e[1] * d1 + r.e[2] * d2 + r.e[3] * d3;
-                if (TWO) {
-                  if (kin) {
-                    const long long to = (i * p.nnei + j0 + b + u) * (long long)M + k;
-                    const FP t = p.two[to];
-                    p.dy_dtwo[to] = (FP)r.mult * g * dot;
-                    g = g * t + g;
-                    gd += t * gd;
-                  }
-                }
-                vx[u] += gd * dot;
-                v[4 * u + 0] += g * d0;
-                v[4 * u + 1] += g * d1;
-                v[4 * u + 2] += g * d2;
-                v[4 * u + 3] += g * d3;
+            const FP xx = rc.xx;
+            FP gd = dpoly(a, xx);
+            FP g = poly(a, xx) + gd * rc.delta;
+            // rc.e is pre-multiplied by the fold multiplicity
+            const FP dot = rc.e[0] * d0 + rc.e[1] * d1 + rc.e[2] * d2 + rc.e[3] * d3;
+            if (TWO) {
+              if (act[cc]) {
+                const long long to = (i * p.nnei + j0 + b + u) * (long long)M + c0 + kk;
+                const FP t = p.two[to];
+                p.dy_dtwo[to] = g * dot;
+                g = g * t + g;
+                gd += t * gd;
               }
             }
-          }
-        }
-        const FP tot = reduce_scatter32(v, lane);
-        const FP totx = reduce_scatter8(vx, lane);
-        const int u = lane >> 2;
-        if (b + u < nproc) {
-          const FP mult = (FP)rec[b + u].mult;
-          const int j = j0 + b + u;
-          if (fuse_x) {
-            gem[(long long)j * 4 + (lane & 3)] = ((lane & 3) == 0 ? tot + totx : tot) * mult;
-          } else {
-            gem[(long long)j * 4 + (lane & 3)] = tot * mult;
-            if ((lane & 3) == 0) gx[(long long)j * p.ldx_j] = totx * mult;
+            vx[u] += gd * dot;
+            v[4 * u + 0] += g * d0;
+            v[4 * u + 1] += g * d1;
+            v[4 * u + 2] += g * d2;
+            v[4 * u + 3] += g * d3;
           }
         }
       }
-      jend = j0 + nproc;
+      const FP tot = reduce_scatter32(v, lane);
+      const FP totx = reduce_scatter8(vx, lane);  // already carries the multiplicity (through e)
+      const int u = lane >> 2;
+      if (b + u < nproc) {
+        const FP mult = (FP)rec[b + u].mult;
+        if (fuse_x) {
+          part[(b + u) * 4 + (lane & 3)] = (lane & 3) == 0 ? tot * mult + totx : tot * mult;
+        } else {
+          part[(b + u) * 4 + (lane & 3)] = tot * mult;
+          if ((lane & 3) == 0) part[128 + b + u] = totx;
+        }
+      }
     }
-    // everything behind the fold (or nothing) is zero (tabulate.cc zero-fills the outputs first)
-    for (int j = jend + lane; j < p.nnei; j += 32) {
-      if (!fuse_x) gx[(long long)j * p.ldx_j] = (FP)0.;
+    if (TWO && have) {  // dy_dtwo of the slots behind the processed ones is zero
+      const int nvalid = (p.nnei - j0) < 32 ? (p.nnei - j0) : 32;
+      for (int jz = nproc; jz < nvalid; ++jz)
 #pragma unroll
-      for (int m = 0; m < 4; ++m) gem[(long long)j * 4 + m] = (FP)0.;
+        for (int cc = 0; cc < NC; ++cc)
+          if (act[cc]) p.dy_dtwo[(i * p.nnei + j0 + jz) * (long long)M + c0 + lane + 32 * cc] = (FP)0.;
     }
-    if (TWO) {
-      for (long long e = (long long)jend * M + lane; e < (long long)p.nnei * M; e += 32)
-        p.dy_dtwo[i * p.nnei * (long long)M + e] = (FP)0.;
+    cluster.sync();
+    // CTA `srank` finishes entries [srank*per, srank*per+per) of this warp's buffer
+    if (have) {
+      FP* __restrict__ gem = p.dy_dem + i * p.ldem_i;
+      for (int e = srank * per + lane; e < srank * per + per && e < 160; e += 32) {
+        FP sum = (FP)0.;
+        for (int s2 = 0; s2 < S; ++s2) sum += cluster.map_shared_rank(part, s2)[e];
+        if (e < 128) {
+          const int j = j0 + (e >> 2);
+          if (j < p.nnei) gem[(long long)j * 4 + (e & 3)] = sum;
+        } else if (!fuse_x) {
+          const int j = j0 + (e - 128);
+          if (j < p.nnei) p.dy_dem_x[i * p.ldx_i + (long long)j * p.ldx_j] = sum;
+        }
+      }
     }
-    __syncwarp();
+    i = ni;
+    last = nlast;
   }
+  cluster.sync();  // nobody leaves while a neighbour may still read its shared memory
 }
 
 // ------------------------------------------------------------------------------------------
@@ -581,11 +672,13 @@ int launch_fwd(FP* out, const FP* table, const FP* info, const FP* em_x, long lo
     DPB_REQUIRE(two == nullptr || dz_two != nullptr, "tabulate grad_grad: dz_dy_dtwo is null");
   }
   // channel slicing: the smallest number of slices whose shared-memory window reaches ~150 rows
-  const int nw = 16;
-  const size_t rec_bytes = (size_t)nw * 32 * (sizeof(Rec<FP>) + (GG ? sizeof(RecGG<FP>) : 0));
-  int S = (M + 127) / 128, Mc = 0, H = 0;
+  int S = (M + 127) / 128, Mc = 0, H = 0, nc = 1, nw = 16;
+  size_t rec_bytes = 0;
   for (;; S *= 2) {
     Mc = (M + S - 1) / S;
+    nc = Mc <= 32 ? 1 : (Mc <= 64 ? 2 : 4);
+    nw = nc == 1 ? 32 : 16;
+    rec_bytes = (size_t)nw * 32 * (sizeof(Rec<FP>) + (GG ? sizeof(RecGG<FP>) : 0));
     H = hot_rows<FP>(p.nrow, Mc, rec_bytes);
     if (H >= (p.nrow < 150 ? p.nrow : 150) || Mc <= 32) break;
   }
@@ -595,7 +688,6 @@ int launch_fwd(FP* out, const FP* table, const FP* info, const FP* em_x, long lo
   p.hot_elems = hot_elems_aligned<FP>(H, Mc);
   const size_t smem = (size_t)p.hot_elems * sizeof(FP) + rec_bytes;
   const bool tw = two != nullptr;
-  const int nc = Mc <= 32 ? 1 : (Mc <= 64 ? 2 : 4);
   long long want = ((long long)nloc + nw - 1) / nw;
   const long long cap = (sm_count() + S - 1) / S > 0 ? (long long)((sm_count() + S - 1) / S) : 1;
   dim3 grid((unsigned)(want < cap ? want : cap), (unsigned)S);
@@ -623,6 +715,32 @@ int launch_fwd(FP* out, const FP* table, const FP* info, const FP* em_x, long lo
   return DPB200_OK;
 }
 
+// cluster launch of the backward kernel: grid (x, S), cluster (1, S, 1)
+template <typename K, typename FP>
+int launch_cluster(K kern, const TabParams<FP>& p, int S, int threads, size_t smem, long long want, cudaStream_t st) {
+  DPB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  cudaLaunchConfig_t cfg = {};
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 1;
+  attr[0].val.clusterDim.y = (unsigned)S;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  cfg.blockDim = dim3((unsigned)threads);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cfg.gridDim = dim3(1, (unsigned)S, 1);
+  int nclusters = 0;
+  if (cudaOccupancyMaxActiveClusters(&nclusters, kern, &cfg) != cudaSuccess || nclusters < 1) {
+    cudaGetLastError();
+    nclusters = sm_count() / S > 0 ? sm_count() / S : 1;
+  }
+  cfg.gridDim = dim3((unsigned)(want < nclusters ? want : nclusters), (unsigned)S, 1);
+  DPB_CUDA(cudaLaunchKernelEx(&cfg, kern, p));
+  return DPB200_OK;
+}
+
 template <typename FP>
 int launch_grad(FP* dy_dem_x, FP* dy_dem, FP* dy_dtwo, const FP* table, const FP* info,
                 const FP* em_x, long long ldx_i, int ldx_j, const FP* em, long long ldem_i,
@@ -641,35 +759,39 @@ int launch_grad(FP* dy_dem_x, FP* dy_dem, FP* dy_dtwo, const FP* table, const FP
   p.dy_dem_x = dy_dem_x;
   p.dy_dem = dy_dem;
   p.dy_dtwo = dy_dtwo;
+  DPB_REQUIRE(M <= 1024, "tabulate grad: last_layer_size above 1024 is not supported");
   const int nw = 12;
-  const size_t rec_bytes = (size_t)nw * 32 * sizeof(Rec<FP>);
-  p.Mc = M;
-  p.H = hot_rows<FP>(p.nrow, M, rec_bytes);
-  p.hot_elems = hot_elems_aligned<FP>(p.H, M);
+  const size_t rec_bytes = (size_t)nw * 32 * sizeof(Rec<FP>) + (size_t)2 * nw * 160 * sizeof(FP);
+  int S = (M + 127) / 128, Mc = 0, H = 0;
+  for (;; S *= 2) {  // cluster sizes 1, 2, 4, 8
+    Mc = (M + S - 1) / S;
+    H = hot_rows<FP>(p.nrow, Mc, rec_bytes);
+    if (H >= (p.nrow < 120 ? p.nrow : 120) || Mc <= 32 || S >= 8) break;
+  }
+  S = (M + Mc - 1) / Mc;
+  p.Mc = Mc;
+  p.H = H;
+  p.hot_elems = hot_elems_aligned<FP>(H, Mc);
   const size_t smem = (size_t)p.hot_elems * sizeof(FP) + rec_bytes;
   const bool tw = two != nullptr;
-  long long want = ((long long)nloc + nw - 1) / nw;
-  const long long cap = sm_count();
-  const int grid = (int)(want < cap ? want : cap);
-#define DPB_LAUNCH_GRAD(NC)                                                                         \
-  do {                                                                                              \
-    if (tw) {                                                                                       \
-      auto kern = k_tab_grad<FP, NC, true>;                                                         \
-      DPB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-      kern<<<grid, nw * 32, smem, st>>>(p);                                                         \
-    } else {                                                                                        \
-      auto kern = k_tab_grad<FP, NC, false>;                                                        \
-      DPB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-      kern<<<grid, nw * 32, smem, st>>>(p);                                                         \
-    }                                                                                               \
+  const int nc = Mc <= 32 ? 1 : (Mc <= 64 ? 2 : 4);
+  const long long want = ((long long)nloc + nw - 1) / nw;
+  int rc2 = DPB200_OK;
+#define DPB_LAUNCH_GRAD(NC)                                                              \
+  do {                                                                                   \
+    if (tw)                                                                              \
+      rc2 = launch_cluster(k_tab_grad<FP, NC, true>, p, S, nw * 32, smem, want, st);     \
+    else                                                                                 \
+      rc2 = launch_cluster(k_tab_grad<FP, NC, false>, p, S, nw * 32, smem, want, st);    \
   } while (0)
-  if (M <= 32)
+  if (nc == 1)
     DPB_LAUNCH_GRAD(1);
-  else if (M <= 64)
+  else if (nc == 2)
     DPB_LAUNCH_GRAD(2);
   else
     DPB_LAUNCH_GRAD(4);
 #undef DPB_LAUNCH_GRAD
+  if (rc2) return rc2;
   DPB_CUDA(cudaGetLastError());
   note_launches(1);
   return DPB200_OK;
