@@ -250,11 +250,16 @@ def run_ours(args):
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     ev0.record()
+    marks = []
     for _ in range(args.steps):
         out = step()
+        m = torch.cuda.Event(enable_timing=True)
+        m.record()
+        marks.append(m)
     ev1.record()
     barrier()
     ms = ev0.elapsed_time(ev1)
+    step_ms = [round((ev0 if k == 0 else marks[k - 1]).elapsed_time(marks[k]), 3) for k in range(len(marks))]
     launches = L.launch_count() - l0
     clocks = sampler.stop() if rank == 0 else None
     if world > 1:
@@ -313,11 +318,12 @@ def run_ours(args):
                 "neuron": list(cfg.neuron), "axis_neuron": cfg.axis_neuron, "fitting_neuron": list(cfg.fitting_neuron),
                 "table": "dp-compress restatement, stride 0.01/0.1, extrapolate 5, random-init weights (seed 1)",
                 "skin": 2.0, "nlist_every": 10, "parallelism": parallelism,
+                "cuda_graph": bool(getattr(dp, "use_graph", False)),
                 "atom_virial": bool(args.atom_virial),
                 "l2_policy": "per-step working set (tens of GB of env-mat intermediates) is far larger than the 126 MB L2",
                 "energy": energy,
             },
-            "clocks": clocks, "gpu_launches": int(launches),
+            "clocks": clocks, "gpu_launches": int(launches), "step_ms": step_ms,
         }
         if e2e:
             line["e2e"] = e2e
@@ -357,6 +363,8 @@ def per_kernel(args, torch, ops, model, dp, step, L, dev, nloc, esz):
     orig_fit = model.energy_and_dy
     model.energy_and_dy = wrap("fitting_net(torch)", orig_fit)
     nsteps = 10
+    graph_mode = getattr(dp, "use_graph", False)
+    dp.use_graph = False  # the instrumented pass needs real launches (events cannot be timed inside a graph)
     try:
         for _ in range(nsteps):
             out = step()
@@ -365,6 +373,7 @@ def per_kernel(args, torch, ops, model, dp, step, L, dev, nloc, esz):
         for n in names:
             setattr(ops, n, orig[n])
         model.energy_and_dy = orig_fit
+        dp.use_graph = graph_mode
     nlist = out[3]["nlist"]
     nreal = float((nlist >= 0).sum().item()) / nloc
     cfg = model.cfg

@@ -36,8 +36,10 @@ _SIGS = {
     "copy_coord_{s}": "pppp pp ii f p pz p",
     "copy_coord_cells_{s}": "pppp pp ii pp p pz p",
     "build_nlist_{s}": "ppp p iii f p pz p",
-    "se_a_descriptor_{s}": "pp l ii d p",
-    "se_a_descriptor_grad_{s}": "ppp l ii d p",
+    "se_a_descriptor_{s}": "ppp l ii d p",
+    "se_a_descriptor_grad_{s}": "pppp l ii d p",
+    "mlp_tanh_fwd_{s}": "pppp l i p",
+    "mlp_tanh_bwd_{s}": "pp l pp l i p",
     "halo_pack_{s}": "pppp i p",
     "halo_unpack_add_{s}": "ppp i p",
 }
@@ -63,6 +65,8 @@ class _Lib:
         self.cdll.dpb200_last_error.restype = C.c_char_p
         self.cdll.dpb200_abi_version.restype = C.c_int
         self.cdll.dpb200_launch_count.restype = C.c_longlong
+        self.cdll.dpb200_count_replayed_launches.restype = None
+        self.cdll.dpb200_count_replayed_launches.argtypes = [C.c_longlong]
         for s_ in ("f32", "f64"):
             f = getattr(self.cdll, "dpb200_fma_peak_" + s_)
             f.restype = C.c_int
@@ -81,7 +85,8 @@ class _Lib:
                 f.argtypes = [_T[c] for c in sig.replace(" ", "")]
 
     def exported(self):
-        names = ["dpb200_last_error", "dpb200_abi_version", "dpb200_launch_count", "dpb200_fma_peak_f32",
+        names = ["dpb200_last_error", "dpb200_abi_version", "dpb200_launch_count", "dpb200_count_replayed_launches",
+                 "dpb200_fma_peak_f32",
                  "dpb200_fma_peak_f64", "dpb200_prod_env_mat_a_workspace_bytes",
                  "dpb200_copy_coord_workspace_bytes", "dpb200_build_nlist_workspace_bytes", "dpb200_use_nlist_map"]
         for pat in _SIGS:

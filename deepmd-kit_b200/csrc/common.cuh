@@ -28,6 +28,7 @@ int cuda_fail(cudaError_t e, const char* what, const char* file, int line);
 
 // Bookkeeping for dpb200_launch_count(): every host wrapper reports the kernels it enqueued.
 void note_launches(int n);
+void keep_async_pool();
 
 // Number of SMs of the current device (cached per device).
 int sm_count();

@@ -14,13 +14,14 @@ namespace {
 extern __shared__ __align__(16) unsigned char desc_smem[];
 
 template <typename FP>
-__global__ void __launch_bounds__(128) k_desc_fwd(FP* __restrict__ D, const FP* __restrict__ X, long long nloc, int M,
-                                                  int axis, FP scale) {
+__global__ void __launch_bounds__(128) k_desc_fwd(FP* __restrict__ D, const FP* __restrict__ X,
+                                                  const int* __restrict__ rows, long long nloc, int M, int axis,
+                                                  FP scale) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   FP* xs = reinterpret_cast<FP*>(desc_smem) + (size_t)warp * 4 * M;
   const int nout = M * axis;
   for (long long i = (long long)blockIdx.x * 4 + warp; i < nloc; i += (long long)gridDim.x * 4) {
-    const FP* __restrict__ x = X + i * 4 * M;
+    const FP* __restrict__ x = X + (rows ? (long long)rows[i] : i) * 4 * M;
     __syncwarp();
     for (int e = lane; e < 4 * M; e += 32) xs[e] = x[e] * scale;
     __syncwarp();
@@ -35,18 +36,22 @@ __global__ void __launch_bounds__(128) k_desc_fwd(FP* __restrict__ D, const FP* 
 }
 
 // dX[m][k] = scale * ( sum_{k2<axis} dD[k][k2] xs[m][k2]  +  [k<axis] sum_{k1<M} dD[k1][k] xs[m][k1] ),
-// xs = X*scale
+// xs = X*scale.  Row i of dD/X(gathered) belongs to atom rows[i] (or i): the result is written there.
+// The second term is a column walk over all M rows for only `axis` channels: it is spread over the
+// whole warp as (m, k) = (lane / axis ... ) pairs instead of leaving 3/4 of the lanes idle.
 template <typename FP>
 __global__ void __launch_bounds__(128) k_desc_bwd(FP* __restrict__ dX, const FP* __restrict__ dD,
-                                                  const FP* __restrict__ X, long long nloc, int M, int axis,
-                                                  FP scale) {
+                                                  const FP* __restrict__ X, const int* __restrict__ rows,
+                                                  long long nloc, int M, int axis, FP scale) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int ld = axis + 1;  // padded row of the staged dD: conflict-free column walks
-  FP* xs = reinterpret_cast<FP*>(desc_smem) + (size_t)warp * (4 * M + M * ld);
+  FP* xs = reinterpret_cast<FP*>(desc_smem) + (size_t)warp * (4 * M + M * ld + 4 * axis);
   FP* g = xs + 4 * M;
+  FP* t2 = g + M * ld;  // second term, [4][axis]
   const int nout = M * axis;
   for (long long i = (long long)blockIdx.x * 4 + warp; i < nloc; i += (long long)gridDim.x * 4) {
-    const FP* __restrict__ x = X + i * 4 * M;
+    const long long dst = rows ? (long long)rows[i] : i;
+    const FP* __restrict__ x = X + dst * 4 * M;
     const FP* __restrict__ gd = dD + i * nout;
     __syncwarp();
     for (int e = lane; e < 4 * M; e += 32) xs[e] = x[e] * scale;
@@ -55,7 +60,15 @@ __global__ void __launch_bounds__(128) k_desc_bwd(FP* __restrict__ dX, const FP*
       g[k1 * ld + k2] = __ldcs(gd + e);
     }
     __syncwarp();
-    FP* __restrict__ o = dX + i * 4 * M;
+    // second term: 4*axis outputs, each a dot product over k1 < M
+    for (int o = lane; o < 4 * axis; o += 32) {
+      const int m = o / axis, k = o - m * axis;
+      FP acc = 0;
+      for (int k1 = 0; k1 < M; ++k1) acc += g[k1 * ld + k] * xs[m * M + k1];
+      t2[o] = acc;
+    }
+    __syncwarp();
+    FP* __restrict__ o = dX + dst * 4 * M;
     for (int k = lane; k < M; k += 32) {
       FP a0 = 0, a1 = 0, a2 = 0, a3 = 0;
       for (int k2 = 0; k2 < axis; ++k2) {
@@ -66,13 +79,10 @@ __global__ void __launch_bounds__(128) k_desc_bwd(FP* __restrict__ dX, const FP*
         a3 += w * xs[3 * M + k2];
       }
       if (k < axis) {
-        for (int k1 = 0; k1 < M; ++k1) {
-          const FP w = g[k1 * ld + k];
-          a0 += w * xs[k1];
-          a1 += w * xs[M + k1];
-          a2 += w * xs[2 * M + k1];
-          a3 += w * xs[3 * M + k1];
-        }
+        a0 += t2[k];
+        a1 += t2[axis + k];
+        a2 += t2[2 * axis + k];
+        a3 += t2[3 * axis + k];
       }
       o[k] = a0 * scale;
       o[M + k] = a1 * scale;
@@ -82,13 +92,41 @@ __global__ void __launch_bounds__(128) k_desc_bwd(FP* __restrict__ dX, const FP*
   }
 }
 
+// Fused elementwise passes of the fitting MLP (deepmd/pt/model/network/mlp.py: tanh, resnet_dt, skip):
+//   forward : a = tanh(z) (kept for the backward, overwrites z); y = a*idt (+ h when the widths match)
+//   backward: t = g * idt * (1 - a^2)
 template <typename FP>
-int desc_launch(bool bwd, FP* out, const FP* dD, const FP* X, long long nloc, int M, int axis, double scale,
-                cudaStream_t st) {
+__global__ void k_mlp_act_fwd(FP* __restrict__ z_a, FP* __restrict__ y, const FP* __restrict__ h,
+                              const FP* __restrict__ idt, long long n, int width) {
+  for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < n; e += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(e % width);
+    const FP a = tanh(z_a[e]);
+    z_a[e] = a;
+    FP v = idt ? a * idt[c] : a;
+    if (h) v += h[e];
+    y[e] = v;
+  }
+}
+template <typename FP>
+__global__ void k_mlp_act_bwd(FP* __restrict__ t, const FP* __restrict__ g, long long ldg, const FP* __restrict__ a,
+                              const FP* __restrict__ idt, long long n, int width) {
+  for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < n; e += (long long)gridDim.x * blockDim.x) {
+    const long long r = e / width;
+    const int c = (int)(e - r * width);
+    const FP av = a[e];
+    FP v = g[r * ldg + c] * ((FP)1. - av * av);
+    if (idt) v *= idt[c];
+    t[e] = v;
+  }
+}
+
+template <typename FP>
+int desc_launch(bool bwd, FP* out, const FP* dD, const FP* X, const int* rows, long long nloc, int M, int axis,
+                double scale, cudaStream_t st) {
   DPB_REQUIRE(nloc >= 0 && M >= 1 && axis >= 1 && axis <= M, "descriptor: need 1 <= axis <= M");
   if (nloc == 0) return DPB200_OK;
   DPB_REQUIRE(out && X && (!bwd || dD), "descriptor: null pointer");
-  const size_t smem = (bwd ? (size_t)(4 * M + M * (axis + 1)) : (size_t)4 * M) * sizeof(FP) * 4;
+  const size_t smem = (bwd ? (size_t)(4 * M + M * (axis + 1) + 4 * axis) : (size_t)4 * M) * sizeof(FP) * 4;
   DPB_REQUIRE(smem <= 200 * 1024, "descriptor: M*axis too large for shared memory staging");
   int occ = 0;
   long long want = (nloc + 3) / 4;
@@ -97,13 +135,34 @@ int desc_launch(bool bwd, FP* out, const FP* dD, const FP* X, long long nloc, in
     DPB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     DPB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, 128, smem));
     long long cap = (long long)sm_count() * (occ < 1 ? 1 : occ);
-    kern<<<(int)(want < cap ? want : cap), 128, smem, st>>>(out, dD, X, nloc, M, axis, (FP)scale);
+    kern<<<(int)(want < cap ? want : cap), 128, smem, st>>>(out, dD, X, rows, nloc, M, axis, (FP)scale);
   } else {
     auto kern = k_desc_fwd<FP>;
     DPB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     DPB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, 128, smem));
     long long cap = (long long)sm_count() * (occ < 1 ? 1 : occ);
-    kern<<<(int)(want < cap ? want : cap), 128, smem, st>>>(out, X, nloc, M, axis, (FP)scale);
+    kern<<<(int)(want < cap ? want : cap), 128, smem, st>>>(out, X, rows, nloc, M, axis, (FP)scale);
+  }
+  DPB_CUDA(cudaGetLastError());
+  note_launches(1);
+  return DPB200_OK;
+}
+
+template <typename FP>
+int act_launch(bool bwd, FP* out, FP* z_a, const FP* g, long long ldg, const FP* h, const FP* idt, long long nrow,
+               int width, cudaStream_t st) {
+  DPB_REQUIRE(nrow >= 0 && width >= 1, "mlp activation: bad shape");
+  const long long n = nrow * width;
+  if (n == 0) return DPB200_OK;
+  int grid = ceil_div(n, 256);
+  const int cap = sm_count() * 16;
+  if (grid > cap) grid = cap;
+  if (bwd) {
+    DPB_REQUIRE(out && g && z_a, "mlp activation backward: null pointer");
+    k_mlp_act_bwd<FP><<<grid, 256, 0, st>>>(out, g, ldg, z_a, idt, n, width);
+  } else {
+    DPB_REQUIRE(out && z_a, "mlp activation forward: null pointer");
+    k_mlp_act_fwd<FP><<<grid, 256, 0, st>>>(z_a, out, h, idt, n, width);
   }
   DPB_CUDA(cudaGetLastError());
   note_launches(1);
@@ -115,13 +174,26 @@ int desc_launch(bool bwd, FP* out, const FP* dD, const FP* X, long long nloc, in
 
 extern "C" {
 #define DPB200_DEF_DESC(SUF, FP)                                                                        \
-  int dpb200_se_a_descriptor_##SUF(FP* D, const FP* gr, long long nloc, int M, int axis, double scale,  \
-                                   dpb200_stream_t stream) {                                            \
-    return dpb200::desc_launch<FP>(false, D, nullptr, gr, nloc, M, axis, scale, (cudaStream_t)stream);  \
+  int dpb200_se_a_descriptor_##SUF(FP* D, const FP* gr, const int* rows, long long nloc, int M,         \
+                                   int axis, double scale, dpb200_stream_t stream) {                    \
+    return dpb200::desc_launch<FP>(false, D, nullptr, gr, rows, nloc, M, axis, scale,                   \
+                                   (cudaStream_t)stream);                                               \
   }                                                                                                     \
-  int dpb200_se_a_descriptor_grad_##SUF(FP* dgr, const FP* dD, const FP* gr, long long nloc, int M,     \
-                                        int axis, double scale, dpb200_stream_t stream) {               \
-    return dpb200::desc_launch<FP>(true, dgr, dD, gr, nloc, M, axis, scale, (cudaStream_t)stream);      \
+  int dpb200_se_a_descriptor_grad_##SUF(FP* dgr, const FP* dD, const FP* gr, const int* rows,           \
+                                        long long nloc, int M, int axis, double scale,                  \
+                                        dpb200_stream_t stream) {                                       \
+    return dpb200::desc_launch<FP>(true, dgr, dD, gr, rows, nloc, M, axis, scale,                       \
+                                   (cudaStream_t)stream);                                               \
+  }                                                                                                     \
+  int dpb200_mlp_tanh_fwd_##SUF(FP* z_a, FP* y, const FP* h, const FP* idt, long long nrow, int width,  \
+                                dpb200_stream_t stream) {                                               \
+    return dpb200::act_launch<FP>(false, y, z_a, nullptr, 0, h, idt, nrow, width,                       \
+                                  (cudaStream_t)stream);                                                \
+  }                                                                                                     \
+  int dpb200_mlp_tanh_bwd_##SUF(FP* t, const FP* g, long long ldg, const FP* a, const FP* idt,          \
+                                long long nrow, int width, dpb200_stream_t stream) {                    \
+    return dpb200::act_launch<FP>(true, t, const_cast<FP*>(a), g, ldg, nullptr, idt, nrow, width,       \
+                                  (cudaStream_t)stream);                                                \
   }
 DPB200_DEF_DESC(f64, double)
 DPB200_DEF_DESC(f32, float)

@@ -59,6 +59,24 @@ int fma_peak(double* tflops, cudaStream_t st) {
 
 void note_launches(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 
+// Stream-ordered scratch (cudaMallocAsync) must not go back to the OS at every synchronisation:
+// keep it in the device's default pool (set once per device).
+void keep_async_pool() {
+  static std::mutex mu;
+  static bool done[64];
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return;
+  std::lock_guard<std::mutex> lk(mu);
+  if (done[dev]) return;
+  cudaMemPool_t pool;
+  if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+    unsigned long long thr = ~0ull;
+    cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
+  }
+  cudaGetLastError();
+  done[dev] = true;
+}
+
 void set_error(const std::string& msg) { g_error = msg; }
 
 int cuda_fail(cudaError_t e, const char* what, const char* file, int line) {
@@ -91,6 +109,7 @@ extern "C" {
 const char* dpb200_last_error(void) { return dpb200::g_error.c_str(); }
 int dpb200_abi_version(void) { return 1; }
 long long dpb200_launch_count(void) { return dpb200::g_launches.load(std::memory_order_relaxed); }
+void dpb200_count_replayed_launches(long long n) { dpb200::g_launches.fetch_add(n, std::memory_order_relaxed); }
 int dpb200_fma_peak_f64(double* tflops, dpb200_stream_t stream) {
   DPB_REQUIRE(tflops != nullptr, "fma_peak: null output");
   return dpb200::fma_peak<double>(tflops, (cudaStream_t)stream);

@@ -5,36 +5,33 @@
 // with linear extrapolation outside [lower,max) (tabulate.cc:45-73,122-158), the optional
 // se_atten gate g <- g*t + g, and the `is_sorted` fold of the trailing padding (":197-201").
 //
-// What bounds this op on B200 (measured, profiles/r01_*): not HBM and not yet the FP pipe but the
-// coefficient traffic -- every (neighbour, channel) needs 6 coefficients = 4.8 KB per neighbour in
-// fp64 for M=100 -- which a cache-oblivious kernel pulls from L2 (~90 neighbours/atom).  The row
-// distribution is extremely skewed (water: 50% of all look-ups fall into 16 rows, 90% into ~150,
-// because sw(r)/r flattens towards rcut), so the design keeps the hot rows ON CHIP:
-//   * forward: the channel axis is split over gridDim.y CTAs (slice of Mc channels each) so that a
-//     CTA's shared memory (~190 KB) holds H >= 150 hot rows of ITS slice; look-ups that hit the
-//     window are LDS.128, the rest fall back to the (L2-resident) table.  One WARP per (atom,
-//     slice), lanes over channels, persistent loop, no block barrier after the preload;
-//   * backward: all channels of an atom must meet in one reduction, so a CTA caches full-width
-//     rows (fewer of them) and 8 neighbours x 4 components = 32 partial sums per lane are reduced
-//     with ONE butterfly reduce-scatter (31 shuffles) whose result is exactly the 32 contiguous
-//     dy_dem values of those neighbours -> one coalesced store; dy_dem_x needs 9 more shuffles
-//     (the reference does five full warp reductions per neighbour);
-//   * neighbours are "located" 32 at a time in parallel (exact FP division as the reference),
-//     records {dx, delta, em[4], row, multiplicity} are staged in per-warp shared memory and read
-//     back as broadcast LDS by the channel loop;
-//   * consecutive neighbours are distance-sorted, so ~35% of them share the previous row: the
-//     coefficients stay in registers until the row changes;
-//   * the table is read in the reference layout [row][M][6] (one 48-byte record per lane): no
-//     re-layout pass, no scratch allocation.
+// What bounds this op on B200 (measured, profiles/r01_*): neither HBM nor L2 but the L1/shared
+// data pipe and the issue slots -- every (neighbour, channel) needs 6 coefficients = 4.8 KB per
+// neighbour in fp64 for M=100, ~90 neighbours per atom, against only 9 (forward) / 18 (backward)
+// FMAs per coefficient set.  Design:
+//   * one WARP per centre atom, lanes over channels (NC channels per lane), persistent loop, no
+//     block barrier after the preload.  (Splitting the channel axis over CTAs/clusters to enlarge
+//     the on-chip window was measured and lost: per-neighbour bookkeeping and the backward's
+//     reduction are then paid once per slice -- profiles/r01_ncu_full_v2_sliced_summary.csv.)
+//   * the table is re-laid out once per call as T[row][3][M] of coefficient PAIRS so that one
+//     16-byte request per lane is fully dense (the reference layout [row][M][6] costs 2.5x the L1
+//     wavefronts); the most crowded rows (the row histogram is extremely skewed: 50 % of all
+//     look-ups hit 16 rows because sw(r)/r flattens towards rcut) are kept in shared memory;
+//   * neighbours are distance-sorted, so ~35-40 % of them share the previous row: coefficients
+//     stay in registers until the row changes;
+//   * neighbours are "located" 32 at a time in parallel (exact FP division as the reference) one
+//     work item AHEAD of their use (software prefetch of em_x / em hides the HBM latency), records
+//     {dx, delta, mult*em[4], row} are staged in per-warp shared memory and read back as broadcasts;
+//   * backward: 4 neighbours x 4 components = 16 partial sums per lane are reduced with one
+//     butterfly reduce-scatter (16 shuffles) that leaves the 16 contiguous dy_dem values of those
+//     neighbours in the even lanes -> coalesced store; dy_dem_x needs 6 more shuffles (the
+//     reference does five full warp reductions per neighbour).
 // Not a port of source/lib/src/gpu/tabulate.cu (one thread per channel, stride-6 scalar loads, all
 // coefficients from global memory, serial padding search by thread 0).
-#include <cooperative_groups.h>
-
 #include <cmath>
 
 #include "common.cuh"
 
-namespace cg = cooperative_groups;
 
 namespace dpb200 {
 namespace {
@@ -42,6 +39,7 @@ namespace {
 template <typename FP>
 struct TabParams {
   const FP* table;  // [nrow][M][6], reference layout
+  const FP* T;      // [nrow][3][M][2]: coefficient pairs, channel-contiguous (scratch, built per call)
   FP lower, upper, vmax, s0, s1;
   int first;     // int((upper-lower)/s0)
   int tail_idx;  // row of x >= max
@@ -122,42 +120,52 @@ __device__ __forceinline__ void load4(const double* q, bool vec, double (&e)[4])
   }
 }
 
-// the 6 coefficients of one (row, channel): 48 B (3 x 16 B) in fp64, 24 B (3 x 8 B) in fp32
-__device__ __forceinline__ void load6(const double* q, double (&a)[6]) {
-  const double2 u = *reinterpret_cast<const double2*>(q);
-  const double2 v = *reinterpret_cast<const double2*>(q + 2);
-  const double2 w = *reinterpret_cast<const double2*>(q + 4);
-  a[0] = u.x, a[1] = u.y, a[2] = v.x, a[3] = v.y, a[4] = w.x, a[5] = w.y;
-}
-__device__ __forceinline__ void load6(const float* q, float (&a)[6]) {
-  const float2 u = *reinterpret_cast<const float2*>(q);
-  const float2 v = *reinterpret_cast<const float2*>(q + 2);
-  const float2 w = *reinterpret_cast<const float2*>(q + 4);
-  a[0] = u.x, a[1] = u.y, a[2] = v.x, a[3] = v.y, a[4] = w.x, a[5] = w.y;
-}
-__device__ __forceinline__ void load6_g(const double* q, double (&a)[6]) {
-  const double2 u = __ldg(reinterpret_cast<const double2*>(q));
-  const double2 v = __ldg(reinterpret_cast<const double2*>(q + 2));
-  const double2 w = __ldg(reinterpret_cast<const double2*>(q + 4));
-  a[0] = u.x, a[1] = u.y, a[2] = v.x, a[3] = v.y, a[4] = w.x, a[5] = w.y;
-}
-__device__ __forceinline__ void load6_g(const float* q, float (&a)[6]) {
-  const float2 u = __ldg(reinterpret_cast<const float2*>(q));
-  const float2 v = __ldg(reinterpret_cast<const float2*>(q + 2));
-  const float2 w = __ldg(reinterpret_cast<const float2*>(q + 4));
-  a[0] = u.x, a[1] = u.y, a[2] = v.x, a[3] = v.y, a[4] = w.x, a[5] = w.y;
+template <typename FP>
+struct Pair2;
+template <>
+struct Pair2<double> {
+  using type = double2;
+};
+template <>
+struct Pair2<float> {
+  using type = float2;
+};
+
+// [row][M][6] -> [row][3][M] pairs
+template <typename FP>
+__global__ void k_table_relayout(FP* __restrict__ T, const FP* __restrict__ table, long long nrow, int M) {
+  const long long n = nrow * 6 * (long long)M;
+  for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < n;
+       e += (long long)gridDim.x * blockDim.x) {
+    const int h = (int)(e & 1);
+    const long long t = e >> 1;
+    const int k = (int)(t % M);
+    const long long rq = t / M;
+    const int q = (int)(rq % 3);
+    const long long r = rq / 3;
+    T[e] = table[(r * M + k) * 6 + 2 * q + h];
+  }
 }
 
-// Coefficients of (row, slice channel kk): shared-memory window [r0, r0+H) or the global table.
+// Coefficients of (row, channel k): shared-memory window [r0, r0+H) or the global pair table.
 template <typename FP>
-__device__ __forceinline__ void fetch_coef(FP (&a)[6], const FP* __restrict__ hot, const FP* __restrict__ table,
-                                           int row, int r0, int H, int Mc, int M, int c0, int kk) {
+__device__ __forceinline__ void fetch_coef(FP (&a)[6], const FP* __restrict__ hot, const FP* __restrict__ T,
+                                           int row, int r0, int H, int M, int k) {
+  using P2 = typename Pair2<FP>::type;
   const unsigned rel = (unsigned)(row - r0);
+  P2 u, v, w;
   if (rel < (unsigned)H) {
-    load6(hot + ((size_t)rel * Mc + kk) * 6, a);
+    const P2* q = reinterpret_cast<const P2*>(hot) + (size_t)rel * 3 * M + k;
+    u = q[0];
+    v = q[M];
+    w = q[2 * M];
   } else {
-    load6_g(table + ((long long)row * M + c0 + kk) * 6, a);
+    const P2* q = reinterpret_cast<const P2*>(T) + (long long)row * 3 * M + k;
+    u = __ldg(q);
+    v = __ldg(q + M);
+    w = __ldg(q + 2 * M);
   }
+  a[0] = u.x, a[1] = u.y, a[2] = v.x, a[3] = v.y, a[4] = w.x, a[5] = w.y;
 }
 
 // First row of the hot window: the row of the last slot of atom 0 (padding or the farthest
@@ -167,22 +175,20 @@ __device__ __forceinline__ int hot_window_start(const TabParams<FP>& p) {
   FP xx, dl;
   int idx;
   locate(p, p.em_x[(long long)(p.nnei - 1) * p.ldx_j], xx, idx, dl);
-  int r0 = idx - 8;
+  int r0 = idx - 4;
   if (r0 > p.nrow - p.H) r0 = p.nrow - p.H;
   if (r0 < 0) r0 = 0;
   return r0;
 }
 
-// Cooperative preload of rows [r0, r0+H) x channels [c0, c0+mc) into hot[H][Mc][6].
+// Cooperative preload of rows [r0, r0+H) of the pair table into shared memory (same layout).
 template <typename FP>
-__device__ __forceinline__ void preload_hot(FP* __restrict__ hot, const TabParams<FP>& p, int r0, int c0, int mc) {
-  const int per_row = mc * 6;
-  const long long n = (long long)p.H * per_row;
-  for (long long e = threadIdx.x; e < n; e += blockDim.x) {
-    const int r = (int)(e / per_row);
-    const int q = (int)(e - (long long)r * per_row);
-    hot[(size_t)r * p.Mc * 6 + q] = __ldg(p.table + ((long long)(r0 + r) * p.M + c0) * 6 + q);
-  }
+__device__ __forceinline__ void preload_hot(FP* __restrict__ hot, const TabParams<FP>& p, int r0) {
+  using P2 = typename Pair2<FP>::type;
+  const long long n = (long long)p.H * 3 * p.M;
+  const P2* __restrict__ src = reinterpret_cast<const P2*>(p.T) + (long long)r0 * 3 * p.M;
+  P2* dst = reinterpret_cast<P2*>(hot);
+  for (long long e = threadIdx.x; e < n; e += blockDim.x) dst[e] = __ldg(src + e);
 }
 
 // One lane's share of a 32-neighbour chunk, fetched one work item ahead of its use so that the
@@ -263,11 +269,11 @@ extern __shared__ __align__(16) unsigned char tab_smem[];
 
 // ------------------------------------------------------------------------------------------
 // forward (GG=false) and second-order backward (GG=true): both accumulate a [4][M] tile.
-// grid (x: persistent over atoms, y: channel slice); block = nw warps.
-// smem: hot[H][Mc][6] | Rec[nw][32] | RecGG[nw][32] (GG only)
+// grid (x: persistent over atoms, y: block of 32*NC channels); block = nw warps.
+// smem: hot[H][3][M] pairs | Rec[nw][32] | RecGG[nw][32] (GG only)
 // ------------------------------------------------------------------------------------------
 template <typename FP, int NC, bool TWO, bool GG>
-__global__ void __launch_bounds__(NC == 1 ? 1024 : 512) k_tab_fwd(const __grid_constant__ TabParams<FP> p) {
+__global__ void __launch_bounds__(512) k_tab_fwd(const __grid_constant__ TabParams<FP> p) {
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
   const int nw = blockDim.x >> 5;
@@ -275,15 +281,14 @@ __global__ void __launch_bounds__(NC == 1 ? 1024 : 512) k_tab_fwd(const __grid_c
   Rec<FP>* rec = reinterpret_cast<Rec<FP>*>(hot + p.hot_elems) + warp * 32;
   RecGG<FP>* rgg = reinterpret_cast<RecGG<FP>*>(reinterpret_cast<Rec<FP>*>(hot + p.hot_elems) + nw * 32) +
                    (GG ? warp * 32 : 0);
-  const int c0 = blockIdx.y * p.Mc;
-  const int mc = (p.M - c0) < p.Mc ? (p.M - c0) : p.Mc;
+  const int c0 = blockIdx.y * 32 * NC;
   const int r0 = hot_window_start(p);
-  preload_hot(hot, p, r0, c0, mc);
+  preload_hot(hot, p, r0);
   __syncthreads();
 
   bool act[NC];
 #pragma unroll
-  for (int c = 0; c < NC; ++c) act[c] = lane + 32 * c < mc;
+  for (int c = 0; c < NC; ++c) act[c] = c0 + lane + 32 * c < p.M;
 
   const long long stride = (long long)gridDim.x * nw;
   long long i = (long long)blockIdx.x * nw + warp;
@@ -321,7 +326,7 @@ __global__ void __launch_bounds__(NC == 1 ? 1024 : 512) k_tab_fwd(const __grid_c
         cur_row = row;
 #pragma unroll
         for (int c = 0; c < NC; ++c)
-          if (act[c]) fetch_coef(a[c], hot, p.table, row, r0, p.H, p.Mc, p.M, c0, lane + 32 * c);
+          if (act[c]) fetch_coef(a[c], hot, p.T, row, r0, p.H, p.M, c0 + lane + 32 * c);
       }
       const FP xx = r.xx;
       const FP dl = r.delta;
@@ -389,11 +394,11 @@ __global__ void __launch_bounds__(NC == 1 ? 1024 : 512) k_tab_fwd(const __grid_c
 // ------------------------------------------------------------------------------------------
 // first-order backward
 // ------------------------------------------------------------------------------------------
-// v[0..31] per lane -> lane l returns the warp-wide sum of v[l].
+// v[0..15] per lane -> lane l returns the warp-wide sum of v[(l >> 1) & 15].
 template <typename FP>
-__device__ __forceinline__ FP reduce_scatter32(FP (&v)[32], int lane) {
+__device__ __forceinline__ FP reduce_scatter16(FP (&v)[16], int lane) {
 #pragma unroll
-  for (int s = 16, n = 32; s >= 1; s >>= 1, n >>= 1) {
+  for (int s = 16, n = 16; s >= 2; s >>= 1, n >>= 1) {
     const bool up = (lane & s) != 0;
 #pragma unroll
     for (int t = 0; t < n / 2; ++t) {
@@ -402,13 +407,13 @@ __device__ __forceinline__ FP reduce_scatter32(FP (&v)[32], int lane) {
       v[t] = keep + __shfl_xor_sync(kFull, send, s);
     }
   }
-  return v[0];
+  return v[0] + __shfl_xor_sync(kFull, v[0], 1);
 }
-// v[0..7] per lane -> lane l returns the warp-wide sum of v[l >> 2].
+// v[0..3] per lane -> lane l returns the warp-wide sum of v[l >> 3].
 template <typename FP>
-__device__ __forceinline__ FP reduce_scatter8(FP (&v)[8], int lane) {
+__device__ __forceinline__ FP reduce_scatter4(FP (&v)[4], int lane) {
 #pragma unroll
-  for (int s = 16, n = 8; s >= 4; s >>= 1, n >>= 1) {
+  for (int s = 16, n = 4; s >= 8; s >>= 1, n >>= 1) {
     const bool up = (lane & s) != 0;
 #pragma unroll
     for (int t = 0; t < n / 2; ++t) {
@@ -418,168 +423,148 @@ __device__ __forceinline__ FP reduce_scatter8(FP (&v)[8], int lane) {
     }
   }
   FP r = v[0];
+  r += __shfl_xor_sync(kFull, r, 4);
   r += __shfl_xor_sync(kFull, r, 2);
   r += __shfl_xor_sync(kFull, r, 1);
   return r;
 }
 
-// Backward.  grid (x: persistent over atoms, y: S channel slices), thread-block CLUSTER (1, S, 1):
-// the S CTAs of a cluster walk the same atoms in lockstep, each over its own Mc channels with its
-// own shared-memory window of hot rows; per 32-neighbour chunk every warp leaves its 160 partial
-// sums (32 x dy_dem[4] + 32 x dy_dem_x) in its CTA's shared memory, one cluster barrier, then CTA
-// s sums slice s of every buffer across the cluster through distributed shared memory and writes
-// it out (coalesced).  Work items are (atom, chunk) in a fixed order so that all CTAs execute the
-// same number of barriers; chunks behind the fold are empty rounds that write the zero fill.
-// smem: hot[H][Mc][6] | Rec[nw][32] | part[2][nw][160]
+// One warp per atom, all channels of the atom in this warp (blocks of 32*NC channels; for
+// M <= 32*NC the coefficient registers persist across neighbours and atoms).
+// smem: hot[H][3][M] pairs | Rec[nw][32]
 template <typename FP, int NC, bool TWO>
 __global__ void __launch_bounds__(384) k_tab_grad(const __grid_constant__ TabParams<FP> p) {
-  cg::cluster_group cluster = cg::this_cluster();
-  const int S = (int)cluster.num_blocks();
-  const int srank = (int)cluster.block_rank();
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
   const int nw = blockDim.x >> 5;
   FP* hot = reinterpret_cast<FP*>(tab_smem);
   Rec<FP>* rec = reinterpret_cast<Rec<FP>*>(hot + p.hot_elems) + warp * 32;
-  FP* part_base = reinterpret_cast<FP*>(reinterpret_cast<Rec<FP>*>(hot + p.hot_elems) + nw * 32);
   const int M = p.M;
-  const int c0 = blockIdx.y * p.Mc;
-  const int mc = (M - c0) < p.Mc ? (M - c0) : p.Mc;
   const int r0 = hot_window_start(p);
-  preload_hot(hot, p, r0, c0, mc);
+  preload_hot(hot, p, r0);
   __syncthreads();
-  cluster.sync();  // every CTA of the cluster is resident before any DSMEM access
-
-  bool act[NC];
-#pragma unroll
-  for (int c = 0; c < NC; ++c) act[c] = lane + 32 * c < mc;
+  const bool single = M <= 32 * NC;
   const bool fuse_x = p.dy_dem_x == nullptr;  // em_x IS component 0 of em: add its gradient there
-  const int nchunk = (p.nnei + 31) / 32;
-  const long long nblk_atoms = (p.nloc + nw - 1) / nw;  // atom groups of nw
-  const long long T = nblk_atoms > blockIdx.x ? (nblk_atoms - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
-  const long long R = T * nchunk;  // rounds: identical for all CTAs of the cluster
-  const int per = (160 + S - 1) / S;  // entries of every buffer reduced by one CTA
 
-  long long i = ((long long)blockIdx.x) * nw + warp;
+  const long long stride = (long long)gridDim.x * nw;
+  long long i = (long long)blockIdx.x * nw + warp;
+  int j0 = 0;
   Pre<FP, false> pre;
   load_pre(pre, p, i, 0, lane);
   FP last = i < p.nloc ? p.em_x[i * p.ldx_i + (long long)(p.nnei - 1) * p.ldx_j] : (FP)0.;
   FP dyr[4][NC];
-  bool done = false;
+  FP a[NC][6];
+#pragma unroll
+  for (int c = 0; c < NC; ++c)
+#pragma unroll
+    for (int q = 0; q < 6; ++q) a[c][q] = (FP)0.;
+  int cur_row = -1;
 
-  for (long long r = 0; r < R; ++r) {
-    const int c = (int)(r % nchunk);
-    const int j0 = c * 32;
-    const bool have = i < p.nloc;
-    FP* part = part_base + ((size_t)(r & 1) * nw + warp) * 160;
-    if (c == 0) {
-      done = false;
-      if (have) {
-        const FP* __restrict__ dyi = p.dy + i * 4 * (long long)M + c0;
+  while (i < p.nloc) {
+    const FP* __restrict__ dyi = p.dy + i * 4 * (long long)M;
+    if (j0 == 0 && single) {
 #pragma unroll
-        for (int cc = 0; cc < NC; ++cc)
+      for (int c = 0; c < NC; ++c)
 #pragma unroll
-          for (int m = 0; m < 4; ++m) dyr[m][cc] = act[cc] ? dyi[(long long)m * M + lane + 32 * cc] : (FP)0.;
-      }
+        for (int m = 0; m < 4; ++m) dyr[m][c] = (lane + 32 * c < M) ? dyi[(long long)m * M + lane + 32 * c] : (FP)0.;
     }
-    int nproc = 0;
-    if (have && !done) nproc = stage_chunk<FP, false>(p, j0, last, pre, rec, nullptr, lane, done);
-    // next work item (fixed order: next chunk of this atom, then the next atom of this warp)
-    const bool atom_end = c + 1 == nchunk;
-    const long long ni = atom_end ? i + (long long)gridDim.x * nw : i;
+    bool done;
+    const int nproc = stage_chunk<FP, false>(p, j0, last, pre, rec, nullptr, lane, done);
+    const bool atom_end = done || j0 + 32 >= p.nnei;
+    const long long ni = atom_end ? i + stride : i;
     const int nj0 = atom_end ? 0 : j0 + 32;
+    load_pre(pre, p, ni, nj0, lane);
     FP nlast = last;
-    if (!(done && !atom_end)) {  // chunks behind the fold are never staged: skip their loads
-      load_pre(pre, p, ni, nj0, lane);
-      if (atom_end && ni < p.nloc) nlast = p.em_x[ni * p.ldx_i + (long long)(p.nnei - 1) * p.ldx_j];
-    }
-#pragma unroll
-    for (int q = 0; q < 5; ++q) part[lane + 32 * q] = (FP)0.;
-    __syncwarp();
+    if (atom_end && ni < p.nloc) nlast = p.em_x[ni * p.ldx_i + (long long)(p.nnei - 1) * p.ldx_j];
 
-    for (int b = 0; b < nproc; b += 8) {
-      FP v[32];
-      FP vx[8];
+    FP* __restrict__ gem = p.dy_dem + i * p.ldem_i;
+    for (int b = 0; b < nproc; b += 4) {
+      FP v[16];
+      FP vx[4];
 #pragma unroll
-      for (int t = 0; t < 32; ++t) v[t] = (FP)0.;
+      for (int t = 0; t < 16; ++t) v[t] = (FP)0.;
 #pragma unroll
-      for (int t = 0; t < 8; ++t) vx[t] = (FP)0.;
+      for (int t = 0; t < 4; ++t) vx[t] = (FP)0.;
+      for (int kb = 0; kb < M; kb += 32 * NC) {
+        if (!single) {
+          cur_row = -1;
 #pragma unroll
-      for (int cc = 0; cc < NC; ++cc) {
-        const int kk = lane + 32 * cc;
-        const FP d0 = dyr[0][cc], d1 = dyr[1][cc], d2 = dyr[2][cc], d3 = dyr[3][cc];
-        FP a[6] = {(FP)0., (FP)0., (FP)0., (FP)0., (FP)0., (FP)0.};
-        int cur_row = -1;
+          for (int c = 0; c < NC; ++c)
 #pragma unroll
-        for (int u = 0; u < 8; ++u) {
+            for (int m = 0; m < 4; ++m) {
+              const int k = kb + lane + 32 * c;
+              dyr[m][c] = k < M ? dyi[(long long)m * M + k] : (FP)0.;
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
           if (b + u < nproc) {  // warp-uniform
             const Rec<FP>& rc = rec[b + u];
             if (rc.idx != cur_row) {
               cur_row = rc.idx;
-              if (act[cc]) fetch_coef(a, hot, p.table, cur_row, r0, p.H, p.Mc, M, c0, kk);
+#pragma unroll
+              for (int c = 0; c < NC; ++c)
+                if (kb + lane + 32 * c < M) fetch_coef(a[c], hot, p.T, cur_row, r0, p.H, M, kb + lane + 32 * c);
             }
             const FP xx = rc.xx;
-            FP gd = dpoly(a, xx);
-            FP g = poly(a, xx) + gd * rc.delta;
-            // rc.e is pre-multiplied by the fold multiplicity
-            const FP dot = rc.e[0] * d0 + rc.e[1] * d1 + rc.e[2] * d2 + rc.e[3] * d3;
-            if (TWO) {
-              if (act[cc]) {
-                const long long to = (i * p.nnei + j0 + b + u) * (long long)M + c0 + kk;
-                const FP t = p.two[to];
-                p.dy_dtwo[to] = g * dot;
-                g = g * t + g;
-                gd += t * gd;
+            const FP dl = rc.delta;
+            const FP e0 = rc.e[0], e1 = rc.e[1], e2 = rc.e[2], e3 = rc.e[3];  // pre-multiplied by the fold multiplicity
+#pragma unroll
+            for (int c = 0; c < NC; ++c) {
+              FP gd = dpoly(a[c], xx);
+              FP g = poly(a[c], xx) + gd * dl;
+              const FP dot = e0 * dyr[0][c] + e1 * dyr[1][c] + e2 * dyr[2][c] + e3 * dyr[3][c];
+              if (TWO) {
+                const int k = kb + lane + 32 * c;
+                if (k < M) {
+                  const long long to = (i * p.nnei + j0 + b + u) * (long long)M + k;
+                  const FP t = p.two[to];
+                  p.dy_dtwo[to] = g * dot;
+                  g = g * t + g;
+                  gd += t * gd;
+                }
               }
+              vx[u] += gd * dot;
+              v[4 * u + 0] += g * dyr[0][c];
+              v[4 * u + 1] += g * dyr[1][c];
+              v[4 * u + 2] += g * dyr[2][c];
+              v[4 * u + 3] += g * dyr[3][c];
             }
-            vx[u] += gd * dot;
-            v[4 * u + 0] += g * d0;
-            v[4 * u + 1] += g * d1;
-            v[4 * u + 2] += g * d2;
-            v[4 * u + 3] += g * d3;
           }
         }
       }
-      const FP tot = reduce_scatter32(v, lane);
-      const FP totx = reduce_scatter8(vx, lane);  // already carries the multiplicity (through e)
-      const int u = lane >> 2;
-      if (b + u < nproc) {
+      const FP tot = reduce_scatter16(v, lane);   // (u, m) = (lane >> 3, (lane >> 1) & 3)
+      const FP totx = reduce_scatter4(vx, lane);  // u = lane >> 3; carries the multiplicity through e
+      const int u = lane >> 3;
+      if (b + u < nproc && (lane & 1) == 0) {
         const FP mult = (FP)rec[b + u].mult;
+        const int m = (lane >> 1) & 3;
+        const int j = j0 + b + u;
         if (fuse_x) {
-          part[(b + u) * 4 + (lane & 3)] = (lane & 3) == 0 ? tot * mult + totx : tot * mult;
+          gem[(long long)j * 4 + m] = m == 0 ? tot * mult + totx : tot * mult;
         } else {
-          part[(b + u) * 4 + (lane & 3)] = tot * mult;
-          if ((lane & 3) == 0) part[128 + b + u] = totx;
+          gem[(long long)j * 4 + m] = tot * mult;
+          if (m == 0) p.dy_dem_x[i * p.ldx_i + (long long)j * p.ldx_j] = totx;
         }
       }
     }
-    if (TWO && have) {  // dy_dtwo of the slots behind the processed ones is zero
-      const int nvalid = (p.nnei - j0) < 32 ? (p.nnei - j0) : 32;
-      for (int jz = nproc; jz < nvalid; ++jz)
+    if (atom_end) {
+      // everything behind the processed slots is zero (tabulate.cc zero-fills the outputs first)
+      const int jend = j0 + nproc;
+      for (int j = jend + lane; j < p.nnei; j += 32) {
+        if (!fuse_x) p.dy_dem_x[i * p.ldx_i + (long long)j * p.ldx_j] = (FP)0.;
 #pragma unroll
-        for (int cc = 0; cc < NC; ++cc)
-          if (act[cc]) p.dy_dtwo[(i * p.nnei + j0 + jz) * (long long)M + c0 + lane + 32 * cc] = (FP)0.;
-    }
-    cluster.sync();
-    // CTA `srank` finishes entries [srank*per, srank*per+per) of this warp's buffer
-    if (have) {
-      FP* __restrict__ gem = p.dy_dem + i * p.ldem_i;
-      for (int e = srank * per + lane; e < srank * per + per && e < 160; e += 32) {
-        FP sum = (FP)0.;
-        for (int s2 = 0; s2 < S; ++s2) sum += cluster.map_shared_rank(part, s2)[e];
-        if (e < 128) {
-          const int j = j0 + (e >> 2);
-          if (j < p.nnei) gem[(long long)j * 4 + (e & 3)] = sum;
-        } else if (!fuse_x) {
-          const int j = j0 + (e - 128);
-          if (j < p.nnei) p.dy_dem_x[i * p.ldx_i + (long long)j * p.ldx_j] = sum;
-        }
+        for (int m = 0; m < 4; ++m) gem[(long long)j * 4 + m] = (FP)0.;
+      }
+      if (TWO) {
+        for (long long e = (long long)jend * M + lane; e < (long long)p.nnei * M; e += 32)
+          p.dy_dtwo[i * p.nnei * (long long)M + e] = (FP)0.;
       }
     }
     i = ni;
+    j0 = nj0;
     last = nlast;
   }
-  cluster.sync();  // nobody leaves while a neighbour may still read its shared memory
 }
 
 // ------------------------------------------------------------------------------------------
@@ -628,20 +613,33 @@ int common_args(TabParams<FP>& p, const FP* table, const FP* em_x, long long ldx
   return DPB200_OK;
 }
 
-// hot rows that fit beside the per-warp records
 template <typename FP>
-int hot_rows(int nrow, int Mc, size_t other_bytes) {
-  const size_t row_bytes = (size_t)Mc * 6 * sizeof(FP);
+int hot_elems_aligned(int H, int Mc) {
+  const long long per16 = 16 / sizeof(FP);
+  const long long n = (long long)H * Mc * 6;
+  return (int)((n + per16 - 1) / per16 * per16);
+}
+
+// hot rows (full width) that fit beside the per-warp records
+template <typename FP>
+int hot_rows(int nrow, int M, size_t other_bytes) {
+  const size_t row_bytes = (size_t)M * 6 * sizeof(FP);
   if (other_bytes + row_bytes > kSmemBudget) return 0;
   long long h = (long long)((kSmemBudget - other_bytes) / row_bytes);
   return (int)(h < nrow ? h : nrow);
 }
 
 template <typename FP>
-int hot_elems_aligned(int H, int Mc) {
-  const long long per16 = 16 / sizeof(FP);
-  const long long n = (long long)H * Mc * 6;
-  return (int)((n + per16 - 1) / per16 * per16);
+int prepare_table(TabParams<FP>& p, FP** scratch, cudaStream_t st) {
+  const long long n = (long long)p.nrow * 6 * p.M;
+  keep_async_pool();
+  DPB_CUDA(cudaMallocAsync((void**)scratch, (size_t)n * sizeof(FP), st));
+  int grid = ceil_div(n, 256);
+  const int cap = sm_count() * 8;
+  if (grid > cap) grid = cap;
+  k_table_relayout<FP><<<grid, 256, 0, st>>>(*scratch, p.table, p.nrow, p.M);
+  p.T = *scratch;
+  return DPB200_OK;
 }
 
 template <typename FP, bool GG>
@@ -671,37 +669,33 @@ int launch_fwd(FP* out, const FP* table, const FP* info, const FP* em_x, long lo
     DPB_REQUIRE(aligned16(dz_em), "tabulate grad_grad: dz_dy_dem must be 16-byte aligned");
     DPB_REQUIRE(two == nullptr || dz_two != nullptr, "tabulate grad_grad: dz_dy_dtwo is null");
   }
-  // channel slicing: the smallest number of slices whose shared-memory window reaches ~150 rows
-  int S = (M + 127) / 128, Mc = 0, H = 0, nc = 1, nw = 16;
-  size_t rec_bytes = 0;
-  for (;; S *= 2) {
-    Mc = (M + S - 1) / S;
-    nc = Mc <= 32 ? 1 : (Mc <= 64 ? 2 : 4);
-    nw = nc == 1 ? 32 : 16;
-    rec_bytes = (size_t)nw * 32 * (sizeof(Rec<FP>) + (GG ? sizeof(RecGG<FP>) : 0));
-    H = hot_rows<FP>(p.nrow, Mc, rec_bytes);
-    if (H >= (p.nrow < 150 ? p.nrow : 150) || Mc <= 32) break;
-  }
-  S = (M + Mc - 1) / Mc;
-  p.Mc = Mc;
-  p.H = H;
-  p.hot_elems = hot_elems_aligned<FP>(H, Mc);
+  const int nc = M <= 32 ? 1 : (M <= 64 ? 2 : 4);
+  const int nw = 16;
+  const size_t rec_bytes = (size_t)nw * 32 * (sizeof(Rec<FP>) + (GG ? sizeof(RecGG<FP>) : 0));
+  p.Mc = M;
+  p.H = hot_rows<FP>(p.nrow, M, rec_bytes);
+  p.hot_elems = hot_elems_aligned<FP>(p.H, M);
   const size_t smem = (size_t)p.hot_elems * sizeof(FP) + rec_bytes;
+  FP* scratch = nullptr;
+  rc = prepare_table(p, &scratch, st);
+  if (rc) return rc;
   const bool tw = two != nullptr;
+  const int nblk = (M + 32 * nc - 1) / (32 * nc);
   long long want = ((long long)nloc + nw - 1) / nw;
-  const long long cap = (sm_count() + S - 1) / S > 0 ? (long long)((sm_count() + S - 1) / S) : 1;
-  dim3 grid((unsigned)(want < cap ? want : cap), (unsigned)S);
-#define DPB_LAUNCH_FWD(NC)                                                                          \
-  do {                                                                                              \
-    if (tw) {                                                                                       \
-      auto kern = k_tab_fwd<FP, NC, true, GG>;                                                      \
-      DPB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-      kern<<<grid, nw * 32, smem, st>>>(p);                                                         \
-    } else {                                                                                        \
-      auto kern = k_tab_fwd<FP, NC, false, GG>;                                                     \
-      DPB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-      kern<<<grid, nw * 32, smem, st>>>(p);                                                         \
-    }                                                                                               \
+  const long long cap = sm_count() / nblk > 0 ? sm_count() / nblk : 1;
+  dim3 grid((unsigned)(want < cap ? want : cap), (unsigned)nblk);
+  cudaError_t e1 = cudaSuccess;
+#define DPB_LAUNCH_FWD(NC)                                                                      \
+  do {                                                                                          \
+    if (tw) {                                                                                   \
+      auto kern = k_tab_fwd<FP, NC, true, GG>;                                                  \
+      e1 = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);  \
+      if (e1 == cudaSuccess) kern<<<grid, nw * 32, smem, st>>>(p);                              \
+    } else {                                                                                    \
+      auto kern = k_tab_fwd<FP, NC, false, GG>;                                                 \
+      e1 = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);  \
+      if (e1 == cudaSuccess) kern<<<grid, nw * 32, smem, st>>>(p);                              \
+    }                                                                                           \
   } while (0)
   if (nc == 1)
     DPB_LAUNCH_FWD(1);
@@ -710,34 +704,10 @@ int launch_fwd(FP* out, const FP* table, const FP* info, const FP* em_x, long lo
   else
     DPB_LAUNCH_FWD(4);
 #undef DPB_LAUNCH_FWD
-  DPB_CUDA(cudaGetLastError());
-  note_launches(1);
-  return DPB200_OK;
-}
-
-// cluster launch of the backward kernel: grid (x, S), cluster (1, S, 1)
-template <typename K, typename FP>
-int launch_cluster(K kern, const TabParams<FP>& p, int S, int threads, size_t smem, long long want, cudaStream_t st) {
-  DPB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  cudaLaunchConfig_t cfg = {};
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = 1;
-  attr[0].val.clusterDim.y = (unsigned)S;
-  attr[0].val.clusterDim.z = 1;
-  cfg.attrs = attr;
-  cfg.numAttrs = 1;
-  cfg.blockDim = dim3((unsigned)threads);
-  cfg.dynamicSmemBytes = smem;
-  cfg.stream = st;
-  cfg.gridDim = dim3(1, (unsigned)S, 1);
-  int nclusters = 0;
-  if (cudaOccupancyMaxActiveClusters(&nclusters, kern, &cfg) != cudaSuccess || nclusters < 1) {
-    cudaGetLastError();
-    nclusters = sm_count() / S > 0 ? sm_count() / S : 1;
-  }
-  cfg.gridDim = dim3((unsigned)(want < nclusters ? want : nclusters), (unsigned)S, 1);
-  DPB_CUDA(cudaLaunchKernelEx(&cfg, kern, p));
+  if (e1 == cudaSuccess) e1 = cudaGetLastError();
+  cudaFreeAsync(scratch, st);
+  DPB_CUDA(e1);
+  note_launches(2);
   return DPB200_OK;
 }
 
@@ -759,41 +729,43 @@ int launch_grad(FP* dy_dem_x, FP* dy_dem, FP* dy_dtwo, const FP* table, const FP
   p.dy_dem_x = dy_dem_x;
   p.dy_dem = dy_dem;
   p.dy_dtwo = dy_dtwo;
-  DPB_REQUIRE(M <= 1024, "tabulate grad: last_layer_size above 1024 is not supported");
   const int nw = 12;
-  const size_t rec_bytes = (size_t)nw * 32 * sizeof(Rec<FP>) + (size_t)2 * nw * 160 * sizeof(FP);
-  int S = (M + 127) / 128, Mc = 0, H = 0;
-  for (;; S *= 2) {  // cluster sizes 1, 2, 4, 8
-    Mc = (M + S - 1) / S;
-    H = hot_rows<FP>(p.nrow, Mc, rec_bytes);
-    if (H >= (p.nrow < 120 ? p.nrow : 120) || Mc <= 32 || S >= 8) break;
-  }
-  S = (M + Mc - 1) / Mc;
-  p.Mc = Mc;
-  p.H = H;
-  p.hot_elems = hot_elems_aligned<FP>(H, Mc);
+  const size_t rec_bytes = (size_t)nw * 32 * sizeof(Rec<FP>);
+  p.Mc = M;
+  p.H = hot_rows<FP>(p.nrow, M, rec_bytes);
+  p.hot_elems = hot_elems_aligned<FP>(p.H, M);
   const size_t smem = (size_t)p.hot_elems * sizeof(FP) + rec_bytes;
+  FP* scratch = nullptr;
+  rc = prepare_table(p, &scratch, st);
+  if (rc) return rc;
   const bool tw = two != nullptr;
-  const int nc = Mc <= 32 ? 1 : (Mc <= 64 ? 2 : 4);
-  const long long want = ((long long)nloc + nw - 1) / nw;
-  int rc2 = DPB200_OK;
-#define DPB_LAUNCH_GRAD(NC)                                                              \
-  do {                                                                                   \
-    if (tw)                                                                              \
-      rc2 = launch_cluster(k_tab_grad<FP, NC, true>, p, S, nw * 32, smem, want, st);     \
-    else                                                                                 \
-      rc2 = launch_cluster(k_tab_grad<FP, NC, false>, p, S, nw * 32, smem, want, st);    \
+  long long want = ((long long)nloc + nw - 1) / nw;
+  const long long cap = sm_count();
+  const int grid = (int)(want < cap ? want : cap);
+  cudaError_t e1 = cudaSuccess;
+#define DPB_LAUNCH_GRAD(NC)                                                                     \
+  do {                                                                                          \
+    if (tw) {                                                                                   \
+      auto kern = k_tab_grad<FP, NC, true>;                                                     \
+      e1 = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);  \
+      if (e1 == cudaSuccess) kern<<<grid, nw * 32, smem, st>>>(p);                              \
+    } else {                                                                                    \
+      auto kern = k_tab_grad<FP, NC, false>;                                                    \
+      e1 = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);  \
+      if (e1 == cudaSuccess) kern<<<grid, nw * 32, smem, st>>>(p);                              \
+    }                                                                                           \
   } while (0)
-  if (nc == 1)
+  if (M <= 32)
     DPB_LAUNCH_GRAD(1);
-  else if (nc == 2)
+  else if (M <= 64)
     DPB_LAUNCH_GRAD(2);
   else
     DPB_LAUNCH_GRAD(4);
 #undef DPB_LAUNCH_GRAD
-  if (rc2) return rc2;
-  DPB_CUDA(cudaGetLastError());
-  note_launches(1);
+  if (e1 == cudaSuccess) e1 = cudaGetLastError();
+  cudaFreeAsync(scratch, st);
+  DPB_CUDA(e1);
+  note_launches(2);
   return DPB200_OK;
 }
 

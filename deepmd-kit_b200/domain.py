@@ -143,7 +143,7 @@ class DomainDeepPot(DeepPotB200):
     and virial (all-reduced) and the forces on this rank's own atoms."""
 
     def __init__(self, model: SeAModel, grid, skin: float = 2.0, nlist_every: int = 10, group=None):
-        super().__init__(model, skin, nlist_every)
+        super().__init__(model, skin, nlist_every, use_graph=False)  # NCCL exchanges stay eager
         self.grid = tuple(grid)
         self.group = group
         self.rank = dist.get_rank(group) if dist.is_initialized() else 0
@@ -190,8 +190,9 @@ class DomainDeepPot(DeepPotB200):
         gt = torch.empty(self.plan.nghost, dtype=torch.int32, device=c.device)
         self.plan.exchange(atype.to(torch.int32).index_select(0, self.plan.sendlist.long()), gt)
         ext_t = torch.cat([atype.to(torch.int32), gt]).contiguous()
-        numneigh, rows = ops.build_nlist(ext_c, nloc, rc, ext_t)
-        perm, ranges = type_partition(atype, m.cfg.ntypes)
+        self.state = None
+        numneigh, rows = ops.build_nlist(ext_c, nloc, rc, ext_t, cache=self._cache)
+        perm, ranges = self._type_partition(atype)
         self.state = NeighborState(nloc, ext_t, None, None, numneigh, rows, perm, ranges)
         return self.state
 

@@ -102,32 +102,30 @@ class FittingNet:
 
     @torch.no_grad()
     def forward_backward(self, x: torch.Tensor):
-        """Atomic energies e[n] and dE/dx[n, dim_in] with a hand-written backward: six GEMMs and a few
-        in-place elementwise passes over [n, width] (no autograd graph, no saved [n, dim_in] copies)."""
+        """Atomic energies e[n] and dE/dx[n, dim_in] with a hand-written backward: six cuBLAS GEMMs; every
+        elementwise chain (tanh, resnet_dt, skip / its derivative) is one dpb200 pass, the skip connection
+        of the backward rides in the GEMM epilogue (beta = 1)."""
         acts = []
         h = x
         for w, b, idt in self.layers:
-            a = torch.addmm(b, h, w).tanh_()
-            y = a * idt if idt is not None else a.clone()
-            if w.shape[0] == w.shape[1]:
-                y.add_(h)
-            elif w.shape[1] == 2 * w.shape[0]:
+            a = torch.addmm(b, h, w)
+            same = w.shape[0] == w.shape[1]
+            y = ops.mlp_tanh_fwd(a, h if same else None, idt)  # a <- tanh(a)
+            if w.shape[1] == 2 * w.shape[0]:
                 y.add_(torch.cat([h, h], 1))
             acts.append(a)
             h = y
         e = torch.addmv(self.head[1], h, self.head[0][:, 0])
-        g = self.head[0][:, 0].unsqueeze(0).expand(x.shape[0], -1)
+        g = self.head[0][:, 0].unsqueeze(0).expand(x.shape[0], -1)  # stride-0 rows: never materialised
         for (w, b, idt), a in zip(reversed(self.layers), reversed(acts)):
-            t = a.mul(a).neg_().add_(1.0).mul_(g)  # g * (1 - tanh^2)
-            if idt is not None:
-                t.mul_(idt)
-            gin = t @ w.t()
+            t = ops.mlp_tanh_bwd(g, a, idt)
             if w.shape[0] == w.shape[1]:
-                gin.add_(g)
+                g = torch.addmm(g, t, w.t())
             elif w.shape[1] == 2 * w.shape[0]:
                 n_in = w.shape[0]
-                gin.add_(g[:, :n_in]).add_(g[:, n_in:])
-            g = gin
+                g = torch.addmm(g[:, :n_in] + g[:, n_in:], t, w.t())
+            else:
+                g = t @ w.t()
         return e, g
 
 
@@ -169,18 +167,17 @@ class SeAModel:
         nloc = xyz.shape[0]
         dy = torch.empty_like(xyz)
         e_atom = torch.empty(nloc, dtype=self.dtype, device=xyz.device)
+        type_perm32 = type_perm.to(torch.int32)
         inv = 1.0 / cfg.nnei
         for t, (a, b) in enumerate(type_ranges):
             for c0 in range(a, b, self.fit_chunk):
                 c1 = min(b, c0 + self.fit_chunk)
-                idx = type_perm[c0:c1]
-                x = xyz.index_select(0, idx)
-                d = ops.se_a_descriptor(x, cfg.axis_neuron, inv)
+                idx = type_perm32[c0:c1]
+                d = ops.se_a_descriptor(xyz, cfg.axis_neuron, inv, rows=idx)  # gathers the atoms of this type
                 e, gd = self.fit[t].forward_backward(d)
                 del d
-                g = ops.se_a_descriptor_grad(gd, x, cfg.axis_neuron, inv)
-                dy.index_copy_(0, idx, g)
-                e_atom.index_copy_(0, idx, e)
+                ops.se_a_descriptor_grad(gd, xyz, cfg.axis_neuron, inv, rows=idx, out=dy)  # scatters back
+                e_atom.index_copy_(0, type_perm[c0:c1], e)
         return e_atom.sum(), e_atom, dy
 
     def evaluate(self, ext_coord, ext_type, numneigh, rows, mapping, nloc, type_perm, type_ranges, atom_virial=False,
@@ -218,6 +215,7 @@ class NeighborState:
     type_perm: torch.Tensor
     type_ranges: list
     ago: int = 0
+    map64: Optional[torch.Tensor] = None
 
 
 def type_partition(atype: torch.Tensor, ntypes: int):
@@ -235,39 +233,100 @@ class DeepPotB200:
     host arrays in and out.  The raw neighbour list is rebuilt every `nlist_every` evaluations with a
     `skin` (the reference MD set-up examples/water/lmp/in.lammps:7-8: neighbor 2.0 bin, every 10)."""
 
-    def __init__(self, model: SeAModel, skin: float = 2.0, nlist_every: int = 10):
+    def __init__(self, model: SeAModel, skin: float = 2.0, nlist_every: int = 10, use_graph: bool = True):
         self.model = model
         self.skin = float(skin)
         self.nlist_every = int(nlist_every)
+        # The steady-state step (everything between two list rebuilds) has static shapes and no host
+        # decisions: it is captured once into a CUDA graph and replayed, so an MD step costs one graph
+        # launch on the host instead of ~400 kernel launches.
+        self.use_graph = bool(use_graph)
+        self._graph = None
+        self._graph_key = None
+        self._graph_launches = 0
         self.state: Optional[NeighborState] = None
+        self._cache = {}  # persistent device buffers of the neighbour-list rebuild
         self._pin_in = None
         self._pin_out = None
 
     def reset(self):
         self.state = None
 
+    def _type_partition(self, atype: torch.Tensor):
+        """Atom types do not change between rebuilds: sort them once per type tensor."""
+        key = (atype.data_ptr(), atype.numel())
+        hit = self._cache.get("perm")
+        if hit is None or hit[0] != key:
+            hit = (key,) + type_partition(atype, self.model.cfg.ntypes)
+            self._cache["perm"] = hit
+        return hit[1], hit[2]
+
     def build_neighbors(self, coord: torch.Tensor, atype: torch.Tensor, box) -> NeighborState:
         m = self.model
         rc = m.cfg.rcut + self.skin
-        c = coord.reshape(-1, 3).clone()
-        ops.normalize_coord(c, box)
-        ext_c, ext_t, mapping = ops.copy_coord(c, atype, box, rc)
+        self.state = None  # the views below alias the cached buffers of the previous list
         nloc = atype.numel()
-        numneigh, rows = ops.build_nlist(ext_c, nloc, rc, ext_t)
-        shift = ext_c - coord.reshape(-1, 3).index_select(0, mapping.long())
-        perm, ranges = type_partition(atype, m.cfg.ntypes)
-        self.state = NeighborState(nloc, ext_t.contiguous(), mapping.contiguous(), shift, numneigh, rows, perm, ranges)
+        c = ops._buf(self._cache, "norm_c", (nloc, 3), coord.dtype, coord.device)
+        c.copy_(coord.reshape(-1, 3))
+        ops.normalize_coord(c, box)
+        ext_c, ext_t, mapping = ops.copy_coord(c, atype, box, rc, cache=self._cache)
+        numneigh, rows = ops.build_nlist(ext_c, nloc, rc, ext_t, cache=self._cache)
+        map64 = ops._buf(self._cache, "map64", (mapping.numel(),), torch.int64, coord.device)
+        map64.copy_(mapping)
+        shift = ops._buf(self._cache, "shift", (mapping.numel(), 3), coord.dtype, coord.device)
+        torch.index_select(coord.reshape(-1, 3), 0, map64, out=shift)
+        torch.sub(ext_c, shift, out=shift)
+        perm, ranges = self._type_partition(atype)
+        self.state = NeighborState(nloc, ext_t, mapping, shift, numneigh, rows, perm, ranges, map64=map64)
         return self.state
 
+    def _step(self, coord, atom_virial, fused):
+        st = self.state
+        ext_c = coord.reshape(-1, 3).index_select(0, st.map64).add_(st.shift)
+        return self.model.evaluate(ext_c, st.ext_type, st.numneigh, st.rows, st.mapping, st.nloc, st.type_perm,
+                                   st.type_ranges, atom_virial=atom_virial, fused=fused)
+
     def eval_device(self, coord: torch.Tensor, atype: torch.Tensor, box, atom_virial=False, fused=True):
-        """Device tensors in, device tensors out (no host copies)."""
+        """Device tensors in, device tensors out (no host copies).  With `use_graph` the returned tensors
+        live in the graph's memory pool and are overwritten by the next call."""
         st = self.state
         if st is None or st.ago >= self.nlist_every or st.nloc != atype.numel():
             st = self.build_neighbors(coord, atype, box)
-        ext_c = coord.reshape(-1, 3).index_select(0, st.mapping.long()) + st.shift
         st.ago += 1
-        return self.model.evaluate(ext_c, st.ext_type, st.numneigh, st.rows, st.mapping, st.nloc, st.type_perm,
-                                   st.type_ranges, atom_virial=atom_virial, fused=fused)
+        if not self.use_graph:
+            return self._step(coord, atom_virial, fused)
+        key = (st.nloc, int(st.ext_type.numel()), int(st.rows.shape[1]), st.rows.data_ptr(), st.ext_type.data_ptr(),
+               bool(atom_virial), bool(fused), coord.dtype)
+        if self._graph is None or self._graph_key != key:
+            self._graph = None
+            self._g_out = None
+            self._g_coord = torch.empty_like(coord.reshape(-1, 3))
+            self._g_coord.copy_(coord.reshape(-1, 3))
+            self._step(self._g_coord, atom_virial, fused)  # eager warm-up (cuBLAS handles, attributes)
+            torch.cuda.synchronize(coord.device)
+            torch.cuda.empty_cache()
+            from ._lib import lib
+
+            n0 = lib().launch_count()
+            graph = torch.cuda.CUDAGraph()
+            try:
+                with torch.cuda.graph(graph):
+                    self._g_out = self._step(self._g_coord, atom_virial, fused)
+            except Exception as exc:  # keep working eagerly, but say so
+                import warnings
+
+                warnings.warn(f"dpb200: CUDA graph capture of the force step failed ({exc!r}); running eagerly")
+                self.use_graph = False
+                torch.cuda.synchronize(coord.device)
+                return self._step(coord, atom_virial, fused)
+            self._graph_launches = lib().launch_count() - n0
+            self._graph, self._graph_key = graph, key
+        self._g_coord.copy_(coord.reshape(-1, 3))
+        self._graph.replay()
+        from ._lib import lib
+
+        lib().cdll.dpb200_count_replayed_launches(self._graph_launches)
+        return self._g_out
 
     def eval(self, coords, cells, atom_types, atomic: bool = False):
         """coords [nframes, natoms*3], cells [nframes, 9], atom_types [natoms] (host arrays).
@@ -283,22 +342,25 @@ class DeepPotB200:
             self._pin_in = torch.empty(nat * 3, dtype=m.dtype).pin_memory()
             self._pin_out = torch.empty(nat * 3 + 10, dtype=m.dtype).pin_memory()
             self._atype = torch.as_tensor(np.asarray(atom_types, np.int32)).to(dev)
-        es, fs, vs, aes, avs = [], [], [], [], []
+        e_out = np.empty((nf, 1), np_dt)
+        f_out = np.empty((nf, nat, 3), np_dt)
+        v_out = np.empty((nf, 9), np_dt)
+        aes, avs = [], []
         for f in range(nf):
-            self._pin_in.copy_(torch.as_tensor(coords[f].astype(np_dt, copy=False)))
+            self._pin_in.copy_(torch.from_numpy(np.ascontiguousarray(coords[f], dtype=np_dt)))
             c = self._pin_in.to(dev, non_blocking=True)
             e, force, virial, ex = self.eval_device(c, self._atype, cells[f], atom_virial=atomic)
             out = torch.cat([force.reshape(-1), virial.reshape(-1), e.reshape(1)])
             self._pin_out.copy_(out, non_blocking=True)
             torch.cuda.current_stream(dev).synchronize()
             o = self._pin_out.numpy()
-            fs.append(o[: nat * 3].reshape(nat, 3).copy())
-            vs.append(o[nat * 3: nat * 3 + 9].copy())
-            es.append(o[nat * 3 + 9: nat * 3 + 10].copy())
+            f_out[f] = o[: nat * 3].reshape(nat, 3)
+            v_out[f] = o[nat * 3: nat * 3 + 9]
+            e_out[f, 0] = o[nat * 3 + 9]
             if atomic:
                 aes.append(ex["atom_energy"].cpu().numpy())
                 avs.append(ex["atom_virial"].cpu().numpy().reshape(nat, 9))
-        res = (np.stack(es), np.stack(fs), np.stack(vs))
+        res = (e_out, f_out, v_out)
         if atomic:
             res = res + (np.stack(aes)[..., None], np.stack(avs))
         return res

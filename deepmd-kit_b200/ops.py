@@ -377,7 +377,24 @@ def normalize_coord(coord, box):
     return coord
 
 
-def copy_coord(coord, atype, box, rcut, mem_nall=None):
+def _buf(cache, name, shape, dtype, dev):
+    """A tensor of `shape` carved from a cached flat buffer (grown when too small): neighbour-list
+    rebuilds then cause no allocator traffic (a 1.5 GB cudaMalloc in the middle of an MD run costs more
+    than the rebuild itself)."""
+    n = 1
+    for d in shape:
+        n *= int(d)
+    if cache is None:
+        return torch.empty(shape, dtype=dtype, device=dev)
+    t = cache.get(name)
+    if t is None or t.numel() < n or t.dtype != dtype or t.device != dev:
+        cache[name] = None
+        t = torch.empty(max(n, 1), dtype=dtype, device=dev)
+        cache[name] = t
+    return t[:n].view(shape)
+
+
+def copy_coord(coord, atype, box, rcut, mem_nall=None, cache=None):
     """deepmd::copy_coord_gpu (coord.h:57-85) with the caller-side retry folded in:
     returns (ext_coord[nall,3], ext_type[nall], mapping[nall])."""
     dev = _need_cuda(("coord", coord), ("type", atype))
@@ -387,17 +404,21 @@ def copy_coord(coord, atype, box, rcut, mem_nall=None):
     nloc = atype.numel()
     b = _box_host(box, coord.dtype)
     L = lib()
-    ws = _workspace(L.cdll.dpb200_copy_coord_workspace_bytes(nloc), dev)
+    ws = _buf(cache, "cc_ws", (max(int(L.cdll.dpb200_copy_coord_workspace_bytes(nloc)), 256),), torch.uint8, dev)
     mem = int(mem_nall) if mem_nall is not None else max(64, 2 * nloc)
+    if cache is not None and mem_nall is None and cache.get("cc_nall"):
+        mem = max(64, int(cache["cc_nall"] * 1.05) + 64)
     for _ in range(8):
-        out_c = torch.empty((mem, 3), dtype=coord.dtype, device=dev)
-        out_t = torch.empty(mem, dtype=torch.int32, device=dev)
-        mapping = torch.empty(mem, dtype=torch.int32, device=dev)
+        out_c = _buf(cache, "cc_c", (mem, 3), coord.dtype, dev)
+        out_t = _buf(cache, "cc_t", (mem,), torch.int32, dev)
+        mapping = _buf(cache, "cc_m", (mem,), torch.int32, dev)
         nall = C.c_int(0)
         rc = L.call("copy_coord_" + s, _p(out_c), _p(out_t), _p(mapping), C.byref(nall), _p(coord), _p(atype), nloc,
                     mem, float(rcut), C.c_void_p(b.data_ptr()), _p(ws), ws.numel(), _stream(dev))
         if rc == 0:
             n = nall.value
+            if cache is not None:
+                cache["cc_nall"] = n
             return out_c[:n], out_t[:n], mapping[:n]
         if mem_nall is not None:
             raise MemoryError(f"copy_coord: nall={nall.value} exceeds mem_nall={mem_nall}")
@@ -405,7 +426,7 @@ def copy_coord(coord, atype, box, rcut, mem_nall=None):
     raise RuntimeError("copy_coord: retry limit reached")
 
 
-def build_nlist(coord, nloc, rcut, atype=None, mem_size=None):
+def build_nlist(coord, nloc, rcut, atype=None, mem_size=None, cache=None):
     """deepmd::build_nlist_gpu (source/lib/include/neighbor_list.h:256-266), cell list, with the
     caller-side doubling retry folded in: returns (numneigh[nloc], rows[nloc, mem_size])."""
     dev = _need_cuda(("coord", coord), ("type", atype))
@@ -415,15 +436,19 @@ def build_nlist(coord, nloc, rcut, atype=None, mem_size=None):
     if atype is not None:
         atype = _c(atype, torch.int32)
     L = lib()
-    ws = _workspace(L.cdll.dpb200_build_nlist_workspace_bytes(nall), dev)
+    ws = _buf(cache, "bn_ws", (max(int(L.cdll.dpb200_build_nlist_workspace_bytes(nall)), 256),), torch.uint8, dev)
     mem = int(mem_size) if mem_size is not None else 256
+    if cache is not None and mem_size is None and cache.get("bn_mem"):
+        mem = int(cache["bn_mem"])
     for _ in range(8):
-        numneigh = torch.empty(nloc, dtype=torch.int32, device=dev)
-        rows = torch.empty((nloc, mem), dtype=torch.int32, device=dev)
+        numneigh = _buf(cache, "bn_n", (nloc,), torch.int32, dev)
+        rows = _buf(cache, "bn_rows", (nloc, mem), torch.int32, dev)
         mx = C.c_int(0)
         rc = L.call("build_nlist_" + s, _p(numneigh), _p(rows), C.byref(mx), _p(coord), nloc, nall, mem, float(rcut),
                     _p(atype), _p(ws), ws.numel(), _stream(dev))
         if rc == 0:
+            if cache is not None:
+                cache["bn_mem"] = mem
             return numneigh, rows
         if mem_size is not None:
             raise MemoryError(f"build_nlist: a row needs {mx.value} entries, mem_size={mem_size}")
@@ -442,26 +467,55 @@ def use_nlist_map(nlist, mapping):
     return nlist
 
 
-def se_a_descriptor(gr, axis, scale):
-    """D = (gr*scale)^T (gr*scale)[:, :axis] per atom: [n,4,M] -> [n, M*axis] (dpb200_se_a_descriptor)."""
-    dev = _need_cuda(("gr", gr))
+def se_a_descriptor(gr, axis, scale, rows=None):
+    """D[i] = (gr[r]*scale)^T (gr[r]*scale)[:, :axis], r = rows[i] (or i): [*,4,M] -> [n, M*axis]."""
+    dev = _need_cuda(("gr", gr), ("rows", rows))
     s = _suffix(gr)
     gr = _c(gr)
-    n, _, M = gr.shape
+    M = gr.shape[2]
+    if rows is not None:
+        rows = _c(rows, torch.int32)
+    n = gr.shape[0] if rows is None else rows.numel()
     out = torch.empty((n, M * int(axis)), dtype=gr.dtype, device=dev)
-    lib().call("se_a_descriptor_" + s, _p(out), _p(gr), n, M, int(axis), float(scale), _stream(dev))
+    lib().call("se_a_descriptor_" + s, _p(out), _p(gr), _p(rows), n, M, int(axis), float(scale), _stream(dev))
     return out
 
 
-def se_a_descriptor_grad(dD, gr, axis, scale):
-    """dE/d(gr) [n,4,M] from dE/dD [n, M*axis] (dpb200_se_a_descriptor_grad)."""
-    dev = _need_cuda(("dD", dD), ("gr", gr))
+def se_a_descriptor_grad(dD, gr, axis, scale, rows=None, out=None):
+    """dE/d(gr[r]) for r = rows[i] (or i) from dE/dD[i]; written into `out` ([*,4,M], default new)."""
+    dev = _need_cuda(("dD", dD), ("gr", gr), ("rows", rows))
     s = _suffix(gr)
     gr, dD = _c(gr), _c(dD, gr.dtype)
-    n, _, M = gr.shape
-    out = torch.empty_like(gr)
-    lib().call("se_a_descriptor_grad_" + s, _p(out), _p(dD), _p(gr), n, M, int(axis), float(scale), _stream(dev))
+    M = gr.shape[2]
+    if rows is not None:
+        rows = _c(rows, torch.int32)
+    n = dD.shape[0]
+    if out is None:
+        out = torch.empty_like(gr)
+    lib().call("se_a_descriptor_grad_" + s, _p(out), _p(dD), _p(gr), _p(rows), n, M, int(axis), float(scale),
+               _stream(dev))
     return out
+
+
+def mlp_tanh_fwd(z, h=None, idt=None):
+    """In place a = tanh(z); returns y = a*idt (+ h).  `z` becomes `a` (kept for the backward)."""
+    dev = _need_cuda(("z", z), ("h", h), ("idt", idt))
+    s = _suffix(z)
+    y = torch.empty_like(z)
+    lib().call("mlp_tanh_fwd_" + s, _p(z), _p(y), _p(h), _p(idt), z.shape[0], z.shape[1], _stream(dev))
+    return y
+
+
+def mlp_tanh_bwd(g, a, idt=None):
+    """t = g * idt * (1 - a^2); g may be a row-strided view (leading stride g.stride(0))."""
+    dev = _need_cuda(("g", g), ("a", a), ("idt", idt))
+    s = _suffix(a)
+    if g.stride(1) != 1 and g.shape[0] > 1:
+        g = g.contiguous()
+    ldg = g.stride(0) if g.shape[0] > 1 else g.shape[1]
+    t = torch.empty_like(a)
+    lib().call("mlp_tanh_bwd_" + s, _p(t), _p(g), int(ldg), _p(a), _p(idt), a.shape[0], a.shape[1], _stream(dev))
+    return t
 
 
 def halo_pack(coord, sendlist, shift):

@@ -46,6 +46,8 @@ const char* dpb200_last_error(void);
 int dpb200_abi_version(void);
 /* Number of dpb200 kernels enqueued by this process so far (all threads). */
 long long dpb200_launch_count(void);
+/* Bookkeeping only: kernels re-issued by replaying a CUDA graph that captured dpb200 calls. */
+void dpb200_count_replayed_launches(long long n);
 /* Measured peak FMA rate (TFLOP/s, 2 flops per FMA) of the FP64 / FP32 pipe of the current device:
  * the roofline denominator of the tabulate kernels (MEASURED_PEAKS.json has no such entry). */
 int dpb200_fma_peak_f64(double* tflops /*host out*/, dpb200_stream_t stream);
@@ -209,16 +211,25 @@ DPB200_DECL_HALO(f32, float)
 #undef DPB200_DECL_HALO
 
 /* ---------------------------------------------------------------------------------------
- * se_e2_a descriptor contraction  D[i] = (gr[i]*scale)^T (gr[i]*scale)[:, :axis]  and its backward
+ * se_e2_a descriptor contraction  D[i] = (gr[r]*scale)^T (gr[r]*scale)[:, :axis]  and its backward
  * (deepmd/pt/model/descriptor/se_a.py:843-850: xyz_scatter /= nnei; matmul(xyz_scatter_1,
- * xyz_scatter_2)).  gr [nloc][4][M] = summed tabulate output, scale = 1/nnei, D [nloc][M*axis],
- * dgr [nloc][4][M] = dE/d(gr) given dD = dE/dD.
+ * xyz_scatter_2)).  gr [*][4][M] = summed tabulate output, scale = 1/nnei, D [nloc][M*axis];
+ * rows (may be NULL = identity): row i of D / dD belongs to atom r = rows[i] of gr / dgr, so the
+ * per-type gather of the fitting net and the scatter of its gradient need no extra pass.
+ * mlp_tanh_fwd / _bwd: the elementwise part of one fitting-net layer (deepmd/pt/model/network/
+ * mlp.py: y = tanh(z)*idt + h; t = g*idt*(1 - tanh^2)), z_a is overwritten by tanh(z).
  * ------------------------------------------------------------------------------------- */
 #define DPB200_DECL_DESC(SUF, FP)                                                                       \
-  int dpb200_se_a_descriptor_##SUF(FP* D, const FP* gr, long long nloc, int M, int axis, double scale,  \
-                                   dpb200_stream_t stream);                                             \
-  int dpb200_se_a_descriptor_grad_##SUF(FP* dgr, const FP* dD, const FP* gr, long long nloc, int M,     \
-                                        int axis, double scale, dpb200_stream_t stream);
+  int dpb200_se_a_descriptor_##SUF(FP* D, const FP* gr, const int* rows, long long nloc, int M,         \
+                                   int axis, double scale, dpb200_stream_t stream);                     \
+  int dpb200_se_a_descriptor_grad_##SUF(FP* dgr, const FP* dD, const FP* gr, const int* rows,           \
+                                        long long nloc, int M, int axis, double scale,                  \
+                                        dpb200_stream_t stream);                                        \
+  int dpb200_mlp_tanh_fwd_##SUF(FP* z_a, FP* y, const FP* h /*nullable*/, const FP* idt /*nullable*/,   \
+                                long long nrow, int width, dpb200_stream_t stream);                     \
+  int dpb200_mlp_tanh_bwd_##SUF(FP* t, const FP* g, long long ldg, const FP* a,                         \
+                                const FP* idt /*nullable*/, long long nrow, int width,                  \
+                                dpb200_stream_t stream);
 DPB200_DECL_DESC(f64, double)
 DPB200_DECL_DESC(f32, float)
 #undef DPB200_DECL_DESC
