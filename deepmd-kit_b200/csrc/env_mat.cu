@@ -132,7 +132,7 @@ __device__ __forceinline__ void rank_and_place(const u64* __restrict__ keys, int
 }
 
 template <typename FP, bool kEnv>
-__global__ void __launch_bounds__(128) k_env_mat_a(const __grid_constant__ EnvParams<FP> p) {
+__global__ void __launch_bounds__(128, 5) k_env_mat_a(const __grid_constant__ EnvParams<FP> p) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
@@ -161,25 +161,41 @@ __global__ void __launch_bounds__(128) k_env_mat_a(const __grid_constant__ EnvPa
     // ---- A: gather, float cutoff test, ballot-compact the survivors' keys ----------------
     for (int s = lane; s < nnei; s += 32) slot_j[s] = -1;
     int nsurv = 0;
-    for (int b = 0; b < n; b += 32) {
-      const int k = b + lane;
-      bool ok = false;
-      u64 key = 0;
-      if (k < n) {
-        const int j = rowp[k];
-        const float4 cj = p.packed[fbase + j];
-        const int tj = __float_as_int(cj.w);
-        // (float)rj - (float)ri, then dx*dx + dy*dy + dz*dz left to right, no contraction
-        const float dx = __fsub_rn(cj.x, ci.x);
-        const float dy = __fsub_rn(cj.y, ci.y);
-        const float dz = __fsub_rn(cj.z, ci.z);
-        const float rr2 = __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
-        ok = (tj >= 0) && (rr2 <= p.rcut2);
-        key = ((u64)(unsigned)tj << kTypeShift) | ((u64)__float_as_uint(rr2) << kIdxBits) | (u64)(unsigned)j;
+    // 8 x 32 candidates per pass: all index loads first, then all coordinate gathers, so that one
+    // pass costs two memory round trips instead of sixteen
+    for (int b0 = 0; b0 < n; b0 += 256) {
+      int jv[8];
+      float4 cv[8];
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        const int k = b0 + 32 * q + lane;
+        jv[q] = k < n ? rowp[k] : -1;
       }
-      const unsigned m = __ballot_sync(kFull, ok);
-      if (ok) keys[nsurv + __popc(m & lt_mask)] = key;
-      nsurv += __popc(m);
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        if (jv[q] >= 0) cv[q] = p.packed[fbase + jv[q]];
+      }
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        if (b0 + 32 * q >= n) break;  // warp-uniform
+        bool ok = false;
+        u64 key = 0;
+        if (jv[q] >= 0) {
+          const int j = jv[q];
+          const float4 cj = cv[q];
+          const int tj = __float_as_int(cj.w);
+          // (float)rj - (float)ri, then dx*dx + dy*dy + dz*dz left to right, no contraction
+          const float dx = __fsub_rn(cj.x, ci.x);
+          const float dy = __fsub_rn(cj.y, ci.y);
+          const float dz = __fsub_rn(cj.z, ci.z);
+          const float rr2 = __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
+          ok = (tj >= 0) && (rr2 <= p.rcut2);
+          key = ((u64)(unsigned)tj << kTypeShift) | ((u64)__float_as_uint(rr2) << kIdxBits) | (u64)(unsigned)j;
+        }
+        const unsigned m = __ballot_sync(kFull, ok);
+        if (ok) keys[nsurv + __popc(m & lt_mask)] = key;
+        nsurv += __popc(m);
+      }
     }
     if (lane < 2) keys[nsurv + lane] = ~0ull;  // sentinels for the paired rank loop
     __syncwarp();

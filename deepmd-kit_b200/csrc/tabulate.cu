@@ -264,6 +264,19 @@ template <typename FP>
 __device__ __forceinline__ FP dpoly(const FP (&a)[6], FP x) {
   return a[1] + ((FP)2. * a[2] + ((FP)3. * a[3] + ((FP)4. * a[4] + (FP)5. * a[5] * x) * x) * x) * x;
 }
+// value and derivative together by synthetic division (Horner twice): 9 FMAs, no multiplies
+template <typename FP>
+__device__ __forceinline__ void poly_both(const FP (&a)[6], FP x, FP& g, FP& gd) {
+  const FP b4 = a[4] + a[5] * x;
+  const FP b3 = a[3] + b4 * x;
+  const FP b2 = a[2] + b3 * x;
+  const FP b1 = a[1] + b2 * x;
+  g = a[0] + b1 * x;
+  const FP c4 = b4 + a[5] * x;
+  const FP c3 = b3 + c4 * x;
+  const FP c2 = b2 + c3 * x;
+  gd = b1 + c2 * x;
+}
 
 extern __shared__ __align__(16) unsigned char tab_smem[];
 
@@ -343,11 +356,16 @@ __global__ void __launch_bounds__(512) k_tab_fwd(const __grid_constant__ TabPara
       const long long two_off = ((i * p.nnei + j0 + jj) * (long long)p.M) + c0 + lane;
 #pragma unroll
       for (int c = 0; c < NC; ++c) {
-        FP g = poly(a[c], xx);
-        FP gd = (FP)0.;
-        if (GG || dl != (FP)0.) {
-          gd = dpoly(a[c], xx);
+        FP g, gd = (FP)0.;
+        if (GG) {
+          poly_both(a[c], xx, g, gd);
           g += gd * dl;
+        } else {
+          g = poly(a[c], xx);
+          if (dl != (FP)0.) {
+            gd = dpoly(a[c], xx);
+            g += gd * dl;
+          }
         }
         if (GG) {
           FP two_grad = (FP)0.;
@@ -511,8 +529,9 @@ __global__ void __launch_bounds__(384) k_tab_grad(const __grid_constant__ TabPar
             const FP e0 = rc.e[0], e1 = rc.e[1], e2 = rc.e[2], e3 = rc.e[3];  // pre-multiplied by the fold multiplicity
 #pragma unroll
             for (int c = 0; c < NC; ++c) {
-              FP gd = dpoly(a[c], xx);
-              FP g = poly(a[c], xx) + gd * dl;
+              FP g, gd;
+              poly_both(a[c], xx, g, gd);
+              g += gd * dl;
               const FP dot = e0 * dyr[0][c] + e1 * dyr[1][c] + e2 * dyr[2][c] + e3 * dyr[3][c];
               if (TWO) {
                 const int k = kb + lane + 32 * c;
