@@ -177,7 +177,13 @@ def run_reference(args):
                          "sample": r["sample"], "stages_us_per_atom": r["stages_us_per_atom"]},
         "e2e": {"value": r["us_per_step_atom"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
-    print(json.dumps(line))
+    _emit(json.dumps(line))
+
+
+def _emit(text):
+    import builtins
+
+    getattr(builtins, "_dpb200_emit", print)(text)
 
 
 # ------------------------------------------------------------------------------------------------
@@ -333,7 +339,7 @@ def run_ours(args):
             line["kernels"] = kernels
         if cpu_base:
             line["cpu_baseline"] = cpu_base
-        print(json.dumps(line))
+        _emit(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
 
@@ -423,6 +429,19 @@ def per_kernel(args, torch, ops, model, dp, step, L, dev, nloc, esz):
 
 def main():
     args = parse()
+    # stdout carries exactly ONE JSON line: everything printed before it (NCCL's version banner, library
+    # chatter) is sent to stderr by pointing fd 1 at fd 2 until the result is ready
+    sys.stdout.flush()
+    saved = os.dup(1)
+    os.dup2(2, 1)
+    real_stdout = os.fdopen(saved, "w")
+    import builtins
+
+    def emit(text):
+        real_stdout.write(text + "\n")
+        real_stdout.flush()
+
+    builtins._dpb200_emit = emit
     if args.impl == "reference":
         run_reference(args)
     else:

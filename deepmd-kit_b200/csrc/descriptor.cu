@@ -6,6 +6,8 @@
 // batched GEMM with K = 4: launch- and pointer-bound).  It is a pure streaming op: read 4*M, write
 // M*axis values per atom (forward), read M*axis + 4*M, write 4*M (backward) -- HBM-bound, so one
 // WARP per atom with the operands staged in shared memory and fully coalesced stores.
+#include <cuda_pipeline.h>
+
 #include "common.cuh"
 
 namespace dpb200 {
@@ -26,40 +28,71 @@ __global__ void __launch_bounds__(128) k_desc_fwd(FP* __restrict__ D, const FP* 
     for (int e = lane; e < 4 * M; e += 32) xs[e] = x[e] * scale;
     __syncwarp();
     FP* __restrict__ d = D + i * nout;
+    int k1 = lane / axis, k2 = lane - k1 * axis;  // (row, column) of element e, advanced without dividing
     for (int e = lane; e < nout; e += 32) {
-      const int k1 = e / axis, k2 = e - k1 * axis;
       const FP v = xs[k1] * xs[k2] + xs[M + k1] * xs[M + k2] + xs[2 * M + k1] * xs[2 * M + k2] +
                    xs[3 * M + k1] * xs[3 * M + k2];
       st_cs(d + e, v);
+      k2 += 32;
+      while (k2 >= axis) {
+        k2 -= axis;
+        ++k1;
+      }
     }
   }
 }
 
 // dX[m][k] = scale * ( sum_{k2<axis} dD[k][k2] xs[m][k2]  +  [k<axis] sum_{k1<M} dD[k1][k] xs[m][k1] ),
-// xs = X*scale.  Row i of dD/X(gathered) belongs to atom rows[i] (or i): the result is written there.
-// The second term is a column walk over all M rows for only `axis` channels: it is spread over the
-// whole warp as (m, k) = (lane / axis ... ) pairs instead of leaving 3/4 of the lanes idle.
+// xs = X*scale.  Row i of dD belongs to atom rows[i] (or i): the result is written there.
+// One warp per atom; the 12.8 KB of dD and the 3.2 KB of X of the NEXT atom stream into the second
+// half of a per-warp double buffer with cp.async (LDGSTS, padded rows: conflict-free column walks)
+// while the current atom is being contracted, so the kernel runs at HBM speed instead of one
+// memory round trip per atom.
 template <typename FP>
-__global__ void __launch_bounds__(128) k_desc_bwd(FP* __restrict__ dX, const FP* __restrict__ dD,
+__global__ void __launch_bounds__(192) k_desc_bwd(FP* __restrict__ dX, const FP* __restrict__ dD,
                                                   const FP* __restrict__ X, const int* __restrict__ rows,
                                                   long long nloc, int M, int axis, FP scale) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int ld = axis + 1;  // padded row of the staged dD: conflict-free column walks
-  FP* xs = reinterpret_cast<FP*>(desc_smem) + (size_t)warp * (4 * M + M * ld + 4 * axis);
-  FP* g = xs + 4 * M;
-  FP* t2 = g + M * ld;  // second term, [4][axis]
+  const int ld = axis + 1;
+  const int per_buf = 4 * M + M * ld;
+  FP* base = reinterpret_cast<FP*>(desc_smem) + (size_t)warp * (2 * per_buf + 4 * axis);
+  FP* t2 = base + 2 * per_buf;  // second term, [4][axis]
   const int nout = M * axis;
-  for (long long i = (long long)blockIdx.x * 4 + warp; i < nloc; i += (long long)gridDim.x * 4) {
-    const long long dst = rows ? (long long)rows[i] : i;
-    const FP* __restrict__ x = X + dst * 4 * M;
+  const int nw = blockDim.x >> 5;
+  const long long stride = (long long)gridDim.x * nw;
+
+  auto issue = [&](long long i, FP* buf) {
+    const long long src = rows ? (long long)rows[i] : i;
+    const FP* __restrict__ x = X + src * 4 * M;
     const FP* __restrict__ gd = dD + i * nout;
-    __syncwarp();
-    for (int e = lane; e < 4 * M; e += 32) xs[e] = x[e] * scale;
+    for (int e = lane; e < 4 * M; e += 32) __pipeline_memcpy_async(buf + e, x + e, sizeof(FP));
+    FP* g = buf + 4 * M;
+    int k1 = lane / axis, k2 = lane - k1 * axis;
     for (int e = lane; e < nout; e += 32) {
-      const int k1 = e / axis, k2 = e - k1 * axis;
-      g[k1 * ld + k2] = __ldcs(gd + e);
+      __pipeline_memcpy_async(g + k1 * ld + k2, gd + e, sizeof(FP));
+      k2 += 32;
+      while (k2 >= axis) {
+        k2 -= axis;
+        ++k1;
+      }
+    }
+    __pipeline_commit();
+  };
+
+  long long i = (long long)blockIdx.x * nw + warp;
+  int cur = 0;
+  if (i < nloc) issue(i, base);
+  while (i < nloc) {
+    const long long ni = i + stride;
+    if (ni < nloc) {
+      issue(ni, base + (cur ^ 1) * per_buf);
+      __pipeline_wait_prior(1);
+    } else {
+      __pipeline_wait_prior(0);
     }
     __syncwarp();
+    const FP* xs = base + cur * per_buf;  // unscaled X
+    const FP* g = xs + 4 * M;
     // second term: 4*axis outputs, each a dot product over k1 < M
     for (int o = lane; o < 4 * axis; o += 32) {
       const int m = o / axis, k = o - m * axis;
@@ -68,7 +101,9 @@ __global__ void __launch_bounds__(128) k_desc_bwd(FP* __restrict__ dX, const FP*
       t2[o] = acc;
     }
     __syncwarp();
+    const long long dst = rows ? (long long)rows[i] : i;
     FP* __restrict__ o = dX + dst * 4 * M;
+    const FP s2 = scale * scale;
     for (int k = lane; k < M; k += 32) {
       FP a0 = 0, a1 = 0, a2 = 0, a3 = 0;
       for (int k2 = 0; k2 < axis; ++k2) {
@@ -84,11 +119,14 @@ __global__ void __launch_bounds__(128) k_desc_bwd(FP* __restrict__ dX, const FP*
         a2 += t2[2 * axis + k];
         a3 += t2[3 * axis + k];
       }
-      o[k] = a0 * scale;
-      o[M + k] = a1 * scale;
-      o[2 * M + k] = a2 * scale;
-      o[3 * M + k] = a3 * scale;
+      o[k] = a0 * s2;
+      o[M + k] = a1 * s2;
+      o[2 * M + k] = a2 * s2;
+      o[3 * M + k] = a3 * s2;
     }
+    __syncwarp();
+    cur ^= 1;
+    i = ni;
   }
 }
 
@@ -126,17 +164,23 @@ int desc_launch(bool bwd, FP* out, const FP* dD, const FP* X, const int* rows, l
   DPB_REQUIRE(nloc >= 0 && M >= 1 && axis >= 1 && axis <= M, "descriptor: need 1 <= axis <= M");
   if (nloc == 0) return DPB200_OK;
   DPB_REQUIRE(out && X && (!bwd || dD), "descriptor: null pointer");
-  const size_t smem = (bwd ? (size_t)(4 * M + M * (axis + 1) + 4 * axis) : (size_t)4 * M) * sizeof(FP) * 4;
-  DPB_REQUIRE(smem <= 200 * 1024, "descriptor: M*axis too large for shared memory staging");
+  const size_t per_warp_bwd = (size_t)(2 * (4 * M + M * (axis + 1)) + 4 * axis) * sizeof(FP);
   int occ = 0;
   long long want = (nloc + 3) / 4;
   if (bwd) {
+    int nw = (int)((220 * 1024) / per_warp_bwd);
+    if (nw > 6) nw = 6;
+    DPB_REQUIRE(nw >= 1, "descriptor: M*axis too large for shared memory staging");
+    const size_t smem = per_warp_bwd * nw;
     auto kern = k_desc_bwd<FP>;
     DPB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    DPB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, 128, smem));
+    DPB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, nw * 32, smem));
+    want = (nloc + nw - 1) / nw;
     long long cap = (long long)sm_count() * (occ < 1 ? 1 : occ);
-    kern<<<(int)(want < cap ? want : cap), 128, smem, st>>>(out, dD, X, rows, nloc, M, axis, (FP)scale);
+    kern<<<(int)(want < cap ? want : cap), nw * 32, smem, st>>>(out, dD, X, rows, nloc, M, axis, (FP)scale);
   } else {
+    const size_t smem = (size_t)4 * M * sizeof(FP) * 4;
+    DPB_REQUIRE(smem <= 200 * 1024, "descriptor: M too large for shared memory staging");
     auto kern = k_desc_fwd<FP>;
     DPB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     DPB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, 128, smem));

@@ -147,25 +147,29 @@ __global__ void k_table_relayout(FP* __restrict__ T, const FP* __restrict__ tabl
   }
 }
 
-// Coefficients of (row, channel k): shared-memory window [r0, r0+H) or the global pair table.
-template <typename FP>
-__device__ __forceinline__ void fetch_coef(FP (&a)[6], const FP* __restrict__ hot, const FP* __restrict__ T,
-                                           int row, int r0, int H, int M, int k) {
+// Coefficients of one table row for the NC channels of this lane (kc[c], clamped to M-1 so that every
+// lane always loads: no divergence, the duplicates cost no extra wavefront): shared-memory window
+// [r0, r0+H) or the global pair table.  The window test is warp-uniform.
+template <typename FP, int NC>
+__device__ __forceinline__ void fetch_row(FP (&a)[NC][6], const FP* __restrict__ hot, const FP* __restrict__ T,
+                                          int row, int r0, int H, int M, const int (&kc)[NC]) {
   using P2 = typename Pair2<FP>::type;
   const unsigned rel = (unsigned)(row - r0);
-  P2 u, v, w;
   if (rel < (unsigned)H) {
-    const P2* q = reinterpret_cast<const P2*>(hot) + (size_t)rel * 3 * M + k;
-    u = q[0];
-    v = q[M];
-    w = q[2 * M];
+    const P2* q = reinterpret_cast<const P2*>(hot) + (size_t)rel * 3 * M;
+#pragma unroll
+    for (int c = 0; c < NC; ++c) {
+      const P2 u = q[kc[c]], v = q[M + kc[c]], w = q[2 * M + kc[c]];
+      a[c][0] = u.x, a[c][1] = u.y, a[c][2] = v.x, a[c][3] = v.y, a[c][4] = w.x, a[c][5] = w.y;
+    }
   } else {
-    const P2* q = reinterpret_cast<const P2*>(T) + (long long)row * 3 * M + k;
-    u = __ldg(q);
-    v = __ldg(q + M);
-    w = __ldg(q + 2 * M);
+    const P2* q = reinterpret_cast<const P2*>(T) + (long long)row * 3 * M;
+#pragma unroll
+    for (int c = 0; c < NC; ++c) {
+      const P2 u = __ldg(q + kc[c]), v = __ldg(q + M + kc[c]), w = __ldg(q + 2 * M + kc[c]);
+      a[c][0] = u.x, a[c][1] = u.y, a[c][2] = v.x, a[c][3] = v.y, a[c][4] = w.x, a[c][5] = w.y;
+    }
   }
-  a[0] = u.x, a[1] = u.y, a[2] = v.x, a[3] = v.y, a[4] = w.x, a[5] = w.y;
 }
 
 // First row of the hot window: the row of the last slot of atom 0 (padding or the farthest
@@ -299,9 +303,9 @@ __global__ void __launch_bounds__(512) k_tab_fwd(const __grid_constant__ TabPara
   preload_hot(hot, p, r0);
   __syncthreads();
 
-  bool act[NC];
+  int kc[NC];  // this lane's channels, clamped: lanes beyond M recompute channel M-1 and never store
 #pragma unroll
-  for (int c = 0; c < NC; ++c) act[c] = c0 + lane + 32 * c < p.M;
+  for (int c = 0; c < NC; ++c) kc[c] = (c0 + lane + 32 * c < p.M) ? c0 + lane + 32 * c : p.M - 1;
 
   const long long stride = (long long)gridDim.x * nw;
   long long i = (long long)blockIdx.x * nw + warp;
@@ -313,7 +317,8 @@ __global__ void __launch_bounds__(512) k_tab_fwd(const __grid_constant__ TabPara
 #pragma unroll
   for (int m = 0; m < 4; ++m)
 #pragma unroll
-    for (int c = 0; c < NC; ++c) acc[m][c] = (FP)0.;
+    for (int c = 0; c < NC; ++c)
+      acc[m][c] = (p.accumulate && i < p.nloc) ? p.out[(i * 4 + m) * (long long)p.M + kc[c]] : (FP)0.;
   FP a[NC][6];
 #pragma unroll
   for (int c = 0; c < NC; ++c)
@@ -337,9 +342,7 @@ __global__ void __launch_bounds__(512) k_tab_fwd(const __grid_constant__ TabPara
       const int row = r.idx;
       if (row != cur_row) {  // warp-uniform
         cur_row = row;
-#pragma unroll
-        for (int c = 0; c < NC; ++c)
-          if (act[c]) fetch_coef(a[c], hot, p.T, row, r0, p.H, p.M, c0 + lane + 32 * c);
+        fetch_row<FP, NC>(a, hot, p.T, row, r0, p.H, p.M, kc);
       }
       const FP xx = r.xx;
       const FP dl = r.delta;
@@ -353,7 +356,7 @@ __global__ void __launch_bounds__(512) k_tab_fwd(const __grid_constant__ TabPara
         for (int m = 0; m < 4; ++m) h[m] = rgg[jj].h[m];
         zx = rgg[jj].zx;
       }
-      const long long two_off = ((i * p.nnei + j0 + jj) * (long long)p.M) + c0 + lane;
+      const long long two_off = (i * p.nnei + j0 + jj) * (long long)p.M;
 #pragma unroll
       for (int c = 0; c < NC; ++c) {
         FP g, gd = (FP)0.;
@@ -369,9 +372,9 @@ __global__ void __launch_bounds__(512) k_tab_fwd(const __grid_constant__ TabPara
         }
         if (GG) {
           FP two_grad = (FP)0.;
-          if (TWO && act[c]) {
-            const FP t = p.two[two_off + 32 * c];
-            two_grad = p.dz_two[two_off + 32 * c] * g;
+          if (TWO) {
+            const FP t = p.two[two_off + kc[c]];
+            two_grad = p.dz_two[two_off + kc[c]] * g;
             g += g * t;
             gd += gd * t;
           }
@@ -379,8 +382,8 @@ __global__ void __launch_bounds__(512) k_tab_fwd(const __grid_constant__ TabPara
 #pragma unroll
           for (int m = 0; m < 4; ++m) acc[m][c] += g * h[m] + sgl * e[m];
         } else {
-          if (TWO && act[c]) {
-            const FP t = p.two[two_off + 32 * c];
+          if (TWO) {
+            const FP t = p.two[two_off + kc[c]];
             g = g * t + g;
           }
 #pragma unroll
@@ -389,18 +392,16 @@ __global__ void __launch_bounds__(512) k_tab_fwd(const __grid_constant__ TabPara
       }
     }
     if (atom_end) {
-      FP* __restrict__ o = p.out + i * 4 * (long long)p.M + c0 + lane;
+      // (accumulate: acc was seeded with the previous contents of out when this atom started)
 #pragma unroll
       for (int c = 0; c < NC; ++c) {
-        if (act[c]) {
+        if (c0 + lane + 32 * c < p.M) {
 #pragma unroll
-          for (int m = 0; m < 4; ++m) {
-            FP* q = o + (long long)m * p.M + 32 * c;
-            *q = p.accumulate ? (*q + acc[m][c]) : acc[m][c];
-          }
+          for (int m = 0; m < 4; ++m) p.out[(i * 4 + m) * (long long)p.M + kc[c]] = acc[m][c];
         }
 #pragma unroll
-        for (int m = 0; m < 4; ++m) acc[m][c] = (FP)0.;
+        for (int m = 0; m < 4; ++m)
+          acc[m][c] = (p.accumulate && ni < p.nloc) ? p.out[(ni * 4 + m) * (long long)p.M + kc[c]] : (FP)0.;
       }
     }
     i = ni;
@@ -477,14 +478,17 @@ __global__ void __launch_bounds__(384) k_tab_grad(const __grid_constant__ TabPar
 #pragma unroll
     for (int q = 0; q < 6; ++q) a[c][q] = (FP)0.;
   int cur_row = -1;
+  int kc[NC];  // clamped channel of (lane, c) in the first channel block
 
   while (i < p.nloc) {
     const FP* __restrict__ dyi = p.dy + i * 4 * (long long)M;
     if (j0 == 0 && single) {
 #pragma unroll
-      for (int c = 0; c < NC; ++c)
+      for (int c = 0; c < NC; ++c) {
+        kc[c] = (lane + 32 * c < M) ? lane + 32 * c : M - 1;
 #pragma unroll
         for (int m = 0; m < 4; ++m) dyr[m][c] = (lane + 32 * c < M) ? dyi[(long long)m * M + lane + 32 * c] : (FP)0.;
+      }
     }
     bool done;
     const int nproc = stage_chunk<FP, false>(p, j0, last, pre, rec, nullptr, lane, done);
@@ -507,12 +511,12 @@ __global__ void __launch_bounds__(384) k_tab_grad(const __grid_constant__ TabPar
         if (!single) {
           cur_row = -1;
 #pragma unroll
-          for (int c = 0; c < NC; ++c)
+          for (int c = 0; c < NC; ++c) {
+            const int k = kb + lane + 32 * c;
+            kc[c] = k < M ? k : M - 1;
 #pragma unroll
-            for (int m = 0; m < 4; ++m) {
-              const int k = kb + lane + 32 * c;
-              dyr[m][c] = k < M ? dyi[(long long)m * M + k] : (FP)0.;
-            }
+            for (int m = 0; m < 4; ++m) dyr[m][c] = k < M ? dyi[(long long)m * M + k] : (FP)0.;
+          }
         }
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
@@ -520,9 +524,7 @@ __global__ void __launch_bounds__(384) k_tab_grad(const __grid_constant__ TabPar
             const Rec<FP>& rc = rec[b + u];
             if (rc.idx != cur_row) {
               cur_row = rc.idx;
-#pragma unroll
-              for (int c = 0; c < NC; ++c)
-                if (kb + lane + 32 * c < M) fetch_coef(a[c], hot, p.T, cur_row, r0, p.H, M, kb + lane + 32 * c);
+              fetch_row<FP, NC>(a, hot, p.T, cur_row, r0, p.H, M, kc);
             }
             const FP xx = rc.xx;
             const FP dl = rc.delta;

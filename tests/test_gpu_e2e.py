@@ -99,3 +99,30 @@ def test_force_is_energy_gradient(pkg):
             c[i, d] += sgn * h
             es.append(dp.eval(c.reshape(1, -1), box.reshape(1, 9), atype)[0][0, 0])
         assert abs(-(es[0] - es[1]) / (2 * h) - f0[0, i, d]) < 1e-7
+
+
+def fcc_box(ncell=6, a0=3.615, jitter=0.05, seed=20260102):
+    """BASELINE config 3 in miniature: FCC copper, single type."""
+    base = np.array([[0, 0, 0], [0.5, 0.5, 0], [0.5, 0, 0.5], [0, 0.5, 0.5]]) * a0
+    cells = np.stack(np.meshgrid(*[np.arange(ncell)] * 3, indexing="ij"), -1).reshape(-1, 3) * a0
+    coord = (cells[:, None, :] + base[None]).reshape(-1, 3)
+    coord = coord + np.random.default_rng(seed).normal(scale=jitter, size=coord.shape)
+    return coord, np.zeros(len(coord), np.int32), np.eye(3) * ncell * a0
+
+
+@pytest.mark.parametrize("dtype", [torch.float64])
+def test_copper_large_sel_e2e(pkg, dtype):
+    """Single type, sel [512] (35 % occupancy), rcut 8: the 'large sel, metallic density' case."""
+    from deepmd_kit_b200.model import COPPER_CONFIG, DeepPotB200, SeAConfig, SeAModel
+
+    cfg = SeAConfig(**COPPER_CONFIG)
+    coord, atype, box = fcc_box()
+    dp = DeepPotB200(SeAModel(cfg, dtype, "cuda:0"), skin=2.0)
+    e, f, v = dp.eval(coord.reshape(1, -1), box.reshape(1, 9), atype)
+    lib = _cpu_lib()
+    lists = pipeline.build_lists(lib, coord, atype, box, cfg.rcut + 2.0)
+    we, wf, wv, ex = pipeline.evaluate(lib, SeAModel(cfg, dtype, "cpu"), lists)
+    assert (ex["nlist"] >= 0).sum(1).mean() > 150
+    assert abs(e[0, 0] - we) <= 1e-10 * abs(we)
+    assert rel(f[0], wf) <= 1e-10
+    assert rel(v[0], wv) <= 1e-10
