@@ -101,6 +101,17 @@ class ClockSampler:
                 "power_w_max": max(pw) if pw else None, "samples": len(sm), "reasons": sorted(reasons)}
 
 
+# DRAM traffic per atom (dram__bytes_read.sum + dram__bytes_write.sum over the launches of one step) from the
+# `ncu --set full` captures summarised in profiles/r01_ncu_full_v3_summary.csv / r01_ncu_full_v1_summary.csv
+# (fp64, 98 304-atom box; the kernels stream per-atom data, so the figure scales with the atom count).
+NCU_DRAM_BYTES_PER_ATOM_F64 = {
+    "prod_env_mat_a": 21917.0,
+    "prod_force_virial_a": 20975.0,
+    "tabulate_sections_fwd": 12247.0,
+    "tabulate_sections_grad": 14046.0,
+}
+
+
 def measured_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -420,8 +431,13 @@ def per_kernel(args, torch, ops, model, dp, step, L, dev, nloc, esz):
     roofline = None
     if top:
         r = ours[top]
+        traffic = None
+        if args.dtype == "f64" and top in NCU_DRAM_BYTES_PER_ATOM_F64:
+            traffic = NCU_DRAM_BYTES_PER_ATOM_F64[top] * nloc
         roofline = {"kernel": top, "bound": r["bound"], "achieved": r["achieved"], "peak": r["peak"], "unit": r["unit"],
-                    "frac": r["frac"], "traffic": None,
+                    "frac": r["frac"], "traffic": traffic,
+                    "traffic_note": "DRAM bytes per step of this operator (ncu --set full, profiles/r01_ncu_full_v3_summary.csv, "
+                                    "scaled per atom)",
                     "peak_source": hbm_src if r["bound"] == "hbm" else "dpb200_fma_peak measured in this run (burst)",
                     "mean_real_neighbours": nreal, "mean_raw_neighbours": raw}
     return table, roofline
