@@ -383,6 +383,10 @@ def per_kernel(args, torch, ops, model, dp, step, L, dev, nloc, esz):
     graph_mode = getattr(dp, "use_graph", False)
     dp.use_graph = False  # the instrumented pass needs real launches (events cannot be timed inside a graph)
     try:
+        for _ in range(2):  # eager warm-up: the graph capture emptied the allocator cache
+            out = step()
+        torch.cuda.synchronize()
+        acc.clear()
         for _ in range(nsteps):
             out = step()
         torch.cuda.synchronize()
@@ -411,8 +415,11 @@ def per_kernel(args, torch, ops, model, dp, step, L, dev, nloc, esz):
     table = {}
     total = 0.0
     for n, evs in acc.items():
-        ms = sum(a.elapsed_time(b) for a, b in evs) / nsteps
-        table[n] = {"ms_per_step": ms, "calls_per_step": len(evs) / nsteps}
+        times = sorted(a.elapsed_time(b) for a, b in evs)
+        med = times[len(times) // 2]
+        ms = med * len(evs) / nsteps  # median call x calls per step (robust against allocator hiccups)
+        table[n] = {"ms_per_step": ms, "calls_per_step": len(evs) / nsteps, "ms_min_call": times[0],
+                    "ms_max_call": times[-1]}
         total += ms
     for n, row in table.items():
         row["share"] = row["ms_per_step"] / total if total > 0 else None

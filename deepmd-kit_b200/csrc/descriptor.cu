@@ -28,15 +28,21 @@ __global__ void __launch_bounds__(128) k_desc_fwd(FP* __restrict__ D, const FP* 
     for (int e = lane; e < 4 * M; e += 32) xs[e] = x[e] * scale;
     __syncwarp();
     FP* __restrict__ d = D + i * nout;
-    int k1 = lane / axis, k2 = lane - k1 * axis;  // (row, column) of element e, advanced without dividing
-    for (int e = lane; e < nout; e += 32) {
-      const FP v = xs[k1] * xs[k2] + xs[M + k1] * xs[M + k2] + xs[2 * M + k1] * xs[2 * M + k2] +
-                   xs[3 * M + k1] * xs[3 * M + k2];
-      st_cs(d + e, v);
-      k2 += 32;
-      while (k2 >= axis) {
-        k2 -= axis;
-        ++k1;
+    if (32 % axis == 0) {  // the column of a lane never changes, its row advances by 32/axis: no division
+      const int k2 = lane % axis, k10 = lane / axis, step = 32 / axis;
+#pragma unroll 4
+      for (int it = 0; it * 32 + lane < nout; ++it) {
+        const int k1 = k10 + it * step;
+        const FP v = xs[k1] * xs[k2] + xs[M + k1] * xs[M + k2] + xs[2 * M + k1] * xs[2 * M + k2] +
+                     xs[3 * M + k1] * xs[3 * M + k2];
+        st_cs(d + it * 32 + lane, v);
+      }
+    } else {
+      for (int e = lane; e < nout; e += 32) {
+        const int k1 = e / axis, k2 = e - k1 * axis;
+        const FP v = xs[k1] * xs[k2] + xs[M + k1] * xs[M + k2] + xs[2 * M + k1] * xs[2 * M + k2] +
+                     xs[3 * M + k1] * xs[3 * M + k2];
+        st_cs(d + e, v);
       }
     }
   }
@@ -67,13 +73,15 @@ __global__ void __launch_bounds__(192) k_desc_bwd(FP* __restrict__ dX, const FP*
     const FP* __restrict__ gd = dD + i * nout;
     for (int e = lane; e < 4 * M; e += 32) __pipeline_memcpy_async(buf + e, x + e, sizeof(FP));
     FP* g = buf + 4 * M;
-    int k1 = lane / axis, k2 = lane - k1 * axis;
-    for (int e = lane; e < nout; e += 32) {
-      __pipeline_memcpy_async(g + k1 * ld + k2, gd + e, sizeof(FP));
-      k2 += 32;
-      while (k2 >= axis) {
-        k2 -= axis;
-        ++k1;
+    if (32 % axis == 0) {
+      const int k2 = lane % axis, k10 = lane / axis, step = 32 / axis;
+#pragma unroll 4
+      for (int it = 0; it * 32 + lane < nout; ++it)
+        __pipeline_memcpy_async(g + (k10 + it * step) * ld + k2, gd + it * 32 + lane, sizeof(FP));
+    } else {
+      for (int e = lane; e < nout; e += 32) {
+        const int k1 = e / axis, k2 = e - k1 * axis;
+        __pipeline_memcpy_async(g + k1 * ld + k2, gd + e, sizeof(FP));
       }
     }
     __pipeline_commit();

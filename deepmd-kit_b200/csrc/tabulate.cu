@@ -147,26 +147,36 @@ __global__ void k_table_relayout(FP* __restrict__ T, const FP* __restrict__ tabl
   }
 }
 
-// Coefficients of one table row for the NC channels of this lane (kc[c], clamped to M-1 so that every
-// lane always loads: no divergence, the duplicates cost no extra wavefront): shared-memory window
-// [r0, r0+H) or the global pair table.  The window test is warp-uniform.
+// Coefficients of one table row for the NC channels of this lane.  ob[c] = byte offset of the lane's
+// channel inside one coefficient-pair block (clamped to channel M-1 so that every lane always loads:
+// no divergence, the duplicates cost no extra wavefront).  Source: the shared-memory window
+// [r0, r0+H) or the global pair table; the window test is warp-uniform.
 template <typename FP, int NC>
 __device__ __forceinline__ void fetch_row(FP (&a)[NC][6], const FP* __restrict__ hot, const FP* __restrict__ T,
-                                          int row, int r0, int H, int M, const int (&kc)[NC]) {
+                                          int row, int r0, int H, int M, const int (&ob)[NC]) {
   using P2 = typename Pair2<FP>::type;
   const unsigned rel = (unsigned)(row - r0);
+  const unsigned qb = (unsigned)M * (unsigned)sizeof(P2);
   if (rel < (unsigned)H) {
-    const P2* q = reinterpret_cast<const P2*>(hot) + (size_t)rel * 3 * M;
+    const char* b0 = reinterpret_cast<const char*>(hot) + rel * (3u * qb);
+    const char* b1 = b0 + qb;
+    const char* b2 = b1 + qb;
 #pragma unroll
     for (int c = 0; c < NC; ++c) {
-      const P2 u = q[kc[c]], v = q[M + kc[c]], w = q[2 * M + kc[c]];
+      const P2 u = *reinterpret_cast<const P2*>(b0 + ob[c]);
+      const P2 v = *reinterpret_cast<const P2*>(b1 + ob[c]);
+      const P2 w = *reinterpret_cast<const P2*>(b2 + ob[c]);
       a[c][0] = u.x, a[c][1] = u.y, a[c][2] = v.x, a[c][3] = v.y, a[c][4] = w.x, a[c][5] = w.y;
     }
   } else {
-    const P2* q = reinterpret_cast<const P2*>(T) + (long long)row * 3 * M;
+    const char* b0 = reinterpret_cast<const char*>(T) + (long long)row * (3u * qb);
+    const char* b1 = b0 + qb;
+    const char* b2 = b1 + qb;
 #pragma unroll
     for (int c = 0; c < NC; ++c) {
-      const P2 u = __ldg(q + kc[c]), v = __ldg(q + M + kc[c]), w = __ldg(q + 2 * M + kc[c]);
+      const P2 u = __ldg(reinterpret_cast<const P2*>(b0 + ob[c]));
+      const P2 v = __ldg(reinterpret_cast<const P2*>(b1 + ob[c]));
+      const P2 w = __ldg(reinterpret_cast<const P2*>(b2 + ob[c]));
       a[c][0] = u.x, a[c][1] = u.y, a[c][2] = v.x, a[c][3] = v.y, a[c][4] = w.x, a[c][5] = w.y;
     }
   }
@@ -232,7 +242,7 @@ __device__ __forceinline__ void load_pre(Pre<FP, GG>& q, const TabParams<FP>& p,
 template <typename FP, bool GG>
 __device__ __forceinline__ int stage_chunk(const TabParams<FP>& p, int j0, FP last, const Pre<FP, GG>& q,
                                            Rec<FP>* __restrict__ rec, RecGG<FP>* __restrict__ rgg,
-                                           int lane, bool& done) {
+                                           int lane, bool& done, bool& any_delta) {
   const int j = j0 + lane;
   const bool valid = j < p.nnei;
   const bool fold = valid && p.is_sorted && (q.x == last) && q.e[1] == (FP)0. && q.e[2] == (FP)0. && q.e[3] == (FP)0.;
@@ -242,6 +252,7 @@ __device__ __forceinline__ int stage_chunk(const TabParams<FP>& p, int j0, FP la
   done = fm != 0u;
   Rec<FP> r;
   locate(p, q.x, r.xx, r.idx, r.delta);
+  any_delta = __any_sync(kFull, lane < nproc && r.delta != (FP)0.);
   r.mult = (fm && lane == nproc - 1) ? (p.nnei - j) : 1;
   const FP mult = (FP)r.mult;
 #pragma unroll
@@ -304,8 +315,12 @@ __global__ void __launch_bounds__(512) k_tab_fwd(const __grid_constant__ TabPara
   __syncthreads();
 
   int kc[NC];  // this lane's channels, clamped: lanes beyond M recompute channel M-1 and never store
+  int ob[NC];  // their byte offsets inside a coefficient-pair block
 #pragma unroll
-  for (int c = 0; c < NC; ++c) kc[c] = (c0 + lane + 32 * c < p.M) ? c0 + lane + 32 * c : p.M - 1;
+  for (int c = 0; c < NC; ++c) {
+    kc[c] = (c0 + lane + 32 * c < p.M) ? c0 + lane + 32 * c : p.M - 1;
+    ob[c] = kc[c] * (int)sizeof(typename Pair2<FP>::type);
+  }
 
   const long long stride = (long long)gridDim.x * nw;
   long long i = (long long)blockIdx.x * nw + warp;
@@ -327,8 +342,8 @@ __global__ void __launch_bounds__(512) k_tab_fwd(const __grid_constant__ TabPara
   int cur_row = -1;  // the coefficient registers stay valid across atoms
 
   while (i < p.nloc) {
-    bool done;
-    const int nproc = stage_chunk<FP, GG>(p, j0, last, pre, rec, rgg, lane, done);
+    bool done, any_delta;
+    const int nproc = stage_chunk<FP, GG>(p, j0, last, pre, rec, rgg, lane, done, any_delta);
     // next work item, fetched now, consumed after this chunk's arithmetic
     const bool atom_end = done || j0 + 32 >= p.nnei;
     const long long ni = atom_end ? i + stride : i;
@@ -337,57 +352,80 @@ __global__ void __launch_bounds__(512) k_tab_fwd(const __grid_constant__ TabPara
     FP nlast = last;
     if (atom_end && ni < p.nloc) nlast = p.em_x[ni * p.ldx_i + (long long)(p.nnei - 1) * p.ldx_j];
 
-    for (int jj = 0; jj < nproc; ++jj) {
-      const Rec<FP>& r = rec[jj];
-      const int row = r.idx;
-      if (row != cur_row) {  // warp-uniform
-        cur_row = row;
-        fetch_row<FP, NC>(a, hot, p.T, row, r0, p.H, p.M, kc);
-      }
-      const FP xx = r.xx;
-      const FP dl = r.delta;
-      FP e[4];
-#pragma unroll
-      for (int m = 0; m < 4; ++m) e[m] = r.e[m];
-      FP h[4];
-      FP zx = (FP)0.;
-      if (GG) {
-#pragma unroll
-        for (int m = 0; m < 4; ++m) h[m] = rgg[jj].h[m];
-        zx = rgg[jj].zx;
-      }
-      const long long two_off = (i * p.nnei + j0 + jj) * (long long)p.M;
-#pragma unroll
-      for (int c = 0; c < NC; ++c) {
-        FP g, gd = (FP)0.;
-        if (GG) {
-          poly_both(a[c], xx, g, gd);
-          g += gd * dl;
-        } else {
-          g = poly(a[c], xx);
-          if (dl != (FP)0.) {
-            gd = dpoly(a[c], xx);
-            g += gd * dl;
-          }
+    if (!GG && !TWO && !any_delta) {
+      // the common case: nothing to gate, nobody outside [lower, max): 9 FMAs per channel, no branches
+#pragma unroll 2
+      for (int jj = 0; jj < nproc; ++jj) {
+        const Rec<FP>& r = rec[jj];
+        const int row = r.idx;
+        if (row != cur_row) {  // warp-uniform
+          cur_row = row;
+          fetch_row<FP, NC>(a, hot, p.T, row, r0, p.H, p.M, ob);
         }
+        const FP xx = r.xx;
+        const FP e0 = r.e[0], e1 = r.e[1], e2 = r.e[2], e3 = r.e[3];
+#pragma unroll
+        for (int c = 0; c < NC; ++c) {
+          const FP g = poly(a[c], xx);
+          acc[0][c] += e0 * g;
+          acc[1][c] += e1 * g;
+          acc[2][c] += e2 * g;
+          acc[3][c] += e3 * g;
+        }
+      }
+    } else {
+      for (int jj = 0; jj < nproc; ++jj) {
+        const Rec<FP>& r = rec[jj];
+        const int row = r.idx;
+        if (row != cur_row) {  // warp-uniform
+          cur_row = row;
+          fetch_row<FP, NC>(a, hot, p.T, row, r0, p.H, p.M, ob);
+        }
+        const FP xx = r.xx;
+        const FP dl = r.delta;
+        FP e[4];
+#pragma unroll
+        for (int m = 0; m < 4; ++m) e[m] = r.e[m];
+        FP h[4];
+        FP zx = (FP)0.;
         if (GG) {
-          FP two_grad = (FP)0.;
-          if (TWO) {
-            const FP t = p.two[two_off + kc[c]];
-            two_grad = p.dz_two[two_off + kc[c]] * g;
-            g += g * t;
-            gd += gd * t;
-          }
-          const FP sgl = zx * gd + two_grad;
 #pragma unroll
-          for (int m = 0; m < 4; ++m) acc[m][c] += g * h[m] + sgl * e[m];
-        } else {
-          if (TWO) {
-            const FP t = p.two[two_off + kc[c]];
-            g = g * t + g;
-          }
+          for (int m = 0; m < 4; ++m) h[m] = rgg[jj].h[m];
+          zx = rgg[jj].zx;
+        }
+        const long long two_off = (i * p.nnei + j0 + jj) * (long long)p.M;
 #pragma unroll
-          for (int m = 0; m < 4; ++m) acc[m][c] += e[m] * g;
+        for (int c = 0; c < NC; ++c) {
+          FP g, gd = (FP)0.;
+          if (GG) {
+            poly_both(a[c], xx, g, gd);
+            g += gd * dl;
+          } else {
+            g = poly(a[c], xx);
+            if (dl != (FP)0.) {
+              gd = dpoly(a[c], xx);
+              g += gd * dl;
+            }
+          }
+          if (GG) {
+            FP two_grad = (FP)0.;
+            if (TWO) {
+              const FP t = p.two[two_off + kc[c]];
+              two_grad = p.dz_two[two_off + kc[c]] * g;
+              g += g * t;
+              gd += gd * t;
+            }
+            const FP sgl = zx * gd + two_grad;
+#pragma unroll
+            for (int m = 0; m < 4; ++m) acc[m][c] += g * h[m] + sgl * e[m];
+          } else {
+            if (TWO) {
+              const FP t = p.two[two_off + kc[c]];
+              g = g * t + g;
+            }
+#pragma unroll
+            for (int m = 0; m < 4; ++m) acc[m][c] += e[m] * g;
+          }
         }
       }
     }
@@ -478,7 +516,8 @@ __global__ void __launch_bounds__(384) k_tab_grad(const __grid_constant__ TabPar
 #pragma unroll
     for (int q = 0; q < 6; ++q) a[c][q] = (FP)0.;
   int cur_row = -1;
-  int kc[NC];  // clamped channel of (lane, c) in the first channel block
+  int kc[NC];  // clamped channel of (lane, c) in the current channel block
+  int ob[NC];  // its byte offset inside a coefficient-pair block
 
   while (i < p.nloc) {
     const FP* __restrict__ dyi = p.dy + i * 4 * (long long)M;
@@ -486,12 +525,13 @@ __global__ void __launch_bounds__(384) k_tab_grad(const __grid_constant__ TabPar
 #pragma unroll
       for (int c = 0; c < NC; ++c) {
         kc[c] = (lane + 32 * c < M) ? lane + 32 * c : M - 1;
+        ob[c] = kc[c] * (int)sizeof(typename Pair2<FP>::type);
 #pragma unroll
         for (int m = 0; m < 4; ++m) dyr[m][c] = (lane + 32 * c < M) ? dyi[(long long)m * M + lane + 32 * c] : (FP)0.;
       }
     }
-    bool done;
-    const int nproc = stage_chunk<FP, false>(p, j0, last, pre, rec, nullptr, lane, done);
+    bool done, any_delta;
+    const int nproc = stage_chunk<FP, false>(p, j0, last, pre, rec, nullptr, lane, done, any_delta);
     const bool atom_end = done || j0 + 32 >= p.nnei;
     const long long ni = atom_end ? i + stride : i;
     const int nj0 = atom_end ? 0 : j0 + 32;
@@ -503,10 +543,13 @@ __global__ void __launch_bounds__(384) k_tab_grad(const __grid_constant__ TabPar
     for (int b = 0; b < nproc; b += 4) {
       FP v[16];
       FP vx[4];
+      if (!single || (nproc - b) < 4) {  // the fast path below initialises by assignment
 #pragma unroll
-      for (int t = 0; t < 16; ++t) v[t] = (FP)0.;
+        for (int t = 0; t < 16; ++t) v[t] = (FP)0.;
 #pragma unroll
-      for (int t = 0; t < 4; ++t) vx[t] = (FP)0.;
+        for (int t = 0; t < 4; ++t) vx[t] = (FP)0.;
+      }
+      const bool assign0 = single && (nproc - b) >= 4;
       for (int kb = 0; kb < M; kb += 32 * NC) {
         if (!single) {
           cur_row = -1;
@@ -514,6 +557,7 @@ __global__ void __launch_bounds__(384) k_tab_grad(const __grid_constant__ TabPar
           for (int c = 0; c < NC; ++c) {
             const int k = kb + lane + 32 * c;
             kc[c] = k < M ? k : M - 1;
+            ob[c] = kc[c] * (int)sizeof(typename Pair2<FP>::type);
 #pragma unroll
             for (int m = 0; m < 4; ++m) dyr[m][c] = k < M ? dyi[(long long)m * M + k] : (FP)0.;
           }
@@ -524,7 +568,7 @@ __global__ void __launch_bounds__(384) k_tab_grad(const __grid_constant__ TabPar
             const Rec<FP>& rc = rec[b + u];
             if (rc.idx != cur_row) {
               cur_row = rc.idx;
-              fetch_row<FP, NC>(a, hot, p.T, cur_row, r0, p.H, M, kc);
+              fetch_row<FP, NC>(a, hot, p.T, cur_row, r0, p.H, M, ob);
             }
             const FP xx = rc.xx;
             const FP dl = rc.delta;
@@ -545,11 +589,19 @@ __global__ void __launch_bounds__(384) k_tab_grad(const __grid_constant__ TabPar
                   gd += t * gd;
                 }
               }
-              vx[u] += gd * dot;
-              v[4 * u + 0] += g * dyr[0][c];
-              v[4 * u + 1] += g * dyr[1][c];
-              v[4 * u + 2] += g * dyr[2][c];
-              v[4 * u + 3] += g * dyr[3][c];
+              if (c == 0 && assign0) {  // first channel group of a full batch: start the sums here
+                vx[u] = gd * dot;
+                v[4 * u + 0] = g * dyr[0][c];
+                v[4 * u + 1] = g * dyr[1][c];
+                v[4 * u + 2] = g * dyr[2][c];
+                v[4 * u + 3] = g * dyr[3][c];
+              } else {
+                vx[u] += gd * dot;
+                v[4 * u + 0] += g * dyr[0][c];
+                v[4 * u + 1] += g * dyr[1][c];
+                v[4 * u + 2] += g * dyr[2][c];
+                v[4 * u + 3] += g * dyr[3][c];
+              }
             }
           }
         }

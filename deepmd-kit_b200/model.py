@@ -248,6 +248,7 @@ class DeepPotB200:
         self._cache = {}  # persistent device buffers of the neighbour-list rebuild
         self._pin_in = None
         self._pin_out = None
+        self._atype_np = None
 
     def reset(self):
         self.state = None
@@ -338,10 +339,15 @@ class DeepPotB200:
         cells = np.asarray(cells, dtype=np.float64).reshape(-1, 9)
         nf, nat = coords.shape[0], len(atom_types)
         np_dt = np.float64 if m.dtype == torch.float64 else np.float32
+        at_np = np.ascontiguousarray(atom_types, dtype=np.int32)
         if self._pin_in is None or self._pin_in.numel() != nat * 3:
             self._pin_in = torch.empty(nat * 3, dtype=m.dtype).pin_memory()
             self._pin_out = torch.empty(nat * 3 + 10, dtype=m.dtype).pin_memory()
-            self._atype = torch.as_tensor(np.asarray(atom_types, np.int32)).to(dev)
+            self._atype_np = None
+        if self._atype_np is None or not np.array_equal(self._atype_np, at_np):
+            self._atype_np = at_np.copy()
+            self._atype = torch.as_tensor(at_np).to(dev)
+            self.state = None  # new types: new list, new type partition
         e_out = np.empty((nf, 1), np_dt)
         f_out = np.empty((nf, nat, 3), np_dt)
         v_out = np.empty((nf, 9), np_dt)
