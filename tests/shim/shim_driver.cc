@@ -1,0 +1,132 @@
+// Test driver for lib/libdeepmd_op_cuda.so (the reference-side C++ binding): calls the reference's
+// own declarations deepmd::prod_env_mat_a_gpu / tabulate_fusion_se_a_gpu / _grad_gpu /
+// prod_force_a_gpu / prod_virial_a_gpu exactly as source/op/tf/*_multi_device.cc would, on inputs read
+// from a flat binary file, and writes the outputs back.  Compiled against the reference headers
+// (tests/shim/build.sh); the pytest side compares the outputs with the CPU oracle.
+#include <cuda_runtime.h>
+
+#include <cstdio>
+#include <cstdlib>
+#include <vector>
+
+#include "neighbor_list.h"
+#include "prod_env_mat.h"
+#include "prod_force.h"
+#include "prod_virial.h"
+#include "tabulate.h"
+
+#define CK(x)                                                                  \
+  do {                                                                         \
+    cudaError_t e = (x);                                                       \
+    if (e != cudaSuccess) {                                                    \
+      fprintf(stderr, "CUDA %s at %d\n", cudaGetErrorString(e), __LINE__);     \
+      exit(2);                                                                 \
+    }                                                                          \
+  } while (0)
+
+template <typename T>
+std::vector<T> rd(FILE* f, size_t n) {
+  std::vector<T> v(n);
+  if (n && fread(v.data(), sizeof(T), n, f) != n) {
+    fprintf(stderr, "short read\n");
+    exit(3);
+  }
+  return v;
+}
+template <typename T>
+T* up(const std::vector<T>& v) {
+  T* d = nullptr;
+  CK(cudaMalloc((void**)&d, sizeof(T) * (v.size() ? v.size() : 1)));
+  CK(cudaMemcpy(d, v.data(), sizeof(T) * v.size(), cudaMemcpyHostToDevice));
+  return d;
+}
+template <typename T>
+void down(FILE* f, const T* d, size_t n) {
+  std::vector<T> v(n);
+  CK(cudaMemcpy(v.data(), d, sizeof(T) * n, cudaMemcpyDeviceToHost));
+  fwrite(v.data(), sizeof(T), n, f);
+}
+
+int main(int argc, char** argv) {
+  if (argc < 3) return 1;
+  FILE* fi = fopen(argv[1], "rb");
+  FILE* fo = fopen(argv[2], "wb");
+  if (!fi || !fo) return 1;
+  // header: nloc nall nnei ntypes max_nbor nspline M
+  auto hd = rd<int>(fi, 7);
+  const int nloc = hd[0], nall = hd[1], nnei = hd[2], ntypes = hd[3], max_nbor = hd[4], nspline = hd[5], M = hd[6];
+  auto sec = rd<int>(fi, ntypes + 1);
+  auto rc = rd<float>(fi, 2);  // rcut, rcut_smth
+  auto coord = rd<double>(fi, (size_t)nall * 3);
+  auto type = rd<int>(fi, nall);
+  auto numneigh = rd<int>(fi, nloc);
+  auto rows = rd<int>(fi, (size_t)nloc * max_nbor);
+  auto avg = rd<double>(fi, (size_t)ntypes * nnei * 4);
+  auto std_ = rd<double>(fi, (size_t)ntypes * nnei * 4);
+  auto table = rd<double>(fi, (size_t)nspline * M * 6);
+  auto info = rd<double>(fi, 6);
+  auto net_deriv = rd<double>(fi, (size_t)nloc * nnei * 4);
+  auto dy = rd<double>(fi, (size_t)nloc * 4 * M);
+
+  double *d_coord = up(coord), *d_avg = up(avg), *d_std = up(std_), *d_table = up(table), *d_nd = up(net_deriv),
+         *d_dy = up(dy);
+  int *d_type = up(type), *d_numneigh = up(numneigh), *d_rows = up(rows);
+  std::vector<int> il(nloc);
+  std::vector<int*> first(nloc);
+  for (int i = 0; i < nloc; ++i) {
+    il[i] = i;
+    first[i] = d_rows + (size_t)i * max_nbor;
+  }
+  int* d_ilist = up(il);
+  int** d_first = nullptr;
+  CK(cudaMalloc((void**)&d_first, sizeof(int*) * nloc));
+  CK(cudaMemcpy(d_first, first.data(), sizeof(int*) * nloc, cudaMemcpyHostToDevice));
+  deepmd::InputNlist gpu_inlist(nloc, d_ilist, d_numneigh, d_first);
+
+  double *em, *dv, *rij, *desc, *gx, *gem, *force, *virial, *atom_virial;
+  int *nlist, *array_int;
+  unsigned long long* array_ll;
+  CK(cudaMalloc((void**)&em, sizeof(double) * nloc * nnei * 4));
+  CK(cudaMalloc((void**)&dv, sizeof(double) * nloc * nnei * 12));
+  CK(cudaMalloc((void**)&rij, sizeof(double) * nloc * nnei * 3));
+  CK(cudaMalloc((void**)&nlist, sizeof(int) * nloc * nnei));
+  CK(cudaMalloc((void**)&array_int, sizeof(int) * (sec.size() + (size_t)nloc * sec.size() + nloc)));
+  CK(cudaMalloc((void**)&array_ll, sizeof(unsigned long long) * (size_t)nloc * max_nbor * 2));
+  CK(cudaMalloc((void**)&desc, sizeof(double) * nloc * 4 * M));
+  CK(cudaMalloc((void**)&gx, sizeof(double) * nloc * nnei));
+  CK(cudaMalloc((void**)&gem, sizeof(double) * nloc * nnei * 4));
+  CK(cudaMalloc((void**)&force, sizeof(double) * nall * 3));
+  CK(cudaMalloc((void**)&virial, sizeof(double) * 9));
+  CK(cudaMalloc((void**)&atom_virial, sizeof(double) * nall * 9));
+
+  try {
+    deepmd::prod_env_mat_a_gpu<double>(em, dv, rij, nlist, d_coord, d_type, gpu_inlist, array_int, array_ll, max_nbor,
+                                       d_avg, d_std, nloc, nall, 1, rc[0], rc[1], sec);
+    // one table over the whole env-mat (em_x = component 0): the op-level call of tabulate_multi_device.cc
+    std::vector<double> h_em((size_t)nloc * nnei * 4), h_x((size_t)nloc * nnei);
+    CK(cudaMemcpy(h_em.data(), em, sizeof(double) * h_em.size(), cudaMemcpyDeviceToHost));
+    for (size_t k = 0; k < h_x.size(); ++k) h_x[k] = h_em[4 * k];
+    double* d_x = up(h_x);
+    deepmd::tabulate_fusion_se_a_gpu<double>(desc, d_table, info.data(), d_x, em, nullptr, nloc, nnei, M);
+    deepmd::tabulate_fusion_se_a_grad_gpu<double>(gx, gem, nullptr, d_table, info.data(), d_x, em, nullptr, d_dy, nloc,
+                                                  nnei, M);
+    deepmd::prod_force_a_gpu<double>(force, d_nd, dv, nlist, nloc, nall, nnei, 1);
+    deepmd::prod_virial_a_gpu<double>(virial, atom_virial, d_nd, dv, rij, nlist, nloc, nall, nnei);
+  } catch (const std::exception& e) {
+    fprintf(stderr, "exception: %s\n", e.what());
+    return 4;
+  }
+  down(fo, em, (size_t)nloc * nnei * 4);
+  down(fo, dv, (size_t)nloc * nnei * 12);
+  down(fo, rij, (size_t)nloc * nnei * 3);
+  down(fo, nlist, (size_t)nloc * nnei);
+  down(fo, desc, (size_t)nloc * 4 * M);
+  down(fo, gx, (size_t)nloc * nnei);
+  down(fo, gem, (size_t)nloc * nnei * 4);
+  down(fo, force, (size_t)nall * 3);
+  down(fo, virial, 9);
+  down(fo, atom_virial, (size_t)nall * 9);
+  fclose(fo);
+  printf("SHIM_DRIVER_OK\n");
+  return 0;
+}

@@ -1,0 +1,100 @@
+"""The reference-side C++ binding on a real GPU: tests/shim/_build/shim_driver (compiled here against
+the reference's own headers, see tests/shim/build.sh) calls deepmd::prod_env_mat_a_gpu,
+tabulate_fusion_se_a_gpu, tabulate_fusion_se_a_grad_gpu, prod_force_a_gpu and prod_virial_a_gpu from
+lib/libdeepmd_op_cuda.so exactly as the reference's op layers do; outputs are checked against the
+CPU oracle.  Plus a CPU-side check of the exported (mangled) symbol set."""
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from oracle import cpu as ocpu
+from _systems import extended_system, random_table, water_like_box
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+DRIVER = os.path.join(ROOT, "tests", "shim", "_build", "shim_driver")
+SHIM = os.path.join(ROOT, "deepmd-kit_b200", "lib", "libdeepmd_op_cuda.so")
+
+WANT = ["prod_env_mat_a_gpu", "format_nbor_list_gpu", "tabulate_fusion_se_a_gpu", "tabulate_fusion_se_a_grad_gpu",
+        "tabulate_fusion_se_a_grad_grad_gpu", "prod_force_a_gpu", "prod_virial_a_gpu", "normalize_coord_gpu",
+        "copy_coord_gpu", "build_nlist_gpu"]
+
+
+def test_shim_exports_reference_symbols():
+    if not os.path.exists(SHIM):
+        pytest.skip("libdeepmd_op_cuda.so not built (needs the reference headers)")
+    out = subprocess.run(["nm", "-DC", "--defined-only", SHIM], capture_output=True, text=True, check=True).stdout
+    for name in WANT:
+        for fp in ("double", "float"):
+            assert f"deepmd::{name}<{fp}>(" in out, f"missing deepmd::{name}<{fp}>"
+    assert "deepmd::use_nlist_map(int*, int const*, int, int)" in out
+    # Itanium-mangled names as a caller compiled against the reference headers would reference them
+    raw = subprocess.run(["nm", "-D", "--defined-only", SHIM], capture_output=True, text=True, check=True).stdout
+    assert "_ZN6deepmd16prod_force_a_gpuIdEEvPT_PKS1_S4_PKiiiii" in raw
+
+
+@pytest.mark.gpu
+def test_shim_driver_matches_oracle(port, tmp_path):
+    if not os.path.exists(DRIVER):
+        pytest.skip("tests/shim/_build/shim_driver not built (needs the reference headers)")
+    rng = np.random.default_rng(5)
+    coord, atype, box = water_like_box(ncopy=2, seed=4, jitter=0.05)
+    s = extended_system(port, coord, atype, box, 6.5)
+    sec = np.array([0, 46, 138], np.int32)
+    nnei, nloc, nall = 138, s["nloc"], len(s["atype"])
+    avg = rng.normal(scale=0.05, size=(2, nnei * 4))
+    avg[:, 1::4] = avg[:, 2::4] = avg[:, 3::4] = 0
+    std = 0.08 + 0.1 * rng.random(size=(2, nnei * 4))
+    M = 100
+    info = np.array([-1.0, 3.0, 15.0, 0.05, 0.5, -1.0])
+    nspline = int((info[1] - info[0]) / info[3] + (info[2] - info[1]) / info[4])
+    table = random_table(nspline, M, rng)
+    nd = rng.normal(size=(nloc, nnei * 4))
+    dy = rng.normal(size=(nloc, 4, M))
+    max_nbor = s["rows"].shape[1]
+    fin, fout = tmp_path / "in.bin", tmp_path / "out.bin"
+    with open(fin, "wb") as f:
+        np.array([nloc, nall, nnei, 2, max_nbor, nspline, M], np.int32).tofile(f)
+        sec.tofile(f)
+        np.array([6.0, 0.5], np.float32).tofile(f)
+        for a, dt in ((s["coord"], np.float64), (s["atype"], np.int32), (s["numneigh"], np.int32), (s["rows"], np.int32),
+                      (avg, np.float64), (std, np.float64), (table, np.float64), (info, np.float64), (nd, np.float64),
+                      (dy, np.float64)):
+            np.ascontiguousarray(a, dtype=dt).tofile(f)
+    r = subprocess.run([DRIVER, str(fin), str(fout)], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0 and "SHIM_DRIVER_OK" in r.stdout, r.stderr[-2000:]
+    raw = open(fout, "rb").read()
+    off = 0
+
+    def take(n, dt):
+        nonlocal off
+        a = np.frombuffer(raw, dtype=dt, count=n, offset=off)
+        off += n * np.dtype(dt).itemsize
+        return a
+
+    em, dv, rij = take(nloc * nnei * 4, np.float64), take(nloc * nnei * 12, np.float64), take(nloc * nnei * 3, np.float64)
+    nlist = take(nloc * nnei, np.int32)
+    desc, gx, gem = take(nloc * 4 * M, np.float64), take(nloc * nnei, np.float64), take(nloc * nnei * 4, np.float64)
+    force, virial, av = take(nall * 3, np.float64), take(9, np.float64), take(nall * 9, np.float64)
+    o, neigh = ocpu.dense_to_csr(s["rows"], s["numneigh"])
+    w_em, w_dv, w_rij, w_nl = port.prod_env_mat_a(s["coord"], s["atype"], o, neigh, avg, std, nloc, 6.0, 0.5, sec)
+    assert np.array_equal(nlist.reshape(nloc, nnei), w_nl)
+
+    def close(a, b, tol=1e-10):
+        b = np.asarray(b).reshape(-1)
+        assert np.abs(a - b).max() <= tol * max(np.abs(b).max(), 1e-300)
+
+    close(em, w_em)
+    close(dv, w_dv)
+    close(rij, w_rij)
+    em3 = w_em.reshape(nloc, nnei, 4)
+    em_x = np.ascontiguousarray(em3[:, :, 0]).reshape(-1, 1)
+    close(desc, port.tabulate_fusion_se_a(table, info, em_x, em3, M), 4e-10)
+    wx, wem, _ = port.tabulate_fusion_se_a_grad(table, info, em_x, em3, dy, M)
+    close(gx, wx, 4e-10)
+    close(gem, wem, 4e-10)
+    close(force, port.prod_force_a(nd, w_dv, w_nl, nall), 4e-10)
+    wv, wav = port.prod_virial_a(nd, w_dv, w_rij, w_nl, nall)
+    close(virial, wv, 2e-9)
+    close(av, wav, 4e-10)
