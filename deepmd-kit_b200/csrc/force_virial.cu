@@ -34,7 +34,8 @@ struct FvParams {
   const FP* rij;
   const int* nlist;
   int nloc, nall, nnei;
-  long long nrows;  // nframes * nloc
+  long long nrows;    // nframes * nloc
+  int center_offset;  // centre atom of row r is r + center_offset (atom-chunked evaluation)
 };
 
 __device__ __forceinline__ void ld2(const double* q, double& a, double& b) {
@@ -91,7 +92,7 @@ __global__ void __launch_bounds__(128) k_force_virial(const __grid_constant__ Fv
 
   for (long long row = (long long)blockIdx.x * 4 + warp; row < p.nrows; row += (long long)gridDim.x * 4) {
     const long long frame = row / p.nloc;
-    const int i = (int)(row - frame * p.nloc);
+    const int i = (int)(row - frame * p.nloc) + p.center_offset;
     const FP* __restrict__ nd = p.net_deriv + row * nnei * 4;
     const FP* __restrict__ ed = p.in_deriv + row * nnei * 12;
     const int* __restrict__ nl = p.nlist + row * nnei;
@@ -155,16 +156,20 @@ __global__ void __launch_bounds__(128) k_force_virial(const __grid_constant__ Fv
 template <typename FP, bool FORCE, bool VIRIAL>
 int launch_fv(FP* force, FP* virial, FP* atom_virial, const FP* net_deriv, const FP* in_deriv,
               const FP* rij, const int* nlist, int nloc, int nall, int nnei, int nframes,
-              cudaStream_t st) {
-  DPB_REQUIRE(nloc >= 0 && nall >= nloc && nnei >= 0 && nframes >= 1, "prod_force/virial: need nall >= nloc >= 0, nnei >= 0, nframes >= 1");
+              cudaStream_t st, int center_offset = 0, int accumulate = 0) {
+  DPB_REQUIRE(nloc >= 0 && nall >= 0 && nnei >= 0 && nframes >= 1 && center_offset >= 0 &&
+                  (long long)center_offset + nloc <= nall,
+              "prod_force/virial: need nall >= center_offset + nloc >= 0, nnei >= 0, nframes >= 1");
   if (FORCE) {
     DPB_REQUIRE(force != nullptr || nall == 0, "prod_force_a: force is null");
-    if (nall > 0) DPB_CUDA(cudaMemsetAsync(force, 0, sizeof(FP) * (size_t)nframes * nall * 3, st));
+    if (nall > 0 && !accumulate) DPB_CUDA(cudaMemsetAsync(force, 0, sizeof(FP) * (size_t)nframes * nall * 3, st));
   }
   if (VIRIAL) {
     DPB_REQUIRE(virial != nullptr, "prod_virial_a: virial is null");
-    DPB_CUDA(cudaMemsetAsync(virial, 0, sizeof(FP) * 9, st));
-    if (atom_virial && nall > 0) DPB_CUDA(cudaMemsetAsync(atom_virial, 0, sizeof(FP) * (size_t)nall * 9, st));
+    if (!accumulate) {
+      DPB_CUDA(cudaMemsetAsync(virial, 0, sizeof(FP) * 9, st));
+      if (atom_virial && nall > 0) DPB_CUDA(cudaMemsetAsync(atom_virial, 0, sizeof(FP) * (size_t)nall * 9, st));
+    }
   }
   const long long nrows = (long long)nframes * nloc;
   if (nrows == 0 || nnei == 0) return DPB200_OK;
@@ -183,6 +188,7 @@ int launch_fv(FP* force, FP* virial, FP* atom_virial, const FP* net_deriv, const
   p.nall = nall;
   p.nnei = nnei;
   p.nrows = nrows;
+  p.center_offset = center_offset;
   auto kern = k_force_virial<FP, FORCE, VIRIAL>;
   int occ = 0;
   DPB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, 128, 0));
@@ -230,6 +236,15 @@ extern "C" {
     return dpb200::launch_fv<FP, true, true>(force, virial, atom_virial, net_deriv, in_deriv,      \
                                              rij, nlist, nloc, nall, nnei, 1,                      \
                                              (cudaStream_t)stream);                                \
+  }                                                                                                \
+  int dpb200_prod_force_virial_a_ex_##SUF(FP* force, FP* virial, FP* atom_virial,                  \
+                                          const FP* net_deriv, const FP* in_deriv, const FP* rij,  \
+                                          const int* nlist, int nrows, int center_offset,          \
+                                          int nall, int nnei, int accumulate,                      \
+                                          dpb200_stream_t stream) {                                \
+    return dpb200::launch_fv<FP, true, true>(force, virial, atom_virial, net_deriv, in_deriv,      \
+                                             rij, nlist, nrows, nall, nnei, 1,                     \
+                                             (cudaStream_t)stream, center_offset, accumulate);     \
   }
 DPB200_DEF_FV(f64, double)
 DPB200_DEF_FV(f32, float)

@@ -106,9 +106,20 @@ def _rows_args(numneigh, rows, firstneigh, max_nbor_size):
 
 
 def prod_env_mat_a(coord, atype, numneigh, rows, avg, std, nloc, nall, rcut, rcut_smth, sec, *, ilist=None,
-                   f_type=None, firstneigh=None, nframes=1, max_nbor_size=None):
+                   f_type=None, firstneigh=None, nframes=1, max_nbor_size=None, row_range=None):
     """deepmd::prod_env_mat_a_gpu (source/lib/include/prod_env_mat.h:91-110): returns
-    (em[nf*nloc, nnei*4], em_deriv[nf*nloc, nnei*12], rij[nf*nloc, nnei*3], nlist[nf*nloc, nnei])."""
+    (em[nf*nloc, nnei*4], em_deriv[nf*nloc, nnei*12], rij[nf*nloc, nnei*3], nlist[nf*nloc, nnei]).
+    row_range=(a, b) (single frame, dense rows): only centre atoms a..b-1, outputs have b-a rows."""
+    if row_range is not None:
+        a, b = int(row_range[0]), int(row_range[1])
+        if nframes != 1 or rows is None or ilist is not None:
+            raise ValueError("dpb200: row_range needs one frame, dense rows and no ilist")
+        numneigh = numneigh[a:b]
+        rows = rows[a:b]
+        ilist = torch.arange(a, b, dtype=torch.int32, device=coord.device)
+        nloc_eff, shift = b - a, a
+    else:
+        nloc_eff, shift = nloc, 0
     dev = _need_cuda(("coord", coord), ("type", atype), ("numneigh", numneigh), ("rows", rows), ("avg", avg),
                      ("std", std), ("ilist", ilist), ("f_type", f_type), ("firstneigh", firstneigh))
     s = _suffix(coord)
@@ -132,7 +143,7 @@ def prod_env_mat_a(coord, atype, numneigh, rows, avg, std, nloc, nall, rcut, rcu
     rows_t, stride, fn, mx = _rows_args(numneigh, rows, firstneigh, max_nbor_size)
     if mx > MAX_NBOR_SIZE:
         raise ValueError(f"dpb200: neighbour rows wider than {MAX_NBOR_SIZE} are not supported")
-    n = nframes * nloc
+    n = nframes * nloc_eff
     em = torch.empty((n, nnei * 4), dtype=coord.dtype, device=dev)
     dv = torch.empty((n, nnei * 12), dtype=coord.dtype, device=dev)
     rij = torch.empty((n, nnei * 3), dtype=coord.dtype, device=dev)
@@ -140,9 +151,14 @@ def prod_env_mat_a(coord, atype, numneigh, rows, avg, std, nloc, nall, rcut, rcu
     L = lib()
     wsb = L.cdll.dpb200_prod_env_mat_a_workspace_bytes(ntypes, nnei, nall, nframes, coord.element_size())
     ws = _workspace(wsb, dev)
-    L.call("prod_env_mat_a_" + s, _p(em), _p(dv), _p(rij), _p(nlist), _p(coord), _p(atype), _p(f_type), _p(ilist),
-           _p(numneigh), _p(fn), _p(rows_t), stride, mx, _p(avg), _p(std), nloc, nall, nframes, float(rcut),
-           float(rcut_smth), sec_c, nsec, _p(ws), ws.numel(), _stream(dev))
+    esz = coord.element_size()
+    # the kernel writes row ilist[r] of each output: with a row range the output pointers are moved
+    # back by `shift` rows so that centre atom a lands in row 0 of the compact chunk buffers
+    po = lambda t, width, b_: C.c_void_p(t.data_ptr() - shift * width * b_)
+    L.call("prod_env_mat_a_" + s, po(em, nnei * 4, esz), po(dv, nnei * 12, esz), po(rij, nnei * 3, esz),
+           po(nlist, nnei, 4), _p(coord), _p(atype), _p(f_type), _p(ilist), _p(numneigh), _p(fn), _p(rows_t), stride, mx,
+           _p(avg), _p(std), nloc_eff, nall, nframes, float(rcut), float(rcut_smth), sec_c, nsec, _p(ws), ws.numel(),
+           _stream(dev))
     return em, dv, rij, nlist
 
 
@@ -356,6 +372,19 @@ def prod_force_virial_a(net_deriv, in_deriv, rij, nlist, nloc, nall, nnei, atom_
     lib().call("prod_force_virial_a_" + s, _p(force), _p(virial), _p(av), _p(net_deriv), _p(in_deriv), _p(rij),
                _p(nlist), nloc, nall, nnei, _stream(dev))
     return force, virial, av
+
+
+def prod_force_virial_a_ex(force, virial, atom_virial, net_deriv, in_deriv, rij, nlist, nrows, center_offset, nall,
+                           nnei, accumulate):
+    """Atom-chunked fused scatter into caller-provided force[nall*3] / virial[9] / atom_virial|None."""
+    dev = _need_cuda(("net_deriv", net_deriv), ("in_deriv", in_deriv), ("rij", rij), ("nlist", nlist), ("force", force))
+    s = _suffix(net_deriv)
+    dt = net_deriv.dtype
+    net_deriv, in_deriv, rij, nlist = _c(net_deriv), _c(in_deriv, dt), _c(rij, dt), _c(nlist, torch.int32)
+    lib().call("prod_force_virial_a_ex_" + s, _p(force), _p(virial), _p(atom_virial), _p(net_deriv), _p(in_deriv),
+               _p(rij), _p(nlist), int(nrows), int(center_offset), int(nall), int(nnei), int(bool(accumulate)),
+               _stream(dev))
+    return force, virial, atom_virial
 
 
 # ------------------------------------------------------------------------------------------------

@@ -151,7 +151,14 @@ DPB200_DECL_TAB(f32, float)
   int dpb200_prod_force_virial_a_##SUF(FP* force, FP* virial, FP* atom_virial,                     \
                                        const FP* net_deriv, const FP* in_deriv, const FP* rij,     \
                                        const int* nlist, int nloc, int nall, int nnei,             \
-                                       dpb200_stream_t stream);
+                                       dpb200_stream_t stream);                                    \
+  /* atom-chunked form: rows r = 0..nrows-1 belong to centre atoms center_offset + r; with           \
+   * accumulate != 0 the outputs are added to instead of zeroed first (sum over chunks) */          \
+  int dpb200_prod_force_virial_a_ex_##SUF(FP* force, FP* virial, FP* atom_virial,                  \
+                                          const FP* net_deriv, const FP* in_deriv, const FP* rij,  \
+                                          const int* nlist, int nrows, int center_offset,          \
+                                          int nall, int nnei, int accumulate,                      \
+                                          dpb200_stream_t stream);
 DPB200_DECL_FV(f64, double)
 DPB200_DECL_FV(f32, float)
 #undef DPB200_DECL_FV
