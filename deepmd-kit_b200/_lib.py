@@ -41,8 +41,19 @@ _SIGS = {
     "se_a_descriptor_grad_{s}": "pppp l ii d p",
     "mlp_tanh_fwd_{s}": "pppp l i p",
     "mlp_tanh_bwd_{s}": "pp l pp l i p",
+    "mlp_tanh_fwd_split_{s}": "pppp l i p p",
+    "mlp_tanh_bwd_split_{s}": "pp l pp l i p p",
+    "tabulate_fusion_se_a_desc_{s}": "ppp pli pl iiiii i d p i p l i p p",
     "halo_pack_{s}": "pppp i p",
     "halo_unpack_add_{s}": "ppp i p",
+}
+
+
+# entry points that exist for one FPTYPE only
+_PLAIN_SIGS = {
+    "split_i8_rows_f64": "p l p p l l i i p",
+    "split_i8_combine_f64": "pp p l i pp ppp l i i p",
+    "split_tf32_f32": "p l p l l i i p",
 }
 
 
@@ -77,6 +88,10 @@ class _Lib:
             f = getattr(self.cdll, fn)
             f.restype = C.c_size_t
             f.argtypes = [_T[c] for c in res]
+        for fn, sig in _PLAIN_SIGS.items():
+            f = getattr(self.cdll, "dpb200_" + fn)
+            f.restype = C.c_int
+            f.argtypes = [_T[c] for c in sig.replace(" ", "")]
         self.cdll.dpb200_use_nlist_map.restype = C.c_int
         self.cdll.dpb200_use_nlist_map.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p]
         for pat, sig in _SIGS.items():
@@ -93,6 +108,7 @@ class _Lib:
         for pat in _SIGS:
             for s in ("f32", "f64"):
                 names.append("dpb200_" + pat.format(s=s))
+        names.extend("dpb200_" + fn for fn in _PLAIN_SIGS)
         return names
 
     def launch_count(self) -> int:

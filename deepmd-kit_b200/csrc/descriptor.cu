@@ -141,28 +141,45 @@ __global__ void __launch_bounds__(192) k_desc_bwd(FP* __restrict__ dX, const FP*
 // Fused elementwise passes of the fitting MLP (deepmd/pt/model/network/mlp.py: tanh, resnet_dt, skip):
 //   forward : a = tanh(z) (kept for the backward, overwrites z); y = a*idt (+ h when the widths match)
 //   backward: t = g * idt * (1 - a^2)
+// `sp` (fp32 only, may be null): the result is ALSO written as the 3xTF32 left operand of the next GEMM,
+// sp[r] = [hi | lo | hi] (3*width floats per row), hi = tf32(v), lo = tf32(v - hi) -- see fitting.cu.
+__device__ __forceinline__ void put_split3(float* sp, long long r, int c, int width, float v) {
+  unsigned u;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(v));
+  const float hi = __uint_as_float(u);
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(v - hi));
+  float* o = sp + r * 3 * width;
+  o[c] = hi;
+  o[width + c] = __uint_as_float(u);
+  o[2 * width + c] = hi;
+}
+__device__ __forceinline__ void put_split3(double*, long long, int, int, double) {}
+
 template <typename FP>
 __global__ void k_mlp_act_fwd(FP* __restrict__ z_a, FP* __restrict__ y, const FP* __restrict__ h,
-                              const FP* __restrict__ idt, long long n, int width) {
+                              const FP* __restrict__ idt, long long n, int width, FP* __restrict__ sp) {
   for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < n; e += (long long)gridDim.x * blockDim.x) {
-    const int c = (int)(e % width);
+    const long long r = e / width;
+    const int c = (int)(e - r * width);
     const FP a = tanh(z_a[e]);
     z_a[e] = a;
     FP v = idt ? a * idt[c] : a;
     if (h) v += h[e];
     y[e] = v;
+    if (sp) put_split3(sp, r, c, width, v);
   }
 }
 template <typename FP>
 __global__ void k_mlp_act_bwd(FP* __restrict__ t, const FP* __restrict__ g, long long ldg, const FP* __restrict__ a,
-                              const FP* __restrict__ idt, long long n, int width) {
+                              const FP* __restrict__ idt, long long n, int width, FP* __restrict__ sp) {
   for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < n; e += (long long)gridDim.x * blockDim.x) {
     const long long r = e / width;
     const int c = (int)(e - r * width);
     const FP av = a[e];
     FP v = g[r * ldg + c] * ((FP)1. - av * av);
     if (idt) v *= idt[c];
-    t[e] = v;
+    if (t) t[e] = v;
+    if (sp) put_split3(sp, r, c, width, v);
   }
 }
 
@@ -202,7 +219,8 @@ int desc_launch(bool bwd, FP* out, const FP* dD, const FP* X, const int* rows, l
 
 template <typename FP>
 int act_launch(bool bwd, FP* out, FP* z_a, const FP* g, long long ldg, const FP* h, const FP* idt, long long nrow,
-               int width, cudaStream_t st) {
+               int width, cudaStream_t st, FP* sp = nullptr) {
+  DPB_REQUIRE(sp == nullptr || sizeof(FP) == 4, "mlp activation: the TF32 split output exists for fp32 only");
   DPB_REQUIRE(nrow >= 0 && width >= 1, "mlp activation: bad shape");
   const long long n = nrow * width;
   if (n == 0) return DPB200_OK;
@@ -210,11 +228,11 @@ int act_launch(bool bwd, FP* out, FP* z_a, const FP* g, long long ldg, const FP*
   const int cap = sm_count() * 16;
   if (grid > cap) grid = cap;
   if (bwd) {
-    DPB_REQUIRE(out && g && z_a, "mlp activation backward: null pointer");
-    k_mlp_act_bwd<FP><<<grid, 256, 0, st>>>(out, g, ldg, z_a, idt, n, width);
+    DPB_REQUIRE((out || sp) && g && z_a, "mlp activation backward: null pointer");
+    k_mlp_act_bwd<FP><<<grid, 256, 0, st>>>(out, g, ldg, z_a, idt, n, width, sp);
   } else {
     DPB_REQUIRE(out && z_a, "mlp activation forward: null pointer");
-    k_mlp_act_fwd<FP><<<grid, 256, 0, st>>>(z_a, out, h, idt, n, width);
+    k_mlp_act_fwd<FP><<<grid, 256, 0, st>>>(z_a, out, h, idt, n, width, sp);
   }
   DPB_CUDA(cudaGetLastError());
   note_launches(1);
@@ -246,6 +264,16 @@ extern "C" {
                                 long long nrow, int width, dpb200_stream_t stream) {                    \
     return dpb200::act_launch<FP>(true, t, const_cast<FP*>(a), g, ldg, nullptr, idt, nrow, width,       \
                                   (cudaStream_t)stream);                                                \
+  }                                                                                                     \
+  int dpb200_mlp_tanh_fwd_split_##SUF(FP* z_a, FP* y, const FP* h, const FP* idt, long long nrow,       \
+                                      int width, FP* split3, dpb200_stream_t stream) {                  \
+    return dpb200::act_launch<FP>(false, y, z_a, nullptr, 0, h, idt, nrow, width,                       \
+                                  (cudaStream_t)stream, split3);                                        \
+  }                                                                                                     \
+  int dpb200_mlp_tanh_bwd_split_##SUF(FP* t, const FP* g, long long ldg, const FP* a, const FP* idt,    \
+                                      long long nrow, int width, FP* split3, dpb200_stream_t stream) {  \
+    return dpb200::act_launch<FP>(true, t, const_cast<FP*>(a), g, ldg, nullptr, idt, nrow, width,       \
+                                  (cudaStream_t)stream, split3);                                        \
   }
 DPB200_DEF_DESC(f64, double)
 DPB200_DEF_DESC(f32, float)

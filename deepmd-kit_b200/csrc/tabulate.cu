@@ -65,6 +65,13 @@ struct TabParams {
   FP* dy_dem_x;
   FP* dy_dem;
   FP* dy_dtwo;
+  // descriptor emission fused into the forward's epilogue (k_tab_fwd<..., DESC = true>)
+  void* desc;           // mode 1: FP [row][M*axis]; mode 2: split operand of the fitting net's first GEMM
+  long long desc_ld;    // elements (of the stored type) per descriptor row
+  const int* desc_row;  // descriptor row of atom i (null: i)
+  int* row_exp;         // mode 2, fp64: binary exponent of the row's fixed-point scale
+  FP desc_scale;        // 1/nnei
+  int desc_mode, axis, nslice;
 };
 
 template <typename FP>
@@ -293,6 +300,148 @@ __device__ __forceinline__ void poly_both(const FP (&a)[6], FP x, FP& g, FP& gd)
   gd = b1 + c2 * x;
 }
 
+// ------------------------------------------------------------------------------------------
+// Fused descriptor epilogue: the warp that just finished atom i holds GR = out[i] ([4][M]) in
+// registers, so the se_e2_a descriptor D = (s GR)^T (s GR)[:, :axis], s = 1/nnei
+// (deepmd/pt/model/descriptor/se_a.py:843-850) is formed here and never makes a round trip
+// through HBM as a separate pass.  It is emitted directly in the operand format of the fitting
+// net's first GEMM:
+//   mode 1  D as FP [row][M*axis]
+//   mode 2  fp64: `nslice` signed 7-bit slices of the row's fixed-point image, most significant
+//           first, int8 [row][nslice][M*axis] + row_exp[row] (split-integer GEMM on the int8
+//           tensor cores, error-free products, fp64-grade sums);
+//           fp32: TF32 head and tail, float [row][2][M*axis] (3xTF32 GEMM).
+// The first `axis` columns of s*GR are staged in the (idle) per-warp record buffer and read back
+// as broadcasts.
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ float tf32_round(float x) {
+  unsigned u;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(x));
+  return __uint_as_float(u);
+}
+
+template <int NC>
+__device__ __forceinline__ void desc_store_split(const TabParams<float>& p, const float (&A)[4][NC], float s2,
+                                                 const float* __restrict__ stage, long long row, int lane) {
+  const int axis = p.axis, M = p.M;
+  float* __restrict__ hi = reinterpret_cast<float*>(p.desc) + row * p.desc_ld;
+  float* __restrict__ lo = hi + (long long)M * axis;
+#pragma unroll
+  for (int c = 0; c < NC; ++c) {
+    const int k1 = lane + 32 * c;
+    if (k1 < M) {
+      for (int k2 = 0; k2 < axis; k2 += 4) {
+        float v[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+        for (int m = 0; m < 4; ++m) {
+          const float4 b = *reinterpret_cast<const float4*>(stage + m * axis + k2);
+          v[0] += A[m][c] * b.x, v[1] += A[m][c] * b.y, v[2] += A[m][c] * b.z, v[3] += A[m][c] * b.w;
+        }
+#pragma unroll
+        for (int t = 0; t < 4; ++t) v[t] *= s2;
+        float4 h, l;
+        h.x = tf32_round(v[0]), h.y = tf32_round(v[1]), h.z = tf32_round(v[2]), h.w = tf32_round(v[3]);
+        l.x = tf32_round(v[0] - h.x), l.y = tf32_round(v[1] - h.y), l.z = tf32_round(v[2] - h.z),
+        l.w = tf32_round(v[3] - h.w);
+        *reinterpret_cast<float4*>(hi + k1 * axis + k2) = h;
+        *reinterpret_cast<float4*>(lo + k1 * axis + k2) = l;
+      }
+    }
+  }
+}
+
+template <int NC>
+__device__ __forceinline__ void desc_store_split(const TabParams<double>& p, const double (&A)[4][NC], double s2,
+                                                 const double* __restrict__ stage, long long row, int lane) {
+  // axis == 16 (checked on the host): one lane owns the 16 contiguous k2 of each of its channels.
+  const int M = p.M, ns = p.nslice;
+  // row scale from the Cauchy-Schwarz bound |D[k1][k2]| <= max_k |A[:,k]|^2 (attained on the diagonal)
+  double r2 = 0.;
+#pragma unroll
+  for (int c = 0; c < NC; ++c) {
+    const double n2 = A[0][c] * A[0][c] + A[1][c] * A[1][c] + A[2][c] * A[2][c] + A[3][c] * A[3][c];
+    r2 = (lane + 32 * c < M && n2 > r2) ? n2 : r2;
+  }
+  r2 *= s2;
+  int e = ((__double2hiint(r2) >> 20) & 0x7ff) - 1023;
+  e = __reduce_max_sync(kFull, e);
+  int E = e + 2;  // |D| < 2^(E-1)
+  E = E < -900 ? -900 : (E > 900 ? 900 : E);
+  if (lane == 0) p.row_exp[row] = E;
+  const int P = 6 + 7 * (ns - 1);  // fixed-point fraction bits
+  const double up = s2 * __hiloint2double((1023 + P - E) << 20, 0);
+  // bias that makes every base-128 digit non-negative: digit' = digit + 64
+  long long bias = 0;
+  for (int k = 0; k < ns; ++k) bias = bias * 128 + 64;
+  signed char* __restrict__ base = reinterpret_cast<signed char*>(p.desc) + row * p.desc_ld;
+  const long long K = (long long)M * 16;
+#pragma unroll
+  for (int c = 0; c < NC; ++c) {  // (unrolled: a runtime channel index would push acc[][] into local memory)
+    const int k1 = lane + 32 * c;
+    if (k1 < M) {
+#pragma unroll 1
+      for (int half = 0; half < 2; ++half) {
+        unsigned long long q[8];
+#pragma unroll
+        for (int t = 0; t < 8; t += 2) {
+          double v0 = 0., v1 = 0.;
+#pragma unroll
+          for (int m = 0; m < 4; ++m) {
+            const double2 b = *reinterpret_cast<const double2*>(stage + m * 16 + half * 8 + t);
+            v0 += A[m][c] * b.x, v1 += A[m][c] * b.y;
+          }
+          q[t] = (unsigned long long)(__double2ll_rn(v0 * up) + bias);
+          q[t + 1] = (unsigned long long)(__double2ll_rn(v1 * up) + bias);
+        }
+        for (int s = 0; s < ns; ++s) {  // slice s = digit ns-1-s
+          const int sh = 7 * (ns - 1 - s);
+          unsigned w[2];
+#pragma unroll
+          for (int g = 0; g < 2; ++g) {
+            const unsigned d0 = (unsigned)(q[4 * g + 0] >> sh) & 127u;
+            const unsigned d1 = (unsigned)(q[4 * g + 1] >> sh) & 127u;
+            const unsigned d2 = (unsigned)(q[4 * g + 2] >> sh) & 127u;
+            const unsigned d3 = (unsigned)(q[4 * g + 3] >> sh) & 127u;
+            const unsigned pk = d0 | (d1 << 8) | (d2 << 16) | (d3 << 24);
+            w[g] = ((pk | 0x80808080u) - 0x40404040u) ^ 0x80808080u;  // per-byte digit' - 64
+          }
+          *reinterpret_cast<uint2*>(base + s * K + (long long)k1 * 16 + half * 8) = make_uint2(w[0], w[1]);
+        }
+      }
+    }
+  }
+}
+
+template <typename FP, int NC>
+__device__ __forceinline__ void desc_epilogue(const TabParams<FP>& p, const FP (&acc)[4][NC], long long i,
+                                              int lane, FP* __restrict__ stage) {
+  const int axis = p.axis, M = p.M;
+  const long long row = p.desc_row ? (long long)p.desc_row[i] : i;
+  const FP s2 = p.desc_scale * p.desc_scale;
+  __syncwarp();  // the chunk's records are no longer needed
+  if (lane < axis) {
+#pragma unroll
+    for (int m = 0; m < 4; ++m) stage[m * axis + lane] = acc[m][0];
+  }
+  __syncwarp();
+  if (p.desc_mode == 2) {
+    desc_store_split<NC>(p, acc, s2, stage, row, lane);
+  } else {
+    FP* __restrict__ d = reinterpret_cast<FP*>(p.desc) + row * p.desc_ld;
+#pragma unroll
+    for (int c = 0; c < NC; ++c) {
+      const int k1 = lane + 32 * c;
+      if (k1 < M) {
+        for (int k2 = 0; k2 < axis; ++k2) {
+          const FP v = acc[0][c] * stage[k2] + acc[1][c] * stage[axis + k2] + acc[2][c] * stage[2 * axis + k2] +
+                       acc[3][c] * stage[3 * axis + k2];
+          st_cs(d + (long long)k1 * axis + k2, v * s2);
+        }
+      }
+    }
+  }
+}
+
 extern __shared__ __align__(16) unsigned char tab_smem[];
 
 // ------------------------------------------------------------------------------------------
@@ -300,7 +449,7 @@ extern __shared__ __align__(16) unsigned char tab_smem[];
 // grid (x: persistent over atoms, y: block of 32*NC channels); block = nw warps.
 // smem: hot[H][3][M] pairs | Rec[nw][32] | RecGG[nw][32] (GG only)
 // ------------------------------------------------------------------------------------------
-template <typename FP, int NC, bool TWO, bool GG>
+template <typename FP, int NC, bool TWO, bool GG, bool DESC = false>
 __global__ void __launch_bounds__(512) k_tab_fwd(const __grid_constant__ TabParams<FP> p) {
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
@@ -437,6 +586,10 @@ __global__ void __launch_bounds__(512) k_tab_fwd(const __grid_constant__ TabPara
 #pragma unroll
           for (int m = 0; m < 4; ++m) p.out[(i * 4 + m) * (long long)p.M + kc[c]] = acc[m][c];
         }
+      }
+      if (DESC) desc_epilogue<FP, NC>(p, acc, i, lane, reinterpret_cast<FP*>(rec));
+#pragma unroll
+      for (int c = 0; c < NC; ++c) {
 #pragma unroll
         for (int m = 0; m < 4; ++m)
           acc[m][c] = (p.accumulate && ni < p.nloc) ? p.out[(ni * 4 + m) * (long long)p.M + kc[c]] : (FP)0.;
@@ -715,14 +868,41 @@ int prepare_table(TabParams<FP>& p, FP** scratch, cudaStream_t st) {
   return DPB200_OK;
 }
 
+struct DescArgs {
+  void* desc;
+  long long desc_ld;
+  const int* desc_row;
+  int* row_exp;
+  double scale;
+  int mode, axis, nslice;
+};
+
 template <typename FP, bool GG>
 int launch_fwd(FP* out, const FP* table, const FP* info, const FP* em_x, long long ldx_i, int ldx_j,
                const FP* em, long long ldem_i, const FP* two, const FP* dz_x, const FP* dz_em,
                const FP* dz_two, int nloc, int nnei, int M, int is_sorted, int accumulate,
-               cudaStream_t st) {
+               cudaStream_t st, const DescArgs* da = nullptr) {
   DPB_REQUIRE(nloc >= 0 && nnei >= 0 && M >= 0, "tabulate: negative size");
   if (nloc == 0 || M == 0) return DPB200_OK;
   DPB_REQUIRE(out != nullptr, "tabulate: out is null");
+  if (da) {
+    const bool plain = !GG && two == nullptr && nnei > 0;
+    DPB_REQUIRE(plain, "tabulate+descriptor: plain se_a forward with nnei > 0 only");
+    DPB_REQUIRE(da->desc != nullptr && (da->mode == 1 || da->mode == 2), "tabulate+descriptor: desc is null / bad mode");
+    DPB_REQUIRE(M <= 128 && da->axis >= 1 && da->axis <= 32 && da->axis <= M,
+                "tabulate+descriptor: needs M <= 128 and axis <= min(32, M)");
+    DPB_REQUIRE(aligned16(da->desc), "tabulate+descriptor: desc must be 16-byte aligned");
+    if (da->mode == 2 && sizeof(FP) == 8) {
+      DPB_REQUIRE(da->axis == 16 && da->nslice >= 2 && da->nslice <= 8 && da->row_exp != nullptr &&
+                      da->desc_ld % 16 == 0 && da->desc_ld >= (long long)da->nslice * M * 16,
+                  "tabulate+descriptor: int8 split needs axis == 16, 2 <= nslice <= 8, row_exp, 16-byte rows");
+    } else if (da->mode == 2) {
+      DPB_REQUIRE(da->axis % 4 == 0 && da->desc_ld % 4 == 0 && da->desc_ld >= 2LL * M * da->axis,
+                  "tabulate+descriptor: TF32 split needs axis % 4 == 0 and 16-byte rows of >= 2*M*axis floats");
+    } else {
+      DPB_REQUIRE(da->desc_ld >= (long long)M * da->axis, "tabulate+descriptor: desc_ld < M*axis");
+    }
+  }
   if (nnei == 0) {  // an empty neighbour axis is a valid empty reduction (tabulate.cc:176-181)
     if (!accumulate) DPB_CUDA(cudaMemsetAsync(out, 0, sizeof(FP) * (size_t)nloc * 4 * M, st));
     return DPB200_OK;
@@ -737,6 +917,16 @@ int launch_fwd(FP* out, const FP* table, const FP* info, const FP* em_x, long lo
   p.dz_x = dz_x;
   p.dz_em = dz_em;
   p.dz_two = dz_two;
+  if (da) {
+    p.desc = da->desc;
+    p.desc_ld = da->desc_ld;
+    p.desc_row = da->desc_row;
+    p.row_exp = da->row_exp;
+    p.desc_scale = (FP)da->scale;
+    p.desc_mode = da->mode;
+    p.axis = da->axis;
+    p.nslice = da->nslice;
+  }
   if (GG) {
     DPB_REQUIRE(dz_x != nullptr && dz_em != nullptr, "tabulate grad_grad: dz_dy_dem_x / dz_dy_dem are null");
     DPB_REQUIRE(aligned16(dz_em), "tabulate grad_grad: dz_dy_dem must be 16-byte aligned");
@@ -760,7 +950,11 @@ int launch_fwd(FP* out, const FP* table, const FP* info, const FP* em_x, long lo
   cudaError_t e1 = cudaSuccess;
 #define DPB_LAUNCH_FWD(NC)                                                                      \
   do {                                                                                          \
-    if (tw) {                                                                                   \
+    if (da) {                                                                                   \
+      auto kern = k_tab_fwd<FP, NC, false, false, true>;                                        \
+      e1 = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);  \
+      if (e1 == cudaSuccess) kern<<<grid, nw * 32, smem, st>>>(p);                              \
+    } else if (tw) {                                                                                   \
       auto kern = k_tab_fwd<FP, NC, true, GG>;                                                  \
       e1 = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);  \
       if (e1 == cudaSuccess) kern<<<grid, nw * 32, smem, st>>>(p);                              \
@@ -867,6 +1061,17 @@ extern "C" {
                                          two_embed, nullptr, nullptr, nullptr, nloc, nnei,         \
                                          last_layer_size, is_sorted, accumulate,                   \
                                          (cudaStream_t)stream);                                    \
+  }                                                                                                \
+  int dpb200_tabulate_fusion_se_a_desc_##SUF(                                                      \
+      FP* out, const FP* table, const FP* table_info, const FP* em_x, long long ldx_i, int ldx_j,  \
+      const FP* em, long long ldem_i, int nloc, int nnei, int last_layer_size, int is_sorted,      \
+      int accumulate, int axis, double scale, const int* desc_row, int desc_mode, void* desc,      \
+      long long desc_ld, int nslice, int* row_exp, dpb200_stream_t stream) {                       \
+    dpb200::DescArgs da = {desc, desc_ld, desc_row, row_exp, scale, desc_mode, axis, nslice};      \
+    return dpb200::launch_fwd<FP, false>(out, table, table_info, em_x, ldx_i, ldx_j, em, ldem_i,   \
+                                         nullptr, nullptr, nullptr, nullptr, nloc, nnei,           \
+                                         last_layer_size, is_sorted, accumulate,                   \
+                                         (cudaStream_t)stream, &da);                               \
   }                                                                                                \
   int dpb200_tabulate_fusion_se_a_grad_##SUF(FP* dy_dem_x, FP* dy_dem, FP* dy_dtwo,                \
                                              const FP* table, const FP* table_info,                \

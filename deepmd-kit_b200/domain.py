@@ -192,8 +192,8 @@ class DomainDeepPot(DeepPotB200):
         ext_t = torch.cat([atype.to(torch.int32), gt]).contiguous()
         self.state = None
         numneigh, rows = ops.build_nlist(ext_c, nloc, rc, ext_t, cache=self._cache)
-        perm, ranges = self._type_partition(atype)
-        self.state = NeighborState(nloc, ext_t, None, None, numneigh, rows, perm, ranges)
+        perm, ranges, inv = self._type_partition(atype)
+        self.state = NeighborState(nloc, ext_t, None, None, numneigh, rows, perm, ranges, type_inv=inv)
         return self.state
 
     def eval_device(self, coord, atype, box, atom_virial=False, fused=True):
@@ -204,7 +204,8 @@ class DomainDeepPot(DeepPotB200):
         ext_c = self.halo_forward(c)
         st.ago += 1
         e, f_ext, virial, ex = self.model.evaluate(ext_c, st.ext_type, st.numneigh, st.rows, None, st.nloc,
-                                                   st.type_perm, st.type_ranges, atom_virial=atom_virial, fused=fused)
+                                                   st.type_perm, st.type_ranges, atom_virial=atom_virial, fused=fused,
+                                                   type_inv=st.type_inv)
         force = self.halo_reverse(f_ext, st.nloc)
         red = torch.cat([e.reshape(1), virial.reshape(9)])
         if dist.is_initialized() and dist.get_world_size(self.group) > 1:

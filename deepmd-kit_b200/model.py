@@ -64,6 +64,49 @@ class SeAConfig:
 COPPER_CONFIG = dict(ntypes=1, sel=(512,), rcut=8.0, rcut_smth=2.0, stats=[(0.06, 0.12, 0.07)], min_nbor_dist=2.0)
 
 
+def split_i8_cols(w: torch.Tensor, nslice: int):
+    """Host-side split of an fp64 weight matrix [K, N] into signed 7-bit slices per COLUMN scale:
+    w[:, c] = 2^col_exp[c] * sum_j slice_j[:, c] 2^(-6-7j).  Returns (slices int8 [nslice, K, N], most
+    significant first; col_exp int32 [N]).  Same digit convention as csrc/fitting.cu / tabulate.cu."""
+    w = w.detach().to("cpu", torch.float64)
+    m = w.abs().amax(0)
+    _, ex = torch.frexp(torch.where(m > 0, m, torch.ones_like(m)))  # m = mant * 2^ex, mant in [0.5, 1)
+    E = (ex + 1).to(torch.int32)  # |w| * 2^-E < 0.5
+    P = 6 + 7 * (nslice - 1)
+    q = torch.round(torch.ldexp(w, (P - E).to(torch.int32).unsqueeze(0).expand_as(w))).to(torch.int64)
+    bias = 0
+    for _ in range(nslice):
+        bias = bias * 128 + 64
+    q = q + bias
+    digits = [(((q >> (7 * k)) & 127) - 64).to(torch.int8) for k in range(nslice)]  # k = 0 least significant
+    return torch.stack(digits[::-1]), E
+
+
+def _tf32_round(x: torch.Tensor) -> torch.Tensor:
+    """Round-to-nearest (ties away, as cvt.rna.tf32.f32) of fp32 values to 10 mantissa bits."""
+    i = x.contiguous().view(torch.int32)
+    r = ((i + 0x1000) & ~0x1FFF).view(torch.float32)
+    return torch.where(torch.isfinite(x), r, x)
+
+
+def split_tf32_weight(w: torch.Tensor):
+    w = w.to(torch.float32)
+    hi = _tf32_round(w)
+    lo = _tf32_round(w - hi)
+    return hi, lo
+
+
+class _tf32_matmul:
+    """TF32 tensor-core GEMMs for the 3xTF32 products only (operands are pre-split, so the products are exact)."""
+
+    def __enter__(self):
+        self.prev = torch.backends.cuda.matmul.allow_tf32
+        torch.backends.cuda.matmul.allow_tf32 = True
+
+    def __exit__(self, *a):
+        torch.backends.cuda.matmul.allow_tf32 = self.prev
+
+
 class FittingNet:
     """Energy fitting net of one atom type: D -> neuron... -> 1, tanh, `resnet_dt` skip connections
     on equal-width layers (deepmd/pt/model/network/mlp.py), default normal init, bias_atom_e = 0."""
@@ -81,6 +124,31 @@ class FittingNet:
         w = torch.empty(n_in, 1, dtype=torch.float64).normal_(0.0, 1.0 / math.sqrt(n_in + 1), generator=g)
         b = torch.empty(1, dtype=torch.float64).normal_(0.0, 1.0, generator=g)
         self.head = (w.to(device, dtype), b.to(device, dtype))
+        self.dtype = dtype
+        self.split = None
+
+    def prepare_split(self, nslice: int = 7):
+        """Pre-split weights for the tensor-core GEMMs (see csrc/fitting.cu):
+        fp64: first layer as reversed int8 slice stack [nslice*K, N] + column exponents;
+        fp32: every layer as 3xTF32 stacks [Whi; Whi; Wlo] (forward) and of W^T (backward)."""
+        dev = self.layers[0][0].device
+        if self.dtype == torch.float64:
+            w0 = self.layers[0][0]
+            sl, ce = split_i8_cols(w0, nslice)  # [ns, K, N]
+            wrev = torch.cat([sl[k] for k in range(nslice - 1, -1, -1)], 0).contiguous()  # W_{ns-1}; ...; W_0
+            self.split = dict(nslice=nslice, wrev=wrev.to(dev), col_exp=ce.to(dev), K=w0.shape[0])
+        else:
+            fw, bw = [], []
+            for li, (w, b, idt) in enumerate(self.layers):
+                hi, lo = split_tf32_weight(w)
+                if li == 0:
+                    fw.append((torch.cat([hi, hi], 0).contiguous(), lo.contiguous()))  # operand [hi | lo]
+                else:
+                    fw.append(torch.cat([hi, hi, lo], 0).contiguous())  # operand [hi | lo | hi]
+                ht, lt = hi.t().contiguous(), lo.t().contiguous()
+                bw.append(torch.cat([ht, ht, lt], 0).contiguous())
+            self.split = dict(fw=fw, bw=bw, K=self.layers[0][0].shape[0])
+        return self
 
     def to(self, device, dtype):
         self.layers = [(w.to(device, dtype), b.to(device, dtype), None if i is None else i.to(device, dtype))
@@ -129,6 +197,79 @@ class FittingNet:
         return e, g
 
 
+    @torch.no_grad()
+    def forward_backward_split(self, xs: torch.Tensor, row_exp, n: int):
+        """forward_backward on a PRE-SPLIT descriptor block (rows of tabulate_sections_desc mode 2; xs may hold
+        more than n rows, the extra ones are ignored).  fp64: the first GEMM runs as `nslice` error-free int8
+        tensor-core GEMMs (one per order, K-concatenated) recombined in fp64; fp32: every GEMM is a 3xTF32 product."""
+        sp = self.split
+        if self.dtype == torch.float64:
+            ns, K = sp["nslice"], sp["K"]
+            w0, b0, idt0 = self.layers[0]
+            N = w0.shape[1]
+            m = max(n, 32)  # torch._int_mm needs more than 16 rows
+            acc = torch.empty((ns, m, N), dtype=torch.int32, device=xs.device)
+            for d in range(ns):
+                torch._int_mm(xs[:m, : (d + 1) * K], sp["wrev"][(ns - 1 - d) * K:], out=acc[d])
+            if m != n:
+                acc = acc[:, :n].contiguous()
+            a0, h = ops.split_i8_combine(acc, row_exp, sp["col_exp"], bias=b0, idt=idt0)
+            del acc
+            acts = [a0]
+            for w, b, idt in self.layers[1:]:
+                a = torch.addmm(b, h, w)
+                same = w.shape[0] == w.shape[1]
+                y = ops.mlp_tanh_fwd(a, h if same else None, idt)
+                if w.shape[1] == 2 * w.shape[0]:
+                    y.add_(torch.cat([h, h], 1))
+                acts.append(a)
+                h = y
+            e = torch.addmv(self.head[1], h, self.head[0][:, 0])
+            g = self.head[0][:, 0].unsqueeze(0).expand(n, -1)
+            for (w, b, idt), a in zip(reversed(self.layers), reversed(acts)):
+                t = ops.mlp_tanh_bwd(g, a, idt)
+                if w.shape[0] == w.shape[1]:
+                    g = torch.addmm(g, t, w.t())
+                elif w.shape[1] == 2 * w.shape[0]:
+                    n_in = w.shape[0]
+                    g = torch.addmm(g[:, :n_in] + g[:, n_in:], t, w.t())
+                else:
+                    g = t @ w.t()
+            return e, g
+        K = sp["K"]
+        with _tf32_matmul():
+            acts = []
+            h = None
+            hs = None
+            for li, (w, b, idt) in enumerate(self.layers):
+                if li == 0:
+                    wcat, wlo = sp["fw"][0]
+                    a = torch.addmm(b, xs[:n, : 2 * K], wcat)
+                    a.addmm_(xs[:n, :K], wlo)
+                else:
+                    a = torch.addmm(b, hs, sp["fw"][li])
+                same = w.shape[0] == w.shape[1]
+                y, ys = ops.mlp_tanh_fwd(a, h if (same and li > 0) else None, idt, split3=True)
+                if li > 0 and w.shape[1] == 2 * w.shape[0]:
+                    y.add_(torch.cat([h, h], 1))
+                    ys = ops.split_tf32(y, 3)
+                acts.append(a)
+                h, hs = y, ys
+            e = torch.addmv(self.head[1], h, self.head[0][:, 0])
+            g = self.head[0][:, 0].unsqueeze(0).expand(n, -1)
+            for li in range(len(self.layers) - 1, -1, -1):
+                w, b, idt = self.layers[li]
+                t3 = ops.mlp_tanh_bwd(g, acts[li], idt, split3=True)
+                if li > 0 and w.shape[0] == w.shape[1]:
+                    g = torch.addmm(g, t3, sp["bw"][li])
+                elif li > 0 and w.shape[1] == 2 * w.shape[0]:
+                    n_in = w.shape[0]
+                    g = torch.addmm(g[:, :n_in] + g[:, n_in:], t3, sp["bw"][li])
+                else:
+                    g = t3 @ sp["bw"][li]
+        return e, g
+
+
 class SeAModel:
     """Random-init compressed se_e2_a model (weights of the named architecture, tabulated with the
     restated `dp compress`)."""
@@ -158,6 +299,17 @@ class SeAModel:
         self.fit = [FittingNet(dim_d, cfg.fitting_neuron, cfg.fitting_resnet_dt, cfg.seed + 101 * t, dtype, self.device)
                     for t in range(cfg.ntypes)]
         self.fit_chunk = 1 << 17
+        # Tensor-core fitting net (csrc/fitting.cu): the descriptor leaves the tabulate forward already split
+        # (int8 slices in fp64, TF32 head/tail in fp32).  Needs axis == 16 (fp64) / axis % 4 == 0 (fp32),
+        # M <= 128 and a first fitting layer without skip connection.
+        self.nslice = 7
+        w0 = self.fit[0].layers[0][0]
+        ok_axis = cfg.axis_neuron == 16 if dtype == torch.float64 else cfg.axis_neuron % 4 == 0
+        self.use_split = bool(ok_axis and self.M <= 128 and cfg.axis_neuron <= 32 and w0.shape[1] not in
+                              (w0.shape[0], 2 * w0.shape[0]) and self.device.type == "cuda")
+        if self.use_split:
+            for f in self.fit:
+                f.prepare_split(self.nslice)
 
     # -- descriptor contraction (dpb200 kernels) + fitting net (cuBLAS GEMMs through torch, hand-written
     #    backward).  The fitting net is library code here; SURVEY 8f-1 lists its fusion as the next item.
@@ -180,15 +332,42 @@ class SeAModel:
                 e_atom.index_copy_(0, type_perm[c0:c1], e)
         return e_atom.sum(), e_atom, dy
 
+    def energy_and_dy_split(self, xyz, desc, row_exp, type_perm, type_ranges):
+        """energy_and_dy on the pre-split descriptor rows emitted by tabulate_sections_desc (type-sorted order)."""
+        cfg = self.cfg
+        nloc = xyz.shape[0]
+        dy = torch.empty_like(xyz)
+        e_atom = torch.empty(nloc, dtype=self.dtype, device=xyz.device)
+        type_perm32 = type_perm.to(torch.int32)
+        inv = 1.0 / cfg.nnei
+        for t, (a, b) in enumerate(type_ranges):
+            for c0 in range(a, b, self.fit_chunk):
+                c1 = min(b, c0 + self.fit_chunk)
+                e, gd = self.fit[t].forward_backward_split(desc[c0:], None if row_exp is None else row_exp[c0:c1],
+                                                           c1 - c0)
+                ops.se_a_descriptor_grad(gd, xyz, cfg.axis_neuron, inv, rows=type_perm32[c0:c1], out=dy)
+                e_atom.index_copy_(0, type_perm[c0:c1], e)
+        return e_atom.sum(), e_atom, dy
+
     def evaluate(self, ext_coord, ext_type, numneigh, rows, mapping, nloc, type_perm, type_ranges, atom_virial=False,
-                 fused=True):
+                 fused=True, type_inv=None):
         """One force evaluation on an extended system. Returns (E, force[nloc,3], virial[9], extras)."""
         cfg = self.cfg
         nall = ext_type.numel()
         em, dv, rij, nlist = ops.prod_env_mat_a(ext_coord.reshape(-1), ext_type, numneigh, rows, self.davg, self.dstd,
                                                 nloc, nall, cfg.rcut, cfg.rcut_smth, cfg.sec)
-        xyz = ops.tabulate_sections_fwd(self.tables, self.infos, em, cfg.sec, self.M)
-        energy, e_atom, dy = self.energy_and_dy(xyz, type_perm, type_ranges)
+        if self.use_split:
+            if type_inv is None:
+                type_inv = torch.empty(nloc, dtype=torch.int32, device=type_perm.device)
+                type_inv[type_perm] = torch.arange(nloc, dtype=torch.int32, device=type_perm.device)
+            xyz, desc, row_exp = ops.tabulate_sections_desc(self.tables, self.infos, em, cfg.sec, self.M,
+                                                            cfg.axis_neuron, 1.0 / cfg.nnei, desc_row=type_inv, mode=2,
+                                                            nslice=self.nslice, pad_rows=32)
+            energy, e_atom, dy = self.energy_and_dy_split(xyz, desc, row_exp, type_perm, type_ranges)
+            del desc
+        else:
+            xyz = ops.tabulate_sections_fwd(self.tables, self.infos, em, cfg.sec, self.M)
+            energy, e_atom, dy = self.energy_and_dy(xyz, type_perm, type_ranges)
         net_deriv = ops.tabulate_sections_grad(self.tables, self.infos, em, dy, cfg.sec, self.M)
         if mapping is not None:
             ops.use_nlist_map(nlist, mapping)
@@ -216,6 +395,7 @@ class NeighborState:
     type_ranges: list
     ago: int = 0
     map64: Optional[torch.Tensor] = None
+    type_inv: Optional[torch.Tensor] = None  # int32 inverse of type_perm: descriptor row of atom i
 
 
 def type_partition(atype: torch.Tensor, ntypes: int):
@@ -258,9 +438,12 @@ class DeepPotB200:
         key = (atype.data_ptr(), atype.numel())
         hit = self._cache.get("perm")
         if hit is None or hit[0] != key:
-            hit = (key,) + type_partition(atype, self.model.cfg.ntypes)
+            perm, ranges = type_partition(atype, self.model.cfg.ntypes)
+            inv = torch.empty(perm.numel(), dtype=torch.int32, device=perm.device)
+            inv[perm] = torch.arange(perm.numel(), dtype=torch.int32, device=perm.device)
+            hit = (key, perm, ranges, inv)
             self._cache["perm"] = hit
-        return hit[1], hit[2]
+        return hit[1], hit[2], hit[3]
 
     def build_neighbors(self, coord: torch.Tensor, atype: torch.Tensor, box) -> NeighborState:
         m = self.model
@@ -277,15 +460,15 @@ class DeepPotB200:
         shift = ops._buf(self._cache, "shift", (mapping.numel(), 3), coord.dtype, coord.device)
         torch.index_select(coord.reshape(-1, 3), 0, map64, out=shift)
         torch.sub(ext_c, shift, out=shift)
-        perm, ranges = self._type_partition(atype)
-        self.state = NeighborState(nloc, ext_t, mapping, shift, numneigh, rows, perm, ranges, map64=map64)
+        perm, ranges, inv = self._type_partition(atype)
+        self.state = NeighborState(nloc, ext_t, mapping, shift, numneigh, rows, perm, ranges, map64=map64, type_inv=inv)
         return self.state
 
     def _step(self, coord, atom_virial, fused):
         st = self.state
         ext_c = coord.reshape(-1, 3).index_select(0, st.map64).add_(st.shift)
         return self.model.evaluate(ext_c, st.ext_type, st.numneigh, st.rows, st.mapping, st.nloc, st.type_perm,
-                                   st.type_ranges, atom_virial=atom_virial, fused=fused)
+                                   st.type_ranges, atom_virial=atom_virial, fused=fused, type_inv=st.type_inv)
 
     def eval_device(self, coord: torch.Tensor, atype: torch.Tensor, box, atom_virial=False, fused=True):
         """Device tensors in, device tensors out (no host copies).  With `use_graph` the returned tensors

@@ -526,22 +526,124 @@ def se_a_descriptor_grad(dD, gr, axis, scale, rows=None, out=None):
     return out
 
 
-def mlp_tanh_fwd(z, h=None, idt=None):
-    """In place a = tanh(z); returns y = a*idt (+ h).  `z` becomes `a` (kept for the backward)."""
+def tabulate_sections_desc(tables, infos, em, sec, last_layer_size, axis, scale, desc_row=None, mode=1, nslice=7,
+                           pad_rows=0, is_sorted=True):
+    """tabulate_sections_fwd with the se_e2_a descriptor contraction fused into the last section's
+    epilogue (dpb200_tabulate_fusion_se_a_desc).  Returns (out [nloc,4,M], desc, row_exp|None):
+      mode 1            desc = D [nloc+pad, M*axis] in em.dtype;
+      mode 2, float64   desc = int8 [nloc+pad, nslice*M*axis] signed 7-bit slices, row_exp int32 [nloc+pad];
+      mode 2, float32   desc = float32 [nloc+pad, 2*M*axis] = TF32 head | tail.
+    Row desc_row[i] (int32; None: i) belongs to atom i; `pad_rows` extra zero rows are appended."""
+    dev = _need_cuda(("em", em), ("desc_row", desc_row))
+    s = _suffix(em)
+    em = _c(em)
+    nloc = em.shape[0]
+    nnei = int(sec[-1])
+    M = int(last_layer_size)
+    axis = int(axis)
+    K = M * axis
+    out = torch.empty((nloc, 4, M), dtype=em.dtype, device=dev)
+    rows = nloc + int(pad_rows)
+    row_exp = None
+    if mode == 1:
+        desc = torch.empty((rows, K), dtype=em.dtype, device=dev)
+    elif em.dtype == torch.float64:
+        desc = torch.empty((rows, int(nslice) * K), dtype=torch.int8, device=dev)
+        row_exp = torch.empty((rows,), dtype=torch.int32, device=dev)
+        if pad_rows:
+            row_exp[nloc:].zero_()
+    else:
+        desc = torch.empty((rows, 2 * K), dtype=torch.float32, device=dev)
+    if pad_rows:
+        desc[nloc:].zero_()
+    if desc_row is not None:
+        desc_row = _c(desc_row, torch.int32)
+    live = [t for t in range(len(tables)) if int(sec[t + 1] - sec[t]) > 0]
+    if not live:
+        raise ValueError("dpb200: tabulate_sections_desc needs at least one non-empty type section")
+    esz = em.element_size()
+    for n_done, t in enumerate(live):
+        n_t = int(sec[t + 1] - sec[t])
+        ti = _info_host(infos[t], em.dtype)
+        base = C.c_void_p(em.data_ptr() + int(sec[t]) * 4 * esz)
+        acc = 0 if n_done == 0 else 1
+        if t != live[-1]:
+            lib().call("tabulate_fusion_se_a_ex_" + s, _p(out), _p(_c(tables[t])), C.c_void_p(ti.data_ptr()), base,
+                       nnei * 4, 4, base, nnei * 4, None, nloc, n_t, M, int(bool(is_sorted)), acc, _stream(dev))
+        else:
+            lib().call("tabulate_fusion_se_a_desc_" + s, _p(out), _p(_c(tables[t])), C.c_void_p(ti.data_ptr()), base,
+                       nnei * 4, 4, base, nnei * 4, nloc, n_t, M, int(bool(is_sorted)), acc, axis, float(scale),
+                       _p(desc_row), int(mode), _p(desc), int(desc.shape[1]), int(nslice), _p(row_exp), _stream(dev))
+    return out, desc, row_exp
+
+
+def split_i8_rows(x, nslice):
+    """fp64 [n, w] -> (int8 [n, nslice*w] signed 7-bit slices, most significant first; row_exp int32 [n]):
+    x = 2^row_exp * sum_s slice_s * 2^(-6-7s)  (truncated after nslice digits)."""
+    dev = _need_cuda(("x", x))
+    if x.dtype != torch.float64 or x.dim() != 2 or x.stride(1) != 1:
+        raise ValueError("dpb200: split_i8_rows needs a float64 matrix with unit column stride")
+    n, w = x.shape
+    out = torch.empty((n, int(nslice) * w), dtype=torch.int8, device=dev)
+    ex = torch.empty((n,), dtype=torch.int32, device=dev)
+    lib().call("split_i8_rows_f64", _p(out), int(out.shape[1]), _p(ex), _p(x), int(x.stride(0)) if n > 1 else w, n, w,
+               int(nslice), _stream(dev))
+    return out, ex
+
+
+def split_i8_combine(acc, row_exp, col_exp, bias=None, idt=None, h=None, activation=True):
+    """acc int32 [nslice, n, w] (order sums of the split-integer GEMM) -> fp64.  activation: returns
+    (a = tanh(z), y = a*idt + h); otherwise z."""
+    dev = _need_cuda(("acc", acc), ("row_exp", row_exp), ("col_exp", col_exp), ("bias", bias), ("idt", idt), ("h", h))
+    if acc.dtype != torch.int32 or acc.dim() != 3 or not acc.is_contiguous():
+        raise ValueError("dpb200: split_i8_combine needs a contiguous int32 [nslice, n, w] tensor")
+    ns, n, w = acc.shape
+    a = torch.empty((n, w), dtype=torch.float64, device=dev)
+    y = torch.empty((n, w), dtype=torch.float64, device=dev) if activation else None
+    lib().call("split_i8_combine_f64", _p(a), _p(y), _p(acc), n * w, ns, _p(row_exp), _p(col_exp), _p(bias), _p(idt),
+               _p(h), n, w, int(bool(activation)), _stream(dev))
+    return (a, y) if activation else a
+
+
+def split_tf32(x, copies=3):
+    """fp32 [n, w] -> [n, copies*w] = [hi | lo (| hi)], hi = tf32(x), lo = tf32(x - hi)."""
+    dev = _need_cuda(("x", x))
+    if x.dtype != torch.float32 or x.dim() != 2 or x.stride(1) != 1:
+        raise ValueError("dpb200: split_tf32 needs a float32 matrix with unit column stride")
+    n, w = x.shape
+    out = torch.empty((n, int(copies) * w), dtype=torch.float32, device=dev)
+    lib().call("split_tf32_f32", _p(out), int(out.shape[1]), _p(x), int(x.stride(0)) if n > 1 else w, n, w, int(copies),
+               _stream(dev))
+    return out
+
+
+def mlp_tanh_fwd(z, h=None, idt=None, split3=False):
+    """In place a = tanh(z); returns y = a*idt (+ h).  `z` becomes `a` (kept for the backward).
+    split3 (fp32): also returns y as the 3xTF32 operand [hi | lo | hi] ([n, 3w])."""
     dev = _need_cuda(("z", z), ("h", h), ("idt", idt))
     s = _suffix(z)
     y = torch.empty_like(z)
-    lib().call("mlp_tanh_fwd_" + s, _p(z), _p(y), _p(h), _p(idt), z.shape[0], z.shape[1], _stream(dev))
-    return y
+    if not split3:
+        lib().call("mlp_tanh_fwd_" + s, _p(z), _p(y), _p(h), _p(idt), z.shape[0], z.shape[1], _stream(dev))
+        return y
+    sp = torch.empty((z.shape[0], 3 * z.shape[1]), dtype=z.dtype, device=dev)
+    lib().call("mlp_tanh_fwd_split_" + s, _p(z), _p(y), _p(h), _p(idt), z.shape[0], z.shape[1], _p(sp), _stream(dev))
+    return y, sp
 
 
-def mlp_tanh_bwd(g, a, idt=None):
-    """t = g * idt * (1 - a^2); g may be a row-strided view (leading stride g.stride(0))."""
+def mlp_tanh_bwd(g, a, idt=None, split3=False):
+    """t = g * idt * (1 - a^2); g may be a row-strided view (leading stride g.stride(0)).
+    split3 (fp32): returns t only as the 3xTF32 operand [hi | lo | hi] ([n, 3w])."""
     dev = _need_cuda(("g", g), ("a", a), ("idt", idt))
     s = _suffix(a)
     if g.stride(1) != 1 and g.shape[0] > 1:
         g = g.contiguous()
     ldg = g.stride(0) if g.shape[0] > 1 else g.shape[1]
+    if split3:
+        sp = torch.empty((a.shape[0], 3 * a.shape[1]), dtype=a.dtype, device=dev)
+        lib().call("mlp_tanh_bwd_split_" + s, None, _p(g), int(ldg), _p(a), _p(idt), a.shape[0], a.shape[1], _p(sp),
+                   _stream(dev))
+        return sp
     t = torch.empty_like(a)
     lib().call("mlp_tanh_bwd_" + s, _p(t), _p(g), int(ldg), _p(a), _p(idt), a.shape[0], a.shape[1], _stream(dev))
     return t

@@ -127,6 +127,20 @@ DPB200_DECL_ENV(f32, float)
       FP* dy_dem_x, FP* dy_dem, FP* dy_dtwo, const FP* table, const FP* table_info,                \
       const FP* em_x, long long ldx_i, int ldx_j, const FP* em, long long ldem_i,                  \
       const FP* two_embed, const FP* dy, int nloc, int nnei, int last_layer_size, int is_sorted,   \
+      dpb200_stream_t stream);                                                                     \
+  /* `_ex` forward of the LAST type section with the se_e2_a descriptor contraction fused into its \
+   * epilogue (deepmd/pt/model/descriptor/se_a.py:843-850): after out[i] is complete,              \
+   * D = (scale*out[i])^T (scale*out[i])[:, :axis] is written to row desc_row[i] (NULL: i) of      \
+   * `desc` (row stride desc_ld elements), in the operand format of the fitting net's first GEMM:  \
+   *   desc_mode 1: FP [M*axis];                                                                    \
+   *   desc_mode 2, f64: int8 [nslice][M*axis] signed 7-bit slices (most significant first) of     \
+   *     D * 2^-row_exp[row] (needs axis == 16);  f32: float [2][M*axis] = TF32 head | tail.        \
+   * M <= 128, axis <= 32, desc 16-byte aligned. */                                                \
+  int dpb200_tabulate_fusion_se_a_desc_##SUF(                                                      \
+      FP* out, const FP* table, const FP* table_info, const FP* em_x, long long ldx_i, int ldx_j,  \
+      const FP* em, long long ldem_i, int nloc, int nnei, int last_layer_size, int is_sorted,      \
+      int accumulate, int axis, double scale, const int* desc_row /*nullable*/, int desc_mode,     \
+      void* desc, long long desc_ld, int nslice, int* row_exp /*f64 mode 2*/,                      \
       dpb200_stream_t stream);
 DPB200_DECL_TAB(f64, double)
 DPB200_DECL_TAB(f32, float)
@@ -236,10 +250,35 @@ DPB200_DECL_HALO(f32, float)
                                 long long nrow, int width, dpb200_stream_t stream);                     \
   int dpb200_mlp_tanh_bwd_##SUF(FP* t, const FP* g, long long ldg, const FP* a,                         \
                                 const FP* idt /*nullable*/, long long nrow, int width,                  \
-                                dpb200_stream_t stream);
+                                dpb200_stream_t stream);                                                \
+  /* same, the result additionally (t may be NULL in _bwd_split) written as the 3xTF32 left operand   \
+   * [hi | lo | hi] of the next GEMM (split3: [nrow][3*width]; fp32 only, must be NULL for f64) */      \
+  int dpb200_mlp_tanh_fwd_split_##SUF(FP* z_a, FP* y, const FP* h, const FP* idt, long long nrow,       \
+                                      int width, FP* split3, dpb200_stream_t stream);                   \
+  int dpb200_mlp_tanh_bwd_split_##SUF(FP* t, const FP* g, long long ldg, const FP* a, const FP* idt,    \
+                                      long long nrow, int width, FP* split3, dpb200_stream_t stream);
 DPB200_DECL_DESC(f64, double)
 DPB200_DECL_DESC(f32, float)
 #undef DPB200_DECL_DESC
+
+/* ---------------------------------------------------------------------------------------
+ * Split operands for the fitting net's GEMMs on the tensor cores (csrc/fitting.cu): the GEMMs are
+ * library calls; these kernels make them fp64 / fp32 accurate.
+ *  split_i8_rows   : x [nrow][width] (row stride ldx) -> out int8 [nrow][nslice][width] (row stride
+ *                    ld_out bytes), row_exp[nrow]:  x = 2^row_exp * sum_s out[s] 2^(-6-7s)
+ *  split_i8_combine: z = 2^(row_exp[r]+col_exp[c]-12) * sum_d acc[d][r][c] 2^(-7d) + bias[c], acc[d] =
+ *                    int32 [nrow][width] at acc + d*acc_stride = sum_{i+j=d} X_i.W_j;  activation != 0:
+ *                    a_out = tanh(z), y_out = a*idt + h (mlp.py layer);  == 0: a_out = z.
+ *  split_tf32      : x -> [hi | lo (| hi)] with hi = tf32(x), lo = tf32(x - hi), copies = 2 | 3.
+ * ------------------------------------------------------------------------------------- */
+int dpb200_split_i8_rows_f64(signed char* out, long long ld_out, int* row_exp, const double* x, long long ldx,
+                             long long nrow, int width, int nslice, dpb200_stream_t stream);
+int dpb200_split_i8_combine_f64(double* a_out, double* y_out, const int* acc, long long acc_stride, int nslice,
+                                const int* row_exp, const int* col_exp, const double* bias /*nullable*/,
+                                const double* idt /*nullable*/, const double* h /*nullable*/, long long nrow,
+                                int width, int activation, dpb200_stream_t stream);
+int dpb200_split_tf32_f32(float* out, long long ld_out, const float* x, long long ldx, long long nrow, int width,
+                          int copies, dpb200_stream_t stream);
 
 /* use_nlist_map (neighbor_list.h:219-222): nlist[k] = map[nlist[k]] for entries >= 0. */
 int dpb200_use_nlist_map(int* nlist, const int* nlist_map, int nloc, int nnei, dpb200_stream_t stream);

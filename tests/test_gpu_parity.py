@@ -574,3 +574,120 @@ def test_fitting_forward_backward_matches_autograd():
         e2, g2 = f.forward_backward(x.detach())
         assert float((e.detach() - e2).abs().max()) <= tol * float(e.detach().abs().max())
         assert float((ga - g2).abs().max()) <= tol * float(ga.abs().max())
+
+
+# ------------------------------------------------------------------------------------------------
+# fused descriptor epilogue + split-operand fitting GEMMs (csrc/fitting.cu, tabulate.cu desc_epilogue)
+# ------------------------------------------------------------------------------------------------
+def _two_section_case(dtype, nloc=97, sel=(46, 92), M=100, seed=11):
+    rng = np.random.default_rng(seed)
+    nnei = sum(sel)
+    tables, infos = [], []
+    for t in range(len(sel)):
+        info = np.array([-0.4, 2.0, 6.0, 0.05, 0.5, -1.0], dtype)
+        nspline = int((info[1] - info[0]) / info[3]) + int((info[2] - info[1]) / info[4]) + 1
+        tables.append(T(random_table(nspline, M, rng, dtype)))
+        infos.append(torch.as_tensor(info))
+    em = rng.normal(scale=0.3, size=(nloc, nnei, 4)).astype(dtype)
+    em[:, :, 0] = np.sort(rng.uniform(-0.2, 2.5, size=(nloc, nnei)), axis=1)[:, ::-1]
+    # trailing padding per section, like a real env-mat
+    for i in range(nloc):
+        for t, (a, b) in enumerate(zip(np.cumsum((0,) + sel[:-1]), np.cumsum(sel))):
+            k = int(rng.integers(0, (b - a) // 2))
+            if k:
+                em[i, b - k:b, 0] = -0.37
+                em[i, b - k:b, 1:] = 0
+    sec = [0] + list(np.cumsum(sel))
+    return tables, infos, T(em.reshape(nloc, -1)), sec, M
+
+
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+def test_tabulate_desc_epilogue(ops, dtype):
+    tables, infos, em, sec, M = _two_section_case(dtype)
+    axis, nnei = 16, sec[-1]
+    nloc = em.shape[0]
+    want_out = ops.tabulate_sections_fwd(tables, infos, em, sec, M)
+    want_d = ops.se_a_descriptor(want_out, axis, 1.0 / nnei)
+    perm = torch.randperm(nloc, device=DEV).to(torch.int32)
+    # mode 1: plain D, permuted rows
+    out, d1, _ = ops.tabulate_sections_desc(tables, infos, em, sec, M, axis, 1.0 / nnei, desc_row=perm, mode=1)
+    assert torch.equal(out, want_out)
+    got = torch.empty_like(want_d)
+    got[:] = d1[perm.long()]
+    close(N(got), N(want_d), dtype)
+    # mode 2: split operand
+    out, d2, ex = ops.tabulate_sections_desc(tables, infos, em, sec, M, axis, 1.0 / nnei, desc_row=perm, mode=2,
+                                             nslice=7, pad_rows=32)
+    assert torch.equal(out, want_out)
+    assert d2.shape[0] == nloc + 32 and int(d2[nloc:].abs().sum()) == 0
+    K = M * axis
+    d2 = d2[perm.long()]
+    if dtype == np.float64:
+        sl = d2.reshape(nloc, 7, K).to(torch.float64)
+        assert int(sl.abs().max()) <= 64
+        w = torch.tensor([2.0 ** (-6 - 7 * s) for s in range(7)], dtype=torch.float64, device=DEV)
+        rec = (sl * w[None, :, None]).sum(1) * torch.ldexp(torch.ones((), dtype=torch.float64, device=DEV),
+                                                           ex[perm.long()].to(torch.int32))[:, None]
+        rowmax = want_d.abs().amax(1, keepdim=True)
+        err = ((rec - want_d).abs() / rowmax).max().item()
+        assert err < 2.0 ** -44, err
+    else:
+        hi, lo = d2[:, :K], d2[:, K:]
+        assert torch.equal(hi.view(torch.int32) & 0x1FFF, torch.zeros_like(hi, dtype=torch.int32))
+        assert torch.equal(lo.view(torch.int32) & 0x1FFF, torch.zeros_like(lo, dtype=torch.int32))
+        rowmax = want_d.abs().amax(1, keepdim=True)
+        assert (((hi + lo) - want_d).abs() / rowmax).max().item() < 2e-6
+
+
+def test_split_i8_gemm_matches_fp64(ops):
+    """sum over orders of K-concatenated int8 GEMMs == the fp64 product to ~2^-45 of the row/column scales."""
+    from deepmd_kit_b200.model import split_i8_cols
+
+    torch.manual_seed(5)
+    n, K, Nn, ns = 300, 1600, 240, 7
+    x = (torch.randn(n, K, dtype=torch.float64, device=DEV) * torch.logspace(-6, 1, n, dtype=torch.float64, device=DEV)[:, None])
+    w = torch.randn(K, Nn, dtype=torch.float64) * 0.03
+    xs, ex = ops.split_i8_rows(x, ns)
+    sl, ce = split_i8_cols(w, ns)
+    wrev = torch.cat([sl[k] for k in range(ns - 1, -1, -1)], 0).contiguous().to(DEV)
+    acc = torch.empty((ns, n, Nn), dtype=torch.int32, device=DEV)
+    for d in range(ns):
+        torch._int_mm(xs[:, : (d + 1) * K], wrev[(ns - 1 - d) * K:], out=acc[d])
+    z = ops.split_i8_combine(acc, ex, ce.to(DEV), activation=False)
+    want = x @ w.to(DEV)
+    scale = x.abs().amax(1, keepdim=True) * w.abs().amax(0, keepdim=True).to(DEV) * K ** 0.5
+    assert ((z - want).abs() / scale).max().item() < 1e-13
+    # with the fused layer epilogue
+    b = torch.randn(Nn, dtype=torch.float64, device=DEV)
+    idt = torch.rand(Nn, dtype=torch.float64, device=DEV)
+    a, y = ops.split_i8_combine(acc, ex, ce.to(DEV), bias=b, idt=idt)
+    assert torch.allclose(a, torch.tanh(want + b), rtol=0, atol=1e-12)
+    assert torch.allclose(y, torch.tanh(want + b) * idt, rtol=0, atol=1e-12)
+
+
+@pytest.mark.parametrize("dtype", [torch.float64, torch.float32])
+def test_fitting_split_matches_plain(ops, dtype):
+    """Tensor-core fitting net (int8 split / 3xTF32) against the plain GEMM forward/backward."""
+    from deepmd_kit_b200.model import FittingNet
+
+    torch.manual_seed(2)
+    n, K = 700, 1600
+    net = FittingNet(K, (240, 240, 240), True, 7, dtype, DEV).prepare_split(7)
+    d = torch.randn(n, K, dtype=dtype, device=DEV) * 0.02
+    e0, g0 = net.forward_backward(d)
+    if dtype == torch.float64:
+        xs, ex = ops.split_i8_rows(d, 7)
+        e1, g1 = net.forward_backward_split(xs, ex, n)
+        tol = 1e-11
+        ref_e, ref_g = e0, g0
+    else:
+        xs = ops.split_tf32(d, 2)
+        e1, g1 = net.forward_backward_split(xs, None, n)
+        net64 = FittingNet(K, (240, 240, 240), True, 7, torch.float64, DEV)
+        ref_e, ref_g = net64.forward_backward(d.double())
+        tol = 1e-5
+        # the plain fp32 path is the yardstick: the split path must not be worse than twice its error
+        tol_e = max(tol, 2 * ((e0.double() - ref_e).abs().max() / ref_e.abs().max()).item())
+        assert ((e1.double() - ref_e).abs().max() / ref_e.abs().max()).item() <= tol_e
+    assert ((e1.double() - ref_e.double()).abs().max() / ref_e.abs().max()).item() <= tol
+    assert ((g1.double() - ref_g.double()).abs().max() / ref_g.abs().max()).item() <= tol
