@@ -45,6 +45,41 @@ __device__ __forceinline__ T warp_sum(T v) {
   return v;
 }
 
+// Butterfly reduce-scatter: v[0..15] per lane -> lane l returns the warp-wide sum of v[(l >> 1) & 15].
+template <typename FP>
+__device__ __forceinline__ FP reduce_scatter16(FP (&v)[16], int lane) {
+#pragma unroll
+  for (int s = 16, n = 16; s >= 2; s >>= 1, n >>= 1) {
+    const bool up = (lane & s) != 0;
+#pragma unroll
+    for (int t = 0; t < n / 2; ++t) {
+      const FP send = up ? v[t] : v[t + n / 2];
+      const FP keep = up ? v[t + n / 2] : v[t];
+      v[t] = keep + __shfl_xor_sync(kFull, send, s);
+    }
+  }
+  return v[0] + __shfl_xor_sync(kFull, v[0], 1);
+}
+// Generic form: v[0..N-1] per lane (N = 2, 4, 8, 16, 32) -> lane l returns the warp-wide sum of
+// v[l >> log2(32 / N)].
+template <int N, typename FP>
+__device__ __forceinline__ FP reduce_scatter(FP (&v)[N], int lane) {
+  int s = 16;
+#pragma unroll
+  for (int n = N; n >= 2; n >>= 1, s >>= 1) {
+    const bool up = (lane & s) != 0;
+#pragma unroll
+    for (int t = 0; t < n / 2; ++t) {
+      const FP send = up ? v[t] : v[t + n / 2];
+      const FP keep = up ? v[t + n / 2] : v[t];
+      v[t] = keep + __shfl_xor_sync(kFull, send, s);
+    }
+  }
+  FP r = v[0];
+  for (; s >= 1; s >>= 1) r += __shfl_xor_sync(kFull, r, s);
+  return r;
+}
+
 // Streaming (evict-first) global stores for write-once outputs.
 __device__ __forceinline__ void st_cs(float* p, float v) { __stcs(p, v); }
 __device__ __forceinline__ void st_cs(double* p, double v) { __stcs(p, v); }

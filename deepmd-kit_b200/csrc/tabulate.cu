@@ -604,21 +604,6 @@ __global__ void __launch_bounds__(512) k_tab_fwd(const __grid_constant__ TabPara
 // ------------------------------------------------------------------------------------------
 // first-order backward
 // ------------------------------------------------------------------------------------------
-// v[0..15] per lane -> lane l returns the warp-wide sum of v[(l >> 1) & 15].
-template <typename FP>
-__device__ __forceinline__ FP reduce_scatter16(FP (&v)[16], int lane) {
-#pragma unroll
-  for (int s = 16, n = 16; s >= 2; s >>= 1, n >>= 1) {
-    const bool up = (lane & s) != 0;
-#pragma unroll
-    for (int t = 0; t < n / 2; ++t) {
-      const FP send = up ? v[t] : v[t + n / 2];
-      const FP keep = up ? v[t + n / 2] : v[t];
-      v[t] = keep + __shfl_xor_sync(kFull, send, s);
-    }
-  }
-  return v[0] + __shfl_xor_sync(kFull, v[0], 1);
-}
 // v[0..3] per lane -> lane l returns the warp-wide sum of v[l >> 3].
 template <typename FP>
 __device__ __forceinline__ FP reduce_scatter4(FP (&v)[4], int lane) {

@@ -66,5 +66,21 @@ nn = min(nloc, 1 << 17)
 gd = torch.randn(nn, M * cfg.axis_neuron, dtype=dtype, device=dev)
 out = torch.empty_like(xyz)
 timeit("se_a_descriptor_grad", lambda: ops.se_a_descriptor_grad(gd, xyz, cfg.axis_neuron, 1.0 / nnei, rows=perm32[:nn], out=out))
-timeit("energy_and_dy (fitting)", lambda: model.energy_and_dy(xyz, st.type_perm, st.type_ranges))
+timeit("energy_and_dy (plain GEMMs)", lambda: model.energy_and_dy(xyz, st.type_perm, st.type_ranges))
+if model.use_split:
+    inv = 1.0 / nnei
+    timeit("tabulate_sections_desc(split)", lambda: ops.tabulate_sections_desc(
+        model.tables, model.infos, em, cfg.sec, M, cfg.axis_neuron, inv, desc_row=st.type_inv, mode=2,
+        nslice=model.nslice, pad_rows=32), flops_per_atom=18 * (nreal + 2) * M)
+    _, desc, rexp = ops.tabulate_sections_desc(model.tables, model.infos, em, cfg.sec, M, cfg.axis_neuron, inv,
+                                               desc_row=st.type_inv, mode=2, nslice=model.nslice, pad_rows=32)
+    timeit("fit fwd+bwd split, 1 chunk", lambda: model.fit[0].forward_backward_split(
+        desc, None if rexp is None else rexp[:nn], nn))
+    dd = ops.se_a_descriptor(xyz, cfg.axis_neuron, inv, rows=perm32[:nn])
+    timeit("fit fwd+bwd plain, 1 chunk", lambda: model.fit[0].forward_backward(dd))
+    timeit("energy_and_dy_split", lambda: model.energy_and_dy_split(xyz, desc, rexp, st.type_perm, st.type_ranges))
+    e0, _, dy0 = model.energy_and_dy(xyz, st.type_perm, st.type_ranges)
+    e1, _, dy1 = model.energy_and_dy_split(xyz, desc, rexp, st.type_perm, st.type_ranges)
+    print(f"split vs plain: dE/E = {abs((e1 - e0) / e0).item():.3e}  max|d dy|/max|dy| = "
+          f"{((dy1 - dy0).abs().max() / dy0.abs().max()).item():.3e}", flush=True)
 timeit("build_neighbors", lambda: dp.build_neighbors(c, t, box))
