@@ -29,6 +29,8 @@
 // Not a port of source/lib/src/gpu/tabulate.cu (one thread per channel, stride-6 scalar loads, all
 // coefficients from global memory, serial padding search by thread 0).
 #include <cmath>
+#include <cstdlib>
+#include <type_traits>
 
 #include "common.cuh"
 
@@ -779,6 +781,258 @@ __global__ void __launch_bounds__(384) k_tab_grad(const __grid_constant__ TabPar
 }
 
 // ------------------------------------------------------------------------------------------
+// FP64 tensor-core variants (plain se_a, M <= 128): the env-mat contraction is a small dense
+// product per atom -- forward  out[4 x M] = E^T[4 x n] . G[n x M],  backward
+// dy_dem[n x 4] = G[n x M] . dy^T[M x 4]  (and the same with G' for the em_x gradient) -- so it runs
+// on the FP64 tensor cores (DMMA m8n8k4) while the FMA pipe only evaluates the quintic: 5 (forward)
+// / 9 (backward) FMAs per (neighbour, channel) instead of 9 / 19 on the SIMT path above, every lane
+// owns a live (neighbour, channel) pair (no 100-of-128 channel padding), and the backward needs no
+// cross-lane reduction at all.  Fragment ownership of mma.m8n8k4.f64: A[r][k] at lane 4r+k,
+// B[k][c] at lane 4c+k, C[r][2k..2k+1] at lane 4r+k.
+//   forward : A = E^T (rows = the 4 env-mat components, rows 4..7 zero), k = 4 neighbours,
+//             B = G (k = neighbour, column = channel 8t + lane/4), one C tile per 8 channels.
+//   backward: A = G / G' (row = neighbour 8s + lane/4, k = channel 4t + lane%4),
+//             B = dy^T (k = channel, columns 0..3 = component, 4..7 zero), C = [8 neighbours x 4].
+// Coefficients are not cached in registers here (every lane evaluates a different row): they come
+// from the shared-memory hot window (lanes of one row read one contiguous segment, equal rows are
+// broadcast) or, outside the window, from L1/L2.
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double b) {
+  asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+      : "+d"(c0), "+d"(c1)
+      : "d"(a), "d"(b));
+}
+
+template <int NT, bool DESC>
+__global__ void __launch_bounds__(512) k_tab_fwd_mma(const __grid_constant__ TabParams<double> p) {
+  using FP = double;
+  const int lane = threadIdx.x & 31;
+  const int warp = threadIdx.x >> 5;
+  const int nw = blockDim.x >> 5;
+  FP* hot = reinterpret_cast<FP*>(tab_smem);
+  Rec<FP>* rec = reinterpret_cast<Rec<FP>*>(hot + p.hot_elems) + warp * 32;
+  const int r0 = hot_window_start(p);
+  preload_hot(hot, p, r0);
+  __syncthreads();
+  const int M = p.M;
+  const int q = lane >> 2, kk = lane & 3;
+  const unsigned qb = (unsigned)M * 16u;  // bytes of one coefficient-pair block
+  const unsigned off_q = (unsigned)q * 16u;
+  const unsigned off_last = (unsigned)((8 * (NT - 1) + q < M) ? 8 * (NT - 1) + q : M - 1) * 16u;
+
+  const long long stride = (long long)gridDim.x * nw;
+  long long i = (long long)blockIdx.x * nw + warp;
+  int j0 = 0;
+  Pre<FP, false> pre;
+  load_pre(pre, p, i, 0, lane);
+  FP last = i < p.nloc ? p.em_x[i * p.ldx_i + (long long)(p.nnei - 1) * p.ldx_j] : (FP)0.;
+  FP acc[NT][2];
+  auto seed = [&](long long ii) {
+#pragma unroll
+    for (int t = 0; t < NT; ++t) {
+      const int ch = 8 * t + 2 * kk;
+      const bool rd = p.accumulate && ii < p.nloc && q < 4;
+      acc[t][0] = (rd && ch < M) ? p.out[(ii * 4 + q) * (long long)M + ch] : (FP)0.;
+      acc[t][1] = (rd && ch + 1 < M) ? p.out[(ii * 4 + q) * (long long)M + ch + 1] : (FP)0.;
+    }
+  };
+  seed(i);
+
+  while (i < p.nloc) {
+    bool done, any_delta;
+    const int nproc = stage_chunk<FP, false>(p, j0, last, pre, rec, nullptr, lane, done, any_delta);
+    const bool atom_end = done || j0 + 32 >= p.nnei;
+    const long long ni = atom_end ? i + stride : i;
+    const int nj0 = atom_end ? 0 : j0 + 32;
+    load_pre(pre, p, ni, nj0, lane);
+    FP nlast = last;
+    if (atom_end && ni < p.nloc) nlast = p.em_x[ni * p.ldx_i + (long long)(p.nnei - 1) * p.ldx_j];
+
+    for (int s = 0; s < nproc; s += 4) {
+      const int nb = s + kk;
+      const bool live = nb < nproc;
+      const Rec<FP>& r = rec[live ? nb : nproc - 1];
+      const FP xx = r.xx;
+      const FP dl = r.delta;
+      const FP eq = r.e[q & 3];
+      const FP af = (live && q < 4) ? eq : (FP)0.;
+      const unsigned rel = (unsigned)(r.idx - r0);
+      const bool inwin = rel < (unsigned)p.H;
+#define DPB_FWD_TILES(BASE)                                                                   \
+  _Pragma("unroll") for (int t = 0; t < NT; ++t) {                                            \
+    const unsigned off = (t == NT - 1) ? off_last : (unsigned)t * 128u + off_q;               \
+    const double2 u = *reinterpret_cast<const double2*>((BASE) + off);                        \
+    const double2 v = *reinterpret_cast<const double2*>((BASE) + qb + off);                   \
+    const double2 w = *reinterpret_cast<const double2*>((BASE) + 2u * qb + off);              \
+    FP g = u.x + (u.y + (v.x + (v.y + (w.x + w.y * xx) * xx) * xx) * xx) * xx;                \
+    if (any_delta && dl != (FP)0.)                                                            \
+      g += (u.y + ((FP)2. * v.x + ((FP)3. * v.y + ((FP)4. * w.x + (FP)5. * w.y * xx) * xx) * xx) * xx) * dl; \
+    dmma884(acc[t][0], acc[t][1], af, g);                                                     \
+  }
+      if (__all_sync(kFull, inwin)) {
+        const char* b = reinterpret_cast<const char*>(hot) + rel * (3u * qb);
+        DPB_FWD_TILES(b)
+      } else {
+        const char* b = inwin ? reinterpret_cast<const char*>(hot) + rel * (3u * qb)
+                              : reinterpret_cast<const char*>(p.T) + (long long)r.idx * (3u * qb);
+        DPB_FWD_TILES(b)
+      }
+#undef DPB_FWD_TILES
+    }
+    if (atom_end) {
+      if (q < 4) {
+#pragma unroll
+        for (int t = 0; t < NT; ++t) {
+          const int ch = 8 * t + 2 * kk;
+          if (ch < M) p.out[(i * 4 + q) * (long long)M + ch] = acc[t][0];
+          if (ch + 1 < M) p.out[(i * 4 + q) * (long long)M + ch + 1] = acc[t][1];
+        }
+      }
+      if (DESC) {
+        // the descriptor epilogue wants channel-per-lane ownership: read the row back (L1/L2 hit)
+        __syncwarp();
+        FP a4[4][4];
+#pragma unroll
+        for (int c = 0; c < 4; ++c)
+#pragma unroll
+          for (int m = 0; m < 4; ++m) {
+            const int k = lane + 32 * c;
+            a4[m][c] = k < M ? __ldcg(p.out + (i * 4 + m) * (long long)M + k) : (FP)0.;
+          }
+        desc_epilogue<FP, 4>(p, a4, i, lane, reinterpret_cast<FP*>(rec));
+      }
+      seed(ni);
+    }
+    i = ni;
+    j0 = nj0;
+    last = nlast;
+  }
+}
+
+template <int KT>
+__global__ void __launch_bounds__(384) k_tab_grad_mma(const __grid_constant__ TabParams<double> p) {
+  using FP = double;
+  const int lane = threadIdx.x & 31;
+  const int warp = threadIdx.x >> 5;
+  const int nw = blockDim.x >> 5;
+  FP* hot = reinterpret_cast<FP*>(tab_smem);
+  Rec<FP>* rec = reinterpret_cast<Rec<FP>*>(hot + p.hot_elems) + warp * 32;
+  const int M = p.M;
+  const int r0 = hot_window_start(p);
+  preload_hot(hot, p, r0);
+  __syncthreads();
+  const bool fuse_x = p.dy_dem_x == nullptr;
+  const int q = lane >> 2, kk = lane & 3;
+  const unsigned qb = (unsigned)M * 16u;
+  const unsigned off_k = (unsigned)kk * 16u;
+  const unsigned off_last = (unsigned)((4 * (KT - 1) + kk < M) ? 4 * (KT - 1) + kk : M - 1) * 16u;
+
+  const long long stride = (long long)gridDim.x * nw;
+  long long i = (long long)blockIdx.x * nw + warp;
+  int j0 = 0;
+  Pre<FP, false> pre;
+  load_pre(pre, p, i, 0, lane);
+  FP last = i < p.nloc ? p.em_x[i * p.ldx_i + (long long)(p.nnei - 1) * p.ldx_j] : (FP)0.;
+  FP bf[KT];  // B fragments: dy[m = q][channel 4t + kk] (q < 4), constant per atom
+
+  while (i < p.nloc) {
+    if (j0 == 0) {
+      const FP* __restrict__ dyi = p.dy + i * 4 * (long long)M;
+#pragma unroll
+      for (int t = 0; t < KT; ++t) {
+        const int ch = 4 * t + kk;
+        bf[t] = (q < 4 && ch < M) ? dyi[(long long)q * M + ch] : (FP)0.;
+      }
+    }
+    bool done, any_delta;
+    const int nproc = stage_chunk<FP, false>(p, j0, last, pre, rec, nullptr, lane, done, any_delta);
+    const bool atom_end = done || j0 + 32 >= p.nnei;
+    const long long ni = atom_end ? i + stride : i;
+    const int nj0 = atom_end ? 0 : j0 + 32;
+    load_pre(pre, p, ni, nj0, lane);
+    FP nlast = last;
+    if (atom_end && ni < p.nloc) nlast = p.em_x[ni * p.ldx_i + (long long)(p.nnei - 1) * p.ldx_j];
+
+    FP* __restrict__ gem = p.dy_dem + i * p.ldem_i;
+    for (int s = 0; s < nproc; s += 8) {
+      const int nb = s + q;
+      const bool live = nb < nproc;
+      const Rec<FP>& r = rec[live ? nb : nproc - 1];
+      const FP xx = r.xx;
+      const FP dl = r.delta;
+      const unsigned rel = (unsigned)(r.idx - r0);
+      const bool inwin = rel < (unsigned)p.H;
+      FP c1a = 0., c1b = 0., c2a = 0., c2b = 0.;
+#define DPB_GRAD_STEPS(BASE)                                                                  \
+  _Pragma("unroll") for (int t = 0; t < KT; ++t) {                                            \
+    const unsigned off = (t == KT - 1) ? off_last : (unsigned)t * 64u + off_k;                \
+    const double2 u = *reinterpret_cast<const double2*>((BASE) + off);                        \
+    const double2 v = *reinterpret_cast<const double2*>((BASE) + qb + off);                   \
+    const double2 w = *reinterpret_cast<const double2*>((BASE) + 2u * qb + off);              \
+    const FP b4 = w.x + w.y * xx;                                                             \
+    const FP b3 = v.y + b4 * xx;                                                              \
+    const FP b2 = v.x + b3 * xx;                                                              \
+    const FP b1 = u.y + b2 * xx;                                                              \
+    FP g = u.x + b1 * xx;                                                                     \
+    const FP d4 = b4 + w.y * xx;                                                              \
+    const FP d3 = b3 + d4 * xx;                                                               \
+    const FP d2 = b2 + d3 * xx;                                                               \
+    const FP gd = b1 + d2 * xx;                                                               \
+    if (any_delta) g += gd * dl;                                                              \
+    dmma884(c1a, c1b, g, bf[t]);                                                              \
+    dmma884(c2a, c2b, gd, bf[t]);                                                             \
+  }
+      if (__all_sync(kFull, inwin)) {
+        const char* b = reinterpret_cast<const char*>(hot) + rel * (3u * qb);
+        DPB_GRAD_STEPS(b)
+      } else {
+        const char* b = inwin ? reinterpret_cast<const char*>(hot) + rel * (3u * qb)
+                              : reinterpret_cast<const char*>(p.T) + (long long)r.idx * (3u * qb);
+        DPB_GRAD_STEPS(b)
+      }
+#undef DPB_GRAD_STEPS
+      // C row = neighbour q, columns 2kk, 2kk+1 (components; valid for kk < 2)
+      const FP ea = r.e[(2 * kk) & 3], eb = r.e[(2 * kk + 1) & 3];  // pre-multiplied by the fold multiplicity
+      FP part = kk < 2 ? ea * c2a + eb * c2b : (FP)0.;
+      part += __shfl_xor_sync(kFull, part, 1);
+      if (live && kk < 2) {
+        const FP mult = (FP)r.mult;
+        const int j = j0 + nb;
+        FP v0 = c1a * mult;
+        const FP v1 = c1b * mult;
+        if (kk == 0) {
+          if (fuse_x)
+            v0 += part;
+          else
+            p.dy_dem_x[i * p.ldx_i + (long long)j * p.ldx_j] = part;
+        }
+        gem[(long long)j * 4 + 2 * kk] = v0;
+        gem[(long long)j * 4 + 2 * kk + 1] = v1;
+      }
+    }
+    if (atom_end) {
+      const int jend = j0 + nproc;
+      for (int j = jend + lane; j < p.nnei; j += 32) {
+        if (!fuse_x) p.dy_dem_x[i * p.ldx_i + (long long)j * p.ldx_j] = (FP)0.;
+#pragma unroll
+        for (int m = 0; m < 4; ++m) gem[(long long)j * 4 + m] = (FP)0.;
+      }
+    }
+    i = ni;
+    j0 = nj0;
+    last = nlast;
+  }
+}
+
+inline bool use_mma_path() {
+  static const bool on = [] {
+    const char* e = getenv("DPB200_TAB_MMA");
+    return !(e && e[0] == '0');
+  }();
+  return on;
+}
+
+// ------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------
 constexpr size_t kSmemBudget = 225 * 1024;
@@ -933,6 +1187,34 @@ int launch_fwd(FP* out, const FP* table, const FP* info, const FP* em_x, long lo
   const long long cap = sm_count() / nblk > 0 ? sm_count() / nblk : 1;
   dim3 grid((unsigned)(want < cap ? want : cap), (unsigned)nblk);
   cudaError_t e1 = cudaSuccess;
+  bool launched = false;
+  if constexpr (std::is_same<FP, double>::value && !GG) {
+    const int nt = (M + 7) / 8;
+    if (!tw && use_mma_path() && (nt == 4 || nt == 8 || nt == 10 || nt == 13 || nt == 16)) {
+      dim3 g1((unsigned)(want < sm_count() ? want : sm_count()));
+#define DPB_LAUNCH_FWD_MMA(NT)                                                                  \
+  do {                                                                                          \
+    if (da) {                                                                                   \
+      auto kern = k_tab_fwd_mma<NT, true>;                                                      \
+      e1 = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);  \
+      if (e1 == cudaSuccess) kern<<<g1, nw * 32, smem, st>>>(p);                                \
+    } else {                                                                                    \
+      auto kern = k_tab_fwd_mma<NT, false>;                                                     \
+      e1 = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);  \
+      if (e1 == cudaSuccess) kern<<<g1, nw * 32, smem, st>>>(p);                                \
+    }                                                                                           \
+  } while (0)
+      switch (nt) {
+        case 4: DPB_LAUNCH_FWD_MMA(4); break;
+        case 8: DPB_LAUNCH_FWD_MMA(8); break;
+        case 10: DPB_LAUNCH_FWD_MMA(10); break;
+        case 13: DPB_LAUNCH_FWD_MMA(13); break;
+        default: DPB_LAUNCH_FWD_MMA(16); break;
+      }
+#undef DPB_LAUNCH_FWD_MMA
+      launched = true;
+    }
+  }
 #define DPB_LAUNCH_FWD(NC)                                                                      \
   do {                                                                                          \
     if (da) {                                                                                   \
@@ -949,7 +1231,8 @@ int launch_fwd(FP* out, const FP* table, const FP* info, const FP* em_x, long lo
       if (e1 == cudaSuccess) kern<<<grid, nw * 32, smem, st>>>(p);                              \
     }                                                                                           \
   } while (0)
-  if (nc == 1)
+  if (launched) {
+  } else if (nc == 1)
     DPB_LAUNCH_FWD(1);
   else if (nc == 2)
     DPB_LAUNCH_FWD(2);
@@ -995,6 +1278,27 @@ int launch_grad(FP* dy_dem_x, FP* dy_dem, FP* dy_dtwo, const FP* table, const FP
   const long long cap = sm_count();
   const int grid = (int)(want < cap ? want : cap);
   cudaError_t e1 = cudaSuccess;
+  bool launched = false;
+  if constexpr (std::is_same<FP, double>::value) {
+    const int kt = (M + 3) / 4;
+    if (!tw && use_mma_path() && (kt == 8 || kt == 16 || kt == 20 || kt == 25 || kt == 32)) {
+#define DPB_LAUNCH_GRAD_MMA(KT)                                                                 \
+  do {                                                                                          \
+    auto kern = k_tab_grad_mma<KT>;                                                             \
+    e1 = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);    \
+    if (e1 == cudaSuccess) kern<<<grid, nw * 32, smem, st>>>(p);                                \
+  } while (0)
+      switch (kt) {
+        case 8: DPB_LAUNCH_GRAD_MMA(8); break;
+        case 16: DPB_LAUNCH_GRAD_MMA(16); break;
+        case 20: DPB_LAUNCH_GRAD_MMA(20); break;
+        case 25: DPB_LAUNCH_GRAD_MMA(25); break;
+        default: DPB_LAUNCH_GRAD_MMA(32); break;
+      }
+#undef DPB_LAUNCH_GRAD_MMA
+      launched = true;
+    }
+  }
 #define DPB_LAUNCH_GRAD(NC)                                                                     \
   do {                                                                                          \
     if (tw) {                                                                                   \
@@ -1007,7 +1311,8 @@ int launch_grad(FP* dy_dem_x, FP* dy_dem, FP* dy_dtwo, const FP* table, const FP
       if (e1 == cudaSuccess) kern<<<grid, nw * 32, smem, st>>>(p);                              \
     }                                                                                           \
   } while (0)
-  if (M <= 32)
+  if (launched) {
+  } else if (M <= 32)
     DPB_LAUNCH_GRAD(1);
   else if (M <= 64)
     DPB_LAUNCH_GRAD(2);

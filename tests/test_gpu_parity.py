@@ -229,7 +229,8 @@ def _random_tab_case(rng, dtype, nloc, nnei, M, nreal_max=None, unsorted=False):
 
 
 @pytest.mark.parametrize("dtype", [np.float64, np.float32])
-@pytest.mark.parametrize("nnei,M", [(46, 100), (92, 100), (7, 8), (33, 32), (64, 40), (20, 160), (138, 128)])
+@pytest.mark.parametrize("nnei,M", [(46, 100), (92, 100), (7, 8), (33, 32), (64, 40), (20, 160), (138, 128), (50, 80), (41, 64), (30, 97), (29, 26),
+                                    (9, 104)])
 @pytest.mark.parametrize("is_sorted", [True, False])
 def test_tabulate_vs_oracle(ops, port, dtype, nnei, M, is_sorted):
     rng = np.random.default_rng(nnei * 1000 + M)
@@ -645,7 +646,7 @@ def test_split_i8_gemm_matches_fp64(ops):
 
     torch.manual_seed(5)
     n, K, Nn, ns = 300, 1600, 240, 7
-    x = (torch.randn(n, K, dtype=torch.float64, device=DEV) * torch.logspace(-6, 1, n, dtype=torch.float64, device=DEV)[:, None])
+    x = (torch.randn(n, K, dtype=torch.float64, device=DEV) * torch.logspace(-6, 0, n, dtype=torch.float64, device=DEV)[:, None])
     w = torch.randn(K, Nn, dtype=torch.float64) * 0.03
     xs, ex = ops.split_i8_rows(x, ns)
     sl, ce = split_i8_cols(w, ns)
@@ -661,8 +662,8 @@ def test_split_i8_gemm_matches_fp64(ops):
     b = torch.randn(Nn, dtype=torch.float64, device=DEV)
     idt = torch.rand(Nn, dtype=torch.float64, device=DEV)
     a, y = ops.split_i8_combine(acc, ex, ce.to(DEV), bias=b, idt=idt)
-    assert torch.allclose(a, torch.tanh(want + b), rtol=0, atol=1e-12)
-    assert torch.allclose(y, torch.tanh(want + b) * idt, rtol=0, atol=1e-12)
+    assert torch.allclose(a, torch.tanh(want + b), rtol=0, atol=1e-11)
+    assert torch.allclose(y, torch.tanh(want + b) * idt, rtol=0, atol=1e-11)
 
 
 @pytest.mark.parametrize("dtype", [torch.float64, torch.float32])
