@@ -56,7 +56,8 @@ struct TabParams {
   int nloc, nnei, M, is_sorted, accumulate, vec_ok;
   int Mc;  // channels per CTA slice (forward: gridDim.y slices; backward: Mc == M)
   int H;   // hot rows kept in shared memory
-  int hot_elems;  // H*Mc*6 rounded up to a 16-byte boundary (start of the per-warp records)
+  int hot_elems;  // H*Mc*6 (+ padding) rounded up to a 16-byte boundary (start of the per-warp records)
+  int hot_pad;    // bytes of padding after every hot row (tensor-core forward: 32, see k_tab_fwd_mma)
   // forward / second order
   FP* out;  // [nloc][4][M]
   const FP* dz_x;
@@ -211,7 +212,16 @@ __device__ __forceinline__ void preload_hot(FP* __restrict__ hot, const TabParam
   const long long n = (long long)p.H * 3 * p.M;
   const P2* __restrict__ src = reinterpret_cast<const P2*>(p.T) + (long long)r0 * 3 * p.M;
   P2* dst = reinterpret_cast<P2*>(hot);
-  for (long long e = threadIdx.x; e < n; e += blockDim.x) dst[e] = __ldg(src + e);
+  if (p.hot_pad == 0) {
+    for (long long e = threadIdx.x; e < n; e += blockDim.x) dst[e] = __ldg(src + e);
+  } else {
+    const int per_row = 3 * p.M;
+    const int stride = per_row + p.hot_pad / (int)sizeof(P2);
+    for (long long e = threadIdx.x; e < n; e += blockDim.x) {
+      const int r = (int)(e / per_row);
+      dst[(long long)r * stride + (e - (long long)r * per_row)] = __ldg(src + e);
+    }
+  }
 }
 
 // One lane's share of a 32-neighbour chunk, fetched one work item ahead of its use so that the
@@ -817,6 +827,7 @@ __global__ void __launch_bounds__(512) k_tab_fwd_mma(const __grid_constant__ Tab
   const int M = p.M;
   const int q = lane >> 2, kk = lane & 3;
   const unsigned qb = (unsigned)M * 16u;  // bytes of one coefficient-pair block
+  const unsigned hstride = 3u * qb + (unsigned)p.hot_pad;  // padded: the 4 rows of a step hit 4 different bank groups
   const unsigned off_q = (unsigned)q * 16u;
   const unsigned off_last = (unsigned)((8 * (NT - 1) + q < M) ? 8 * (NT - 1) + q : M - 1) * 16u;
 
@@ -870,10 +881,13 @@ __global__ void __launch_bounds__(512) k_tab_fwd_mma(const __grid_constant__ Tab
     dmma884(acc[t][0], acc[t][1], af, g);                                                     \
   }
       if (__all_sync(kFull, inwin)) {
-        const char* b = reinterpret_cast<const char*>(hot) + rel * (3u * qb);
+        const char* b = reinterpret_cast<const char*>(hot) + rel * hstride;
+        DPB_FWD_TILES(b)
+      } else if (!__any_sync(kFull, inwin)) {
+        const char* __restrict__ b = reinterpret_cast<const char*>(p.T) + (long long)r.idx * (3u * qb);
         DPB_FWD_TILES(b)
       } else {
-        const char* b = inwin ? reinterpret_cast<const char*>(hot) + rel * (3u * qb)
+        const char* b = inwin ? reinterpret_cast<const char*>(hot) + rel * hstride
                               : reinterpret_cast<const char*>(p.T) + (long long)r.idx * (3u * qb);
         DPB_FWD_TILES(b)
       }
@@ -909,8 +923,11 @@ __global__ void __launch_bounds__(512) k_tab_fwd_mma(const __grid_constant__ Tab
   }
 }
 
-template <int KT>
-__global__ void __launch_bounds__(384) k_tab_grad_mma(const __grid_constant__ TabParams<double> p) {
+// BSM: the B fragments (dy of the current atom) live in a per-warp shared-memory tile instead of 2*KT
+// registers, which lets MAXT / 32 warps (instead of 12) share an SM: the kernel is latency-bound on the
+// coefficient fetches of rows outside the hot window, so warps in flight are what it needs.
+template <int KT, bool BSM, int MAXT>
+__global__ void __launch_bounds__(MAXT) k_tab_grad_mma(const __grid_constant__ TabParams<double> p) {
   using FP = double;
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
@@ -918,6 +935,7 @@ __global__ void __launch_bounds__(384) k_tab_grad_mma(const __grid_constant__ Ta
   FP* hot = reinterpret_cast<FP*>(tab_smem);
   Rec<FP>* rec = reinterpret_cast<Rec<FP>*>(hot + p.hot_elems) + warp * 32;
   const int M = p.M;
+  FP* dyt = reinterpret_cast<FP*>(reinterpret_cast<Rec<FP>*>(hot + p.hot_elems) + nw * 32) + (BSM ? warp * 4 * M : 0);
   const int r0 = hot_window_start(p);
   preload_hot(hot, p, r0);
   __syncthreads();
@@ -933,15 +951,22 @@ __global__ void __launch_bounds__(384) k_tab_grad_mma(const __grid_constant__ Ta
   Pre<FP, false> pre;
   load_pre(pre, p, i, 0, lane);
   FP last = i < p.nloc ? p.em_x[i * p.ldx_i + (long long)(p.nnei - 1) * p.ldx_j] : (FP)0.;
-  FP bf[KT];  // B fragments: dy[m = q][channel 4t + kk] (q < 4), constant per atom
+  FP bf[BSM ? 1 : KT];  // B fragments: dy[m = q][channel 4t + kk] (q < 4), constant per atom
+  const FP* bsrc = dyt + (q & 3) * M + kk;
 
   while (i < p.nloc) {
     if (j0 == 0) {
       const FP* __restrict__ dyi = p.dy + i * 4 * (long long)M;
+      if (BSM) {
+        __syncwarp();
+        for (int e = lane; e < 4 * M; e += 32) dyt[e] = dyi[e];
+        __syncwarp();
+      } else {
 #pragma unroll
-      for (int t = 0; t < KT; ++t) {
-        const int ch = 4 * t + kk;
-        bf[t] = (q < 4 && ch < M) ? dyi[(long long)q * M + ch] : (FP)0.;
+        for (int t = 0; t < KT; ++t) {
+          const int ch = 4 * t + kk;
+          bf[BSM ? 0 : t] = (q < 4 && ch < M) ? dyi[(long long)q * M + ch] : (FP)0.;
+        }
       }
     }
     bool done, any_delta;
@@ -979,11 +1004,15 @@ __global__ void __launch_bounds__(384) k_tab_grad_mma(const __grid_constant__ Ta
     const FP d2 = b2 + d3 * xx;                                                               \
     const FP gd = b1 + d2 * xx;                                                               \
     if (any_delta) g += gd * dl;                                                              \
-    dmma884(c1a, c1b, g, bf[t]);                                                              \
-    dmma884(c2a, c2b, gd, bf[t]);                                                             \
+    const FP bt = BSM ? ((q < 4 && 4 * t + kk < M) ? bsrc[4 * t] : (FP)0.) : bf[BSM ? 0 : t]; \
+    dmma884(c1a, c1b, g, bt);                                                                 \
+    dmma884(c2a, c2b, gd, bt);                                                                \
   }
       if (__all_sync(kFull, inwin)) {
         const char* b = reinterpret_cast<const char*>(hot) + rel * (3u * qb);
+        DPB_GRAD_STEPS(b)
+      } else if (!__any_sync(kFull, inwin)) {
+        const char* __restrict__ b = reinterpret_cast<const char*>(p.T) + (long long)r.idx * (3u * qb);
         DPB_GRAD_STEPS(b)
       } else {
         const char* b = inwin ? reinterpret_cast<const char*>(hot) + rel * (3u * qb)
@@ -1022,6 +1051,30 @@ __global__ void __launch_bounds__(384) k_tab_grad_mma(const __grid_constant__ Ta
     j0 = nj0;
     last = nlast;
   }
+}
+
+inline int grad_variant() {
+  static const int v = [] {
+    const char* e = getenv("DPB200_GRAD_VARIANT");
+    return e ? atoi(e) : 1;
+  }();
+  return v;
+}
+
+inline int hot_rows_cap() {
+  static const int v = [] {
+    const char* e = getenv("DPB200_TAB_HOT_ROWS");
+    return e ? atoi(e) : (1 << 30);
+  }();
+  return v;
+}
+
+inline bool use_mma_fwd() {
+  static const bool on = [] {
+    const char* e = getenv("DPB200_TAB_MMA_FWD");
+    return e && e[0] == '1';
+  }();
+  return on;
 }
 
 inline bool use_mma_path() {
@@ -1091,6 +1144,7 @@ int hot_rows(int nrow, int M, size_t other_bytes) {
   const size_t row_bytes = (size_t)M * 6 * sizeof(FP);
   if (other_bytes + row_bytes > kSmemBudget) return 0;
   long long h = (long long)((kSmemBudget - other_bytes) / row_bytes);
+  if (h > hot_rows_cap()) h = hot_rows_cap();
   return (int)(h < nrow ? h : nrow);
 }
 
@@ -1190,8 +1244,20 @@ int launch_fwd(FP* out, const FP* table, const FP* info, const FP* em_x, long lo
   bool launched = false;
   if constexpr (std::is_same<FP, double>::value && !GG) {
     const int nt = (M + 7) / 8;
-    if (!tw && use_mma_path() && (nt == 4 || nt == 8 || nt == 10 || nt == 13 || nt == 16)) {
+    // Measured on B200 (gpurun_out/tab_variants.log): the forward gathers 4 different rows per quarter-warp and
+    // ends up L1/shared-bound (9.3 ms vs 5.7 ms for the SIMT kernel at 332k atoms), so it is opt-in; the backward
+    // (2 rows per quarter-warp, no cross-lane reduction) wins 11.5 -> 8.3 ms and is the default.
+    if (!tw && use_mma_fwd() && (nt == 4 || nt == 8 || nt == 10 || nt == 13 || nt == 16)) {
       dim3 g1((unsigned)(want < sm_count() ? want : sm_count()));
+      {  // padded hot rows (bank-conflict-free 4-row gathers)
+        p.hot_pad = 32;
+        const size_t row_bytes = (size_t)M * 6 * sizeof(FP) + 32;
+        long long h = rec_bytes + row_bytes > kSmemBudget ? 0 : (long long)((kSmemBudget - rec_bytes) / row_bytes);
+        if (h > hot_rows_cap()) h = hot_rows_cap();
+        p.H = (int)(h < p.nrow ? h : p.nrow);
+        p.hot_elems = (int)(((size_t)p.H * row_bytes + 15) / 16 * 16 / sizeof(FP));
+      }
+      const size_t smem = (size_t)p.hot_elems * sizeof(FP) + rec_bytes;
 #define DPB_LAUNCH_FWD_MMA(NT)                                                                  \
   do {                                                                                          \
     if (da) {                                                                                   \
@@ -1282,11 +1348,31 @@ int launch_grad(FP* dy_dem_x, FP* dy_dem, FP* dy_dtwo, const FP* table, const FP
   if constexpr (std::is_same<FP, double>::value) {
     const int kt = (M + 3) / 4;
     if (!tw && use_mma_path() && (kt == 8 || kt == 16 || kt == 20 || kt == 25 || kt == 32)) {
+      // variant 0: B fragments in registers, 12 warps; 1: in shared memory, 16 warps; 2: 24 warps
+      const int variant = grad_variant();
+      const int nwv = variant == 0 ? 12 : (variant == 1 ? 16 : 24);
+      const size_t extra = variant == 0 ? 0 : (size_t)nwv * 4 * M * sizeof(FP);
+      const size_t recv = (size_t)nwv * 32 * sizeof(Rec<FP>);
+      p.H = hot_rows<FP>(p.nrow, M, recv + extra);
+      p.hot_elems = hot_elems_aligned<FP>(p.H, M);
+      const size_t smemv = (size_t)p.hot_elems * sizeof(FP) + recv + extra;
+      long long wantv = ((long long)nloc + nwv - 1) / nwv;
+      const int gridv = (int)(wantv < cap ? wantv : cap);
 #define DPB_LAUNCH_GRAD_MMA(KT)                                                                 \
   do {                                                                                          \
-    auto kern = k_tab_grad_mma<KT>;                                                             \
-    e1 = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);    \
-    if (e1 == cudaSuccess) kern<<<grid, nw * 32, smem, st>>>(p);                                \
+    if (variant == 0) {                                                                         \
+      auto kern = k_tab_grad_mma<KT, false, 384>;                                               \
+      e1 = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemv); \
+      if (e1 == cudaSuccess) kern<<<gridv, nwv * 32, smemv, st>>>(p);                           \
+    } else if (variant == 1) {                                                                  \
+      auto kern = k_tab_grad_mma<KT, true, 512>;                                                \
+      e1 = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemv); \
+      if (e1 == cudaSuccess) kern<<<gridv, nwv * 32, smemv, st>>>(p);                           \
+    } else {                                                                                    \
+      auto kern = k_tab_grad_mma<KT, true, 768>;                                                \
+      e1 = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemv); \
+      if (e1 == cudaSuccess) kern<<<gridv, nwv * 32, smemv, st>>>(p);                           \
+    }                                                                                           \
   } while (0)
       switch (kt) {
         case 8: DPB_LAUNCH_GRAD_MMA(8); break;

@@ -53,6 +53,8 @@ timeit("tabulate_sections_fwd", lambda: ops.tabulate_sections_fwd(model.tables, 
 dy = torch.randn_like(xyz)
 timeit("tabulate_sections_grad", lambda: ops.tabulate_sections_grad(model.tables, model.infos, em, dy, cfg.sec, M),
        flops_per_atom=36 * (nreal + 2) * M)
+if os.environ.get("OPB_ONLY") == "tab":
+    sys.exit(0)
 nd = ops.tabulate_sections_grad(model.tables, model.infos, em, dy, cfg.sec, M)
 nl2 = nlist.clone(); ops.use_nlist_map(nl2, st.mapping)
 timeit("prod_force_virial_a", lambda: ops.prod_force_virial_a(nd, dv, rij, nl2, nloc, nloc, nnei),
