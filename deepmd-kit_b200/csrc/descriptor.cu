@@ -8,6 +8,8 @@
 // WARP per atom with the operands staged in shared memory and fully coalesced stores.
 #include <cuda_pipeline.h>
 
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace dpb200 {
@@ -231,6 +233,88 @@ __global__ void __launch_bounds__(128, 4) k_desc_bwd_v2(FP* __restrict__ dX, con
   }
 }
 
+// Backward on the FP64 tensor cores (axis == 16, M >= 16; DMMA m8n8k4, fragment ownership: A[r][k] at
+// lane 4r+k, B[k][c] at lane 4c+k, C[r][2k..2k+1] at lane 4r+k).  Per atom, with G = dD[i] ([M][16]) and
+// X = gr ([4][M]):
+//   term 2  T2[4 x 16] = X[4 x M] . G[M x 16]          A = X (rows 4..7 zero), k = 4 channels per step,
+//                                                       B = G rows 4j..4j+3, two 8-column halves
+//   term 1  T1[4 x M]  = X[:, :16][4 x 16] . G^T[16 x M] A = the first four A fragments of term 2,
+//                                                       B = G^T, one C tile per 8 channels
+// and dX = scale^2 (T1 + [channel < 16] T2): the C tiles of term 2 own exactly the lanes of the first two
+// tiles of term 1, so they seed those accumulators.  ~100 DMMA and ~130 8-byte loads per atom, every
+// fetched sector fully used, no shared memory, no shuffles; dD is read once from HBM (term 1 re-reads it
+// from L2).  The SIMT versions above remain for other shapes and for fp32.
+__device__ __forceinline__ void dmma884d(double& c0, double& c1, double a, double b) {
+  asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+      : "+d"(c0), "+d"(c1)
+      : "d"(a), "d"(b));
+}
+
+__global__ void __launch_bounds__(256) k_desc_bwd_mma(double* __restrict__ dX, const double* __restrict__ dD,
+                                                      const double* __restrict__ X, const int* __restrict__ rows,
+                                                      long long nloc, int M, double scale) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int q = lane >> 2, kk = lane & 3;
+  const double s2 = scale * scale;
+  const int KT = (M + 3) >> 2, NT = (M + 7) >> 3;
+  for (long long i = (long long)blockIdx.x * 8 + warp; i < nloc; i += (long long)gridDim.x * 8) {
+    const long long src = rows ? (long long)rows[i] : i;
+    const double* __restrict__ x = X + src * 4 * M + (long long)(q & 3) * M;
+    const double* __restrict__ g = dD + i * (long long)M * 16;
+    double c00 = 0., c01 = 0., c10 = 0., c11 = 0., d00 = 0., d01 = 0., d10 = 0., d11 = 0.;
+    double as[4];
+    // term 2 (first four steps unrolled: their A fragments are term 1's)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int ch = 4 * j + kk;  // < 16 <= M
+      as[j] = q < 4 ? x[ch] : 0.;
+      const double b0 = __ldg(g + ch * 16 + q), b1 = __ldg(g + ch * 16 + q + 8);
+      if (j & 1) {
+        dmma884d(d00, d01, as[j], b0);
+        dmma884d(d10, d11, as[j], b1);
+      } else {
+        dmma884d(c00, c01, as[j], b0);
+        dmma884d(c10, c11, as[j], b1);
+      }
+    }
+#pragma unroll 4
+    for (int j = 4; j < KT; ++j) {
+      const int ch = 4 * j + kk;
+      const bool ok = ch < M;
+      const int chc = ok ? ch : M - 1;
+      const double a = (q < 4 && ok) ? x[chc] : 0.;
+      const double b0 = __ldg(g + chc * 16 + q), b1 = __ldg(g + chc * 16 + q + 8);
+      if (j & 1) {
+        dmma884d(d00, d01, a, b0);
+        dmma884d(d10, d11, a, b1);
+      } else {
+        dmma884d(c00, c01, a, b0);
+        dmma884d(c10, c11, a, b1);
+      }
+    }
+    c00 += d00, c01 += d01, c10 += d10, c11 += d11;
+    // term 1
+    double* __restrict__ o = dX + src * 4 * M + (long long)(q & 3) * M;
+#pragma unroll 2
+    for (int t = 0; t < NT; ++t) {
+      const int row = 8 * t + q;
+      const double* __restrict__ gr = g + (long long)(row < M ? row : M - 1) * 16 + kk;
+      double e0 = t == 0 ? c00 : (t == 1 ? c10 : 0.);
+      double e1 = t == 0 ? c01 : (t == 1 ? c11 : 0.);
+      const double b0 = __ldg(gr), b1 = __ldg(gr + 4), b2 = __ldg(gr + 8), b3 = __ldg(gr + 12);
+      dmma884d(e0, e1, as[0], b0);
+      dmma884d(e0, e1, as[1], b1);
+      dmma884d(e0, e1, as[2], b2);
+      dmma884d(e0, e1, as[3], b3);
+      if (q < 4) {
+        const int ch = 8 * t + 2 * kk;
+        if (ch < M) o[ch] = e0 * s2;
+        if (ch + 1 < M) o[ch + 1] = e1 * s2;
+      }
+    }
+  }
+}
+
 // Fused elementwise passes of the fitting MLP (deepmd/pt/model/network/mlp.py: tanh, resnet_dt, skip):
 //   forward : a = tanh(z) (kept for the backward, overwrites z); y = a*idt (+ h when the widths match)
 //   backward: t = g * idt * (1 - a^2)
@@ -276,6 +360,14 @@ __global__ void k_mlp_act_bwd(FP* __restrict__ t, const FP* __restrict__ g, long
   }
 }
 
+inline bool desc_mma_enabled() {
+  static const bool on = [] {
+    const char* e = getenv("DPB200_DESC_MMA");
+    return !(e && e[0] == '0');
+  }();
+  return on;
+}
+
 template <typename FP>
 int desc_launch(bool bwd, FP* out, const FP* dD, const FP* X, const int* rows, long long nloc, int M, int axis,
                 double scale, cudaStream_t st) {
@@ -287,7 +379,14 @@ int desc_launch(bool bwd, FP* out, const FP* dD, const FP* X, const int* rows, l
   long long want = (nloc + 3) / 4;
   const bool v2 = bwd && M <= 128 && axis % 4 == 0 && axis <= 32 &&
                   (reinterpret_cast<uintptr_t>(dD) & 15) == 0 && ((long long)M * axis * sizeof(FP)) % 16 == 0;
-  if (v2) {
+  if (bwd && sizeof(FP) == 8 && axis == 16 && M >= 16 && desc_mma_enabled()) {
+    want = (nloc + 7) / 8;
+    auto kern = k_desc_bwd_mma;
+    DPB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, 256, 0));
+    long long cap = (long long)sm_count() * (occ < 1 ? 1 : occ);
+    kern<<<(int)(want < cap ? want : cap), 256, 0, st>>>(reinterpret_cast<double*>(out), reinterpret_cast<const double*>(dD),
+                                                         reinterpret_cast<const double*>(X), rows, nloc, M, scale);
+  } else if (v2) {
     want = (nloc + 3) / 4;
     const int nc = M <= 32 ? 1 : (M <= 64 ? 2 : 4);
 #define DPB_DESC_BWD(NC)                                                                                  \

@@ -534,7 +534,7 @@ def test_op_prod_env_mat_a_modes(ops, port, dtype):
 
 # ------------------------------------------------------------------ descriptor contraction ----
 @pytest.mark.parametrize("dtype", [np.float64, np.float32])
-@pytest.mark.parametrize("M,axis", [(100, 16), (8, 4), (33, 33)])
+@pytest.mark.parametrize("M,axis", [(100, 16), (8, 4), (33, 33), (16, 16), (97, 16), (128, 16), (64, 8), (50, 12)])
 def test_descriptor_contraction(ops, dtype, M, axis):
     """dpb200_se_a_descriptor / _grad against the plain torch statement of
     deepmd/pt/model/descriptor/se_a.py:843-850 (and autograd for the backward)."""
