@@ -302,7 +302,7 @@ class SeAModel:
         # Tensor-core fitting net (csrc/fitting.cu): the descriptor leaves the tabulate forward already split
         # (int8 slices in fp64, TF32 head/tail in fp32).  Needs axis == 16 (fp64) / axis % 4 == 0 (fp32),
         # M <= 128 and a first fitting layer without skip connection.
-        self.nslice = 7
+        self.nslice = 6  # 6 + 5*7 = 41 fraction bits per operand: GEMM error ~1e-12 of the row*column scale
         w0 = self.fit[0].layers[0][0]
         ok_axis = cfg.axis_neuron == 16 if dtype == torch.float64 else cfg.axis_neuron % 4 == 0
         self.use_split = bool(ok_axis and self.M <= 128 and cfg.axis_neuron <= 32 and w0.shape[1] not in
