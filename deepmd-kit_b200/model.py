@@ -543,7 +543,8 @@ class DeepPotB200:
             self._pin_out.copy_(out, non_blocking=True)
             torch.cuda.current_stream(dev).synchronize()
             o = self._pin_out.numpy()
-            f_out[f] = o[: nat * 3].reshape(nat, 3)
+            # (torch's CPU copy is multi-threaded; a 37 MB numpy assignment is a single-threaded memcpy)
+            torch.from_numpy(f_out[f].reshape(-1)).copy_(self._pin_out[: nat * 3])
             v_out[f] = o[nat * 3: nat * 3 + 9]
             e_out[f, 0] = o[nat * 3 + 9]
             if atomic:

@@ -136,3 +136,49 @@ def test_model_tables_and_cpu_reference_pipeline(pkg, port):
             c[i, d] += sgn * h
             es.append(pipeline.evaluate(port, m, pipeline.build_lists(port, c, atype, box, 8.0))[0])
         assert abs(-(es[0] - es[1]) / (2 * h) - f0[i, d]) < 1e-7
+
+
+def test_split_i8_cols_reconstructs_the_weights(pkg):
+    """Host-side operand split of the int8 tensor-core GEMM (model.split_i8_cols): signed 7-bit digits,
+    most significant first, per-column exponent; the reconstruction error is below 2^-(6+7(ns-1)) of the
+    column scale and the order-truncated product matches the fp64 product."""
+    from deepmd_kit_b200.model import split_i8_cols
+
+    torch.manual_seed(0)
+    w = torch.randn(64, 24, dtype=torch.float64) * torch.logspace(-3, 2, 24, dtype=torch.float64)[None, :]
+    w[:, 3] = 0.0  # an all-zero column must not produce NaN / overflow
+    for ns in (2, 6, 7):
+        sl, ce = split_i8_cols(w, ns)
+        assert sl.shape == (ns, 64, 24) and sl.dtype == torch.int8 and ce.dtype == torch.int32
+        assert int(sl.abs().max()) <= 64
+        scale = torch.ldexp(torch.ones(24, dtype=torch.float64), ce)
+        rec = sum(sl[s].double() * 2.0 ** (-6 - 7 * s) for s in range(ns)) * scale[None, :]
+        err = ((rec - w).abs() / scale[None, :]).max().item()
+        assert err <= 2.0 ** (-6 - 7 * (ns - 1)) * 0.51, (ns, err)
+    # K-concatenated order sums == exact integer products, recombined
+    ns = 6
+    x = torch.randn(5, 64, dtype=torch.float64)
+    xs, xe = split_i8_cols(x.t().contiguous(), ns)  # per-row scale of x == per-column scale of x^T
+    xs = xs.permute(0, 2, 1).contiguous()  # [ns, 5, 64]
+    sl, ce = split_i8_cols(w, ns)
+    acc = torch.zeros(5, 24, dtype=torch.float64)
+    for d in range(ns):
+        od = sum(xs[i].to(torch.int64) @ sl[d - i].to(torch.int64) for i in range(d + 1))
+        assert int(od.abs().max()) < 2 ** 31  # fits the tensor cores' int32 accumulators
+        acc += od.double() * 2.0 ** (-12 - 7 * d)
+    got = acc * torch.ldexp(torch.ones(5, dtype=torch.float64), xe)[:, None] * torch.ldexp(
+        torch.ones(24, dtype=torch.float64), ce)[None, :]
+    want = x @ w
+    tol = 1e-11 * (x.abs().amax(1, keepdim=True) * w.abs().amax(0, keepdim=True) * 8)
+    assert bool(((got - want).abs() <= tol).all())
+
+
+def test_tf32_split_is_exact_to_2pow22(pkg):
+    from deepmd_kit_b200.model import split_tf32_weight
+
+    torch.manual_seed(1)
+    w = torch.randn(1000, dtype=torch.float32) * torch.logspace(-8, 8, 1000)
+    hi, lo = split_tf32_weight(w)
+    for part in (hi, lo):  # 10 explicit mantissa bits: the low 13 bits of the fp32 pattern are clear
+        assert int((part.view(torch.int32) & 0x1FFF).abs().max()) == 0
+    assert float(((hi.double() + lo.double() - w.double()).abs() / w.double().abs()).max()) <= 2.0 ** -21
