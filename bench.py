@@ -39,6 +39,9 @@ def parse():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--dtype", default="f64", choices=["f64", "f32"])
+    ap.add_argument("--workload", default="water", choices=["water", "copper"],
+                    help="water: BASELINE config 2 (the metric's configuration); copper: config 3 (FCC, sel 512, rcut 8; "
+                         "--ncopy = conventional cells per axis, 100 = 4 M atoms; 1 GPU only, evaluated in atom slabs)")
     ap.add_argument("--ncopy", type=int, default=20, help="replicas of the 192-atom frame per axis and per GPU")
     ap.add_argument("--jitter", type=float, default=0.01)
     ap.add_argument("--cpu-ncopy", type=int, default=4, help="replicas per axis of the bounded CPU sample")
@@ -222,12 +225,22 @@ def run_ours(args):
     L = pkg._lib.lib()
     dtype = torch.float64 if args.dtype == "f64" else torch.float32
     np_dt = np.float64 if args.dtype == "f64" else np.float32
-    cfg = SeAConfig()
+    if args.workload == "copper":
+        from deepmd_kit_b200.model import COPPER_CONFIG
+
+        if world != 1:
+            raise SystemExit("bench.py --workload copper runs on one GPU")
+        cfg = SeAConfig(**COPPER_CONFIG)
+    else:
+        cfg = SeAConfig()
     model = SeAModel(cfg, dtype, dev)
     esz = 8 if args.dtype == "f64" else 4
 
     if world == 1:
-        coord, atype, box = g.water_box(args.ncopy, args.jitter)
+        if args.workload == "copper":
+            coord, atype, box = g.copper_box(args.ncopy, 0.05)
+        else:
+            coord, atype, box = g.water_box(args.ncopy, args.jitter)
         natoms_total = len(atype)
         dp = DeepPotB200(model, skin=2.0, nlist_every=10)
         coord_d = torch.as_tensor(coord.astype(np_dt)).to(dev)
@@ -315,7 +328,7 @@ def run_ours(args):
     kernels, roofline = per_kernel(args, torch, ops, model, dp, step, L, dev, len(atype), esz)
 
     cpu_base = None
-    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+    if rank == 0 and world == 1 and not args.no_cpu_baseline and args.workload == "water":
         try:
             r = cpu_pipeline_timing(args, 10 ** 6, 1, seconds=args.cpu_seconds)
             cpu_base = {"value": r["us_per_step_atom"], "unit": UNIT, "cores": r["cores"], "kind": r["kind"],
@@ -329,8 +342,12 @@ def run_ours(args):
             "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": False, "scaling": "weak",
             "vs_baseline": None, "dtype": args.dtype, "data": "synthetic",
             "config": {
-                "workload": f"se_e2_a compressed water, {natoms_total}-atom box ({args.ncopy}^3 replicas of the 192-atom "
-                            f"frame per GPU, Gaussian jitter {args.jitter} A), {args.dtype}, {world}xB200",
+                "workload": (f"se_e2_a compressed water, {natoms_total}-atom box ({args.ncopy}^3 replicas of the 192-atom "
+                             f"frame per GPU, Gaussian jitter {args.jitter} A), {args.dtype}, {world}xB200")
+                if args.workload == "water" else
+                (f"se_e2_a compressed copper FCC, {natoms_total} atoms ({args.ncopy}^3 cells, a0 3.615 A, jitter 0.05 A), "
+                 f"{args.dtype}, 1xB200, evaluated in "
+                 f"{1 if dp.state.chunks is None else len(dp.state.chunks)} atom slab(s)"),
                 "natoms": natoms_total, "rcut": cfg.rcut, "rcut_smth": cfg.rcut_smth, "sel": list(cfg.sel),
                 "neuron": list(cfg.neuron), "axis_neuron": cfg.axis_neuron, "fitting_neuron": list(cfg.fitting_neuron),
                 "table": "dp-compress restatement, stride 0.01/0.1, extrapolate 5, random-init weights (seed 1)",
@@ -400,8 +417,17 @@ def per_kernel(args, torch, ops, model, dp, step, L, dev, nloc, esz):
         model.energy_and_dy_split = orig_fit_split
         dp.use_graph = graph_mode
     nlist = out[3]["nlist"]
-    nreal = float((nlist >= 0).sum().item()) / nloc
     cfg = model.cfg
+    if nlist is None:  # slab-wise evaluation: count the real neighbours of the first slab
+        st0 = dp.state
+        a, b = st0.chunks[0][0], st0.chunks[0][1]
+        nl0 = orig["prod_env_mat_a"](dp._last_ext_coord.reshape(-1), st0.ext_type, st0.numneigh, st0.rows, model.davg,
+                                     model.dstd, st0.nloc, int(st0.ext_type.numel()), cfg.rcut, cfg.rcut_smth, cfg.sec,
+                                     row_range=(a, b))[3]
+        nreal = float((nl0 >= 0).sum().item()) / (b - a)
+        del nl0
+    else:
+        nreal = float((nlist >= 0).sum().item()) / nloc
     nnei, M, nt = cfg.nnei, model.M, cfg.ntypes
     st = dp.state
     nall = int(st.ext_type.numel())

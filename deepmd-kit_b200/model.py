@@ -349,6 +349,51 @@ class SeAModel:
                 e_atom.index_copy_(0, type_perm[c0:c1], e)
         return e_atom.sum(), e_atom, dy
 
+    def bytes_per_atom(self) -> int:
+        """Device bytes of per-atom intermediates of one evaluation (env-mat, its derivative, rij, nlist, dE/d(em),
+        table output and its gradient, the descriptor in GEMM operand form, fitting activations)."""
+        cfg = self.cfg
+        F = 8 if self.dtype == torch.float64 else 4
+        K = self.M * cfg.axis_neuron
+        desc = (self.nslice * K if self.dtype == torch.float64 else 8 * K) if self.use_split else 0
+        fit = max((sum(int(n) for n in cfg.fitting_neuron) * 3 + K) * F, 0) * min(1.0, self.fit_chunk / 1e6)
+        return int(cfg.nnei * (4 + 12 + 3 + 4) * F + cfg.nnei * 4 + 3 * 4 * self.M * F + desc + fit)
+
+    def evaluate_chunked(self, ext_coord, ext_type, numneigh, rows, mapping, nloc, chunks, atom_virial=False):
+        """evaluate() in slabs of centre atoms: only one slab's intermediates are alive at a time (BASELINE config 3,
+        4 M copper atoms with sel 512, needs 95 KB of them per atom: 380 GB).  `chunks` = [(a, b, perm, ranges, inv)]
+        with the type partition of centre atoms a..b-1 (indices relative to a).  Forces / virial accumulate through
+        dpb200_prod_force_virial_a_ex."""
+        cfg = self.cfg
+        nall = ext_type.numel()
+        n_out = nloc if mapping is not None else nall
+        dev = ext_coord.device
+        force = torch.empty(n_out * 3, dtype=self.dtype, device=dev)
+        virial = torch.empty(9, dtype=self.dtype, device=dev)
+        av = torch.empty(n_out * 9, dtype=self.dtype, device=dev) if atom_virial else None
+        e_atom = torch.empty(nloc, dtype=self.dtype, device=dev)
+        coord_flat = ext_coord.reshape(-1)
+        for ci, (a, b, perm, ranges, inv) in enumerate(chunks):
+            em, dv, rij, nlist = ops.prod_env_mat_a(coord_flat, ext_type, numneigh, rows, self.davg, self.dstd, nloc, nall,
+                                                    cfg.rcut, cfg.rcut_smth, cfg.sec, row_range=(a, b))
+            if self.use_split:
+                xyz, desc, row_exp = ops.tabulate_sections_desc(self.tables, self.infos, em, cfg.sec, self.M,
+                                                                cfg.axis_neuron, 1.0 / cfg.nnei, desc_row=inv, mode=2,
+                                                                nslice=self.nslice, pad_rows=32)
+                _, e_c, dy = self.energy_and_dy_split(xyz, desc, row_exp, perm, ranges)
+                del desc
+            else:
+                xyz = ops.tabulate_sections_fwd(self.tables, self.infos, em, cfg.sec, self.M)
+                _, e_c, dy = self.energy_and_dy(xyz, perm, ranges)
+            net_deriv = ops.tabulate_sections_grad(self.tables, self.infos, em, dy, cfg.sec, self.M)
+            if mapping is not None:
+                ops.use_nlist_map(nlist, mapping)
+            ops.prod_force_virial_a_ex(force, virial, av, net_deriv, dv, rij, nlist, b - a, a, n_out, cfg.nnei,
+                                       accumulate=ci > 0)
+            e_atom[a:b] = e_c
+            del em, dv, rij, nlist, xyz, dy, net_deriv
+        return e_atom.sum(), force.reshape(-1, 3), virial, dict(atom_energy=e_atom, atom_virial=av, nlist=None)
+
     def evaluate(self, ext_coord, ext_type, numneigh, rows, mapping, nloc, type_perm, type_ranges, atom_virial=False,
                  fused=True, type_inv=None):
         """One force evaluation on an extended system. Returns (E, force[nloc,3], virial[9], extras)."""
@@ -396,6 +441,7 @@ class NeighborState:
     ago: int = 0
     map64: Optional[torch.Tensor] = None
     type_inv: Optional[torch.Tensor] = None  # int32 inverse of type_perm: descriptor row of atom i
+    chunks: Optional[list] = None  # atom slabs [(a, b, perm, ranges, inv)] when the evaluation is chunked
 
 
 def type_partition(atype: torch.Tensor, ntypes: int):
@@ -413,8 +459,12 @@ class DeepPotB200:
     host arrays in and out.  The raw neighbour list is rebuilt every `nlist_every` evaluations with a
     `skin` (the reference MD set-up examples/water/lmp/in.lammps:7-8: neighbor 2.0 bin, every 10)."""
 
-    def __init__(self, model: SeAModel, skin: float = 2.0, nlist_every: int = 10, use_graph: bool = True):
+    def __init__(self, model: SeAModel, skin: float = 2.0, nlist_every: int = 10, use_graph: bool = True,
+                 atom_chunk="auto"):
         self.model = model
+        # centre atoms per slab of the evaluation: None = one slab, "auto" = one slab unless the per-atom
+        # intermediates would not fit in 60 % of the device memory
+        self.atom_chunk = atom_chunk
         self.skin = float(skin)
         self.nlist_every = int(nlist_every)
         # The steady-state step (everything between two list rebuilds) has static shapes and no host
@@ -443,7 +493,44 @@ class DeepPotB200:
             inv[perm] = torch.arange(perm.numel(), dtype=torch.int32, device=perm.device)
             hit = (key, perm, ranges, inv)
             self._cache["perm"] = hit
+            self._cache.pop("chunks", None)
         return hit[1], hit[2], hit[3]
+
+    def _chunk_size(self, nloc: int):
+        c = self.atom_chunk
+        if c is None:
+            return None
+        if c == "auto":
+            dev = self.model.device
+            if dev.type != "cuda":
+                return None
+            total = torch.cuda.get_device_properties(dev).total_memory
+            per = self.model.bytes_per_atom()
+            if per * nloc <= 0.6 * total:
+                return None
+            c = max(1024, int(0.45 * total / per) // 1024 * 1024)
+        c = int(c)
+        return c if c < nloc else None
+
+    def _chunks(self, atype: torch.Tensor):
+        """Type partition of every slab of centre atoms (cached with the type tensor)."""
+        nloc = atype.numel()
+        c = self._chunk_size(nloc)
+        if c is None:
+            return None
+        hit = self._cache.get("chunks")
+        key = (atype.data_ptr(), nloc, c)
+        if hit is None or hit[0] != key:
+            out = []
+            for a in range(0, nloc, c):
+                b = min(nloc, a + c)
+                perm, ranges = type_partition(atype[a:b], self.model.cfg.ntypes)
+                inv = torch.empty(b - a, dtype=torch.int32, device=perm.device)
+                inv[perm] = torch.arange(b - a, dtype=torch.int32, device=perm.device)
+                out.append((a, b, perm, ranges, inv))
+            hit = (key, out)
+            self._cache["chunks"] = hit
+        return hit[1]
 
     def build_neighbors(self, coord: torch.Tensor, atype: torch.Tensor, box) -> NeighborState:
         m = self.model
@@ -461,12 +548,17 @@ class DeepPotB200:
         torch.index_select(coord.reshape(-1, 3), 0, map64, out=shift)
         torch.sub(ext_c, shift, out=shift)
         perm, ranges, inv = self._type_partition(atype)
-        self.state = NeighborState(nloc, ext_t, mapping, shift, numneigh, rows, perm, ranges, map64=map64, type_inv=inv)
+        self.state = NeighborState(nloc, ext_t, mapping, shift, numneigh, rows, perm, ranges, map64=map64, type_inv=inv,
+                                   chunks=self._chunks(atype))
         return self.state
 
     def _step(self, coord, atom_virial, fused):
         st = self.state
         ext_c = coord.reshape(-1, 3).index_select(0, st.map64).add_(st.shift)
+        self._last_ext_coord = ext_c
+        if st.chunks is not None:
+            return self.model.evaluate_chunked(ext_c, st.ext_type, st.numneigh, st.rows, st.mapping, st.nloc, st.chunks,
+                                               atom_virial=atom_virial)
         return self.model.evaluate(ext_c, st.ext_type, st.numneigh, st.rows, st.mapping, st.nloc, st.type_perm,
                                    st.type_ranges, atom_virial=atom_virial, fused=fused, type_inv=st.type_inv)
 
@@ -480,7 +572,7 @@ class DeepPotB200:
         if not self.use_graph:
             return self._step(coord, atom_virial, fused)
         key = (st.nloc, int(st.ext_type.numel()), int(st.rows.shape[1]), st.rows.data_ptr(), st.ext_type.data_ptr(),
-               bool(atom_virial), bool(fused), coord.dtype)
+               bool(atom_virial), bool(fused), coord.dtype, None if st.chunks is None else len(st.chunks))
         if self._graph is None or self._graph_key != key:
             self._graph = None
             self._g_out = None

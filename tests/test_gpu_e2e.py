@@ -126,3 +126,23 @@ def test_copper_large_sel_e2e(pkg, dtype):
     assert abs(e[0, 0] - we) <= 1e-10 * abs(we)
     assert rel(f[0], wf) <= 1e-10
     assert rel(v[0], wv) <= 1e-10
+
+
+@pytest.mark.parametrize("dtype", [torch.float64, torch.float32])
+def test_atom_chunked_evaluation_matches_one_slab(pkg, dtype):
+    """Slab-wise evaluation (bounded memory, BASELINE config 3) == the one-slab evaluation."""
+    from deepmd_kit_b200.model import DeepPotB200, SeAConfig, SeAModel
+
+    coord, atype, box = g.water_box(2, 0.01)
+    model = SeAModel(SeAConfig(), dtype, "cuda:0")
+    ref = DeepPotB200(model, atom_chunk=None, use_graph=False).eval(coord.reshape(1, -1), box.reshape(1, 9), atype,
+                                                                    atomic=True)
+    for chunk, graph in ((500, False), (1024, True)):
+        dp = DeepPotB200(model, atom_chunk=chunk, use_graph=graph)
+        got = dp.eval(coord.reshape(1, -1), box.reshape(1, 9), atype, atomic=True)
+        assert dp.state.chunks is not None and len(dp.state.chunks) == -(-len(atype) // chunk)
+        tol = 1e-12 if dtype == torch.float64 else 2e-5
+        for a, b in zip(got, ref):
+            assert rel(a, b) <= tol
+        got2 = dp.eval(coord.reshape(1, -1), box.reshape(1, 9), atype)  # graph replay / list reuse
+        assert rel(got2[1], ref[1]) <= tol
