@@ -105,13 +105,19 @@ class ClockSampler:
 
 
 # DRAM traffic per atom (dram__bytes_read.sum + dram__bytes_write.sum over the launches of one step) from the
-# `ncu --set full` captures summarised in profiles/r01_ncu_full_v3_summary.csv / r01_ncu_full_v1_summary.csv
-# (fp64, 98 304-atom box; the kernels stream per-atom data, so the figure scales with the atom count).
+# `ncu --set full` captures summarised in profiles/r01_ncu_full_v6_summary.csv (fp64, 98 304-atom box; the kernels
+# stream per-atom data, so the figure scales with the atom count).  tabulate_sections_desc = first section (3 973)
+# + last section with the fused descriptor epilogue (17 860: it also writes the 9.6 KB int8 operand of the fitting
+# net); tabulate_sections_grad = 5 798 (first section, measured) + the second section's share of the earlier
+# capture (profiles/r01_ncu_full_v3_summary.csv: 14 046 for both).
 NCU_DRAM_BYTES_PER_ATOM_F64 = {
-    "prod_env_mat_a": 21917.0,
-    "prod_force_virial_a": 20975.0,
-    "tabulate_sections_fwd": 12247.0,
+    "prod_env_mat_a": 22279.0,
+    "prod_force_virial_a": 20890.0,
+    "prod_force_virial_a_ex": 20890.0,
+    "tabulate_sections_fwd": 12271.0,
+    "tabulate_sections_desc": 21833.0,
     "tabulate_sections_grad": 14046.0,
+    "se_a_descriptor_grad": 22367.0,
 }
 
 
@@ -376,7 +382,7 @@ def per_kernel(args, torch, ops, model, dp, step, L, dev, nloc, esz):
     """CUDA-event time of every dpb200 operator inside the real step (events on the launching stream),
     and the roofline of each against measured peaks."""
     names = ["prod_env_mat_a", "tabulate_sections_fwd", "tabulate_sections_desc", "tabulate_sections_grad",
-             "prod_force_virial_a", "use_nlist_map",
+             "prod_force_virial_a", "prod_force_virial_a_ex", "use_nlist_map",
              "normalize_coord", "copy_coord", "build_nlist", "se_a_descriptor", "se_a_descriptor_grad", "halo_pack",
              "halo_unpack_add"]
     acc = {}
@@ -439,6 +445,7 @@ def per_kernel(args, torch, ops, model, dp, step, L, dev, nloc, esz):
     alg = {
         "prod_env_mat_a": ("hbm", (19 * nnei * F + 4 * nnei) + 4 * raw + 3 * F * (1 + nall / nloc)),
         "prod_force_virial_a": ("hbm", (19 * nnei * F + 4 * nnei) + 3 * F + (9 * F if args.atom_virial else 0)),
+        "prod_force_virial_a_ex": ("hbm", (19 * nnei * F + 4 * nnei) + 3 * F + (9 * F if args.atom_virial else 0)),
         "tabulate_sections_fwd": ("fp", 18 * npr * M),
         "tabulate_sections_desc": ("fp", 18 * npr * M),  # the fused descriptor epilogue is not counted
         "tabulate_sections_grad": ("fp", 36 * npr * M),
@@ -474,7 +481,7 @@ def per_kernel(args, torch, ops, model, dp, step, L, dev, nloc, esz):
             traffic = NCU_DRAM_BYTES_PER_ATOM_F64[top] * nloc
         roofline = {"kernel": top, "bound": r["bound"], "achieved": r["achieved"], "peak": r["peak"], "unit": r["unit"],
                     "frac": r["frac"], "traffic": traffic,
-                    "traffic_note": "DRAM bytes per step of this operator (ncu --set full, profiles/r01_ncu_full_v3_summary.csv, "
+                    "traffic_note": "DRAM bytes per step of this operator (ncu --set full, profiles/r01_ncu_full_v6_summary.csv, "
                                     "scaled per atom)",
                     "peak_source": hbm_src if r["bound"] == "hbm" else "dpb200_fma_peak measured in this run (burst)",
                     "mean_real_neighbours": nreal, "mean_raw_neighbours": raw}

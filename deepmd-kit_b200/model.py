@@ -572,7 +572,8 @@ class DeepPotB200:
         if not self.use_graph:
             return self._step(coord, atom_virial, fused)
         key = (st.nloc, int(st.ext_type.numel()), int(st.rows.shape[1]), st.rows.data_ptr(), st.ext_type.data_ptr(),
-               bool(atom_virial), bool(fused), coord.dtype, None if st.chunks is None else len(st.chunks))
+               bool(atom_virial), bool(fused), coord.dtype, st.type_perm.data_ptr(),
+               None if st.chunks is None else tuple(c[2].data_ptr() for c in st.chunks))
         if self._graph is None or self._graph_key != key:
             self._graph = None
             self._g_out = None
@@ -597,6 +598,9 @@ class DeepPotB200:
                 return self._step(coord, atom_virial, fused)
             self._graph_launches = lib().launch_count() - n0
             self._graph, self._graph_key = graph, key
+            # the graph reads these index tensors on every replay: keep them alive with it
+            self._graph_refs = (st.type_perm, st.type_inv, st.chunks, st.rows, st.ext_type, st.numneigh, st.mapping,
+                                st.map64, st.shift)
         self._g_coord.copy_(coord.reshape(-1, 3))
         self._graph.replay()
         from ._lib import lib
