@@ -43,7 +43,8 @@ _SIGS = {
     "mlp_tanh_bwd_{s}": "pp l pp l i p",
     "mlp_tanh_fwd_split_{s}": "pppp l i p p",
     "mlp_tanh_bwd_split_{s}": "pp l pp l i p p",
-    "tabulate_fusion_se_a_desc_{s}": "ppp pli pl iiiii i d p i p l i p p",
+    "tabulate_fusion_se_a_desc_{s}": "ppp pli pl iiiii i d p i p l i p i p",
+    "tabulate_fusion_se_a_grad_fx_{s}": "pp pp pli pl p iiii i p",
     "halo_pack_{s}": "pppp i p",
     "halo_unpack_add_{s}": "ppp i p",
 }

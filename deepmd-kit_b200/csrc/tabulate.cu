@@ -28,6 +28,8 @@
 //     reference does five full warp reductions per neighbour).
 // Not a port of source/lib/src/gpu/tabulate.cu (one thread per channel, stride-6 scalar loads, all
 // coefficients from global memory, serial padding search by thread 0).
+#include <cuda_fp16.h>
+
 #include <cmath>
 #include <cstdlib>
 #include <type_traits>
@@ -58,6 +60,9 @@ struct TabParams {
   int H;   // hot rows kept in shared memory
   int hot_elems;  // H*Mc*6 (+ padding) rounded up to a 16-byte boundary (start of the per-warp records)
   int hot_pad;    // bytes of padding after every hot row (tensor-core forward: 32, see k_tab_fwd_mma)
+  int nblk;       // 16-byte blocks per (row, channel): 3 (coefficient pairs) or 2 (compressed, see k_table_relayout_cm)
+  const FP* T3;   // compressed mode: the full pair table as well (stride-1 "coarse" rows are never compressed)
+  float a5_mul, a5_inv;  // compressed layout: a5 is stored as half(a5 * a5_mul); a5_inv = 1 / a5_mul (powers of two)
   // forward / second order
   FP* out;  // [nloc][4][M]
   const FP* dz_x;
@@ -157,6 +162,81 @@ __global__ void k_table_relayout(FP* __restrict__ T, const FP* __restrict__ tabl
   }
 }
 
+// Compressed coefficients (fp64, opt-in by the caller who has validated its table: DPB200_TAB_COMPRESSED_COEF).
+// The table kernels are bound by the L1/shared data pipe (48 B of coefficients per evaluation), and for a
+// dp-compress table the high-order terms are tiny: a3 x^3 <= 5e-8 |a0|, a4 x^4 <= 2e-10, a5 x^5 <= 5e-13 on the
+// stride-0.01 rows.  So a3 and a4 are stored as fp32 and a5 as fp16 in the 16 low mantissa bits of a2 (which keeps
+// 36 bits: 1.5e-11 relative on a term that is <= 1e-5 |a0|):  32 B per (row, channel) = two 16-byte blocks
+//   block 0 = {a0, a1}   block 1 = {a2 | half(a5), (float a3, float a4)}
+// Errors against the fp64 table: < 1e-14 |a0| on the value and < 1e-12 |a1| on the derivative for the water
+// table (model.py computes the bound for the actual table and only then sets the flag).
+__device__ __forceinline__ double2 pack_cm(double a2, double a3, double a4, double a5, float a5_mul) {
+  const unsigned short h5 = __half_as_ushort(__float2half_rn((float)(a5 * (double)a5_mul)));
+  const unsigned long long b2 = ((unsigned long long)__double_as_longlong(a2) & ~0xffffull) | (unsigned long long)h5;
+  const unsigned long long b34 = (unsigned long long)__float_as_uint((float)a3) |
+                                 ((unsigned long long)__float_as_uint((float)a4) << 32);
+  return make_double2(__longlong_as_double((long long)b2), __longlong_as_double((long long)b34));
+}
+__device__ __forceinline__ void unpack_cm(const double2 v, double& a2, float& a3, float& a4, float& a5) {
+  const unsigned long long b2 = (unsigned long long)__double_as_longlong(v.x);
+  const unsigned long long b34 = (unsigned long long)__double_as_longlong(v.y);
+  a2 = v.x;  // the 16 borrowed bits are noise at 2^-36 relative
+  a5 = __half2float(__ushort_as_half((unsigned short)(b2 & 0xffffull)));
+  a3 = __uint_as_float((unsigned)(b34 & 0xffffffffull));
+  a4 = __uint_as_float((unsigned)(b34 >> 32));
+}
+
+// [row][M][6] -> [row][2][M] blocks
+__global__ void k_table_relayout_cm(double2* __restrict__ T, const double* __restrict__ table, long long nrow, int M,
+                                    float a5_mul) {
+  const long long n = nrow * (long long)M;
+  for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < n;
+       e += (long long)gridDim.x * blockDim.x) {
+    const long long r = e / M;
+    const int k = (int)(e - r * M);
+    const double* a = table + e * 6;
+    T[(r * 2 + 0) * M + k] = make_double2(a[0], a[1]);
+    T[(r * 2 + 1) * M + k] = pack_cm(a[2], a[3], a[4], a[5], a5_mul);
+  }
+}
+
+// fetch_row for the compressed layout: the coefficients are expanded to fp64 registers, the rest of the
+// kernel is unchanged (8 instead of 12 sixteen-byte requests per lane and row).
+template <int NC>
+__device__ __forceinline__ void fetch_row_cm(double (&a)[NC][6], const double* __restrict__ hot,
+                                             const double* __restrict__ T, int row, int r0, int H, int M,
+                                             const int (&ob)[NC], float a5_inv) {
+  const unsigned rel = (unsigned)(row - r0);
+  const unsigned qb = (unsigned)M * 16u;
+  const bool inwin = rel < (unsigned)H;
+  const char* b0 = inwin ? reinterpret_cast<const char*>(hot) + rel * (2u * qb)
+                         : reinterpret_cast<const char*>(T) + (long long)row * (2u * qb);
+  if (inwin) {
+#pragma unroll
+    for (int c = 0; c < NC; ++c) {
+      const double2 u = *reinterpret_cast<const double2*>(b0 + ob[c]);
+      const double2 v = *reinterpret_cast<const double2*>(b0 + qb + ob[c]);
+      float a3, a4, a5;
+      a[c][0] = u.x, a[c][1] = u.y;
+      unpack_cm(v, a[c][2], a3, a4, a5);
+      a[c][3] = (double)a3, a[c][4] = (double)a4, a[c][5] = (double)(a5 * a5_inv);
+    }
+  } else {
+#pragma unroll
+    for (int c = 0; c < NC; ++c) {
+      const double2 u = __ldg(reinterpret_cast<const double2*>(b0 + ob[c]));
+      const double2 v = __ldg(reinterpret_cast<const double2*>(b0 + qb + ob[c]));
+      float a3, a4, a5;
+      a[c][0] = u.x, a[c][1] = u.y;
+      unpack_cm(v, a[c][2], a3, a4, a5);
+      a[c][3] = (double)a3, a[c][4] = (double)a4, a[c][5] = (double)(a5 * a5_inv);
+    }
+  }
+}
+template <int NC>
+__device__ __forceinline__ void fetch_row_cm(float (&)[NC][6], const float*, const float*, int, int, int, int,
+                                             const int (&)[NC], float) {}
+
 // Coefficients of one table row for the NC channels of this lane.  ob[c] = byte offset of the lane's
 // channel inside one coefficient-pair block (clamped to channel M-1 so that every lane always loads:
 // no divergence, the duplicates cost no extra wavefront).  Source: the shared-memory window
@@ -209,13 +289,13 @@ __device__ __forceinline__ int hot_window_start(const TabParams<FP>& p) {
 template <typename FP>
 __device__ __forceinline__ void preload_hot(FP* __restrict__ hot, const TabParams<FP>& p, int r0) {
   using P2 = typename Pair2<FP>::type;
-  const long long n = (long long)p.H * 3 * p.M;
-  const P2* __restrict__ src = reinterpret_cast<const P2*>(p.T) + (long long)r0 * 3 * p.M;
+  const long long n = (long long)p.H * p.nblk * p.M;
+  const P2* __restrict__ src = reinterpret_cast<const P2*>(p.T) + (long long)r0 * p.nblk * p.M;
   P2* dst = reinterpret_cast<P2*>(hot);
   if (p.hot_pad == 0) {
     for (long long e = threadIdx.x; e < n; e += blockDim.x) dst[e] = __ldg(src + e);
   } else {
-    const int per_row = 3 * p.M;
+    const int per_row = p.nblk * p.M;
     const int stride = per_row + p.hot_pad / (int)sizeof(P2);
     for (long long e = threadIdx.x; e < n; e += blockDim.x) {
       const int r = (int)(e / per_row);
@@ -461,7 +541,7 @@ extern __shared__ __align__(16) unsigned char tab_smem[];
 // grid (x: persistent over atoms, y: block of 32*NC channels); block = nw warps.
 // smem: hot[H][3][M] pairs | Rec[nw][32] | RecGG[nw][32] (GG only)
 // ------------------------------------------------------------------------------------------
-template <typename FP, int NC, bool TWO, bool GG, bool DESC = false>
+template <typename FP, int NC, bool TWO, bool GG, bool DESC = false, bool CM = false>
 __global__ void __launch_bounds__(512) k_tab_fwd(const __grid_constant__ TabParams<FP> p) {
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
@@ -521,7 +601,12 @@ __global__ void __launch_bounds__(512) k_tab_fwd(const __grid_constant__ TabPara
         const int row = r.idx;
         if (row != cur_row) {  // warp-uniform
           cur_row = row;
-          fetch_row<FP, NC>(a, hot, p.T, row, r0, p.H, p.M, ob);
+          if (CM && row < p.first)
+            fetch_row_cm<NC>(a, hot, p.T, row, r0, p.H, p.M, ob, p.a5_inv);
+          else if (CM)
+            fetch_row<FP, NC>(a, hot, p.T3, row, 0, 0, p.M, ob);  // coarse row: full precision from L2
+          else
+            fetch_row<FP, NC>(a, hot, p.T, row, r0, p.H, p.M, ob);
         }
         const FP xx = r.xx;
         const FP e0 = r.e[0], e1 = r.e[1], e2 = r.e[2], e3 = r.e[3];
@@ -540,7 +625,12 @@ __global__ void __launch_bounds__(512) k_tab_fwd(const __grid_constant__ TabPara
         const int row = r.idx;
         if (row != cur_row) {  // warp-uniform
           cur_row = row;
-          fetch_row<FP, NC>(a, hot, p.T, row, r0, p.H, p.M, ob);
+          if (CM && row < p.first)
+            fetch_row_cm<NC>(a, hot, p.T, row, r0, p.H, p.M, ob, p.a5_inv);
+          else if (CM)
+            fetch_row<FP, NC>(a, hot, p.T3, row, 0, 0, p.M, ob);  // coarse row: full precision from L2
+          else
+            fetch_row<FP, NC>(a, hot, p.T, row, r0, p.H, p.M, ob);
         }
         const FP xx = r.xx;
         const FP dl = r.delta;
@@ -926,7 +1016,7 @@ __global__ void __launch_bounds__(512) k_tab_fwd_mma(const __grid_constant__ Tab
 // BSM: the B fragments (dy of the current atom) live in a per-warp shared-memory tile instead of 2*KT
 // registers, which lets MAXT / 32 warps (instead of 12) share an SM: the kernel is latency-bound on the
 // coefficient fetches of rows outside the hot window, so warps in flight are what it needs.
-template <int KT, bool BSM, int MAXT>
+template <int KT, bool BSM, int MAXT, bool CM = false>
 __global__ void __launch_bounds__(MAXT) k_tab_grad_mma(const __grid_constant__ TabParams<double> p) {
   using FP = double;
   const int lane = threadIdx.x & 31;
@@ -942,6 +1032,7 @@ __global__ void __launch_bounds__(MAXT) k_tab_grad_mma(const __grid_constant__ T
   const bool fuse_x = p.dy_dem_x == nullptr;
   const int q = lane >> 2, kk = lane & 3;
   const unsigned qb = (unsigned)M * 16u;
+  const unsigned rowb = (CM ? 2u : 3u) * qb;  // bytes per table row
   const unsigned off_k = (unsigned)kk * 16u;
   const unsigned off_last = (unsigned)((4 * (KT - 1) + kk < M) ? 4 * (KT - 1) + kk : M - 1) * 16u;
 
@@ -984,40 +1075,65 @@ __global__ void __launch_bounds__(MAXT) k_tab_grad_mma(const __grid_constant__ T
       const bool live = nb < nproc;
       const Rec<FP>& r = rec[live ? nb : nproc - 1];
       const FP xx = r.xx;
+      const float xf = (float)xx;
+      const float xs = xf * p.a5_inv;  // a5 is stored pre-multiplied by a power of two (fp16 range)
       const FP dl = r.delta;
       const unsigned rel = (unsigned)(r.idx - r0);
       const bool inwin = rel < (unsigned)p.H;
       FP c1a = 0., c1b = 0., c2a = 0., c2b = 0.;
-#define DPB_GRAD_STEPS(BASE)                                                                  \
+#define DPB_GRAD_STEPS(BASE, COMP)                                                            \
   _Pragma("unroll") for (int t = 0; t < KT; ++t) {                                            \
     const unsigned off = (t == KT - 1) ? off_last : (unsigned)t * 64u + off_k;                \
-    const double2 u = *reinterpret_cast<const double2*>((BASE) + off);                        \
-    const double2 v = *reinterpret_cast<const double2*>((BASE) + qb + off);                   \
-    const double2 w = *reinterpret_cast<const double2*>((BASE) + 2u * qb + off);              \
-    const FP b4 = w.x + w.y * xx;                                                             \
-    const FP b3 = v.y + b4 * xx;                                                              \
-    const FP b2 = v.x + b3 * xx;                                                              \
-    const FP b1 = u.y + b2 * xx;                                                              \
-    FP g = u.x + b1 * xx;                                                                     \
-    const FP d4 = b4 + w.y * xx;                                                              \
-    const FP d3 = b3 + d4 * xx;                                                               \
-    const FP d2 = b2 + d3 * xx;                                                               \
-    const FP gd = b1 + d2 * xx;                                                               \
+    FP g, gd;                                                                                 \
+    if (COMP) {                                                                               \
+      /* a3..a5 are fp32 / fp16: the top of both Horner chains runs on the FP32 pipe */       \
+      const double2 u = *reinterpret_cast<const double2*>((BASE) + off);                      \
+      const double2 v = *reinterpret_cast<const double2*>((BASE) + qb + off);                 \
+      double a2;                                                                              \
+      float a3, a4, a5;                                                                       \
+      unpack_cm(v, a2, a3, a4, a5);                                                           \
+      const float f4 = fmaf(a5, xs, a4);                                                      \
+      const float f3 = fmaf(f4, xf, a3);                                                      \
+      const float e4 = fmaf(a5, xs, f4);                                                      \
+      const float e3 = fmaf(e4, xf, f3);                                                      \
+      const FP b2 = a2 + (FP)f3 * xx;                                                         \
+      const FP b1 = u.y + b2 * xx;                                                            \
+      g = u.x + b1 * xx;                                                                      \
+      const FP d2 = b2 + (FP)e3 * xx;                                                         \
+      gd = b1 + d2 * xx;                                                                      \
+    } else {                                                                                  \
+      const double2 u = *reinterpret_cast<const double2*>((BASE) + off);                      \
+      const double2 v = *reinterpret_cast<const double2*>((BASE) + qb + off);                 \
+      const double2 w = *reinterpret_cast<const double2*>((BASE) + 2u * qb + off);            \
+      const FP b4 = w.x + w.y * xx;                                                           \
+      const FP b3 = v.y + b4 * xx;                                                            \
+      const FP b2 = v.x + b3 * xx;                                                            \
+      const FP b1 = u.y + b2 * xx;                                                            \
+      g = u.x + b1 * xx;                                                                      \
+      const FP d4 = b4 + w.y * xx;                                                            \
+      const FP d3 = b3 + d4 * xx;                                                             \
+      const FP d2 = b2 + d3 * xx;                                                             \
+      gd = b1 + d2 * xx;                                                                      \
+    }                                                                                         \
     if (any_delta) g += gd * dl;                                                              \
     const FP bt = BSM ? ((q < 4 && 4 * t + kk < M) ? bsrc[4 * t] : (FP)0.) : bf[BSM ? 0 : t]; \
     dmma884(c1a, c1b, g, bt);                                                                 \
     dmma884(c2a, c2b, gd, bt);                                                                \
   }
-      if (__all_sync(kFull, inwin)) {
-        const char* b = reinterpret_cast<const char*>(hot) + rel * (3u * qb);
-        DPB_GRAD_STEPS(b)
+      if (CM && __any_sync(kFull, r.idx >= p.first)) {
+        // a stride-1 (extrapolation) row in this step: those are not compressed, take the full table for all lanes
+        const char* __restrict__ b = reinterpret_cast<const char*>(p.T3) + (long long)r.idx * (3u * qb);
+        DPB_GRAD_STEPS(b, false)
+      } else if (__all_sync(kFull, inwin)) {
+        const char* b = reinterpret_cast<const char*>(hot) + rel * rowb;
+        DPB_GRAD_STEPS(b, CM)
       } else if (!__any_sync(kFull, inwin)) {
-        const char* __restrict__ b = reinterpret_cast<const char*>(p.T) + (long long)r.idx * (3u * qb);
-        DPB_GRAD_STEPS(b)
+        const char* __restrict__ b = reinterpret_cast<const char*>(p.T) + (long long)r.idx * rowb;
+        DPB_GRAD_STEPS(b, CM)
       } else {
-        const char* b = inwin ? reinterpret_cast<const char*>(hot) + rel * (3u * qb)
-                              : reinterpret_cast<const char*>(p.T) + (long long)r.idx * (3u * qb);
-        DPB_GRAD_STEPS(b)
+        const char* b = inwin ? reinterpret_cast<const char*>(hot) + rel * rowb
+                              : reinterpret_cast<const char*>(p.T) + (long long)r.idx * rowb;
+        DPB_GRAD_STEPS(b, CM)
       }
 #undef DPB_GRAD_STEPS
       // C row = neighbour q, columns 2kk, 2kk+1 (components; valid for kk < 2)
@@ -1161,6 +1277,49 @@ int prepare_table(TabParams<FP>& p, FP** scratch, cudaStream_t st) {
   return DPB200_OK;
 }
 
+inline int prepare_table_cm(TabParams<double>& p, double** scratch, cudaStream_t st) {
+  const long long n = (long long)p.nrow * 4 * p.M;  // two 16-byte blocks per (row, channel)
+  keep_async_pool();
+  DPB_CUDA(cudaMallocAsync((void**)scratch, (size_t)n * sizeof(double), st));
+  int grid = ceil_div((long long)p.nrow * p.M, 256);
+  const int cap = sm_count() * 8;
+  if (grid > cap) grid = cap;
+  k_table_relayout_cm<<<grid, 256, 0, st>>>(reinterpret_cast<double2*>(*scratch), p.table, p.nrow, p.M, p.a5_mul);
+  p.T = *scratch;
+  return DPB200_OK;
+}
+// full pair table next to the compressed one (for the stride-1 rows)
+inline int prepare_table_full(TabParams<double>& p, double** scratch3, cudaStream_t st) {
+  const long long n = (long long)p.nrow * 6 * p.M;
+  DPB_CUDA(cudaMallocAsync((void**)scratch3, (size_t)n * sizeof(double), st));
+  int grid = ceil_div(n, 256);
+  const int cap = sm_count() * 8;
+  if (grid > cap) grid = cap;
+  k_table_relayout<double><<<grid, 256, 0, st>>>(*scratch3, p.table, p.nrow, p.M);
+  p.T3 = *scratch3;
+  return DPB200_OK;
+}
+inline int prepare_table_full(TabParams<float>&, float**, cudaStream_t) { return DPB200_ERR_INVALID; }
+inline int prepare_table_cm(TabParams<float>&, float**, cudaStream_t) { return DPB200_ERR_INVALID; }
+
+// bits 8..15 of `flags`: signed power-of-two exponent k, a5 is stored as half(a5 * 2^k)
+template <typename FP>
+void set_a5_scale(TabParams<FP>& p, int flags) {
+  const int k = (int)(signed char)((flags >> 8) & 0xff);
+  p.a5_mul = std::ldexp(1.0f, k);
+  p.a5_inv = std::ldexp(1.0f, -k);
+}
+
+// hot rows / shared-memory sizing for `blocks` 16-byte blocks per (row, channel)
+template <typename FP>
+void size_hot_window(TabParams<FP>& p, int M, size_t other_bytes, int blocks) {
+  const size_t row_bytes = (size_t)M * 16 * blocks;
+  long long h = other_bytes + row_bytes > kSmemBudget ? 0 : (long long)((kSmemBudget - other_bytes) / row_bytes);
+  if (h > hot_rows_cap()) h = hot_rows_cap();
+  p.H = (int)(h < p.nrow ? h : p.nrow);
+  p.hot_elems = (int)(((size_t)p.H * row_bytes + 15) / 16 * 16 / sizeof(FP));
+}
+
 struct DescArgs {
   void* desc;
   long long desc_ld;
@@ -1174,10 +1333,12 @@ template <typename FP, bool GG>
 int launch_fwd(FP* out, const FP* table, const FP* info, const FP* em_x, long long ldx_i, int ldx_j,
                const FP* em, long long ldem_i, const FP* two, const FP* dz_x, const FP* dz_em,
                const FP* dz_two, int nloc, int nnei, int M, int is_sorted, int accumulate,
-               cudaStream_t st, const DescArgs* da = nullptr) {
+               cudaStream_t st, const DescArgs* da = nullptr, int flags = 0) {
   DPB_REQUIRE(nloc >= 0 && nnei >= 0 && M >= 0, "tabulate: negative size");
   if (nloc == 0 || M == 0) return DPB200_OK;
   DPB_REQUIRE(out != nullptr, "tabulate: out is null");
+  // compressed coefficients: fp64, plain se_a forward, SIMT kernel
+  const bool cm = (flags & DPB200_TAB_COMPRESSED_COEF) && sizeof(FP) == 8 && !GG && two == nullptr && !use_mma_fwd();
   if (da) {
     const bool plain = !GG && two == nullptr && nnei > 0;
     DPB_REQUIRE(plain, "tabulate+descriptor: plain se_a forward with nnei > 0 only");
@@ -1229,12 +1390,19 @@ int launch_fwd(FP* out, const FP* table, const FP* info, const FP* em_x, long lo
   const int nw = 16;
   const size_t rec_bytes = (size_t)nw * 32 * (sizeof(Rec<FP>) + (GG ? sizeof(RecGG<FP>) : 0));
   p.Mc = M;
-  p.H = hot_rows<FP>(p.nrow, M, rec_bytes);
-  p.hot_elems = hot_elems_aligned<FP>(p.H, M);
+  p.nblk = cm ? 2 : 3;
+  set_a5_scale(p, flags);
+  size_hot_window(p, M, rec_bytes, p.nblk);
   const size_t smem = (size_t)p.hot_elems * sizeof(FP) + rec_bytes;
   FP* scratch = nullptr;
-  rc = prepare_table(p, &scratch, st);
+  FP* scratch3 = nullptr;
+  rc = cm ? prepare_table_cm(p, &scratch, st) : prepare_table(p, &scratch, st);
   if (rc) return rc;
+  if (cm) {
+    rc = prepare_table_full(p, &scratch3, st);
+    if (rc) return rc;
+    if (p.H > p.first) p.H = p.first;  // the shared-memory window holds compressed (stride-0) rows only
+  }
   const bool tw = two != nullptr;
   const int nblk = (M + 32 * nc - 1) / (32 * nc);
   long long want = ((long long)nloc + nw - 1) / nw;
@@ -1283,7 +1451,15 @@ int launch_fwd(FP* out, const FP* table, const FP* info, const FP* em_x, long lo
   }
 #define DPB_LAUNCH_FWD(NC)                                                                      \
   do {                                                                                          \
-    if (da) {                                                                                   \
+    if (da && cm) {                                                                             \
+      auto kern = k_tab_fwd<FP, NC, false, false, true, true>;                                  \
+      e1 = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);  \
+      if (e1 == cudaSuccess) kern<<<grid, nw * 32, smem, st>>>(p);                              \
+    } else if (cm) {                                                                            \
+      auto kern = k_tab_fwd<FP, NC, false, false, false, true>;                                 \
+      e1 = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);  \
+      if (e1 == cudaSuccess) kern<<<grid, nw * 32, smem, st>>>(p);                              \
+    } else if (da) {                                                                            \
       auto kern = k_tab_fwd<FP, NC, false, false, true>;                                        \
       e1 = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);  \
       if (e1 == cudaSuccess) kern<<<grid, nw * 32, smem, st>>>(p);                              \
@@ -1307,8 +1483,9 @@ int launch_fwd(FP* out, const FP* table, const FP* info, const FP* em_x, long lo
 #undef DPB_LAUNCH_FWD
   if (e1 == cudaSuccess) e1 = cudaGetLastError();
   cudaFreeAsync(scratch, st);
+  if (scratch3) cudaFreeAsync(scratch3, st);
   DPB_CUDA(e1);
-  note_launches(2);
+  note_launches(scratch3 ? 3 : 2);
   return DPB200_OK;
 }
 
@@ -1316,7 +1493,7 @@ template <typename FP>
 int launch_grad(FP* dy_dem_x, FP* dy_dem, FP* dy_dtwo, const FP* table, const FP* info,
                 const FP* em_x, long long ldx_i, int ldx_j, const FP* em, long long ldem_i,
                 const FP* two, const FP* dy, int nloc, int nnei, int M, int is_sorted,
-                cudaStream_t st) {
+                cudaStream_t st, int flags = 0) {
   DPB_REQUIRE(nloc >= 0 && nnei >= 0 && M >= 0, "tabulate grad: negative size");
   if (nloc == 0 || nnei == 0) return DPB200_OK;  // tabulate.cc: nothing to write
   DPB_REQUIRE(dy_dem != nullptr && dy != nullptr, "tabulate grad: null pointer");
@@ -1332,35 +1509,48 @@ int launch_grad(FP* dy_dem_x, FP* dy_dem, FP* dy_dtwo, const FP* table, const FP
   p.dy_dtwo = dy_dtwo;
   const int nw = 12;
   const size_t rec_bytes = (size_t)nw * 32 * sizeof(Rec<FP>);
+  const bool tw = two != nullptr;
+  const int kt = (M + 3) / 4;
+  const bool mma_ok = std::is_same<FP, double>::value && !tw && use_mma_path() &&
+                      (kt == 8 || kt == 16 || kt == 20 || kt == 25 || kt == 32);
+  const bool cm = mma_ok && (flags & DPB200_TAB_COMPRESSED_COEF) && grad_variant() == 1;
   p.Mc = M;
-  p.H = hot_rows<FP>(p.nrow, M, rec_bytes);
-  p.hot_elems = hot_elems_aligned<FP>(p.H, M);
+  p.nblk = cm ? 2 : 3;
+  set_a5_scale(p, flags);
+  size_hot_window(p, M, rec_bytes, p.nblk);
   const size_t smem = (size_t)p.hot_elems * sizeof(FP) + rec_bytes;
   FP* scratch = nullptr;
-  rc = prepare_table(p, &scratch, st);
+  FP* scratch3 = nullptr;
+  rc = cm ? prepare_table_cm(p, &scratch, st) : prepare_table(p, &scratch, st);
   if (rc) return rc;
-  const bool tw = two != nullptr;
+  if (cm) {
+    rc = prepare_table_full(p, &scratch3, st);
+    if (rc) return rc;
+  }
   long long want = ((long long)nloc + nw - 1) / nw;
   const long long cap = sm_count();
   const int grid = (int)(want < cap ? want : cap);
   cudaError_t e1 = cudaSuccess;
   bool launched = false;
   if constexpr (std::is_same<FP, double>::value) {
-    const int kt = (M + 3) / 4;
-    if (!tw && use_mma_path() && (kt == 8 || kt == 16 || kt == 20 || kt == 25 || kt == 32)) {
+    if (mma_ok) {
       // variant 0: B fragments in registers, 12 warps; 1: in shared memory, 16 warps; 2: 24 warps
       const int variant = grad_variant();
       const int nwv = variant == 0 ? 12 : (variant == 1 ? 16 : 24);
       const size_t extra = variant == 0 ? 0 : (size_t)nwv * 4 * M * sizeof(FP);
       const size_t recv = (size_t)nwv * 32 * sizeof(Rec<FP>);
-      p.H = hot_rows<FP>(p.nrow, M, recv + extra);
-      p.hot_elems = hot_elems_aligned<FP>(p.H, M);
+      size_hot_window(p, M, recv + extra, p.nblk);
+      if (cm && p.H > p.first) p.H = p.first;  // the window holds compressed (stride-0) rows only
       const size_t smemv = (size_t)p.hot_elems * sizeof(FP) + recv + extra;
       long long wantv = ((long long)nloc + nwv - 1) / nwv;
       const int gridv = (int)(wantv < cap ? wantv : cap);
 #define DPB_LAUNCH_GRAD_MMA(KT)                                                                 \
   do {                                                                                          \
-    if (variant == 0) {                                                                         \
+    if (cm) {                                                                                   \
+      auto kern = k_tab_grad_mma<KT, true, 512, true>;                                          \
+      e1 = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemv); \
+      if (e1 == cudaSuccess) kern<<<gridv, nwv * 32, smemv, st>>>(p);                           \
+    } else if (variant == 0) {                                                                  \
       auto kern = k_tab_grad_mma<KT, false, 384>;                                               \
       e1 = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemv); \
       if (e1 == cudaSuccess) kern<<<gridv, nwv * 32, smemv, st>>>(p);                           \
@@ -1407,8 +1597,9 @@ int launch_grad(FP* dy_dem_x, FP* dy_dem, FP* dy_dtwo, const FP* table, const FP
 #undef DPB_LAUNCH_GRAD
   if (e1 == cudaSuccess) e1 = cudaGetLastError();
   cudaFreeAsync(scratch, st);
+  if (scratch3) cudaFreeAsync(scratch3, st);
   DPB_CUDA(e1);
-  note_launches(2);
+  note_launches(scratch3 ? 3 : 2);
   return DPB200_OK;
 }
 
@@ -1442,12 +1633,21 @@ extern "C" {
       FP* out, const FP* table, const FP* table_info, const FP* em_x, long long ldx_i, int ldx_j,  \
       const FP* em, long long ldem_i, int nloc, int nnei, int last_layer_size, int is_sorted,      \
       int accumulate, int axis, double scale, const int* desc_row, int desc_mode, void* desc,      \
-      long long desc_ld, int nslice, int* row_exp, dpb200_stream_t stream) {                       \
+      long long desc_ld, int nslice, int* row_exp, int flags, dpb200_stream_t stream) {            \
     dpb200::DescArgs da = {desc, desc_ld, desc_row, row_exp, scale, desc_mode, axis, nslice};      \
     return dpb200::launch_fwd<FP, false>(out, table, table_info, em_x, ldx_i, ldx_j, em, ldem_i,   \
                                          nullptr, nullptr, nullptr, nullptr, nloc, nnei,           \
                                          last_layer_size, is_sorted, accumulate,                   \
-                                         (cudaStream_t)stream, &da);                               \
+                                         (cudaStream_t)stream, desc_mode == 0 ? nullptr : &da,     \
+                                         flags);                                                   \
+  }                                                                                                \
+  int dpb200_tabulate_fusion_se_a_grad_fx_##SUF(                                                   \
+      FP* dy_dem_x, FP* dy_dem, const FP* table, const FP* table_info, const FP* em_x,             \
+      long long ldx_i, int ldx_j, const FP* em, long long ldem_i, const FP* dy, int nloc,          \
+      int nnei, int last_layer_size, int is_sorted, int flags, dpb200_stream_t stream) {           \
+    return dpb200::launch_grad<FP>(dy_dem_x, dy_dem, nullptr, table, table_info, em_x, ldx_i,      \
+                                   ldx_j, em, ldem_i, nullptr, dy, nloc, nnei, last_layer_size,    \
+                                   is_sorted, (cudaStream_t)stream, flags);                        \
   }                                                                                                \
   int dpb200_tabulate_fusion_se_a_grad_##SUF(FP* dy_dem_x, FP* dy_dem, FP* dy_dtwo,                \
                                              const FP* table, const FP* table_info,                \

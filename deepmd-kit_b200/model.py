@@ -310,6 +310,14 @@ class SeAModel:
         if self.use_split:
             for f in self.fit:
                 f.prepare_split(self.nslice)
+        # Compressed table coefficients (include/dpb200.h DPB200_TAB_COMPRESSED_COEF): the table kernels are bound by
+        # the on-chip coefficient stream; for a dp-compress table the high-order terms tolerate fp32 / fp16 storage
+        # at the 1e-12 level.  Checked per table here, on the host, once.
+        self.coef_flags = None
+        if dtype == torch.float64 and self.device.type == "cuda":
+            fl = [ops.compressed_coef_flags(t, i) for t, i in zip(self.tables64, infos)]
+            if all(fl):
+                self.coef_flags = fl
 
     # -- descriptor contraction (dpb200 kernels) + fitting net (cuBLAS GEMMs through torch, hand-written
     #    backward).  The fitting net is library code here; SURVEY 8f-1 lists its fusion as the next item.
@@ -379,13 +387,13 @@ class SeAModel:
             if self.use_split:
                 xyz, desc, row_exp = ops.tabulate_sections_desc(self.tables, self.infos, em, cfg.sec, self.M,
                                                                 cfg.axis_neuron, 1.0 / cfg.nnei, desc_row=inv, mode=2,
-                                                                nslice=self.nslice, pad_rows=32)
+                                                                nslice=self.nslice, pad_rows=32, flags=self.coef_flags)
                 _, e_c, dy = self.energy_and_dy_split(xyz, desc, row_exp, perm, ranges)
                 del desc
             else:
                 xyz = ops.tabulate_sections_fwd(self.tables, self.infos, em, cfg.sec, self.M)
                 _, e_c, dy = self.energy_and_dy(xyz, perm, ranges)
-            net_deriv = ops.tabulate_sections_grad(self.tables, self.infos, em, dy, cfg.sec, self.M)
+            net_deriv = ops.tabulate_sections_grad(self.tables, self.infos, em, dy, cfg.sec, self.M, flags=self.coef_flags)
             if mapping is not None:
                 ops.use_nlist_map(nlist, mapping)
             ops.prod_force_virial_a_ex(force, virial, av, net_deriv, dv, rij, nlist, b - a, a, n_out, cfg.nnei,
@@ -407,13 +415,13 @@ class SeAModel:
                 type_inv[type_perm] = torch.arange(nloc, dtype=torch.int32, device=type_perm.device)
             xyz, desc, row_exp = ops.tabulate_sections_desc(self.tables, self.infos, em, cfg.sec, self.M,
                                                             cfg.axis_neuron, 1.0 / cfg.nnei, desc_row=type_inv, mode=2,
-                                                            nslice=self.nslice, pad_rows=32)
+                                                            nslice=self.nslice, pad_rows=32, flags=self.coef_flags)
             energy, e_atom, dy = self.energy_and_dy_split(xyz, desc, row_exp, type_perm, type_ranges)
             del desc
         else:
             xyz = ops.tabulate_sections_fwd(self.tables, self.infos, em, cfg.sec, self.M)
             energy, e_atom, dy = self.energy_and_dy(xyz, type_perm, type_ranges)
-        net_deriv = ops.tabulate_sections_grad(self.tables, self.infos, em, dy, cfg.sec, self.M)
+        net_deriv = ops.tabulate_sections_grad(self.tables, self.infos, em, dy, cfg.sec, self.M, flags=self.coef_flags)
         if mapping is not None:
             ops.use_nlist_map(nlist, mapping)
             n_out = nloc

@@ -305,7 +305,36 @@ def tabulate_sections_fwd(tables, infos, em, sec, last_layer_size, is_sorted=Tru
     return out
 
 
-def tabulate_sections_grad(tables, infos, em, dy, sec, last_layer_size, is_sorted=True):
+def compressed_coef_flags(table: torch.Tensor, info, tol: float = 3e-12) -> int:
+    """Host-side gate for DPB200_TAB_COMPRESSED_COEF (include/dpb200.h): returns the flags word for THIS table
+    ([nrow, M*6] fp64) if, on every stride-0 row (the stride-1 extrapolation rows are never compressed), storing
+    a3, a4 as fp32, a5 as fp16 (scaled by a power of two) and a2 with 36 mantissa bits changes the quintic by less
+    than tol * max|a0| and its derivative by less than tol * max|a1|; else 0.
+    Rounding model: a2 2^-37; a3, a4 2^-25 storage + 2^-24 fp32 Horner step; a5 2^-11."""
+    t = table.detach().to("cpu", torch.float64)
+    lower, upper, vmax, s0, s1 = [float(x) for x in info[:5]]
+    nrow = t.shape[0]
+    a = t.reshape(nrow, -1, 6).abs()
+    first = min(nrow, int((upper - lower) / s0))
+    m0, m1 = float(a[..., 0].max()), float(a[..., 1].max())
+    if not (m0 > 0 and m1 > 0 and first > 0):
+        return 0
+    e2, e34, e5 = 2.0 ** -37, 1.5 * 2.0 ** -24, 2.0 ** -11 + 2.0 ** -23
+    blk, s = a[:first], s0
+    ev = e2 * blk[..., 2] * s ** 2 + e34 * (blk[..., 3] * s ** 3 + blk[..., 4] * s ** 4) + e5 * blk[..., 5] * s ** 5
+    ed = 2 * e2 * blk[..., 2] * s + e34 * (3 * blk[..., 3] * s ** 2 + 4 * blk[..., 4] * s ** 3) + e5 * 5 * blk[..., 5] * s ** 4
+    if float(ev.max()) > tol * m0 or float(ed.max()) > tol * m1:
+        return 0
+    m5 = float(blk[..., 5].max())
+    k = 0
+    if m5 > 0:
+        import math
+
+        k = max(-120, min(120, 13 - int(math.floor(math.log2(m5)))))  # max|a5| * 2^k in [2^13, 2^14)
+    return 1 | ((k & 0xff) << 8)
+
+
+def tabulate_sections_grad(tables, infos, em, dy, sec, last_layer_size, is_sorted=True, flags=None):
     """Backward of tabulate_sections_fwd: d/d(em) as one [nloc, nnei*4] matrix (the em_x gradient is
     added into component 0 inside the kernel, which is what autograd does with the
     `ss = rr[..., :1]` slice of deepmd/pt/model/descriptor/se_a.py:818-820)."""
@@ -324,10 +353,10 @@ def tabulate_sections_grad(tables, infos, em, dy, sec, last_layer_size, is_sorte
         ti = _info_host(info, em.dtype)
         off = int(sec[t])
         base = em.data_ptr() + off * 4 * esz
-        lib().call("tabulate_fusion_se_a_grad_ex_" + s, None,
-                   C.c_void_p(g_em.data_ptr() + off * 4 * esz), None, _p(_c(table)), C.c_void_p(ti.data_ptr()),
-                   C.c_void_p(base), nnei * 4, 4, C.c_void_p(base), nnei * 4, None, _p(dy), nloc, n_t, M,
-                   int(bool(is_sorted)), _stream(dev))
+        lib().call("tabulate_fusion_se_a_grad_fx_" + s, None,
+                   C.c_void_p(g_em.data_ptr() + off * 4 * esz), _p(_c(table)), C.c_void_p(ti.data_ptr()),
+                   C.c_void_p(base), nnei * 4, 4, C.c_void_p(base), nnei * 4, _p(dy), nloc, n_t, M,
+                   int(bool(is_sorted)), 0 if flags is None else int(flags[t]), _stream(dev))
     return g_em
 
 
@@ -527,13 +556,14 @@ def se_a_descriptor_grad(dD, gr, axis, scale, rows=None, out=None):
 
 
 def tabulate_sections_desc(tables, infos, em, sec, last_layer_size, axis, scale, desc_row=None, mode=1, nslice=7,
-                           pad_rows=0, is_sorted=True):
+                           pad_rows=0, is_sorted=True, flags=None):
     """tabulate_sections_fwd with the se_e2_a descriptor contraction fused into the last section's
     epilogue (dpb200_tabulate_fusion_se_a_desc).  Returns (out [nloc,4,M], desc, row_exp|None):
       mode 1            desc = D [nloc+pad, M*axis] in em.dtype;
       mode 2, float64   desc = int8 [nloc+pad, nslice*M*axis] signed 7-bit slices, row_exp int32 [nloc+pad];
       mode 2, float32   desc = float32 [nloc+pad, 2*M*axis] = TF32 head | tail.
-    Row desc_row[i] (int32; None: i) belongs to atom i; `pad_rows` extra zero rows are appended."""
+    Row desc_row[i] (int32; None: i) belongs to atom i; `pad_rows` extra zero rows are appended.
+    flags: per-table DPB200_TAB_COMPRESSED_COEF words from `compressed_coef_flags` (None: full fp64 coefficients)."""
     dev = _need_cuda(("em", em), ("desc_row", desc_row))
     s = _suffix(em)
     em = _c(em)
@@ -567,13 +597,15 @@ def tabulate_sections_desc(tables, infos, em, sec, last_layer_size, axis, scale,
         ti = _info_host(infos[t], em.dtype)
         base = C.c_void_p(em.data_ptr() + int(sec[t]) * 4 * esz)
         acc = 0 if n_done == 0 else 1
+        fl = 0 if flags is None else int(flags[t])
         if t != live[-1]:
-            lib().call("tabulate_fusion_se_a_ex_" + s, _p(out), _p(_c(tables[t])), C.c_void_p(ti.data_ptr()), base,
-                       nnei * 4, 4, base, nnei * 4, None, nloc, n_t, M, int(bool(is_sorted)), acc, _stream(dev))
+            lib().call("tabulate_fusion_se_a_desc_" + s, _p(out), _p(_c(tables[t])), C.c_void_p(ti.data_ptr()), base,
+                       nnei * 4, 4, base, nnei * 4, nloc, n_t, M, int(bool(is_sorted)), acc, axis, float(scale),
+                       None, 0, None, 0, 0, None, fl, _stream(dev))
         else:
             lib().call("tabulate_fusion_se_a_desc_" + s, _p(out), _p(_c(tables[t])), C.c_void_p(ti.data_ptr()), base,
                        nnei * 4, 4, base, nnei * 4, nloc, n_t, M, int(bool(is_sorted)), acc, axis, float(scale),
-                       _p(desc_row), int(mode), _p(desc), int(desc.shape[1]), int(nslice), _p(row_exp), _stream(dev))
+                       _p(desc_row), int(mode), _p(desc), int(desc.shape[1]), int(nslice), _p(row_exp), fl, _stream(dev))
     return out, desc, row_exp
 
 

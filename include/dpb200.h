@@ -36,6 +36,8 @@ extern "C" {
 #define DPB200_ERR_OOM (-3)            /* maps to deepmd::deepmd_exception_oom (errors.h:17-22) */
 #define DPB200_ERR_NLIST_CAPACITY (-4) /* maps to deepmd_exception_nlist_capacity (errors.h:30-33) */
 
+#define DPB200_TAB_COMPRESSED_COEF 1   /* flags bit of the dpb200_tabulate_fusion_se_a_desc / _grad_fx entry points */
+
 #define DPB200_MAX_NBOR_SIZE 4096 /* GPU_MAX_NBOR_SIZE, source/lib/include/gpu_cuda.h:20 */
 #define DPB200_MAX_TYPES 128      /* 7 type bits in the sort key (same limit as prod_env_mat.cu:83-104) */
 #define DPB200_MAX_NALL (1 << 26) /* 26 index bits in the sort key (reference: 1<<24) */
@@ -132,16 +134,29 @@ DPB200_DECL_ENV(f32, float)
    * epilogue (deepmd/pt/model/descriptor/se_a.py:843-850): after out[i] is complete,              \
    * D = (scale*out[i])^T (scale*out[i])[:, :axis] is written to row desc_row[i] (NULL: i) of      \
    * `desc` (row stride desc_ld elements), in the operand format of the fitting net's first GEMM:  \
+   *   desc_mode 0: no descriptor (plain `_ex` forward, but honouring `flags`);                     \
    *   desc_mode 1: FP [M*axis];                                                                    \
    *   desc_mode 2, f64: int8 [nslice][M*axis] signed 7-bit slices (most significant first) of     \
    *     D * 2^-row_exp[row] (needs axis == 16);  f32: float [2][M*axis] = TF32 head | tail.        \
-   * M <= 128, axis <= 32, desc 16-byte aligned. */                                                \
+   * M <= 128, axis <= 32, desc 16-byte aligned.                                                   \
+   * flags: DPB200_TAB_COMPRESSED_COEF (f64 only, ignored for f32) = the caller has checked that    \
+   * for THIS table a3, a4 may be rounded to fp32, a5 to fp16 and a2 to 36 mantissa bits (true for  \
+   * dp-compress tables with stride 0.01: error < 1e-12 relative; see csrc/tabulate.cu pack_cm).    \
+   * Bits 8..15 of flags: signed exponent k, a5 is stored as half(a5 * 2^k) (choose k so that       \
+   * max|a5| * 2^k ~ 2^14).  The kernels then stream 32 instead of 48 bytes per coefficient set.    \
+   * The reference-facing                                                                           \
+   * entry points above never do this. */                                                          \
   int dpb200_tabulate_fusion_se_a_desc_##SUF(                                                      \
       FP* out, const FP* table, const FP* table_info, const FP* em_x, long long ldx_i, int ldx_j,  \
       const FP* em, long long ldem_i, int nloc, int nnei, int last_layer_size, int is_sorted,      \
       int accumulate, int axis, double scale, const int* desc_row /*nullable*/, int desc_mode,     \
-      void* desc, long long desc_ld, int nslice, int* row_exp /*f64 mode 2*/,                      \
-      dpb200_stream_t stream);
+      void* desc, long long desc_ld, int nslice, int* row_exp /*f64 mode 2*/, int flags,           \
+      dpb200_stream_t stream);                                                                     \
+  /* grad_ex (plain se_a, dy_dem_x may be NULL) with `flags` */                                    \
+  int dpb200_tabulate_fusion_se_a_grad_fx_##SUF(                                                   \
+      FP* dy_dem_x, FP* dy_dem, const FP* table, const FP* table_info, const FP* em_x,             \
+      long long ldx_i, int ldx_j, const FP* em, long long ldem_i, const FP* dy, int nloc,          \
+      int nnei, int last_layer_size, int is_sorted, int flags, dpb200_stream_t stream);
 DPB200_DECL_TAB(f64, double)
 DPB200_DECL_TAB(f32, float)
 #undef DPB200_DECL_TAB

@@ -692,3 +692,45 @@ def test_fitting_split_matches_plain(ops, dtype):
         assert ((e1.double() - ref_e).abs().max() / ref_e.abs().max()).item() <= tol_e
     assert ((e1.double() - ref_e.double()).abs().max() / ref_e.abs().max()).item() <= tol
     assert ((g1.double() - ref_g.double()).abs().max() / ref_g.abs().max()).item() <= tol
+
+
+def test_compressed_coefficients_match_full_table(ops):
+    """DPB200_TAB_COMPRESSED_COEF (fp32 a3/a4, fp16 a5 on the stride-0 rows of a dp-compress table) against the
+    full fp64 table on the same inputs, forward + fused descriptor and backward; inputs reach the stride-1
+    (never compressed) rows and both extrapolation branches as well."""
+    import __graft_entry__ as g
+
+    g.load_package()
+    from deepmd_kit_b200.model import SeAConfig, SeAModel
+
+    cfg = SeAConfig()
+    model = SeAModel(cfg, torch.float64, DEV)
+    assert model.coef_flags is not None and all(f & 1 for f in model.coef_flags)
+    rng = np.random.default_rng(3)
+    nloc, nnei = 301, cfg.nnei
+    em = rng.normal(scale=0.4, size=(nloc, nnei, 4))
+    x = np.sort(rng.uniform(-0.9, 4.0, size=(nloc, nnei)), axis=1)[:, ::-1].copy()
+    x[:7, :5] = rng.uniform(9.5, 40.0, size=(7, 5))   # stride-1 rows
+    x[7:9, :3] = 50.0                                  # beyond max
+    x[9:11, -3:] = -1.5                                # below lower
+    em[:, :, 0] = x
+    for i in range(nloc):  # trailing padding in both sections
+        for a, b in ((0, 46), (46, 138)):
+            k = int(rng.integers(0, (b - a) // 2))
+            if k:
+                em[i, b - k:b, 0] = -0.36
+                em[i, b - k:b, 1:] = 0
+    em_t = T(em.reshape(nloc, -1))
+    inv = 1.0 / nnei
+    out0, d0, e0 = ops.tabulate_sections_desc(model.tables, model.infos, em_t, cfg.sec, model.M, 16, inv, mode=2, nslice=6)
+    out1, d1, e1 = ops.tabulate_sections_desc(model.tables, model.infos, em_t, cfg.sec, model.M, 16, inv, mode=2, nslice=6,
+                                              flags=model.coef_flags)
+    assert ((out1 - out0).abs().max() / out0.abs().max()).item() < 1e-11
+    assert torch.equal(e0, e1) and (d1.to(torch.int32) - d0.to(torch.int32)).abs().max().item() <= 64
+    dy = torch.randn_like(out0)
+    g0 = ops.tabulate_sections_grad(model.tables, model.infos, em_t, dy, cfg.sec, model.M)
+    g1 = ops.tabulate_sections_grad(model.tables, model.infos, em_t, dy, cfg.sec, model.M, flags=model.coef_flags)
+    assert ((g1 - g0).abs().max() / g0.abs().max()).item() < 1e-11
+    # a table that does not qualify is refused by the gate
+    tab = random_table(57, 100, rng, np.float64)
+    assert ops.compressed_coef_flags(torch.as_tensor(tab), np.array([-0.4, 2.0, 6.0, 0.05, 0.5, -1.0])) == 0
