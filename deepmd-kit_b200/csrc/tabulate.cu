@@ -28,8 +28,6 @@
 //     reference does five full warp reductions per neighbour).
 // Not a port of source/lib/src/gpu/tabulate.cu (one thread per channel, stride-6 scalar loads, all
 // coefficients from global memory, serial padding search by thread 0).
-#include <cuda_fp16.h>
-
 #include <cmath>
 #include <cstdlib>
 #include <type_traits>
@@ -62,7 +60,6 @@ struct TabParams {
   int hot_pad;    // bytes of padding after every hot row (tensor-core forward: 32, see k_tab_fwd_mma)
   int nblk;       // 16-byte blocks per (row, channel): 3 (coefficient pairs) or 2 (compressed, see k_table_relayout_cm)
   const FP* T3;   // compressed mode: the full pair table as well (stride-1 "coarse" rows are never compressed)
-  float a5_mul, a5_inv;  // compressed layout: a5 is stored as half(a5 * a5_mul); a5_inv = 1 / a5_mul (powers of two)
   // forward / second order
   FP* out;  // [nloc][4][M]
   const FP* dz_x;
@@ -165,30 +162,35 @@ __global__ void k_table_relayout(FP* __restrict__ T, const FP* __restrict__ tabl
 // Compressed coefficients (fp64, opt-in by the caller who has validated its table: DPB200_TAB_COMPRESSED_COEF).
 // The table kernels are bound by the L1/shared data pipe (48 B of coefficients per evaluation), and for a
 // dp-compress table the high-order terms are tiny: a3 x^3 <= 5e-8 |a0|, a4 x^4 <= 2e-10, a5 x^5 <= 5e-13 on the
-// stride-0.01 rows.  So a3 and a4 are stored as fp32 and a5 as fp16 in the 16 low mantissa bits of a2 (which keeps
+// stride-0.01 rows.  So a3 and a4 are stored as fp32 and a5 as bf16 in the 16 low mantissa bits of a2 (which keeps
 // 36 bits: 1.5e-11 relative on a term that is <= 1e-5 |a0|):  32 B per (row, channel) = two 16-byte blocks
-//   block 0 = {a0, a1}   block 1 = {a2 | half(a5), (float a3, float a4)}
+//   block 0 = {a0, a1}   block 1 = {a2 | bf16(a5), (float a3, float a4)}
 // Errors against the fp64 table: < 1e-14 |a0| on the value and < 1e-12 |a1| on the derivative for the water
 // table (model.py computes the bound for the actual table and only then sets the flag).
-__device__ __forceinline__ double2 pack_cm(double a2, double a3, double a4, double a5, float a5_mul) {
-  const unsigned short h5 = __half_as_ushort(__float2half_rn((float)(a5 * (double)a5_mul)));
-  const unsigned long long b2 = ((unsigned long long)__double_as_longlong(a2) & ~0xffffull) | (unsigned long long)h5;
+__device__ __forceinline__ double2 pack_cm(double a2, double a3, double a4, double a5) {
+  const unsigned f5 = __float_as_uint((float)a5);
+  const unsigned h5 = (f5 + 0x7fffu + ((f5 >> 16) & 1u)) >> 16;  // bf16, round to nearest even
+  const unsigned long long b2 = ((unsigned long long)__double_as_longlong(a2) & ~0xffffull) | (unsigned long long)(h5 & 0xffffu);
   const unsigned long long b34 = (unsigned long long)__float_as_uint((float)a3) |
                                  ((unsigned long long)__float_as_uint((float)a4) << 32);
   return make_double2(__longlong_as_double((long long)b2), __longlong_as_double((long long)b34));
 }
 __device__ __forceinline__ void unpack_cm(const double2 v, double& a2, float& a3, float& a4, float& a5) {
-  const unsigned long long b2 = (unsigned long long)__double_as_longlong(v.x);
-  const unsigned long long b34 = (unsigned long long)__double_as_longlong(v.y);
   a2 = v.x;  // the 16 borrowed bits are noise at 2^-36 relative
-  a5 = __half2float(__ushort_as_half((unsigned short)(b2 & 0xffffull)));
-  a3 = __uint_as_float((unsigned)(b34 & 0xffffffffull));
-  a4 = __uint_as_float((unsigned)(b34 >> 32));
+  a5 = __uint_as_float((unsigned)__double2loint(v.x) << 16);
+  a3 = __uint_as_float((unsigned)__double2loint(v.y));
+  a4 = __uint_as_float((unsigned)__double2hiint(v.y));
+}
+// fp32 -> fp64 with integer instructions (the F2F conversion pipe is slow): exact for normal numbers; zeros and
+// denormals come out as values below 2^-126, which is noise for a Horner partial sum
+__device__ __forceinline__ double f2d_bits(float f) {
+  const unsigned u = __float_as_uint(f);
+  const unsigned hi = (u & 0x80000000u) | (((u >> 3) & 0x0fffffffu) + 0x38000000u);
+  return __hiloint2double((int)hi, (int)(u << 29));
 }
 
 // [row][M][6] -> [row][2][M] blocks
-__global__ void k_table_relayout_cm(double2* __restrict__ T, const double* __restrict__ table, long long nrow, int M,
-                                    float a5_mul) {
+__global__ void k_table_relayout_cm(double2* __restrict__ T, const double* __restrict__ table, long long nrow, int M) {
   const long long n = nrow * (long long)M;
   for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < n;
        e += (long long)gridDim.x * blockDim.x) {
@@ -196,46 +198,9 @@ __global__ void k_table_relayout_cm(double2* __restrict__ T, const double* __res
     const int k = (int)(e - r * M);
     const double* a = table + e * 6;
     T[(r * 2 + 0) * M + k] = make_double2(a[0], a[1]);
-    T[(r * 2 + 1) * M + k] = pack_cm(a[2], a[3], a[4], a[5], a5_mul);
+    T[(r * 2 + 1) * M + k] = pack_cm(a[2], a[3], a[4], a[5]);
   }
 }
-
-// fetch_row for the compressed layout: the coefficients are expanded to fp64 registers, the rest of the
-// kernel is unchanged (8 instead of 12 sixteen-byte requests per lane and row).
-template <int NC>
-__device__ __forceinline__ void fetch_row_cm(double (&a)[NC][6], const double* __restrict__ hot,
-                                             const double* __restrict__ T, int row, int r0, int H, int M,
-                                             const int (&ob)[NC], float a5_inv) {
-  const unsigned rel = (unsigned)(row - r0);
-  const unsigned qb = (unsigned)M * 16u;
-  const bool inwin = rel < (unsigned)H;
-  const char* b0 = inwin ? reinterpret_cast<const char*>(hot) + rel * (2u * qb)
-                         : reinterpret_cast<const char*>(T) + (long long)row * (2u * qb);
-  if (inwin) {
-#pragma unroll
-    for (int c = 0; c < NC; ++c) {
-      const double2 u = *reinterpret_cast<const double2*>(b0 + ob[c]);
-      const double2 v = *reinterpret_cast<const double2*>(b0 + qb + ob[c]);
-      float a3, a4, a5;
-      a[c][0] = u.x, a[c][1] = u.y;
-      unpack_cm(v, a[c][2], a3, a4, a5);
-      a[c][3] = (double)a3, a[c][4] = (double)a4, a[c][5] = (double)(a5 * a5_inv);
-    }
-  } else {
-#pragma unroll
-    for (int c = 0; c < NC; ++c) {
-      const double2 u = __ldg(reinterpret_cast<const double2*>(b0 + ob[c]));
-      const double2 v = __ldg(reinterpret_cast<const double2*>(b0 + qb + ob[c]));
-      float a3, a4, a5;
-      a[c][0] = u.x, a[c][1] = u.y;
-      unpack_cm(v, a[c][2], a3, a4, a5);
-      a[c][3] = (double)a3, a[c][4] = (double)a4, a[c][5] = (double)(a5 * a5_inv);
-    }
-  }
-}
-template <int NC>
-__device__ __forceinline__ void fetch_row_cm(float (&)[NC][6], const float*, const float*, int, int, int, int,
-                                             const int (&)[NC], float) {}
 
 // Coefficients of one table row for the NC channels of this lane.  ob[c] = byte offset of the lane's
 // channel inside one coefficient-pair block (clamped to channel M-1 so that every lane always loads:
@@ -541,7 +506,7 @@ extern __shared__ __align__(16) unsigned char tab_smem[];
 // grid (x: persistent over atoms, y: block of 32*NC channels); block = nw warps.
 // smem: hot[H][3][M] pairs | Rec[nw][32] | RecGG[nw][32] (GG only)
 // ------------------------------------------------------------------------------------------
-template <typename FP, int NC, bool TWO, bool GG, bool DESC = false, bool CM = false>
+template <typename FP, int NC, bool TWO, bool GG, bool DESC = false>
 __global__ void __launch_bounds__(512) k_tab_fwd(const __grid_constant__ TabParams<FP> p) {
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
@@ -601,12 +566,7 @@ __global__ void __launch_bounds__(512) k_tab_fwd(const __grid_constant__ TabPara
         const int row = r.idx;
         if (row != cur_row) {  // warp-uniform
           cur_row = row;
-          if (CM && row < p.first)
-            fetch_row_cm<NC>(a, hot, p.T, row, r0, p.H, p.M, ob, p.a5_inv);
-          else if (CM)
-            fetch_row<FP, NC>(a, hot, p.T3, row, 0, 0, p.M, ob);  // coarse row: full precision from L2
-          else
-            fetch_row<FP, NC>(a, hot, p.T, row, r0, p.H, p.M, ob);
+          fetch_row<FP, NC>(a, hot, p.T, row, r0, p.H, p.M, ob);
         }
         const FP xx = r.xx;
         const FP e0 = r.e[0], e1 = r.e[1], e2 = r.e[2], e3 = r.e[3];
@@ -625,12 +585,7 @@ __global__ void __launch_bounds__(512) k_tab_fwd(const __grid_constant__ TabPara
         const int row = r.idx;
         if (row != cur_row) {  // warp-uniform
           cur_row = row;
-          if (CM && row < p.first)
-            fetch_row_cm<NC>(a, hot, p.T, row, r0, p.H, p.M, ob, p.a5_inv);
-          else if (CM)
-            fetch_row<FP, NC>(a, hot, p.T3, row, 0, 0, p.M, ob);  // coarse row: full precision from L2
-          else
-            fetch_row<FP, NC>(a, hot, p.T, row, r0, p.H, p.M, ob);
+          fetch_row<FP, NC>(a, hot, p.T, row, r0, p.H, p.M, ob);
         }
         const FP xx = r.xx;
         const FP dl = r.delta;
@@ -1076,7 +1031,6 @@ __global__ void __launch_bounds__(MAXT) k_tab_grad_mma(const __grid_constant__ T
       const Rec<FP>& r = rec[live ? nb : nproc - 1];
       const FP xx = r.xx;
       const float xf = (float)xx;
-      const float xs = xf * p.a5_inv;  // a5 is stored pre-multiplied by a power of two (fp16 range)
       const FP dl = r.delta;
       const unsigned rel = (unsigned)(r.idx - r0);
       const bool inwin = rel < (unsigned)p.H;
@@ -1092,14 +1046,14 @@ __global__ void __launch_bounds__(MAXT) k_tab_grad_mma(const __grid_constant__ T
       double a2;                                                                              \
       float a3, a4, a5;                                                                       \
       unpack_cm(v, a2, a3, a4, a5);                                                           \
-      const float f4 = fmaf(a5, xs, a4);                                                      \
+      const float f4 = fmaf(a5, xf, a4);                                                      \
       const float f3 = fmaf(f4, xf, a3);                                                      \
-      const float e4 = fmaf(a5, xs, f4);                                                      \
+      const float e4 = fmaf(a5, xf, f4);                                                      \
       const float e3 = fmaf(e4, xf, f3);                                                      \
-      const FP b2 = a2 + (FP)f3 * xx;                                                         \
+      const FP b2 = a2 + f2d_bits(f3) * xx;                                                      \
       const FP b1 = u.y + b2 * xx;                                                            \
       g = u.x + b1 * xx;                                                                      \
-      const FP d2 = b2 + (FP)e3 * xx;                                                         \
+      const FP d2 = b2 + f2d_bits(e3) * xx;                                                      \
       gd = b1 + d2 * xx;                                                                      \
     } else {                                                                                  \
       const double2 u = *reinterpret_cast<const double2*>((BASE) + off);                      \
@@ -1284,7 +1238,7 @@ inline int prepare_table_cm(TabParams<double>& p, double** scratch, cudaStream_t
   int grid = ceil_div((long long)p.nrow * p.M, 256);
   const int cap = sm_count() * 8;
   if (grid > cap) grid = cap;
-  k_table_relayout_cm<<<grid, 256, 0, st>>>(reinterpret_cast<double2*>(*scratch), p.table, p.nrow, p.M, p.a5_mul);
+  k_table_relayout_cm<<<grid, 256, 0, st>>>(reinterpret_cast<double2*>(*scratch), p.table, p.nrow, p.M);
   p.T = *scratch;
   return DPB200_OK;
 }
@@ -1301,14 +1255,6 @@ inline int prepare_table_full(TabParams<double>& p, double** scratch3, cudaStrea
 }
 inline int prepare_table_full(TabParams<float>&, float**, cudaStream_t) { return DPB200_ERR_INVALID; }
 inline int prepare_table_cm(TabParams<float>&, float**, cudaStream_t) { return DPB200_ERR_INVALID; }
-
-// bits 8..15 of `flags`: signed power-of-two exponent k, a5 is stored as half(a5 * 2^k)
-template <typename FP>
-void set_a5_scale(TabParams<FP>& p, int flags) {
-  const int k = (int)(signed char)((flags >> 8) & 0xff);
-  p.a5_mul = std::ldexp(1.0f, k);
-  p.a5_inv = std::ldexp(1.0f, -k);
-}
 
 // hot rows / shared-memory sizing for `blocks` 16-byte blocks per (row, channel)
 template <typename FP>
@@ -1337,8 +1283,11 @@ int launch_fwd(FP* out, const FP* table, const FP* info, const FP* em_x, long lo
   DPB_REQUIRE(nloc >= 0 && nnei >= 0 && M >= 0, "tabulate: negative size");
   if (nloc == 0 || M == 0) return DPB200_OK;
   DPB_REQUIRE(out != nullptr, "tabulate: out is null");
-  // compressed coefficients: fp64, plain se_a forward, SIMT kernel
-  const bool cm = (flags & DPB200_TAB_COMPRESSED_COEF) && sizeof(FP) == 8 && !GG && two == nullptr && !use_mma_fwd();
+  // DPB200_TAB_COMPRESSED_COEF is honoured by the backward only: the SIMT forward keeps a row's coefficients in
+  // registers across neighbours, so it would have to expand them to fp64 at fetch time (12 conversions per
+  // row) -- measured 8 % slower than the full table (gpurun_out, op_bench: 7.65 vs 7.06 ms at 332 k atoms).
+  (void)flags;
+  const bool cm = false;
   if (da) {
     const bool plain = !GG && two == nullptr && nnei > 0;
     DPB_REQUIRE(plain, "tabulate+descriptor: plain se_a forward with nnei > 0 only");
@@ -1391,7 +1340,6 @@ int launch_fwd(FP* out, const FP* table, const FP* info, const FP* em_x, long lo
   const size_t rec_bytes = (size_t)nw * 32 * (sizeof(Rec<FP>) + (GG ? sizeof(RecGG<FP>) : 0));
   p.Mc = M;
   p.nblk = cm ? 2 : 3;
-  set_a5_scale(p, flags);
   size_hot_window(p, M, rec_bytes, p.nblk);
   const size_t smem = (size_t)p.hot_elems * sizeof(FP) + rec_bytes;
   FP* scratch = nullptr;
@@ -1451,15 +1399,7 @@ int launch_fwd(FP* out, const FP* table, const FP* info, const FP* em_x, long lo
   }
 #define DPB_LAUNCH_FWD(NC)                                                                      \
   do {                                                                                          \
-    if (da && cm) {                                                                             \
-      auto kern = k_tab_fwd<FP, NC, false, false, true, true>;                                  \
-      e1 = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);  \
-      if (e1 == cudaSuccess) kern<<<grid, nw * 32, smem, st>>>(p);                              \
-    } else if (cm) {                                                                            \
-      auto kern = k_tab_fwd<FP, NC, false, false, false, true>;                                 \
-      e1 = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);  \
-      if (e1 == cudaSuccess) kern<<<grid, nw * 32, smem, st>>>(p);                              \
-    } else if (da) {                                                                            \
+    if (da) {                                                                            \
       auto kern = k_tab_fwd<FP, NC, false, false, true>;                                        \
       e1 = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);  \
       if (e1 == cudaSuccess) kern<<<grid, nw * 32, smem, st>>>(p);                              \
@@ -1516,7 +1456,6 @@ int launch_grad(FP* dy_dem_x, FP* dy_dem, FP* dy_dtwo, const FP* table, const FP
   const bool cm = mma_ok && (flags & DPB200_TAB_COMPRESSED_COEF) && grad_variant() == 1;
   p.Mc = M;
   p.nblk = cm ? 2 : 3;
-  set_a5_scale(p, flags);
   size_hot_window(p, M, rec_bytes, p.nblk);
   const size_t smem = (size_t)p.hot_elems * sizeof(FP) + rec_bytes;
   FP* scratch = nullptr;

@@ -314,7 +314,9 @@ class SeAModel:
         # the on-chip coefficient stream; for a dp-compress table the high-order terms tolerate fp32 / fp16 storage
         # at the 1e-12 level.  Checked per table here, on the host, once.
         self.coef_flags = None
-        if dtype == torch.float64 and self.device.type == "cuda":
+        import os
+
+        if dtype == torch.float64 and self.device.type == "cuda" and os.environ.get("DPB200_TAB_COMPRESS", "1") != "0":
             fl = [ops.compressed_coef_flags(t, i) for t, i in zip(self.tables64, infos)]
             if all(fl):
                 self.coef_flags = fl

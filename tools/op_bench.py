@@ -53,6 +53,12 @@ timeit("tabulate_sections_fwd", lambda: ops.tabulate_sections_fwd(model.tables, 
 dy = torch.randn_like(xyz)
 timeit("tabulate_sections_grad", lambda: ops.tabulate_sections_grad(model.tables, model.infos, em, dy, cfg.sec, M),
        flops_per_atom=36 * (nreal + 2) * M)
+timeit("tabulate_sections_desc(split)", lambda: ops.tabulate_sections_desc(
+    model.tables, model.infos, em, cfg.sec, M, cfg.axis_neuron, 1.0 / nnei, mode=2, nslice=model.nslice, pad_rows=32,
+    flags=model.coef_flags), flops_per_atom=18 * (nreal + 2) * M)
+if getattr(model, "coef_flags", None):
+    timeit("tabulate_sections_grad(cm)", lambda: ops.tabulate_sections_grad(
+        model.tables, model.infos, em, dy, cfg.sec, M, flags=model.coef_flags), flops_per_atom=36 * (nreal + 2) * M)
 if os.environ.get("OPB_ONLY") == "tab":
     sys.exit(0)
 nd = ops.tabulate_sections_grad(model.tables, model.infos, em, dy, cfg.sec, M)
@@ -73,7 +79,7 @@ if model.use_split:
     inv = 1.0 / nnei
     timeit("tabulate_sections_desc(split)", lambda: ops.tabulate_sections_desc(
         model.tables, model.infos, em, cfg.sec, M, cfg.axis_neuron, inv, desc_row=st.type_inv, mode=2,
-        nslice=model.nslice, pad_rows=32), flops_per_atom=18 * (nreal + 2) * M)
+        nslice=model.nslice, pad_rows=32, flags=model.coef_flags), flops_per_atom=18 * (nreal + 2) * M)
     _, desc, rexp = ops.tabulate_sections_desc(model.tables, model.infos, em, cfg.sec, M, cfg.axis_neuron, inv,
                                                desc_row=st.type_inv, mode=2, nslice=model.nslice, pad_rows=32)
     timeit("fit fwd+bwd split, 1 chunk", lambda: model.fit[0].forward_backward_split(
