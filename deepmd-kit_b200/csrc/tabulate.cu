@@ -28,6 +28,8 @@
 //     reference does five full warp reductions per neighbour).
 // Not a port of source/lib/src/gpu/tabulate.cu (one thread per channel, stride-6 scalar loads, all
 // coefficients from global memory, serial padding search by thread 0).
+#include <cuda_fp16.h>
+
 #include <cmath>
 #include <cstdlib>
 #include <type_traits>
@@ -60,6 +62,7 @@ struct TabParams {
   int hot_pad;    // bytes of padding after every hot row (tensor-core forward: 32, see k_tab_fwd_mma)
   int nblk;       // 16-byte blocks per (row, channel): 3 (coefficient pairs) or 2 (compressed, see k_table_relayout_cm)
   const FP* T3;   // compressed mode: the full pair table as well (stride-1 "coarse" rows are never compressed)
+  float a5_mul, a5_inv;  // compressed layout: a5 is stored as half(a5 * a5_mul); a5_inv = 1 / a5_mul (powers of two)
   // forward / second order
   FP* out;  // [nloc][4][M]
   const FP* dz_x;
@@ -162,35 +165,32 @@ __global__ void k_table_relayout(FP* __restrict__ T, const FP* __restrict__ tabl
 // Compressed coefficients (fp64, opt-in by the caller who has validated its table: DPB200_TAB_COMPRESSED_COEF).
 // The table kernels are bound by the L1/shared data pipe (48 B of coefficients per evaluation), and for a
 // dp-compress table the high-order terms are tiny: a3 x^3 <= 5e-8 |a0|, a4 x^4 <= 2e-10, a5 x^5 <= 5e-13 on the
-// stride-0.01 rows.  So a3 and a4 are stored as fp32 and a5 as bf16 in the 16 low mantissa bits of a2 (which keeps
+// stride-0.01 rows.  So a3 and a4 are stored as fp32 and a5 as fp16 in the 16 low mantissa bits of a2 (which keeps
 // 36 bits: 1.5e-11 relative on a term that is <= 1e-5 |a0|):  32 B per (row, channel) = two 16-byte blocks
-//   block 0 = {a0, a1}   block 1 = {a2 | bf16(a5), (float a3, float a4)}
-// Errors against the fp64 table: < 1e-14 |a0| on the value and < 1e-12 |a1| on the derivative for the water
-// table (model.py computes the bound for the actual table and only then sets the flag).
-__device__ __forceinline__ double2 pack_cm(double a2, double a3, double a4, double a5) {
-  const unsigned f5 = __float_as_uint((float)a5);
-  const unsigned h5 = (f5 + 0x7fffu + ((f5 >> 16) & 1u)) >> 16;  // bf16, round to nearest even
-  const unsigned long long b2 = ((unsigned long long)__double_as_longlong(a2) & ~0xffffull) | (unsigned long long)(h5 & 0xffffu);
+//   block 0 = {a0, a1}   block 1 = {a2 | half(a5), (float a3, float a4)}
+// Errors against the fp64 table: < 1e-14 |a0| on the value and < 3e-12 |a1| on the derivative for the water
+// table (ops.compressed_coef_flags computes the bound for the actual table and only then sets the flag).
+// Unpacking stays off the integer ALU (the kernel is sensitive to it: a bf16 a5 unpacked with one shift, or
+// widening fp32 -> fp64 with integer instructions, measured 8 % and 24 % slower than the F2F conversions).
+__device__ __forceinline__ double2 pack_cm(double a2, double a3, double a4, double a5, float a5_mul) {
+  const unsigned short h5 = __half_as_ushort(__float2half_rn((float)(a5 * (double)a5_mul)));
+  const unsigned long long b2 = ((unsigned long long)__double_as_longlong(a2) & ~0xffffull) | (unsigned long long)h5;
   const unsigned long long b34 = (unsigned long long)__float_as_uint((float)a3) |
                                  ((unsigned long long)__float_as_uint((float)a4) << 32);
   return make_double2(__longlong_as_double((long long)b2), __longlong_as_double((long long)b34));
 }
 __device__ __forceinline__ void unpack_cm(const double2 v, double& a2, float& a3, float& a4, float& a5) {
+  const unsigned long long b2 = (unsigned long long)__double_as_longlong(v.x);
+  const unsigned long long b34 = (unsigned long long)__double_as_longlong(v.y);
   a2 = v.x;  // the 16 borrowed bits are noise at 2^-36 relative
-  a5 = __uint_as_float((unsigned)__double2loint(v.x) << 16);
-  a3 = __uint_as_float((unsigned)__double2loint(v.y));
-  a4 = __uint_as_float((unsigned)__double2hiint(v.y));
-}
-// fp32 -> fp64 with integer instructions (the F2F conversion pipe is slow): exact for normal numbers; zeros and
-// denormals come out as values below 2^-126, which is noise for a Horner partial sum
-__device__ __forceinline__ double f2d_bits(float f) {
-  const unsigned u = __float_as_uint(f);
-  const unsigned hi = (u & 0x80000000u) | (((u >> 3) & 0x0fffffffu) + 0x38000000u);
-  return __hiloint2double((int)hi, (int)(u << 29));
+  a5 = __half2float(__ushort_as_half((unsigned short)(b2 & 0xffffull)));
+  a3 = __uint_as_float((unsigned)(b34 & 0xffffffffull));
+  a4 = __uint_as_float((unsigned)(b34 >> 32));
 }
 
 // [row][M][6] -> [row][2][M] blocks
-__global__ void k_table_relayout_cm(double2* __restrict__ T, const double* __restrict__ table, long long nrow, int M) {
+__global__ void k_table_relayout_cm(double2* __restrict__ T, const double* __restrict__ table, long long nrow, int M,
+                                    float a5_mul) {
   const long long n = nrow * (long long)M;
   for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < n;
        e += (long long)gridDim.x * blockDim.x) {
@@ -198,7 +198,7 @@ __global__ void k_table_relayout_cm(double2* __restrict__ T, const double* __res
     const int k = (int)(e - r * M);
     const double* a = table + e * 6;
     T[(r * 2 + 0) * M + k] = make_double2(a[0], a[1]);
-    T[(r * 2 + 1) * M + k] = pack_cm(a[2], a[3], a[4], a[5]);
+    T[(r * 2 + 1) * M + k] = pack_cm(a[2], a[3], a[4], a[5], a5_mul);
   }
 }
 
@@ -980,7 +980,10 @@ __global__ void __launch_bounds__(MAXT) k_tab_grad_mma(const __grid_constant__ T
   FP* hot = reinterpret_cast<FP*>(tab_smem);
   Rec<FP>* rec = reinterpret_cast<Rec<FP>*>(hot + p.hot_elems) + warp * 32;
   const int M = p.M;
-  FP* dyt = reinterpret_cast<FP*>(reinterpret_cast<Rec<FP>*>(hot + p.hot_elems) + nw * 32) + (BSM ? warp * 4 * M : 0);
+  // per-warp dy tile [5][4*KT]: rows 0..3 = components (channels >= M zero), row 4 = zeros for the lanes that own
+  // the unused B columns 4..7 -- the B fragment load needs no predicate (the kernel is sensitive to ALU work)
+  constexpr int MP = 4 * KT;
+  FP* dyt = reinterpret_cast<FP*>(reinterpret_cast<Rec<FP>*>(hot + p.hot_elems) + nw * 32) + (BSM ? warp * 5 * MP : 0);
   const int r0 = hot_window_start(p);
   preload_hot(hot, p, r0);
   __syncthreads();
@@ -998,14 +1001,21 @@ __global__ void __launch_bounds__(MAXT) k_tab_grad_mma(const __grid_constant__ T
   load_pre(pre, p, i, 0, lane);
   FP last = i < p.nloc ? p.em_x[i * p.ldx_i + (long long)(p.nnei - 1) * p.ldx_j] : (FP)0.;
   FP bf[BSM ? 1 : KT];  // B fragments: dy[m = q][channel 4t + kk] (q < 4), constant per atom
-  const FP* bsrc = dyt + (q & 3) * M + kk;
+  const FP* bsrc = dyt + (q < 4 ? q : 4) * MP + kk;
+  if (BSM) {
+    for (int e = lane; e < 5 * MP; e += 32) dyt[e] = (FP)0.;
+    __syncwarp();
+  }
 
   while (i < p.nloc) {
     if (j0 == 0) {
       const FP* __restrict__ dyi = p.dy + i * 4 * (long long)M;
       if (BSM) {
         __syncwarp();
-        for (int e = lane; e < 4 * M; e += 32) dyt[e] = dyi[e];
+        for (int e = lane; e < 4 * M; e += 32) {
+          const int m = e / M;
+          dyt[m * MP + (e - m * M)] = dyi[e];
+        }
         __syncwarp();
       } else {
 #pragma unroll
@@ -1031,6 +1041,7 @@ __global__ void __launch_bounds__(MAXT) k_tab_grad_mma(const __grid_constant__ T
       const Rec<FP>& r = rec[live ? nb : nproc - 1];
       const FP xx = r.xx;
       const float xf = (float)xx;
+      const float xs = xf * p.a5_inv;  // a5 is stored pre-multiplied by a power of two (fp16 range)
       const FP dl = r.delta;
       const unsigned rel = (unsigned)(r.idx - r0);
       const bool inwin = rel < (unsigned)p.H;
@@ -1046,14 +1057,14 @@ __global__ void __launch_bounds__(MAXT) k_tab_grad_mma(const __grid_constant__ T
       double a2;                                                                              \
       float a3, a4, a5;                                                                       \
       unpack_cm(v, a2, a3, a4, a5);                                                           \
-      const float f4 = fmaf(a5, xf, a4);                                                      \
+      const float f4 = fmaf(a5, xs, a4);                                                      \
       const float f3 = fmaf(f4, xf, a3);                                                      \
-      const float e4 = fmaf(a5, xf, f4);                                                      \
+      const float e4 = fmaf(a5, xs, f4);                                                      \
       const float e3 = fmaf(e4, xf, f3);                                                      \
-      const FP b2 = a2 + f2d_bits(f3) * xx;                                                      \
+      const FP b2 = a2 + (FP)f3 * xx;                                                         \
       const FP b1 = u.y + b2 * xx;                                                            \
       g = u.x + b1 * xx;                                                                      \
-      const FP d2 = b2 + f2d_bits(e3) * xx;                                                      \
+      const FP d2 = b2 + (FP)e3 * xx;                                                         \
       gd = b1 + d2 * xx;                                                                      \
     } else {                                                                                  \
       const double2 u = *reinterpret_cast<const double2*>((BASE) + off);                      \
@@ -1069,8 +1080,8 @@ __global__ void __launch_bounds__(MAXT) k_tab_grad_mma(const __grid_constant__ T
       const FP d2 = b2 + d3 * xx;                                                             \
       gd = b1 + d2 * xx;                                                                      \
     }                                                                                         \
-    if (any_delta) g += gd * dl;                                                              \
-    const FP bt = BSM ? ((q < 4 && 4 * t + kk < M) ? bsrc[4 * t] : (FP)0.) : bf[BSM ? 0 : t]; \
+    g += gd * dl; /* dl == 0 inside [lower, max): one FMA instead of a select pair */         \
+    const FP bt = BSM ? bsrc[4 * t] : bf[BSM ? 0 : t];                                        \
     dmma884(c1a, c1b, g, bt);                                                                 \
     dmma884(c2a, c2b, gd, bt);                                                                \
   }
@@ -1238,7 +1249,7 @@ inline int prepare_table_cm(TabParams<double>& p, double** scratch, cudaStream_t
   int grid = ceil_div((long long)p.nrow * p.M, 256);
   const int cap = sm_count() * 8;
   if (grid > cap) grid = cap;
-  k_table_relayout_cm<<<grid, 256, 0, st>>>(reinterpret_cast<double2*>(*scratch), p.table, p.nrow, p.M);
+  k_table_relayout_cm<<<grid, 256, 0, st>>>(reinterpret_cast<double2*>(*scratch), p.table, p.nrow, p.M, p.a5_mul);
   p.T = *scratch;
   return DPB200_OK;
 }
@@ -1255,6 +1266,14 @@ inline int prepare_table_full(TabParams<double>& p, double** scratch3, cudaStrea
 }
 inline int prepare_table_full(TabParams<float>&, float**, cudaStream_t) { return DPB200_ERR_INVALID; }
 inline int prepare_table_cm(TabParams<float>&, float**, cudaStream_t) { return DPB200_ERR_INVALID; }
+
+// bits 8..15 of `flags`: signed power-of-two exponent k, a5 is stored as half(a5 * 2^k)
+template <typename FP>
+void set_a5_scale(TabParams<FP>& p, int flags) {
+  const int k = (int)(signed char)((flags >> 8) & 0xff);
+  p.a5_mul = std::ldexp(1.0f, k);
+  p.a5_inv = std::ldexp(1.0f, -k);
+}
 
 // hot rows / shared-memory sizing for `blocks` 16-byte blocks per (row, channel)
 template <typename FP>
@@ -1285,7 +1304,7 @@ int launch_fwd(FP* out, const FP* table, const FP* info, const FP* em_x, long lo
   DPB_REQUIRE(out != nullptr, "tabulate: out is null");
   // DPB200_TAB_COMPRESSED_COEF is honoured by the backward only: the SIMT forward keeps a row's coefficients in
   // registers across neighbours, so it would have to expand them to fp64 at fetch time (12 conversions per
-  // row) -- measured 8 % slower than the full table (gpurun_out, op_bench: 7.65 vs 7.06 ms at 332 k atoms).
+  // row) -- measured 8 % slower than the full table (op_bench: 7.65 vs 7.06 ms at 332 k atoms).
   (void)flags;
   const bool cm = false;
   if (da) {
@@ -1340,6 +1359,7 @@ int launch_fwd(FP* out, const FP* table, const FP* info, const FP* em_x, long lo
   const size_t rec_bytes = (size_t)nw * 32 * (sizeof(Rec<FP>) + (GG ? sizeof(RecGG<FP>) : 0));
   p.Mc = M;
   p.nblk = cm ? 2 : 3;
+  set_a5_scale(p, flags);
   size_hot_window(p, M, rec_bytes, p.nblk);
   const size_t smem = (size_t)p.hot_elems * sizeof(FP) + rec_bytes;
   FP* scratch = nullptr;
@@ -1456,6 +1476,7 @@ int launch_grad(FP* dy_dem_x, FP* dy_dem, FP* dy_dtwo, const FP* table, const FP
   const bool cm = mma_ok && (flags & DPB200_TAB_COMPRESSED_COEF) && grad_variant() == 1;
   p.Mc = M;
   p.nblk = cm ? 2 : 3;
+  set_a5_scale(p, flags);
   size_hot_window(p, M, rec_bytes, p.nblk);
   const size_t smem = (size_t)p.hot_elems * sizeof(FP) + rec_bytes;
   FP* scratch = nullptr;
@@ -1476,7 +1497,7 @@ int launch_grad(FP* dy_dem_x, FP* dy_dem, FP* dy_dtwo, const FP* table, const FP
       // variant 0: B fragments in registers, 12 warps; 1: in shared memory, 16 warps; 2: 24 warps
       const int variant = grad_variant();
       const int nwv = variant == 0 ? 12 : (variant == 1 ? 16 : 24);
-      const size_t extra = variant == 0 ? 0 : (size_t)nwv * 4 * M * sizeof(FP);
+      const size_t extra = variant == 0 ? 0 : (size_t)nwv * 5 * (4 * kt) * sizeof(FP);
       const size_t recv = (size_t)nwv * 32 * sizeof(Rec<FP>);
       size_hot_window(p, M, recv + extra, p.nblk);
       if (cm && p.H > p.first) p.H = p.first;  // the window holds compressed (stride-0) rows only

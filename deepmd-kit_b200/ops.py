@@ -308,9 +308,9 @@ def tabulate_sections_fwd(tables, infos, em, sec, last_layer_size, is_sorted=Tru
 def compressed_coef_flags(table: torch.Tensor, info, tol: float = 3e-12) -> int:
     """Host-side gate for DPB200_TAB_COMPRESSED_COEF (include/dpb200.h): returns the flags word for THIS table
     ([nrow, M*6] fp64) if, on every stride-0 row (the stride-1 extrapolation rows are never compressed), storing
-    a3, a4 as fp32, a5 as bf16 and a2 with 36 mantissa bits changes the quintic by less than tol * max|a0| and its
-    derivative by less than tol * max|a1|; else 0.
-    Rounding model: a2 2^-37; a3, a4 2^-25 storage + 2^-24 fp32 Horner step; a5 2^-9."""
+    a3, a4 as fp32, a5 as fp16 (scaled by a power of two) and a2 with 36 mantissa bits changes the quintic by less
+    than tol * max|a0| and its derivative by less than tol * max|a1|; else 0.
+    Rounding model: a2 2^-37; a3, a4 2^-25 storage + 2^-24 fp32 Horner step; a5 2^-11."""
     t = table.detach().to("cpu", torch.float64)
     lower, upper, vmax, s0, s1 = [float(x) for x in info[:5]]
     nrow = t.shape[0]
@@ -319,13 +319,19 @@ def compressed_coef_flags(table: torch.Tensor, info, tol: float = 3e-12) -> int:
     m0, m1 = float(a[..., 0].max()), float(a[..., 1].max())
     if not (m0 > 0 and m1 > 0 and first > 0):
         return 0
-    e2, e34, e5 = 2.0 ** -37, 1.5 * 2.0 ** -24, 2.0 ** -9 + 2.0 ** -23
+    e2, e34, e5 = 2.0 ** -37, 1.5 * 2.0 ** -24, 2.0 ** -11 + 2.0 ** -23
     blk, s = a[:first], s0
     ev = e2 * blk[..., 2] * s ** 2 + e34 * (blk[..., 3] * s ** 3 + blk[..., 4] * s ** 4) + e5 * blk[..., 5] * s ** 5
     ed = 2 * e2 * blk[..., 2] * s + e34 * (3 * blk[..., 3] * s ** 2 + 4 * blk[..., 4] * s ** 3) + e5 * 5 * blk[..., 5] * s ** 4
     if float(ev.max()) > tol * m0 or float(ed.max()) > tol * m1:
         return 0
-    return 1
+    m5 = float(blk[..., 5].max())
+    k = 0
+    if m5 > 0:
+        import math
+
+        k = max(-120, min(120, 13 - int(math.floor(math.log2(m5)))))  # max|a5| * 2^k in [2^13, 2^14)
+    return 1 | ((k & 0xff) << 8)
 
 
 def tabulate_sections_grad(tables, infos, em, dy, sec, last_layer_size, is_sorted=True, flags=None):

@@ -140,10 +140,11 @@ DPB200_DECL_ENV(f32, float)
    *     D * 2^-row_exp[row] (needs axis == 16);  f32: float [2][M*axis] = TF32 head | tail.        \
    * M <= 128, axis <= 32, desc 16-byte aligned.                                                   \
    * flags: DPB200_TAB_COMPRESSED_COEF (f64 only, ignored for f32) = the caller has checked that    \
-   * for THIS table a3, a4 may be rounded to fp32, a5 to bf16 and a2 to 36 mantissa bits (true for  \
+   * for THIS table a3, a4 may be rounded to fp32, a5 to fp16 and a2 to 36 mantissa bits (true for  \
    * dp-compress tables with stride 0.01: error < 1e-12 relative; see csrc/tabulate.cu pack_cm).    \
-   * The backward then streams 32 instead of 48 bytes per coefficient set (the forward ignores the  \
-   * flag: measured slower).  The reference-facing                                                  \
+   * Bits 8..15 of flags: signed exponent k, a5 is stored as half(a5 * 2^k) (choose k so that       \
+   * max|a5| * 2^k ~ 2^14).  The backward then streams 32 instead of 48 bytes per coefficient set  \
+   * (the forward ignores the flag: measured slower).  The reference-facing                         \
    * entry points above never do this. */                                                          \
   int dpb200_tabulate_fusion_se_a_desc_##SUF(                                                      \
       FP* out, const FP* table, const FP* table_info, const FP* em_x, long long ldx_i, int ldx_j,  \
