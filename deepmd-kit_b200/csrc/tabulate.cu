@@ -364,7 +364,7 @@ __device__ __forceinline__ void poly_both(const FP (&a)[6], FP x, FP& g, FP& gd)
 // through HBM as a separate pass.  It is emitted directly in the operand format of the fitting
 // net's first GEMM:
 //   mode 1  D as FP [row][M*axis]
-//   mode 2  fp64: `nslice` signed 8-bit slices of the row's fixed-point image, most significant
+//   mode 2  fp64: `nslice` signed 7-bit slices of the row's fixed-point image, most significant
 //           first, int8 [row][nslice][M*axis] + row_exp[row] (split-integer GEMM on the int8
 //           tensor cores, error-free products, fp64-grade sums);
 //           fp32: TF32 head and tail, float [row][2][M*axis] (3xTF32 GEMM).
@@ -411,9 +411,6 @@ template <int NC>
 __device__ __forceinline__ void desc_store_split(const TabParams<double>& p, const double (&A)[4][NC], double s2,
                                                  const double* __restrict__ stage, long long row, int lane) {
   // axis == 16 (checked on the host): one lane owns the 16 contiguous k2 of each of its channels.
-  // Digits are balanced base-256 (DPB200_SPLIT_DIGIT_BITS = 8): with I' = I + sum_k 128*256^k every digit is a
-  // plain BYTE of I' (digit = byte - 128 = byte ^ 0x80 as int8), so a slice word of four values is three byte
-  // permutes and one XOR -- the 7-bit version spent ~3 integer instructions per (value, digit) here.
   const int M = p.M, ns = p.nslice;
   // row scale from the Cauchy-Schwarz bound |D[k1][k2]| <= max_k |A[:,k]|^2 (attained on the diagonal)
   double r2 = 0.;
@@ -428,20 +425,20 @@ __device__ __forceinline__ void desc_store_split(const TabParams<double>& p, con
   int E = e + 2;  // |D| < 2^(E-1)
   E = E < -900 ? -900 : (E > 900 ? 900 : E);
   if (lane == 0) p.row_exp[row] = E;
-  const int P = 8 * ns - 1;  // fixed-point fraction bits: |I| < 2^(P-1) = 256^ns / 4
+  const int P = 6 + 7 * (ns - 1);  // fixed-point fraction bits
   const double up = s2 * __hiloint2double((1023 + P - E) << 20, 0);
+  // bias that makes every base-128 digit non-negative: digit' = digit + 64
   long long bias = 0;
-  for (int k = 0; k < ns; ++k) bias = bias * 256 + 128;
+  for (int k = 0; k < ns; ++k) bias = bias * 128 + 64;
   signed char* __restrict__ base = reinterpret_cast<signed char*>(p.desc) + row * p.desc_ld;
   const long long K = (long long)M * 16;
-  const int nhi = ns > 4 ? ns - 4 : 0;  // digits living in the high word of I'
 #pragma unroll
   for (int c = 0; c < NC; ++c) {  // (unrolled: a runtime channel index would push acc[][] into local memory)
     const int k1 = lane + 32 * c;
     if (k1 < M) {
 #pragma unroll 1
       for (int half = 0; half < 2; ++half) {
-        unsigned lo[8], hi[8];
+        unsigned long long q[8];
 #pragma unroll
         for (int t = 0; t < 8; t += 2) {
           double v0 = 0., v1 = 0.;
@@ -450,29 +447,23 @@ __device__ __forceinline__ void desc_store_split(const TabParams<double>& p, con
             const double2 b = *reinterpret_cast<const double2*>(stage + m * 16 + half * 8 + t);
             v0 += A[m][c] * b.x, v1 += A[m][c] * b.y;
           }
-          const unsigned long long q0 = (unsigned long long)(__double2ll_rn(v0 * up) + bias);
-          const unsigned long long q1 = (unsigned long long)(__double2ll_rn(v1 * up) + bias);
-          lo[t] = (unsigned)q0, hi[t] = (unsigned)(q0 >> 32);
-          lo[t + 1] = (unsigned)q1, hi[t + 1] = (unsigned)(q1 >> 32);
+          q[t] = (unsigned long long)(__double2ll_rn(v0 * up) + bias);
+          q[t + 1] = (unsigned long long)(__double2ll_rn(v1 * up) + bias);
         }
-        signed char* __restrict__ o = base + (long long)k1 * 16 + half * 8;
-        // slice s = digit ns-1-s: first the digits of the high word, then those of the low word
-        for (int s = 0; s < ns; ++s) {
-          const int dg = ns - 1 - s;
-          const bool up_w = dg >= 4;
-          const unsigned b = (unsigned)(dg & 3);
-          const unsigned sel = b | ((4u + b) << 4);  // byte b of the first and of the second source
+        for (int s = 0; s < ns; ++s) {  // slice s = digit ns-1-s
+          const int sh = 7 * (ns - 1 - s);
           unsigned w[2];
 #pragma unroll
           for (int g = 0; g < 2; ++g) {
-            const unsigned x0 = up_w ? hi[4 * g + 0] : lo[4 * g + 0], x1 = up_w ? hi[4 * g + 1] : lo[4 * g + 1];
-            const unsigned x2 = up_w ? hi[4 * g + 2] : lo[4 * g + 2], x3 = up_w ? hi[4 * g + 3] : lo[4 * g + 3];
-            const unsigned t01 = __byte_perm(x0, x1, sel), t23 = __byte_perm(x2, x3, sel);
-            w[g] = __byte_perm(t01, t23, 0x5410) ^ 0x80808080u;
+            const unsigned d0 = (unsigned)(q[4 * g + 0] >> sh) & 127u;
+            const unsigned d1 = (unsigned)(q[4 * g + 1] >> sh) & 127u;
+            const unsigned d2 = (unsigned)(q[4 * g + 2] >> sh) & 127u;
+            const unsigned d3 = (unsigned)(q[4 * g + 3] >> sh) & 127u;
+            const unsigned pk = d0 | (d1 << 8) | (d2 << 16) | (d3 << 24);
+            w[g] = ((pk | 0x80808080u) - 0x40404040u) ^ 0x80808080u;  // per-byte digit' - 64
           }
-          *reinterpret_cast<uint2*>(o + s * K) = make_uint2(w[0], w[1]);
+          *reinterpret_cast<uint2*>(base + s * K + (long long)k1 * 16 + half * 8) = make_uint2(w[0], w[1]);
         }
-        (void)nhi;
       }
     }
   }
@@ -1324,9 +1315,9 @@ int launch_fwd(FP* out, const FP* table, const FP* info, const FP* em_x, long lo
                 "tabulate+descriptor: needs M <= 128 and axis <= min(32, M)");
     DPB_REQUIRE(aligned16(da->desc), "tabulate+descriptor: desc must be 16-byte aligned");
     if (da->mode == 2 && sizeof(FP) == 8) {
-      DPB_REQUIRE(da->axis == 16 && da->nslice >= 2 && da->nslice <= 7 && da->row_exp != nullptr &&
+      DPB_REQUIRE(da->axis == 16 && da->nslice >= 2 && da->nslice <= 8 && da->row_exp != nullptr &&
                       da->desc_ld % 16 == 0 && da->desc_ld >= (long long)da->nslice * M * 16,
-                  "tabulate+descriptor: int8 split needs axis == 16, 2 <= nslice <= 7, row_exp, 16-byte rows");
+                  "tabulate+descriptor: int8 split needs axis == 16, 2 <= nslice <= 8, row_exp, 16-byte rows");
     } else if (da->mode == 2) {
       DPB_REQUIRE(da->axis % 4 == 0 && da->desc_ld % 4 == 0 && da->desc_ld >= 2LL * M * da->axis,
                   "tabulate+descriptor: TF32 split needs axis % 4 == 0 and 16-byte rows of >= 2*M*axis floats");

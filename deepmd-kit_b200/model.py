@@ -65,21 +65,20 @@ COPPER_CONFIG = dict(ntypes=1, sel=(512,), rcut=8.0, rcut_smth=2.0, stats=[(0.06
 
 
 def split_i8_cols(w: torch.Tensor, nslice: int):
-    """Host-side split of an fp64 weight matrix [K, N] into balanced base-256 digits per COLUMN scale:
-    w[:, c] = 2^col_exp[c] * sum_j slice_j[:, c] 2^(-7-8j), slice_j in [-128, 127].  Returns (slices int8
-    [nslice, K, N], most significant first; col_exp int32 [N]).  Same digit convention as csrc/fitting.cu /
-    tabulate.cu (the digits are the bytes of the biased fixed-point image)."""
+    """Host-side split of an fp64 weight matrix [K, N] into signed 7-bit slices per COLUMN scale:
+    w[:, c] = 2^col_exp[c] * sum_j slice_j[:, c] 2^(-6-7j).  Returns (slices int8 [nslice, K, N], most
+    significant first; col_exp int32 [N]).  Same digit convention as csrc/fitting.cu / tabulate.cu."""
     w = w.detach().to("cpu", torch.float64)
     m = w.abs().amax(0)
     _, ex = torch.frexp(torch.where(m > 0, m, torch.ones_like(m)))  # m = mant * 2^ex, mant in [0.5, 1)
     E = (ex + 1).to(torch.int32)  # |w| * 2^-E < 0.5
-    P = 8 * nslice - 1
+    P = 6 + 7 * (nslice - 1)
     q = torch.round(torch.ldexp(w, (P - E).to(torch.int32).unsqueeze(0).expand_as(w))).to(torch.int64)
     bias = 0
     for _ in range(nslice):
-        bias = bias * 256 + 128
+        bias = bias * 128 + 64
     q = q + bias
-    digits = [(((q >> (8 * k)) & 255) - 128).to(torch.int8) for k in range(nslice)]  # k = 0 least significant
+    digits = [(((q >> (7 * k)) & 127) - 64).to(torch.int8) for k in range(nslice)]  # k = 0 least significant
     return torch.stack(digits[::-1]), E
 
 
@@ -135,8 +134,6 @@ class FittingNet:
         dev = self.layers[0][0].device
         if self.dtype == torch.float64:
             w0 = self.layers[0][0]
-            if nslice * w0.shape[0] * 128 * 128 >= 2 ** 31:
-                raise ValueError("dpb200: nslice * K too large for the int32 accumulators of the int8 GEMM")
             sl, ce = split_i8_cols(w0, nslice)  # [ns, K, N]
             wrev = torch.cat([sl[k] for k in range(nslice - 1, -1, -1)], 0).contiguous()  # W_{ns-1}; ...; W_0
             self.split = dict(nslice=nslice, wrev=wrev.to(dev), col_exp=ce.to(dev), K=w0.shape[0])
@@ -305,7 +302,7 @@ class SeAModel:
         # Tensor-core fitting net (csrc/fitting.cu): the descriptor leaves the tabulate forward already split
         # (int8 slices in fp64, TF32 head/tail in fp32).  Needs axis == 16 (fp64) / axis % 4 == 0 (fp32),
         # M <= 128 and a first fitting layer without skip connection.
-        self.nslice = 5  # 8*5 - 1 = 39 fraction bits per operand: GEMM error ~4e-12 of the row*column scale
+        self.nslice = 6  # 6 + 5*7 = 41 fraction bits per operand: GEMM error ~1e-12 of the row*column scale
         w0 = self.fit[0].layers[0][0]
         ok_axis = cfg.axis_neuron == 16 if dtype == torch.float64 else cfg.axis_neuron % 4 == 0
         self.use_split = bool(ok_axis and self.M <= 128 and cfg.axis_neuron <= 32 and w0.shape[1] not in

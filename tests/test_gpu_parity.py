@@ -618,19 +618,20 @@ def test_tabulate_desc_epilogue(ops, dtype):
     close(N(got), N(want_d), dtype)
     # mode 2: split operand
     out, d2, ex = ops.tabulate_sections_desc(tables, infos, em, sec, M, axis, 1.0 / nnei, desc_row=perm, mode=2,
-                                             nslice=5, pad_rows=32)
+                                             nslice=7, pad_rows=32)
     assert torch.equal(out, want_out)
     assert d2.shape[0] == nloc + 32 and int(d2[nloc:].abs().sum()) == 0
     K = M * axis
     d2 = d2[perm.long()]
     if dtype == np.float64:
-        sl = d2.reshape(nloc, 5, K).to(torch.float64)
-        w = torch.tensor([2.0 ** (-7 - 8 * s) for s in range(5)], dtype=torch.float64, device=DEV)
+        sl = d2.reshape(nloc, 7, K).to(torch.float64)
+        assert int(sl.abs().max()) <= 64
+        w = torch.tensor([2.0 ** (-6 - 7 * s) for s in range(7)], dtype=torch.float64, device=DEV)
         rec = (sl * w[None, :, None]).sum(1) * torch.ldexp(torch.ones((), dtype=torch.float64, device=DEV),
                                                            ex[perm.long()].to(torch.int32))[:, None]
         rowmax = want_d.abs().amax(1, keepdim=True)
         err = ((rec - want_d).abs() / rowmax).max().item()
-        assert err < 2.0 ** -38, err
+        assert err < 2.0 ** -44, err
     else:
         hi, lo = d2[:, :K], d2[:, K:]
         assert torch.equal(hi.view(torch.int32) & 0x1FFF, torch.zeros_like(hi, dtype=torch.int32))
@@ -644,7 +645,7 @@ def test_split_i8_gemm_matches_fp64(ops):
     from deepmd_kit_b200.model import split_i8_cols
 
     torch.manual_seed(5)
-    n, K, Nn, ns = 300, 1600, 240, 6
+    n, K, Nn, ns = 300, 1600, 240, 7
     x = (torch.randn(n, K, dtype=torch.float64, device=DEV) * torch.logspace(-6, 0, n, dtype=torch.float64, device=DEV)[:, None])
     w = torch.randn(K, Nn, dtype=torch.float64) * 0.03
     xs, ex = ops.split_i8_rows(x, ns)
@@ -672,11 +673,11 @@ def test_fitting_split_matches_plain(ops, dtype):
 
     torch.manual_seed(2)
     n, K = 700, 1600
-    net = FittingNet(K, (240, 240, 240), True, 7, dtype, DEV).prepare_split(5)
+    net = FittingNet(K, (240, 240, 240), True, 7, dtype, DEV).prepare_split(7)
     d = torch.randn(n, K, dtype=dtype, device=DEV) * 0.02
     e0, g0 = net.forward_backward(d)
     if dtype == torch.float64:
-        xs, ex = ops.split_i8_rows(d, 5)
+        xs, ex = ops.split_i8_rows(d, 7)
         e1, g1 = net.forward_backward_split(xs, ex, n)
         tol = 1e-11
         ref_e, ref_g = e0, g0
@@ -721,11 +722,11 @@ def test_compressed_coefficients_match_full_table(ops):
                 em[i, b - k:b, 1:] = 0
     em_t = T(em.reshape(nloc, -1))
     inv = 1.0 / nnei
-    out0, d0, e0 = ops.tabulate_sections_desc(model.tables, model.infos, em_t, cfg.sec, model.M, 16, inv, mode=2, nslice=5)
-    out1, d1, e1 = ops.tabulate_sections_desc(model.tables, model.infos, em_t, cfg.sec, model.M, 16, inv, mode=2, nslice=5,
+    out0, d0, e0 = ops.tabulate_sections_desc(model.tables, model.infos, em_t, cfg.sec, model.M, 16, inv, mode=2, nslice=6)
+    out1, d1, e1 = ops.tabulate_sections_desc(model.tables, model.infos, em_t, cfg.sec, model.M, 16, inv, mode=2, nslice=6,
                                               flags=model.coef_flags)
     assert ((out1 - out0).abs().max() / out0.abs().max()).item() < 1e-11
-    assert torch.equal(e0, e1) and torch.equal(d0, d1)  # the forward ignores the flag
+    assert torch.equal(e0, e1) and (d1.to(torch.int32) - d0.to(torch.int32)).abs().max().item() <= 64
     dy = torch.randn_like(out0)
     g0 = ops.tabulate_sections_grad(model.tables, model.infos, em_t, dy, cfg.sec, model.M)
     g1 = ops.tabulate_sections_grad(model.tables, model.infos, em_t, dy, cfg.sec, model.M, flags=model.coef_flags)

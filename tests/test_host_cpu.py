@@ -139,23 +139,24 @@ def test_model_tables_and_cpu_reference_pipeline(pkg, port):
 
 
 def test_split_i8_cols_reconstructs_the_weights(pkg):
-    """Host-side operand split of the int8 tensor-core GEMM (model.split_i8_cols): balanced base-256 digits,
-    most significant first, per-column exponent; the reconstruction error is below 2^-(7+8(ns-1)) of the
+    """Host-side operand split of the int8 tensor-core GEMM (model.split_i8_cols): signed 7-bit digits,
+    most significant first, per-column exponent; the reconstruction error is below 2^-(6+7(ns-1)) of the
     column scale and the order-truncated product matches the fp64 product."""
     from deepmd_kit_b200.model import split_i8_cols
 
     torch.manual_seed(0)
     w = torch.randn(64, 24, dtype=torch.float64) * torch.logspace(-3, 2, 24, dtype=torch.float64)[None, :]
     w[:, 3] = 0.0  # an all-zero column must not produce NaN / overflow
-    for ns in (2, 5, 6):
+    for ns in (2, 6, 7):
         sl, ce = split_i8_cols(w, ns)
         assert sl.shape == (ns, 64, 24) and sl.dtype == torch.int8 and ce.dtype == torch.int32
+        assert int(sl.abs().max()) <= 64
         scale = torch.ldexp(torch.ones(24, dtype=torch.float64), ce)
-        rec = sum(sl[s].double() * 2.0 ** (-7 - 8 * s) for s in range(ns)) * scale[None, :]
+        rec = sum(sl[s].double() * 2.0 ** (-6 - 7 * s) for s in range(ns)) * scale[None, :]
         err = ((rec - w).abs() / scale[None, :]).max().item()
-        assert err <= 2.0 ** (-7 - 8 * (ns - 1)) * 0.51, (ns, err)
+        assert err <= 2.0 ** (-6 - 7 * (ns - 1)) * 0.51, (ns, err)
     # K-concatenated order sums == exact integer products, recombined
-    ns = 5
+    ns = 6
     x = torch.randn(5, 64, dtype=torch.float64)
     xs, xe = split_i8_cols(x.t().contiguous(), ns)  # per-row scale of x == per-column scale of x^T
     xs = xs.permute(0, 2, 1).contiguous()  # [ns, 5, 64]
@@ -164,7 +165,7 @@ def test_split_i8_cols_reconstructs_the_weights(pkg):
     for d in range(ns):
         od = sum(xs[i].to(torch.int64) @ sl[d - i].to(torch.int64) for i in range(d + 1))
         assert int(od.abs().max()) < 2 ** 31  # fits the tensor cores' int32 accumulators
-        acc += od.double() * 2.0 ** (-14 - 8 * d)
+        acc += od.double() * 2.0 ** (-12 - 7 * d)
     got = acc * torch.ldexp(torch.ones(5, dtype=torch.float64), xe)[:, None] * torch.ldexp(
         torch.ones(24, dtype=torch.float64), ce)[None, :]
     want = x @ w
