@@ -202,6 +202,50 @@ __global__ void k_table_relayout_cm(double2* __restrict__ T, const double* __res
   }
 }
 
+template <typename FP>
+__device__ __forceinline__ FP poly(const FP (&a)[6], FP x);
+// fetch_row for the compressed layout in the SIMT forward: a0..a2 go to the fp64 registers, a3..a5 stay fp32
+// (8 instead of 12 sixteen-byte requests per lane and row, 9 instead of 12 registers per channel).
+template <int NC, int NA>
+__device__ __forceinline__ void fetch_row_cmf(double (&a)[NC][6], float (&af_)[NA][3], const double* __restrict__ hot,
+                                              const double* __restrict__ T, int row, int r0, int H, int M,
+                                              const int (&ob)[NC], float a5_inv) {
+  const unsigned rel = (unsigned)(row - r0);
+  const unsigned qb = (unsigned)M * 16u;
+  if (rel < (unsigned)H) {
+    const char* b0 = reinterpret_cast<const char*>(hot) + rel * (2u * qb);
+#pragma unroll
+    for (int c = 0; c < NC; ++c) {
+      const double2 u = *reinterpret_cast<const double2*>(b0 + ob[c]);
+      const double2 v = *reinterpret_cast<const double2*>(b0 + qb + ob[c]);
+      a[c][0] = u.x, a[c][1] = u.y;
+      float (&af)[3] = af_[NA == NC ? c : 0];
+      unpack_cm(v, a[c][2], af[0], af[1], af[2]);
+      af[2] *= a5_inv;
+    }
+  } else {
+    const char* b0 = reinterpret_cast<const char*>(T) + (long long)row * (2u * qb);
+#pragma unroll
+    for (int c = 0; c < NC; ++c) {
+      const double2 u = __ldg(reinterpret_cast<const double2*>(b0 + ob[c]));
+      const double2 v = __ldg(reinterpret_cast<const double2*>(b0 + qb + ob[c]));
+      a[c][0] = u.x, a[c][1] = u.y;
+      float (&af)[3] = af_[NA == NC ? c : 0];
+      unpack_cm(v, a[c][2], af[0], af[1], af[2]);
+      af[2] *= a5_inv;
+    }
+  }
+}
+template <int NC, int NA>
+__device__ __forceinline__ void fetch_row_cmf(float (&)[NC][6], float (&)[NA][3], const float*, const float*, int, int,
+                                              int, int, const int (&)[NC], float) {}
+// value of the quintic with the top two Horner steps on the FP32 pipe
+__device__ __forceinline__ double poly_cm(const double (&a)[6], const float (&f)[3], double x, float xf) {
+  const float t = fmaf(fmaf(f[2], xf, f[1]), xf, f[0]);
+  return a[0] + (a[1] + (a[2] + (double)t * x) * x) * x;
+}
+__device__ __forceinline__ float poly_cm(const float (&a)[6], const float (&)[3], float x, float) { return poly(a, x); }
+
 // Coefficients of one table row for the NC channels of this lane.  ob[c] = byte offset of the lane's
 // channel inside one coefficient-pair block (clamped to channel M-1 so that every lane always loads:
 // no divergence, the duplicates cost no extra wavefront).  Source: the shared-memory window
@@ -506,7 +550,7 @@ extern __shared__ __align__(16) unsigned char tab_smem[];
 // grid (x: persistent over atoms, y: block of 32*NC channels); block = nw warps.
 // smem: hot[H][3][M] pairs | Rec[nw][32] | RecGG[nw][32] (GG only)
 // ------------------------------------------------------------------------------------------
-template <typename FP, int NC, bool TWO, bool GG, bool DESC = false>
+template <typename FP, int NC, bool TWO, bool GG, bool DESC = false, bool CM = false>
 __global__ void __launch_bounds__(512) k_tab_fwd(const __grid_constant__ TabParams<FP> p) {
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
@@ -541,10 +585,13 @@ __global__ void __launch_bounds__(512) k_tab_fwd(const __grid_constant__ TabPara
     for (int c = 0; c < NC; ++c)
       acc[m][c] = (p.accumulate && i < p.nloc) ? p.out[(i * 4 + m) * (long long)p.M + kc[c]] : (FP)0.;
   FP a[NC][6];
+  float af[CM ? NC : 1][3];  // compressed coefficients: a3, a4, a5 of the cached row stay fp32
 #pragma unroll
   for (int c = 0; c < NC; ++c)
 #pragma unroll
     for (int q = 0; q < 6; ++q) a[c][q] = (FP)0.;
+#pragma unroll
+  for (int c = 0; c < (CM ? NC : 1); ++c) af[c][0] = af[c][1] = af[c][2] = 0.f;
   int cur_row = -1;  // the coefficient registers stay valid across atoms
 
   while (i < p.nloc) {
@@ -566,13 +613,17 @@ __global__ void __launch_bounds__(512) k_tab_fwd(const __grid_constant__ TabPara
         const int row = r.idx;
         if (row != cur_row) {  // warp-uniform
           cur_row = row;
-          fetch_row<FP, NC>(a, hot, p.T, row, r0, p.H, p.M, ob);
+          if (CM)
+            fetch_row_cmf(a, af, hot, p.T, row, r0, p.H, p.M, ob, p.a5_inv);
+          else
+            fetch_row<FP, NC>(a, hot, p.T, row, r0, p.H, p.M, ob);
         }
         const FP xx = r.xx;
+        const float xf = (float)xx;
         const FP e0 = r.e[0], e1 = r.e[1], e2 = r.e[2], e3 = r.e[3];
 #pragma unroll
         for (int c = 0; c < NC; ++c) {
-          const FP g = poly(a[c], xx);
+          const FP g = CM ? poly_cm(a[c], af[CM ? c : 0], xx, xf) : poly(a[c], xx);
           acc[0][c] += e0 * g;
           acc[1][c] += e1 * g;
           acc[2][c] += e2 * g;
@@ -585,7 +636,10 @@ __global__ void __launch_bounds__(512) k_tab_fwd(const __grid_constant__ TabPara
         const int row = r.idx;
         if (row != cur_row) {  // warp-uniform
           cur_row = row;
-          fetch_row<FP, NC>(a, hot, p.T, row, r0, p.H, p.M, ob);
+          if (CM)
+            fetch_row_cmf(a, af, hot, p.T, row, r0, p.H, p.M, ob, p.a5_inv);
+          else
+            fetch_row<FP, NC>(a, hot, p.T, row, r0, p.H, p.M, ob);
         }
         const FP xx = r.xx;
         const FP dl = r.delta;
@@ -603,13 +657,16 @@ __global__ void __launch_bounds__(512) k_tab_fwd(const __grid_constant__ TabPara
 #pragma unroll
         for (int c = 0; c < NC; ++c) {
           FP g, gd = (FP)0.;
+          FP w6[6];  // this (rare) path evaluates in fp64 throughout
+#pragma unroll
+          for (int k = 0; k < 6; ++k) w6[k] = (CM && k >= 3) ? (FP)af[CM ? c : 0][k - 3] : a[c][k];
           if (GG) {
-            poly_both(a[c], xx, g, gd);
+            poly_both(w6, xx, g, gd);
             g += gd * dl;
           } else {
-            g = poly(a[c], xx);
+            g = poly(w6, xx);
             if (dl != (FP)0.) {
-              gd = dpoly(a[c], xx);
+              gd = dpoly(w6, xx);
               g += gd * dl;
             }
           }
@@ -1158,6 +1215,14 @@ inline bool use_mma_fwd() {
   return on;
 }
 
+inline bool fwd_cm_enabled() {
+  static const bool on = [] {
+    const char* e = getenv("DPB200_TAB_FWD_CM");
+    return !(e && e[0] == '0');
+  }();
+  return on;
+}
+
 inline bool use_mma_path() {
   static const bool on = [] {
     const char* e = getenv("DPB200_TAB_MMA");
@@ -1302,11 +1367,10 @@ int launch_fwd(FP* out, const FP* table, const FP* info, const FP* em_x, long lo
   DPB_REQUIRE(nloc >= 0 && nnei >= 0 && M >= 0, "tabulate: negative size");
   if (nloc == 0 || M == 0) return DPB200_OK;
   DPB_REQUIRE(out != nullptr, "tabulate: out is null");
-  // DPB200_TAB_COMPRESSED_COEF is honoured by the backward only: the SIMT forward keeps a row's coefficients in
-  // registers across neighbours, so it would have to expand them to fp64 at fetch time (12 conversions per
-  // row) -- measured 8 % slower than the full table (op_bench: 7.65 vs 7.06 ms at 332 k atoms).
-  (void)flags;
-  const bool cm = false;
+  // compressed coefficients in the SIMT forward: a3..a5 stay fp32 in the row cache and the top two Horner steps
+  // run on the FP32 pipe (widening them to fp64 at fetch time instead was measured 8 % SLOWER than the full table)
+  const bool cm = (flags & DPB200_TAB_COMPRESSED_COEF) && sizeof(FP) == 8 && !GG && two == nullptr && !use_mma_fwd() &&
+                  fwd_cm_enabled();
   if (da) {
     const bool plain = !GG && two == nullptr && nnei > 0;
     DPB_REQUIRE(plain, "tabulate+descriptor: plain se_a forward with nnei > 0 only");
@@ -1366,11 +1430,8 @@ int launch_fwd(FP* out, const FP* table, const FP* info, const FP* em_x, long lo
   FP* scratch3 = nullptr;
   rc = cm ? prepare_table_cm(p, &scratch, st) : prepare_table(p, &scratch, st);
   if (rc) return rc;
-  if (cm) {
-    rc = prepare_table_full(p, &scratch3, st);
-    if (rc) return rc;
-    if (p.H > p.first) p.H = p.first;  // the shared-memory window holds compressed (stride-0) rows only
-  }
+  // (the forward needs the VALUE only: the compressed table is accurate enough on the stride-1 rows too -- the
+  //  host-side gate checks that -- so no second table here)
   const bool tw = two != nullptr;
   const int nblk = (M + 32 * nc - 1) / (32 * nc);
   long long want = ((long long)nloc + nw - 1) / nw;
@@ -1419,7 +1480,15 @@ int launch_fwd(FP* out, const FP* table, const FP* info, const FP* em_x, long lo
   }
 #define DPB_LAUNCH_FWD(NC)                                                                      \
   do {                                                                                          \
-    if (da) {                                                                            \
+    if (da && cm) {                                                                             \
+      auto kern = k_tab_fwd<FP, NC, false, false, true, true>;                                  \
+      e1 = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);  \
+      if (e1 == cudaSuccess) kern<<<grid, nw * 32, smem, st>>>(p);                              \
+    } else if (cm) {                                                                            \
+      auto kern = k_tab_fwd<FP, NC, false, false, false, true>;                                 \
+      e1 = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);  \
+      if (e1 == cudaSuccess) kern<<<grid, nw * 32, smem, st>>>(p);                              \
+    } else if (da) {                                                                            \
       auto kern = k_tab_fwd<FP, NC, false, false, true>;                                        \
       e1 = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);  \
       if (e1 == cudaSuccess) kern<<<grid, nw * 32, smem, st>>>(p);                              \

@@ -325,12 +325,20 @@ def compressed_coef_flags(table: torch.Tensor, info, tol: float = 3e-12) -> int:
     ed = 2 * e2 * blk[..., 2] * s + e34 * (3 * blk[..., 3] * s ** 2 + 4 * blk[..., 4] * s ** 3) + e5 * 5 * blk[..., 5] * s ** 4
     if float(ev.max()) > tol * m0 or float(ed.max()) > tol * m1:
         return 0
+    # the forward (value only) reads the compressed form on the stride-1 rows as well
+    if first < nrow:
+        c = a[first:]
+        evc = e2 * c[..., 2] * s1 ** 2 + e34 * (c[..., 3] * s1 ** 3 + c[..., 4] * s1 ** 4) + e5 * c[..., 5] * s1 ** 5
+        if float(evc.max()) > tol * m0:
+            return 0
     m5 = float(blk[..., 5].max())
     k = 0
     if m5 > 0:
         import math
 
-        k = max(-120, min(120, 13 - int(math.floor(math.log2(m5)))))  # max|a5| * 2^k in [2^13, 2^14)
+        k = max(-120, min(120, 13 - int(math.floor(math.log2(m5)))))  # max|a5| * 2^k in [2^13, 2^14) on stride-0 rows
+    if float(a[..., 5].max()) * 2.0 ** k >= 6.0e4:  # fp16 range on every row
+        return 0
     return 1 | ((k & 0xff) << 8)
 
 

@@ -726,7 +726,14 @@ def test_compressed_coefficients_match_full_table(ops):
     out1, d1, e1 = ops.tabulate_sections_desc(model.tables, model.infos, em_t, cfg.sec, model.M, 16, inv, mode=2, nslice=6,
                                               flags=model.coef_flags)
     assert ((out1 - out0).abs().max() / out0.abs().max()).item() < 1e-11
-    assert torch.equal(e0, e1) and (d1.to(torch.int32) - d0.to(torch.int32)).abs().max().item() <= 64
+    # the slices of the two descriptors may differ in the last digits only: compare the reconstructed rows
+    K = model.M * 16
+    w6 = torch.tensor([2.0 ** (-6 - 7 * s) for s in range(6)], dtype=torch.float64, device=DEV)
+    r0_ = (d0[:nloc].reshape(nloc, 6, K).double() * w6[None, :, None]).sum(1) * torch.ldexp(
+        torch.ones(nloc, dtype=torch.float64, device=DEV), e0[:nloc])[:, None]
+    r1_ = (d1[:nloc].reshape(nloc, 6, K).double() * w6[None, :, None]).sum(1) * torch.ldexp(
+        torch.ones(nloc, dtype=torch.float64, device=DEV), e1[:nloc])[:, None]
+    assert ((r1_ - r0_).abs().max() / r0_.abs().max()).item() < 1e-11
     dy = torch.randn_like(out0)
     g0 = ops.tabulate_sections_grad(model.tables, model.infos, em_t, dy, cfg.sec, model.M)
     g1 = ops.tabulate_sections_grad(model.tables, model.infos, em_t, dy, cfg.sec, model.M, flags=model.coef_flags)
