@@ -26,9 +26,11 @@ for rep in range(2):
     xyz = ops.tabulate_sections_fwd(model.tables, model.infos, em, cfg.sec, M)
     if model.use_split:
         ops.tabulate_sections_desc(model.tables, model.infos, em, cfg.sec, M, cfg.axis_neuron, 1.0 / nnei,
-                                   desc_row=st.type_inv, mode=2, nslice=model.nslice, pad_rows=32)
+                                   desc_row=st.type_inv, mode=2, nslice=model.nslice, pad_rows=32,
+                                   flags=model.coef_flags)
     dy = torch.randn_like(xyz)
-    nd = ops.tabulate_sections_grad(model.tables, model.infos, em, dy, cfg.sec, M)
+    nd = ops.tabulate_sections_grad(model.tables, model.infos, em, dy, cfg.sec, M)  # full table
+    nd = ops.tabulate_sections_grad(model.tables, model.infos, em, dy, cfg.sec, M, flags=model.coef_flags)
     gd = torch.randn(nloc, M * cfg.axis_neuron, dtype=dtype, device=dev)
     ops.se_a_descriptor_grad(gd, xyz, cfg.axis_neuron, 1.0 / nnei, rows=st.type_perm.to(torch.int32), out=torch.empty_like(xyz))
     nl2 = nlist.clone(); ops.use_nlist_map(nl2, st.mapping)
