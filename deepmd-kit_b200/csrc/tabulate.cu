@@ -204,6 +204,56 @@ __global__ void k_table_relayout_cm(double2* __restrict__ T, const double* __res
 
 template <typename FP>
 __device__ __forceinline__ FP poly(const FP (&a)[6], FP x);
+// fp32 flavour of DPB200_TAB_COMPRESSED_COEF: at fp32 precision the quintic of a dp-compress table IS a cubic
+// (a4 x^4 <= 2e-10 |a0|, a5 x^5 <= 5e-13 |a0| on the stride-0.01 rows, 4 a4 x^3 <= 1e-7 |a1|), so the kernels
+// stream one float4 {a0, a1, a2, a3} per (row, channel) instead of three float2 pairs and evaluate 3 (value) /
+// 5 (value + derivative) FMAs instead of 5 / 9.  Same host-side gate (ops.compressed_coef_flags).
+__global__ void k_table_relayout_c32(float4* __restrict__ T, const float* __restrict__ table, long long nrow, int M) {
+  const long long n = nrow * (long long)M;
+  for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < n;
+       e += (long long)gridDim.x * blockDim.x) {
+    const float* a = table + e * 6;
+    T[e] = make_float4(a[0], a[1], a[2], a[3]);
+  }
+}
+template <int NC>
+__device__ __forceinline__ void fetch_row_c32(float (&a)[NC][6], const float* __restrict__ hot,
+                                              const float* __restrict__ T, int row, int r0, int H, int M,
+                                              const int (&ob)[NC]) {
+  const unsigned rel = (unsigned)(row - r0);
+  const unsigned rb = (unsigned)M * 16u;
+  if (rel < (unsigned)H) {
+    const char* b0 = reinterpret_cast<const char*>(hot) + rel * rb;
+#pragma unroll
+    for (int c = 0; c < NC; ++c) {
+      const float4 u = *reinterpret_cast<const float4*>(b0 + 2 * ob[c]);
+      a[c][0] = u.x, a[c][1] = u.y, a[c][2] = u.z, a[c][3] = u.w;
+    }
+  } else {
+    const char* b0 = reinterpret_cast<const char*>(T) + (long long)row * rb;
+#pragma unroll
+    for (int c = 0; c < NC; ++c) {
+      const float4 u = __ldg(reinterpret_cast<const float4*>(b0 + 2 * ob[c]));
+      a[c][0] = u.x, a[c][1] = u.y, a[c][2] = u.z, a[c][3] = u.w;
+    }
+  }
+}
+template <int NC>
+__device__ __forceinline__ void fetch_row_c32(double (&)[NC][6], const double*, const double*, int, int, int, int,
+                                              const int (&)[NC]) {}
+template <typename FP>
+__device__ __forceinline__ FP poly3(const FP (&a)[6], FP x) {
+  return a[0] + (a[1] + (a[2] + a[3] * x) * x) * x;
+}
+template <typename FP>
+__device__ __forceinline__ void poly3_both(const FP (&a)[6], FP x, FP& g, FP& gd) {
+  const FP b2 = a[2] + a[3] * x;
+  const FP b1 = a[1] + b2 * x;
+  g = a[0] + b1 * x;
+  const FP c2 = b2 + a[3] * x;
+  gd = b1 + c2 * x;
+}
+
 // fetch_row for the compressed layout in the SIMT forward: a0..a2 go to the fp64 registers, a3..a5 stay fp32
 // (8 instead of 12 sixteen-byte requests per lane and row, 9 instead of 12 registers per channel).
 template <int NC, int NA>
@@ -613,7 +663,9 @@ __global__ void __launch_bounds__(512) k_tab_fwd(const __grid_constant__ TabPara
         const int row = r.idx;
         if (row != cur_row) {  // warp-uniform
           cur_row = row;
-          if (CM)
+          if (CM && sizeof(FP) == 4)
+            fetch_row_c32<NC>(a, hot, p.T, row, r0, p.H, p.M, ob);
+          else if (CM)
             fetch_row_cmf(a, af, hot, p.T, row, r0, p.H, p.M, ob, p.a5_inv);
           else
             fetch_row<FP, NC>(a, hot, p.T, row, r0, p.H, p.M, ob);
@@ -623,7 +675,7 @@ __global__ void __launch_bounds__(512) k_tab_fwd(const __grid_constant__ TabPara
         const FP e0 = r.e[0], e1 = r.e[1], e2 = r.e[2], e3 = r.e[3];
 #pragma unroll
         for (int c = 0; c < NC; ++c) {
-          const FP g = CM ? poly_cm(a[c], af[CM ? c : 0], xx, xf) : poly(a[c], xx);
+          const FP g = (CM && sizeof(FP) == 4) ? poly3(a[c], xx) : (CM ? poly_cm(a[c], af[CM ? c : 0], xx, xf) : poly(a[c], xx));
           acc[0][c] += e0 * g;
           acc[1][c] += e1 * g;
           acc[2][c] += e2 * g;
@@ -636,7 +688,9 @@ __global__ void __launch_bounds__(512) k_tab_fwd(const __grid_constant__ TabPara
         const int row = r.idx;
         if (row != cur_row) {  // warp-uniform
           cur_row = row;
-          if (CM)
+          if (CM && sizeof(FP) == 4)
+            fetch_row_c32<NC>(a, hot, p.T, row, r0, p.H, p.M, ob);  // a4 = a5 = 0 from the initialisation
+          else if (CM)
             fetch_row_cmf(a, af, hot, p.T, row, r0, p.H, p.M, ob, p.a5_inv);
           else
             fetch_row<FP, NC>(a, hot, p.T, row, r0, p.H, p.M, ob);
@@ -659,7 +713,7 @@ __global__ void __launch_bounds__(512) k_tab_fwd(const __grid_constant__ TabPara
           FP g, gd = (FP)0.;
           FP w6[6];  // this (rare) path evaluates in fp64 throughout
 #pragma unroll
-          for (int k = 0; k < 6; ++k) w6[k] = (CM && k >= 3) ? (FP)af[CM ? c : 0][k - 3] : a[c][k];
+          for (int k = 0; k < 6; ++k) w6[k] = (CM && sizeof(FP) == 8 && k >= 3) ? (FP)af[CM ? c : 0][k - 3] : a[c][k];
           if (GG) {
             poly_both(w6, xx, g, gd);
             g += gd * dl;
@@ -741,7 +795,7 @@ __device__ __forceinline__ FP reduce_scatter4(FP (&v)[4], int lane) {
 // One warp per atom, all channels of the atom in this warp (blocks of 32*NC channels; for
 // M <= 32*NC the coefficient registers persist across neighbours and atoms).
 // smem: hot[H][3][M] pairs | Rec[nw][32]
-template <typename FP, int NC, bool TWO>
+template <typename FP, int NC, bool TWO, bool CM = false>
 __global__ void __launch_bounds__(384) k_tab_grad(const __grid_constant__ TabParams<FP> p) {
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
@@ -820,7 +874,10 @@ __global__ void __launch_bounds__(384) k_tab_grad(const __grid_constant__ TabPar
             const Rec<FP>& rc = rec[b + u];
             if (rc.idx != cur_row) {
               cur_row = rc.idx;
-              fetch_row<FP, NC>(a, hot, p.T, cur_row, r0, p.H, M, ob);
+              if (CM)
+                fetch_row_c32<NC>(a, hot, p.T, cur_row, r0, p.H, M, ob);
+              else
+                fetch_row<FP, NC>(a, hot, p.T, cur_row, r0, p.H, M, ob);
             }
             const FP xx = rc.xx;
             const FP dl = rc.delta;
@@ -828,7 +885,10 @@ __global__ void __launch_bounds__(384) k_tab_grad(const __grid_constant__ TabPar
 #pragma unroll
             for (int c = 0; c < NC; ++c) {
               FP g, gd;
-              poly_both(a[c], xx, g, gd);
+              if (CM)
+                poly3_both(a[c], xx, g, gd);
+              else
+                poly_both(a[c], xx, g, gd);
               g += gd * dl;
               const FP dot = e0 * dyr[0][c] + e1 * dyr[1][c] + e2 * dyr[2][c] + e3 * dyr[3][c];
               if (TWO) {
@@ -1318,6 +1378,20 @@ inline int prepare_table_cm(TabParams<double>& p, double** scratch, cudaStream_t
   p.T = *scratch;
   return DPB200_OK;
 }
+inline int prepare_table_cm(TabParams<float>& p, float** scratch, cudaStream_t st, int) {
+  const long long n = (long long)p.nrow * 4 * p.M;  // one float4 per (row, channel)
+  keep_async_pool();
+  DPB_CUDA(cudaMallocAsync((void**)scratch, (size_t)n * sizeof(float), st));
+  int grid = ceil_div((long long)p.nrow * p.M, 256);
+  const int cap = sm_count() * 8;
+  if (grid > cap) grid = cap;
+  k_table_relayout_c32<<<grid, 256, 0, st>>>(reinterpret_cast<float4*>(*scratch), p.table, p.nrow, p.M);
+  p.T = *scratch;
+  return DPB200_OK;
+}
+inline int prepare_table_cm(TabParams<double>& p, double** scratch, cudaStream_t st, int) {
+  return prepare_table_cm(p, scratch, st);
+}
 // full pair table next to the compressed one (for the stride-1 rows)
 inline int prepare_table_full(TabParams<double>& p, double** scratch3, cudaStream_t st) {
   const long long n = (long long)p.nrow * 6 * p.M;
@@ -1330,7 +1404,6 @@ inline int prepare_table_full(TabParams<double>& p, double** scratch3, cudaStrea
   return DPB200_OK;
 }
 inline int prepare_table_full(TabParams<float>&, float**, cudaStream_t) { return DPB200_ERR_INVALID; }
-inline int prepare_table_cm(TabParams<float>&, float**, cudaStream_t) { return DPB200_ERR_INVALID; }
 
 // bits 8..15 of `flags`: signed power-of-two exponent k, a5 is stored as half(a5 * 2^k)
 template <typename FP>
@@ -1340,10 +1413,10 @@ void set_a5_scale(TabParams<FP>& p, int flags) {
   p.a5_inv = std::ldexp(1.0f, -k);
 }
 
-// hot rows / shared-memory sizing for `blocks` 16-byte blocks per (row, channel)
+// hot rows / shared-memory sizing for `blocks` coefficient-pair blocks (2 * sizeof(FP) bytes) per (row, channel)
 template <typename FP>
 void size_hot_window(TabParams<FP>& p, int M, size_t other_bytes, int blocks) {
-  const size_t row_bytes = (size_t)M * 16 * blocks;
+  const size_t row_bytes = (size_t)M * 2 * sizeof(FP) * blocks;  // `blocks` pair blocks per (row, channel)
   long long h = other_bytes + row_bytes > kSmemBudget ? 0 : (long long)((kSmemBudget - other_bytes) / row_bytes);
   if (h > hot_rows_cap()) h = hot_rows_cap();
   p.H = (int)(h < p.nrow ? h : p.nrow);
@@ -1369,8 +1442,7 @@ int launch_fwd(FP* out, const FP* table, const FP* info, const FP* em_x, long lo
   DPB_REQUIRE(out != nullptr, "tabulate: out is null");
   // compressed coefficients in the SIMT forward: a3..a5 stay fp32 in the row cache and the top two Horner steps
   // run on the FP32 pipe (widening them to fp64 at fetch time instead was measured 8 % SLOWER than the full table)
-  const bool cm = (flags & DPB200_TAB_COMPRESSED_COEF) && sizeof(FP) == 8 && !GG && two == nullptr && !use_mma_fwd() &&
-                  fwd_cm_enabled();
+  const bool cm = (flags & DPB200_TAB_COMPRESSED_COEF) && !GG && two == nullptr && !use_mma_fwd() && fwd_cm_enabled();
   if (da) {
     const bool plain = !GG && two == nullptr && nnei > 0;
     DPB_REQUIRE(plain, "tabulate+descriptor: plain se_a forward with nnei > 0 only");
@@ -1428,7 +1500,7 @@ int launch_fwd(FP* out, const FP* table, const FP* info, const FP* em_x, long lo
   const size_t smem = (size_t)p.hot_elems * sizeof(FP) + rec_bytes;
   FP* scratch = nullptr;
   FP* scratch3 = nullptr;
-  rc = cm ? prepare_table_cm(p, &scratch, st) : prepare_table(p, &scratch, st);
+  rc = cm ? prepare_table_cm(p, &scratch, st, 0) : prepare_table(p, &scratch, st);
   if (rc) return rc;
   // (the forward needs the VALUE only: the compressed table is accurate enough on the stride-1 rows too -- the
   //  host-side gate checks that -- so no second table here)
@@ -1542,7 +1614,8 @@ int launch_grad(FP* dy_dem_x, FP* dy_dem, FP* dy_dtwo, const FP* table, const FP
   const int kt = (M + 3) / 4;
   const bool mma_ok = std::is_same<FP, double>::value && !tw && use_mma_path() &&
                       (kt == 8 || kt == 16 || kt == 20 || kt == 25 || kt == 32);
-  const bool cm = mma_ok && (flags & DPB200_TAB_COMPRESSED_COEF) && grad_variant() == 1;
+  const bool cm32 = sizeof(FP) == 4 && !tw && (flags & DPB200_TAB_COMPRESSED_COEF) && fwd_cm_enabled();
+  const bool cm = cm32 || (mma_ok && (flags & DPB200_TAB_COMPRESSED_COEF) && grad_variant() == 1);
   p.Mc = M;
   p.nblk = cm ? 2 : 3;
   set_a5_scale(p, flags);
@@ -1550,9 +1623,9 @@ int launch_grad(FP* dy_dem_x, FP* dy_dem, FP* dy_dtwo, const FP* table, const FP
   const size_t smem = (size_t)p.hot_elems * sizeof(FP) + rec_bytes;
   FP* scratch = nullptr;
   FP* scratch3 = nullptr;
-  rc = cm ? prepare_table_cm(p, &scratch, st) : prepare_table(p, &scratch, st);
+  rc = cm ? prepare_table_cm(p, &scratch, st, 0) : prepare_table(p, &scratch, st);
   if (rc) return rc;
-  if (cm) {
+  if (cm && !cm32) {
     rc = prepare_table_full(p, &scratch3, st);
     if (rc) return rc;
   }
@@ -1606,7 +1679,11 @@ int launch_grad(FP* dy_dem_x, FP* dy_dem, FP* dy_dtwo, const FP* table, const FP
   }
 #define DPB_LAUNCH_GRAD(NC)                                                                     \
   do {                                                                                          \
-    if (tw) {                                                                                   \
+    if (cm32) {                                                                                 \
+      auto kern = k_tab_grad<FP, NC, false, true>;                                              \
+      e1 = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);  \
+      if (e1 == cudaSuccess) kern<<<grid, nw * 32, smem, st>>>(p);                              \
+    } else if (tw) {                                                                                   \
       auto kern = k_tab_grad<FP, NC, true>;                                                     \
       e1 = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);  \
       if (e1 == cudaSuccess) kern<<<grid, nw * 32, smem, st>>>(p);                              \

@@ -316,8 +316,9 @@ class SeAModel:
         self.coef_flags = None
         import os
 
-        if dtype == torch.float64 and self.device.type == "cuda" and os.environ.get("DPB200_TAB_COMPRESS", "1") != "0":
-            fl = [ops.compressed_coef_flags(t, i) for t, i in zip(self.tables64, infos)]
+        if self.device.type == "cuda" and os.environ.get("DPB200_TAB_COMPRESS", "1") != "0":
+            gate = ops.compressed_coef_flags if dtype == torch.float64 else ops.compressed_coef_flags_f32
+            fl = [gate(t, i) for t, i in zip(self.tables64, infos)]
             if all(fl):
                 self.coef_flags = fl
 

@@ -305,6 +305,29 @@ def tabulate_sections_fwd(tables, infos, em, sec, last_layer_size, is_sorted=Tru
     return out
 
 
+def compressed_coef_flags_f32(table: torch.Tensor, info, tol_v: float = 1e-7, tol_d: float = 2e-6) -> int:
+    """fp32 flavour of the gate: the kernels keep {a0..a3} only (one float4 per row and channel).  Allowed when
+    dropping a4 x^4 + a5 x^5 changes the quintic by less than tol_v * max|a0| (about one fp32 ulp) and its derivative
+    by less than tol_d * max|a1| on the stride-0 rows; ten times those bounds (still within the 1e-5 fp32 parity
+    tolerance) on the stride-1 rows, which only inputs outside the tabulated range reach."""
+    t = table.detach().to("cpu", torch.float64)
+    lower, upper, vmax, s0, s1 = [float(x) for x in info[:5]]
+    nrow = t.shape[0]
+    a = t.reshape(nrow, -1, 6).abs()
+    first = min(nrow, int((upper - lower) / s0))
+    m0, m1 = float(a[..., 0].max()), float(a[..., 1].max())
+    if not (m0 > 0 and m1 > 0):
+        return 0
+    for blk, s, f in ((a[:first], s0, 1.0), (a[first:], s1, 10.0)):
+        if blk.numel() == 0:
+            continue
+        ev = blk[..., 4] * s ** 4 + blk[..., 5] * s ** 5
+        ed = 4 * blk[..., 4] * s ** 3 + 5 * blk[..., 5] * s ** 4
+        if float(ev.max()) > f * tol_v * m0 or float(ed.max()) > f * tol_d * m1:
+            return 0
+    return 1
+
+
 def compressed_coef_flags(table: torch.Tensor, info, tol: float = 3e-12) -> int:
     """Host-side gate for DPB200_TAB_COMPRESSED_COEF (include/dpb200.h): returns the flags word for THIS table
     ([nrow, M*6] fp64) if, on every stride-0 row (the stride-1 extrapolation rows are never compressed), storing

@@ -741,3 +741,34 @@ def test_compressed_coefficients_match_full_table(ops):
     # a table that does not qualify is refused by the gate
     tab = random_table(57, 100, rng, np.float64)
     assert ops.compressed_coef_flags(torch.as_tensor(tab), np.array([-0.4, 2.0, 6.0, 0.05, 0.5, -1.0])) == 0
+
+
+def test_compressed_coefficients_fp32_cubic(ops):
+    """fp32 flavour: {a0..a3} only (float4 per row and channel) against the full fp32 table, forward and backward."""
+    import __graft_entry__ as g
+
+    g.load_package()
+    from deepmd_kit_b200.model import SeAConfig, SeAModel
+
+    cfg = SeAConfig()
+    model = SeAModel(cfg, torch.float32, DEV)
+    assert model.coef_flags is not None and all(model.coef_flags)
+    rng = np.random.default_rng(4)
+    nloc, nnei = 257, cfg.nnei
+    em = rng.normal(scale=0.4, size=(nloc, nnei, 4)).astype(np.float32)
+    x = np.sort(rng.uniform(-0.9, 4.0, size=(nloc, nnei)), axis=1)[:, ::-1].copy()
+    x[:5, :4] = rng.uniform(9.5, 40.0, size=(5, 4))
+    x[5:7, :2] = 50.0
+    x[7:9, -3:] = -1.5
+    em[:, :, 0] = x
+    em_t = T(em.reshape(nloc, -1))
+    inv = 1.0 / nnei
+    out0, d0, _ = ops.tabulate_sections_desc(model.tables, model.infos, em_t, cfg.sec, model.M, 16, inv, mode=2)
+    out1, d1, _ = ops.tabulate_sections_desc(model.tables, model.infos, em_t, cfg.sec, model.M, 16, inv, mode=2,
+                                             flags=model.coef_flags)
+    assert ((out1 - out0).abs().max() / out0.abs().max()).item() < 2e-6
+    assert ((d1 - d0).abs().max() / d0.abs().max()).item() < 5e-6
+    dy = torch.randn_like(out0)
+    g0 = ops.tabulate_sections_grad(model.tables, model.infos, em_t, dy, cfg.sec, model.M)
+    g1 = ops.tabulate_sections_grad(model.tables, model.infos, em_t, dy, cfg.sec, model.M, flags=model.coef_flags)
+    assert ((g1 - g0).abs().max() / g0.abs().max()).item() < 5e-6
