@@ -1251,6 +1251,128 @@ __global__ void __launch_bounds__(MAXT) k_tab_grad_mma(const __grid_constant__ T
   }
 }
 
+// fp32 flavour of the tensor-core backward: fp32 operands and results, cubic float4 coefficients (the fp32 form of
+// DPB200_TAB_COMPRESSED_COEF: ONE 16-byte request per (neighbour, channel)), the quintic's value and derivative on the
+// FP32 pipe (5 FMAs), the contraction on the FP64 tensor cores with fp64 accumulation (the only mma.sync shape
+// whose fragment ownership -- one A element per lane -- fits "each lane evaluates one (neighbour, channel)";
+// the products are exact in fp64, so this is also more accurate than the fp32 SIMT kernel).
+template <int KT>
+__global__ void __launch_bounds__(512) k_tab_grad_mma_f32(const __grid_constant__ TabParams<float> p) {
+  using FP = float;
+  const int lane = threadIdx.x & 31;
+  const int warp = threadIdx.x >> 5;
+  const int nw = blockDim.x >> 5;
+  FP* hot = reinterpret_cast<FP*>(tab_smem);
+  Rec<FP>* rec = reinterpret_cast<Rec<FP>*>(hot + p.hot_elems) + warp * 32;
+  const int M = p.M;
+  constexpr int MP = 4 * KT;
+  double* dyt = reinterpret_cast<double*>(reinterpret_cast<Rec<FP>*>(hot + p.hot_elems) + nw * 32) + warp * 5 * MP;
+  const int r0 = hot_window_start(p);
+  preload_hot(hot, p, r0);
+  __syncthreads();
+  const bool fuse_x = p.dy_dem_x == nullptr;
+  const int q = lane >> 2, kk = lane & 3;
+  const unsigned rowb = (unsigned)M * 16u;  // one float4 per channel
+  const unsigned off_k = (unsigned)kk * 16u;
+  const unsigned off_last = (unsigned)((4 * (KT - 1) + kk < M) ? 4 * (KT - 1) + kk : M - 1) * 16u;
+
+  const long long stride = (long long)gridDim.x * nw;
+  long long i = (long long)blockIdx.x * nw + warp;
+  int j0 = 0;
+  Pre<FP, false> pre;
+  load_pre(pre, p, i, 0, lane);
+  FP last = i < p.nloc ? p.em_x[i * p.ldx_i + (long long)(p.nnei - 1) * p.ldx_j] : (FP)0.;
+  const double* bsrc = dyt + (q < 4 ? q : 4) * MP + kk;
+  for (int e = lane; e < 5 * MP; e += 32) dyt[e] = 0.;
+  __syncwarp();
+
+  while (i < p.nloc) {
+    if (j0 == 0) {
+      const FP* __restrict__ dyi = p.dy + i * 4 * (long long)M;
+      __syncwarp();
+      for (int e = lane; e < 4 * M; e += 32) {
+        const int m = e / M;
+        dyt[m * MP + (e - m * M)] = (double)dyi[e];
+      }
+      __syncwarp();
+    }
+    bool done, any_delta;
+    const int nproc = stage_chunk<FP, false>(p, j0, last, pre, rec, nullptr, lane, done, any_delta);
+    const bool atom_end = done || j0 + 32 >= p.nnei;
+    const long long ni = atom_end ? i + stride : i;
+    const int nj0 = atom_end ? 0 : j0 + 32;
+    load_pre(pre, p, ni, nj0, lane);
+    FP nlast = last;
+    if (atom_end && ni < p.nloc) nlast = p.em_x[ni * p.ldx_i + (long long)(p.nnei - 1) * p.ldx_j];
+
+    FP* __restrict__ gem = p.dy_dem + i * p.ldem_i;
+    for (int s = 0; s < nproc; s += 8) {
+      const int nb = s + q;
+      const bool live = nb < nproc;
+      const Rec<FP>& r = rec[live ? nb : nproc - 1];
+      const FP xx = r.xx;
+      const FP dl = r.delta;
+      const unsigned rel = (unsigned)(r.idx - r0);
+      const bool inwin = rel < (unsigned)p.H;
+      double c1a = 0., c1b = 0., c2a = 0., c2b = 0.;
+#define DPB_GRAD32_STEPS(BASE)                                                                \
+  _Pragma("unroll") for (int t = 0; t < KT; ++t) {                                            \
+    const unsigned off = (t == KT - 1) ? off_last : (unsigned)t * 64u + off_k;                \
+    const float4 u = *reinterpret_cast<const float4*>((BASE) + off);                          \
+    const FP b2 = u.z + u.w * xx;                                                             \
+    const FP b1 = u.y + b2 * xx;                                                              \
+    FP g = u.x + b1 * xx;                                                                     \
+    const FP d2 = b2 + u.w * xx;                                                              \
+    const FP gd = b1 + d2 * xx;                                                               \
+    g += gd * dl;                                                                             \
+    const double bt = bsrc[4 * t];                                                            \
+    dmma884(c1a, c1b, (double)g, bt);                                                         \
+    dmma884(c2a, c2b, (double)gd, bt);                                                        \
+  }
+      if (__all_sync(kFull, inwin)) {
+        const char* b = reinterpret_cast<const char*>(hot) + rel * rowb;
+        DPB_GRAD32_STEPS(b)
+      } else if (!__any_sync(kFull, inwin)) {
+        const char* __restrict__ b = reinterpret_cast<const char*>(p.T) + (long long)r.idx * rowb;
+        DPB_GRAD32_STEPS(b)
+      } else {
+        const char* b = inwin ? reinterpret_cast<const char*>(hot) + rel * rowb
+                              : reinterpret_cast<const char*>(p.T) + (long long)r.idx * rowb;
+        DPB_GRAD32_STEPS(b)
+      }
+#undef DPB_GRAD32_STEPS
+      const double ea = (double)r.e[(2 * kk) & 3], eb = (double)r.e[(2 * kk + 1) & 3];
+      double part = kk < 2 ? ea * c2a + eb * c2b : 0.;
+      part += __shfl_xor_sync(kFull, part, 1);
+      if (live && kk < 2) {
+        const double mult = (double)r.mult;
+        const int j = j0 + nb;
+        double v0 = c1a * mult;
+        const double v1 = c1b * mult;
+        if (kk == 0) {
+          if (fuse_x)
+            v0 += part;
+          else
+            p.dy_dem_x[i * p.ldx_i + (long long)j * p.ldx_j] = (FP)part;
+        }
+        gem[(long long)j * 4 + 2 * kk] = (FP)v0;
+        gem[(long long)j * 4 + 2 * kk + 1] = (FP)v1;
+      }
+    }
+    if (atom_end) {
+      const int jend = j0 + nproc;
+      for (int j = jend + lane; j < p.nnei; j += 32) {
+        if (!fuse_x) p.dy_dem_x[i * p.ldx_i + (long long)j * p.ldx_j] = (FP)0.;
+#pragma unroll
+        for (int m = 0; m < 4; ++m) gem[(long long)j * 4 + m] = (FP)0.;
+      }
+    }
+    i = ni;
+    j0 = nj0;
+    last = nlast;
+  }
+}
+
 inline int grad_variant() {
   static const int v = [] {
     const char* e = getenv("DPB200_GRAD_VARIANT");
@@ -1634,6 +1756,33 @@ int launch_grad(FP* dy_dem_x, FP* dy_dem, FP* dy_dtwo, const FP* table, const FP
   const int grid = (int)(want < cap ? want : cap);
   cudaError_t e1 = cudaSuccess;
   bool launched = false;
+  if constexpr (std::is_same<FP, float>::value) {
+    if (cm32 && use_mma_path() && (kt == 8 || kt == 16 || kt == 20 || kt == 25 || kt == 32)) {
+      const int nwv = 16;
+      const size_t extra = (size_t)nwv * 5 * (4 * kt) * sizeof(double);
+      const size_t recv = (size_t)nwv * 32 * sizeof(Rec<FP>);
+      size_hot_window(p, M, recv + extra, p.nblk);
+      // the double tile behind the records must be 8-byte aligned: hot_elems is a multiple of 16 bytes, Rec is 32 bytes
+      const size_t smemv = (size_t)p.hot_elems * sizeof(FP) + recv + extra;
+      long long wantv = ((long long)nloc + nwv - 1) / nwv;
+      const int gridv = (int)(wantv < cap ? wantv : cap);
+#define DPB_LAUNCH_GRAD_MMA32(KT)                                                               \
+  do {                                                                                          \
+    auto kern = k_tab_grad_mma_f32<KT>;                                                         \
+    e1 = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemv);   \
+    if (e1 == cudaSuccess) kern<<<gridv, nwv * 32, smemv, st>>>(p);                             \
+  } while (0)
+      switch (kt) {
+        case 8: DPB_LAUNCH_GRAD_MMA32(8); break;
+        case 16: DPB_LAUNCH_GRAD_MMA32(16); break;
+        case 20: DPB_LAUNCH_GRAD_MMA32(20); break;
+        case 25: DPB_LAUNCH_GRAD_MMA32(25); break;
+        default: DPB_LAUNCH_GRAD_MMA32(32); break;
+      }
+#undef DPB_LAUNCH_GRAD_MMA32
+      launched = true;
+    }
+  }
   if constexpr (std::is_same<FP, double>::value) {
     if (mma_ok) {
       // variant 0: B fragments in registers, 12 warps; 1: in shared memory, 16 warps; 2: 24 warps
