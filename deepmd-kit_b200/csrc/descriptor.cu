@@ -250,8 +250,10 @@ __device__ __forceinline__ void dmma884d(double& c0, double& c1, double a, doubl
       : "d"(a), "d"(b));
 }
 
-__global__ void __launch_bounds__(256) k_desc_bwd_mma(double* __restrict__ dX, const double* __restrict__ dD,
-                                                      const double* __restrict__ X, const int* __restrict__ rows,
+// (FP = float: fp32 operands and results, the products and sums still run on the FP64 tensor cores)
+template <typename FP>
+__global__ void __launch_bounds__(256) k_desc_bwd_mma(FP* __restrict__ dX, const FP* __restrict__ dD,
+                                                      const FP* __restrict__ X, const int* __restrict__ rows,
                                                       long long nloc, int M, double scale) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int q = lane >> 2, kk = lane & 3;
@@ -259,16 +261,16 @@ __global__ void __launch_bounds__(256) k_desc_bwd_mma(double* __restrict__ dX, c
   const int KT = (M + 3) >> 2, NT = (M + 7) >> 3;
   for (long long i = (long long)blockIdx.x * 8 + warp; i < nloc; i += (long long)gridDim.x * 8) {
     const long long src = rows ? (long long)rows[i] : i;
-    const double* __restrict__ x = X + src * 4 * M + (long long)(q & 3) * M;
-    const double* __restrict__ g = dD + i * (long long)M * 16;
+    const FP* __restrict__ x = X + src * 4 * M + (long long)(q & 3) * M;
+    const FP* __restrict__ g = dD + i * (long long)M * 16;
     double c00 = 0., c01 = 0., c10 = 0., c11 = 0., d00 = 0., d01 = 0., d10 = 0., d11 = 0.;
     double as[4];
     // term 2 (first four steps unrolled: their A fragments are term 1's)
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       const int ch = 4 * j + kk;  // < 16 <= M
-      as[j] = q < 4 ? x[ch] : 0.;
-      const double b0 = __ldg(g + ch * 16 + q), b1 = __ldg(g + ch * 16 + q + 8);
+      as[j] = q < 4 ? (double)x[ch] : 0.;
+      const double b0 = (double)__ldg(g + ch * 16 + q), b1 = (double)__ldg(g + ch * 16 + q + 8);
       if (j & 1) {
         dmma884d(d00, d01, as[j], b0);
         dmma884d(d10, d11, as[j], b1);
@@ -282,8 +284,8 @@ __global__ void __launch_bounds__(256) k_desc_bwd_mma(double* __restrict__ dX, c
       const int ch = 4 * j + kk;
       const bool ok = ch < M;
       const int chc = ok ? ch : M - 1;
-      const double a = (q < 4 && ok) ? x[chc] : 0.;
-      const double b0 = __ldg(g + chc * 16 + q), b1 = __ldg(g + chc * 16 + q + 8);
+      const double a = (q < 4 && ok) ? (double)x[chc] : 0.;
+      const double b0 = (double)__ldg(g + chc * 16 + q), b1 = (double)__ldg(g + chc * 16 + q + 8);
       if (j & 1) {
         dmma884d(d00, d01, a, b0);
         dmma884d(d10, d11, a, b1);
@@ -294,22 +296,22 @@ __global__ void __launch_bounds__(256) k_desc_bwd_mma(double* __restrict__ dX, c
     }
     c00 += d00, c01 += d01, c10 += d10, c11 += d11;
     // term 1
-    double* __restrict__ o = dX + src * 4 * M + (long long)(q & 3) * M;
+    FP* __restrict__ o = dX + src * 4 * M + (long long)(q & 3) * M;
 #pragma unroll 2
     for (int t = 0; t < NT; ++t) {
       const int row = 8 * t + q;
-      const double* __restrict__ gr = g + (long long)(row < M ? row : M - 1) * 16 + kk;
+      const FP* __restrict__ gr = g + (long long)(row < M ? row : M - 1) * 16 + kk;
       double e0 = t == 0 ? c00 : (t == 1 ? c10 : 0.);
       double e1 = t == 0 ? c01 : (t == 1 ? c11 : 0.);
-      const double b0 = __ldg(gr), b1 = __ldg(gr + 4), b2 = __ldg(gr + 8), b3 = __ldg(gr + 12);
+      const double b0 = (double)__ldg(gr), b1 = (double)__ldg(gr + 4), b2 = (double)__ldg(gr + 8), b3 = (double)__ldg(gr + 12);
       dmma884d(e0, e1, as[0], b0);
       dmma884d(e0, e1, as[1], b1);
       dmma884d(e0, e1, as[2], b2);
       dmma884d(e0, e1, as[3], b3);
       if (q < 4) {
         const int ch = 8 * t + 2 * kk;
-        if (ch < M) o[ch] = e0 * s2;
-        if (ch + 1 < M) o[ch + 1] = e1 * s2;
+        if (ch < M) o[ch] = (FP)(e0 * s2);
+        if (ch + 1 < M) o[ch + 1] = (FP)(e1 * s2);
       }
     }
   }
@@ -379,13 +381,12 @@ int desc_launch(bool bwd, FP* out, const FP* dD, const FP* X, const int* rows, l
   long long want = (nloc + 3) / 4;
   const bool v2 = bwd && M <= 128 && axis % 4 == 0 && axis <= 32 &&
                   (reinterpret_cast<uintptr_t>(dD) & 15) == 0 && ((long long)M * axis * sizeof(FP)) % 16 == 0;
-  if (bwd && sizeof(FP) == 8 && axis == 16 && M >= 16 && desc_mma_enabled()) {
+  if (bwd && axis == 16 && M >= 16 && desc_mma_enabled()) {
     want = (nloc + 7) / 8;
-    auto kern = k_desc_bwd_mma;
+    auto kern = k_desc_bwd_mma<FP>;
     DPB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, 256, 0));
     long long cap = (long long)sm_count() * (occ < 1 ? 1 : occ);
-    kern<<<(int)(want < cap ? want : cap), 256, 0, st>>>(reinterpret_cast<double*>(out), reinterpret_cast<const double*>(dD),
-                                                         reinterpret_cast<const double*>(X), rows, nloc, M, scale);
+    kern<<<(int)(want < cap ? want : cap), 256, 0, st>>>(out, dD, X, rows, nloc, M, scale);
   } else if (v2) {
     want = (nloc + 3) / 4;
     const int nc = M <= 32 ? 1 : (M <= 64 ? 2 : 4);
