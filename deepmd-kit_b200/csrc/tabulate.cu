@@ -1565,8 +1565,12 @@ int launch_fwd(FP* out, const FP* table, const FP* info, const FP* em_x, long lo
   // compressed coefficients in the SIMT forward: a3..a5 stay fp32 in the row cache and the top two Horner steps
   // run on the FP32 pipe (widening them to fp64 at fetch time instead was measured 8 % SLOWER than the full table)
   const bool cm = (flags & DPB200_TAB_COMPRESSED_COEF) && !GG && two == nullptr && !use_mma_fwd() && fwd_cm_enabled();
-  if (da) {
-    const bool plain = !GG && two == nullptr && nnei > 0;
+  if (GG && da) {
+    set_error("tabulate+descriptor: plain se_a forward only");
+    return DPB200_ERR_INVALID;
+  }
+  if constexpr (!GG) if (da) {
+    const bool plain = two == nullptr && nnei > 0;
     DPB_REQUIRE(plain, "tabulate+descriptor: plain se_a forward with nnei > 0 only");
     DPB_REQUIRE(da->desc != nullptr && (da->mode == 1 || da->mode == 2), "tabulate+descriptor: desc is null / bad mode");
     DPB_REQUIRE(M <= 128 && da->axis >= 1 && da->axis <= 32 && da->axis <= M,
