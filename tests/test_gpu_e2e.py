@@ -146,3 +146,41 @@ def test_atom_chunked_evaluation_matches_one_slab(pkg, dtype):
             assert rel(a, b) <= tol
         got2 = dp.eval(coord.reshape(1, -1), box.reshape(1, 9), atype)  # graph replay / list reuse
         assert rel(got2[1], ref[1]) <= tol
+
+
+@pytest.mark.parametrize("dtype", [torch.float64, torch.float32])
+def test_properties_at_full_benchmark_size(pkg, dtype):
+    """BASELINE config 2 at its full size (20^3 replicas = 1 536 000 atoms, variant A: exact replication, so every
+    distance tie of the formatter is exercised 8000 times): energy extensive, every replica carries the forces of the
+    192-atom cell, net force zero, virial extensive and symmetric.  Runs the production path (CUDA graph, fused
+    descriptor epilogue, split-operand fitting net, tensor-core backward)."""
+    from deepmd_kit_b200.model import DeepPotB200, SeAConfig, SeAModel
+
+    free, _ = torch.cuda.mem_get_info()
+    if free < 100e9:
+        pytest.skip("needs ~80 GB of free device memory")
+    tol = 1e-10 if dtype == torch.float64 else 2e-5
+    model = SeAModel(SeAConfig(), dtype, "cuda:0")
+    c1, t1, b1 = g.water_box(1)
+    e1, f1, v1 = DeepPotB200(model).eval(c1.reshape(1, -1), b1.reshape(1, 9), t1)
+    n = 20
+    c, t, b = g.water_box(n)
+    dp = DeepPotB200(model)
+    e, f, v = dp.eval(c.reshape(1, -1), b.reshape(1, 9), t)
+    nrep = n ** 3
+    assert abs(e[0, 0] - nrep * e1[0, 0]) <= 10 * tol * abs(e[0, 0])
+    fmax = np.abs(f1[0]).max()
+    # fp32: coordinates up to 249 A carry 1.5e-5 A of representation error (the reference forms rij in FPTYPE too),
+    # which the stiff O-H bonds turn into ~1e-3 eV/A force differences between replicas
+    ftol = tol if dtype == torch.float64 else 2e-3
+    assert np.abs(f[0].reshape(nrep, 192, 3) - f1[0][None]).max() <= ftol * fmax
+    assert np.abs(f[0].astype(np.float64).sum(0)).max() <= ftol * fmax * nrep ** 0.5 * 10
+    vtol = 10 * tol if dtype == torch.float64 else 2e-3
+    assert np.abs(v[0] - nrep * v1[0]).max() <= vtol * np.abs(v[0]).max()
+    vm = v[0].reshape(3, 3)
+    assert np.abs(vm - vm.T).max() <= vtol * np.abs(vm).max()
+    # second evaluation replays the graph on the reused list
+    e2, f2, _ = dp.eval(c.reshape(1, -1), b.reshape(1, 9), t)
+    assert np.abs(f2[0] - f[0]).max() <= ftol * fmax
+    del dp
+    torch.cuda.empty_cache()
