@@ -298,7 +298,9 @@ class SeAModel:
         dim_d = self.M * cfg.axis_neuron
         self.fit = [FittingNet(dim_d, cfg.fitting_neuron, cfg.fitting_resnet_dt, cfg.seed + 101 * t, dtype, self.device)
                     for t in range(cfg.ntypes)]
-        self.fit_chunk = 1 << 17
+        import os as _os
+
+        self.fit_chunk = int(_os.environ.get("DPB200_FIT_CHUNK", str(1 << 17)))
         # Tensor-core fitting net (csrc/fitting.cu): the descriptor leaves the tabulate forward already split
         # (int8 slices in fp64, TF32 head/tail in fp32).  Needs axis == 16 (fp64) / axis % 4 == 0 (fp32),
         # M <= 128 and a first fitting layer without skip connection.
