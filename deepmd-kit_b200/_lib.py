@@ -33,6 +33,9 @@ _SIGS = {
     "prod_virial_a_{s}": "pppppp iii p",
     "prod_force_virial_a_{s}": "ppppppp iii p",
     "prod_force_virial_a_ex_{s}": "ppppppp iiiii p",
+    "prod_force_grad_a_{s}": "pppp iii p",
+    "prod_force_grad_a_ex_{s}": "pppp iiii p",
+    "prod_virial_grad_a_{s}": "ppppp ii p",
     "normalize_coord_{s}": "pip p",
     "copy_coord_{s}": "pppp pp ii f p pz p",
     "copy_coord_cells_{s}": "pppp pp ii pp p pz p",

@@ -27,7 +27,9 @@
 #include "neighbor_list.h"
 #include "prod_env_mat.h"
 #include "prod_force.h"
+#include "prod_force_grad.h"
 #include "prod_virial.h"
+#include "prod_virial_grad.h"
 #include "region.h"
 #include "tabulate.h"
 
@@ -81,6 +83,8 @@ struct Fn<double> {
   static constexpr auto tab_gg = dpb200_tabulate_fusion_se_a_grad_grad_f64;
   static constexpr auto force = dpb200_prod_force_a_f64;
   static constexpr auto virial = dpb200_prod_virial_a_f64;
+  static constexpr auto force_grad = dpb200_prod_force_grad_a_f64;
+  static constexpr auto virial_grad = dpb200_prod_virial_grad_a_f64;
   static constexpr auto normalize = dpb200_normalize_coord_f64;
   static constexpr auto copy_coord = dpb200_copy_coord_cells_f64;
   static constexpr auto build = dpb200_build_nlist_f64;
@@ -94,6 +98,8 @@ struct Fn<float> {
   static constexpr auto tab_gg = dpb200_tabulate_fusion_se_a_grad_grad_f32;
   static constexpr auto force = dpb200_prod_force_a_f32;
   static constexpr auto virial = dpb200_prod_virial_a_f32;
+  static constexpr auto force_grad = dpb200_prod_force_grad_a_f32;
+  static constexpr auto virial_grad = dpb200_prod_virial_grad_a_f32;
   static constexpr auto normalize = dpb200_normalize_coord_f32;
   static constexpr auto copy_coord = dpb200_copy_coord_cells_f32;
   static constexpr auto build = dpb200_build_nlist_f32;
@@ -197,6 +203,21 @@ DPB_EXPORT void prod_virial_a_gpu(FPTYPE* virial, FPTYPE* atom_virial, const FPT
   sync_default_stream("prod_virial_a_gpu");
 }
 
+// source/lib/include/prod_force_grad.h:26-33, prod_virial_grad.h:26-33
+template <typename FPTYPE>
+DPB_EXPORT void prod_force_grad_a_gpu(FPTYPE* grad_net, const FPTYPE* grad, const FPTYPE* env_deriv, const int* nlist,
+                                      const int nloc, const int nnei, const int nframes) {
+  check(Fn<FPTYPE>::force_grad(grad_net, grad, env_deriv, nlist, nloc, nnei, nframes, nullptr), "prod_force_grad_a_gpu");
+  sync_default_stream("prod_force_grad_a_gpu");
+}
+
+template <typename FPTYPE>
+DPB_EXPORT void prod_virial_grad_a_gpu(FPTYPE* grad_net, const FPTYPE* grad, const FPTYPE* env_deriv,
+                                       const FPTYPE* rij, const int* nlist, const int nloc, const int nnei) {
+  check(Fn<FPTYPE>::virial_grad(grad_net, grad, env_deriv, rij, nlist, nloc, nnei, nullptr), "prod_virial_grad_a_gpu");
+  sync_default_stream("prod_virial_grad_a_gpu");
+}
+
 DPB_EXPORT void use_nlist_map(int* nlist, const int* nlist_map, const int nloc, const int nnei) {
   check(dpb200_use_nlist_map(nlist, nlist_map, nloc, nnei, nullptr), "use_nlist_map");
   sync_default_stream("use_nlist_map");
@@ -285,6 +306,8 @@ DPB_EXPORT int build_nlist_gpu(InputNlist& nlist, int* max_list_size, int* nlist
                                      const int);                                                                     \
   template void prod_virial_a_gpu<FP>(FP*, FP*, const FP*, const FP*, const FP*, const int*, const int, const int,    \
                                       const int);                                                                    \
+  template void prod_force_grad_a_gpu<FP>(FP*, const FP*, const FP*, const int*, const int, const int, const int);    \
+  template void prod_virial_grad_a_gpu<FP>(FP*, const FP*, const FP*, const FP*, const int*, const int, const int);   \
   template void normalize_coord_gpu<FP>(FP*, const int, const deepmd::Region<FP>&);                                   \
   template int copy_coord_gpu<FP>(FP*, int*, int*, int*, int*, const FP*, const int*, const int&, const int&,         \
                                   const int&, const int&, const int*, const deepmd::Region<FP>&);                    \

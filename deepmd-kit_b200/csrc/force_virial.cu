@@ -153,6 +153,83 @@ __global__ void __launch_bounds__(128) k_force_virial(const __grid_constant__ Fv
   }
 }
 
+// ------------------------------------------------------------------------------------------
+// Gradients of prod_force_a / prod_virial_a with respect to net_deriv (the backward of the force / virial
+// outputs when a compressed model is trained on forces and virials): deepmd::prod_force_grad_a_gpu
+// (source/lib/include/prod_force_grad.h:26-33, CPU semantics src/prod_force_grad.cc:22-77) and
+// deepmd::prod_virial_grad_a_gpu (prod_virial_grad.h:26-33, src/prod_virial_grad.cc:21-63).
+//   force : gn[r][4k+c] = sum_d ( g[frame][j][d] - g[r][d] ) * ed[r][4k+c][d],  j = nlist[r][k] (j >= nloc -> j % nloc;
+//           j < 0: only the centre term)
+//   virial: gn[i][4k+c] = sum_{d0,d1} g[d0][d1] * rij[i][k][d1] * ed[i][4k+c][d0]   (0 for j < 0)
+// Pure streaming ops (read 12 values, write 1 per element): one thread per output element, the three
+// derivative components of consecutive elements are consecutive in memory.
+// ------------------------------------------------------------------------------------------
+template <typename FP>
+__global__ void k_force_grad(FP* __restrict__ gn, const FP* __restrict__ g, const FP* __restrict__ ed,
+                             const int* __restrict__ nlist, int nloc, int ngrad, int nnei, long long nrows) {
+  // grad holds `ngrad` atoms per frame (the reference op: ngrad == nloc; the adjoint of a scatter into nall
+  // atoms: ngrad == nall); neighbour indices beyond it are folded with j % ngrad
+  const long long n = nrows * nnei * 4;
+  for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < n; e += (long long)gridDim.x * blockDim.x) {
+    const long long rk = e >> 2;  // (row, neighbour slot)
+    const long long r = rk / nnei;
+    const long long frame = r / nloc;
+    int j = nlist[rk];
+    if (j >= ngrad) j = j % ngrad;
+    const FP* __restrict__ d = ed + e * 3;
+    const FP* __restrict__ gi = g + (frame * ngrad + (r - frame * nloc)) * 3;
+    FP gx = -gi[0], gy = -gi[1], gz = -gi[2];
+    if (j >= 0) {
+      const FP* __restrict__ gj = g + (frame * ngrad + j) * 3;
+      gx += gj[0], gy += gj[1], gz += gj[2];
+    }
+    // the reference accumulates centre and neighbour terms separately; the difference is rounding only
+    gn[e] = gx * d[0] + gy * d[1] + gz * d[2];
+  }
+}
+
+template <typename FP>
+__global__ void k_virial_grad(FP* __restrict__ gn, const FP* __restrict__ g, const FP* __restrict__ ed,
+                              const FP* __restrict__ rij, const int* __restrict__ nlist, int nnei, long long nloc) {
+  const long long n = nloc * nnei * 4;
+  FP gg[9];
+#pragma unroll
+  for (int k = 0; k < 9; ++k) gg[k] = g[k];
+  for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < n; e += (long long)gridDim.x * blockDim.x) {
+    const long long ik = e >> 2;
+    FP v = (FP)0.;
+    if (nlist[ik] >= 0) {
+      const FP* __restrict__ d = ed + e * 3;
+      const FP* __restrict__ rr = rij + ik * 3;
+#pragma unroll
+      for (int d0 = 0; d0 < 3; ++d0) v += (gg[d0 * 3] * rr[0] + gg[d0 * 3 + 1] * rr[1] + gg[d0 * 3 + 2] * rr[2]) * d[d0];
+    }
+    gn[e] = v;
+  }
+}
+
+template <typename FP>
+int launch_fv_grad(bool virial, FP* grad_net, const FP* grad, const FP* in_deriv, const FP* rij, const int* nlist,
+                   int nloc, int nnei, int nframes, cudaStream_t st, int ngrad = -1) {
+  if (ngrad < 0) ngrad = nloc;
+  DPB_REQUIRE(nloc >= 0 && nnei >= 0 && nframes >= 1 && ngrad >= nloc,
+              "prod_force/virial_grad: need nloc, nnei >= 0, nframes >= 1, ngrad >= nloc");
+  const long long nrows = (long long)nframes * nloc;
+  const long long n = nrows * nnei * 4;
+  if (n == 0) return DPB200_OK;
+  DPB_REQUIRE(grad_net && grad && in_deriv && nlist && (!virial || rij), "prod_force/virial_grad: null pointer");
+  int grid = ceil_div(n, 256);
+  const int cap = sm_count() * 16;
+  if (grid > cap) grid = cap;
+  if (virial)
+    k_virial_grad<FP><<<grid, 256, 0, st>>>(grad_net, grad, in_deriv, rij, nlist, nnei, nrows);
+  else
+    k_force_grad<FP><<<grid, 256, 0, st>>>(grad_net, grad, in_deriv, nlist, nloc, ngrad, nnei, nrows);
+  DPB_CUDA(cudaGetLastError());
+  note_launches(1);
+  return DPB200_OK;
+}
+
 template <typename FP, bool FORCE, bool VIRIAL>
 int launch_fv(FP* force, FP* virial, FP* atom_virial, const FP* net_deriv, const FP* in_deriv,
               const FP* rij, const int* nlist, int nloc, int nall, int nnei, int nframes,
@@ -248,6 +325,29 @@ extern "C" {
   }
 DPB200_DEF_FV(f64, double)
 DPB200_DEF_FV(f32, float)
+
+#define DPB200_DEF_FVG(SUF, FP)                                                                    \
+  int dpb200_prod_force_grad_a_##SUF(FP* grad_net, const FP* grad, const FP* in_deriv,             \
+                                     const int* nlist, int nloc, int nnei, int nframes,            \
+                                     dpb200_stream_t stream) {                                     \
+    return dpb200::launch_fv_grad<FP>(false, grad_net, grad, in_deriv, nullptr, nlist, nloc, nnei, \
+                                      nframes, (cudaStream_t)stream);                              \
+  }                                                                                                \
+  int dpb200_prod_force_grad_a_ex_##SUF(FP* grad_net, const FP* grad, const FP* in_deriv,          \
+                                        const int* nlist, int nloc, int ngrad, int nnei,           \
+                                        int nframes, dpb200_stream_t stream) {                     \
+    return dpb200::launch_fv_grad<FP>(false, grad_net, grad, in_deriv, nullptr, nlist, nloc, nnei, \
+                                      nframes, (cudaStream_t)stream, ngrad);                       \
+  }                                                                                                \
+  int dpb200_prod_virial_grad_a_##SUF(FP* grad_net, const FP* grad, const FP* in_deriv,            \
+                                      const FP* rij, const int* nlist, int nloc, int nnei,         \
+                                      dpb200_stream_t stream) {                                    \
+    return dpb200::launch_fv_grad<FP>(true, grad_net, grad, in_deriv, rij, nlist, nloc, nnei, 1,   \
+                                      (cudaStream_t)stream);                                       \
+  }
+DPB200_DEF_FVG(f64, double)
+DPB200_DEF_FVG(f32, float)
+#undef DPB200_DEF_FVG
 #undef DPB200_DEF_FV
 
 int dpb200_use_nlist_map(int* nlist, const int* nlist_map, int nloc, int nnei, dpb200_stream_t stream) {

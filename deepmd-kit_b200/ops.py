@@ -434,6 +434,33 @@ def prod_force_virial_a(net_deriv, in_deriv, rij, nlist, nloc, nall, nnei, atom_
     return force, virial, av
 
 
+def prod_force_grad_a(grad, in_deriv, nlist, nloc, nnei, nframes=1, ngrad=None):
+    """deepmd::prod_force_grad_a_gpu (source/lib/include/prod_force_grad.h:26-33): gradient of prod_force_a with
+    respect to net_deriv, grad [nframes, ngrad*3] -> grad_net [nframes*nloc, nnei*4].  ngrad (default nloc, the
+    reference op): atoms per frame in `grad`; neighbour indices beyond it are folded with j % ngrad."""
+    dev = _need_cuda(("grad", grad), ("in_deriv", in_deriv), ("nlist", nlist))
+    s = _suffix(grad)
+    dt = grad.dtype
+    grad, in_deriv, nlist = _c(grad), _c(in_deriv, dt), _c(nlist, torch.int32)
+    ngrad = nloc if ngrad is None else int(ngrad)
+    out = torch.empty((nframes * nloc, nnei * 4), dtype=dt, device=dev)
+    lib().call("prod_force_grad_a_ex_" + s, _p(out), _p(grad), _p(in_deriv), _p(nlist), int(nloc), ngrad, int(nnei),
+               int(nframes), _stream(dev))
+    return out
+
+
+def prod_virial_grad_a(grad, in_deriv, rij, nlist, nloc, nnei):
+    """deepmd::prod_virial_grad_a_gpu (prod_virial_grad.h:26-33): grad [9] -> grad_net [nloc, nnei*4]."""
+    dev = _need_cuda(("grad", grad), ("in_deriv", in_deriv), ("rij", rij), ("nlist", nlist))
+    s = _suffix(grad)
+    dt = grad.dtype
+    grad, in_deriv, rij, nlist = _c(grad), _c(in_deriv, dt), _c(rij, dt), _c(nlist, torch.int32)
+    out = torch.empty((nloc, nnei * 4), dtype=dt, device=dev)
+    lib().call("prod_virial_grad_a_" + s, _p(out), _p(grad), _p(in_deriv), _p(rij), _p(nlist), int(nloc), int(nnei),
+               _stream(dev))
+    return out
+
+
 def prod_force_virial_a_ex(force, virial, atom_virial, net_deriv, in_deriv, rij, nlist, nrows, center_offset, nall,
                            nnei, accumulate):
     """Atom-chunked fused scatter into caller-provided force[nall*3] / virial[9] / atom_virial|None."""
@@ -892,7 +919,7 @@ def _op_prod_force_se_a(net_deriv, in_deriv, nlist, natoms, n_a_sel: int, n_r_se
         raise ValueError("number of samples should match")
     if nloc * nnei * 4 != net_deriv.shape[1] or nloc * nnei * 12 != in_deriv.shape[1] or nloc * nnei != nlist.shape[1]:
         raise ValueError("number of descriptors should match")
-    return prod_force_a(net_deriv, in_deriv, nlist, nloc, nall, nnei, nf)
+    return _ForceOp.apply(net_deriv, in_deriv, nlist, nloc, nall, nnei)
 
 
 def _op_prod_virial_se_a(net_deriv, in_deriv, rij, nlist, natoms, n_a_sel: int, n_r_sel: int):
@@ -912,6 +939,84 @@ def _op_prod_virial_se_a(net_deriv, in_deriv, rij, nlist, natoms, n_a_sel: int, 
         vs.append(v.reshape(1, 9))
         avs.append(av.reshape(1, -1))
     return torch.cat(vs, 0), torch.cat(avs, 0)
+
+
+def _natoms(natoms):
+    nat = natoms.detach().to("cpu").reshape(-1).tolist()
+    return int(nat[0]), int(nat[1])
+
+
+def _op_prod_force_se_a_grad(grad, net_deriv, in_deriv, nlist, natoms, n_a_sel: int, n_r_sel: int):
+    """ProdForceSeAGrad (source/op/tf/prod_force_grad_multi_device.cc:5-14, 36-160): grad [nf, nloc*3]."""
+    nloc, _ = _natoms(natoms)
+    nnei = int(n_a_sel) + int(n_r_sel)
+    if grad.dim() != 2 or net_deriv.dim() != 2 or in_deriv.dim() != 2 or nlist.dim() != 2:
+        raise ValueError("Dim of grad, net deriv, input deriv and nlist should be 2")
+    nf = net_deriv.shape[0]
+    if grad.shape[0] != nf or in_deriv.shape[0] != nf or nlist.shape[0] != nf:
+        raise ValueError("number of frames should match")
+    if grad.shape[1] != nloc * 3:
+        raise ValueError("input grad shape should be 3 x natoms")
+    if nloc * nnei * 12 != in_deriv.shape[1] or nloc * nnei != nlist.shape[1]:
+        raise ValueError("number of descriptors should match")
+    return prod_force_grad_a(grad, in_deriv, nlist, nloc, nnei, nf).reshape(nf, -1)
+
+
+def _op_prod_virial_se_a_grad(grad, net_deriv, in_deriv, rij, nlist, natoms, n_a_sel: int, n_r_sel: int):
+    """ProdVirialSeAGrad (source/op/tf/prod_virial_grad_multi_device.cc:5-15, 37-170): grad [nf, 9]."""
+    nloc, _ = _natoms(natoms)
+    nnei = int(n_a_sel) + int(n_r_sel)
+    if grad.dim() != 2 or net_deriv.dim() != 2 or in_deriv.dim() != 2 or rij.dim() != 2 or nlist.dim() != 2:
+        raise ValueError("Dim of grad, net deriv, input deriv, rij and nlist should be 2")
+    nf = net_deriv.shape[0]
+    if grad.shape[0] != nf or grad.shape[1] != 9:
+        raise ValueError("input grad shape should be 3 x 3")
+    if nloc * nnei * 12 != in_deriv.shape[1] or nloc * nnei * 3 != rij.shape[1] or nloc * nnei != nlist.shape[1]:
+        raise ValueError("number of descriptors should match")
+    return torch.cat([prod_virial_grad_a(grad[f], in_deriv[f], rij[f], nlist[f], nloc, nnei).reshape(1, -1)
+                      for f in range(nf)], 0)
+
+
+class _ForceOp(torch.autograd.Function):
+    """prod_force_se_a, differentiable in net_deriv (deepmd/tf/op/_prod_force_se_a_grad.py)."""
+
+    @staticmethod
+    def forward(ctx, net_deriv, in_deriv, nlist, nloc, nall, nnei):
+        ctx.save_for_backward(in_deriv, nlist)
+        ctx.dims = (nloc, nall, nnei, net_deriv.shape[0])
+        return prod_force_a(net_deriv, in_deriv, nlist, nloc, nall, nnei, net_deriv.shape[0])
+
+    @staticmethod
+    def backward(ctx, g):
+        in_deriv, nlist = ctx.saved_tensors
+        nloc, nall, nnei, nf = ctx.dims
+        gn = prod_force_grad_a(g.contiguous(), in_deriv, nlist, nloc, nnei, nf, ngrad=nall)
+        return gn.reshape(nf, -1), None, None, None, None, None
+
+
+class _VirialOp(torch.autograd.Function):
+    """prod_virial_se_a, differentiable in net_deriv through the virial output (_prod_virial_se_a_grad.py)."""
+
+    @staticmethod
+    def forward(ctx, net_deriv, in_deriv, rij, nlist, nloc, nall, nnei):
+        ctx.save_for_backward(in_deriv, rij, nlist)
+        ctx.dims = (nloc, nnei, net_deriv.shape[0])
+        vs, avs = [], []
+        for f in range(net_deriv.shape[0]):
+            v, av = prod_virial_a(net_deriv[f], in_deriv[f], rij[f], nlist[f], nloc, nall, nnei)
+            vs.append(v.reshape(1, 9))
+            avs.append(av.reshape(1, -1))
+        av = torch.cat(avs, 0)
+        ctx.mark_non_differentiable(av)
+        return torch.cat(vs, 0), av
+
+    @staticmethod
+    def backward(ctx, gv, _gav):
+        in_deriv, rij, nlist = ctx.saved_tensors
+        nloc, nnei, nf = ctx.dims
+        gn = torch.cat([prod_virial_grad_a(gv[f].contiguous(), in_deriv[f], rij[f], nlist[f], nloc, nnei).reshape(1, -1)
+                        for f in range(nf)], 0)
+        return gn, None, None, None, None, None, None
 
 
 _REGISTERED = False
@@ -939,7 +1044,14 @@ def register_torch_ops():
     L.impl("tabulate_fusion_se_a", _op_tabulate_fusion_se_a, "CompositeImplicitAutograd")
     L.impl("tabulate_fusion_se_atten", _op_tabulate_fusion_se_atten, "CompositeImplicitAutograd")
     L.impl("prod_env_mat_a", _op_prod_env_mat_a, "CompositeExplicitAutograd")
-    L.impl("prod_force_se_a", _op_prod_force_se_a, "CompositeExplicitAutograd")
-    L.impl("prod_virial_se_a", _op_prod_virial_se_a, "CompositeExplicitAutograd")
+    L.define("prod_force_se_a_grad(Tensor grad, Tensor net_deriv, Tensor in_deriv, Tensor nlist, Tensor natoms, "
+             "int n_a_sel, int n_r_sel) -> Tensor")
+    L.define("prod_virial_se_a_grad(Tensor grad, Tensor net_deriv, Tensor in_deriv, Tensor rij, Tensor nlist, "
+             "Tensor natoms, int n_a_sel, int n_r_sel) -> Tensor")
+    # (CompositeImplicitAutograd: the autograd.Function inside provides the derivative w.r.t. net_deriv)
+    L.impl("prod_force_se_a", _op_prod_force_se_a, "CompositeImplicitAutograd")
+    L.impl("prod_virial_se_a", _op_prod_virial_se_a, "CompositeImplicitAutograd")
+    L.impl("prod_force_se_a_grad", _op_prod_force_se_a_grad, "CompositeExplicitAutograd")
+    L.impl("prod_virial_se_a_grad", _op_prod_virial_se_a_grad, "CompositeExplicitAutograd")
     _LIBRARY = L
     _REGISTERED = True

@@ -192,6 +192,27 @@ DPB200_DECL_FV(f64, double)
 DPB200_DECL_FV(f32, float)
 #undef DPB200_DECL_FV
 
+/* Gradients of the two scatters with respect to net_deriv (backward of force / virial when a compressed
+ * model is trained).  Replace deepmd::prod_force_grad_a_gpu (source/lib/include/prod_force_grad.h:26-33;
+ * CPU semantics source/lib/src/prod_force_grad.cc:22-77: grad [nframes*nloc*3], neighbour indices >= nloc are
+ * folded with j % nloc) and deepmd::prod_virial_grad_a_gpu (prod_virial_grad.h:26-33; prod_virial_grad.cc:21-63:
+ * grad [9], one frame).  grad_net [nframes*nloc*nnei*4] is fully written. */
+#define DPB200_DECL_FVG(SUF, FP)                                                                   \
+  int dpb200_prod_force_grad_a_##SUF(FP* grad_net, const FP* grad, const FP* in_deriv,             \
+                                     const int* nlist, int nloc, int nnei, int nframes,            \
+                                     dpb200_stream_t stream);                                      \
+  /* same with grad holding `ngrad` >= nloc atoms per frame (fold modulus ngrad): with ngrad = nall   \
+   * this is the exact adjoint of dpb200_prod_force_a for forces on ghost atoms */                  \
+  int dpb200_prod_force_grad_a_ex_##SUF(FP* grad_net, const FP* grad, const FP* in_deriv,          \
+                                        const int* nlist, int nloc, int ngrad, int nnei,           \
+                                        int nframes, dpb200_stream_t stream);                      \
+  int dpb200_prod_virial_grad_a_##SUF(FP* grad_net, const FP* grad, const FP* in_deriv,            \
+                                      const FP* rij, const int* nlist, int nloc, int nnei,         \
+                                      dpb200_stream_t stream);
+DPB200_DECL_FVG(f64, double)
+DPB200_DECL_FVG(f32, float)
+#undef DPB200_DECL_FVG
+
 /* ---------------------------------------------------------------------------------------
  * Neighbour-list front end (cell list; the reference GPU path is O(nloc*nall)).
  *  normalize_coord : deepmd::normalize_coord_gpu (source/lib/include/coord.h:47-55)

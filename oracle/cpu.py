@@ -242,6 +242,35 @@ class CpuLib:
                    _p(nlist), C.c_int(nloc), C.c_int(nall), C.c_int(nnei))
         return virial, atom_virial
 
+    # -- f2: gradients of a11 / a12 w.r.t. net_deriv -----------------------------------
+    def prod_force_grad_a(self, grad, env_deriv, nlist, nframes=1):
+        """grad [nframes*nloc, 3] -> grad_net [nframes*nloc, nnei*4]; nlist [nframes*nloc, nnei]."""
+        grad = np.ascontiguousarray(grad)
+        dt = grad.dtype
+        s = _fp(dt)
+        env_deriv = np.ascontiguousarray(env_deriv, dtype=dt)
+        nlist = np.ascontiguousarray(nlist, dtype=np.int32)
+        nrow, nnei = nlist.shape
+        nloc = nrow // nframes
+        out = np.zeros((nrow, nnei * 4), dt)
+        self._call("prod_force_grad_a_" + s, _p(out), _p(grad), _p(env_deriv), _p(nlist), C.c_int(nloc), C.c_int(nnei),
+                   C.c_int(nframes))
+        return out
+
+    def prod_virial_grad_a(self, grad, env_deriv, rij, nlist):
+        """grad [9] -> grad_net [nloc, nnei*4]."""
+        grad = np.ascontiguousarray(grad)
+        dt = grad.dtype
+        s = _fp(dt)
+        env_deriv = np.ascontiguousarray(env_deriv, dtype=dt)
+        rij = np.ascontiguousarray(rij, dtype=dt)
+        nlist = np.ascontiguousarray(nlist, dtype=np.int32)
+        nloc, nnei = nlist.shape
+        out = np.zeros((nloc, nnei * 4), dt)
+        self._call("prod_virial_grad_a_" + s, _p(out), _p(grad), _p(env_deriv), _p(rij), _p(nlist), C.c_int(nloc),
+                   C.c_int(nnei))
+        return out
+
     # -- a2 / a3 / a4 --------------------------------------------------------------
     def normalize_coord(self, coord, box):
         coord = np.array(coord, copy=True, order="C")

@@ -11,6 +11,7 @@
 //   source/lib/include/tabulate.h:28-68       (tabulate_fusion_se_a{,_grad,_grad_grad}_cpu)
 //   source/lib/include/prod_force.h:19-27     (prod_force_a_cpu)
 //   source/lib/include/prod_virial.h:6-15     (prod_virial_a_cpu)
+//   source/lib/include/prod_force_grad.h:8-15, prod_virial_grad.h:8-15 (prod_{force,virial}_grad_a_cpu)
 //   source/lib/include/neighbor_list.h:166-176,301-352 (build_nlist_cpu, legacy build_nlist / copy_coord)
 //   source/lib/include/coord.h:9-46           (normalize_coord_cpu, copy_coord_cpu, compute_cell_info)
 #include <cstdint>
@@ -25,7 +26,9 @@
 #include "neighbor_list.h"
 #include "prod_env_mat.h"
 #include "prod_force.h"
+#include "prod_force_grad.h"
 #include "prod_virial.h"
+#include "prod_virial_grad.h"
 #include "region.h"
 #include "tabulate.h"
 
@@ -225,6 +228,20 @@ const char* ref_last_error() { return g_err.c_str(); }
     return guarded([&] {                                                                   \
       deepmd::prod_virial_a_cpu<FP>(virial, atom_virial, net_deriv, in_deriv, rij, nlist,  \
                                     nloc, nall, nnei);                                     \
+    });                                                                                    \
+  }                                                                                        \
+  int ref_prod_force_grad_a_##SUF(FP* grad_net, const FP* grad, const FP* in_deriv,        \
+                                  const int* nlist, int nloc, int nnei, int nframes) {     \
+    return guarded([&] {                                                                   \
+      deepmd::prod_force_grad_a_cpu<FP>(grad_net, grad, in_deriv, nlist, nloc, nnei,       \
+                                        nframes);                                          \
+    });                                                                                    \
+  }                                                                                        \
+  int ref_prod_virial_grad_a_##SUF(FP* grad_net, const FP* grad, const FP* in_deriv,       \
+                                   const FP* rij, const int* nlist, int nloc, int nnei) {  \
+    return guarded([&] {                                                                   \
+      deepmd::prod_virial_grad_a_cpu<FP>(grad_net, grad, in_deriv, rij, nlist, nloc,       \
+                                         nnei);                                            \
     });                                                                                    \
   }                                                                                        \
   int ref_build_nlist_cpu_##SUF(int* numneigh, int* rows, int* max_list_size,              \

@@ -24,6 +24,8 @@ SOURCES = {
     "tabulate_se_a.json": ("source/lib/tests/test_tabulate_se_a.cc", ["TestTabulateSeA"]),
     "prod_force_a.json": ("source/lib/tests/test_prod_force_a.cc", ["TestProdForceA"]),
     "prod_virial_a.json": ("source/lib/tests/test_prod_virial_a.cc", ["TestProdVirialA"]),
+    "prod_force_grad_a.json": ("source/lib/tests/test_prod_force_grad_a.cc", ["TestProdForceGradA"]),
+    "prod_virial_grad_a.json": ("source/lib/tests/test_prod_virial_grad_a.cc", ["TestProdVirialGradA"]),
     "coord.json": ("source/lib/tests/test_coord.cc", ["TestNormCoord", "TestCopyCoord", "TestCopyCoordMoreCell"]),
     "neighbor_list.json": ("source/lib/tests/test_neighbor_list.cc", ["TestNeighborList"]),
 }

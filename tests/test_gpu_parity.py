@@ -772,3 +772,70 @@ def test_compressed_coefficients_fp32_cubic(ops):
     g0 = ops.tabulate_sections_grad(model.tables, model.infos, em_t, dy, cfg.sec, model.M)
     g1 = ops.tabulate_sections_grad(model.tables, model.infos, em_t, dy, cfg.sec, model.M, flags=model.coef_flags)
     assert ((g1 - g0).abs().max() / g0.abs().max()).item() < 5e-6
+
+
+# ------------------------------------------------------------------------------------------------
+# gradients of prod_force_a / prod_virial_a with respect to net_deriv
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+def test_prod_force_virial_grad_vs_oracle(ops, port, dtype):
+    """dpb200_prod_force_grad_a / _virial_grad_a against the restated reference (prod_force_grad.cc:22-77,
+    prod_virial_grad.cc:21-63) on a periodic box, two frames, incl. ghost indices folded with j % nloc."""
+    coord, atype, box = water_like_box(ncopy=2, seed=3, jitter=0.05)
+    s = extended_system(port, coord, atype, box, 6.0, dtype=np.float64)
+    sec = [0, 20, 60]
+    nnei = sec[-1]
+    off = np.concatenate([[0], np.cumsum(s["numneigh"])]).astype(np.int32)
+    neigh = np.concatenate([s["rows"][i, : s["numneigh"][i]] for i in range(s["nloc"])]).astype(np.int32)
+    nlist, _ = port.format_nlist(s["coord"], s["atype"], off, neigh, 6.0, sec)
+    em, dv, rij = port.env_mat_a(s["coord"], s["atype"], nlist, 0.5, 6.0, sec)
+    nloc = s["nloc"]
+    rng = np.random.default_rng(9)
+    dv, rij = dv.astype(dtype), rij.astype(dtype)
+    gf = rng.normal(size=(2 * nloc, 3)).astype(dtype)
+    gv = rng.normal(size=9).astype(dtype)
+    dv2, nl2 = np.concatenate([dv, dv]), np.concatenate([nlist, nlist])
+    want_f = port.prod_force_grad_a(gf, dv2, nl2, nframes=2)
+    want_v = port.prod_virial_grad_a(gv, dv, rij, nlist)
+    got_f = ops.prod_force_grad_a(T(gf.reshape(2, -1)), T(dv2), T(nl2), nloc, nnei, nframes=2)
+    got_v = ops.prod_virial_grad_a(T(gv), T(dv), T(rij), T(nlist), nloc, nnei)
+    close(N(got_f), want_f, dtype, fac=4)
+    close(N(got_v), want_v, dtype, fac=4)
+    assert (nlist >= nloc).any()  # ghosts present: the j % nloc fold was exercised
+
+
+def test_force_virial_ops_are_differentiable(ops, port):
+    """torch.ops.deepmd.prod_force_se_a / prod_virial_se_a backward == the adjoint of the forward (exact for ghosts:
+    ngrad = nall), and the explicit *_grad ops follow the TF schemas."""
+    torch.ops.deepmd  # registered at import
+    coord, atype, box = water_like_box(ncopy=1, seed=4, jitter=0.05)
+    s = extended_system(port, coord, atype, box, 6.0, dtype=np.float64)
+    sec = [0, 20, 60]
+    nnei = sec[-1]
+    off = np.concatenate([[0], np.cumsum(s["numneigh"])]).astype(np.int32)
+    neigh = np.concatenate([s["rows"][i, : s["numneigh"][i]] for i in range(s["nloc"])]).astype(np.int32)
+    nlist, _ = port.format_nlist(s["coord"], s["atype"], off, neigh, 6.0, sec)
+    em, dv, rij = port.env_mat_a(s["coord"], s["atype"], nlist, 0.5, 6.0, sec)
+    nloc, nall = s["nloc"], len(s["atype"])
+    natoms = torch.tensor([nloc, nall, 0, 0], dtype=torch.int32)
+    rng = np.random.default_rng(1)
+    nd = T(rng.normal(size=(1, nloc * nnei * 4))).requires_grad_(True)
+    dv_t, rij_t, nl_t = T(dv.reshape(1, -1)), T(rij.reshape(1, -1)), T(nlist.reshape(1, -1))
+    force = torch.ops.deepmd.prod_force_se_a(nd, dv_t, nl_t, natoms, nnei, 0)
+    virial, _ = torch.ops.deepmd.prod_virial_se_a(nd, dv_t, rij_t, nl_t, natoms, nnei, 0)
+    wf, wv = torch.randn_like(force), torch.randn_like(virial)
+    (g,) = torch.autograd.grad((force * wf).sum() + (virial * wv).sum(), nd)
+    # adjoint through linearity: d/d(nd) <w, F(nd)> = F^T w, checked with a random direction
+    u = torch.randn_like(nd)
+    fu = torch.ops.deepmd.prod_force_se_a(u, dv_t, nl_t, natoms, nnei, 0)
+    vu, _ = torch.ops.deepmd.prod_virial_se_a(u, dv_t, rij_t, nl_t, natoms, nnei, 0)
+    lhs = (g * u).sum().item()
+    rhs = ((fu * wf).sum() + (vu * wv).sum()).item()
+    assert abs(lhs - rhs) <= 1e-10 * abs(rhs)
+    # explicit grad ops (TF schema: grad over the nloc local atoms)
+    gf = torch.randn(1, nloc * 3, dtype=torch.float64, device=DEV)
+    got = torch.ops.deepmd.prod_force_se_a_grad(gf, nd.detach(), dv_t, nl_t, natoms, nnei, 0)
+    close(N(got), port.prod_force_grad_a(N(gf).reshape(nloc, 3), dv, nlist), np.float64, fac=4)
+    gvv = torch.randn(1, 9, dtype=torch.float64, device=DEV)
+    got = torch.ops.deepmd.prod_virial_se_a_grad(gvv, nd.detach(), dv_t, rij_t, nl_t, natoms, nnei, 0)
+    close(N(got), port.prod_virial_grad_a(N(gvv).reshape(9), dv, rij, nlist), np.float64, fac=4)

@@ -144,6 +144,49 @@ def test_golden_prod_virial(port):
     np.testing.assert_allclose(av.reshape(-1), g["expected_atom_virial"], atol=1e-5)
 
 
+def test_golden_prod_force_grad(port):
+    """source/lib/tests/test_prod_force_grad_a.cc:16-131: grad = 10 - 0.1*k, two identical frames."""
+    g = golden("prod_force_grad_a.json")["TestProdForceGradA"]
+    s, nlist, dv, rij, _ = _force_virial_inputs(port, g)
+    nloc = s["nloc"]
+    grad = (10 - 0.1 * np.arange(nloc * 3, dtype=np.float64)).reshape(nloc, 3)
+    out = port.prod_force_grad_a(np.concatenate([grad, grad]), np.concatenate([dv, dv]), np.concatenate([nlist, nlist]),
+                                 nframes=2)
+    np.testing.assert_allclose(out.reshape(-1), np.tile(g["expected_grad_net"], 2), atol=1e-5)
+
+
+def test_golden_prod_virial_grad(port):
+    """source/lib/tests/test_prod_virial_grad_a.cc:11-135: grad = 10 - k."""
+    g = golden("prod_virial_grad_a.json")["TestProdVirialGradA"]
+    s, nlist, dv, rij, _ = _force_virial_inputs(port, g)
+    out = port.prod_virial_grad_a(10 - np.arange(9, dtype=np.float64), dv, rij, nlist)
+    np.testing.assert_allclose(out.reshape(-1), g["expected_grad_net"], atol=1e-5)
+
+
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+def test_grad_ops_port_matches_reference_and_adjoint(port, ref, dtype):
+    """The restated gradient ops equal the reference library bitwise, and they ARE the adjoints of
+    prod_force_a / prod_virial_a:  <grad, force(nd)> = <force_grad(grad), nd>."""
+    g = golden("prod_force_a.json")["TestProdForceA"]
+    s, nlist, dv, rij, nd = _force_virial_inputs(port, g)
+    rng = np.random.default_rng(5)
+    nloc, nall = s["nloc"], len(s["atype"])
+    dv, rij, nd = dv.astype(dtype), rij.astype(dtype), rng.normal(size=nd.shape).astype(dtype)
+    gf = rng.normal(size=(nloc, 3)).astype(dtype)
+    gv = rng.normal(size=9).astype(dtype)
+    a = port.prod_force_grad_a(gf, dv, nlist)
+    b = port.prod_virial_grad_a(gv, dv, rij, nlist)
+    assert (a == ref.prod_force_grad_a(gf, dv, nlist)).all()
+    np.testing.assert_allclose(b, ref.prod_virial_grad_a(gv, dv, rij, nlist), rtol=0, atol=(1e-13 if dtype == np.float64 else 1e-5))
+    if dtype == np.float64:
+        # adjoint identity on the local block (ghosts folded with j % nloc, as prod_force_grad does)
+        nl_loc = np.where(nlist >= 0, nlist % nloc, -1).astype(np.int32)
+        f = port.prod_force_a(nd, dv, nl_loc, nloc)
+        assert abs((gf * f).sum() - (a * nd).sum()) < 1e-10 * abs((a * nd).sum())
+        v, _ = port.prod_virial_a(nd, dv, rij, nlist, nall)
+        assert abs((gv * v).sum() - (b * nd).sum()) < 1e-10 * abs((b * nd).sum())
+
+
 # ----------------------------------------------------------- restatement == reference
 def test_ref_legacy_fixture_matches_port(port, ref):
     g = golden("env_mat_a.json")["TestEnvMatA"]
