@@ -785,8 +785,7 @@ def test_prod_force_virial_grad_vs_oracle(ops, port, dtype):
     s = extended_system(port, coord, atype, box, 6.0, dtype=np.float64)
     sec = [0, 20, 60]
     nnei = sec[-1]
-    off = np.concatenate([[0], np.cumsum(s["numneigh"])]).astype(np.int32)
-    neigh = np.concatenate([s["rows"][i, : s["numneigh"][i]] for i in range(s["nloc"])]).astype(np.int32)
+    off, neigh = ocpu.dense_to_csr(s["rows"], s["numneigh"])
     nlist, _ = port.format_nlist(s["coord"], s["atype"], off, neigh, 6.0, sec)
     em, dv, rij = port.env_mat_a(s["coord"], s["atype"], nlist, 0.5, 6.0, sec)
     nloc = s["nloc"]
@@ -812,8 +811,7 @@ def test_force_virial_ops_are_differentiable(ops, port):
     s = extended_system(port, coord, atype, box, 6.0, dtype=np.float64)
     sec = [0, 20, 60]
     nnei = sec[-1]
-    off = np.concatenate([[0], np.cumsum(s["numneigh"])]).astype(np.int32)
-    neigh = np.concatenate([s["rows"][i, : s["numneigh"][i]] for i in range(s["nloc"])]).astype(np.int32)
+    off, neigh = ocpu.dense_to_csr(s["rows"], s["numneigh"])
     nlist, _ = port.format_nlist(s["coord"], s["atype"], off, neigh, 6.0, sec)
     em, dv, rij = port.env_mat_a(s["coord"], s["atype"], nlist, 0.5, 6.0, sec)
     nloc, nall = s["nloc"], len(s["atype"])
