@@ -933,12 +933,7 @@ def _op_prod_virial_se_a(net_deriv, in_deriv, rij, nlist, natoms, n_a_sel: int, 
     if nloc * nnei * 4 != net_deriv.shape[1] or nloc * nnei * 12 != in_deriv.shape[1] or \
             nloc * nnei * 3 != rij.shape[1] or nloc * nnei != nlist.shape[1]:
         raise ValueError("number of descriptors should match")
-    vs, avs = [], []
-    for f in range(nf):
-        v, av = prod_virial_a(net_deriv[f], in_deriv[f], rij[f], nlist[f], nloc, nall, nnei)
-        vs.append(v.reshape(1, 9))
-        avs.append(av.reshape(1, -1))
-    return torch.cat(vs, 0), torch.cat(avs, 0)
+    return _VirialOp.apply(net_deriv, in_deriv, rij, nlist, nloc, nall, nnei)
 
 
 def _natoms(natoms):
