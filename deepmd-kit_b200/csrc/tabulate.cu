@@ -29,6 +29,7 @@
 // Not a port of source/lib/src/gpu/tabulate.cu (one thread per channel, stride-6 scalar loads, all
 // coefficients from global memory, serial padding search by thread 0).
 #include <cuda_fp16.h>
+#include <cuda_pipeline.h>
 
 #include <cmath>
 #include <cstdlib>
@@ -60,6 +61,7 @@ struct TabParams {
   int H;   // hot rows kept in shared memory
   int hot_elems;  // H*Mc*6 (+ padding) rounded up to a 16-byte boundary (start of the per-warp records)
   int hot_pad;    // bytes of padding after every hot row (tensor-core forward: 32, see k_tab_fwd_mma)
+  int two_ring;   // se_atten: two_embed rows are staged through a per-warp shared-memory ring with cp.async
   int nblk;       // 16-byte blocks per (row, channel): 3 (coefficient pairs) or 2 (compressed, see k_table_relayout_cm)
   const FP* T3;   // compressed mode: the full pair table as well (stride-1 "coarse" rows are never compressed)
   float a5_mul, a5_inv;  // compressed layout: a5 is stored as half(a5 * a5_mul); a5_inv = 1 / a5_mul (powers of two)
@@ -593,6 +595,28 @@ __device__ __forceinline__ void desc_epilogue(const TabParams<FP>& p, const FP (
   }
 }
 
+// se_atten: two_embed ([nloc][nnei][M], 800 B per neighbour for M = 100 in fp64) is streamed once and is the
+// dominant HBM traffic of the gated op.  Its loads sit on the per-neighbour critical path, so the row of the
+// neighbour kTwoAhead slots ahead is pulled into L2 while the current one is evaluated (one 32-byte sector per
+// lane; no registers, no shared memory): the kernel then waits for L2, not for HBM.
+constexpr int kTwoAhead = 8;
+// ... and, when the rows are 16-byte aligned, copied asynchronously (cp.async, no registers) into a per-warp ring of
+// kRing rows in shared memory kRing-1 neighbours ahead, so that the gate value is a shared-memory read.
+constexpr int kRing = 8;
+template <typename FP>
+__device__ __forceinline__ void ring_issue(FP* __restrict__ ring, int Mp, const FP* __restrict__ two, long long row,
+                                           int slot_row, int M, int lane) {
+  const char* src = reinterpret_cast<const char*>(two + row * (long long)M);
+  char* dst = reinterpret_cast<char*>(ring + (slot_row % kRing) * Mp);
+  const int pieces = M * (int)sizeof(FP) / 16;
+  for (int q = lane; q < pieces; q += 32) __pipeline_memcpy_async(dst + 16 * q, src + 16 * q, 16);
+}
+template <typename FP>
+__device__ __forceinline__ void prefetch_two(const FP* __restrict__ two, long long row, int M, int lane) {
+  const int e = lane * (32 / (int)sizeof(FP));
+  if (e < M) asm volatile("prefetch.global.L2 [%0];" ::"l"(two + row * (long long)M + e));
+}
+
 extern __shared__ __align__(16) unsigned char tab_smem[];
 
 // ------------------------------------------------------------------------------------------
@@ -609,6 +633,11 @@ __global__ void __launch_bounds__(512) k_tab_fwd(const __grid_constant__ TabPara
   Rec<FP>* rec = reinterpret_cast<Rec<FP>*>(hot + p.hot_elems) + warp * 32;
   RecGG<FP>* rgg = reinterpret_cast<RecGG<FP>*>(reinterpret_cast<Rec<FP>*>(hot + p.hot_elems) + nw * 32) +
                    (GG ? warp * 32 : 0);
+  const int Mp = (p.M * (int)sizeof(FP) + 15) / 16 * 16 / (int)sizeof(FP);
+  FP* ring = reinterpret_cast<FP*>(reinterpret_cast<RecGG<FP>*>(reinterpret_cast<Rec<FP>*>(hot + p.hot_elems) + nw * 32) +
+                                   (GG ? nw * 32 : 0)) +
+             warp * kRing * Mp;
+  const bool ring_on = TWO && !GG && p.two_ring != 0;
   const int c0 = blockIdx.y * 32 * NC;
   const int r0 = hot_window_start(p);
   preload_hot(hot, p, r0);
@@ -683,7 +712,26 @@ __global__ void __launch_bounds__(512) k_tab_fwd(const __grid_constant__ TabPara
         }
       }
     } else {
+      if (ring_on) {
+        __syncwarp();
+        for (int jp = 0; jp < kRing - 1; ++jp) {
+          if (jp < nproc) ring_issue(ring, Mp, p.two, i * p.nnei + j0 + jp, jp, p.M, lane);
+          __pipeline_commit();
+        }
+      } else if (TWO) {
+        for (int jp = 0; jp < kTwoAhead && jp < nproc; ++jp) prefetch_two(p.two, i * p.nnei + j0 + jp, p.M, lane);
+      }
       for (int jj = 0; jj < nproc; ++jj) {
+        if (ring_on) {
+          __syncwarp();  // slot (jj-1) % kRing was read in the previous iteration
+          const int jp = jj + kRing - 1;
+          if (jp < nproc) ring_issue(ring, Mp, p.two, i * p.nnei + j0 + jp, jp, p.M, lane);
+          __pipeline_commit();
+          __pipeline_wait_prior(kRing - 1);  // the group of row jj has landed
+          __syncwarp();
+        } else if (TWO && jj + kTwoAhead < nproc) {
+          prefetch_two(p.two, i * p.nnei + j0 + jj + kTwoAhead, p.M, lane);
+        }
         const Rec<FP>& r = rec[jj];
         const int row = r.idx;
         if (row != cur_row) {  // warp-uniform
@@ -737,7 +785,7 @@ __global__ void __launch_bounds__(512) k_tab_fwd(const __grid_constant__ TabPara
             for (int m = 0; m < 4; ++m) acc[m][c] += g * h[m] + sgl * e[m];
           } else {
             if (TWO) {
-              const FP t = p.two[two_off + kc[c]];
+              const FP t = ring_on ? ring[(jj % kRing) * Mp + kc[c]] : p.two[two_off + kc[c]];
               g = g * t + g;
             }
 #pragma unroll
@@ -803,6 +851,9 @@ __global__ void __launch_bounds__(384) k_tab_grad(const __grid_constant__ TabPar
   FP* hot = reinterpret_cast<FP*>(tab_smem);
   Rec<FP>* rec = reinterpret_cast<Rec<FP>*>(hot + p.hot_elems) + warp * 32;
   const int M = p.M;
+  const int Mp = (M * (int)sizeof(FP) + 15) / 16 * 16 / (int)sizeof(FP);
+  FP* ring = reinterpret_cast<FP*>(reinterpret_cast<Rec<FP>*>(hot + p.hot_elems) + nw * 32) + warp * kRing * Mp;
+  const bool ring_on = TWO && p.two_ring != 0;
   const int r0 = hot_window_start(p);
   preload_hot(hot, p, r0);
   __syncthreads();
@@ -846,7 +897,24 @@ __global__ void __launch_bounds__(384) k_tab_grad(const __grid_constant__ TabPar
     if (atom_end && ni < p.nloc) nlast = p.em_x[ni * p.ldx_i + (long long)(p.nnei - 1) * p.ldx_j];
 
     FP* __restrict__ gem = p.dy_dem + i * p.ldem_i;
+    if (ring_on) {
+      __syncwarp();
+      for (int jp = 0; jp < kRing; ++jp) {
+        if (jp < nproc) ring_issue(ring, Mp, p.two, i * p.nnei + j0 + jp, jp, M, lane);
+        __pipeline_commit();
+      }
+    } else if (TWO) {
+      for (int jp = 0; jp < kTwoAhead && jp < nproc; ++jp) prefetch_two(p.two, i * p.nnei + j0 + jp, M, lane);
+    }
     for (int b = 0; b < nproc; b += 4) {
+      if (ring_on) {
+        __pipeline_wait_prior(4);  // 8 + 4*(b/4) groups committed, rows b..b+3 are among the first 4*(b/4 + 1)
+        __syncwarp();
+      } else if (TWO) {
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+          if (b + kTwoAhead + u < nproc) prefetch_two(p.two, i * p.nnei + j0 + b + kTwoAhead + u, M, lane);
+      }
       FP v[16];
       FP vx[4];
       if (!single || (nproc - b) < 4) {  // the fast path below initialises by assignment
@@ -895,7 +963,7 @@ __global__ void __launch_bounds__(384) k_tab_grad(const __grid_constant__ TabPar
                 const int k = kb + lane + 32 * c;
                 if (k < M) {
                   const long long to = (i * p.nnei + j0 + b + u) * (long long)M + k;
-                  const FP t = p.two[to];
+                  const FP t = ring_on ? ring[((b + u) % kRing) * Mp + k] : p.two[to];
                   p.dy_dtwo[to] = g * dot;
                   g = g * t + g;
                   gd += t * gd;
@@ -916,6 +984,15 @@ __global__ void __launch_bounds__(384) k_tab_grad(const __grid_constant__ TabPar
               }
             }
           }
+        }
+      }
+      if (ring_on) {
+        __syncwarp();  // rows b..b+3 consumed: their slots take rows b+8..b+11
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int jp = b + kRing + u;
+          if (jp < nproc) ring_issue(ring, Mp, p.two, i * p.nnei + j0 + jp, jp, M, lane);
+          __pipeline_commit();
         }
       }
       const FP tot = reduce_scatter16(v, lane);   // (u, m) = (lane >> 3, (lane >> 1) & 3)
@@ -1618,7 +1695,11 @@ int launch_fwd(FP* out, const FP* table, const FP* info, const FP* em_x, long lo
   }
   const int nc = M <= 32 ? 1 : (M <= 64 ? 2 : 4);
   const int nw = 16;
-  const size_t rec_bytes = (size_t)nw * 32 * (sizeof(Rec<FP>) + (GG ? sizeof(RecGG<FP>) : 0));
+  // se_atten: per-warp cp.async ring for two_embed rows (needs 16-byte aligned rows)
+  const bool ring = !GG && two != nullptr && ((size_t)M * sizeof(FP)) % 16 == 0 && aligned16(two) && M <= 128;
+  p.two_ring = ring ? 1 : 0;
+  const size_t rec_bytes = (size_t)nw * 32 * (sizeof(Rec<FP>) + (GG ? sizeof(RecGG<FP>) : 0)) +
+                           (ring ? (size_t)nw * kRing * M * sizeof(FP) : 0);
   p.Mc = M;
   p.nblk = cm ? 2 : 3;
   set_a5_scale(p, flags);
@@ -1735,8 +1816,10 @@ int launch_grad(FP* dy_dem_x, FP* dy_dem, FP* dy_dtwo, const FP* table, const FP
   p.dy_dem = dy_dem;
   p.dy_dtwo = dy_dtwo;
   const int nw = 12;
-  const size_t rec_bytes = (size_t)nw * 32 * sizeof(Rec<FP>);
   const bool tw = two != nullptr;
+  const bool ring = tw && ((size_t)M * sizeof(FP)) % 16 == 0 && aligned16(two) && M <= 32 * 4;
+  p.two_ring = ring ? 1 : 0;
+  const size_t rec_bytes = (size_t)nw * 32 * sizeof(Rec<FP>) + (ring ? (size_t)nw * kRing * M * sizeof(FP) : 0);
   const int kt = (M + 3) / 4;
   const bool mma_ok = std::is_same<FP, double>::value && !tw && use_mma_path() &&
                       (kt == 8 || kt == 16 || kt == 20 || kt == 25 || kt == 32);
