@@ -602,7 +602,7 @@ __device__ __forceinline__ void desc_epilogue(const TabParams<FP>& p, const FP (
 constexpr int kTwoAhead = 8;
 // ... and, when the rows are 16-byte aligned, copied asynchronously (cp.async, no registers) into a per-warp ring of
 // kRing rows in shared memory kRing-1 neighbours ahead, so that the gate value is a shared-memory read.
-constexpr int kRing = 8;
+constexpr int kRing = 8;  // (a power of two)
 template <typename FP>
 __device__ __forceinline__ void ring_issue(FP* __restrict__ ring, int Mp, const FP* __restrict__ two, long long row,
                                            int slot_row, int M, int lane) {
@@ -705,6 +705,41 @@ __global__ void __launch_bounds__(512) k_tab_fwd(const __grid_constant__ TabPara
 #pragma unroll
         for (int c = 0; c < NC; ++c) {
           const FP g = (CM && sizeof(FP) == 4) ? poly3(a[c], xx) : (CM ? poly_cm(a[c], af[CM ? c : 0], xx, xf) : poly(a[c], xx));
+          acc[0][c] += e0 * g;
+          acc[1][c] += e1 * g;
+          acc[2][c] += e2 * g;
+          acc[3][c] += e3 * g;
+        }
+      }
+    } else if (!GG && TWO && ring_on && !any_delta) {
+      // se_atten, nobody outside [lower, max): the gate row of every neighbour arrives through the cp.async ring;
+      // same arithmetic as the general path below, without its per-neighbour branches and 64-bit index math
+      const FP* __restrict__ two_base = p.two + (i * p.nnei + j0) * (long long)p.M;
+      __syncwarp();
+      for (int jp = 0; jp < kRing - 1; ++jp) {
+        if (jp < nproc) ring_issue(ring, Mp, two_base, jp, jp, p.M, lane);
+        __pipeline_commit();
+      }
+      for (int jj = 0; jj < nproc; ++jj) {
+        __syncwarp();  // slot (jj-1) % kRing was read in the previous iteration
+        const int jp = jj + kRing - 1;
+        if (jp < nproc) ring_issue(ring, Mp, two_base, jp, jp, p.M, lane);
+        __pipeline_commit();
+        __pipeline_wait_prior(kRing - 1);  // the group of row jj has landed
+        __syncwarp();
+        const Rec<FP>& r = rec[jj];
+        const int row = r.idx;
+        if (row != cur_row) {  // warp-uniform
+          cur_row = row;
+          fetch_row<FP, NC>(a, hot, p.T, row, r0, p.H, p.M, ob);
+        }
+        const FP xx = r.xx;
+        const FP e0 = r.e[0], e1 = r.e[1], e2 = r.e[2], e3 = r.e[3];
+        const FP* __restrict__ tw = ring + (jj & (kRing - 1)) * Mp;
+#pragma unroll
+        for (int c = 0; c < NC; ++c) {
+          FP g = poly(a[c], xx);
+          g = g * tw[kc[c]] + g;
           acc[0][c] += e0 * g;
           acc[1][c] += e1 * g;
           acc[2][c] += e2 * g;
