@@ -471,6 +471,19 @@ def per_kernel(args, torch, ops, model, dp, step, L, dev, nloc, esz):
                 a = per_atom * nloc / t / 1e12
                 row.update(bound="fp64-fma" if args.dtype == "f64" else "fp32-fma", achieved=a, peak=fma,
                            unit="TFLOP/s", frac=a / fma, alg_flops_per_atom=per_atom)
+    # what ncu names as the limiter of each kernel (profiles/r01_ncu_full_v7_summary.csv, 98 304-atom capture)
+    limiter = {
+        "prod_env_mat_a": "l1tex 73 %, issue 54 %, dram 41 %",
+        "tabulate_sections_fwd": "l1tex (shared-memory coefficient stream) 82-84 %, fp64 pipe 33-35 %",
+        "tabulate_sections_desc": "l1tex 72-84 %, fp64 pipe 30-35 %",
+        "tabulate_sections_grad": "l1tex 78-81 %, tensor (DMMA) 37-40 %, fp64 pipe 15-16 %",
+        "se_a_descriptor_grad": "dram 53 %, l1tex 64 %, tensor (DMMA) 29 %",
+        "prod_force_virial_a": "dram 65 % of ncu peak (0.92 of the measured copy bandwidth)",
+    }
+    if args.dtype == "f64":
+        for n, row in table.items():
+            if n in limiter:
+                row["ncu_limiter"] = limiter[n]
     ours = {n: r for n, r in table.items() if "bound" in r}
     top = max(ours, key=lambda n: ours[n]["ms_per_step"]) if ours else None
     roofline = None
