@@ -1,6 +1,6 @@
 // Test driver for lib/libdeepmd_op_cuda.so (the reference-side C++ binding): calls the reference's
 // own declarations deepmd::prod_env_mat_a_gpu / tabulate_fusion_se_a_gpu / _grad_gpu /
-// prod_force_a_gpu / prod_virial_a_gpu exactly as source/op/tf/*_multi_device.cc would, on inputs read
+// prod_force_a_gpu / prod_virial_a_gpu / prod_force_grad_a_gpu / prod_virial_grad_a_gpu exactly as source/op/tf/*_multi_device.cc would, on inputs read
 // from a flat binary file, and writes the outputs back.  Compiled against the reference headers
 // (tests/shim/build.sh); the pytest side compares the outputs with the CPU oracle.
 #include <cuda_runtime.h>
@@ -12,7 +12,9 @@
 #include "neighbor_list.h"
 #include "prod_env_mat.h"
 #include "prod_force.h"
+#include "prod_force_grad.h"
 #include "prod_virial.h"
+#include "prod_virial_grad.h"
 #include "tabulate.h"
 
 #define CK(x)                                                                  \
@@ -98,6 +100,9 @@ int main(int argc, char** argv) {
   CK(cudaMalloc((void**)&force, sizeof(double) * nall * 3));
   CK(cudaMalloc((void**)&virial, sizeof(double) * 9));
   CK(cudaMalloc((void**)&atom_virial, sizeof(double) * nall * 9));
+  double *gn_f, *gn_v;
+  CK(cudaMalloc((void**)&gn_f, sizeof(double) * nloc * nnei * 4));
+  CK(cudaMalloc((void**)&gn_v, sizeof(double) * nloc * nnei * 4));
 
   try {
     deepmd::prod_env_mat_a_gpu<double>(em, dv, rij, nlist, d_coord, d_type, gpu_inlist, array_int, array_ll, max_nbor,
@@ -112,6 +117,9 @@ int main(int argc, char** argv) {
                                                   nnei, M);
     deepmd::prod_force_a_gpu<double>(force, d_nd, dv, nlist, nloc, nall, nnei, 1);
     deepmd::prod_virial_a_gpu<double>(virial, atom_virial, d_nd, dv, rij, nlist, nloc, nall, nnei);
+    // gradients w.r.t. net_deriv, fed with the first nloc force rows / the virial just computed
+    deepmd::prod_force_grad_a_gpu<double>(gn_f, force, dv, nlist, nloc, nnei, 1);
+    deepmd::prod_virial_grad_a_gpu<double>(gn_v, virial, dv, rij, nlist, nloc, nnei);
   } catch (const std::exception& e) {
     fprintf(stderr, "exception: %s\n", e.what());
     return 4;
@@ -126,6 +134,8 @@ int main(int argc, char** argv) {
   down(fo, force, (size_t)nall * 3);
   down(fo, virial, 9);
   down(fo, atom_virial, (size_t)nall * 9);
+  down(fo, gn_f, (size_t)nloc * nnei * 4);
+  down(fo, gn_v, (size_t)nloc * nnei * 4);
   fclose(fo);
   printf("SHIM_DRIVER_OK\n");
   return 0;

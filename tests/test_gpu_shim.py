@@ -17,7 +17,8 @@ DRIVER = os.path.join(ROOT, "tests", "shim", "_build", "shim_driver")
 SHIM = os.path.join(ROOT, "deepmd-kit_b200", "lib", "libdeepmd_op_cuda.so")
 
 WANT = ["prod_env_mat_a_gpu", "format_nbor_list_gpu", "tabulate_fusion_se_a_gpu", "tabulate_fusion_se_a_grad_gpu",
-        "tabulate_fusion_se_a_grad_grad_gpu", "prod_force_a_gpu", "prod_virial_a_gpu", "normalize_coord_gpu",
+        "tabulate_fusion_se_a_grad_grad_gpu", "prod_force_a_gpu", "prod_virial_a_gpu", "prod_force_grad_a_gpu",
+        "prod_virial_grad_a_gpu", "normalize_coord_gpu",
         "copy_coord_gpu", "build_nlist_gpu"]
 
 
@@ -77,6 +78,7 @@ def test_shim_driver_matches_oracle(port, tmp_path):
     nlist = take(nloc * nnei, np.int32)
     desc, gx, gem = take(nloc * 4 * M, np.float64), take(nloc * nnei, np.float64), take(nloc * nnei * 4, np.float64)
     force, virial, av = take(nall * 3, np.float64), take(9, np.float64), take(nall * 9, np.float64)
+    gn_f, gn_v = take(nloc * nnei * 4, np.float64), take(nloc * nnei * 4, np.float64)
     o, neigh = ocpu.dense_to_csr(s["rows"], s["numneigh"])
     w_em, w_dv, w_rij, w_nl = port.prod_env_mat_a(s["coord"], s["atype"], o, neigh, avg, std, nloc, 6.0, 0.5, sec)
     assert np.array_equal(nlist.reshape(nloc, nnei), w_nl)
@@ -98,3 +100,6 @@ def test_shim_driver_matches_oracle(port, tmp_path):
     wv, wav = port.prod_virial_a(nd, w_dv, w_rij, w_nl, nall)
     close(virial, wv, 2e-9)
     close(av, wav, 4e-10)
+    wf = port.prod_force_a(nd, w_dv, w_nl, nall)
+    close(gn_f, port.prod_force_grad_a(wf[:nloc], w_dv, w_nl), 4e-10)
+    close(gn_v, port.prod_virial_grad_a(wv, w_dv, w_rij, w_nl), 2e-9)
