@@ -190,9 +190,17 @@ def run_reference(args):
         "impl": "reference", "metric": METRIC, "value": r["us_per_step_atom"], "unit": UNIT, "n_gpus": args.gpus,
         "steps": r["steps"], "warmup": args.warmup, "ms_per_step": r["ms_per_step"], "higher_is_better": False,
         "scaling": "weak", "vs_baseline": None, "dtype": args.dtype, "data": "synthetic",
-        "config": {"workload": "se_e2_a compressed water (rcut 6.0, sel [46,92], neuron [25,50,100], axis 16, fitting "
-                               "[240,240,240]), reference CPU ops (libdeepmd *_cpu, OpenMP) + torch CPU fitting net; "
-                               "each step = one evaluation of a bounded sample", "sample_natoms": r["natoms"]},
+        # the arm's own configuration (same workload string and model keys as run_ours), plus what was actually timed
+        "config": {"workload": f"se_e2_a compressed water, {192 * args.ncopy ** 3 * args.gpus}-atom box ({args.ncopy}^3 "
+                               f"replicas of the 192-atom frame per GPU, Gaussian jitter {args.jitter} A), {args.dtype}, "
+                               f"{args.gpus}xB200",
+                   "natoms": 192 * args.ncopy ** 3 * args.gpus, "rcut": 6.0, "rcut_smth": 0.5, "sel": [46, 92],
+                   "neuron": [25, 50, 100], "axis_neuron": 16, "fitting_neuron": [240, 240, 240],
+                   "table": "dp-compress restatement, stride 0.01/0.1, extrapolate 5, random-init weights (seed 1)",
+                   "reference_implementation": "reference CPU ops (libdeepmd *_cpu, OpenMP, all host cores) + torch CPU "
+                                               "fitting net; each step = one evaluation of a bounded sample of the "
+                                               "workload (us/step/atom is size-independent)",
+                   "sample_natoms": r["natoms"]},
         "cpu_baseline": {"value": r["us_per_step_atom"], "unit": UNIT, "cores": r["cores"], "kind": r["kind"],
                          "sample": r["sample"], "stages_us_per_atom": r["stages_us_per_atom"]},
         "e2e": {"value": r["us_per_step_atom"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
