@@ -182,3 +182,48 @@ def test_tf32_split_is_exact_to_2pow22(pkg):
     for part in (hi, lo):  # 10 explicit mantissa bits: the low 13 bits of the fp32 pattern are clear
         assert int((part.view(torch.int32) & 0x1FFF).abs().max()) == 0
     assert float(((hi.double() + lo.double() - w.double()).abs() / w.double().abs()).max()) <= 2.0 ** -21
+
+
+def test_compressed_coefficient_gates(pkg):
+    """Host-side gates of DPB200_TAB_COMPRESSED_COEF: dp-compress tables of the benchmark models qualify (fp64 and fp32
+    forms), an arbitrary table with O(1) high-order coefficients and coarse strides does not."""
+    from deepmd_kit_b200 import ops
+    from deepmd_kit_b200.model import COPPER_CONFIG, SeAConfig, SeAModel
+
+    for cfg in (SeAConfig(), SeAConfig(**COPPER_CONFIG)):
+        m = SeAModel(cfg, torch.float64, "cpu")
+        assert m.coef_flags is None  # never enabled off the GPU path
+        for t, i in zip(m.tables64, m.infos):
+            assert ops.compressed_coef_flags(t, i) & 1
+            assert ops.compressed_coef_flags_f32(t, i) == 1
+            # the fp16 scale of a5 keeps the largest stride-0 coefficient inside the fp16 range
+            k = ((ops.compressed_coef_flags(t, i) >> 8) & 0xFF)
+            k = k - 256 if k >= 128 else k
+            first = int((float(i[1]) - float(i[0])) / float(i[3]))
+            a5 = t.reshape(t.shape[0], -1, 6)[:first, :, 5].abs().max().item()
+            assert 2.0 ** 12 <= a5 * 2.0 ** k < 2.0 ** 15
+    rng = np.random.default_rng(0)
+    info = np.array([-0.4, 2.0, 6.0, 0.05, 0.5, -1.0])
+    nrow = int((info[1] - info[0]) / info[3]) + int((info[2] - info[1]) / info[4]) + 1
+    bad = torch.as_tensor(rng.normal(size=(nrow, 100 * 6)))
+    assert ops.compressed_coef_flags(bad, info) == 0
+    assert ops.compressed_coef_flags_f32(bad, info) == 0
+    assert ops.compressed_coef_flags(torch.zeros(nrow, 600, dtype=torch.float64), info) == 0
+
+
+def test_bench_reference_arm_contract():
+    """`bench.py --impl reference` prints ONE JSON line with the contract's keys (CPU only, tiny sample)."""
+    import json
+    import subprocess
+    import sys
+
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup",
+                        "1", "--cpu-ncopy", "1"], capture_output=True, text=True, timeout=600, cwd=ROOT)
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [ln for ln in r.stdout.splitlines() if ln.strip()]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["unit"] == "us/step/atom" and d["higher_is_better"] is False
+    assert d["value"] > 0 and d["cpu_baseline"]["value"] == d["value"] and d["cpu_baseline"]["cores"] >= 1
+    assert d["e2e"] == {"value": d["value"], "unit": d["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    assert d["config"]["natoms"] == 1536000 and "workload" in d["config"]
