@@ -8,6 +8,8 @@ g.load_package()
 from deepmd_kit_b200 import ops
 from deepmd_kit_b200.model import DeepPotB200, SeAConfig, SeAModel
 
+if os.environ.get("OPB_BLASLT"):
+    torch.backends.cuda.preferred_blas_library("cublaslt")
 ncopy = int(sys.argv[1]) if len(sys.argv) > 1 else 12
 dtype = torch.float64 if (len(sys.argv) < 3 or sys.argv[2] == "f64") else torch.float32
 reps = int(sys.argv[3]) if len(sys.argv) > 3 else 15
