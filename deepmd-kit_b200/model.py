@@ -150,6 +150,94 @@ class FittingNet:
             self.split = dict(fw=fw, bw=bw, K=self.layers[0][0].shape[0])
         return self
 
+    def prepare_tc(self, nslice: int = 6):
+        """Weights of all GEMMs of the net (forward and backward) as signed 7-bit int8 slices in the B-operand
+        layout of dpb200_fit_gemm_i8 ([nslice][N][K padded to 64], K contiguous) + column scales 2^(col_exp-12),
+        and the fixed exponents of the hidden activations (|y_l| < sum_k<=l max|idt_k|).  Returns False when the
+        architecture is outside what csrc/fit_tc.cu covers (fp64, first layer without skip connection, equal-width
+        hidden layers)."""
+        if self.dtype != torch.float64:
+            return False
+        dev = self.layers[0][0].device
+        widths = [w.shape for w, _, _ in self.layers]
+        if widths[0][0] in (widths[0][1], 2 * widths[0][1]) or widths[0][1] == 2 * widths[0][0] or widths[0][0] % 16:
+            return False
+        for (k_in, k_out) in widths[1:]:
+            if k_in != k_out:
+                return False
+
+        def pack(w):  # w [K, N] -> slices [ns, N, Kp], col_scale [N]
+            sl, ce = split_i8_cols(w, nslice)
+            K, N = w.shape
+            Kp = (K + 63) // 64 * 64
+            b = torch.zeros((nslice, N, Kp), dtype=torch.int8)
+            b[:, :, :K] = sl.permute(0, 2, 1)
+            return b.contiguous().to(dev), torch.ldexp(torch.ones(N, dtype=torch.float64), ce - 12).to(dev), Kp
+
+        tc = dict(nslice=nslice, fw=[], bw=[], exp=[])
+        bound = 0.0
+        for li, (w, b, idt) in enumerate(self.layers):
+            w64 = w.detach().to("cpu", torch.float64)
+            tc["fw"].append(pack(w64))
+            tc["bw"].append(pack(w64.t().contiguous()))
+            amp = 1.0 if idt is None else float(idt.abs().max())
+            bound = amp if li == 0 else bound + amp
+            tc["exp"].append(int(math.floor(math.log2(bound))) + 2)
+        tc["w_head"] = self.head[0][:, 0].contiguous()
+        tc["b_head"] = float(self.head[1][0])
+        self.tc = tc
+        return True
+
+    @torch.no_grad()
+    def forward_backward_tc(self, xs: torch.Tensor, row_exp: torch.Tensor, n: int):
+        """forward_backward on the pre-split descriptor rows with every GEMM on the int8 tensor cores
+        (csrc/fit_tc.cu): per layer ONE kernel does the split product, the recombination and the layer's
+        elementwise chain; the activations travel between layers as int8 slices.  Returns (e [n], dE/dD [n, K0])."""
+        tc = self.tc
+        ns = tc["nslice"]
+        dev = xs.device
+        nb = ops.fit_blocked_rows(n)
+        K0 = self.layers[0][0].shape[0]
+        ts, ys = [], []
+        a, a_ss, a_rs, a_exp, a_fixed, K = xs, K0, xs.stride(0), row_exp, 0, K0
+        nl = len(self.layers)
+        for li, (w, b, idt) in enumerate(self.layers):
+            N = w.shape[1]
+            bsl, cs, Kp = tc["fw"][li]
+            t = torch.empty(nb * N, dtype=torch.float64, device=dev)
+            y = torch.empty(nb * N, dtype=torch.float64, device=dev)
+            last = li == nl - 1
+            kp_out = (N + 15) // 16 * 16
+            sl = None if last else torch.empty((n, ns * kp_out), dtype=torch.int8, device=dev)
+            ops.fit_gemm_i8(0, n, N, K, a, a_ss, a_rs, a_exp, a_fixed, bsl, Kp, cs, bias=b, idt=idt,
+                            skip=ys[-1] if li > 0 else None, out0=t, out1=y, slices_out=sl,
+                            ld_slices=0 if last else ns * kp_out, kp_out=kp_out, out_exp=tc["exp"][li], nslice=ns)
+            ts.append(t)
+            ys.append(y)
+            if not last:
+                a, a_ss, a_rs, a_exp, a_fixed, K = sl, kp_out, ns * kp_out, None, tc["exp"][li], kp_out
+        N = self.layers[-1][0].shape[1]
+        kp = (N + 15) // 16 * 16
+        e, dz, dz_exp = ops.fit_head(ts[-1], ys[-1], tc["w_head"], self.layers[-1][2], tc["b_head"], n, N, kp, ns)
+        g_prev = None
+        for li in range(nl - 1, 0, -1):
+            w, b, idt = self.layers[li]
+            n_in = w.shape[0]
+            bsl, cs, Kp = tc["bw"][li]
+            need_g = li - 1 > 0
+            g = torch.empty(nb * n_in, dtype=torch.float64, device=dev) if need_g else None
+            dzn = torch.empty(nb * n_in, dtype=torch.float64, device=dev)
+            ops.fit_gemm_i8(1, n, n_in, kp, dz, kp, ns * kp, dz_exp, 0, bsl, Kp, cs, idt=self.layers[li - 1][2],
+                            skip=g_prev, skip_vec=tc["w_head"] if g_prev is None else None, t_in=ts[li - 1],
+                            out0=g, out1=dzn, nslice=ns)
+            g_prev = g
+            kp = (n_in + 15) // 16 * 16
+            dz, dz_exp = ops.fit_slice_rows(dzn, n, n_in, kp, ns)
+        bsl, cs, Kp = tc["bw"][0]
+        gd = torch.empty((n, K0), dtype=torch.float64, device=dev)
+        ops.fit_gemm_i8(2, n, K0, kp, dz, kp, ns * kp, dz_exp, 0, bsl, Kp, cs, out0=gd, ld_out=K0, nslice=ns)
+        return e, gd
+
     def to(self, device, dtype):
         self.layers = [(w.to(device, dtype), b.to(device, dtype), None if i is None else i.to(device, dtype))
                        for w, b, i in self.layers]
@@ -309,9 +397,14 @@ class SeAModel:
         ok_axis = cfg.axis_neuron == 16 if dtype == torch.float64 else cfg.axis_neuron % 4 == 0
         self.use_split = bool(ok_axis and self.M <= 128 and cfg.axis_neuron <= 32 and w0.shape[1] not in
                               (w0.shape[0], 2 * w0.shape[0]) and self.device.type == "cuda")
+        # fp64: every GEMM of the net on the tcgen05 int8 path (csrc/fit_tc.cu); DPB200_FIT_TC=0 keeps the
+        # library GEMMs (cuBLASLt int8 first layer + DGEMM) of round 1 as the comparison path.
+        self.use_tc = False
         if self.use_split:
             for f in self.fit:
                 f.prepare_split(self.nslice)
+            if dtype == torch.float64 and self.nslice == 6 and _os.environ.get("DPB200_FIT_TC", "1") != "0":
+                self.use_tc = all([f.prepare_tc(self.nslice) for f in self.fit])
         # Compressed table coefficients (include/dpb200.h DPB200_TAB_COMPRESSED_COEF): the table kernels are bound by
         # the on-chip coefficient stream; for a dp-compress table the high-order terms tolerate fp32 / fp16 storage
         # at the 1e-12 level.  Checked per table here, on the host, once.
@@ -356,8 +449,11 @@ class SeAModel:
         for t, (a, b) in enumerate(type_ranges):
             for c0 in range(a, b, self.fit_chunk):
                 c1 = min(b, c0 + self.fit_chunk)
-                e, gd = self.fit[t].forward_backward_split(desc[c0:], None if row_exp is None else row_exp[c0:c1],
-                                                           c1 - c0)
+                if self.use_tc:
+                    e, gd = self.fit[t].forward_backward_tc(desc[c0:c1], row_exp[c0:c1], c1 - c0)
+                else:
+                    e, gd = self.fit[t].forward_backward_split(desc[c0:], None if row_exp is None else row_exp[c0:c1],
+                                                               c1 - c0)
                 ops.se_a_descriptor_grad(gd, xyz, cfg.axis_neuron, inv, rows=type_perm32[c0:c1], out=dy)
                 e_atom.index_copy_(0, type_perm[c0:c1], e)
         return e_atom.sum(), e_atom, dy

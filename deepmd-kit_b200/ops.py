@@ -739,6 +739,59 @@ def mlp_tanh_bwd(g, a, idt=None, split3=False):
     return t
 
 
+def fit_gemm_i8(mode, n, N, K, a_slices, a_slice_stride, a_row_stride, row_exp, row_exp_fixed, b_slices, b_k_stride,
+                col_scale, bias=None, idt=None, skip=None, skip_vec=None, t_in=None, out0=None, out1=None, ld_out=0,
+                slices_out=None, ld_slices=0, kp_out=0, out_exp=0, nslice=6):
+    """One fitting-net GEMM on the int8 tensor cores (dpb200_fit_gemm_i8_f64, csrc/fit_tc.cu): mode 0 forward layer,
+    1 backward layer, 2 plain product.  fp64 intermediates are in the row-blocked layout of fit_blocked()."""
+    dev = _need_cuda(("a_slices", a_slices), ("b_slices", b_slices), ("col_scale", col_scale), ("row_exp", row_exp),
+                     ("bias", bias), ("idt", idt), ("skip", skip), ("skip_vec", skip_vec), ("t_in", t_in),
+                     ("out0", out0), ("out1", out1), ("slices_out", slices_out))
+    lib().call("fit_gemm_i8_f64", int(mode), int(n), int(N), int(K), int(nslice), _p(a_slices), int(a_slice_stride),
+               int(a_row_stride), _p(row_exp), int(row_exp_fixed), _p(b_slices), int(b_k_stride), _p(col_scale),
+               _p(bias), _p(idt), _p(skip), _p(skip_vec), _p(t_in), _p(out0), _p(out1), int(ld_out), _p(slices_out),
+               int(ld_slices), int(kp_out), int(out_exp), _stream(dev))
+
+
+def fit_blocked_rows(n):
+    return (int(n) + 127) // 128 * 128
+
+
+def fit_blocked(src, n, N, to_blocked=True):
+    """Row-major fp64 [n, N] <-> the row-blocked column-major layout of the tensor-core fitting net:
+    element (r, c) at ((r // 128) * N + c) * 128 + r % 128 (flat tensor of fit_blocked_rows(n) * N elements)."""
+    dev = _need_cuda(("src", src))
+    if to_blocked:
+        src = _c(src, torch.float64)
+        dst = torch.zeros(fit_blocked_rows(n) * int(N), dtype=torch.float64, device=dev)
+        lib().call("fit_blocked_f64", _p(dst), _p(src), int(N), int(n), int(N), 1, _stream(dev))
+    else:
+        dst = torch.empty((int(n), int(N)), dtype=torch.float64, device=dev)
+        lib().call("fit_blocked_f64", _p(dst), _p(src), int(N), int(n), int(N), 0, _stream(dev))
+    return dst
+
+
+def fit_slice_rows(x_blocked, n, N, kp, nslice=6):
+    """Blocked fp64 [n, N] -> (int8 [n, nslice*kp] slices with per-row exponent, row_exp int32 [n])."""
+    dev = _need_cuda(("x", x_blocked))
+    out = torch.empty((int(n), int(nslice) * int(kp)), dtype=torch.int8, device=dev)
+    ex = torch.empty((int(n),), dtype=torch.int32, device=dev)
+    lib().call("fit_slice_rows_f64", _p(out), int(out.shape[1]), int(kp), _p(ex), _p(x_blocked), int(n), int(N),
+               int(nslice), _stream(dev))
+    return out, ex
+
+
+def fit_head(t, y, w_head, idt, b_head, n, N, kp, nslice=6):
+    """Energy head + seed of the backward chain: e = y . w_head + b_head; dz = w_head * idt * (1 - t^2) as int8 slices."""
+    dev = _need_cuda(("t", t), ("y", y), ("w_head", w_head), ("idt", idt))
+    e = torch.empty((int(n),), dtype=torch.float64, device=dev)
+    out = torch.empty((int(n), int(nslice) * int(kp)), dtype=torch.int8, device=dev)
+    ex = torch.empty((int(n),), dtype=torch.int32, device=dev)
+    lib().call("fit_head_f64", _p(e), _p(out), int(out.shape[1]), int(kp), _p(ex), _p(t), _p(y), _p(w_head), _p(idt),
+               float(b_head), int(n), int(N), int(nslice), _stream(dev))
+    return e, out, ex
+
+
 def halo_pack(coord, sendlist, shift):
     """sendbuf[k] = coord[sendlist[k]] + shift[k] (dpb200_halo_pack)."""
     dev = _need_cuda(("coord", coord), ("sendlist", sendlist), ("shift", shift))
