@@ -38,9 +38,10 @@ namespace dpb200 {
 namespace {
 
 constexpr int kTileM = 128;
-constexpr int kChunkK = 64;  // bytes of K per pipeline stage = one SWIZZLE_64B row
-constexpr int kStages = 2;
-constexpr int kThreads = 192;
+constexpr int kChunkK = 64;   // bytes of K per operand unit = one SWIZZLE_64B row
+constexpr int kStages = 5;    // operand ring of HALF chunks: slices [0, NS/2) or [NS/2, NS) of one K-chunk
+constexpr int kEpiWarps = 20; // 5 column groups of 16 x 4 TMEM lane quadrants
+constexpr int kThreads = 32 * (2 + kEpiWarps);
 
 enum { EPI_FWD = 0, EPI_BWD = 1, EPI_PLAIN = 2 };
 
@@ -52,11 +53,10 @@ struct GemmParams {
   long long m_blocks; // row blocks of 128
   const int* row_exp; // per-row exponent of the A operand, or null -> row_exp_fixed
   int row_exp_fixed;
-  const double* col_scale;  // [N] 2^(col_exp - 12)
-  const double* bias;       // [N]             (FWD)
-  const double* idt;        // [N] or null     (FWD: of this layer; BWD: of the layer below)
+  const double* colv;       // [N][4] per output column: {2^(col_exp - 12), add, mul, 0}
+                            //   FWD: add = bias, mul = idt (1 without resnet_dt)
+                            //   BWD: add = head weight (0 unless the layer above is the head), mul = idt of the layer below
   const double* skip;       // blocked [n][N] or null (FWD: y_prev; BWD: g of the layer above)
-  const double* skip_vec;   // [N] or null     (BWD of the last hidden layer: g = head weights)
   const double* t_in;       // blocked [n][N]  (BWD: tanh values of the layer below)
   double* out0;             // FWD: t (blocked); BWD: g (blocked, nullable); PLAIN: row-major
   double* out1;             // FWD: y (blocked); BWD: dz (blocked)
@@ -65,6 +65,8 @@ struct GemmParams {
   int Kp_out;
   int out_exp;
   long long ld_out;  // PLAIN: leading dimension
+  int wide_store;    // PLAIN: rows are 32-byte aligned (256-bit stores)
+  long long* dbg;    // optional per-role cycle counters of every CTA ([grid][16]; profiling only)
 };
 
 // ---------------------------------------------------------------------------------------- PTX wrappers
@@ -150,6 +152,22 @@ __device__ __forceinline__ uint64_t smem_desc_sw64(uint32_t saddr) {
   return d;
 }
 
+// One elected lane of a converged warp (the compiler then knows the region is single-threaded and feeds the
+// uniform-register operands of UTCIMMA without a per-instruction waterfall loop).
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t.reg .pred P;\n\t"
+      "elect.sync _|P, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, P;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
+}
+// descriptor of the tile `byte_off` bytes after the one described by `base_lo` (same layout; < 256 KB of smem)
+__device__ __forceinline__ uint64_t desc_at(uint32_t base_lo, uint32_t byte_off) {
+  return ((uint64_t)0x80004020u << 32) | (uint64_t)(base_lo + (byte_off >> 4));
+}
+
 // Instruction descriptor (cute::UMMA::InstrDescriptor): D = s32, A = B = signed int8, both K-major, M x N.
 __host__ __device__ constexpr uint32_t idesc_i8(int M, int N) {
   return (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
@@ -188,19 +206,73 @@ extern __shared__ __align__(16) unsigned char fit_smem_raw[];
 
 template <int NS, int NT>
 struct SmemLayout {
-  static constexpr int kABytes = kTileM * kChunkK;  // one slice of the A chunk
+  static constexpr int NH = NS / 2;                 // slices per half chunk
+  static constexpr int kABytes = kTileM * kChunkK;  // one slice of one A chunk
   static constexpr int kBBytes = NT * kChunkK;
-  static constexpr int kStageBytes = NS * (kABytes + kBBytes);
+  static constexpr int kAHalf = NH * kABytes;       // [NH][128][64]
+  static constexpr int kBHalf = NH * kBBytes;       // [NH][NT][64]: consecutive slices = consecutive row groups
+  static constexpr int kStageBytes = kAHalf + kBHalf;
   static constexpr int kBarOff = kStages * kStageBytes;
-  static constexpr int kTotal = kBarOff + 128 + 1024;  // + slack to align the tiles to 1024 B
+  static constexpr int kColvOff = kBarOff + 512;       // per epilogue warp: colv of its 16 columns (512 B)
+  static constexpr int kTotal = kColvOff + kEpiWarps * 512 + 1024;  // + slack to align the tiles to 1024 B
 };
+
+// int32 -> double without the conversion unit: 2^52 + 2^31 + a has the bits {0x43300000, a ^ 0x80000000}
+__device__ __forceinline__ double i2d(int a) {
+  return __hiloint2double(0x43300000, a ^ (int)0x80000000) - 4503601774854144.0;
+}
+
+// Branch-free tanh, absolute error ~1e-16 (the callers need absolute, not relative, accuracy: t feeds
+// y = t*idt + skip and 1 - t^2):  u = exp(-2|x|), tanh = sign(x) (1 - u) / (1 + u).
+__device__ __forceinline__ double tanh_bf(double x) {
+  const double a = fmin(fabs(x), 20.0);
+  const double t = -2.0 * a;
+  double kf = fma(t, 1.4426950408889634, 6755399441055744.0);
+  const int ki = __double2loint(kf);
+  kf -= 6755399441055744.0;
+  double r = fma(kf, -6.93147180369123816490e-01, t);
+  r = fma(kf, -1.90821492927058770002e-10, r);
+  double p = 2.505210838544172e-08;              // 1/11!  (|r| <= ln2/2: truncation 6e-15 of u)
+  p = fma(p, r, 2.755731922398589e-07);          // 1/10!
+  p = fma(p, r, 2.7557319223985893e-06);         // 1/9!
+  p = fma(p, r, 2.48015873015873e-05);           // 1/8!
+  p = fma(p, r, 1.984126984126984e-04);          // 1/7!
+  p = fma(p, r, 1.388888888888889e-03);          // 1/6!
+  p = fma(p, r, 8.333333333333333e-03);          // 1/5!
+  p = fma(p, r, 4.1666666666666664e-02);         // 1/4!
+  p = fma(p, r, 1.6666666666666666e-01);         // 1/3!
+  p = fma(p, r, 0.5);
+  p = fma(p, r, 1.0);
+  p = fma(p, r, 1.0);
+  const double u = p * __hiloint2double((1023 + ki) << 20, 0);
+  const double num = 1.0 - u, den = 1.0 + u;  // den in [1, 2]
+  double rc;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(rc) : "d"(den));
+  rc = fma(fma(-den, rc, 1.0), rc, rc);
+  rc = fma(fma(-den, rc, 1.0), rc, rc);
+  return copysign(num * rc, x);
+}
+
+__device__ __forceinline__ void st_256(double* p, double a, double b, double c, double d) {
+  asm volatile("st.global.cs.v4.f64 [%0], {%1, %2, %3, %4};" ::"l"(p), "d"(a), "d"(b), "d"(c), "d"(d) : "memory");
+}
+
+__device__ __forceinline__ double4 ldg_256(const double* p) {
+  double4 v;
+  asm("ld.global.nc.v4.f64 {%0, %1, %2, %3}, [%4];" : "=d"(v.x), "=d"(v.y), "=d"(v.z), "=d"(v.w) : "l"(p));
+  return v;
+}
 
 template <int NS, int NT, int EPI>
 __global__ void __launch_bounds__(kThreads, 1)
     k_fit_gemm(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                const __grid_constant__ GemmParams p) {
   using L = SmemLayout<NS, NT>;
-  static_assert(NS * NT <= 512 && NT % 16 == 0 && NT <= 256, "accumulators must fit in tensor memory");
+  constexpr int NH = L::NH;
+  static_assert(NS % 2 == 0 && NS * NT <= 512 && NT % 16 == 0 && NH * NT <= 256,
+                "accumulators must fit in tensor memory, one MMA spans up to NS/2 slices of B");
+  static_assert(NT / 16 * 4 == kEpiWarps, "one epilogue warp per (lane quadrant, 16-column group)");
+  static_assert(L::kStageBytes % 1024 == 0 && L::kAHalf % 1024 == 0, "tiles must stay 1024-byte aligned");
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   unsigned char* fit_smem = fit_smem_raw + ((1024u - (smem_u32(fit_smem_raw) & 1023u)) & 1023u);
@@ -217,7 +289,7 @@ __global__ void __launch_bounds__(kThreads, 1)
       mbar_init(bar_empty + 8 * s, 1);
     }
     mbar_init(bar_tfull, 1);
-    mbar_init(bar_tempty, 128);
+    mbar_init(bar_tempty, 32 * kEpiWarps);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
@@ -238,157 +310,241 @@ __global__ void __launch_bounds__(kThreads, 1)
 
   if (warp == 0) {
     // ---------------------------------------------------------------- TMA producer
+    // One stage = half a K-chunk: A slices [h*NH, (h+1)*NH) as [NH][128][64 B] and the same slices of B as
+    // [NH][NT][64 B], one bulk tensor copy each.
     if (lane == 0) {
-      int stage = 0;
-      uint32_t phase = 0;
+      uint32_t it = 0;
+      long long w_empty = 0;
+      const long long t_begin = clock64();
       for (long long tile = blockIdx.x; tile < total; tile += gridDim.x) {
         const int mb = (int)(tile / p.n_tiles);
         const int nb = (int)(tile - (long long)mb * p.n_tiles);
         for (int kc = 0; kc < nk; ++kc) {
-          mbar_wait(bar_empty + 8 * stage, phase ^ 1);
-          const uint32_t fb = bar_full + 8 * stage;
-          mbar_expect_tx(fb, (uint32_t)L::kStageBytes);
-          const uint32_t sa = smem0 + stage * L::kStageBytes;
-          const uint32_t sb = sa + NS * L::kABytes;
 #pragma unroll
-          for (int s = 0; s < NS; ++s) {
-            tma_load_3d(sa + s * L::kABytes, &tmA, kc * kChunkK, s, mb * kTileM, fb);
-            tma_load_3d(sb + s * L::kBBytes, &tmB, kc * kChunkK, nb * NT, s, fb);
+          for (int h = 0; h < 2; ++h, ++it) {
+            const uint32_t stage = it % kStages;
+            const long long c0 = p.dbg ? clock64() : 0;
+            mbar_wait(bar_empty + 8 * stage, ((it / kStages) & 1u) ^ 1u);
+            if (p.dbg) w_empty += clock64() - c0;
+            const uint32_t fb = bar_full + 8 * stage;
+            mbar_expect_tx(fb, (uint32_t)L::kStageBytes);
+            const uint32_t sa = smem0 + stage * L::kStageBytes;
+            tma_load_3d(sa, &tmA, kc * kChunkK, mb * kTileM, h * NH, fb);
+            tma_load_3d(sa + L::kAHalf, &tmB, kc * kChunkK, nb * NT, h * NH, fb);
           }
-          if (++stage == kStages) stage = 0, phase ^= 1;
         }
+      }
+      if (p.dbg) {
+        p.dbg[blockIdx.x * 16 + 0] = clock64() - t_begin;
+        p.dbg[blockIdx.x * 16 + 1] = w_empty;
       }
     }
   } else if (warp == 1) {
     // ---------------------------------------------------------------- MMA issuer
-    constexpr uint32_t idesc = idesc_i8(kTileM, NT);
-    int stage = 0;
-    uint32_t phase = 0, acc_phase = 0;
+    // The product A_i . B_j belongs to order i + j, whose accumulator is the column block (i + j) * NT of tensor
+    // memory.  Slices of B that are consecutive in shared memory are consecutive row groups of ONE K-major tile, so
+    // A_i . [B_j; B_j+1; ..] is a single tcgen05.mma of N = NT * count whose result lands in the consecutive
+    // order blocks i + j, i + j + 1, ...: 9 instructions per K-step instead of 21, and the A tile is read from
+    // shared memory 9 times instead of 21 (the N = NT products are bound by the shared-memory read of A).
+    const uint32_t lo0 = (uint32_t)smem_desc_sw64(smem0);
+    const bool leader = elect_one();
+    uint32_t it = 0, acc_phase = 0;
+    long long w_tempty = 0, w_full = 0;
+    const long long t_begin = clock64();
     for (long long tile = blockIdx.x; tile < total; tile += gridDim.x) {
+      long long c0 = p.dbg ? clock64() : 0;
       mbar_wait(bar_tempty, acc_phase ^ 1);
+      if (p.dbg) w_tempty += clock64() - c0;
       tc_fence_after();
-      uint32_t started = 0;
-      for (int kc = 0; kc < nk; ++kc) {
-        mbar_wait(bar_full + 8 * stage, phase);
+      for (int kc = 0; kc < nk; ++kc, it += 2) {
+        const uint32_t s0 = it % kStages, s1 = (it + 1) % kStages;
+        const uint32_t o0 = s0 * L::kStageBytes, o1 = s1 * L::kStageBytes;
+        c0 = p.dbg ? clock64() : 0;
+        mbar_wait(bar_full + 8 * s0, (it / kStages) & 1u);
+        // the first chunk of a tile needs both halves at once: A_0 . B_hi must be the first write of the upper orders
+        if (kc == 0) mbar_wait(bar_full + 8 * s1, ((it + 1) / kStages) & 1u);
+        if (p.dbg) w_full += clock64() - c0;
         tc_fence_after();
-        if (lane == 0) {
-          const uint32_t sa = smem0 + stage * L::kStageBytes;
-          const uint32_t sb = sa + NS * L::kABytes;
+        if (leader) {
 #pragma unroll
           for (int k = 0; k < kChunkK / 32; ++k) {
+            const uint32_t acc = (kc == 0 && k == 0) ? 0u : 1u;
+            // A_0 . B_lo -> orders 0..NH-1 ; A_0 . B_hi -> orders NH..NS-1 (first chunk only, see above)
+            mma_i8(tmem_base, desc_at(lo0, o0 + k * 32), desc_at(lo0, o0 + L::kAHalf + k * 32), idesc_i8(kTileM, NH * NT),
+                   acc);
+            if (kc == 0)
+              mma_i8(tmem_base + NH * NT, desc_at(lo0, o0 + k * 32), desc_at(lo0, o1 + L::kAHalf + k * 32),
+                     idesc_i8(kTileM, NH * NT), acc);
 #pragma unroll
-            for (int i = 0; i < NS; ++i) {
-              const uint64_t ad = smem_desc_sw64(sa + i * L::kABytes + k * 32);
-#pragma unroll
-              for (int j = 0; j < NS - i; ++j) {
-                const uint64_t bd = smem_desc_sw64(sb + j * L::kBBytes + k * 32);
-                const int d = i + j;
-                mma_i8(tmem_base + d * NT, ad, bd, idesc, (started >> d) & 1u);
-                started |= 1u << d;
-              }
-            }
+            for (int i = 1; i < NH; ++i)  // A_i . B_lo -> orders i..i+NH-1
+              mma_i8(tmem_base + i * NT, desc_at(lo0, o0 + i * L::kABytes + k * 32),
+                     desc_at(lo0, o0 + L::kAHalf + k * 32), idesc_i8(kTileM, NH * NT), 1u);
           }
-          tc_commit(bar_empty + 8 * stage);
+        }
+        __syncwarp();
+        if (kc != 0) {
+          c0 = p.dbg ? clock64() : 0;
+          mbar_wait(bar_full + 8 * s1, ((it + 1) / kStages) & 1u);
+          if (p.dbg) w_full += clock64() - c0;
+          tc_fence_after();
+        }
+        if (leader) {
+#pragma unroll
+          for (int k = 0; k < kChunkK / 32; ++k) {
+            if (kc != 0)
+              mma_i8(tmem_base + NH * NT, desc_at(lo0, o0 + k * 32), desc_at(lo0, o1 + L::kAHalf + k * 32),
+                     idesc_i8(kTileM, NH * NT), 1u);
+#pragma unroll
+            for (int i = 1; i < NH; ++i)  // A_i . B_hi[0 .. NH-i) -> orders NH+i..NS-1
+              mma_i8(tmem_base + (NH + i) * NT, desc_at(lo0, o0 + i * L::kABytes + k * 32),
+                     desc_at(lo0, o1 + L::kAHalf + k * 32), idesc_i8(kTileM, (NH - i) * NT), 1u);
+#pragma unroll
+            for (int i = NH; i < NS; ++i)  // A_i (upper half) . B_lo[0 .. NS-i) -> orders i..NS-1
+              mma_i8(tmem_base + i * NT, desc_at(lo0, o1 + (i - NH) * L::kABytes + k * 32),
+                     desc_at(lo0, o0 + L::kAHalf + k * 32), idesc_i8(kTileM, (NS - i) * NT), 1u);
+          }
+          tc_commit(bar_empty + 8 * s0);
+          tc_commit(bar_empty + 8 * s1);
           if (kc == nk - 1) tc_commit(bar_tfull);
         }
         __syncwarp();
-        if (++stage == kStages) stage = 0, phase ^= 1;
       }
       acc_phase ^= 1;
     }
+    if (p.dbg && lane == 0) {
+      p.dbg[blockIdx.x * 16 + 2] = clock64() - t_begin;
+      p.dbg[blockIdx.x * 16 + 3] = w_tempty;
+      p.dbg[blockIdx.x * 16 + 4] = w_full;
+    }
   } else {
-    // ---------------------------------------------------------------- epilogue (thread = row)
+    // ---------------------------------------------------------------- epilogue (thread = row, 16 columns)
     const int quad = warp & 3;
+    const int cg = (warp - 2) >> 2;
+    const int cc = cg * 16;
     const int row_in_tile = quad * 32 + lane;
-    const uint32_t lane_addr = tmem_base + ((uint32_t)(quad * 32) << 16);
+    const uint32_t lane_addr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)cc;
+    double* cvs = reinterpret_cast<double*>(fit_smem + L::kColvOff + (warp - 2) * 512);
     uint32_t acc_phase = 0;
+    long long w_tfull = 0, t_drain = 0, t_math = 0;
+    const long long t_begin = clock64();
     for (long long tile = blockIdx.x; tile < total; tile += gridDim.x) {
       const int mb = (int)(tile / p.n_tiles);
       const int nb = (int)(tile - (long long)mb * p.n_tiles);
       const long long r = (long long)mb * kTileM + row_in_tile;
       const bool row_ok = r < p.n;
-      const double rs = pow2i(row_ok && p.row_exp ? p.row_exp[r] : p.row_exp_fixed);
+      const int c0 = nb * NT + cc;
+      const bool live = c0 < p.N;  // (warp-uniform)
+      // blocked offset of (r, c0): ((mb * N + c) * 128 + row_in_tile)
+      const long long boff = ((long long)mb * p.N + c0) * kTileM + row_in_tile;
+      const double rs = pow2i(live && row_ok && p.row_exp ? __ldg(p.row_exp + r) : p.row_exp_fixed);
+      // per-column constants of this warp's 16 columns -> shared memory (read back as broadcasts in the math below;
+      // a global load per element would put an L2 round trip on every element's critical path)
+      __syncwarp();
+      if (live && lane < 16) {
+        const double4 c4 = ldg_256(p.colv + 4 * (long long)(c0 + lane));
+        *reinterpret_cast<double2*>(cvs + 4 * lane) = make_double2(c4.x, c4.y);
+        *reinterpret_cast<double2*>(cvs + 4 * lane + 2) = make_double2(c4.z, c4.w);
+      }
+      __syncwarp();
+      const long long e0 = p.dbg ? clock64() : 0;
       mbar_wait(bar_tfull, acc_phase);
+      const long long e1 = p.dbg ? clock64() : 0;
       tc_fence_after();
-#pragma unroll 1
-      for (int cc = 0; cc < NT; cc += 16) {
-        const int c0 = nb * NT + cc;
-        if (c0 >= p.N) break;  // (uniform)
-        double v[16];
-        {
-          int a[16];
-          tmem_ld16(lane_addr + (uint32_t)((NS - 1) * NT + cc), a);
+      double v[16];
+      if (live) {
+        int a[16];
+        tmem_ld16(lane_addr + (uint32_t)((NS - 1) * NT), a);
+        tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 16; ++j) v[j] = i2d(a[j]);
+#pragma unroll
+        for (int d = NS - 2; d >= 0; --d) {
+          tmem_ld16(lane_addr + (uint32_t)(d * NT), a);
           tmem_ld_wait();
 #pragma unroll
-          for (int j = 0; j < 16; ++j) v[j] = (double)a[j];
-#pragma unroll
-          for (int d = NS - 2; d >= 0; --d) {
-            tmem_ld16(lane_addr + (uint32_t)(d * NT + cc), a);
-            tmem_ld_wait();
-#pragma unroll
-            for (int j = 0; j < 16; ++j) v[j] = v[j] * 0.0078125 + (double)a[j];
-          }
-        }
-        // blocked offset of (r, c0): ((mb * N + c) * 128 + row_in_tile)
-        const long long boff = ((long long)mb * p.N + c0) * kTileM + row_in_tile;
-        if (EPI == EPI_FWD) {
-          double y[16];
-#pragma unroll
-          for (int j = 0; j < 16; ++j) {
-            const int c = c0 + j;
-            const bool ok = c < p.N;
-            const int cs = ok ? c : p.N - 1;
-            const double z = v[j] * rs * __ldg(p.col_scale + cs) + __ldg(p.bias + cs);
-            const double t = tanh(z);
-            double yy = p.idt ? t * __ldg(p.idt + cs) : t;
-            if (p.skip && row_ok && ok) yy += p.skip[boff + (long long)j * kTileM];
-            y[j] = ok ? yy : 0.;
-            if (row_ok && ok) {
-              p.out0[boff + (long long)j * kTileM] = t;
-              p.out1[boff + (long long)j * kTileM] = yy;
-            }
-          }
-          if (p.slices_out && row_ok) {
-            // (columns >= N inside the padded K of the next layer are written as zero digits)
-            const double up = pow2i(6 + 7 * (NS - 1) - p.out_exp);
-            if (c0 + 16 <= p.Kp_out) store_slices16<NS>(p.slices_out + r * p.ld_slices + c0, p.Kp_out, y, up);
-          }
-        } else if (EPI == EPI_BWD) {
-#pragma unroll
-          for (int j = 0; j < 16; ++j) {
-            const int c = c0 + j;
-            if (c < p.N && row_ok) {
-              double g = v[j] * rs * __ldg(p.col_scale + c);
-              if (p.skip) g += p.skip[boff + (long long)j * kTileM];
-              if (p.skip_vec) g += __ldg(p.skip_vec + c);
-              const double t = p.t_in[boff + (long long)j * kTileM];
-              double dz = g * (1. - t * t);
-              if (p.idt) dz *= __ldg(p.idt + c);
-              if (p.out0) p.out0[boff + (long long)j * kTileM] = g;
-              p.out1[boff + (long long)j * kTileM] = dz;
-            }
-          }
-        } else {
-          if (row_ok) {
-            double* __restrict__ o = p.out0 + r * p.ld_out + c0;
-            if (c0 + 16 <= p.N && (p.ld_out & 1) == 0) {
-#pragma unroll
-              for (int j = 0; j < 16; j += 2) {
-                const double a0 = v[j] * rs * __ldg(p.col_scale + c0 + j);
-                const double a1 = v[j + 1] * rs * __ldg(p.col_scale + c0 + j + 1);
-                __stcs(reinterpret_cast<double2*>(o + j), make_double2(a0, a1));
-              }
-            } else {
-#pragma unroll
-              for (int j = 0; j < 16; ++j)
-                if (c0 + j < p.N) o[j] = v[j] * rs * __ldg(p.col_scale + c0 + j);
-            }
-          }
+          for (int j = 0; j < 16; ++j) v[j] = fma(v[j], 0.0078125, i2d(a[j]));
         }
       }
+      // the accumulators are in registers: the next tile's products may overwrite tensor memory now
       tc_fence_before();
       mbar_arrive(bar_tempty);
       acc_phase ^= 1;
+      const long long e2 = p.dbg ? clock64() : 0;
+      if (p.dbg) w_tfull += e1 - e0, t_drain += e2 - e1;
+      if (!live) continue;
+      // N is a multiple of 16 (host check) and the blocked matrices are padded to whole row blocks, so only the
+      // row-major outputs (slices, PLAIN) need the row predicate.  Inputs are fetched 8 columns at a time.
+      if (EPI == EPI_FWD) {
+        const double* __restrict__ sk = p.skip ? p.skip + boff : nullptr;
+        double* __restrict__ o0 = p.out0 + boff;
+        double* __restrict__ o1 = p.out1 + boff;
+#pragma unroll
+        for (int h = 0; h < 16; h += 8) {
+          double xin[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) xin[j] = sk ? __ldcs(sk + (h + j) * kTileM) : 0.;
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const double2 c01 = *reinterpret_cast<const double2*>(cvs + 4 * (h + j));
+            const double2 c23 = *reinterpret_cast<const double2*>(cvs + 4 * (h + j) + 2);
+            const double4 c4 = make_double4(c01.x, c01.y, c23.x, c23.y);
+            const double t = tanh_bf(fma(v[h + j], rs * c4.x, c4.y));
+            const double yy = fma(t, c4.z, xin[j]);
+            v[h + j] = yy;
+            __stcs(o0 + (h + j) * kTileM, t);
+            __stcs(o1 + (h + j) * kTileM, yy);
+          }
+        }
+        if (row_ok && p.slices_out) {
+          const double up = pow2i(6 + 7 * (NS - 1) - p.out_exp);
+          store_slices16<NS>(p.slices_out + r * p.ld_slices + c0, p.Kp_out, v, up);
+        }
+      } else if (EPI == EPI_BWD) {
+        const double* __restrict__ sk = p.skip ? p.skip + boff : nullptr;
+        const double* __restrict__ ti = p.t_in + boff;
+        double* __restrict__ o0 = p.out0 ? p.out0 + boff : nullptr;
+        double* __restrict__ o1 = p.out1 + boff;
+#pragma unroll
+        for (int h = 0; h < 16; h += 8) {
+          double xin[8], tin[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            xin[j] = sk ? __ldcs(sk + (h + j) * kTileM) : 0.;
+            tin[j] = __ldcs(ti + (h + j) * kTileM);
+          }
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const double2 c01 = *reinterpret_cast<const double2*>(cvs + 4 * (h + j));
+            const double2 c23 = *reinterpret_cast<const double2*>(cvs + 4 * (h + j) + 2);
+            const double4 c4 = make_double4(c01.x, c01.y, c23.x, c23.y);
+            const double g = fma(v[h + j], rs * c4.x, xin[j] + c4.y);
+            const double dz = g * c4.z * fma(-tin[j], tin[j], 1.0);
+            if (o0) __stcs(o0 + (h + j) * kTileM, g);
+            __stcs(o1 + (h + j) * kTileM, dz);
+          }
+        }
+      } else {
+        if (row_ok) {
+          double* __restrict__ o = p.out0 + r * p.ld_out + c0;
+#pragma unroll
+          for (int j = 0; j < 16; ++j) v[j] *= rs * cvs[4 * j];
+          if (p.wide_store) {  // 32-byte aligned rows: one full sector per store
+#pragma unroll
+            for (int j = 0; j < 16; j += 4) st_256(o + j, v[j], v[j + 1], v[j + 2], v[j + 3]);
+          } else {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) __stcs(o + j, v[j]);
+          }
+        }
+      }
+      if (p.dbg) t_math += clock64() - e2;
+    }
+    if (p.dbg && lane == 0 && (warp == 2 || warp == 21)) {
+      long long* d = p.dbg + blockIdx.x * 16 + (warp == 2 ? 5 : 9);
+      d[0] = clock64() - t_begin;
+      d[1] = w_tfull;
+      d[2] = t_drain;
+      d[3] = t_math;
     }
   }
 
@@ -524,24 +680,33 @@ int launch_gemm(const CUtensorMap& ma, const CUtensorMap& mb, const GemmParams& 
 }  // namespace
 }  // namespace dpb200
 
+namespace dpb200 {
+namespace {
+long long* g_fit_dbg = nullptr;
+}
+}  // namespace dpb200
+
 extern "C" {
+
+/* profiling hook: device buffer of [grid][16] cycle counters filled by the next fit_gemm launches (NULL: off) */
+void dpb200_fit_gemm_debug(long long* dbg) { dpb200::g_fit_dbg = dbg; }
 
 int dpb200_fit_gemm_i8_f64(int mode, long long nrow, int N, int K, int nslice, const signed char* a_slices,
                            long long a_slice_stride, long long a_row_stride, const int* row_exp, int row_exp_fixed,
-                           const signed char* b_slices, int b_k_stride, const double* col_scale, const double* bias,
-                           const double* idt, const double* skip, const double* skip_vec, const double* t_in,
-                           double* out0, double* out1, long long ld_out, signed char* slices_out,
+                           const signed char* b_slices, int b_k_stride, const double* colv, const double* skip,
+                           const double* t_in, double* out0, double* out1, long long ld_out, signed char* slices_out,
                            long long ld_slices, int kp_out, int out_exp, dpb200_stream_t stream) {
   using namespace dpb200;
   DPB_REQUIRE(mode >= 0 && mode <= 2, "fit_gemm: mode must be 0 (forward), 1 (backward) or 2 (plain)");
   DPB_REQUIRE(nslice == 6, "fit_gemm: only 6 operand slices are built");
-  DPB_REQUIRE(nrow >= 0 && N >= 1 && K >= 1, "fit_gemm: bad shape");
+  DPB_REQUIRE(nrow >= 0 && N >= 16 && N % 16 == 0 && K >= 1, "fit_gemm: N must be a positive multiple of 16");
   if (nrow == 0) return DPB200_OK;
-  DPB_REQUIRE(a_slices && b_slices && col_scale && (out0 || mode == EPI_BWD), "fit_gemm: null pointer");
+  DPB_REQUIRE(a_slices && b_slices && colv && (out0 || mode == EPI_BWD) && ((uintptr_t)colv & 31) == 0,
+              "fit_gemm: null pointer (colv must be 32-byte aligned)");
   DPB_REQUIRE(K % 16 == 0 && a_slice_stride % 16 == 0 && a_row_stride % 16 == 0 && b_k_stride % 64 == 0 &&
                   b_k_stride >= K && ((uintptr_t)a_slices & 15) == 0 && ((uintptr_t)b_slices & 15) == 0,
               "fit_gemm: operands must be 16-byte aligned with K a multiple of 16 and the weight rows padded to 64");
-  DPB_REQUIRE(mode != EPI_FWD || (bias && out1), "fit_gemm: forward needs bias and both outputs");
+  DPB_REQUIRE(mode != EPI_FWD || out1, "fit_gemm: forward needs both outputs");
   DPB_REQUIRE(mode != EPI_BWD || (t_in && out1), "fit_gemm: backward needs t_in and the dz output");
   DPB_REQUIRE(!slices_out || (kp_out % 16 == 0 && kp_out >= N && ld_slices >= (long long)nslice * kp_out &&
                               ((uintptr_t)slices_out & 15) == 0 && ld_slices % 16 == 0),
@@ -555,11 +720,8 @@ int dpb200_fit_gemm_i8_f64(int mode, long long nrow, int N, int K, int nslice, c
   p.m_blocks = (nrow + kTileM - 1) / kTileM;
   p.row_exp = row_exp;
   p.row_exp_fixed = row_exp_fixed;
-  p.col_scale = col_scale;
-  p.bias = bias;
-  p.idt = idt;
+  p.colv = colv;
   p.skip = skip;
-  p.skip_vec = skip_vec;
   p.t_in = t_in;
   p.out0 = out0;
   p.out1 = out1;
@@ -568,14 +730,17 @@ int dpb200_fit_gemm_i8_f64(int mode, long long nrow, int N, int K, int nslice, c
   p.Kp_out = kp_out;
   p.out_exp = out_exp;
   p.ld_out = ld_out;
+  p.dbg = g_fit_dbg;
+  p.wide_store = (mode == EPI_PLAIN && ld_out % 4 == 0 && ((uintptr_t)out0 & 31) == 0) ? 1 : 0;
   CUtensorMap ma, mb;
-  // A: [nrow][nslice][K] bytes (slice stride, row stride given); K beyond the tensor is zero-filled by TMA
-  int rc = make_map(&ma, a_slices, (unsigned long long)K, (unsigned long long)nslice, (unsigned long long)nrow,
-                    (unsigned long long)a_slice_stride, (unsigned long long)a_row_stride, 1, kTileM);
+  // A: [nrow][nslice][K] bytes seen as {K, row, slice} (byte strides given); box {64, 128, NS/2} lands in shared
+  // memory as [slice][row][64]; rows / K beyond the tensor are zero-filled by TMA
+  int rc = make_map(&ma, a_slices, (unsigned long long)K, (unsigned long long)nrow, (unsigned long long)nslice,
+                    (unsigned long long)a_row_stride, (unsigned long long)a_slice_stride, kTileM, NS / 2);
   if (rc != DPB200_OK) return rc;
   // B: [nslice][N][b_k_stride] bytes (weights transposed: row = output column, K contiguous, zero padded)
   rc = make_map(&mb, b_slices, (unsigned long long)b_k_stride, (unsigned long long)N, (unsigned long long)nslice,
-                (unsigned long long)b_k_stride, (unsigned long long)b_k_stride * N, NT, 1);
+                (unsigned long long)b_k_stride, (unsigned long long)b_k_stride * N, NT, NS / 2);
   if (rc != DPB200_OK) return rc;
   cudaStream_t st = (cudaStream_t)stream;
   if (mode == EPI_FWD) return launch_gemm<NS, NT, EPI_FWD>(ma, mb, p, st);

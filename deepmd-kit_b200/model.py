@@ -166,20 +166,32 @@ class FittingNet:
             if k_in != k_out:
                 return False
 
-        def pack(w):  # w [K, N] -> slices [ns, N, Kp], col_scale [N]
+        def pack(w, add=None, mul=None):  # w [K, N] -> B slices [ns, N, Kp], colv [N, 4] = {scale, add, mul, 0}, Kp
             sl, ce = split_i8_cols(w, nslice)
             K, N = w.shape
             Kp = (K + 63) // 64 * 64
             b = torch.zeros((nslice, N, Kp), dtype=torch.int8)
             b[:, :, :K] = sl.permute(0, 2, 1)
-            return b.contiguous().to(dev), torch.ldexp(torch.ones(N, dtype=torch.float64), ce - 12).to(dev), Kp
+            colv = torch.zeros((N, 4), dtype=torch.float64)
+            colv[:, 0] = torch.ldexp(torch.ones(N, dtype=torch.float64), ce - 12)
+            if add is not None:
+                colv[:, 1] = add.detach().to("cpu", torch.float64)
+            colv[:, 2] = 1.0 if mul is None else mul.detach().to("cpu", torch.float64)
+            return b.contiguous().to(dev), colv.contiguous().to(dev), Kp
 
+        if any(w.shape[1] % 16 for w, _, _ in self.layers):
+            return False
         tc = dict(nslice=nslice, fw=[], bw=[], exp=[])
         bound = 0.0
+        nl = len(self.layers)
         for li, (w, b, idt) in enumerate(self.layers):
             w64 = w.detach().to("cpu", torch.float64)
-            tc["fw"].append(pack(w64))
-            tc["bw"].append(pack(w64.t().contiguous()))
+            tc["fw"].append(pack(w64, add=b, mul=idt))
+            if li == 0:
+                tc["bw"].append(pack(w64.t().contiguous()))
+            else:  # epilogue of the backward GEMM of layer li: g_{li-1} (+ head weights on top), times idt_{li-1}
+                tc["bw"].append(pack(w64.t().contiguous(), add=self.head[0][:, 0] if li == nl - 1 else None,
+                                     mul=self.layers[li - 1][2]))
             amp = 1.0 if idt is None else float(idt.abs().max())
             bound = amp if li == 0 else bound + amp
             tc["exp"].append(int(math.floor(math.log2(bound))) + 2)
@@ -209,9 +221,9 @@ class FittingNet:
             last = li == nl - 1
             kp_out = (N + 15) // 16 * 16
             sl = None if last else torch.empty((n, ns * kp_out), dtype=torch.int8, device=dev)
-            ops.fit_gemm_i8(0, n, N, K, a, a_ss, a_rs, a_exp, a_fixed, bsl, Kp, cs, bias=b, idt=idt,
-                            skip=ys[-1] if li > 0 else None, out0=t, out1=y, slices_out=sl,
-                            ld_slices=0 if last else ns * kp_out, kp_out=kp_out, out_exp=tc["exp"][li], nslice=ns)
+            ops.fit_gemm_i8(0, n, N, K, a, a_ss, a_rs, a_exp, a_fixed, bsl, Kp, cs, skip=ys[-1] if li > 0 else None,
+                            out0=t, out1=y, slices_out=sl, ld_slices=0 if last else ns * kp_out, kp_out=kp_out,
+                            out_exp=tc["exp"][li], nslice=ns)
             ts.append(t)
             ys.append(y)
             if not last:
@@ -227,8 +239,7 @@ class FittingNet:
             need_g = li - 1 > 0
             g = torch.empty(nb * n_in, dtype=torch.float64, device=dev) if need_g else None
             dzn = torch.empty(nb * n_in, dtype=torch.float64, device=dev)
-            ops.fit_gemm_i8(1, n, n_in, kp, dz, kp, ns * kp, dz_exp, 0, bsl, Kp, cs, idt=self.layers[li - 1][2],
-                            skip=g_prev, skip_vec=tc["w_head"] if g_prev is None else None, t_in=ts[li - 1],
+            ops.fit_gemm_i8(1, n, n_in, kp, dz, kp, ns * kp, dz_exp, 0, bsl, Kp, cs, skip=g_prev, t_in=ts[li - 1],
                             out0=g, out1=dzn, nslice=ns)
             g_prev = g
             kp = (n_in + 15) // 16 * 16

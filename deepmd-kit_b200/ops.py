@@ -740,17 +740,17 @@ def mlp_tanh_bwd(g, a, idt=None, split3=False):
 
 
 def fit_gemm_i8(mode, n, N, K, a_slices, a_slice_stride, a_row_stride, row_exp, row_exp_fixed, b_slices, b_k_stride,
-                col_scale, bias=None, idt=None, skip=None, skip_vec=None, t_in=None, out0=None, out1=None, ld_out=0,
-                slices_out=None, ld_slices=0, kp_out=0, out_exp=0, nslice=6):
+                colv, skip=None, t_in=None, out0=None, out1=None, ld_out=0, slices_out=None, ld_slices=0, kp_out=0,
+                out_exp=0, nslice=6):
     """One fitting-net GEMM on the int8 tensor cores (dpb200_fit_gemm_i8_f64, csrc/fit_tc.cu): mode 0 forward layer,
-    1 backward layer, 2 plain product.  fp64 intermediates are in the row-blocked layout of fit_blocked()."""
-    dev = _need_cuda(("a_slices", a_slices), ("b_slices", b_slices), ("col_scale", col_scale), ("row_exp", row_exp),
-                     ("bias", bias), ("idt", idt), ("skip", skip), ("skip_vec", skip_vec), ("t_in", t_in),
-                     ("out0", out0), ("out1", out1), ("slices_out", slices_out))
+    1 backward layer, 2 plain product.  colv [N, 4] = {2^(col_exp-12), add, mul, 0} per output column; fp64
+    intermediates are in the row-blocked layout of fit_blocked()."""
+    dev = _need_cuda(("a_slices", a_slices), ("b_slices", b_slices), ("colv", colv), ("row_exp", row_exp),
+                     ("skip", skip), ("t_in", t_in), ("out0", out0), ("out1", out1), ("slices_out", slices_out))
     lib().call("fit_gemm_i8_f64", int(mode), int(n), int(N), int(K), int(nslice), _p(a_slices), int(a_slice_stride),
-               int(a_row_stride), _p(row_exp), int(row_exp_fixed), _p(b_slices), int(b_k_stride), _p(col_scale),
-               _p(bias), _p(idt), _p(skip), _p(skip_vec), _p(t_in), _p(out0), _p(out1), int(ld_out), _p(slices_out),
-               int(ld_slices), int(kp_out), int(out_exp), _stream(dev))
+               int(a_row_stride), _p(row_exp), int(row_exp_fixed), _p(b_slices), int(b_k_stride), _p(colv), _p(skip),
+               _p(t_in), _p(out0), _p(out1), int(ld_out), _p(slices_out), int(ld_slices), int(kp_out), int(out_exp),
+               _stream(dev))
 
 
 def fit_blocked_rows(n):

@@ -323,12 +323,14 @@ int dpb200_split_tf32_f32(float* out, long long ld_out, const float* x, long lon
  * accumulators stay in tensor memory, the layer's elementwise chain fused into the epilogue.
  *  fit_gemm_i8 : C[nrow][N] = A.B^T, A = int8 slices [nrow][nslice][K] (byte strides a_slice_stride /
  *                a_row_stride; per-row exponent row_exp[r] or row_exp_fixed when row_exp == NULL), B = int8
- *                slices [nslice][N][b_k_stride] (K contiguous, zero padded to a multiple of 64),
- *                col_scale[c] = 2^(col_exp[c]-12).  fp64 matrices other than `out0` of mode 2 use the
- *                row-blocked layout: element (r, c) at ((r/128)*N + c)*128 + r%128.
- *                mode 0  z = C + bias, t = tanh(z), y = t*idt (+ skip): out0 = t, out1 = y, slices_out
- *                        (nullable) = y as [nrow][nslice][kp_out] int8 with the fixed exponent out_exp;
- *                mode 1  g = C (+ skip) (+ skip_vec[c]), dz = g*idt*(1 - t_in^2): out0 = g (nullable), out1 = dz;
+ *                slices [nslice][N][b_k_stride] (K contiguous, zero padded to a multiple of 64), N % 16 == 0.
+ *                colv [N][4] (32-byte aligned) = per output column {2^(col_exp-12), add, mul, 0}.
+ *                fp64 matrices other than `out0` of mode 2 use the row-blocked layout: element (r, c) at
+ *                ((r/128)*N + c)*128 + r%128, allocated for whole blocks of 128 rows.
+ *                mode 0  t = tanh(C + add), y = t*mul (+ skip): out0 = t, out1 = y, slices_out (nullable) = y as
+ *                        [nrow][nslice][kp_out] int8 with the fixed exponent out_exp   (add = bias, mul = idt);
+ *                mode 1  g = C + add (+ skip), dz = g*mul*(1 - t_in^2): out0 = g (nullable), out1 = dz
+ *                        (add = head weights or 0, mul = idt of the layer below);
  *                mode 2  out0[r*ld_out + c] = C  (row-major).
  *  fit_slice_rows : blocked fp64 [nrow][N] -> int8 slices [nrow][nslice][kp] + row_exp (A operand of mode 1 / 2).
  *  fit_head    : e[r] = y[r,:].w_head + b_head and the backward seed dz = w_head*idt*(1 - t^2) as slices.
@@ -336,9 +338,8 @@ int dpb200_split_tf32_f32(float* out, long long ld_out, const float* x, long lon
  * ------------------------------------------------------------------------------------- */
 int dpb200_fit_gemm_i8_f64(int mode, long long nrow, int N, int K, int nslice, const signed char* a_slices,
                            long long a_slice_stride, long long a_row_stride, const int* row_exp /*nullable*/,
-                           int row_exp_fixed, const signed char* b_slices, int b_k_stride, const double* col_scale,
-                           const double* bias, const double* idt /*nullable*/, const double* skip /*nullable*/,
-                           const double* skip_vec /*nullable*/, const double* t_in, double* out0, double* out1,
+                           int row_exp_fixed, const signed char* b_slices, int b_k_stride, const double* colv,
+                           const double* skip /*nullable*/, const double* t_in, double* out0, double* out1,
                            long long ld_out, signed char* slices_out /*nullable*/, long long ld_slices, int kp_out,
                            int out_exp, dpb200_stream_t stream);
 int dpb200_fit_slice_rows_f64(signed char* out, long long ld_out, int kp, int* row_exp, const double* x,
@@ -348,6 +349,9 @@ int dpb200_fit_head_f64(double* e_out, signed char* out, long long ld_out, int k
                         long long nrow, int N, int nslice, dpb200_stream_t stream);
 int dpb200_fit_blocked_f64(double* dst, const double* src, long long ld, long long nrow, int N, int to_blocked,
                            dpb200_stream_t stream);
+/* Profiling hook: the following fit_gemm launches write per-role cycle counters ([grid][16] long long, device
+ * memory: TMA producer / MMA issuer / two epilogue warps: total, barrier waits, drain, math); NULL switches it off. */
+void dpb200_fit_gemm_debug(long long* counters);
 
 /* use_nlist_map (neighbor_list.h:219-222): nlist[k] = map[nlist[k]] for entries >= 0. */
 int dpb200_use_nlist_map(int* nlist, const int* nlist_map, int nloc, int nnei, dpb200_stream_t stream);

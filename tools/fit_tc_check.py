@@ -24,7 +24,10 @@ def pack(w, ns=6):
     Kp = (K + 63) // 64 * 64
     b = torch.zeros((ns, N, Kp), dtype=torch.int8)
     b[:, :, :K] = sl.permute(0, 2, 1)
-    return b.contiguous().to(dev), torch.ldexp(torch.ones(N, dtype=torch.float64), ce - 12).to(dev), Kp
+    colv = torch.zeros((N, 4), dtype=torch.float64)
+    colv[:, 0] = torch.ldexp(torch.ones(N, dtype=torch.float64), ce - 12)
+    colv[:, 2] = 1.0
+    return b.contiguous().to(dev), colv.to(dev), Kp
 
 
 def plain(n, K, N, seed=0):
@@ -80,7 +83,7 @@ def timeit(fn, reps=5):
 
 def main():
     print(torch.cuda.get_device_name(0), flush=True)
-    for shape in [(128, 64, 80), (128, 64, 16), (100, 128, 80), (300, 240, 240), (1000, 1600, 240), (257, 240, 1600),
+    for shape in [(128, 64, 80), (128, 64, 16), (100, 128, 80), (300, 240, 240), (200, 48, 96), (1000, 1600, 240), (257, 240, 1600),
                   (4096, 1600, 240)]:
         try:
             plain(*shape)
@@ -111,16 +114,20 @@ def main():
         sl = torch.empty((n, 6 * 240), dtype=torch.int8, device=dev)
         bsl, cs, Kp = tc["fw"][0]
         w, b, idt = net.layers[0]
-        t0 = timeit(lambda: ops.fit_gemm_i8(0, n, 240, 1600, xs, 1600, xs.stride(0), ex, 0, bsl, Kp, cs, bias=b, idt=idt,
+        t0 = timeit(lambda: ops.fit_gemm_i8(0, n, 240, 1600, xs, 1600, xs.stride(0), ex, 0, bsl, Kp, cs,
                                             out0=t, out1=y, slices_out=sl, ld_slices=1440, kp_out=240, out_exp=tc["exp"][0]))
         bsl1, cs1, Kp1 = tc["fw"][1]
+        exr0 = torch.zeros(n, dtype=torch.int32, device=dev)
         w1, b1, idt1 = net.layers[1]
         t2 = torch.empty_like(t)
         y2 = torch.empty_like(t)
         sl2 = torch.empty_like(sl)
-        t1 = timeit(lambda: ops.fit_gemm_i8(0, n, 240, 240, sl, 240, 1440, None, tc["exp"][0], bsl1, Kp1, cs1, bias=b1,
-                                            idt=idt1, skip=y, out0=t2, out1=y2, slices_out=sl2, ld_slices=1440, kp_out=240,
+        t1 = timeit(lambda: ops.fit_gemm_i8(0, n, 240, 240, sl, 240, 1440, None, tc["exp"][0], bsl1, Kp1, cs1,
+                                            skip=y, out0=t2, out1=y2, slices_out=sl2, ld_slices=1440, kp_out=240,
                                             out_exp=tc["exp"][1]))
+        bslh, csh, Kph = tc["bw"][1]
+        t1b = timeit(lambda: ops.fit_gemm_i8(1, n, 240, 240, sl, 240, 1440, exr0, 0, bslh, Kph, csh, skip=y, t_in=t,
+                                             out0=t2, out1=y2))
         bslb, csb, Kpb = tc["bw"][0]
         gd = torch.empty((n, 1600), dtype=torch.float64, device=dev)
         exr = torch.zeros(n, dtype=torch.int32, device=dev)
@@ -129,7 +136,7 @@ def main():
         t5 = timeit(lambda: ops.fit_head(t, y, tc["w_head"], idt, tc["b_head"], n, 240, 240))
         f0 = 2.0 * n * 1600 * 240 * 21 / 1e12
         f1 = 2.0 * n * 240 * 240 * 21 / 1e12
-        print(f"[time] L0 fwd {t0:.3f} ms ({f0 / t0 * 1e3:.0f} TOP/s int8) | hidden fwd {t1:.3f} ms ({f1 / t1 * 1e3:.0f}) | "
+        print(f"[time] L0 fwd {t0:.3f} ms ({f0 / t0 * 1e3:.0f} TOP/s int8) | hidden fwd {t1:.3f} ms ({f1 / t1 * 1e3:.0f}) | hidden bwd {t1b:.3f} ms | "
               f"L0 bwd {t3:.3f} ms ({f0 / t3 * 1e3:.0f}) | slice {t4:.3f} ms | head {t5:.3f} ms", flush=True)
     return 0
 
