@@ -6,8 +6,9 @@
 // fp64 parity (1e-10) rules out a reduced-precision product, and B200's FP64 tensor pipe peaks at ~33-40
 // TFLOP/s, so every GEMM of the net is made EXACT on the int8 tensor cores by operand splitting
 // (csrc/fitting.cu has the digit convention):
-//     x = 2^Ex sum_i X_i 2^(-6-7i),   w = 2^Ew sum_j W_j 2^(-6-7j),    X_i, W_j signed 7-bit digits
-//     x.w = 2^(Ex+Ew-12) sum_d 2^(-7d) S_d,     S_d = sum_{i+j=d} X_i.W_j   (int32, error free),  d < NS
+//     x = 2^Ex sum_i X_i 2^(-7-8i),   w = 2^Ew sum_j W_j 2^(-7-8j),    X_i, W_j balanced base-256 digits (int8)
+//     x.w = 2^(Ex+Ew-14) sum_d 2^(-8d) S_d,     S_d = sum_{i+j=d} X_i.W_j   (int32, error free),  d < NS
+// (NS = 6: 47 fraction bits per operand; the dropped orders d >= NS are below 2^-48 of the row * column scale)
 // One CTA owns a [128 rows x NT columns] output tile and keeps ALL NS order accumulators S_d of the tile in
 // tensor memory (NS*NT <= 512 columns of 128 lanes x 32 bit); the NS(NS+1)/2 slice products of one K-chunk are
 // tcgen05.mma instructions issued by one thread against the same staged operand tiles, so the operands are
@@ -30,6 +31,7 @@
 
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <mutex>
 
 #include "common.cuh"
@@ -53,7 +55,7 @@ struct GemmParams {
   long long m_blocks; // row blocks of 128
   const int* row_exp; // per-row exponent of the A operand, or null -> row_exp_fixed
   int row_exp_fixed;
-  const double* colv;       // [N][4] per output column: {2^(col_exp - 12), add, mul, 0}
+  const double* colv;       // [N][4] per output column: {2^(col_exp - 14), add, mul, 0}
                             //   FWD: add = bias, mul = idt (1 without resnet_dt)
                             //   BWD: add = head weight (0 unless the layer above is the head), mul = idt of the layer below
   const double* skip;       // blocked [n][N] or null (FWD: y_prev; BWD: g of the layer above)
@@ -114,10 +116,34 @@ __device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map
       "l"(map), "r"(c0), "r"(c1), "r"(c2), "r"(bar)
       : "memory");
 }
+// multicast variant: the box lands at the same CTA-relative offset of every CTA in `mask` and signals the barrier
+// at the same offset there
+__device__ __forceinline__ void tma_load_3d_mc(uint32_t dst, const CUtensorMap* map, int c0, int c1, int c2,
+                                               uint32_t bar, uint16_t mask) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%2, "
+      "%3, %4}], [%5], %6;" ::"r"(dst),
+      "l"(map), "r"(c0), "r"(c1), "r"(c2), "r"(bar), "h"(mask)
+      : "memory");
+}
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+// arrive on the barrier at the same offset in every CTA of `mask` once the MMAs issued so far have completed
+__device__ __forceinline__ void tc_commit_mc(uint32_t bar, uint16_t mask) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar),
+               "h"(mask)
+               : "memory");
 }
 // D[tmem] (+)= A[smem] . B[smem]^T, int8 x int8 -> int32
 __device__ __forceinline__ void mma_i8(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
@@ -175,28 +201,34 @@ __host__ __device__ constexpr uint32_t idesc_i8(int M, int N) {
 
 __device__ __forceinline__ double pow2i(int e) { return __hiloint2double((1023 + e) << 20, 0); }
 
-// NS slices of 16 fp64 values (fixed-point image q = round(v * 2^(P - E)) + bias) -> one 16-byte store per slice
+// NS slices of 16 fp64 values -> one 16-byte store per slice.  Fixed-point image u = round(v * up) + bias with
+// bias = sum_k 128 * 256^k: byte k of u is digit_k + 128, so the signed digit is that byte with its top bit flipped.
+// Slice s (most significant first) holds byte NS-1-s of the 16 values.
 template <int NS>
 __device__ __forceinline__ void store_slices16(signed char* __restrict__ base, long long slice_stride,
                                                const double (&v)[16], double up) {
-  long long bias = 0;
+  static_assert(NS <= 8, "the fixed-point image must fit in 64 bits");
+  unsigned long long bias = 0;
 #pragma unroll
-  for (int k = 0; k < NS; ++k) bias = bias * 128 + 64;
-  unsigned long long q[16];
+  for (int k = 0; k < NS; ++k) bias = bias * 256ull + 128ull;
+  unsigned lo[16], hi[16];
 #pragma unroll
-  for (int j = 0; j < 16; ++j) q[j] = (unsigned long long)(__double2ll_rn(v[j] * up) + bias);
+  for (int j = 0; j < 16; ++j) {
+    const unsigned long long u = (unsigned long long)__double2ll_rn(v[j] * up) + bias;
+    lo[j] = (unsigned)u;
+    hi[j] = (unsigned)(u >> 32);
+  }
 #pragma unroll
   for (int s = 0; s < NS; ++s) {
-    const int sh = 7 * (NS - 1 - s);
+    const int kb = NS - 1 - s;  // byte of the image
     unsigned w[4];
 #pragma unroll
     for (int g = 0; g < 4; ++g) {
-      const unsigned d0 = (unsigned)(q[4 * g + 0] >> sh) & 127u;
-      const unsigned d1 = (unsigned)(q[4 * g + 1] >> sh) & 127u;
-      const unsigned d2 = (unsigned)(q[4 * g + 2] >> sh) & 127u;
-      const unsigned d3 = (unsigned)(q[4 * g + 3] >> sh) & 127u;
-      const unsigned pk = d0 | (d1 << 8) | (d2 << 16) | (d3 << 24);
-      w[g] = ((pk | 0x80808080u) - 0x40404040u) ^ 0x80808080u;  // per byte: digit' - 64
+      const unsigned sel = (unsigned)(kb & 3) | ((unsigned)(4 + (kb & 3)) << 4);
+      const unsigned t0 = kb < 4 ? __byte_perm(lo[4 * g], lo[4 * g + 1], sel) : __byte_perm(hi[4 * g], hi[4 * g + 1], sel);
+      const unsigned t1 =
+          kb < 4 ? __byte_perm(lo[4 * g + 2], lo[4 * g + 3], sel) : __byte_perm(hi[4 * g + 2], hi[4 * g + 3], sel);
+      w[g] = __byte_perm(t0, t1, 0x5410) ^ 0x80808080u;
     }
     *reinterpret_cast<uint4*>(base + s * slice_stride) = make_uint4(w[0], w[1], w[2], w[3]);
   }
@@ -263,12 +295,20 @@ __device__ __forceinline__ double4 ldg_256(const double* p) {
   return v;
 }
 
-template <int NS, int NT, int EPI>
+// CN = CTAs per cluster.  The CN CTAs of a cluster work on CN neighbouring column tiles of the same row block in
+// lockstep and share the A operand: every CTA fetches 1/CN of each A stage and TMA multicasts it into the shared
+// memory of all of them (CN = 3: one slice each; CN = 4: 32 rows of every slice each).  The kernel is bound by
+// the L2 -> SM path (A 48 KB + B 30 KB per K-chunk against ~1700 cycles of MMA): multicast removes (CN-1)/CN of
+// the A traffic.
+template <int NS, int NT, int EPI, int CN>
 __global__ void __launch_bounds__(kThreads, 1)
     k_fit_gemm(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                const __grid_constant__ GemmParams p) {
   using L = SmemLayout<NS, NT>;
   constexpr int NH = L::NH;
+  static_assert(CN == 1 || CN == NH || CN == 4, "A is shared by slice (CN = NS/2) or by 32-row quarters (CN = 4)");
+  constexpr uint16_t kMaskAll = (uint16_t)((1u << CN) - 1u);
+  const uint32_t crank = CN > 1 ? cluster_ctarank() : 0u;
   static_assert(NS % 2 == 0 && NS * NT <= 512 && NT % 16 == 0 && NH * NT <= 256,
                 "accumulators must fit in tensor memory, one MMA spans up to NS/2 slices of B");
   static_assert(NT / 16 * 4 == kEpiWarps, "one epilogue warp per (lane quadrant, 16-column group)");
@@ -286,7 +326,7 @@ __global__ void __launch_bounds__(kThreads, 1)
   if (threadIdx.x == 0) {
     for (int s = 0; s < kStages; ++s) {
       mbar_init(bar_full + 8 * s, 1);
-      mbar_init(bar_empty + 8 * s, 1);
+      mbar_init(bar_empty + 8 * s, CN);  // released by the MMA warps of all CTAs that receive the multicast
     }
     mbar_init(bar_tfull, 1);
     mbar_init(bar_tempty, 32 * kEpiWarps);
@@ -301,11 +341,17 @@ __global__ void __launch_bounds__(kThreads, 1)
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
   tc_fence_before();
-  __syncthreads();
+  if (CN > 1)
+    cluster_sync_all();  // peers' barriers are initialised before any multicast or remote arrive can reach them
+  else
+    __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  const long long total = p.m_blocks * p.n_tiles;
+  // work units of a cluster: (row block, group of CN column tiles); CTA `crank` takes column tile group*CN + crank
+  const int groups = p.n_tiles / CN;
+  const long long total = p.m_blocks * groups;
+  const long long unit0 = blockIdx.x / CN, unit_step = gridDim.x / CN;
   const int nk = p.nk;
 
   if (warp == 0) {
@@ -316,9 +362,9 @@ __global__ void __launch_bounds__(kThreads, 1)
       uint32_t it = 0;
       long long w_empty = 0;
       const long long t_begin = clock64();
-      for (long long tile = blockIdx.x; tile < total; tile += gridDim.x) {
-        const int mb = (int)(tile / p.n_tiles);
-        const int nb = (int)(tile - (long long)mb * p.n_tiles);
+      for (long long tile = unit0; tile < total; tile += unit_step) {
+        const int mb = (int)(tile / groups);
+        const int nb = (int)(tile - (long long)mb * groups) * CN + (int)crank;
         for (int kc = 0; kc < nk; ++kc) {
 #pragma unroll
           for (int h = 0; h < 2; ++h, ++it) {
@@ -329,7 +375,16 @@ __global__ void __launch_bounds__(kThreads, 1)
             const uint32_t fb = bar_full + 8 * stage;
             mbar_expect_tx(fb, (uint32_t)L::kStageBytes);
             const uint32_t sa = smem0 + stage * L::kStageBytes;
-            tma_load_3d(sa, &tmA, kc * kChunkK, mb * kTileM, h * NH, fb);
+            if (CN == 1) {
+              tma_load_3d(sa, &tmA, kc * kChunkK, mb * kTileM, h * NH, fb);
+            } else if (CN == NH) {  // my slice of the half chunk, to everybody
+              tma_load_3d_mc(sa + crank * L::kABytes, &tmA, kc * kChunkK, mb * kTileM, h * NH + (int)crank, fb, kMaskAll);
+            } else {  // my 32 rows of every slice, to everybody
+#pragma unroll
+              for (int sl = 0; sl < NH; ++sl)
+                tma_load_3d_mc(sa + sl * L::kABytes + crank * (kTileM / 4) * kChunkK, &tmA, kc * kChunkK,
+                               mb * kTileM + (int)crank * (kTileM / 4), h * NH + sl, fb, kMaskAll);
+            }
             tma_load_3d(sa + L::kAHalf, &tmB, kc * kChunkK, nb * NT, h * NH, fb);
           }
         }
@@ -351,7 +406,7 @@ __global__ void __launch_bounds__(kThreads, 1)
     uint32_t it = 0, acc_phase = 0;
     long long w_tempty = 0, w_full = 0;
     const long long t_begin = clock64();
-    for (long long tile = blockIdx.x; tile < total; tile += gridDim.x) {
+    for (long long tile = unit0; tile < total; tile += unit_step) {
       long long c0 = p.dbg ? clock64() : 0;
       mbar_wait(bar_tempty, acc_phase ^ 1);
       if (p.dbg) w_tempty += clock64() - c0;
@@ -403,8 +458,13 @@ __global__ void __launch_bounds__(kThreads, 1)
               mma_i8(tmem_base + i * NT, desc_at(lo0, o1 + (i - NH) * L::kABytes + k * 32),
                      desc_at(lo0, o0 + L::kAHalf + k * 32), idesc_i8(kTileM, (NS - i) * NT), 1u);
           }
-          tc_commit(bar_empty + 8 * s0);
-          tc_commit(bar_empty + 8 * s1);
+          if (CN == 1) {
+            tc_commit(bar_empty + 8 * s0);
+            tc_commit(bar_empty + 8 * s1);
+          } else {
+            tc_commit_mc(bar_empty + 8 * s0, kMaskAll);
+            tc_commit_mc(bar_empty + 8 * s1, kMaskAll);
+          }
           if (kc == nk - 1) tc_commit(bar_tfull);
         }
         __syncwarp();
@@ -427,9 +487,9 @@ __global__ void __launch_bounds__(kThreads, 1)
     uint32_t acc_phase = 0;
     long long w_tfull = 0, t_drain = 0, t_math = 0;
     const long long t_begin = clock64();
-    for (long long tile = blockIdx.x; tile < total; tile += gridDim.x) {
-      const int mb = (int)(tile / p.n_tiles);
-      const int nb = (int)(tile - (long long)mb * p.n_tiles);
+    for (long long tile = unit0; tile < total; tile += unit_step) {
+      const int mb = (int)(tile / groups);
+      const int nb = (int)(tile - (long long)mb * groups) * CN + (int)crank;
       const long long r = (long long)mb * kTileM + row_in_tile;
       const bool row_ok = r < p.n;
       const int c0 = nb * NT + cc;
@@ -462,7 +522,7 @@ __global__ void __launch_bounds__(kThreads, 1)
           tmem_ld16(lane_addr + (uint32_t)(d * NT), a);
           tmem_ld_wait();
 #pragma unroll
-          for (int j = 0; j < 16; ++j) v[j] = fma(v[j], 0.0078125, i2d(a[j]));
+          for (int j = 0; j < 16; ++j) v[j] = fma(v[j], 0.00390625, i2d(a[j]));
         }
       }
       // the accumulators are in registers: the next tile's products may overwrite tensor memory now
@@ -496,7 +556,7 @@ __global__ void __launch_bounds__(kThreads, 1)
           }
         }
         if (row_ok && p.slices_out) {
-          const double up = pow2i(6 + 7 * (NS - 1) - p.out_exp);
+          const double up = pow2i(7 + 8 * (NS - 1) - p.out_exp);
           store_slices16<NS>(p.slices_out + r * p.ld_slices + c0, p.Kp_out, v, up);
         }
       } else if (EPI == EPI_BWD) {
@@ -549,7 +609,10 @@ __global__ void __launch_bounds__(kThreads, 1)
   }
 
   tc_fence_before();
-  __syncthreads();
+  if (CN > 1)
+    cluster_sync_all();  // no CTA leaves while a peer may still multicast into it or arrive on its barriers
+  else
+    __syncthreads();
   if (warp == 1) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
   }
@@ -585,7 +648,7 @@ __global__ void __launch_bounds__(128) k_fit_slice(signed char* __restrict__ out
   int E = ((__double2hiint(m) >> 20) & 0x7ff) - 1023 + 2;
   E = E < -900 ? -900 : (E > 900 ? 900 : E);
   row_exp[r] = E;
-  const double up = pow2i(6 + 7 * (NS - 1) - E);
+  const double up = pow2i(7 + 8 * (NS - 1) - E);
   signed char* __restrict__ o = out + r * ld_out;
   for (int c0 = 0; c0 < Kp; c0 += 16) {
     double v[16];
@@ -661,20 +724,56 @@ int make_map(CUtensorMap* map, const void* base, unsigned long long d0, unsigned
   return DPB200_OK;
 }
 
-template <int NS, int NT, int EPI>
+template <int NS, int NT, int EPI, int CN>
 int launch_gemm(const CUtensorMap& ma, const CUtensorMap& mb, const GemmParams& p, cudaStream_t st) {
   using L = SmemLayout<NS, NT>;
-  static bool attr_done = false;
-  if (!attr_done) {
-    DPB_CUDA(cudaFuncSetAttribute(k_fit_gemm<NS, NT, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kTotal));
-    attr_done = true;
+  auto kern = k_fit_gemm<NS, NT, EPI, CN>;
+  static int max_clusters = 0;  // clusters of CN CTAs that can be resident at once (one CTA per SM)
+  if (max_clusters == 0) {
+    DPB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kTotal));
+    if (CN > 1) {
+      cudaLaunchConfig_t q = {};
+      q.gridDim = dim3((unsigned)(sm_count() / CN * CN));
+      q.blockDim = dim3(kThreads);
+      q.dynamicSmemBytes = L::kTotal;
+      cudaLaunchAttribute at[1];
+      at[0].id = cudaLaunchAttributeClusterDimension;
+      at[0].val.clusterDim.x = CN;
+      at[0].val.clusterDim.y = 1;
+      at[0].val.clusterDim.z = 1;
+      q.attrs = at;
+      q.numAttrs = 1;
+      int n = 0;
+      DPB_CUDA(cudaOccupancyMaxActiveClusters(&n, kern, &q));
+      max_clusters = n > 0 ? n : 1;
+    } else {
+      max_clusters = sm_count();
+    }
   }
-  const long long total = p.m_blocks * p.n_tiles;
-  const int grid = (int)(total < sm_count() ? total : sm_count());
-  k_fit_gemm<NS, NT, EPI><<<grid, kThreads, L::kTotal, st>>>(ma, mb, p);
-  DPB_CUDA(cudaGetLastError());
+  const long long total = p.m_blocks * (p.n_tiles / CN);
+  const int clusters = (int)(total < max_clusters ? total : max_clusters);
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)(clusters * CN));
+  cfg.blockDim = dim3(kThreads);
+  cfg.dynamicSmemBytes = L::kTotal;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = CN;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = CN > 1 ? 1 : 0;
+  DPB_CUDA(cudaLaunchKernelEx(&cfg, kern, ma, mb, p));
   note_launches(1);
   return DPB200_OK;
+}
+
+template <int NS, int NT, int CN>
+int launch_mode(int mode, const CUtensorMap& ma, const CUtensorMap& mb, const GemmParams& p, cudaStream_t st) {
+  if (mode == EPI_FWD) return launch_gemm<NS, NT, EPI_FWD, CN>(ma, mb, p, st);
+  if (mode == EPI_BWD) return launch_gemm<NS, NT, EPI_BWD, CN>(ma, mb, p, st);
+  return launch_gemm<NS, NT, EPI_PLAIN, CN>(ma, mb, p, st);
 }
 
 }  // namespace
@@ -733,19 +832,31 @@ int dpb200_fit_gemm_i8_f64(int mode, long long nrow, int N, int K, int nslice, c
   p.dbg = g_fit_dbg;
   p.wide_store = (mode == EPI_PLAIN && ld_out % 4 == 0 && ((uintptr_t)out0 & 31) == 0) ? 1 : 0;
   CUtensorMap ma, mb;
-  // A: [nrow][nslice][K] bytes seen as {K, row, slice} (byte strides given); box {64, 128, NS/2} lands in shared
-  // memory as [slice][row][64]; rows / K beyond the tensor are zero-filled by TMA
+  // Cluster width: the CTAs of a cluster share A by TMA multicast (csrc kernel comment).  DPB200_FIT_CLUSTER=1
+  // switches the sharing off (comparison runs).
+  static const int cluster_env = [] {
+    const char* e = getenv("DPB200_FIT_CLUSTER");
+    return e ? atoi(e) : 0;
+  }();
+  int cn = 1;
+  if (p.n_tiles % 4 == 0 && nrow >= 4 * kTileM) cn = 4;
+  else if (p.n_tiles % 3 == 0 && nrow >= 3 * kTileM) cn = 3;
+  if (cluster_env == 1 || (cluster_env > 1 && p.n_tiles % cluster_env != 0)) cn = 1;
+  else if (cluster_env == 3 || cluster_env == 4) cn = cluster_env;
+  // A: [nrow][nslice][K] bytes seen as {K, row, slice} (byte strides given); the box lands in shared memory as
+  // [slice][row][64]; rows / K beyond the tensor are zero-filled by TMA
+  const unsigned a_rows = cn == 4 ? kTileM / 4 : kTileM, a_slices_box = cn == 1 ? NS / 2 : 1;
   int rc = make_map(&ma, a_slices, (unsigned long long)K, (unsigned long long)nrow, (unsigned long long)nslice,
-                    (unsigned long long)a_row_stride, (unsigned long long)a_slice_stride, kTileM, NS / 2);
+                    (unsigned long long)a_row_stride, (unsigned long long)a_slice_stride, a_rows, a_slices_box);
   if (rc != DPB200_OK) return rc;
   // B: [nslice][N][b_k_stride] bytes (weights transposed: row = output column, K contiguous, zero padded)
   rc = make_map(&mb, b_slices, (unsigned long long)b_k_stride, (unsigned long long)N, (unsigned long long)nslice,
                 (unsigned long long)b_k_stride, (unsigned long long)b_k_stride * N, NT, NS / 2);
   if (rc != DPB200_OK) return rc;
   cudaStream_t st = (cudaStream_t)stream;
-  if (mode == EPI_FWD) return launch_gemm<NS, NT, EPI_FWD>(ma, mb, p, st);
-  if (mode == EPI_BWD) return launch_gemm<NS, NT, EPI_BWD>(ma, mb, p, st);
-  return launch_gemm<NS, NT, EPI_PLAIN>(ma, mb, p, st);
+  if (cn == 4) return launch_mode<NS, NT, 4>(mode, ma, mb, p, st);
+  if (cn == 3) return launch_mode<NS, NT, 3>(mode, ma, mb, p, st);
+  return launch_mode<NS, NT, 1>(mode, ma, mb, p, st);
 }
 
 int dpb200_fit_slice_rows_f64(signed char* out, long long ld_out, int kp, int* row_exp, const double* x,

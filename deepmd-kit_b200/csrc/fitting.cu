@@ -7,12 +7,12 @@
 // gpurun_out/gemm_probe.log), so the products are made exact (or exact to 2^-22) by splitting
 // the operands:
 //
-//   fp64  x = 2^Ex * sum_i X_i 2^(-6-7i),  X_i signed 7-bit digits (int8)   [rows: per-row Ex]
-//         w = 2^Ew * sum_j W_j 2^(-6-7j)                                      [cols: per-col Ew]
-//         x.w = 2^(Ex+Ew-12) * sum_d 2^(-7d) * sum_{i+j=d} X_i.W_j            (d < nslice)
+//   fp64  x = 2^Ex * sum_i X_i 2^(-7-8i),  X_i balanced base-256 digits (int8, -128..127)   [rows: per-row Ex]
+//         w = 2^Ew * sum_j W_j 2^(-7-8j)                                                     [cols: per-col Ew]
+//         x.w = 2^(Ex+Ew-14) * sum_d 2^(-8d) * sum_{i+j=d} X_i.W_j            (d < nslice)
 //         Every X_i.W_j is an error-free int8 GEMM with int32 accumulation; the products of one order
 //         d are ONE GEMM over the concatenated K axis [X_0|..|X_d] . [W_d;..;W_0].  The order sums
-//         are recombined here in fp64 (Horner in 2^-7), with bias / tanh / resnet_dt fused in.
+//         are recombined here in fp64 (Horner in 2^-8), with bias / tanh / resnet_dt fused in.
 //   fp32  x = hi + lo with hi, lo representable in TF32:  x.w ~= hi.whi + lo.whi + hi.wlo
 //         (3xTF32, relative error 2^-22), again one GEMM over a concatenated K axis.
 //
@@ -26,7 +26,7 @@
 namespace dpb200 {
 namespace {
 
-// z = 2^(row_exp[r] + col_exp[c] - 12) * sum_d acc[d][r][c] 2^(-7d) + bias[c];
+// z = 2^(row_exp[r] + col_exp[c] - 14) * sum_d acc[d][r][c] 2^(-8d) + bias[c];
 // a = tanh(z) (kept for the backward), y = a * idt (+ h).
 __global__ void k_split_i8_combine(double* __restrict__ a_out, double* __restrict__ y_out,
                                    const int* __restrict__ acc, long long acc_stride, int ns,
@@ -37,8 +37,8 @@ __global__ void k_split_i8_combine(double* __restrict__ a_out, double* __restric
     const long long r = e / width;
     const int c = (int)(e - r * width);
     double s = (double)acc[(long long)(ns - 1) * acc_stride + e];
-    for (int d = ns - 2; d >= 0; --d) s = s * 0.0078125 + (double)acc[(long long)d * acc_stride + e];
-    const int ex = row_exp[r] + col_exp[c] - 12;
+    for (int d = ns - 2; d >= 0; --d) s = s * 0.00390625 + (double)acc[(long long)d * acc_stride + e];
+    const int ex = row_exp[r] + col_exp[c] - 14;
     double z = ldexp(s, ex);
     if (bias) z += bias[c];
     if (act) {
@@ -53,16 +53,16 @@ __global__ void k_split_i8_combine(double* __restrict__ a_out, double* __restric
   }
 }
 
-// Split an fp64 matrix [n][width] row-wise into `ns` signed 7-bit slices, most significant first:
+// Split an fp64 matrix [n][width] row-wise into `ns` balanced base-256 digit slices, most significant first:
 // out[r][s][c] int8 (row stride ld_out bytes), row_exp[r].  One warp per row.
 __global__ void k_split_i8_rows(signed char* __restrict__ out, long long ld_out, int* __restrict__ row_exp,
                                 const double* __restrict__ x, long long ldx, long long n, int width, int ns) {
   const int lane = threadIdx.x & 31;
   const long long wid = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
   const long long nw = ((long long)gridDim.x * blockDim.x) >> 5;
-  long long bias = 0;
-  for (int k = 0; k < ns; ++k) bias = bias * 128 + 64;
-  const int P = 6 + 7 * (ns - 1);
+  unsigned long long bias = 0;
+  for (int k = 0; k < ns; ++k) bias = bias * 256ull + 128ull;
+  const int P = 7 + 8 * (ns - 1);
   for (long long r = wid; r < n; r += nw) {
     const double* __restrict__ xr = x + r * ldx;
     double m = 0.;
@@ -75,9 +75,9 @@ __global__ void k_split_i8_rows(signed char* __restrict__ out, long long ld_out,
     const double up = __hiloint2double((1023 + P - E) << 20, 0);
     signed char* __restrict__ o = out + r * ld_out;
     for (int c = lane; c < width; c += 32) {
-      const unsigned long long q = (unsigned long long)(__double2ll_rn(xr[c] * up) + bias);
+      const unsigned long long q = (unsigned long long)__double2ll_rn(xr[c] * up) + bias;
       for (int s = 0; s < ns; ++s)
-        o[(long long)s * width + c] = (signed char)((int)((q >> (7 * (ns - 1 - s))) & 127ull) - 64);
+        o[(long long)s * width + c] = (signed char)((int)((q >> (8 * (ns - 1 - s))) & 255ull) - 128);
     }
   }
 }

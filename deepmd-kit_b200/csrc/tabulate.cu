@@ -460,7 +460,7 @@ __device__ __forceinline__ void poly_both(const FP (&a)[6], FP x, FP& g, FP& gd)
 // through HBM as a separate pass.  It is emitted directly in the operand format of the fitting
 // net's first GEMM:
 //   mode 1  D as FP [row][M*axis]
-//   mode 2  fp64: `nslice` signed 7-bit slices of the row's fixed-point image, most significant
+//   mode 2  fp64: `nslice` balanced base-256 digit slices of the row's fixed-point image, most significant
 //           first, int8 [row][nslice][M*axis] + row_exp[row] (split-integer GEMM on the int8
 //           tensor cores, error-free products, fp64-grade sums);
 //           fp32: TF32 head and tail, float [row][2][M*axis] (3xTF32 GEMM).
@@ -521,11 +521,11 @@ __device__ __forceinline__ void desc_store_split(const TabParams<double>& p, con
   int E = e + 2;  // |D| < 2^(E-1)
   E = E < -900 ? -900 : (E > 900 ? 900 : E);
   if (lane == 0) p.row_exp[row] = E;
-  const int P = 6 + 7 * (ns - 1);  // fixed-point fraction bits
+  const int P = 7 + 8 * (ns - 1);  // fixed-point fraction bits
   const double up = s2 * __hiloint2double((1023 + P - E) << 20, 0);
-  // bias that makes every base-128 digit non-negative: digit' = digit + 64
-  long long bias = 0;
-  for (int k = 0; k < ns; ++k) bias = bias * 128 + 64;
+  // bias that makes every base-256 digit non-negative: byte k of the image = digit_k + 128
+  unsigned long long bias = 0;
+  for (int k = 0; k < ns; ++k) bias = bias * 256ull + 128ull;
   signed char* __restrict__ base = reinterpret_cast<signed char*>(p.desc) + row * p.desc_ld;
   const long long K = (long long)M * 16;
 #pragma unroll
@@ -534,7 +534,7 @@ __device__ __forceinline__ void desc_store_split(const TabParams<double>& p, con
     if (k1 < M) {
 #pragma unroll 1
       for (int half = 0; half < 2; ++half) {
-        unsigned long long q[8];
+        unsigned lo[8], hi[8];
 #pragma unroll
         for (int t = 0; t < 8; t += 2) {
           double v0 = 0., v1 = 0.;
@@ -543,20 +543,21 @@ __device__ __forceinline__ void desc_store_split(const TabParams<double>& p, con
             const double2 b = *reinterpret_cast<const double2*>(stage + m * 16 + half * 8 + t);
             v0 += A[m][c] * b.x, v1 += A[m][c] * b.y;
           }
-          q[t] = (unsigned long long)(__double2ll_rn(v0 * up) + bias);
-          q[t + 1] = (unsigned long long)(__double2ll_rn(v1 * up) + bias);
+          const unsigned long long u0 = (unsigned long long)__double2ll_rn(v0 * up) + bias;
+          const unsigned long long u1 = (unsigned long long)__double2ll_rn(v1 * up) + bias;
+          lo[t] = (unsigned)u0, hi[t] = (unsigned)(u0 >> 32);
+          lo[t + 1] = (unsigned)u1, hi[t + 1] = (unsigned)(u1 >> 32);
         }
-        for (int s = 0; s < ns; ++s) {  // slice s = digit ns-1-s
-          const int sh = 7 * (ns - 1 - s);
+        for (int s = 0; s < ns; ++s) {  // slice s = byte ns-1-s of the image, top bit flipped = signed digit
+          const int kb = ns - 1 - s;
+          const unsigned sel = (unsigned)(kb & 3) | ((unsigned)(4 + (kb & 3)) << 4);
           unsigned w[2];
 #pragma unroll
           for (int g = 0; g < 2; ++g) {
-            const unsigned d0 = (unsigned)(q[4 * g + 0] >> sh) & 127u;
-            const unsigned d1 = (unsigned)(q[4 * g + 1] >> sh) & 127u;
-            const unsigned d2 = (unsigned)(q[4 * g + 2] >> sh) & 127u;
-            const unsigned d3 = (unsigned)(q[4 * g + 3] >> sh) & 127u;
-            const unsigned pk = d0 | (d1 << 8) | (d2 << 16) | (d3 << 24);
-            w[g] = ((pk | 0x80808080u) - 0x40404040u) ^ 0x80808080u;  // per-byte digit' - 64
+            const unsigned t0 = kb < 4 ? __byte_perm(lo[4 * g], lo[4 * g + 1], sel) : __byte_perm(hi[4 * g], hi[4 * g + 1], sel);
+            const unsigned t1 = kb < 4 ? __byte_perm(lo[4 * g + 2], lo[4 * g + 3], sel)
+                                       : __byte_perm(hi[4 * g + 2], hi[4 * g + 3], sel);
+            w[g] = __byte_perm(t0, t1, 0x5410) ^ 0x80808080u;
           }
           *reinterpret_cast<uint2*>(base + s * K + (long long)k1 * 16 + half * 8) = make_uint2(w[0], w[1]);
         }

@@ -65,20 +65,20 @@ COPPER_CONFIG = dict(ntypes=1, sel=(512,), rcut=8.0, rcut_smth=2.0, stats=[(0.06
 
 
 def split_i8_cols(w: torch.Tensor, nslice: int):
-    """Host-side split of an fp64 weight matrix [K, N] into signed 7-bit slices per COLUMN scale:
-    w[:, c] = 2^col_exp[c] * sum_j slice_j[:, c] 2^(-6-7j).  Returns (slices int8 [nslice, K, N], most
-    significant first; col_exp int32 [N]).  Same digit convention as csrc/fitting.cu / tabulate.cu."""
+    """Host-side split of an fp64 weight matrix [K, N] into balanced base-256 digit slices per COLUMN scale:
+    w[:, c] = 2^col_exp[c] * sum_j slice_j[:, c] 2^(-7-8j).  Returns (slices int8 [nslice, K, N], most
+    significant first; col_exp int32 [N]).  Same digit convention as csrc/fitting.cu / fit_tc.cu / tabulate.cu."""
     w = w.detach().to("cpu", torch.float64)
     m = w.abs().amax(0)
     _, ex = torch.frexp(torch.where(m > 0, m, torch.ones_like(m)))  # m = mant * 2^ex, mant in [0.5, 1)
     E = (ex + 1).to(torch.int32)  # |w| * 2^-E < 0.5
-    P = 6 + 7 * (nslice - 1)
+    P = 7 + 8 * (nslice - 1)
     q = torch.round(torch.ldexp(w, (P - E).to(torch.int32).unsqueeze(0).expand_as(w))).to(torch.int64)
-    bias = 0
-    for _ in range(nslice):
-        bias = bias * 128 + 64
-    q = q + bias
-    digits = [(((q >> (7 * k)) & 127) - 64).to(torch.int8) for k in range(nslice)]  # k = 0 least significant
+    digits = []
+    for _ in range(nslice):  # least significant first: d = ((q + 128) mod 256) - 128 in [-128, 127]
+        d = ((q + 128) & 255) - 128
+        digits.append(d.to(torch.int8))
+        q = (q - d) >> 8
     return torch.stack(digits[::-1]), E
 
 
@@ -151,7 +151,7 @@ class FittingNet:
         return self
 
     def prepare_tc(self, nslice: int = 6):
-        """Weights of all GEMMs of the net (forward and backward) as signed 7-bit int8 slices in the B-operand
+        """Weights of all GEMMs of the net (forward and backward) as balanced base-256 int8 digit slices in the B-operand
         layout of dpb200_fit_gemm_i8 ([nslice][N][K padded to 64], K contiguous) + column scales 2^(col_exp-12),
         and the fixed exponents of the hidden activations (|y_l| < sum_k<=l max|idt_k|).  Returns False when the
         architecture is outside what csrc/fit_tc.cu covers (fp64, first layer without skip connection, equal-width
@@ -173,7 +173,7 @@ class FittingNet:
             b = torch.zeros((nslice, N, Kp), dtype=torch.int8)
             b[:, :, :K] = sl.permute(0, 2, 1)
             colv = torch.zeros((N, 4), dtype=torch.float64)
-            colv[:, 0] = torch.ldexp(torch.ones(N, dtype=torch.float64), ce - 12)
+            colv[:, 0] = torch.ldexp(torch.ones(N, dtype=torch.float64), ce - 14)
             if add is not None:
                 colv[:, 1] = add.detach().to("cpu", torch.float64)
             colv[:, 2] = 1.0 if mul is None else mul.detach().to("cpu", torch.float64)
@@ -403,7 +403,7 @@ class SeAModel:
         # Tensor-core fitting net (csrc/fitting.cu): the descriptor leaves the tabulate forward already split
         # (int8 slices in fp64, TF32 head/tail in fp32).  Needs axis == 16 (fp64) / axis % 4 == 0 (fp32),
         # M <= 128 and a first fitting layer without skip connection.
-        self.nslice = 6  # 6 + 5*7 = 41 fraction bits per operand: GEMM error ~1e-12 of the row*column scale
+        self.nslice = 6  # 7 + 5*8 = 47 fraction bits per operand: GEMM error ~1e-14 of the row*column scale
         w0 = self.fit[0].layers[0][0]
         ok_axis = cfg.axis_neuron == 16 if dtype == torch.float64 else cfg.axis_neuron % 4 == 0
         self.use_split = bool(ok_axis and self.M <= 128 and cfg.axis_neuron <= 32 and w0.shape[1] not in

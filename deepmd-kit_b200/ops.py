@@ -618,7 +618,7 @@ def tabulate_sections_desc(tables, infos, em, sec, last_layer_size, axis, scale,
     """tabulate_sections_fwd with the se_e2_a descriptor contraction fused into the last section's
     epilogue (dpb200_tabulate_fusion_se_a_desc).  Returns (out [nloc,4,M], desc, row_exp|None):
       mode 1            desc = D [nloc+pad, M*axis] in em.dtype;
-      mode 2, float64   desc = int8 [nloc+pad, nslice*M*axis] signed 7-bit slices, row_exp int32 [nloc+pad];
+      mode 2, float64   desc = int8 [nloc+pad, nslice*M*axis] balanced base-256 digit slices, row_exp int32 [nloc+pad];
       mode 2, float32   desc = float32 [nloc+pad, 2*M*axis] = TF32 head | tail.
     Row desc_row[i] (int32; None: i) belongs to atom i; `pad_rows` extra zero rows are appended.
     flags: per-table DPB200_TAB_COMPRESSED_COEF words from `compressed_coef_flags` (None: full fp64 coefficients)."""
@@ -668,8 +668,8 @@ def tabulate_sections_desc(tables, infos, em, sec, last_layer_size, axis, scale,
 
 
 def split_i8_rows(x, nslice):
-    """fp64 [n, w] -> (int8 [n, nslice*w] signed 7-bit slices, most significant first; row_exp int32 [n]):
-    x = 2^row_exp * sum_s slice_s * 2^(-6-7s)  (truncated after nslice digits)."""
+    """fp64 [n, w] -> (int8 [n, nslice*w] balanced base-256 digit slices, most significant first; row_exp int32 [n]):
+    x = 2^row_exp * sum_s slice_s * 2^(-7-8s)  (truncated after nslice digits)."""
     dev = _need_cuda(("x", x))
     if x.dtype != torch.float64 or x.dim() != 2 or x.stride(1) != 1:
         raise ValueError("dpb200: split_i8_rows needs a float64 matrix with unit column stride")

@@ -136,7 +136,7 @@ DPB200_DECL_ENV(f32, float)
    * `desc` (row stride desc_ld elements), in the operand format of the fitting net's first GEMM:  \
    *   desc_mode 0: no descriptor (plain `_ex` forward, but honouring `flags`);                     \
    *   desc_mode 1: FP [M*axis];                                                                    \
-   *   desc_mode 2, f64: int8 [nslice][M*axis] signed 7-bit slices (most significant first) of     \
+   *   desc_mode 2, f64: int8 [nslice][M*axis] balanced base-256 digit slices (most significant first) of     \
    *     D * 2^-row_exp[row] (needs axis == 16);  f32: float [2][M*axis] = TF32 head | tail.        \
    * M <= 128, axis <= 32, desc 16-byte aligned.                                                   \
    * flags: DPB200_TAB_COMPRESSED_COEF (f64 only, ignored for f32) = the caller has checked that    \
@@ -301,8 +301,8 @@ DPB200_DECL_DESC(f32, float)
  * Split operands for the fitting net's GEMMs on the tensor cores (csrc/fitting.cu): the GEMMs are
  * library calls; these kernels make them fp64 / fp32 accurate.
  *  split_i8_rows   : x [nrow][width] (row stride ldx) -> out int8 [nrow][nslice][width] (row stride
- *                    ld_out bytes), row_exp[nrow]:  x = 2^row_exp * sum_s out[s] 2^(-6-7s)
- *  split_i8_combine: z = 2^(row_exp[r]+col_exp[c]-12) * sum_d acc[d][r][c] 2^(-7d) + bias[c], acc[d] =
+ *                    ld_out bytes), row_exp[nrow]:  x = 2^row_exp * sum_s out[s] 2^(-7-8s)
+ *  split_i8_combine: z = 2^(row_exp[r]+col_exp[c]-14) * sum_d acc[d][r][c] 2^(-8d) + bias[c], acc[d] =
  *                    int32 [nrow][width] at acc + d*acc_stride = sum_{i+j=d} X_i.W_j;  activation != 0:
  *                    a_out = tanh(z), y_out = a*idt + h (mlp.py layer);  == 0: a_out = z.
  *  split_tf32      : x -> [hi | lo (| hi)] with hi = tf32(x), lo = tf32(x - hi), copies = 2 | 3.
@@ -324,7 +324,7 @@ int dpb200_split_tf32_f32(float* out, long long ld_out, const float* x, long lon
  *  fit_gemm_i8 : C[nrow][N] = A.B^T, A = int8 slices [nrow][nslice][K] (byte strides a_slice_stride /
  *                a_row_stride; per-row exponent row_exp[r] or row_exp_fixed when row_exp == NULL), B = int8
  *                slices [nslice][N][b_k_stride] (K contiguous, zero padded to a multiple of 64), N % 16 == 0.
- *                colv [N][4] (32-byte aligned) = per output column {2^(col_exp-12), add, mul, 0}.
+ *                colv [N][4] (32-byte aligned) = per output column {2^(col_exp-14), add, mul, 0}.
  *                fp64 matrices other than `out0` of mode 2 use the row-blocked layout: element (r, c) at
  *                ((r/128)*N + c)*128 + r%128, allocated for whole blocks of 128 rows.
  *                mode 0  t = tanh(C + add), y = t*mul (+ skip): out0 = t, out1 = y, slices_out (nullable) = y as

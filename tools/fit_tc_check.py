@@ -25,7 +25,7 @@ def pack(w, ns=6):
     b = torch.zeros((ns, N, Kp), dtype=torch.int8)
     b[:, :, :K] = sl.permute(0, 2, 1)
     colv = torch.zeros((N, 4), dtype=torch.float64)
-    colv[:, 0] = torch.ldexp(torch.ones(N, dtype=torch.float64), ce - 12)
+    colv[:, 0] = torch.ldexp(torch.ones(N, dtype=torch.float64), ce - 14)
     colv[:, 2] = 1.0
     return b.contiguous().to(dev), colv.to(dev), Kp
 
