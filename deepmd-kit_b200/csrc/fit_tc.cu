@@ -497,6 +497,14 @@ __global__ void __launch_bounds__(kThreads, 1)
       // blocked offset of (r, c0): ((mb * N + c) * 128 + row_in_tile)
       const long long boff = ((long long)mb * p.N + c0) * kTileM + row_in_tile;
       const double rs = pow2i(live && row_ok && p.row_exp ? __ldg(p.row_exp + r) : p.row_exp_fixed);
+      // the fp64 inputs of the elementwise chain are streamed from HBM: pull them into L2 while the MMAs run
+      if (live && EPI != EPI_PLAIN) {
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          if (p.skip) asm volatile("prefetch.global.L2 [%0];" ::"l"(p.skip + boff + (long long)j * kTileM));
+          if (EPI == EPI_BWD) asm volatile("prefetch.global.L2 [%0];" ::"l"(p.t_in + boff + (long long)j * kTileM));
+        }
+      }
       // per-column constants of this warp's 16 columns -> shared memory (read back as broadcasts in the math below;
       // a global load per element would put an L2 round trip on every element's critical path)
       __syncwarp();
@@ -623,50 +631,58 @@ __global__ void __launch_bounds__(kThreads, 1)
 // row.  HEAD: the matrix is t of the last hidden layer; the values sliced are dz = w_head * idt * (1 - t^2)
 // (the seed of the backward chain) and the atomic energy e = y . w_head + b_head is produced on the way.
 // ------------------------------------------------------------------------------------------------------
+// One block = 32 rows x (N / 16) warps: warp w owns columns [16 w, 16 w + 16), lane = row.  Every load instruction of
+// a warp reads 256 contiguous bytes of the blocked layout; the 16 values stay in registers while the row maximum is
+// reduced across the warps through shared memory, so the matrix is read exactly once.
 template <int NS, bool HEAD>
-__global__ void __launch_bounds__(128) k_fit_slice(signed char* __restrict__ out, long long ld_out, int Kp,
-                                                   int* __restrict__ row_exp, const double* __restrict__ x,
-                                                   const double* __restrict__ y, const double* __restrict__ w_head,
-                                                   const double* __restrict__ idt, double b_head,
-                                                   double* __restrict__ e_out, long long n, int N) {
-  const long long mb = blockIdx.x;
-  const long long r = mb * kTileM + threadIdx.x;
-  if (r >= n) return;
-  const double* __restrict__ xb = x + mb * (long long)N * kTileM + threadIdx.x;
-  double m = 0., e = b_head;
-  for (int c = 0; c < N; ++c) {
-    double v = xb[(long long)c * kTileM];
-    if (HEAD) {
-      const double w = __ldg(w_head + c);
-      e += y[mb * (long long)N * kTileM + (long long)c * kTileM + threadIdx.x] * w;
-      v = w * (1. - v * v);
-      if (idt) v *= __ldg(idt + c);
-    }
-    m = fmax(m, fabs(v));
+__global__ void __launch_bounds__(1024) k_fit_slice(signed char* __restrict__ out, long long ld_out, int Kp,
+                                                    int* __restrict__ row_exp, const double* __restrict__ x,
+                                                    const double* __restrict__ y, const double* __restrict__ w_head,
+                                                    const double* __restrict__ idt, double b_head,
+                                                    double* __restrict__ e_out, long long n, int N) {
+  __shared__ int s_exp[32];
+  __shared__ double s_e[32];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const long long r = (long long)blockIdx.x * 32 + lane;
+  const int c0 = warp * 16;
+  if (warp == 0) {
+    s_exp[lane] = -2000;
+    s_e[lane] = b_head;
   }
-  if (HEAD) e_out[r] = e;
-  int E = ((__double2hiint(m) >> 20) & 0x7ff) - 1023 + 2;
-  E = E < -900 ? -900 : (E > 900 ? 900 : E);
-  row_exp[r] = E;
-  const double up = pow2i(7 + 8 * (NS - 1) - E);
-  signed char* __restrict__ o = out + r * ld_out;
-  for (int c0 = 0; c0 < Kp; c0 += 16) {
-    double v[16];
+  __syncthreads();
+  // (r / 128) * N * 128 + c * 128 + r % 128
+  const long long boff = (r >> 7) * (long long)N * kTileM + (long long)c0 * kTileM + (r & (kTileM - 1));
+  double v[16];
+#pragma unroll
+  for (int j = 0; j < 16; ++j) v[j] = __ldcs(x + boff + (long long)j * kTileM);
+  if (HEAD) {
+    double yv[16];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) yv[j] = __ldcs(y + boff + (long long)j * kTileM);
+    double e = 0.;
 #pragma unroll
     for (int j = 0; j < 16; ++j) {
-      const int c = c0 + j;
-      double t = 0.;
-      if (c < N) {
-        t = xb[(long long)c * kTileM];
-        if (HEAD) {
-          t = __ldg(w_head + c) * (1. - t * t);
-          if (idt) t *= __ldg(idt + c);
-        }
-      }
-      v[j] = t;
+      const double w = __ldg(w_head + c0 + j);
+      e = fma(yv[j], w, e);
+      double d = w * fma(-v[j], v[j], 1.0);
+      if (idt) d *= __ldg(idt + c0 + j);
+      v[j] = d;
     }
-    store_slices16<NS>(o + c0, Kp, v, up);
+    atomicAdd(&s_e[lane], e);
   }
+  double m = 0.;
+#pragma unroll
+  for (int j = 0; j < 16; ++j) m = fmax(m, fabs(v[j]));
+  atomicMax(&s_exp[lane], ((__double2hiint(m) >> 20) & 0x7ff) - 1023 + 2);
+  __syncthreads();
+  if (r >= n) return;
+  int E = s_exp[lane];
+  E = E < -900 ? -900 : (E > 900 ? 900 : E);
+  if (warp == 0) {
+    row_exp[r] = E;
+    if (HEAD) e_out[r] = s_e[lane];
+  }
+  store_slices16<NS>(out + r * ld_out + c0, Kp, v, pow2i(7 + 8 * (NS - 1) - E));
 }
 
 // row-major [n][N] (leading dimension ld) <-> blocked layout (tests and the non-tensor-core callers)
@@ -863,11 +879,12 @@ int dpb200_fit_slice_rows_f64(signed char* out, long long ld_out, int kp, int* r
                               long long nrow, int N, int nslice, dpb200_stream_t stream) {
   using namespace dpb200;
   DPB_REQUIRE(nslice == 6, "fit_slice_rows: only 6 operand slices are built");
-  DPB_REQUIRE(nrow >= 0 && N >= 1 && kp % 16 == 0 && kp >= N && ld_out >= (long long)nslice * kp && ld_out % 16 == 0,
-              "fit_slice_rows: bad shape");
+  DPB_REQUIRE(nrow >= 0 && N >= 16 && N % 16 == 0 && N <= 512 && kp == N && ld_out >= (long long)nslice * kp &&
+                  ld_out % 16 == 0,
+              "fit_slice_rows: N must be a multiple of 16 up to 512 and kp == N");
   if (nrow == 0) return DPB200_OK;
   DPB_REQUIRE(out && row_exp && x && ((uintptr_t)out & 15) == 0, "fit_slice_rows: null or unaligned pointer");
-  k_fit_slice<6, false><<<(unsigned)((nrow + kTileM - 1) / kTileM), kTileM, 0, (cudaStream_t)stream>>>(
+  k_fit_slice<6, false><<<(unsigned)((nrow + 31) / 32), 32 * (N / 16), 0, (cudaStream_t)stream>>>(
       out, ld_out, kp, row_exp, x, nullptr, nullptr, nullptr, 0., nullptr, nrow, N);
   DPB_CUDA(cudaGetLastError());
   note_launches(1);
@@ -879,12 +896,13 @@ int dpb200_fit_head_f64(double* e_out, signed char* out, long long ld_out, int k
                         int N, int nslice, dpb200_stream_t stream) {
   using namespace dpb200;
   DPB_REQUIRE(nslice == 6, "fit_head: only 6 operand slices are built");
-  DPB_REQUIRE(nrow >= 0 && N >= 1 && kp % 16 == 0 && kp >= N && ld_out >= (long long)nslice * kp && ld_out % 16 == 0,
-              "fit_head: bad shape");
+  DPB_REQUIRE(nrow >= 0 && N >= 16 && N % 16 == 0 && N <= 512 && kp == N && ld_out >= (long long)nslice * kp &&
+                  ld_out % 16 == 0,
+              "fit_head: N must be a multiple of 16 up to 512 and kp == N");
   if (nrow == 0) return DPB200_OK;
   DPB_REQUIRE(e_out && out && row_exp && t && y && w_head && ((uintptr_t)out & 15) == 0,
               "fit_head: null or unaligned pointer");
-  k_fit_slice<6, true><<<(unsigned)((nrow + kTileM - 1) / kTileM), kTileM, 0, (cudaStream_t)stream>>>(
+  k_fit_slice<6, true><<<(unsigned)((nrow + 31) / 32), 32 * (N / 16), 0, (cudaStream_t)stream>>>(
       out, ld_out, kp, row_exp, t, y, w_head, idt, b_head, e_out, nrow, N);
   DPB_CUDA(cudaGetLastError());
   note_launches(1);
