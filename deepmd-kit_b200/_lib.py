@@ -58,6 +58,7 @@ _PLAIN_SIGS = {
     "split_i8_rows_f64": "p l p p l l i i p",
     "split_i8_combine_f64": "pp p l i pp ppp l i i p",
     "split_tf32_f32": "p l p l l i i p",
+    "scatter_nlist_rows": "ppp i p ii p",
     "fit_gemm_i8_f64": "i l iii p l l p i p i p p p pp l p l i i p",
     "fit_slice_rows_f64": "p l i p p l i i p",
     "fit_head_f64": "p p l i p pppp d l i i p",

@@ -56,16 +56,22 @@ void sync_default_stream(const char* what) {
 struct Workspace {
   void* ptr = nullptr;
   bool owned = false;
+  // Uses the caller's scratch when it is large enough once aligned up to 256 bytes (no device allocation, hence no
+  // implicit device synchronisation per call); allocates otherwise.
   Workspace(void* scratch, size_t scratch_bytes, size_t need) {
-    if (scratch != nullptr && scratch_bytes >= need && (reinterpret_cast<uintptr_t>(scratch) & 255) == 0) {
-      ptr = scratch;
-    } else {
-      if (cudaMalloc(&ptr, need) != cudaSuccess) {
-        cudaGetLastError();
-        throw deepmd::deepmd_exception_oom("dpb200 workspace allocation failed");
+    if (scratch != nullptr) {
+      const uintptr_t base = reinterpret_cast<uintptr_t>(scratch);
+      const uintptr_t aligned = (base + 255) & ~uintptr_t(255);
+      if (aligned - base <= scratch_bytes && scratch_bytes - (aligned - base) >= need) {
+        ptr = reinterpret_cast<void*>(aligned);
+        return;
       }
-      owned = true;
     }
+    if (cudaMalloc(&ptr, need) != cudaSuccess) {
+      cudaGetLastError();
+      throw deepmd::deepmd_exception_oom("dpb200 workspace allocation failed");
+    }
+    owned = true;
   }
   ~Workspace() {
     if (owned) cudaFree(ptr);
@@ -247,12 +253,18 @@ DPB_EXPORT int copy_coord_gpu(FPTYPE* out_c, int* out_t, int* mapping, int* nall
                               const deepmd::Region<FPTYPE>& region) {
   FPTYPE b[9];
   fetch_box(b, region);
-  // the cutoff is not an argument of the reference function: the caller hands over the cell grid it
-  // built with compute_cell_info (coord.cc:68-108): ncell = cell_info[3..5], ngcell = cell_info[12..14]
+  // the cutoff is not an argument of the reference function: the caller hands over the cell grid it built with
+  // compute_cell_info (coord.cc:68-108): ncell = cell_info[3..5], ngcell = cell_info[12..14].  cell_info is a
+  // DEVICE array (prod_env_mat_multi_device.cc:2437-2450 uploads it; coord.cu reads it inside kernels only).
+  int ci[23];
+  if (cudaMemcpy(ci, cell_info, sizeof(ci), cudaMemcpyDeviceToHost) != cudaSuccess) {
+    cudaGetLastError();
+    throw deepmd::deepmd_exception("dpb200 copy_coord_gpu: cannot read cell_info from the device");
+  }
   const size_t need = dpb200_copy_coord_workspace_bytes(nloc);
   Workspace ws(nullptr, 0, need);
-  const int rc = Fn<FPTYPE>::copy_coord(out_c, out_t, mapping, nall, in_c, in_t, nloc, mem_nall, cell_info + 3,
-                                        cell_info + 12, b, ws.ptr, need, nullptr);
+  const int rc = Fn<FPTYPE>::copy_coord(out_c, out_t, mapping, nall, in_c, in_t, nloc, mem_nall, ci + 3, ci + 12, b,
+                                        ws.ptr, need, nullptr);
   check(rc, "copy_coord_gpu");
   sync_default_stream("copy_coord_gpu");
   return rc;
@@ -262,29 +274,35 @@ template <typename FPTYPE>
 DPB_EXPORT int build_nlist_gpu(InputNlist& nlist, int* max_list_size, int* nlist_data, const FPTYPE* c_cpy,
                                const int& nloc, const int& nall, const int& mem_size, const float& rcut,
                                const int& nframes, const int* type) {
-  if (nframes != 1) {
-    throw deepmd::deepmd_exception("dpb200 build_nlist_gpu: one frame per call");
+  // Contract of source/lib/src/gpu/neighbor_list.cu:197-250: row r = frame * nloc + atom; its neighbours (ascending
+  // index) go to the caller-owned row firstneigh[r], numneigh[r] and ilist[r] = atom are filled, nlist_data
+  // (2 * nrows * mem_size ints) is scratch, a row capacity below nall is refused with 1.
+  if (mem_size < nall) {
+    return 1;
   }
-  // nlist.{ilist,numneigh,firstneigh} are device arrays owned by the caller; rows live in
-  // nlist_data (2*nloc*mem_size ints of caller scratch): we use its first nloc*mem_size ints.
+  const long long nrows = (long long)nframes * nloc;
   const size_t need = dpb200_build_nlist_workspace_bytes(nall);
   Workspace ws(nullptr, 0, need);
-  const int rc = Fn<FPTYPE>::build(nlist.numneigh, nlist_data, max_list_size, c_cpy, nloc, nall, mem_size, rcut, type,
-                                   ws.ptr, need, nullptr);
-  check(rc, "build_nlist_gpu");
-  if (rc == 0) {
-    std::vector<int> il(nloc);
-    std::vector<int*> rows(nloc);
-    for (int i = 0; i < nloc; ++i) {
-      il[i] = i;
-      rows[i] = nlist_data + (size_t)i * mem_size;
+  int max_nei = 0;
+  for (int f = 0; f < nframes; ++f) {
+    int frame_max = 0;
+    const int rc = Fn<FPTYPE>::build(nlist.numneigh + (long long)f * nloc, nlist_data + (long long)f * nloc * mem_size,
+                                     &frame_max, c_cpy + (long long)f * nall * 3, nloc, nall, mem_size, rcut,
+                                     type ? type + (long long)f * nall : nullptr, ws.ptr, need, nullptr);
+    check(rc, "build_nlist_gpu");
+    if (rc != 0) {
+      sync_default_stream("build_nlist_gpu");
+      return rc;
     }
-    cudaMemcpy(nlist.ilist, il.data(), sizeof(int) * nloc, cudaMemcpyHostToDevice);
-    cudaMemcpy(nlist.firstneigh, rows.data(), sizeof(int*) * nloc, cudaMemcpyHostToDevice);
-    nlist.inum = nloc;
+    max_nei = frame_max > max_nei ? frame_max : max_nei;
   }
+  check(dpb200_scatter_nlist_rows(nlist.firstneigh, nlist.ilist, nlist_data, mem_size, nlist.numneigh, (int)nrows, nloc,
+                                  nullptr),
+        "build_nlist_gpu");
+  nlist.inum = (int)nrows;
+  *max_list_size = max_nei;
   sync_default_stream("build_nlist_gpu");
-  return rc;
+  return 0;
 }
 
 #define DPB_INSTANTIATE(FP)                                                                                          \

@@ -189,7 +189,7 @@ __global__ void __launch_bounds__(128, 5) k_env_mat_a(const __grid_constant__ En
           const float dy = __fsub_rn(cj.y, ci.y);
           const float dz = __fsub_rn(cj.z, ci.z);
           const float rr2 = __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
-          ok = (tj >= 0) && (rr2 <= p.rcut2);
+          ok = (tj >= 0) && (tj < ntypes) && (rr2 <= p.rcut2);  // a type outside sec[] has no section: skipped
           key = ((u64)(unsigned)tj << kTypeShift) | ((u64)__float_as_uint(rr2) << kIdxBits) | (u64)(unsigned)j;
         }
         const unsigned m = __ballot_sync(kFull, ok);

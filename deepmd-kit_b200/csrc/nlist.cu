@@ -636,6 +636,26 @@ int do_build_nlist(int* numneigh, int* rows, int* max_list_size, const FP* coord
 }  // namespace
 }  // namespace dpb200
 
+namespace dpb200 {
+namespace {
+// Dense rows [nrows][row_stride] -> the caller-owned rows of an InputNlist (firstneigh[i] = device pointer of row
+// i, neighbor_list.h:20-57); ilist[i] = i % nloc as build_nlist of source/lib/src/gpu/neighbor_list.cu:78-93.
+__global__ void k_scatter_rows(int* const* __restrict__ firstneigh, int* __restrict__ ilist,
+                               const int* __restrict__ rows, int row_stride, const int* __restrict__ numneigh,
+                               int nrows, int nloc) {
+  const int lane = threadIdx.x & 31;
+  const int nw = (gridDim.x * blockDim.x) >> 5;
+  for (int r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; r < nrows; r += nw) {
+    int* __restrict__ dst = firstneigh[r];
+    const int* __restrict__ src = rows + (long long)r * row_stride;
+    const int n = numneigh[r];
+    for (int j = lane; j < n; j += 32) dst[j] = src[j];
+    if (lane == 0 && ilist) ilist[r] = r % nloc;
+  }
+}
+}  // namespace
+}  // namespace dpb200
+
 extern "C" {
 
 size_t dpb200_copy_coord_workspace_bytes(int nloc) {
@@ -676,5 +696,20 @@ size_t dpb200_build_nlist_workspace_bytes(int nall) { return dpb200::build_ws(na
 DPB200_DEF_NL(f64, double)
 DPB200_DEF_NL(f32, float)
 #undef DPB200_DEF_NL
+
+int dpb200_scatter_nlist_rows(int* const* firstneigh, int* ilist, const int* rows, int row_stride,
+                              const int* numneigh, int nrows, int nloc, dpb200_stream_t stream) {
+  using namespace dpb200;
+  DPB_REQUIRE(nrows >= 0 && row_stride >= 0 && nloc >= 1, "scatter_nlist_rows: bad shape");
+  if (nrows == 0) return DPB200_OK;
+  DPB_REQUIRE(firstneigh && rows && numneigh, "scatter_nlist_rows: null pointer");
+  int grid = ceil_div(nrows, 8);
+  const int cap = sm_count() * 8;
+  if (grid > cap) grid = cap;
+  k_scatter_rows<<<grid, 256, 0, (cudaStream_t)stream>>>(firstneigh, ilist, rows, row_stride, numneigh, nrows, nloc);
+  DPB_CUDA(cudaGetLastError());
+  note_launches(1);
+  return DPB200_OK;
+}
 
 }  // extern "C"

@@ -562,6 +562,8 @@ class NeighborState:
     map64: Optional[torch.Tensor] = None
     type_inv: Optional[torch.Tensor] = None  # int32 inverse of type_perm: descriptor row of atom i
     chunks: Optional[list] = None  # atom slabs [(a, b, perm, ranges, inv)] when the evaluation is chunked
+    box: Optional[np.ndarray] = None  # cell the list was built for (host copy)
+    ref_coord: Optional[torch.Tensor] = None  # coordinates the list was built from
 
 
 def type_partition(atype: torch.Tensor, ntypes: int):
@@ -668,9 +670,27 @@ class DeepPotB200:
         torch.index_select(coord.reshape(-1, 3), 0, map64, out=shift)
         torch.sub(ext_c, shift, out=shift)
         perm, ranges, inv = self._type_partition(atype)
+        ref = ops._buf(self._cache, "ref_coord", (nloc, 3), coord.dtype, coord.device)
+        ref.copy_(coord.reshape(-1, 3))
         self.state = NeighborState(nloc, ext_t, mapping, shift, numneigh, rows, perm, ranges, map64=map64, type_inv=inv,
-                                   chunks=self._chunks(atype))
+                                   chunks=self._chunks(atype), box=np.array(box, dtype=np.float64).reshape(9).copy(),
+                                   ref_coord=ref)
         return self.state
+
+    def _list_is_stale(self, coord: torch.Tensor, atype: torch.Tensor, box) -> bool:
+        """The raw list (cutoff rcut + skin) and the ghost image shifts stay valid while the cell is the one they
+        were built for and no atom has moved more than skin / 2 from its build-time position (the LAMMPS `check yes`
+        criterion); `nlist_every` only caps the reuse (examples/water/lmp/in.lammps:7-8: every 10).  Independent
+        frames handed to eval() therefore never see another frame's list."""
+        st = self.state
+        if st is None or st.nloc != atype.numel() or st.ago >= self.nlist_every:
+            return True
+        if not np.array_equal(st.box, np.asarray(box, dtype=np.float64).reshape(9)):
+            return True
+        if self.skin <= 0.0:
+            return True
+        d2 = (coord.reshape(-1, 3) - st.ref_coord).square_().sum(1).max()
+        return bool(d2.item() > (0.5 * self.skin) ** 2)
 
     def _step(self, coord, atom_virial, fused):
         st = self.state
@@ -686,7 +706,7 @@ class DeepPotB200:
         """Device tensors in, device tensors out (no host copies).  With `use_graph` the returned tensors
         live in the graph's memory pool and are overwritten by the next call."""
         st = self.state
-        if st is None or st.ago >= self.nlist_every or st.nloc != atype.numel():
+        if self._list_is_stale(coord, atype, box):
             st = self.build_neighbors(coord, atype, box)
         st.ago += 1
         if not self.use_graph:

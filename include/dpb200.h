@@ -250,6 +250,11 @@ size_t dpb200_build_nlist_workspace_bytes(int nall);
 DPB200_DECL_NL(f64, double)
 DPB200_DECL_NL(f32, float)
 #undef DPB200_DECL_NL
+/* Copy dense rows [nrows][row_stride] into the caller-owned rows of an InputNlist (firstneigh: device array of
+ * device row pointers, neighbor_list.h:20-57) and fill ilist[i] = i % nloc (nullable) -- what fill_nlist /
+ * build_nlist of source/lib/src/gpu/neighbor_list.cu:78-128 leave behind for the caller of build_nlist_gpu. */
+int dpb200_scatter_nlist_rows(int* const* firstneigh, int* ilist /*nullable*/, const int* rows, int row_stride,
+                              const int* numneigh, int nrows, int nloc, dpb200_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------
  * Ghost halo for the spatially decomposed multi-GPU path.  Replaces what LAMMPS' Comm does around

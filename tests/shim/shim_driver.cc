@@ -7,14 +7,17 @@
 
 #include <cstdio>
 #include <cstdlib>
+#include <string>
 #include <vector>
 
+#include "coord.h"
 #include "neighbor_list.h"
 #include "prod_env_mat.h"
 #include "prod_force.h"
 #include "prod_force_grad.h"
 #include "prod_virial.h"
 #include "prod_virial_grad.h"
+#include "region.h"
 #include "tabulate.h"
 
 #define CK(x)                                                                  \
@@ -49,7 +52,118 @@ void down(FILE* f, const T* d, size_t n) {
   fwrite(v.data(), sizeof(T), n, f);
 }
 
+// Second mode (`shim_driver nlist in out`): the neighbour front end exactly as _norm_copy_coord_gpu and
+// _build_nlist_gpu of source/op/tf/prod_env_mat_multi_device.cc:2399-2600 drive it -- Region and cell_info live in
+// DEVICE memory, the rows are written into the caller-owned jlist through firstneigh, ind_data is separate scratch.
+// (init_region_cpu / compute_cell_info are host functions of the reference CPU library: oracle/_ref.)
+static int nlist_mode(const char* in, const char* out) {
+  FILE* fi = fopen(in, "rb");
+  FILE* fo = fopen(out, "wb");
+  if (!fi || !fo) return 1;
+  auto hd = rd<int>(fi, 3);  // nloc, mem_cpy, nframes
+  const int nloc = hd[0], mem_cpy = hd[1], nframes = hd[2];
+  auto rc = rd<float>(fi, 1);
+  auto box = rd<double>(fi, 9);
+  auto coord = rd<double>(fi, (size_t)nloc * 3);
+  auto type = rd<int>(fi, nloc);
+  deepmd::Region<double> region;
+  deepmd::init_region_cpu(region, box.data());
+  std::vector<double> box_info(18);
+  for (int k = 0; k < 9; ++k) box_info[k] = region.boxt[k], box_info[9 + k] = region.rec_boxt[k];
+  std::vector<int> cell_info(23);
+  deepmd::compute_cell_info(cell_info.data(), rc[0], region);
+  const int loc_cellnum = cell_info[21], total_cellnum = cell_info[22];
+  double* box_dev = up(box_info);
+  std::vector<int> ints(23 + (size_t)nloc * 3 + loc_cellnum + (size_t)total_cellnum * 3 * 2 + loc_cellnum + 1 +
+                        total_cellnum + 1 + nloc, 0);
+  for (int k = 0; k < 23; ++k) ints[k] = cell_info[k];
+  int* cell_info_dev = up(ints);
+  deepmd::Region<double> region_dev(box_dev, box_dev + 9);
+  double* tmp_coord = up(coord);
+  int* d_type = up(type);
+  double* coord_cpy;
+  int* type_cpy;
+  CK(cudaMalloc((void**)&coord_cpy, sizeof(double) * (size_t)mem_cpy * 3));
+  CK(cudaMalloc((void**)&type_cpy, sizeof(int) * (size_t)mem_cpy * 2));
+  int* idx_mapping = type_cpy + mem_cpy;
+  int nall = nloc, ret_small = -1, ret = -1, ret_cap = -1, max_nnei = 0;
+  std::vector<int> numneigh_h, ilist_h, jlist_h;
+  int mem_nnei = 0;
+  try {
+    deepmd::normalize_coord_gpu(tmp_coord, nloc, region_dev);
+    // a copy buffer that is too small must be reported with 1, not written past
+    ret_small = deepmd::copy_coord_gpu(coord_cpy, type_cpy, idx_mapping, &nall, cell_info_dev + 23, tmp_coord, d_type, nloc,
+                                       nloc + 1, loc_cellnum, total_cellnum, cell_info_dev, region_dev);
+    ret = deepmd::copy_coord_gpu(coord_cpy, type_cpy, idx_mapping, &nall, cell_info_dev + 23, tmp_coord, d_type, nloc,
+                                 mem_cpy, loc_cellnum, total_cellnum, cell_info_dev, region_dev);
+    if (ret != 0) {
+      fprintf(stderr, "copy_coord_gpu returned %d\n", ret);
+      return 5;
+    }
+    // nframes identical frames of the extended system
+    const long long nrows = (long long)nframes * nloc;
+    double* c_frames;
+    int* t_frames;
+    CK(cudaMalloc((void**)&c_frames, sizeof(double) * (size_t)nframes * nall * 3));
+    CK(cudaMalloc((void**)&t_frames, sizeof(int) * (size_t)nframes * nall));
+    for (int f = 0; f < nframes; ++f) {
+      CK(cudaMemcpy(c_frames + (size_t)f * nall * 3, coord_cpy, sizeof(double) * nall * 3, cudaMemcpyDeviceToDevice));
+      CK(cudaMemcpy(t_frames + (size_t)f * nall, type_cpy, sizeof(int) * nall, cudaMemcpyDeviceToDevice));
+    }
+    mem_nnei = nall;
+    int *ilist, *numneigh, *jlist;
+    int** firstneigh;
+    CK(cudaMalloc((void**)&ilist, sizeof(int) * nrows * 2));
+    numneigh = ilist + nrows;
+    CK(cudaMalloc((void**)&jlist, sizeof(int) * (size_t)nrows * mem_nnei * 3));
+    CK(cudaMemset(jlist, 0xff, sizeof(int) * (size_t)nrows * mem_nnei * 3));
+    int* ind_data = jlist + (size_t)nrows * mem_nnei;
+    CK(cudaMalloc((void**)&firstneigh, sizeof(int*) * nrows));
+    std::vector<int*> first(nrows);
+    for (long long i = 0; i < nrows; ++i) first[i] = jlist + i * mem_nnei;
+    CK(cudaMemcpy(firstneigh, first.data(), sizeof(int*) * nrows, cudaMemcpyHostToDevice));
+    deepmd::InputNlist inlist((int)nrows, ilist, numneigh, firstneigh);
+    ret_cap = deepmd::build_nlist_gpu(inlist, &max_nnei, ind_data, c_frames, nloc, nall, nall - 1, rc[0], nframes, t_frames);
+    ret = deepmd::build_nlist_gpu(inlist, &max_nnei, ind_data, c_frames, nloc, nall, mem_nnei, rc[0], nframes, t_frames);
+    if (ret != 0) {
+      fprintf(stderr, "build_nlist_gpu returned %d\n", ret);
+      return 5;
+    }
+    // the caller's firstneigh table must be untouched and the rows must be in jlist
+    std::vector<int*> first_after(nrows);
+    CK(cudaMemcpy(first_after.data(), firstneigh, sizeof(int*) * nrows, cudaMemcpyDeviceToHost));
+    for (long long i = 0; i < nrows; ++i)
+      if (first_after[i] != first[i]) {
+        fprintf(stderr, "firstneigh[%lld] was overwritten\n", i);
+        return 6;
+      }
+    numneigh_h.resize(nrows);
+    ilist_h.resize(nrows);
+    jlist_h.resize((size_t)nrows * mem_nnei);
+    CK(cudaMemcpy(numneigh_h.data(), numneigh, sizeof(int) * nrows, cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(ilist_h.data(), ilist, sizeof(int) * nrows, cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(jlist_h.data(), jlist, sizeof(int) * jlist_h.size(), cudaMemcpyDeviceToHost));
+  } catch (const std::exception& e) {
+    fprintf(stderr, "exception: %s\n", e.what());
+    return 4;
+  }
+  int head[6] = {nall, ret_small, ret_cap, max_nnei, mem_nnei, nframes};
+  fwrite(head, sizeof(int), 6, fo);
+  down(fo, tmp_coord, (size_t)nloc * 3);
+  down(fo, coord_cpy, (size_t)nall * 3);
+  down(fo, type_cpy, (size_t)nall);
+  down(fo, idx_mapping, (size_t)nall);
+  fwrite(ilist_h.data(), sizeof(int), ilist_h.size(), fo);
+  fwrite(numneigh_h.data(), sizeof(int), numneigh_h.size(), fo);
+  // rows, compacted: numneigh entries each
+  for (size_t i = 0; i < numneigh_h.size(); ++i) fwrite(jlist_h.data() + i * mem_nnei, sizeof(int), numneigh_h[i], fo);
+  fclose(fo);
+  printf("SHIM_DRIVER_OK\n");
+  return 0;
+}
+
 int main(int argc, char** argv) {
+  if (argc >= 4 && std::string(argv[1]) == "nlist") return nlist_mode(argv[2], argv[3]);
   if (argc < 3) return 1;
   FILE* fi = fopen(argv[1], "rb");
   FILE* fo = fopen(argv[2], "wb");

@@ -103,3 +103,59 @@ def test_shim_driver_matches_oracle(port, tmp_path):
     wf = port.prod_force_a(nd, w_dv, w_nl, nall)
     close(gn_f, port.prod_force_grad_a(wf[:nloc], w_dv, w_nl), 4e-10)
     close(gn_v, port.prod_virial_grad_a(wv, w_dv, w_rij, w_nl), 2e-9)
+
+
+@pytest.mark.gpu
+def test_shim_neighbour_front_end(port, tmp_path):
+    """normalize_coord_gpu / copy_coord_gpu / build_nlist_gpu driven as _norm_copy_coord_gpu and _build_nlist_gpu of
+    source/op/tf/prod_env_mat_multi_device.cc:2399-2600 drive them: Region and cell_info in DEVICE memory, rows
+    written into the caller-owned jlist through firstneigh (which must stay untouched), two frames per call,
+    `1` returned for a copy buffer / row capacity that is too small."""
+    if not os.path.exists(DRIVER):
+        pytest.skip("tests/shim/_build/shim_driver not built (needs the reference headers)")
+    coord, atype, box = water_like_box(ncopy=1, seed=21, jitter=0.2)
+    coord = coord + 3.7  # some atoms outside the cell: normalize_coord_gpu has work to do
+    nloc, rc, nframes = len(atype), 6.0, 2
+    fin, fout = tmp_path / "nl_in.bin", tmp_path / "nl_out.bin"
+    mem_cpy = 40 * nloc
+    with open(fin, "wb") as f:
+        np.array([nloc, mem_cpy, nframes], np.int32).tofile(f)
+        np.array([rc], np.float32).tofile(f)
+        np.ascontiguousarray(box, np.float64).tofile(f)
+        np.ascontiguousarray(coord, np.float64).tofile(f)
+        np.ascontiguousarray(atype, np.int32).tofile(f)
+    r = subprocess.run([DRIVER, "nlist", str(fin), str(fout)], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0 and "SHIM_DRIVER_OK" in r.stdout, (r.stdout[-500:], r.stderr[-2000:])
+    raw = open(fout, "rb").read()
+    off = 0
+
+    def take(n, dt):
+        nonlocal off
+        a = np.frombuffer(raw, dtype=dt, count=n, offset=off)
+        off += n * np.dtype(dt).itemsize
+        return a
+
+    nall, ret_small, ret_cap, max_nnei, mem_nnei, nf = take(6, np.int32)
+    assert ret_small == 1 and ret_cap == 1 and nf == nframes and mem_nnei == nall
+    cn = take(nloc * 3, np.float64).reshape(nloc, 3)
+    ext_c = take(nall * 3, np.float64).reshape(nall, 3)
+    ext_t, ext_m = take(nall, np.int32), take(nall, np.int32)
+    ilist, numneigh = take(nframes * nloc, np.int32), take(nframes * nloc, np.int32)
+    rows = [take(int(k), np.int32) for k in numneigh]
+    w = port.normalize_coord(coord, box)
+    assert np.array_equal(cn, w)
+    wc, wt, wm = port.copy_coord(w, atype, box, rc)
+    assert nall == len(wt)
+    assert np.array_equal(ext_c[:nloc], w) and np.array_equal(ext_m[:nloc], np.arange(nloc))
+
+    def key(c, t, m):
+        return sorted((int(m[i]), int(t[i])) + tuple(np.round(c[i], 6)) for i in range(nloc, len(t)))
+
+    assert key(ext_c, ext_t, ext_m) == key(wc, wt, wm)
+    wn, wr = port.build_nlist(ext_c, nloc, rc, atype=ext_t)
+    assert max_nnei == wn.max()
+    for fr in range(nframes):
+        assert np.array_equal(ilist[fr * nloc:(fr + 1) * nloc], np.arange(nloc))
+        assert np.array_equal(numneigh[fr * nloc:(fr + 1) * nloc], wn)
+        for i in range(nloc):
+            assert np.array_equal(rows[fr * nloc + i], wr[i, : wn[i]])
