@@ -373,21 +373,40 @@ class SeAModel:
     """Random-init compressed se_e2_a model (weights of the named architecture, tabulated with the
     restated `dp compress`)."""
 
-    def __init__(self, cfg: SeAConfig, dtype=torch.float64, device="cuda"):
+    def __init__(self, cfg: SeAConfig, dtype=torch.float64, device="cuda", weights: Optional[dict] = None):
+        """weights=None: random-init nets of the architecture in `cfg` with the WATER_STATS-style `cfg.stats`.
+        weights = dict(davg, dstd [ntypes, nnei, 4], embed=[(weights, biases) per neighbour type], fit=[dict(layers=[(w, b,
+        idt|None)], head=(w, b)) per centre type], bias_atom_e [ntypes]): a trained model (see from_reference)."""
         self.cfg = cfg
         self.dtype = dtype
         self.device = torch.device(device)
         nnei = cfg.nnei
-        davg = np.zeros((cfg.ntypes, nnei, 4))
-        dstd = np.ones((cfg.ntypes, nnei, 4))
-        for t, (a0, s0, s1) in enumerate(cfg.stats):
-            davg[t, :, 0] = a0
-            dstd[t, :, 0] = s0
-            dstd[t, :, 1:] = s1
+        if weights is None:
+            davg = np.zeros((cfg.ntypes, nnei, 4))
+            dstd = np.ones((cfg.ntypes, nnei, 4))
+            for t, (a0, s0, s1) in enumerate(cfg.stats):
+                davg[t, :, 0] = a0
+                dstd[t, :, 0] = s0
+                dstd[t, :, 1:] = s1
+            self.embed = [EmbeddingNet(cfg.neuron, cfg.seed + 17 * t) for t in range(cfg.ntypes)]
+        else:
+            davg = np.asarray(weights["davg"], np.float64).reshape(cfg.ntypes, nnei, 4)
+            dstd = np.asarray(weights["dstd"], np.float64).reshape(cfg.ntypes, nnei, 4)
+            self.embed = []
+            for ws, bs in weights["embed"]:
+                net = EmbeddingNet(cfg.neuron, 0)
+                net.weights = [torch.as_tensor(np.asarray(w, np.float64)) for w in ws]
+                net.biases = [torch.as_tensor(np.asarray(b, np.float64)).reshape(-1) for b in bs]
+                assert [tuple(w.shape) for w in net.weights] == [
+                    (a, b) for a, b in zip([1] + list(cfg.neuron[:-1]), cfg.neuron)], "embedding net shape"
+                self.embed.append(net)
+        self.bias_atom_e = torch.zeros(cfg.ntypes, dtype=dtype, device=self.device)
+        if weights is not None and weights.get("bias_atom_e") is not None:
+            self.bias_atom_e = torch.as_tensor(np.asarray(weights["bias_atom_e"], np.float64).reshape(-1), dtype=dtype,
+                                               device=self.device)
         self.davg_np, self.dstd_np = davg, dstd
         self.davg = torch.as_tensor(davg.reshape(cfg.ntypes, -1), dtype=dtype, device=self.device)
         self.dstd = torch.as_tensor(dstd.reshape(cfg.ntypes, -1), dtype=dtype, device=self.device)
-        self.embed = [EmbeddingNet(cfg.neuron, cfg.seed + 17 * t) for t in range(cfg.ntypes)]
         tables, infos = compress_se_a(self.embed, davg[:, 0, :], dstd[:, 0, :], cfg.sel, cfg.min_nbor_dist,
                                       cfg.rcut_smth, cfg.rcut, cfg.stride0, cfg.stride1, cfg.extrapolate)
         self.tables64 = tables
@@ -397,6 +416,15 @@ class SeAModel:
         dim_d = self.M * cfg.axis_neuron
         self.fit = [FittingNet(dim_d, cfg.fitting_neuron, cfg.fitting_resnet_dt, cfg.seed + 101 * t, dtype, self.device)
                     for t in range(cfg.ntypes)]
+        if weights is not None:
+            for f, fw in zip(self.fit, weights["fit"]):
+                f.layers = [(torch.as_tensor(np.asarray(w, np.float64)).to(self.device, dtype),
+                             torch.as_tensor(np.asarray(b, np.float64)).reshape(-1).to(self.device, dtype),
+                             None if i is None else torch.as_tensor(np.asarray(i, np.float64)).reshape(-1).to(self.device, dtype))
+                            for w, b, i in fw["layers"]]
+                hw, hb = fw["head"]
+                f.head = (torch.as_tensor(np.asarray(hw, np.float64)).reshape(-1, 1).to(self.device, dtype),
+                          torch.as_tensor(np.asarray(hb, np.float64)).reshape(1).to(self.device, dtype))
         import os as _os
 
         self.fit_chunk = int(_os.environ.get("DPB200_FIT_CHUNK", str(1 << 17)))
@@ -428,6 +456,22 @@ class SeAModel:
             if all(fl):
                 self.coef_flags = fl
 
+    @classmethod
+    def from_reference(cls, data: dict, dtype=torch.float64, device="cuda", min_nbor_dist: float = 0.8, **compress):
+        """A trained reference se_e2_a + energy model (type_one_side) from its serialized weights: `data` is the dict
+        written by tests/golden/make_deeppot_sea.py from a deepmd.pt state_dict (atomic_model.descriptor.sea.{mean,
+        stddev, filter_layers.networks.<neighbour type>}, atomic_model.fitting_net.{filter_layers.networks.<centre
+        type>, bias_atom_e}; deepmd/pt/model/descriptor/se_a.py, deepmd/pt/model/task/fitting.py) plus the
+        model_def_script entries sel, rcut, rcut_smth, neuron, axis_neuron, fitting neuron / resnet_dt.  The embedding
+        nets are tabulated here (compress.py = `dp compress`), everything else is used as is."""
+        d = data["descriptor"]
+        f = data["fitting_net"]
+        cfg = SeAConfig(ntypes=len(d["sel"]), sel=tuple(d["sel"]), rcut=float(d["rcut"]), rcut_smth=float(d["rcut_smth"]),
+                        neuron=tuple(d["neuron"]), axis_neuron=int(d["axis_neuron"]),
+                        fitting_neuron=tuple(f["neuron"]), fitting_resnet_dt=bool(f["resnet_dt"]),
+                        min_nbor_dist=float(min_nbor_dist), **compress)
+        return cls(cfg, dtype, device, weights=data["weights"])
+
     # -- descriptor contraction (dpb200 kernels) + fitting net (cuBLAS GEMMs through torch, hand-written
     #    backward).  The fitting net is library code here; SURVEY 8f-1 lists its fusion as the next item.
     def energy_and_dy(self, xyz: torch.Tensor, type_perm: torch.Tensor, type_ranges):
@@ -446,7 +490,7 @@ class SeAModel:
                 e, gd = self.fit[t].forward_backward(d)
                 del d
                 ops.se_a_descriptor_grad(gd, xyz, cfg.axis_neuron, inv, rows=idx, out=dy)  # scatters back
-                e_atom.index_copy_(0, type_perm[c0:c1], e)
+                e_atom.index_copy_(0, type_perm[c0:c1], e + self.bias_atom_e[t])
         return e_atom.sum(), e_atom, dy
 
     def energy_and_dy_split(self, xyz, desc, row_exp, type_perm, type_ranges):
@@ -466,7 +510,7 @@ class SeAModel:
                     e, gd = self.fit[t].forward_backward_split(desc[c0:], None if row_exp is None else row_exp[c0:c1],
                                                                c1 - c0)
                 ops.se_a_descriptor_grad(gd, xyz, cfg.axis_neuron, inv, rows=type_perm32[c0:c1], out=dy)
-                e_atom.index_copy_(0, type_perm[c0:c1], e)
+                e_atom.index_copy_(0, type_perm[c0:c1], e + self.bias_atom_e[t])
         return e_atom.sum(), e_atom, dy
 
     def bytes_per_atom(self) -> int:

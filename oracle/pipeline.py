@@ -50,7 +50,7 @@ def reference_energy_and_dy(model, xyz, perm, ranges):
     for t, (a, b) in enumerate(ranges):
         idx = perm[a:b]
         if idx.numel():
-            e_atom = e_atom.index_add(0, idx, model.fit[t](d.index_select(0, idx)))
+            e_atom = e_atom.index_add(0, idx, model.fit[t](d.index_select(0, idx)) + model.bias_atom_e[t].to(x.dtype))
     energy = e_atom.sum()
     (dy,) = torch.autograd.grad(energy, x)
     return energy.detach(), e_atom.detach(), dy

@@ -49,3 +49,21 @@ def ref():
     if not cpu.available("reference"):
         pytest.skip("oracle/_ref/libdeepmd_ref.so not built (needs /root/reference)")
     return cpu.CpuLib("reference")
+
+
+@pytest.fixture(scope="session", params=["port", "reference"])
+def olib(request):
+    """CPU checker of the GPU operator tests, both flavours: our restatement (`port`, oracle/dp_oracle.c) and the
+    unmodified reference CPU library compiled from /root/reference (`reference`, oracle/_ref; prebuilt, travels to
+    the GPU box).  Every GPU parity test runs against both."""
+    from oracle import cpu
+
+    kind = request.param
+    if not cpu.available(kind):
+        try:
+            cpu.build(kind)
+        except Exception:
+            pass
+    if not cpu.available(kind):
+        pytest.skip(f"CPU checker `{kind}` is not built")
+    return cpu.CpuLib(kind)

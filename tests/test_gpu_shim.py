@@ -36,12 +36,12 @@ def test_shim_exports_reference_symbols():
 
 
 @pytest.mark.gpu
-def test_shim_driver_matches_oracle(port, tmp_path):
+def test_shim_driver_matches_oracle(olib, tmp_path):
     if not os.path.exists(DRIVER):
         pytest.skip("tests/shim/_build/shim_driver not built (needs the reference headers)")
     rng = np.random.default_rng(5)
     coord, atype, box = water_like_box(ncopy=2, seed=4, jitter=0.05)
-    s = extended_system(port, coord, atype, box, 6.5)
+    s = extended_system(olib, coord, atype, box, 6.5)
     sec = np.array([0, 46, 138], np.int32)
     nnei, nloc, nall = 138, s["nloc"], len(s["atype"])
     avg = rng.normal(scale=0.05, size=(2, nnei * 4))
@@ -80,7 +80,7 @@ def test_shim_driver_matches_oracle(port, tmp_path):
     force, virial, av = take(nall * 3, np.float64), take(9, np.float64), take(nall * 9, np.float64)
     gn_f, gn_v = take(nloc * nnei * 4, np.float64), take(nloc * nnei * 4, np.float64)
     o, neigh = ocpu.dense_to_csr(s["rows"], s["numneigh"])
-    w_em, w_dv, w_rij, w_nl = port.prod_env_mat_a(s["coord"], s["atype"], o, neigh, avg, std, nloc, 6.0, 0.5, sec)
+    w_em, w_dv, w_rij, w_nl = olib.prod_env_mat_a(s["coord"], s["atype"], o, neigh, avg, std, nloc, 6.0, 0.5, sec)
     assert np.array_equal(nlist.reshape(nloc, nnei), w_nl)
 
     def close(a, b, tol=1e-10):
@@ -92,21 +92,21 @@ def test_shim_driver_matches_oracle(port, tmp_path):
     close(rij, w_rij)
     em3 = w_em.reshape(nloc, nnei, 4)
     em_x = np.ascontiguousarray(em3[:, :, 0]).reshape(-1, 1)
-    close(desc, port.tabulate_fusion_se_a(table, info, em_x, em3, M), 4e-10)
-    wx, wem, _ = port.tabulate_fusion_se_a_grad(table, info, em_x, em3, dy, M)
+    close(desc, olib.tabulate_fusion_se_a(table, info, em_x, em3, M), 4e-10)
+    wx, wem, _ = olib.tabulate_fusion_se_a_grad(table, info, em_x, em3, dy, M)
     close(gx, wx, 4e-10)
     close(gem, wem, 4e-10)
-    close(force, port.prod_force_a(nd, w_dv, w_nl, nall), 4e-10)
-    wv, wav = port.prod_virial_a(nd, w_dv, w_rij, w_nl, nall)
+    close(force, olib.prod_force_a(nd, w_dv, w_nl, nall), 4e-10)
+    wv, wav = olib.prod_virial_a(nd, w_dv, w_rij, w_nl, nall)
     close(virial, wv, 2e-9)
     close(av, wav, 4e-10)
-    wf = port.prod_force_a(nd, w_dv, w_nl, nall)
-    close(gn_f, port.prod_force_grad_a(wf[:nloc], w_dv, w_nl), 4e-10)
-    close(gn_v, port.prod_virial_grad_a(wv, w_dv, w_rij, w_nl), 2e-9)
+    wf = olib.prod_force_a(nd, w_dv, w_nl, nall)
+    close(gn_f, olib.prod_force_grad_a(wf[:nloc], w_dv, w_nl), 4e-10)
+    close(gn_v, olib.prod_virial_grad_a(wv, w_dv, w_rij, w_nl), 2e-9)
 
 
 @pytest.mark.gpu
-def test_shim_neighbour_front_end(port, tmp_path):
+def test_shim_neighbour_front_end(olib, tmp_path):
     """normalize_coord_gpu / copy_coord_gpu / build_nlist_gpu driven as _norm_copy_coord_gpu and _build_nlist_gpu of
     source/op/tf/prod_env_mat_multi_device.cc:2399-2600 drive them: Region and cell_info in DEVICE memory, rows
     written into the caller-owned jlist through firstneigh (which must stay untouched), two frames per call,
@@ -142,9 +142,9 @@ def test_shim_neighbour_front_end(port, tmp_path):
     ext_t, ext_m = take(nall, np.int32), take(nall, np.int32)
     ilist, numneigh = take(nframes * nloc, np.int32), take(nframes * nloc, np.int32)
     rows = [take(int(k), np.int32) for k in numneigh]
-    w = port.normalize_coord(coord, box)
+    w = olib.normalize_coord(coord, box)
     assert np.array_equal(cn, w)
-    wc, wt, wm = port.copy_coord(w, atype, box, rc)
+    wc, wt, wm = olib.copy_coord(w, atype, box, rc)
     assert nall == len(wt)
     assert np.array_equal(ext_c[:nloc], w) and np.array_equal(ext_m[:nloc], np.arange(nloc))
 
@@ -152,7 +152,7 @@ def test_shim_neighbour_front_end(port, tmp_path):
         return sorted((int(m[i]), int(t[i])) + tuple(np.round(c[i], 6)) for i in range(nloc, len(t)))
 
     assert key(ext_c, ext_t, ext_m) == key(wc, wt, wm)
-    wn, wr = port.build_nlist(ext_c, nloc, rc, atype=ext_t)
+    wn, wr = olib.build_nlist(ext_c, nloc, rc, atype=ext_t)
     assert max_nnei == wn.max()
     for fr in range(nframes):
         assert np.array_equal(ilist[fr * nloc:(fr + 1) * nloc], np.arange(nloc))
