@@ -104,21 +104,16 @@ class ClockSampler:
                 "power_w_max": max(pw) if pw else None, "samples": len(sm), "reasons": sorted(reasons)}
 
 
-# DRAM traffic per atom (dram__bytes_read.sum + dram__bytes_write.sum over the launches of one step) from the
-# `ncu --set full` captures summarised in profiles/r01_ncu_full_v6_summary.csv (fp64, 98 304-atom box; the kernels
-# stream per-atom data, so the figure scales with the atom count).  tabulate_sections_desc = first section (3 973)
-# + last section with the fused descriptor epilogue (17 860: it also writes the 9.6 KB int8 operand of the fitting
-# net); tabulate_sections_grad = 5 798 (first section, measured) + the second section's share of the earlier
-# capture (profiles/r01_ncu_full_v3_summary.csv: 14 046 for both).
-NCU_DRAM_BYTES_PER_ATOM_F64 = {
-    "prod_env_mat_a": 22279.0,
-    "prod_force_virial_a": 20890.0,
-    "prod_force_virial_a_ex": 20890.0,
-    "tabulate_sections_fwd": 12271.0,
-    "tabulate_sections_desc": 21833.0,
-    "tabulate_sections_grad": 14046.0,
-    "se_a_descriptor_grad": 22367.0,
-}
+# DRAM traffic per atom and operator (dram__bytes_read.sum + dram__bytes_write.sum over the launches of one step):
+# written by tools/ncu_step_summary.py from the `ncu --set full` capture of `bench.py --ncopy 8` committed under
+# profiles/ (the kernels stream per-atom data, so the figure scales with the atom count).  No capture, no number.
+def ncu_dram_bytes_per_atom():
+    p = os.path.join(ROOT, "profiles", "r02_dram_bytes_per_atom.json")
+    if not os.path.exists(p):
+        return {}, None
+    with open(p) as f:
+        d = json.load(f)
+    return d.get("f64", {}), "profiles/r02_dram_bytes_per_atom.json (" + d.get("source", "ncu --set full") + ")"
 
 
 def measured_peaks():
@@ -126,8 +121,8 @@ def measured_peaks():
     if os.path.exists(p):
         with open(p) as f:
             d = json.load(f)
-        return float(d["hbm_gbs"]), "MEASURED_PEAKS.json"
-    return 6650.0, "fallback (B200_PROFILING.md)"
+        return d, "MEASURED_PEAKS.json"
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0}, "fallback (B200_PROFILING.md)"
 
 
 # ------------------------------------------------------------------------------------------------
@@ -138,9 +133,7 @@ def cpu_pipeline_timing(args, steps, warmup, seconds=None):
     import __graft_entry__ as g
     from oracle import cpu as ocpu
     from oracle import pipeline
-
-    g.load_package()
-    from deepmd_kit_b200.model import SeAConfig, SeAModel
+    from oracle.refmodel import RefWaterModel  # same seeds / tables as the product's SeAModel, no product import
 
     kind = "reference" if ocpu.available("reference") else "port"
     lib = ocpu.CpuLib(kind)
@@ -155,8 +148,8 @@ def cpu_pipeline_timing(args, steps, warmup, seconds=None):
     torch.set_num_threads(ncores)
     dtype = torch.float64 if args.dtype == "f64" else torch.float32
     np_dt = np.float64 if args.dtype == "f64" else np.float32
-    cfg = SeAConfig()
-    model = SeAModel(cfg, dtype, "cpu")
+    model = RefWaterModel(dtype)
+    cfg = model.cfg
     coord, atype, box = g.water_box(args.cpu_ncopy, args.jitter)
     nat = len(atype)
     t0 = time.perf_counter()
@@ -204,8 +197,17 @@ def run_reference(args):
         "cpu_baseline": {"value": r["us_per_step_atom"], "unit": UNIT, "cores": r["cores"], "kind": r["kind"],
                          "sample": r["sample"], "stages_us_per_atom": r["stages_us_per_atom"]},
         "e2e": {"value": r["us_per_step_atom"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "product_native_loaded": _maps_contain("libdpb200"),
     }
     _emit(json.dumps(line))
+
+
+def _maps_contain(name):
+    try:
+        with open("/proc/self/maps") as f:
+            return any(name in ln for ln in f)
+    except OSError:
+        return None
 
 
 def _emit(text):
@@ -392,7 +394,7 @@ def per_kernel(args, torch, ops, model, dp, step, L, dev, nloc, esz):
     names = ["prod_env_mat_a", "tabulate_sections_fwd", "tabulate_sections_desc", "tabulate_sections_grad",
              "prod_force_virial_a", "prod_force_virial_a_ex", "use_nlist_map",
              "normalize_coord", "copy_coord", "build_nlist", "se_a_descriptor", "se_a_descriptor_grad", "halo_pack",
-             "halo_unpack_add"]
+             "halo_unpack_add", "fit_gemm_i8", "fit_head", "fit_slice_rows"]
     acc = {}
     orig = {}
 
@@ -411,8 +413,9 @@ def per_kernel(args, torch, ops, model, dp, step, L, dev, nloc, esz):
         setattr(ops, n, wrap(n, orig[n]))
     orig_fit = model.energy_and_dy
     orig_fit_split = model.energy_and_dy_split
-    model.energy_and_dy = wrap("fitting_net(GEMMs + glue + descriptor_grad)", orig_fit)
-    model.energy_and_dy_split = wrap("fitting_net(GEMMs + glue + descriptor_grad)", orig_fit_split)
+    umbrella = "fitting_net (total: fit_gemm_i8 + fit_head + fit_slice_rows + se_a_descriptor_grad + torch glue)"
+    model.energy_and_dy = wrap(umbrella, orig_fit)
+    model.energy_and_dy_split = wrap(umbrella, orig_fit_split)
     nsteps = 10
     graph_mode = getattr(dp, "use_graph", False)
     dp.use_graph = False  # the instrumented pass needs real launches (events cannot be timed inside a graph)
@@ -447,9 +450,16 @@ def per_kernel(args, torch, ops, model, dp, step, L, dev, nloc, esz):
     nall = int(st.ext_type.numel())
     raw = float(st.numneigh.sum().item()) / nloc
     F = esz
-    hbm, hbm_src = measured_peaks()
+    peaks, hbm_src = measured_peaks()
+    hbm = float(peaks["hbm_gbs"])
     fma = L.fma_peak(args.dtype, None)
     npr = nreal + nt  # one folded padding entry per table
+    # int8 tensor-core work of the fitting net: every GEMM of the forward and of the input-gradient backward as
+    # NS(NS+1)/2 = 21 exact slice products (csrc/fit_tc.cu), 2 ops per MAC
+    widths = [M * cfg.axis_neuron] + list(cfg.fitting_neuron)
+    fit_mac = sum(a * b for a, b in zip(widths[:-1], widths[1:]))
+    fit_int8_ops = 2.0 * 21 * (2 * fit_mac)
+    int8_peak = 2.0 * float(peaks.get("bf16_tflops_sustained", peaks.get("bf16_tflops", 1400.0)))
     alg = {
         "prod_env_mat_a": ("hbm", (19 * nnei * F + 4 * nnei) + 4 * raw + 3 * F * (1 + nall / nloc)),
         "prod_force_virial_a": ("hbm", (19 * nnei * F + 4 * nnei) + 3 * F + (9 * F if args.atom_virial else 0)),
@@ -457,38 +467,47 @@ def per_kernel(args, torch, ops, model, dp, step, L, dev, nloc, esz):
         "tabulate_sections_fwd": ("fp", 18 * npr * M),
         "tabulate_sections_desc": ("fp", 18 * npr * M),  # the fused descriptor epilogue is not counted
         "tabulate_sections_grad": ("fp", 36 * npr * M),
+        # descriptor backward: reads dE/dD [M*axis] and GR [4*M], writes dE/dGR [4*M]
+        "se_a_descriptor_grad": ("hbm", (M * cfg.axis_neuron + 8 * M) * F),
+        "fit_gemm_i8": ("tensor", fit_int8_ops),
     }
     table = {}
     total = 0.0
     for n, evs in acc.items():
         times = sorted(a.elapsed_time(b) for a, b in evs)
         med = times[len(times) // 2]
-        ms = med * len(evs) / nsteps  # median call x calls per step (robust against allocator hiccups)
+        # median call x calls per step (robust against allocator hiccups); kernels with several call shapes per
+        # step (the six GEMMs of the fitting net) are summed instead
+        ms = sum(times) / nsteps if n.startswith("fit_") else med * len(evs) / nsteps
         table[n] = {"ms_per_step": ms, "calls_per_step": len(evs) / nsteps, "ms_min_call": times[0],
                     "ms_max_call": times[-1]}
-        total += ms
+        if n == umbrella:
+            table[n]["umbrella"] = True  # contains other rows of this table: not part of the shares
+        else:
+            total += ms
     for n, row in table.items():
-        row["share"] = row["ms_per_step"] / total if total > 0 else None
+        row["share"] = None if row.get("umbrella") else (row["ms_per_step"] / total if total > 0 else None)
         if n in alg and row["ms_per_step"] > 0:
             kind, per_atom = alg[n]
             t = row["ms_per_step"] * 1e-3
-            if kind == "hbm":
+            if kind == "tensor":
+                a = per_atom * nloc / t / 1e12
+                row.update(bound="tensor", achieved=a, peak=int8_peak, unit="TOP/s (int8)", frac=a / int8_peak,
+                           alg_int8_ops_per_atom=per_atom, fp64_equivalent_tflops=2.0 * 2 * fit_mac * nloc / t / 1e12,
+                           peak_source=hbm_src + ": 2 x bf16_tflops_sustained (dense int8 runs at twice the bf16 rate on "
+                                                 "B200; the kernel is timed inside a long step)")
+            elif kind == "hbm":
                 a = per_atom * nloc / t / 1e9
                 row.update(bound="hbm", achieved=a, peak=hbm, unit="GB/s", frac=a / hbm, alg_bytes_per_atom=per_atom)
             else:
                 a = per_atom * nloc / t / 1e12
                 row.update(bound="fp64-fma" if args.dtype == "f64" else "fp32-fma", achieved=a, peak=fma,
                            unit="TFLOP/s", frac=a / fma, alg_flops_per_atom=per_atom)
-    # what ncu names as the limiter of each kernel (profiles/r01_ncu_full_v7_summary.csv, 98 304-atom capture)
-    limiter = {
-        "prod_env_mat_a": "l1tex 73 %, issue 54 %, dram 41 %",
-        "tabulate_sections_fwd": "l1tex (shared-memory coefficient stream) 82-84 %, fp64 pipe 33-35 %",
-        "tabulate_sections_desc": "l1tex 72-84 %, fp64 pipe 30-35 %",
-        "tabulate_sections_grad": "l1tex 78-81 %, tensor (DMMA) 37-40 %, fp64 pipe 15-16 %",
-        "se_a_descriptor_grad": "dram 53 %, l1tex 64 %, tensor (DMMA) 29 %",
-        "prod_force_virial_a": "dram 65 % of ncu peak (0.92 of the measured copy bandwidth)",
-    }
-    if args.dtype == "f64":
+    # what ncu names as the limiter of each kernel: profiles/r02_ncu_full_summary.csv (tools/ncu_step_summary.py)
+    lim_path = os.path.join(ROOT, "profiles", "r02_ncu_limiters.json")
+    if args.dtype == "f64" and os.path.exists(lim_path):
+        with open(lim_path) as f:
+            limiter = json.load(f)
         for n, row in table.items():
             if n in limiter:
                 row["ncu_limiter"] = limiter[n]
@@ -497,15 +516,20 @@ def per_kernel(args, torch, ops, model, dp, step, L, dev, nloc, esz):
     roofline = None
     if top:
         r = ours[top]
-        traffic = None
-        if args.dtype == "f64" and top in NCU_DRAM_BYTES_PER_ATOM_F64:
-            traffic = NCU_DRAM_BYTES_PER_ATOM_F64[top] * nloc
-        roofline = {"kernel": top, "bound": r["bound"], "achieved": r["achieved"], "peak": r["peak"], "unit": r["unit"],
-                    "frac": r["frac"], "traffic": traffic,
-                    "traffic_note": "DRAM bytes per step of this operator (ncu --set full, profiles/r01_ncu_full_v6_summary.csv, "
-                                    "scaled per atom)",
-                    "peak_source": hbm_src if r["bound"] == "hbm" else "dpb200_fma_peak measured in this run (burst)",
+        dram, dram_src = ncu_dram_bytes_per_atom()
+        traffic = dram[top] * nloc if (args.dtype == "f64" and top in dram) else None
+        roofline = {"kernel": top, "bound": "tensor" if r["bound"] == "tensor" else ("hbm" if r["bound"] == "hbm" else r["bound"]),
+                    "achieved": r["achieved"], "peak": r["peak"], "unit": r["unit"], "frac": r["frac"], "traffic": traffic,
+                    "traffic_note": ("DRAM bytes per step of this operator, " + dram_src) if traffic is not None else
+                                    "no ncu capture of this kernel is committed for this build",
+                    "peak_source": r.get("peak_source", hbm_src if r["bound"] == "hbm" else
+                                         "dpb200_fma_peak measured in this run (burst); nominal B200 FP64 is ~40 TFLOP/s"),
                     "mean_real_neighbours": nreal, "mean_raw_neighbours": raw}
+        # every operator with a roofline, largest first (the headline object above is the dominant one)
+        roofline["all"] = [dict(kernel=n, ms_per_step=ours[n]["ms_per_step"], bound=ours[n]["bound"],
+                                achieved=ours[n]["achieved"], peak=ours[n]["peak"], unit=ours[n]["unit"],
+                                frac=ours[n]["frac"])
+                           for n in sorted(ours, key=lambda q: -ours[q]["ms_per_step"])]
     return table, roofline
 
 

@@ -193,12 +193,25 @@ class DomainDeepPot(DeepPotB200):
         self.state = None
         numneigh, rows = ops.build_nlist(ext_c, nloc, rc, ext_t, cache=self._cache)
         perm, ranges, inv = self._type_partition(atype)
-        self.state = NeighborState(nloc, ext_t, None, None, numneigh, rows, perm, ranges, type_inv=inv)
+        ref = ops._buf(self._cache, "ref_coord", (nloc, 3), c.dtype, c.device)
+        ref.copy_(c)
+        self.state = NeighborState(nloc, ext_t, None, None, numneigh, rows, perm, ranges, type_inv=inv,
+                                   box=np.array(box, dtype=np.float64).reshape(9).copy(), ref_coord=ref)
         return self.state
+
+    def _any_rank_stale(self, coord, atype, box) -> bool:
+        """The halo plan and the raw list are rebuilt by ALL ranks together: the local staleness test of
+        DeepPotB200 (cell changed, an atom moved more than skin / 2, reuse cap reached) is OR-reduced."""
+        stale = self._list_is_stale(coord, atype, box)
+        if dist.is_initialized() and dist.get_world_size(self.group) > 1:
+            flag = torch.tensor([1 if stale else 0], dtype=torch.int32, device=coord.device)
+            dist.all_reduce(flag, op=dist.ReduceOp.MAX, group=self.group)
+            stale = bool(flag.item())
+        return stale
 
     def eval_device(self, coord, atype, box, atom_virial=False, fused=True):
         st = self.state
-        if st is None or st.ago >= self.nlist_every or st.nloc != atype.numel():
+        if self._any_rank_stale(coord, atype, box):
             st = self.build_neighbors(coord, atype, box)
         c = coord.reshape(-1, 3)
         ext_c = self.halo_forward(c)

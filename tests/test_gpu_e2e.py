@@ -246,3 +246,30 @@ def test_copper_10976_matches_reference_cpu(pkg):
     assert abs(e[0, 0] - we) <= 1e-10 * abs(we)
     assert rel(f[0], wf) <= 1e-10
     assert rel(v[0], wv) <= 1e-10
+
+
+def test_domain_path_on_one_gpu_matches_plain(pkg):
+    """DomainDeepPot with a 1 x 1 x 1 grid: every halo direction is a periodic self-image, so halo_pack, the local
+    exchange and halo_unpack_add (the multi-GPU data path) run on a single GPU and must reproduce DeepPotB200."""
+    from deepmd_kit_b200.domain import DomainDeepPot
+    from deepmd_kit_b200.model import DeepPotB200, SeAConfig, SeAModel
+
+    cfg = SeAConfig()
+    coord, atype, box = g.water_box(2, 0.01)
+    model = SeAModel(cfg, torch.float64, "cuda:0")
+    e0, f0, v0 = DeepPotB200(model, skin=2.0).eval(coord.reshape(1, -1), box.reshape(1, 9), atype)
+    dd = DomainDeepPot(model, (1, 1, 1), skin=2.0)
+    c = torch.as_tensor(coord, device="cuda:0")
+    t = torch.as_tensor(atype, device="cuda:0")
+    e, f, v, ex = dd.eval_device(c, t, box, atom_virial=True)
+    assert dd.plan.nghost > len(atype)  # (rc + skin = 8 A shell of a 24.9 A box: more ghosts than atoms)
+    assert abs(float(e) - e0[0, 0]) <= 1e-10 * abs(e0[0, 0])
+    assert rel(f.cpu().numpy(), f0[0]) <= 1e-10
+    assert rel(v.cpu().numpy(), v0[0]) <= 1e-10
+    assert rel(ex["atom_virial"].reshape(-1, 9).sum(0).cpu().numpy(), v0[0]) <= 1e-9
+    # second step: small displacement, the plan and the list are reused
+    c2 = c + 0.01 * torch.randn_like(c)
+    e2, f2, v2, _ = dd.eval_device(c2, t, box)
+    e3, f3, v3 = DeepPotB200(model, skin=2.0).eval(c2.cpu().numpy().reshape(1, -1), box.reshape(1, 9), atype)
+    assert dd.state.ago == 2
+    assert rel(f2.cpu().numpy(), f3[0]) <= 1e-10

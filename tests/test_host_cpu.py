@@ -227,3 +227,24 @@ def test_bench_reference_arm_contract():
     assert d["value"] > 0 and d["cpu_baseline"]["value"] == d["value"] and d["cpu_baseline"]["cores"] >= 1
     assert d["e2e"] == {"value": d["value"], "unit": d["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     assert d["config"]["natoms"] == 1536000 and "workload" in d["config"]
+
+
+def test_reference_arm_model_equals_product_model(pkg):
+    """bench.py --impl reference builds its model data without importing the product (oracle/refmodel.py): weights,
+    statistics and tables must be bit-identical to the product's SeAModel, or the two arms would time different work."""
+    from deepmd_kit_b200.model import SeAConfig, SeAModel
+    from oracle.refmodel import RefWaterModel
+
+    a = SeAModel(SeAConfig(), torch.float64, "cpu")
+    b = RefWaterModel(torch.float64)
+    assert torch.equal(a.davg, b.davg) and torch.equal(a.dstd, b.dstd)
+    for ta, tb in zip(a.tables, b.tables):
+        assert torch.equal(ta, tb)
+    for ia, ib in zip(a.infos, b.infos):
+        assert torch.equal(ia, ib)
+    for fa, fb in zip(a.fit, b.fit):
+        for (w0, b0, i0), (w1, b1, i1) in zip(fa.layers, fb.layers):
+            assert torch.equal(w0, w1) and torch.equal(b0, b1) and torch.equal(i0, i1)
+        assert torch.equal(fa.head[0], fb.head[0]) and torch.equal(fa.head[1], fb.head[1])
+    x = torch.randn(7, 1600, dtype=torch.float64)
+    assert torch.equal(fa(x), fb(x))
