@@ -39,9 +39,10 @@ def parse():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--dtype", default="f64", choices=["f64", "f32"])
-    ap.add_argument("--workload", default="water", choices=["water", "copper"],
+    ap.add_argument("--workload", default="water", choices=["water", "copper", "se_atten"],
                     help="water: BASELINE config 2 (the metric's configuration); copper: config 3 (FCC, sel 512, rcut 8; "
-                         "--ncopy = conventional cells per axis, 100 = 4 M atoms; 1 GPU only, evaluated in atom slabs)")
+                         "--ncopy = conventional cells per axis, 100 = 4 M atoms; 1 GPU only, evaluated in atom slabs); "
+                         "se_atten: config 5 (DPA-1 se_atten_v2 strip / smooth, attn_layer 0, sel 120; --ncopy 14 = 526 848 atoms)")
     ap.add_argument("--ncopy", type=int, default=20, help="replicas of the 192-atom frame per axis and per GPU")
     ap.add_argument("--jitter", type=float, default=0.01)
     ap.add_argument("--cpu-ncopy", type=int, default=4, help="replicas per axis of the bounded CPU sample")
@@ -247,9 +248,13 @@ def run_ours(args):
         if world != 1:
             raise SystemExit("bench.py --workload copper runs on one GPU")
         cfg = SeAConfig(**COPPER_CONFIG)
+    elif args.workload == "se_atten":
+        from deepmd_kit_b200.atten import SeAttenConfig, SeAttenModel
+
+        cfg = SeAttenConfig()
     else:
         cfg = SeAConfig()
-    model = SeAModel(cfg, dtype, dev)
+    model = SeAttenModel(cfg, dtype, dev) if args.workload == "se_atten" else SeAModel(cfg, dtype, dev)
     esz = 8 if args.dtype == "f64" else 4
 
     if world == 1:
@@ -361,11 +366,15 @@ def run_ours(args):
                 "workload": (f"se_e2_a compressed water, {natoms_total}-atom box ({args.ncopy}^3 replicas of the 192-atom "
                              f"frame per GPU, Gaussian jitter {args.jitter} A), {args.dtype}, {world}xB200")
                 if args.workload == "water" else
+                (f"DPA-1 se_atten_v2 (strip, smooth, attn_layer 0, sel 120) compressed water, {natoms_total}-atom box "
+                 f"({args.ncopy}^3 replicas of the 192-atom frame per GPU, jitter {args.jitter} A), {args.dtype}, {world}xB200")
+                if args.workload == "se_atten" else
                 (f"se_e2_a compressed copper FCC, {natoms_total} atoms ({args.ncopy}^3 cells, a0 3.615 A, jitter 0.05 A), "
                  f"{args.dtype}, 1xB200, evaluated in "
                  f"{1 if dp.state.chunks is None else len(dp.state.chunks)} atom slab(s)"),
                 "natoms": natoms_total, "rcut": cfg.rcut, "rcut_smth": cfg.rcut_smth, "sel": list(cfg.sel),
                 "neuron": list(cfg.neuron), "axis_neuron": cfg.axis_neuron, "fitting_neuron": list(cfg.fitting_neuron),
+                "bench_workload": args.workload,
                 "table": "dp-compress restatement, stride 0.01/0.1, extrapolate 5, random-init weights (seed 1)",
                 "skin": 2.0, "nlist_every": 10, "parallelism": parallelism,
                 "cuda_graph": bool(getattr(dp, "use_graph", False)),
@@ -394,7 +403,9 @@ def per_kernel(args, torch, ops, model, dp, step, L, dev, nloc, esz):
     names = ["prod_env_mat_a", "tabulate_sections_fwd", "tabulate_sections_desc", "tabulate_sections_grad",
              "prod_force_virial_a", "prod_force_virial_a_ex", "use_nlist_map",
              "normalize_coord", "copy_coord", "build_nlist", "se_a_descriptor", "se_a_descriptor_grad", "halo_pack",
-             "halo_unpack_add", "fit_gemm_i8", "fit_head", "fit_slice_rows"]
+             "halo_unpack_add", "fit_gemm_i8", "fit_head", "fit_slice_rows", "tabulate_fusion_se_a",
+             "tabulate_fusion_se_a_grad", "split_i8_rows", "tabulate_fusion_se_atten_gate",
+             "tabulate_fusion_se_atten_gate_grad"]
     acc = {}
     orig = {}
 
@@ -411,11 +422,13 @@ def per_kernel(args, torch, ops, model, dp, step, L, dev, nloc, esz):
     for n in names:
         orig[n] = getattr(ops, n)
         setattr(ops, n, wrap(n, orig[n]))
-    orig_fit = model.energy_and_dy
-    orig_fit_split = model.energy_and_dy_split
     umbrella = "fitting_net (total: fit_gemm_i8 + fit_head + fit_slice_rows + se_a_descriptor_grad + torch glue)"
-    model.energy_and_dy = wrap(umbrella, orig_fit)
-    model.energy_and_dy_split = wrap(umbrella, orig_fit_split)
+    has_fit = hasattr(model, "energy_and_dy")
+    if has_fit:
+        orig_fit = model.energy_and_dy
+        orig_fit_split = model.energy_and_dy_split
+        model.energy_and_dy = wrap(umbrella, orig_fit)
+        model.energy_and_dy_split = wrap(umbrella, orig_fit_split)
     nsteps = 10
     graph_mode = getattr(dp, "use_graph", False)
     dp.use_graph = False  # the instrumented pass needs real launches (events cannot be timed inside a graph)
@@ -430,8 +443,9 @@ def per_kernel(args, torch, ops, model, dp, step, L, dev, nloc, esz):
     finally:
         for n in names:
             setattr(ops, n, orig[n])
-        model.energy_and_dy = orig_fit
-        model.energy_and_dy_split = orig_fit_split
+        if has_fit:
+            model.energy_and_dy = orig_fit
+            model.energy_and_dy_split = orig_fit_split
         dp.use_graph = graph_mode
     nlist = out[3]["nlist"]
     cfg = model.cfg
@@ -445,7 +459,7 @@ def per_kernel(args, torch, ops, model, dp, step, L, dev, nloc, esz):
         del nl0
     else:
         nreal = float((nlist >= 0).sum().item()) / nloc
-    nnei, M, nt = cfg.nnei, model.M, cfg.ntypes
+    nnei, M, nt = cfg.nnei, model.M, len(cfg.sel)  # nt = tables per atom (type sections)
     st = dp.state
     nall = int(st.ext_type.numel())
     raw = float(st.numneigh.sum().item()) / nloc
@@ -456,7 +470,7 @@ def per_kernel(args, torch, ops, model, dp, step, L, dev, nloc, esz):
     npr = nreal + nt  # one folded padding entry per table
     # int8 tensor-core work of the fitting net: every GEMM of the forward and of the input-gradient backward as
     # NS(NS+1)/2 = 21 exact slice products (csrc/fit_tc.cu), 2 ops per MAC
-    widths = [M * cfg.axis_neuron] + list(cfg.fitting_neuron)
+    widths = [getattr(model, "dim_in", M * cfg.axis_neuron)] + list(cfg.fitting_neuron)
     fit_mac = sum(a * b for a, b in zip(widths[:-1], widths[1:]))
     fit_int8_ops = 2.0 * 21 * (2 * fit_mac)
     int8_peak = 2.0 * float(peaks.get("bf16_tflops_sustained", peaks.get("bf16_tflops", 1400.0)))
@@ -471,6 +485,13 @@ def per_kernel(args, torch, ops, model, dp, step, L, dev, nloc, esz):
         "se_a_descriptor_grad": ("hbm", (M * cfg.axis_neuron + 8 * M) * F),
         "fit_gemm_i8": ("tensor", fit_int8_ops),
     }
+    if args.workload == "se_atten":
+        # the gated operator streams the materialised two_embed rows of the real neighbours (reference op signature)
+        alg["tabulate_fusion_se_a"] = ("hbm", nreal * M * F + 5 * nnei * F + 4 * M * F)
+        alg["tabulate_fusion_se_a_grad"] = ("hbm", 2 * nreal * M * F + 10 * nnei * F + 4 * M * F)
+        # pair-indexed gate: no two_embed stream, the op is bound like the plain se_a table kernels
+        alg["tabulate_fusion_se_atten_gate"] = ("fp", 20 * npr * M)
+        alg["tabulate_fusion_se_atten_gate_grad"] = ("fp", 42 * npr * M)
     table = {}
     total = 0.0
     for n, evs in acc.items():

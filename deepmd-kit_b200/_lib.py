@@ -23,10 +23,13 @@ _T = {"p": C.c_void_p, "i": C.c_int, "l": C.c_longlong, "f": C.c_float, "z": C.c
 # name -> argument codes (p pointer, i int, l long long, f float, z size_t); `{s}` = f32 | f64
 _SIGS = {
     "prod_env_mat_a_{s}": "pppp ppppppp ii pp iii ff pi pz p",
+    "prod_env_mat_a_ex_{s}": "pppp ppppppp ii pp i iii ff pi pz p",
     "format_nlist_{s}": "p pp pppp ii iii f pi pz p",
     "tabulate_fusion_se_a_{s}": "pppppp iiii p",
     "tabulate_fusion_se_a_grad_{s}": "ppp pp ppp p iiii p",
     "tabulate_fusion_se_a_grad_grad_{s}": "p pp ppp ppp iiii p",
+    "tabulate_fusion_se_atten_gate_{s}": "ppppp ppp iiii p",
+    "tabulate_fusion_se_atten_gate_grad_{s}": "ppp pp pp ppp p iiii p",
     "tabulate_fusion_se_a_ex_{s}": "ppp pli pl p iiiii p",
     "tabulate_fusion_se_a_grad_ex_{s}": "ppp pp pli pl p p iiii p",
     "prod_force_a_{s}": "pppp iiii p",

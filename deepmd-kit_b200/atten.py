@@ -1,0 +1,268 @@
+"""Compressed se_atten (DPA-1, `se_atten_v2`: strip-mode type embedding, smooth, attn_layer = 0) energy / force /
+virial evaluation — BASELINE config 5, examples/water/se_atten_compressible/input.json.
+
+Model path of deepmd/pt/model/descriptor/se_atten.py:892-1016 with geometric + type-embedding compression
+(dpa1.py:640-700), driven through the dpb200 operators:
+
+    prod_env_mat_a with ONE type-agnostic section (sel = 120, neighbours ordered by distance only: f_type = 0)
+    sw(r_ij)                                    smooth switch of every neighbour (se_atten.py: `sw`)
+    two_embed = tt_full[center*(nt+1) + nei] * sw      type-pair gate, tt_full = strip net on the type embeddings
+                                                       ((ntypes+1)^2 x M table, `type_embd_data` se_atten.py:666-720)
+    moment = tabulate_fusion_se_atten(table, em_x, em, two_embed) / nnei        g * (1 + two_embed) folded in the op
+    D = moment^T moment[:, :axis]  ++ type embedding of the centre atom   (dpa1.py:769-770 concat_output_tebd)
+    one fitting net for all types (mixed types) + bias_atom_e[type]
+    backward: tabulate_fusion_se_atten_grad -> dE/d(em) (prod_force_a / prod_virial_a) and dE/d(two_embed) ->
+    dE/d(sw) -> the pair force through the switch function.
+
+`SeAttenModel` offers the interface DeepPotB200 expects from a model (cfg, evaluate, bytes_per_atom), so the same
+facade, neighbour-list management and CUDA-graph replay serve both descriptors.
+"""
+from __future__ import annotations
+
+import math
+from dataclasses import dataclass
+from typing import Sequence
+
+import numpy as np
+import torch
+
+from . import ops
+from .compress import EmbeddingNet, build_table, env_mat_range
+from .model import FittingNet
+
+
+@dataclass
+class SeAttenConfig:
+    """examples/water/se_atten_compressible/input.json."""
+    ntypes: int = 2
+    nsel: int = 120
+    rcut: float = 6.0
+    rcut_smth: float = 0.5
+    neuron: Sequence[int] = (25, 50, 100)
+    axis_neuron: int = 16
+    tebd_dim: int = 8
+    fitting_neuron: Sequence[int] = (240, 240, 240)
+    fitting_resnet_dt: bool = True
+    stats: Sequence[Sequence[float]] = ((0.05033, 0.13984, 0.08580), (0.04810, 0.12388, 0.07672))
+    seed: int = 1
+    stride0: float = 0.01
+    stride1: float = 0.1
+    extrapolate: float = 5.0
+    min_nbor_dist: float = 0.9
+
+    @property
+    def sel(self):
+        return (self.nsel,)
+
+    @property
+    def nnei(self) -> int:
+        return int(self.nsel)
+
+    @property
+    def sec(self):
+        return [0, int(self.nsel)]
+
+
+def _mlp_init(widths, seed):
+    g = torch.Generator().manual_seed(seed)
+    ws, bs = [], []
+    for n_in, n_out in zip(widths[:-1], widths[1:]):
+        ws.append(torch.empty(n_in, n_out, dtype=torch.float64).normal_(0.0, 1.0 / math.sqrt(n_in + n_out), generator=g))
+        bs.append(torch.empty(n_out, dtype=torch.float64).normal_(0.0, 1.0, generator=g))
+    return ws, bs
+
+
+def _mlp_tanh_resnet(x, ws, bs):
+    """tanh MLP with the embedding-net skip rules (same width: + x, doubled width: + concat(x, x))."""
+    for w, b in zip(ws, bs):
+        y = torch.tanh(x @ w + b)
+        if w.shape[1] == w.shape[0]:
+            y = y + x
+        elif w.shape[1] == 2 * w.shape[0]:
+            y = y + torch.cat([x, x], 1)
+        x = y
+    return x
+
+
+def switch_and_derivative(r: torch.Tensor, rmin: float, rmax: float):
+    """spline5 switch (source/lib/include/switcher.h:61-84) and d sw / d r, elementwise."""
+    uu = ((r - rmin) / (rmax - rmin)).clamp(0.0, 1.0)
+    sw = uu * uu * uu * (-6.0 * uu * uu + 15.0 * uu - 10.0) + 1.0
+    dsw = (3.0 * uu * uu * (-6.0 * uu * uu + 15.0 * uu - 10.0) + uu * uu * uu * (-12.0 * uu + 15.0)) / (rmax - rmin)
+    inside = (r >= rmin) & (r < rmax)
+    sw = torch.where(r < rmin, torch.ones_like(sw), torch.where(inside, sw, torch.zeros_like(sw)))
+    dsw = torch.where(inside, dsw, torch.zeros_like(dsw))
+    return sw, dsw
+
+
+class SeAttenModel:
+    """Random-init compressed se_atten_v2 model (weights of the named architecture; geometric table through the
+    restated `dp compress`, type-pair table through the strip net)."""
+
+    def __init__(self, cfg: SeAttenConfig, dtype=torch.float64, device="cuda"):
+        self.cfg = cfg
+        self.dtype = dtype
+        self.device = torch.device(device)
+        nt, nnei = cfg.ntypes, cfg.nnei
+        davg = np.zeros((nt, nnei, 4))
+        dstd = np.ones((nt, nnei, 4))
+        for t, (a0, s0, s1) in enumerate(cfg.stats):
+            davg[t, :, 0] = a0
+            dstd[t, :, 0] = s0
+            dstd[t, :, 1:] = s1
+        self.davg = torch.as_tensor(davg.reshape(nt, -1), dtype=dtype, device=self.device)
+        self.dstd = torch.as_tensor(dstd.reshape(nt, -1), dtype=dtype, device=self.device)
+        # one type-agnostic geometric embedding net -> one table over the range of all centre types
+        self.embed = EmbeddingNet(cfg.neuron, cfg.seed)
+        lower, upper = env_mat_range(davg[:, 0, :], dstd[:, 0, :], cfg.min_nbor_dist, cfg.rcut_smth, cfg.rcut)
+        ll, uu = float(lower.min()), float(upper.max())
+        self.table64 = build_table(self.embed, ll, uu, cfg.stride0, cfg.stride1, cfg.extrapolate)
+        self.table = self.table64.to(self.device, dtype).contiguous()
+        self.info = torch.tensor([ll, uu, uu * cfg.extrapolate, cfg.stride0, cfg.stride1, -1.0], dtype=dtype)
+        self.M = int(cfg.neuron[-1])
+        # type embedding (ntypes + 1 rows, the last one is the zero padding row) and the two-side strip net:
+        # tt_full[center * (nt + 1) + nei] = strip([tebd[nei], tebd[center]])   (se_atten.py:698-711)
+        g = torch.Generator().manual_seed(cfg.seed + 7)
+        tebd = torch.zeros(nt + 1, cfg.tebd_dim, dtype=torch.float64)
+        tebd[:nt] = torch.empty(nt, cfg.tebd_dim, dtype=torch.float64).normal_(0.0, 1.0, generator=g)
+        ws, bs = _mlp_init([2 * cfg.tebd_dim] + list(cfg.neuron), cfg.seed + 13)
+        nei = tebd.view(1, nt + 1, -1).expand(nt + 1, nt + 1, -1)
+        cen = tebd.view(nt + 1, 1, -1).expand(nt + 1, nt + 1, -1)
+        tt = _mlp_tanh_resnet(torch.cat([nei, cen], -1).reshape(-1, 2 * cfg.tebd_dim), ws, bs)
+        self.tebd = tebd.to(self.device, dtype)
+        self.tt_full = tt.to(self.device, dtype).contiguous()  # [(nt+1)^2, M]
+        # fitting net input = [D (M*axis), tebd(centre)] zero-padded to a multiple of 16 (the int8 tensor-core
+        # GEMMs read 16-byte aligned operand rows; the padded inputs are zeros, so their weight rows are inert)
+        self.dim_d = self.M * cfg.axis_neuron
+        self.dim_in = (self.dim_d + cfg.tebd_dim + 15) // 16 * 16
+        self.fit = FittingNet(self.dim_in, cfg.fitting_neuron, cfg.fitting_resnet_dt, cfg.seed + 101, dtype, self.device)
+        self.bias_atom_e = torch.zeros(nt, dtype=dtype, device=self.device)
+        self.fit_chunk = 1 << 17
+        # two_embed [atoms * nnei, M] is 96 KB per atom in fp64 (50 GB for the 526 848-atom box): the gated table
+        # operator runs over slabs of this many centre atoms, the gate being recomputed for the backward
+        self.tab_chunk = 1 << 16
+        # default: the pair-indexed gate entry points (dpb200_tabulate_fusion_se_atten_gate*), which form
+        # tt_full[pair] * sw inside the kernel; False = the reference-schema op fed with the materialised tensor
+        self.use_gate = True
+        self.nslice = 6
+        self.use_tc = bool(dtype == torch.float64 and self.device.type == "cuda" and self.fit.prepare_tc(self.nslice))
+
+    def bytes_per_atom(self) -> int:
+        """Per-atom intermediates alive across the whole evaluation (two_embed and its gradient are only ever
+        materialised for one slab of `tab_chunk` atoms at a time)."""
+        F = 8 if self.dtype == torch.float64 else 4
+        nnei, M = self.cfg.nnei, self.M
+        return int(nnei * (4 + 12 + 3 + 4 + 3) * F + nnei * 4 + 3 * 4 * M * F)
+
+    def gate_scalars(self, ext_type, nlist, rij, a, b):
+        """Centre atoms a..b-1: (pair int32 [(b-a), nnei] row of tt_full, sw, sw', r) of every neighbour slot."""
+        cfg = self.cfg
+        nt1 = cfg.ntypes + 1
+        nl = nlist[a:b]
+        pad = nl < 0
+        nei_t = ext_type.to(torch.int64)[nl.clamp_min(0).to(torch.int64)]
+        nei_t = torch.where(pad | (nei_t < 0), torch.full_like(nei_t, cfg.ntypes), nei_t)
+        cen_t = ext_type[a:b].to(torch.int64)
+        cen_t = torch.where(cen_t < 0, torch.full_like(cen_t, cfg.ntypes), cen_t)
+        pair = (cen_t.view(-1, 1) * nt1 + nei_t)
+        r = rij[a:b].reshape(b - a, cfg.nnei, 3).norm(dim=-1)
+        sw, dsw = switch_and_derivative(r, cfg.rcut_smth, cfg.rcut)
+        sw = torch.where(pad, torch.zeros_like(sw), sw)
+        dsw = torch.where(pad, torch.zeros_like(dsw), dsw)
+        return pair, sw, dsw, r
+
+    def gate(self, ext_type, nlist, rij, a, b):
+        """Materialised two_embed [(b-a)*nnei, M] = tt_full[pair] * sw (the reference op's operand)."""
+        pair, sw, dsw, r = self.gate_scalars(ext_type, nlist, rij, a, b)
+        pair = pair.reshape(-1)
+        two = self.tt_full.index_select(0, pair) * sw.reshape(-1, 1)
+        return two, pair, dsw, r
+
+    def evaluate(self, ext_coord, ext_type, numneigh, rows, mapping, nloc, type_perm=None, type_ranges=None,
+                 atom_virial=False, fused=True, type_inv=None):
+        """One force evaluation on an extended system: (E, force[n_out, 3], virial[9], extras)."""
+        cfg = self.cfg
+        nall = ext_type.numel()
+        nnei, M = cfg.nnei, self.M
+        f_type = torch.zeros_like(ext_type)  # one section: the list is ordered by distance only
+        em, dv, rij, nlist = ops.prod_env_mat_a(ext_coord.reshape(-1), ext_type, numneigh, rows, self.davg, self.dstd, nloc,
+                                                nall, cfg.rcut, cfg.rcut_smth, cfg.sec, f_type=f_type)
+        em3 = em.reshape(nloc, nnei, 4)
+        if self.use_gate:
+            pair, sw, dsw, r = self.gate_scalars(ext_type, nlist, rij, 0, nloc)
+            pair32 = pair.to(torch.int32)
+            em_x = em3[:, :, 0].reshape(-1, 1).contiguous()
+            xyz = ops.tabulate_fusion_se_atten_gate(self.table, self.info, em_x, em3, self.tt_full, pair32, sw, M)
+        else:
+            xyz = torch.empty((nloc, 4, M), dtype=self.dtype, device=em.device)
+            for a in range(0, nloc, self.tab_chunk):
+                b = min(nloc, a + self.tab_chunk)
+                two, _, _, _ = self.gate(ext_type, nlist, rij, a, b)
+                em_xc = em3[a:b, :, 0].reshape(-1, 1).contiguous()
+                xyz[a:b] = ops.tabulate_fusion_se_a(self.table, self.info, em_xc, em3[a:b], M, two_embed=two, is_sorted=True)
+                del two
+        # descriptor + centre type embedding -> fitting net -> dE/dD
+        inv = 1.0 / nnei
+        ctype = ext_type[:nloc].to(torch.int64)
+        ctype_e = torch.where(ctype < 0, torch.full_like(ctype, cfg.ntypes), ctype)
+        e_atom = torch.empty(nloc, dtype=self.dtype, device=em.device)
+        dy = torch.empty_like(xyz)
+        for c0 in range(0, nloc, self.fit_chunk):
+            c1 = min(nloc, c0 + self.fit_chunk)
+            g1 = torch.zeros((c1 - c0, self.dim_in), dtype=self.dtype, device=em.device)
+            g1[:, :self.dim_d] = ops.se_a_descriptor(xyz[c0:c1], cfg.axis_neuron, inv)
+            g1[:, self.dim_d:self.dim_d + cfg.tebd_dim] = self.tebd.index_select(0, ctype_e[c0:c1])
+            if self.use_tc:
+                xs, ex = ops.split_i8_rows(g1, self.nslice)
+                e, gd = self.fit.forward_backward_tc(xs, ex, c1 - c0)
+            else:
+                e, gd = self.fit.forward_backward(g1)
+            e_atom[c0:c1] = e + self.bias_atom_e.index_select(0, ctype_e[c0:c1].clamp_max(cfg.ntypes - 1))
+            dy[c0:c1] = ops.se_a_descriptor_grad(gd[:, :self.dim_d].contiguous(), xyz[c0:c1], cfg.axis_neuron, inv)
+            del g1, gd
+        # dE/d(sw_ij) = sum_k dE/d(two_embed)_ijk * tt_full[pair]_k ; pair force through the switch:
+        # dE/dr_j = q * sw'(r) * (r_j - r_i) / r  (and the opposite on the centre atom)
+        if self.use_gate:
+            gx, gem, q = ops.tabulate_fusion_se_atten_gate_grad(self.table, self.info, em_x, em3, self.tt_full, pair32, sw,
+                                                                dy, M)
+            net_deriv = gem.reshape(nloc, nnei, 4)
+            net_deriv[:, :, 0] += gx.reshape(nloc, nnei)
+            coef = torch.where(r > 0, q * dsw / r.clamp_min(1e-30), torch.zeros_like(q))
+            vec = coef.unsqueeze(-1) * rij.reshape(nloc, nnei, 3)  # dE/dr_j of the switch path
+        else:
+            net_deriv = torch.empty((nloc, nnei, 4), dtype=self.dtype, device=em.device)
+            vec = torch.empty((nloc, nnei, 3), dtype=self.dtype, device=em.device)
+            for a in range(0, nloc, self.tab_chunk):
+                b = min(nloc, a + self.tab_chunk)
+                two, pair, dsw, r = self.gate(ext_type, nlist, rij, a, b)
+                em_xc = em3[a:b, :, 0].reshape(-1, 1).contiguous()
+                gx, gem, gtwo = ops.tabulate_fusion_se_a_grad(self.table, self.info, em_xc, em3[a:b], dy[a:b], M,
+                                                              two_embed=two, is_sorted=True)
+                nd = gem.reshape(b - a, nnei, 4)
+                nd[:, :, 0] += gx.reshape(b - a, nnei)
+                net_deriv[a:b] = nd
+                q = (gtwo * self.tt_full.index_select(0, pair)).sum(1).reshape(b - a, nnei)
+                coef = torch.where(r > 0, q * dsw / r.clamp_min(1e-30), torch.zeros_like(q))
+                vec[a:b] = coef.unsqueeze(-1) * rij[a:b].reshape(b - a, nnei, 3)
+                del gtwo, two, gem, gx
+        if mapping is not None:
+            ops.use_nlist_map(nlist, mapping)
+            n_out = nloc
+        else:
+            n_out = nall
+        force, virial, av = ops.prod_force_virial_a(net_deriv.reshape(nloc, -1), dv, rij, nlist, nloc, n_out, nnei,
+                                                    atom_virial=atom_virial)
+        force = force.reshape(-1, 3)
+        idx = nlist.clamp_min(0).to(torch.int64).reshape(-1)
+        force.index_add_(0, idx, -vec.reshape(-1, 3))  # (padded slots carry vec = 0)
+        force[:nloc] += vec.sum(1)
+        # virial of the switch path: - dE/dr_j (x) r_ij per pair (symmetric: the force is along r_ij)
+        virial = virial - torch.einsum("pi,pj->ij", vec.reshape(-1, 3), rij.reshape(-1, 3)).reshape(9)
+        if atom_virial and av is not None:
+            av = av.reshape(-1, 9)
+            for a in range(0, nloc, self.tab_chunk):
+                b = min(nloc, a + self.tab_chunk)
+                w = -(vec[a:b].reshape(-1, 3, 1) * rij[a:b].reshape(-1, 1, 3))
+                av.index_add_(0, idx[a * nnei:b * nnei], w.reshape(-1, 9))
+            av = av.reshape(-1)
+        return e_atom.sum(), force, virial, dict(atom_energy=e_atom, atom_virial=av, nlist=nlist)

@@ -411,7 +411,7 @@ int launch_env(FP* em, FP* em_deriv, FP* rij, int* nlist, const FP* coord, const
                const int* const* firstneigh, const int* rows, int row_stride, int max_nbor_size,
                const FP* avg, const FP* std_, int nloc, int nall, int nframes, float rcut,
                float rcut_smth, const int* sec, int nsec, void* workspace, size_t workspace_bytes,
-               cudaStream_t stream) {
+               cudaStream_t stream, int ntypes_center = 0) {
   DPB_REQUIRE(nsec >= 2 && nsec - 1 <= DPB200_MAX_TYPES, "prod_env_mat_a: 1 <= ntypes <= 128 required");
   DPB_REQUIRE(nloc >= 0 && nall >= nloc && nframes >= 1, "prod_env_mat_a: need nall >= nloc >= 0, nframes >= 1");
   DPB_REQUIRE(nall <= DPB200_MAX_NALL, "prod_env_mat_a: nall exceeds 2^26 (index bits of the sort key)");
@@ -423,7 +423,10 @@ int launch_env(FP* em, FP* em_deriv, FP* rij, int* nlist, const FP* coord, const
   const long long nrows = (long long)nframes * nloc;
   if (nrows == 0 || nnei == 0) return DPB200_OK;
   DPB_REQUIRE(numneigh != nullptr && (firstneigh != nullptr || rows != nullptr), "prod_env_mat_a: neighbour list pointers are null");
-  const EnvWorkspace w = env_workspace(ntypes, nnei, (long long)nframes * nall, sizeof(FP));
+  // rows of avg / std = centre-atom types; more than the sections when the list is formatted with a coarser
+  // f_type (se_atten: ONE distance-ordered section, statistics per real centre type)
+  const int ntc = ntypes_center > 0 ? ntypes_center : ntypes;
+  const EnvWorkspace w = env_workspace(ntc, nnei, (long long)nframes * nall, sizeof(FP));
   DPB_REQUIRE(workspace != nullptr && workspace_bytes >= w.total, "prod_env_mat_a: workspace too small (see dpb200_prod_env_mat_a_workspace_bytes)");
   DPB_REQUIRE((reinterpret_cast<uintptr_t>(workspace) & 255) == 0, "prod_env_mat_a: workspace must be 256-byte aligned");
 
@@ -437,7 +440,7 @@ int launch_env(FP* em, FP* em_deriv, FP* rij, int* nlist, const FP* coord, const
     DPB_REQUIRE(avg != nullptr && std_ != nullptr, "prod_env_mat_a: avg/std are null");
     DPB_REQUIRE(((reinterpret_cast<uintptr_t>(avg) | reinterpret_cast<uintptr_t>(em)) & 15) == 0,
                 "prod_env_mat_a: avg and em must be 16-byte aligned");
-    const int ntab = ntypes * nnei * 4;
+    const int ntab = ntc * nnei * 4;
     k_norm_tables<FP><<<ceil_div(ntab, 256), 256, 0, stream>>>(inv_std, pad, avg, std_, ntab);
   }
 
@@ -513,6 +516,20 @@ size_t dpb200_prod_env_mat_a_workspace_bytes(int ntypes, int nnei, int nall, int
                                         numneigh, firstneigh, rows, row_stride, max_nbor_size,     \
                                         avg, std, nloc, nall, nframes, rcut, rcut_smth, sec, nsec, \
                                         workspace, workspace_bytes, (cudaStream_t)stream);         \
+  }                                                                                                \
+  int dpb200_prod_env_mat_a_ex_##SUF(FP* em, FP* em_deriv, FP* rij, int* nlist, const FP* coord,   \
+                                     const int* type, const int* f_type, const int* ilist,         \
+                                     const int* numneigh, const int* const* firstneigh,            \
+                                     const int* rows, int row_stride, int max_nbor_size,           \
+                                     const FP* avg, const FP* std, int ntypes_center, int nloc,    \
+                                     int nall, int nframes, float rcut, float rcut_smth,           \
+                                     const int* sec, int nsec, void* workspace,                    \
+                                     size_t workspace_bytes, dpb200_stream_t stream) {             \
+    return dpb200::launch_env<FP, true>(em, em_deriv, rij, nlist, coord, type, f_type, ilist,      \
+                                        numneigh, firstneigh, rows, row_stride, max_nbor_size,     \
+                                        avg, std, nloc, nall, nframes, rcut, rcut_smth, sec, nsec, \
+                                        workspace, workspace_bytes, (cudaStream_t)stream,          \
+                                        ntypes_center);                                            \
   }                                                                                                \
   int dpb200_format_nlist_##SUF(int* nlist, const FP* coord, const int* type, const int* ilist,    \
                                 const int* numneigh, const int* const* firstneigh,                 \

@@ -56,6 +56,11 @@ struct TabParams {
   const FP* em;
   long long ldem_i;
   const FP* two;  // [nloc][nnei][M] or null
+  // se_atten strip gate without the materialised two_embed: two_embed[i][j][k] = gate_tt[gate_pair[i][j]][k] * gate_sw[i][j]
+  const FP* gate_tt;     // [(ntypes+1)^2][M] type-pair table, or null
+  const int* gate_pair;  // [nloc][nnei]
+  const FP* gate_sw;     // [nloc][nnei]
+  FP* gate_q;            // backward: dE/d(gate_sw) [nloc][nnei]
   int nloc, nnei, M, is_sorted, accumulate, vec_ok;
   int Mc;  // channels per CTA slice (forward: gridDim.y slices; backward: Mc == M)
   int H;   // hot rows kept in shared memory
@@ -754,7 +759,7 @@ __global__ void __launch_bounds__(512) k_tab_fwd(const __grid_constant__ TabPara
           if (jp < nproc) ring_issue(ring, Mp, p.two, i * p.nnei + j0 + jp, jp, p.M, lane);
           __pipeline_commit();
         }
-      } else if (TWO) {
+      } else if (TWO && p.two) {
         for (int jp = 0; jp < kTwoAhead && jp < nproc; ++jp) prefetch_two(p.two, i * p.nnei + j0 + jp, p.M, lane);
       }
       for (int jj = 0; jj < nproc; ++jj) {
@@ -765,8 +770,16 @@ __global__ void __launch_bounds__(512) k_tab_fwd(const __grid_constant__ TabPara
           __pipeline_commit();
           __pipeline_wait_prior(kRing - 1);  // the group of row jj has landed
           __syncwarp();
-        } else if (TWO && jj + kTwoAhead < nproc) {
+        } else if (TWO && p.two && jj + kTwoAhead < nproc) {
           prefetch_two(p.two, i * p.nnei + j0 + jj + kTwoAhead, p.M, lane);
+        }
+        // pair-indexed gate: one table row index and one switch value per neighbour (broadcast loads)
+        const FP* __restrict__ gate_row = nullptr;
+        FP gate_s = (FP)0.;
+        if (TWO && p.gate_tt) {
+          const long long gj = i * p.nnei + j0 + jj;
+          gate_row = p.gate_tt + (long long)p.gate_pair[gj] * p.M;
+          gate_s = p.gate_sw[gj];
         }
         const Rec<FP>& r = rec[jj];
         const int row = r.idx;
@@ -821,7 +834,8 @@ __global__ void __launch_bounds__(512) k_tab_fwd(const __grid_constant__ TabPara
             for (int m = 0; m < 4; ++m) acc[m][c] += g * h[m] + sgl * e[m];
           } else {
             if (TWO) {
-              const FP t = ring_on ? ring[(jj % kRing) * Mp + kc[c]] : p.two[two_off + kc[c]];
+              const FP t = gate_row ? gate_row[kc[c]] * gate_s
+                                    : (ring_on ? ring[(jj % kRing) * Mp + kc[c]] : p.two[two_off + kc[c]]);
               g = g * t + g;
             }
 #pragma unroll
@@ -939,20 +953,21 @@ __global__ void __launch_bounds__(384) k_tab_grad(const __grid_constant__ TabPar
         if (jp < nproc) ring_issue(ring, Mp, p.two, i * p.nnei + j0 + jp, jp, M, lane);
         __pipeline_commit();
       }
-    } else if (TWO) {
+    } else if (TWO && p.two) {
       for (int jp = 0; jp < kTwoAhead && jp < nproc; ++jp) prefetch_two(p.two, i * p.nnei + j0 + jp, M, lane);
     }
     for (int b = 0; b < nproc; b += 4) {
       if (ring_on) {
         __pipeline_wait_prior(4);  // 8 + 4*(b/4) groups committed, rows b..b+3 are among the first 4*(b/4 + 1)
         __syncwarp();
-      } else if (TWO) {
+      } else if (TWO && p.two) {
 #pragma unroll
         for (int u = 0; u < 4; ++u)
           if (b + kTwoAhead + u < nproc) prefetch_two(p.two, i * p.nnei + j0 + b + kTwoAhead + u, M, lane);
       }
       FP v[16];
       FP vx[4];
+      FP vq[4] = {(FP)0., (FP)0., (FP)0., (FP)0.};  // gate mode: dE/d(sw) of the four neighbours
       if (!single || (nproc - b) < 4) {  // the fast path below initialises by assignment
 #pragma unroll
         for (int t = 0; t < 16; ++t) v[t] = (FP)0.;
@@ -986,6 +1001,13 @@ __global__ void __launch_bounds__(384) k_tab_grad(const __grid_constant__ TabPar
             const FP xx = rc.xx;
             const FP dl = rc.delta;
             const FP e0 = rc.e[0], e1 = rc.e[1], e2 = rc.e[2], e3 = rc.e[3];  // pre-multiplied by the fold multiplicity
+            const FP* __restrict__ gate_row = nullptr;
+            FP gate_s = (FP)0.;
+            if (TWO && p.gate_tt) {
+              const long long gj = i * p.nnei + j0 + b + u;
+              gate_row = p.gate_tt + (long long)p.gate_pair[gj] * M;
+              gate_s = p.gate_sw[gj];
+            }
 #pragma unroll
             for (int c = 0; c < NC; ++c) {
               FP g, gd;
@@ -998,11 +1020,19 @@ __global__ void __launch_bounds__(384) k_tab_grad(const __grid_constant__ TabPar
               if (TWO) {
                 const int k = kb + lane + 32 * c;
                 if (k < M) {
-                  const long long to = (i * p.nnei + j0 + b + u) * (long long)M + k;
-                  const FP t = ring_on ? ring[((b + u) % kRing) * Mp + k] : p.two[to];
-                  p.dy_dtwo[to] = g * dot;
-                  g = g * t + g;
-                  gd += t * gd;
+                  if (gate_row) {  // dE/d(two_embed) is never stored: contract it with the type-pair row right here
+                    const FP tt = gate_row[k];
+                    vq[u] += g * dot * tt;
+                    const FP t = tt * gate_s;
+                    g = g * t + g;
+                    gd += t * gd;
+                  } else {
+                    const long long to = (i * p.nnei + j0 + b + u) * (long long)M + k;
+                    const FP t = ring_on ? ring[((b + u) % kRing) * Mp + k] : p.two[to];
+                    p.dy_dtwo[to] = g * dot;
+                    g = g * t + g;
+                    gd += t * gd;
+                  }
                 }
               }
               if (c == 0 && assign0) {  // first channel group of a full batch: start the sums here
@@ -1034,6 +1064,10 @@ __global__ void __launch_bounds__(384) k_tab_grad(const __grid_constant__ TabPar
       const FP tot = reduce_scatter16(v, lane);   // (u, m) = (lane >> 3, (lane >> 1) & 3)
       const FP totx = reduce_scatter4(vx, lane);  // u = lane >> 3; carries the multiplicity through e
       const int u = lane >> 3;
+      if (TWO && p.gate_q) {
+        const FP totq = reduce_scatter4(vq, lane);
+        if (b + u < nproc && (lane & 7) == 0) p.gate_q[i * p.nnei + j0 + b + u] = totq;
+      }
       if (b + u < nproc && (lane & 1) == 0) {
         const FP mult = (FP)rec[b + u].mult;
         const int m = (lane >> 1) & 3;
@@ -1054,7 +1088,9 @@ __global__ void __launch_bounds__(384) k_tab_grad(const __grid_constant__ TabPar
 #pragma unroll
         for (int m = 0; m < 4; ++m) gem[(long long)j * 4 + m] = (FP)0.;
       }
-      if (TWO) {
+      if (TWO && p.gate_q) {
+        for (int j = jend + lane; j < p.nnei; j += 32) p.gate_q[i * p.nnei + j] = (FP)0.;
+      } else if (TWO) {
         for (long long e = (long long)jend * M + lane; e < (long long)p.nnei * M; e += 32)
           p.dy_dtwo[i * p.nnei * (long long)M + e] = (FP)0.;
       }
@@ -1667,17 +1703,26 @@ struct DescArgs {
   int mode, axis, nslice;
 };
 
+template <typename FP>
+struct GateArgs {
+  const FP* tt;
+  const int* pair;
+  const FP* sw;
+  FP* q;
+};
+
 template <typename FP, bool GG>
 int launch_fwd(FP* out, const FP* table, const FP* info, const FP* em_x, long long ldx_i, int ldx_j,
                const FP* em, long long ldem_i, const FP* two, const FP* dz_x, const FP* dz_em,
                const FP* dz_two, int nloc, int nnei, int M, int is_sorted, int accumulate,
-               cudaStream_t st, const DescArgs* da = nullptr, int flags = 0) {
+               cudaStream_t st, const DescArgs* da = nullptr, int flags = 0, const GateArgs<FP>* ga = nullptr) {
   DPB_REQUIRE(nloc >= 0 && nnei >= 0 && M >= 0, "tabulate: negative size");
   if (nloc == 0 || M == 0) return DPB200_OK;
   DPB_REQUIRE(out != nullptr, "tabulate: out is null");
+  DPB_REQUIRE(!ga || (!GG && two == nullptr && ga->tt && ga->pair && ga->sw), "tabulate gate: bad arguments");
   // compressed coefficients in the SIMT forward: a3..a5 stay fp32 in the row cache and the top two Horner steps
   // run on the FP32 pipe (widening them to fp64 at fetch time instead was measured 8 % SLOWER than the full table)
-  const bool cm = (flags & DPB200_TAB_COMPRESSED_COEF) && !GG && two == nullptr && !use_mma_fwd() && fwd_cm_enabled();
+  const bool cm = (flags & DPB200_TAB_COMPRESSED_COEF) && !GG && two == nullptr && !ga && !use_mma_fwd() && fwd_cm_enabled();
   if (GG && da) {
     set_error("tabulate+descriptor: plain se_a forward only");
     return DPB200_ERR_INVALID;
@@ -1714,6 +1759,7 @@ int launch_fwd(FP* out, const FP* table, const FP* info, const FP* em_x, long lo
   p.dz_x = dz_x;
   p.dz_em = dz_em;
   p.dz_two = dz_two;
+  if (ga) p.gate_tt = ga->tt, p.gate_pair = ga->pair, p.gate_sw = ga->sw;
   if (da) {
     p.desc = da->desc;
     p.desc_ld = da->desc_ld;
@@ -1747,7 +1793,7 @@ int launch_fwd(FP* out, const FP* table, const FP* info, const FP* em_x, long lo
   if (rc) return rc;
   // (the forward needs the VALUE only: the compressed table is accurate enough on the stride-1 rows too -- the
   //  host-side gate checks that -- so no second table here)
-  const bool tw = two != nullptr;
+  const bool tw = two != nullptr || ga != nullptr;
   const int nblk = (M + 32 * nc - 1) / (32 * nc);
   long long want = ((long long)nloc + nw - 1) / nw;
   const long long cap = sm_count() / nblk > 0 ? sm_count() / nblk : 1;
@@ -1837,11 +1883,12 @@ template <typename FP>
 int launch_grad(FP* dy_dem_x, FP* dy_dem, FP* dy_dtwo, const FP* table, const FP* info,
                 const FP* em_x, long long ldx_i, int ldx_j, const FP* em, long long ldem_i,
                 const FP* two, const FP* dy, int nloc, int nnei, int M, int is_sorted,
-                cudaStream_t st, int flags = 0) {
+                cudaStream_t st, int flags = 0, const GateArgs<FP>* ga = nullptr) {
   DPB_REQUIRE(nloc >= 0 && nnei >= 0 && M >= 0, "tabulate grad: negative size");
   if (nloc == 0 || nnei == 0) return DPB200_OK;  // tabulate.cc: nothing to write
   DPB_REQUIRE(dy_dem != nullptr && dy != nullptr, "tabulate grad: null pointer");
   DPB_REQUIRE(two == nullptr || dy_dtwo != nullptr, "tabulate grad: dy_dtwo is null");
+  DPB_REQUIRE(!ga || (two == nullptr && ga->tt && ga->pair && ga->sw && ga->q), "tabulate gate grad: bad arguments");
   TabParams<FP> p = {};
   int rc = fill_info(p, info, M);
   if (rc) return rc;
@@ -1851,9 +1898,10 @@ int launch_grad(FP* dy_dem_x, FP* dy_dem, FP* dy_dtwo, const FP* table, const FP
   p.dy_dem_x = dy_dem_x;
   p.dy_dem = dy_dem;
   p.dy_dtwo = dy_dtwo;
+  if (ga) p.gate_tt = ga->tt, p.gate_pair = ga->pair, p.gate_sw = ga->sw, p.gate_q = ga->q;
   const int nw = 12;
-  const bool tw = two != nullptr;
-  const bool ring = tw && ((size_t)M * sizeof(FP)) % 16 == 0 && aligned16(two) && M <= 32 * 4;
+  const bool tw = two != nullptr || ga != nullptr;
+  const bool ring = two != nullptr && ((size_t)M * sizeof(FP)) % 16 == 0 && aligned16(two) && M <= 32 * 4;
   p.two_ring = ring ? 1 : 0;
   const size_t rec_bytes = (size_t)nw * 32 * sizeof(Rec<FP>) + (ring ? (size_t)nw * kRing * M * sizeof(FP) : 0);
   const int kt = (M + 3) / 4;
@@ -2045,6 +2093,26 @@ extern "C" {
     return dpb200::launch_grad<FP>(dy_dem_x, dy_dem, dy_dtwo, table, table_info, em_x, ldx_i,      \
                                    ldx_j, em, ldem_i, two_embed, dy, nloc, nnei, last_layer_size,  \
                                    is_sorted, (cudaStream_t)stream);                               \
+  }                                                                                                \
+  int dpb200_tabulate_fusion_se_atten_gate_##SUF(                                                  \
+      FP* out, const FP* table, const FP* table_info, const FP* em_x, const FP* em,                \
+      const FP* tt_full, const int* pair, const FP* sw, int nloc, int nnei, int last_layer_size,   \
+      int is_sorted, dpb200_stream_t stream) {                                                     \
+    dpb200::GateArgs<FP> ga = {tt_full, pair, sw, nullptr};                                        \
+    return dpb200::launch_fwd<FP, false>(out, table, table_info, em_x, nnei, 1, em,                \
+                                         (long long)nnei * 4, nullptr, nullptr, nullptr, nullptr,  \
+                                         nloc, nnei, last_layer_size, is_sorted, 0,                \
+                                         (cudaStream_t)stream, nullptr, 0, &ga);                   \
+  }                                                                                                \
+  int dpb200_tabulate_fusion_se_atten_gate_grad_##SUF(                                             \
+      FP* dy_dem_x, FP* dy_dem, FP* dy_dsw, const FP* table, const FP* table_info,                 \
+      const FP* em_x, const FP* em, const FP* tt_full, const int* pair, const FP* sw,              \
+      const FP* dy, int nloc, int nnei, int last_layer_size, int is_sorted,                        \
+      dpb200_stream_t stream) {                                                                    \
+    dpb200::GateArgs<FP> ga = {tt_full, pair, sw, dy_dsw};                                         \
+    return dpb200::launch_grad<FP>(dy_dem_x, dy_dem, nullptr, table, table_info, em_x, nnei, 1,    \
+                                   em, (long long)nnei * 4, nullptr, dy, nloc, nnei,               \
+                                   last_layer_size, is_sorted, (cudaStream_t)stream, 0, &ga);      \
   }                                                                                                \
   int dpb200_tabulate_fusion_se_a_grad_grad_##SUF(                                                 \
       FP* dz_dy, const FP* table, const FP* table_info, const FP* em_x, const FP* em,              \

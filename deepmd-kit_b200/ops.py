@@ -135,8 +135,10 @@ def prod_env_mat_a(coord, atype, numneigh, rows, avg, std, nloc, nall, rcut, rcu
     if f_type is not None:
         f_type = _c(f_type, torch.int32)
     sec_c, nsec, nnei = _sec_arr(sec)
-    ntypes = nsec - 1
-    if avg.numel() != ntypes * nnei * 4 or std.numel() != ntypes * nnei * 4:
+    # avg / std carry one row per CENTRE type; with a coarser f_type (se_atten: one distance-ordered section)
+    # that is more rows than sections
+    ntypes = avg.numel() // (nnei * 4) if nnei else nsec - 1
+    if avg.numel() != ntypes * nnei * 4 or std.numel() != avg.numel() or ntypes < 1 or (f_type is None and ntypes != nsec - 1):
         raise ValueError("dpb200: avg/std must have ntypes*nnei*4 elements")
     if coord.numel() != nframes * nall * 3 or atype.numel() != nframes * nall:
         raise ValueError("dpb200: coord/type do not match nframes*nall")
@@ -155,9 +157,9 @@ def prod_env_mat_a(coord, atype, numneigh, rows, avg, std, nloc, nall, rcut, rcu
     # the kernel writes row ilist[r] of each output: with a row range the output pointers are moved
     # back by `shift` rows so that centre atom a lands in row 0 of the compact chunk buffers
     po = lambda t, width, b_: C.c_void_p(t.data_ptr() - shift * width * b_)
-    L.call("prod_env_mat_a_" + s, po(em, nnei * 4, esz), po(dv, nnei * 12, esz), po(rij, nnei * 3, esz),
+    L.call("prod_env_mat_a_ex_" + s, po(em, nnei * 4, esz), po(dv, nnei * 12, esz), po(rij, nnei * 3, esz),
            po(nlist, nnei, 4), _p(coord), _p(atype), _p(f_type), _p(ilist), _p(numneigh), _p(fn), _p(rows_t), stride, mx,
-           _p(avg), _p(std), nloc_eff, nall, nframes, float(rcut), float(rcut_smth), sec_c, nsec, _p(ws), ws.numel(),
+           _p(avg), _p(std), ntypes, nloc_eff, nall, nframes, float(rcut), float(rcut_smth), sec_c, nsec, _p(ws), ws.numel(),
            _stream(dev))
     return em, dv, rij, nlist
 
@@ -253,6 +255,44 @@ def tabulate_fusion_se_a_grad(table, table_info, em_x, em, dy, last_layer_size, 
     lib().call("tabulate_fusion_se_a_grad_" + s, _p(g_x), _p(g_em), _p(g_two), _p(table), C.c_void_p(ti.data_ptr()),
                _p(em_x), _p(em), _p(two_embed), _p(dy), nloc, nnei, M, int(bool(is_sorted)), _stream(dev))
     return g_x, g_em, g_two
+
+
+def tabulate_fusion_se_atten_gate(table, table_info, em_x, em, tt_full, pair, sw, last_layer_size, is_sorted=True):
+    """tabulate_fusion_se_atten with two_embed = tt_full[pair] * sw formed inside the kernel (never materialised):
+    pair int32 [nloc, nnei] rows of tt_full [(ntypes+1)^2, M], sw [nloc, nnei].  Returns [nloc, 4, M]."""
+    dev = _need_cuda(("table", table), ("em_x", em_x), ("em", em), ("tt_full", tt_full), ("pair", pair), ("sw", sw))
+    s = _suffix(table)
+    ti = _info_host(table_info, table.dtype)
+    table, em_x, em = _c(table), _c(em_x, table.dtype), _c(em, table.dtype)
+    tt_full, pair, sw = _c(tt_full, table.dtype), _c(pair, torch.int32), _c(sw, table.dtype)
+    nloc, nnei = em.shape[0], em.shape[1]
+    M = int(last_layer_size)
+    if tt_full.shape[-1] != M or pair.numel() != nloc * nnei or sw.numel() != nloc * nnei:
+        raise ValueError("dpb200: gate tensors do not match [nloc, nnei] / M")
+    out = torch.empty((nloc, 4, M), dtype=table.dtype, device=dev)
+    lib().call("tabulate_fusion_se_atten_gate_" + s, _p(out), _p(table), C.c_void_p(ti.data_ptr()), _p(em_x), _p(em),
+               _p(tt_full), _p(pair), _p(sw), nloc, nnei, M, int(bool(is_sorted)), _stream(dev))
+    return out
+
+
+def tabulate_fusion_se_atten_gate_grad(table, table_info, em_x, em, tt_full, pair, sw, dy, last_layer_size,
+                                       is_sorted=True):
+    """Backward of tabulate_fusion_se_atten_gate: (dy_dem_x [nloc*nnei, 1], dy_dem [nloc, nnei, 4], dy_dsw [nloc, nnei])."""
+    dev = _need_cuda(("table", table), ("em_x", em_x), ("em", em), ("tt_full", tt_full), ("pair", pair), ("sw", sw),
+                     ("dy", dy))
+    s = _suffix(table)
+    ti = _info_host(table_info, table.dtype)
+    table, em_x, em, dy = _c(table), _c(em_x, table.dtype), _c(em, table.dtype), _c(dy, table.dtype)
+    tt_full, pair, sw = _c(tt_full, table.dtype), _c(pair, torch.int32), _c(sw, table.dtype)
+    nloc, nnei = em.shape[0], em.shape[1]
+    M = int(last_layer_size)
+    g_x = torch.empty_like(em_x)
+    g_em = torch.empty_like(em)
+    g_sw = torch.empty((nloc, nnei), dtype=table.dtype, device=dev)
+    lib().call("tabulate_fusion_se_atten_gate_grad_" + s, _p(g_x), _p(g_em), _p(g_sw), _p(table),
+               C.c_void_p(ti.data_ptr()), _p(em_x), _p(em), _p(tt_full), _p(pair), _p(sw), _p(dy), nloc, nnei, M,
+               int(bool(is_sorted)), _stream(dev))
+    return g_x, g_em, g_sw
 
 
 def tabulate_fusion_se_a_grad_grad(table, table_info, em_x, em, dz_dy_dem_x, dz_dy_dem, last_layer_size,

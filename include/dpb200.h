@@ -80,6 +80,18 @@ size_t dpb200_prod_env_mat_a_workspace_bytes(int ntypes, int nnei, int nall, int
                                   const FP* avg, const FP* std, int nloc, int nall, int nframes,  \
                                   float rcut, float rcut_smth, const int* sec, int nsec,          \
                                   void* workspace, size_t workspace_bytes, dpb200_stream_t stream); \
+  /* same with avg / std holding `ntypes_center` rows (centre-atom types) independent of the number of  \
+   * sections: se_atten formats ONE distance-ordered section (f_type = 0) but normalises per real centre  \
+   * type (deepmd/pt/model/descriptor/se_atten.py; prod_env_mat_a_cpu indexes avg by type[i] the same way). \
+   * workspace: dpb200_prod_env_mat_a_workspace_bytes(ntypes_center, ...). */                          \
+  int dpb200_prod_env_mat_a_ex_##SUF(FP* em, FP* em_deriv, FP* rij, int* nlist, const FP* coord,  \
+                                     const int* type, const int* f_type, const int* ilist,        \
+                                     const int* numneigh, const int* const* firstneigh,           \
+                                     const int* rows, int row_stride, int max_nbor_size,          \
+                                     const FP* avg, const FP* std, int ntypes_center, int nloc,   \
+                                     int nall, int nframes, float rcut, float rcut_smth,          \
+                                     const int* sec, int nsec, void* workspace,                   \
+                                     size_t workspace_bytes, dpb200_stream_t stream);             \
   /* format only: replaces deepmd::format_nbor_list_gpu (source/lib/include/fmt_nlist.h:22-34) */ \
   int dpb200_format_nlist_##SUF(int* nlist, const FP* coord, const int* type, const int* ilist,   \
                                 const int* numneigh, const int* const* firstneigh,                \
@@ -116,6 +128,20 @@ DPB200_DECL_ENV(f32, float)
                                              const FP* dy, int nloc, int nnei,                     \
                                              int last_layer_size, int is_sorted,                   \
                                              dpb200_stream_t stream);                              \
+  /* se_atten strip gate WITHOUT the materialised two_embed [nloc*nnei][M] (96 KB per atom in fp64):     \
+   * two_embed[i][j][k] = tt_full[pair[i][j]][k] * sw[i][j]  (deepmd/pt/model/descriptor/se_atten.py:979-985: \
+   * gg_t = tt_full[tebd_idx] * sw) is formed inside the kernel; the backward returns                     \
+   * dy_dsw[i][j] = sum_k dy_dtwo[i][j][k] * tt_full[pair][k] instead of dy_dtwo.  Same results as the      \
+   * reference-schema entry points above fed with the materialised tensor. */                           \
+  int dpb200_tabulate_fusion_se_atten_gate_##SUF(                                                  \
+      FP* out, const FP* table, const FP* table_info, const FP* em_x, const FP* em,                \
+      const FP* tt_full, const int* pair, const FP* sw, int nloc, int nnei, int last_layer_size,   \
+      int is_sorted, dpb200_stream_t stream);                                                      \
+  int dpb200_tabulate_fusion_se_atten_gate_grad_##SUF(                                             \
+      FP* dy_dem_x, FP* dy_dem, FP* dy_dsw, const FP* table, const FP* table_info,                 \
+      const FP* em_x, const FP* em, const FP* tt_full, const int* pair, const FP* sw,              \
+      const FP* dy, int nloc, int nnei, int last_layer_size, int is_sorted,                        \
+      dpb200_stream_t stream);                                                                     \
   int dpb200_tabulate_fusion_se_a_grad_grad_##SUF(                                                 \
       FP* dz_dy, const FP* table, const FP* table_info, const FP* em_x, const FP* em,              \
       const FP* two_embed, const FP* dz_dy_dem_x, const FP* dz_dy_dem, const FP* dz_dy_dtwo,       \
