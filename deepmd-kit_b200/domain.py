@@ -158,6 +158,26 @@ class DomainDeepPot(DeepPotB200):
         c = c + np.array(me) * L
         return c, t, b * np.array(self.grid)[:, None]
 
+    def make_local_copper(self, ncell: int, jitter: float = 0.05, a0: float = 3.615, seed: int = 20260102):
+        """This rank's brick of ONE global FCC box of ncell^3 conventional cells (BASELINE config 3, strong scaling:
+        the global box is fixed, every rank generates the cells of its own brick only).  Cells are split as evenly
+        as the grid allows; the brick faces sit on cell boundaries."""
+        me = rank_to_coords(self.rank, self.grid)
+        lo = [ncell * me[d] // self.grid[d] for d in range(3)]
+        hi = [ncell * (me[d] + 1) // self.grid[d] for d in range(3)]
+        base = np.array([[0, 0, 0], [0.5, 0.5, 0], [0.5, 0, 0.5], [0, 0.5, 0.5]]) * a0
+        cells = np.stack(np.meshgrid(*[np.arange(lo[d], hi[d]) for d in range(3)], indexing="ij"), -1).reshape(-1, 3) * a0
+        coord = (cells[:, None, :] + base[None]).reshape(-1, 3)
+        if jitter > 0:
+            coord = coord + np.random.default_rng(seed + 7919 * self.rank).normal(scale=jitter, size=coord.shape)
+        L = ncell * a0
+        # (atoms pushed across a face by the jitter stay with this rank: the halo plan allows skin / 2 of slack;
+        #  the brick bounds of the plan are fractions me/grid of the box, so uneven cell splits must not occur)
+        for d in range(3):
+            if ncell % self.grid[d]:
+                raise ValueError(f"ncell = {ncell} is not divisible by the process grid {self.grid}")
+        return coord, np.zeros(len(coord), np.int32), np.eye(3) * L
+
     # -- host-side pieces (overridable for CPU tests) -----------------------------------------
     def _pack(self, coord, plan):
         return ops.halo_pack(coord, plan.sendlist, plan.shift)
@@ -196,6 +216,7 @@ class DomainDeepPot(DeepPotB200):
         ref = ops._buf(self._cache, "ref_coord", (nloc, 3), c.dtype, c.device)
         ref.copy_(c)
         self.state = NeighborState(nloc, ext_t, None, None, numneigh, rows, perm, ranges, type_inv=inv,
+                                   chunks=self._chunks(atype),
                                    box=np.array(box, dtype=np.float64).reshape(9).copy(), ref_coord=ref)
         return self.state
 
@@ -216,9 +237,13 @@ class DomainDeepPot(DeepPotB200):
         c = coord.reshape(-1, 3)
         ext_c = self.halo_forward(c)
         st.ago += 1
-        e, f_ext, virial, ex = self.model.evaluate(ext_c, st.ext_type, st.numneigh, st.rows, None, st.nloc,
-                                                   st.type_perm, st.type_ranges, atom_virial=atom_virial, fused=fused,
-                                                   type_inv=st.type_inv)
+        if st.chunks is not None:  # per-atom intermediates exceed the device memory: slabs of centre atoms
+            e, f_ext, virial, ex = self.model.evaluate_chunked(ext_c, st.ext_type, st.numneigh, st.rows, None, st.nloc,
+                                                               st.chunks, atom_virial=atom_virial)
+        else:
+            e, f_ext, virial, ex = self.model.evaluate(ext_c, st.ext_type, st.numneigh, st.rows, None, st.nloc,
+                                                       st.type_perm, st.type_ranges, atom_virial=atom_virial,
+                                                       fused=fused, type_inv=st.type_inv)
         force = self.halo_reverse(f_ext, st.nloc)
         red = torch.cat([e.reshape(1), virial.reshape(9)])
         if dist.is_initialized() and dist.get_world_size(self.group) > 1:

@@ -248,3 +248,28 @@ def test_reference_arm_model_equals_product_model(pkg):
         assert torch.equal(fa.head[0], fb.head[0]) and torch.equal(fa.head[1], fb.head[1])
     x = torch.randn(7, 1600, dtype=torch.float64)
     assert torch.equal(fa(x), fb(x))
+
+
+def test_decomposed_copper_box_covers_the_global_box(pkg):
+    """Strong-scaling workload (BASELINE config 3): the bricks generated rank by rank tile the global FCC box exactly
+    and every atom lies inside its rank's brick."""
+    import __graft_entry__ as g
+    from deepmd_kit_b200.domain import DomainDeepPot, rank_to_coords
+
+    grid = (2, 2, 1)
+    want, _, box = g.copper_box(4, jitter=0.0)
+    got = []
+    for r in range(4):
+        dd = DomainDeepPot(None, grid)
+        dd.rank = r
+        c, t, b = dd.make_local_copper(4, jitter=0.0)
+        assert np.array_equal(b, box) and len(t) == len(c) and not t.any()
+        me = np.array(rank_to_coords(r, grid))
+        L = np.diag(box)
+        assert ((c >= me * L / np.array(grid) - 1e-9) & (c < (me + 1) * L / np.array(grid) - 1e-9)).all()
+        got.append(c)
+    got = np.concatenate(got)
+    key = lambda a: sorted(map(tuple, np.round(a, 6)))
+    assert key(got) == key(want)
+    with pytest.raises(ValueError):
+        DomainDeepPot(None, (3, 1, 1)).make_local_copper(4)
