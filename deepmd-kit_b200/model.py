@@ -559,12 +559,14 @@ class SeAModel:
         return e_atom.sum(), force.reshape(-1, 3), virial, dict(atom_energy=e_atom, atom_virial=av, nlist=None)
 
     def evaluate(self, ext_coord, ext_type, numneigh, rows, mapping, nloc, type_perm, type_ranges, atom_virial=False,
-                 fused=True, type_inv=None):
-        """One force evaluation on an extended system. Returns (E, force[nloc,3], virial[9], extras)."""
+                 fused=True, type_inv=None, firstneigh=None, max_nbor_size=None):
+        """One force evaluation on an extended system. Returns (E, force[nloc,3], virial[9], extras).
+        The raw list is either a dense `rows` block or `firstneigh` (device array of device row pointers)."""
         cfg = self.cfg
         nall = ext_type.numel()
         em, dv, rij, nlist = ops.prod_env_mat_a(ext_coord.reshape(-1), ext_type, numneigh, rows, self.davg, self.dstd,
-                                                nloc, nall, cfg.rcut, cfg.rcut_smth, cfg.sec)
+                                                nloc, nall, cfg.rcut, cfg.rcut_smth, cfg.sec, firstneigh=firstneigh,
+                                                max_nbor_size=max_nbor_size)
         if self.use_split:
             if type_inv is None:
                 type_inv = torch.empty(nloc, dtype=torch.int32, device=type_perm.device)
@@ -791,6 +793,38 @@ class DeepPotB200:
 
         lib().cdll.dpb200_count_replayed_launches(self._graph_launches)
         return self._g_out
+
+    def compute_nlist(self, ext_coord: torch.Tensor, ext_type: torch.Tensor, nloc: int, numneigh: torch.Tensor,
+                      rows: Optional[torch.Tensor] = None, firstneigh: Optional[torch.Tensor] = None,
+                      max_nbor_size: Optional[int] = None, ago: int = 0, atom_virial: bool = False):
+        """Device-resident hand-off of an MD code's own neighbour list: the counterpart of
+        DeepPotPT::compute(..., nghost, InputNlist, ago) (source/api_cc/src/DeepPotPT.cc:171-377) and of the Kokkos
+        pair style (source/lmp/pair_deepmd_kokkos.cpp) WITHOUT the per-step host staging the reference does there
+        (host vectors -> padded host list -> H2D; forces D2H): every argument is a DEVICE tensor and so is every result.
+
+        ext_coord [nall, 3], ext_type [nall] int32 (local atoms first, then ghosts; negative type = virtual atom),
+        numneigh [nloc] int32, and the raw rows either as a dense row-major block `rows` [nloc, capacity] int32 or as
+        `firstneigh`, an int64 device tensor of device row pointers (InputNlist layout, neighbor_list.h:20-57);
+        `max_nbor_size` bounds numneigh (default: the row capacity / the largest count).  The list must contain every
+        neighbour within rcut (a skin is fine: rows are re-formatted with the true cutoff every call).  `ago` == 0
+        tells that atom types / the list changed since the previous call (type partition is recomputed).
+        Returns (E, force [nall, 3] INCLUDING the forces on ghost atoms -- the caller's reverse communication folds
+        them, as PairDeepMD::compute does (pair_deepmd.cpp:482-488) --, virial [9], extras)."""
+        m = self.model
+        ext_type = ext_type.to(torch.int32)
+        key = (ext_type.data_ptr(), int(ext_type.numel()), int(nloc))
+        hit = self._cache.get("nl_perm")
+        if ago == 0 or hit is None or hit[0] != key:
+            perm, ranges = type_partition(ext_type[:nloc], m.cfg.ntypes)
+            inv = torch.empty(nloc, dtype=torch.int32, device=perm.device)
+            inv[perm] = torch.arange(nloc, dtype=torch.int32, device=perm.device)
+            hit = (key, perm, ranges, inv)
+            self._cache["nl_perm"] = hit
+        if rows is None and firstneigh is None:
+            raise ValueError("dpb200: compute_nlist needs `rows` or `firstneigh`")
+        return m.evaluate(ext_coord.reshape(-1, 3), ext_type, numneigh.to(torch.int32), rows, None, int(nloc), hit[1],
+                          hit[2], atom_virial=atom_virial, type_inv=hit[3], firstneigh=firstneigh,
+                          max_nbor_size=max_nbor_size)
 
     def eval(self, coords, cells, atom_types, atomic: bool = False):
         """coords [nframes, natoms*3], cells [nframes, 9], atom_types [natoms] (host arrays).

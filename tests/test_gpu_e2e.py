@@ -273,3 +273,39 @@ def test_domain_path_on_one_gpu_matches_plain(pkg):
     e3, f3, v3 = DeepPotB200(model, skin=2.0).eval(c2.cpu().numpy().reshape(1, -1), box.reshape(1, 9), atype)
     assert dd.state.ago == 2
     assert rel(f2.cpu().numpy(), f3[0]) <= 1e-10
+
+
+@pytest.mark.parametrize("form", ["dense", "pointers"])
+def test_compute_with_a_device_neighbour_list(pkg, form):
+    """DeepPotB200.compute_nlist consumes an MD code's own list, device tensors in and out (the
+    counterpart of DeepPotPT::compute(..., InputNlist, ago)): forces on local AND ghost atoms, folded here with the
+    ghost -> owner map as LAMMPS' reverse communication does, must equal the plain evaluation."""
+    from deepmd_kit_b200 import ops
+    from deepmd_kit_b200.model import DeepPotB200, SeAConfig, SeAModel
+
+    cfg = SeAConfig()
+    coord, atype, box = g.water_box(2, 0.01)
+    model = SeAModel(cfg, torch.float64, "cuda:0")
+    e0, f0, v0 = DeepPotB200(model, skin=2.0).eval(coord.reshape(1, -1), box.reshape(1, 9), atype)
+    dev = torch.device("cuda:0")
+    c = torch.as_tensor(coord, device=dev)
+    t = torch.as_tensor(atype, device=dev)
+    nloc = len(atype)
+    rc = cfg.rcut + 1.0  # the "MD code" keeps a 1 A skin
+    ext_c, ext_t, mapping = ops.copy_coord(ops.normalize_coord(c.clone(), box), t, box, rc)
+    numneigh, rows = ops.build_nlist(ext_c, nloc, rc, ext_t)
+    dp = DeepPotB200(model)
+    if form == "dense":
+        e, f, v, ex = dp.compute_nlist(ext_c, ext_t, nloc, numneigh, rows=rows, ago=0)
+    else:  # CSR rows behind device row pointers
+        nn = numneigh.to(torch.int64)
+        keep = torch.arange(rows.shape[1], device=dev)[None, :] < nn[:, None]
+        neigh = rows[keep].contiguous()
+        first = ops.csr_row_pointers(neigh, numneigh)
+        e, f, v, ex = dp.compute_nlist(ext_c, ext_t, nloc, numneigh, firstneigh=first, ago=0)
+        e, f, v, ex = dp.compute_nlist(ext_c, ext_t, nloc, numneigh, firstneigh=first, ago=1)  # cached partition
+    assert f.shape == (ext_t.numel(), 3) and f.is_cuda
+    folded = torch.zeros((nloc, 3), dtype=f.dtype, device=dev).index_add_(0, mapping.long(), f)
+    assert abs(float(e) - e0[0, 0]) <= 1e-10 * abs(e0[0, 0])
+    assert rel(folded.cpu().numpy(), f0[0]) <= 1e-10
+    assert rel(v.cpu().numpy(), v0[0]) <= 1e-10
