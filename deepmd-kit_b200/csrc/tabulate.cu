@@ -1234,6 +1234,9 @@ __global__ void __launch_bounds__(512) k_tab_fwd_mma(const __grid_constant__ Tab
   }
 }
 
+// leading dimension (doubles) of the per-warp dy tile of the tensor-core backward: >= 4*KT and = 4 mod 16
+__host__ __device__ constexpr int grad_mma_tile_ld(int kt) { return (4 * kt + 11) / 16 * 16 + 4; }
+
 // BSM: the B fragments (dy of the current atom) live in a per-warp shared-memory tile instead of 2*KT
 // registers, which lets MAXT / 32 warps (instead of 12) share an SM: the kernel is latency-bound on the
 // coefficient fetches of rows outside the hot window, so warps in flight are what it needs.
@@ -1246,10 +1249,11 @@ __global__ void __launch_bounds__(MAXT) k_tab_grad_mma(const __grid_constant__ T
   FP* hot = reinterpret_cast<FP*>(tab_smem);
   Rec<FP>* rec = reinterpret_cast<Rec<FP>*>(hot + p.hot_elems) + warp * 32;
   const int M = p.M;
-  // per-warp dy tile [5][4*KT]: rows 0..3 = components (channels >= M zero), row 4 = zeros for the lanes that own
-  // the unused B columns 4..7 -- the B fragment load needs no predicate (the kernel is sensitive to ALU work)
-  constexpr int MP = 4 * KT;
-  FP* dyt = reinterpret_cast<FP*>(reinterpret_cast<Rec<FP>*>(hot + p.hot_elems) + nw * 32) + (BSM ? warp * 5 * MP : 0);
+  // per-warp dy tile [4][MP]: rows = components (channels >= M zero).  The lanes that own the unused B columns 4..7
+  // read the row of column n - 4 (a broadcast of the same words: no predicate, no bank conflict; C columns 4..7
+  // are never read).  MP = 4 mod 16 doubles, so the four rows start 8 banks apart and one B load is one wavefront.
+  constexpr int MP = grad_mma_tile_ld(KT);
+  FP* dyt = reinterpret_cast<FP*>(reinterpret_cast<Rec<FP>*>(hot + p.hot_elems) + nw * 32) + (BSM ? warp * 4 * MP : 0);
   const int r0 = hot_window_start(p);
   preload_hot(hot, p, r0);
   __syncthreads();
@@ -1257,6 +1261,7 @@ __global__ void __launch_bounds__(MAXT) k_tab_grad_mma(const __grid_constant__ T
   const int q = lane >> 2, kk = lane & 3;
   const unsigned qb = (unsigned)M * 16u;
   const unsigned rowb = (CM ? 2u : 3u) * qb;  // bytes per table row
+  const unsigned hrowb = rowb + (unsigned)p.hot_pad;  // ... in the shared-memory window (padded, see launch_grad)
   const unsigned off_k = (unsigned)kk * 16u;
   const unsigned off_last = (unsigned)((4 * (KT - 1) + kk < M) ? 4 * (KT - 1) + kk : M - 1) * 16u;
 
@@ -1267,9 +1272,9 @@ __global__ void __launch_bounds__(MAXT) k_tab_grad_mma(const __grid_constant__ T
   load_pre(pre, p, i, 0, lane);
   FP last = i < p.nloc ? p.em_x[i * p.ldx_i + (long long)(p.nnei - 1) * p.ldx_j] : (FP)0.;
   FP bf[BSM ? 1 : KT];  // B fragments: dy[m = q][channel 4t + kk] (q < 4), constant per atom
-  const FP* bsrc = dyt + (q < 4 ? q : 4) * MP + kk;
+  const FP* bsrc = dyt + (q & 3) * MP + kk;
   if (BSM) {
-    for (int e = lane; e < 5 * MP; e += 32) dyt[e] = (FP)0.;
+    for (int e = lane; e < 4 * MP; e += 32) dyt[e] = (FP)0.;
     __syncwarp();
   }
 
@@ -1356,13 +1361,13 @@ __global__ void __launch_bounds__(MAXT) k_tab_grad_mma(const __grid_constant__ T
         const char* __restrict__ b = reinterpret_cast<const char*>(p.T3) + (long long)r.idx * (3u * qb);
         DPB_GRAD_STEPS(b, false)
       } else if (__all_sync(kFull, inwin)) {
-        const char* b = reinterpret_cast<const char*>(hot) + rel * rowb;
+        const char* b = reinterpret_cast<const char*>(hot) + rel * hrowb;
         DPB_GRAD_STEPS(b, CM)
       } else if (!__any_sync(kFull, inwin)) {
         const char* __restrict__ b = reinterpret_cast<const char*>(p.T) + (long long)r.idx * rowb;
         DPB_GRAD_STEPS(b, CM)
       } else {
-        const char* b = inwin ? reinterpret_cast<const char*>(hot) + rel * rowb
+        const char* b = inwin ? reinterpret_cast<const char*>(hot) + rel * hrowb
                               : reinterpret_cast<const char*>(p.T) + (long long)r.idx * rowb;
         DPB_GRAD_STEPS(b, CM)
       }
@@ -1414,8 +1419,8 @@ __global__ void __launch_bounds__(512) k_tab_grad_mma_f32(const __grid_constant_
   FP* hot = reinterpret_cast<FP*>(tab_smem);
   Rec<FP>* rec = reinterpret_cast<Rec<FP>*>(hot + p.hot_elems) + warp * 32;
   const int M = p.M;
-  constexpr int MP = 4 * KT;
-  double* dyt = reinterpret_cast<double*>(reinterpret_cast<Rec<FP>*>(hot + p.hot_elems) + nw * 32) + warp * 5 * MP;
+  constexpr int MP = grad_mma_tile_ld(KT);  // [4][MP], B columns 4..7 alias 0..3 (see k_tab_grad_mma)
+  double* dyt = reinterpret_cast<double*>(reinterpret_cast<Rec<FP>*>(hot + p.hot_elems) + nw * 32) + warp * 4 * MP;
   const int r0 = hot_window_start(p);
   preload_hot(hot, p, r0);
   __syncthreads();
@@ -1431,8 +1436,8 @@ __global__ void __launch_bounds__(512) k_tab_grad_mma_f32(const __grid_constant_
   Pre<FP, false> pre;
   load_pre(pre, p, i, 0, lane);
   FP last = i < p.nloc ? p.em_x[i * p.ldx_i + (long long)(p.nnei - 1) * p.ldx_j] : (FP)0.;
-  const double* bsrc = dyt + (q < 4 ? q : 4) * MP + kk;
-  for (int e = lane; e < 5 * MP; e += 32) dyt[e] = 0.;
+  const double* bsrc = dyt + (q & 3) * MP + kk;
+  for (int e = lane; e < 4 * MP; e += 32) dyt[e] = 0.;
   __syncwarp();
 
   while (i < p.nloc) {
@@ -1534,6 +1539,14 @@ inline int hot_rows_cap() {
   static const int v = [] {
     const char* e = getenv("DPB200_TAB_HOT_ROWS");
     return e ? atoi(e) : (1 << 30);
+  }();
+  return v;
+}
+
+inline int grad_hot_pad() {
+  static const int v = [] {
+    const char* e = getenv("DPB200_TAB_GRAD_PAD");
+    return e ? atoi(e) : 64;
   }();
   return v;
 }
@@ -1687,7 +1700,7 @@ void set_a5_scale(TabParams<FP>& p, int flags) {
 // hot rows / shared-memory sizing for `blocks` coefficient-pair blocks (2 * sizeof(FP) bytes) per (row, channel)
 template <typename FP>
 void size_hot_window(TabParams<FP>& p, int M, size_t other_bytes, int blocks) {
-  const size_t row_bytes = (size_t)M * 2 * sizeof(FP) * blocks;  // `blocks` pair blocks per (row, channel)
+  const size_t row_bytes = (size_t)M * 2 * sizeof(FP) * blocks + p.hot_pad;  // `blocks` pair blocks per (row, channel)
   long long h = other_bytes + row_bytes > kSmemBudget ? 0 : (long long)((kSmemBudget - other_bytes) / row_bytes);
   if (h > hot_rows_cap()) h = hot_rows_cap();
   p.H = (int)(h < p.nrow ? h : p.nrow);
@@ -1930,7 +1943,7 @@ int launch_grad(FP* dy_dem_x, FP* dy_dem, FP* dy_dtwo, const FP* table, const FP
   if constexpr (std::is_same<FP, float>::value) {
     if (cm32 && use_mma_path() && (kt == 8 || kt == 16 || kt == 20 || kt == 25 || kt == 32)) {
       const int nwv = 16;
-      const size_t extra = (size_t)nwv * 5 * (4 * kt) * sizeof(double);
+      const size_t extra = (size_t)nwv * 4 * grad_mma_tile_ld(kt) * sizeof(double);
       const size_t recv = (size_t)nwv * 32 * sizeof(Rec<FP>);
       size_hot_window(p, M, recv + extra, p.nblk);
       // the double tile behind the records must be 8-byte aligned: hot_elems is a multiple of 16 bytes, Rec is 32 bytes
@@ -1959,8 +1972,11 @@ int launch_grad(FP* dy_dem_x, FP* dy_dem, FP* dy_dtwo, const FP* table, const FP
       // variant 0: B fragments in registers, 12 warps; 1: in shared memory, 16 warps; 2: 24 warps
       const int variant = grad_variant();
       const int nwv = variant == 0 ? 12 : (variant == 1 ? 16 : 24);
-      const size_t extra = variant == 0 ? 0 : (size_t)nwv * 5 * (4 * kt) * sizeof(FP);
+      const size_t extra = variant == 0 ? 0 : (size_t)nwv * 4 * grad_mma_tile_ld(kt) * sizeof(FP);
       const size_t recv = (size_t)nwv * 32 * sizeof(Rec<FP>);
+      // window rows are padded by 64 bytes when their size is a multiple of 128: the two neighbours of a quarter-warp
+      // then hit disjoint banks whenever their rows are adjacent (the common case for distance-sorted neighbours)
+      p.hot_pad = ((size_t)M * 16 * p.nblk) % 128 == 0 ? grad_hot_pad() : 0;
       size_hot_window(p, M, recv + extra, p.nblk);
       if (cm && p.H > p.first) p.H = p.first;  // the window holds compressed (stride-0) rows only
       const size_t smemv = (size_t)p.hot_elems * sizeof(FP) + recv + extra;
