@@ -475,10 +475,11 @@ def per_kernel(args, torch, ops, model, dp, step, L, dev, nloc, esz):
     fma = L.fma_peak(args.dtype, None)
     npr = nreal + nt  # one folded padding entry per table
     # int8 tensor-core work of the fitting net: every GEMM of the forward and of the input-gradient backward as
-    # NS(NS+1)/2 = 21 exact slice products (csrc/fit_tc.cu), 2 ops per MAC
+    # NS(NS+1)/2 exact slice products (csrc/fit_tc.cu; NS = 6 for the fp64 model: 21, NS = 4 for fp32: 10), 2 ops per MAC
     widths = [getattr(model, "dim_in", M * cfg.axis_neuron)] + list(cfg.fitting_neuron)
     fit_mac = sum(a * b for a, b in zip(widths[:-1], widths[1:]))
-    fit_int8_ops = 2.0 * 21 * (2 * fit_mac)
+    fit_ns = 6 if args.dtype == "f64" else 4
+    fit_int8_ops = 2.0 * (fit_ns * (fit_ns + 1) // 2) * (2 * fit_mac)
     int8_peak = 2.0 * float(peaks.get("bf16_tflops_sustained", peaks.get("bf16_tflops", 1400.0)))
     alg = {
         "prod_env_mat_a": ("hbm", (19 * nnei * F + 4 * nnei) + 4 * raw + 3 * F * (1 + nall / nloc)),

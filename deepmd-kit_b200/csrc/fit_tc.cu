@@ -68,6 +68,7 @@ struct GemmParams {
   int out_exp;
   long long ld_out;  // PLAIN: leading dimension
   int wide_store;    // PLAIN: rows are 32-byte aligned (256-bit stores)
+  int out_f32;       // PLAIN: out0 is a float matrix (the fp32 model's dE/dD), 16-byte aligned rows
   long long* dbg;    // optional per-role cycle counters of every CTA ([grid][16]; profiling only)
 };
 
@@ -307,6 +308,7 @@ __global__ void __launch_bounds__(kThreads, 1)
   using L = SmemLayout<NS, NT>;
   constexpr int NH = L::NH;
   static_assert(CN == 1 || CN == NH || CN == 4, "A is shared by slice (CN = NS/2) or by 32-row quarters (CN = 4)");
+  static_assert(NS == 4 || NS == 6, "built for 6 (fp64 model) and 4 (fp32 model) operand slices");
   constexpr uint16_t kMaskAll = (uint16_t)((1u << CN) - 1u);
   const uint32_t crank = CN > 1 ? cluster_ctarank() : 0u;
   static_assert(NS % 2 == 0 && NS * NT <= 512 && NT % 16 == 0 && NH * NT <= 256,
@@ -593,10 +595,16 @@ __global__ void __launch_bounds__(kThreads, 1)
         }
       } else {
         if (row_ok) {
-          double* __restrict__ o = p.out0 + r * p.ld_out + c0;
+          double* __restrict__ o = p.out0 + (p.out_f32 ? 0 : r * p.ld_out + c0);
 #pragma unroll
           for (int j = 0; j < 16; ++j) v[j] *= rs * cvs[4 * j];
-          if (p.wide_store) {  // 32-byte aligned rows: one full sector per store
+          if (p.out_f32) {
+            float* __restrict__ of = reinterpret_cast<float*>(p.out0) + r * p.ld_out + c0;
+#pragma unroll
+            for (int j = 0; j < 16; j += 4)
+              __stcs(reinterpret_cast<float4*>(of + j),
+                     make_float4((float)v[j], (float)v[j + 1], (float)v[j + 2], (float)v[j + 3]));
+          } else if (p.wide_store) {  // 32-byte aligned rows: one full sector per store
 #pragma unroll
             for (int j = 0; j < 16; j += 4) st_256(o + j, v[j], v[j + 1], v[j + 2], v[j + 3]);
           } else {
@@ -798,22 +806,15 @@ int launch_mode(int mode, const CUtensorMap& ma, const CUtensorMap& mb, const Ge
 namespace dpb200 {
 namespace {
 long long* g_fit_dbg = nullptr;
-}
-}  // namespace dpb200
 
-extern "C" {
-
-/* profiling hook: device buffer of [grid][16] cycle counters filled by the next fit_gemm launches (NULL: off) */
-void dpb200_fit_gemm_debug(long long* dbg) { dpb200::g_fit_dbg = dbg; }
-
-int dpb200_fit_gemm_i8_f64(int mode, long long nrow, int N, int K, int nslice, const signed char* a_slices,
+template <int NS>
+int fit_gemm_impl(int mode, long long nrow, int N, int K, int nslice, const signed char* a_slices,
                            long long a_slice_stride, long long a_row_stride, const int* row_exp, int row_exp_fixed,
                            const signed char* b_slices, int b_k_stride, const double* colv, const double* skip,
                            const double* t_in, double* out0, double* out1, long long ld_out, signed char* slices_out,
                            long long ld_slices, int kp_out, int out_exp, dpb200_stream_t stream) {
-  using namespace dpb200;
-  DPB_REQUIRE(mode >= 0 && mode <= 2, "fit_gemm: mode must be 0 (forward), 1 (backward) or 2 (plain)");
-  DPB_REQUIRE(nslice == 6, "fit_gemm: only 6 operand slices are built");
+  const bool out_f32 = mode == 3;  // plain product stored as float
+  if (out_f32) mode = EPI_PLAIN;
   DPB_REQUIRE(nrow >= 0 && N >= 16 && N % 16 == 0 && K >= 1, "fit_gemm: N must be a positive multiple of 16");
   if (nrow == 0) return DPB200_OK;
   DPB_REQUIRE(a_slices && b_slices && colv && (out0 || mode == EPI_BWD) && ((uintptr_t)colv & 31) == 0,
@@ -826,7 +827,7 @@ int dpb200_fit_gemm_i8_f64(int mode, long long nrow, int N, int K, int nslice, c
   DPB_REQUIRE(!slices_out || (kp_out % 16 == 0 && kp_out >= N && ld_slices >= (long long)nslice * kp_out &&
                               ((uintptr_t)slices_out & 15) == 0 && ld_slices % 16 == 0),
               "fit_gemm: bad slice output layout");
-  constexpr int NS = 6, NT = 80;
+  constexpr int NT = 80;
   GemmParams p;
   p.n = nrow;
   p.N = N;
@@ -847,6 +848,8 @@ int dpb200_fit_gemm_i8_f64(int mode, long long nrow, int N, int K, int nslice, c
   p.ld_out = ld_out;
   p.dbg = g_fit_dbg;
   p.wide_store = (mode == EPI_PLAIN && ld_out % 4 == 0 && ((uintptr_t)out0 & 31) == 0) ? 1 : 0;
+  p.out_f32 = out_f32 ? 1 : 0;
+  DPB_REQUIRE(!out_f32 || (ld_out % 4 == 0 && ((uintptr_t)out0 & 15) == 0), "fit_gemm: float output rows must be 16-byte aligned");
   CUtensorMap ma, mb;
   // Cluster width: the CTAs of a cluster share A by TMA multicast (csrc kernel comment).  DPB200_FIT_CLUSTER=1
   // switches the sharing off (comparison runs).
@@ -856,9 +859,9 @@ int dpb200_fit_gemm_i8_f64(int mode, long long nrow, int N, int K, int nslice, c
   }();
   int cn = 1;
   if (p.n_tiles % 4 == 0 && nrow >= 4 * kTileM) cn = 4;
-  else if (p.n_tiles % 3 == 0 && nrow >= 3 * kTileM) cn = 3;
+  else if (NS == 6 && p.n_tiles % 3 == 0 && nrow >= 3 * kTileM) cn = 3;
   if (cluster_env == 1 || (cluster_env > 1 && p.n_tiles % cluster_env != 0)) cn = 1;
-  else if (cluster_env == 3 || cluster_env == 4) cn = cluster_env;
+  else if ((cluster_env == 3 && NS == 6) || cluster_env == 4) cn = cluster_env;
   // A: [nrow][nslice][K] bytes seen as {K, row, slice} (byte strides given); the box lands in shared memory as
   // [slice][row][64]; rows / K beyond the tensor are zero-filled by TMA
   const unsigned a_rows = cn == 4 ? kTileM / 4 : kTileM, a_slices_box = cn == 1 ? NS / 2 : 1;
@@ -871,21 +874,53 @@ int dpb200_fit_gemm_i8_f64(int mode, long long nrow, int N, int K, int nslice, c
   if (rc != DPB200_OK) return rc;
   cudaStream_t st = (cudaStream_t)stream;
   if (cn == 4) return launch_mode<NS, NT, 4>(mode, ma, mb, p, st);
-  if (cn == 3) return launch_mode<NS, NT, 3>(mode, ma, mb, p, st);
+  if constexpr (NS == 6) {
+    if (cn == 3) return launch_mode<NS, NT, 3>(mode, ma, mb, p, st);
+  }
   return launch_mode<NS, NT, 1>(mode, ma, mb, p, st);
+}
+
+}  // namespace
+}  // namespace dpb200
+
+extern "C" {
+
+/* profiling hook: device buffer of [grid][16] cycle counters filled by the next fit_gemm launches (NULL: off) */
+void dpb200_fit_gemm_debug(long long* dbg) { dpb200::g_fit_dbg = dbg; }
+
+int dpb200_fit_gemm_i8_f64(int mode, long long nrow, int N, int K, int nslice, const signed char* a_slices,
+                           long long a_slice_stride, long long a_row_stride, const int* row_exp, int row_exp_fixed,
+                           const signed char* b_slices, int b_k_stride, const double* colv, const double* skip,
+                           const double* t_in, double* out0, double* out1, long long ld_out, signed char* slices_out,
+                           long long ld_slices, int kp_out, int out_exp, dpb200_stream_t stream) {
+  using namespace dpb200;
+  DPB_REQUIRE(mode >= 0 && mode <= 3,
+              "fit_gemm: mode must be 0 (forward), 1 (backward), 2 (plain) or 3 (plain, float output)");
+  DPB_REQUIRE(nslice == 6 || nslice == 4, "fit_gemm: built for 6 (fp64 model) or 4 (fp32 model) operand slices");
+  if (nslice == 4)
+    return fit_gemm_impl<4>(mode, nrow, N, K, nslice, a_slices, a_slice_stride, a_row_stride, row_exp, row_exp_fixed,
+                            b_slices, b_k_stride, colv, skip, t_in, out0, out1, ld_out, slices_out, ld_slices, kp_out,
+                            out_exp, stream);
+  return fit_gemm_impl<6>(mode, nrow, N, K, nslice, a_slices, a_slice_stride, a_row_stride, row_exp, row_exp_fixed,
+                          b_slices, b_k_stride, colv, skip, t_in, out0, out1, ld_out, slices_out, ld_slices, kp_out,
+                          out_exp, stream);
 }
 
 int dpb200_fit_slice_rows_f64(signed char* out, long long ld_out, int kp, int* row_exp, const double* x,
                               long long nrow, int N, int nslice, dpb200_stream_t stream) {
   using namespace dpb200;
-  DPB_REQUIRE(nslice == 6, "fit_slice_rows: only 6 operand slices are built");
+  DPB_REQUIRE(nslice == 6 || nslice == 4, "fit_slice_rows: built for 6 or 4 operand slices");
   DPB_REQUIRE(nrow >= 0 && N >= 16 && N % 16 == 0 && N <= 512 && kp == N && ld_out >= (long long)nslice * kp &&
                   ld_out % 16 == 0,
               "fit_slice_rows: N must be a multiple of 16 up to 512 and kp == N");
   if (nrow == 0) return DPB200_OK;
   DPB_REQUIRE(out && row_exp && x && ((uintptr_t)out & 15) == 0, "fit_slice_rows: null or unaligned pointer");
-  k_fit_slice<6, false><<<(unsigned)((nrow + 31) / 32), 32 * (N / 16), 0, (cudaStream_t)stream>>>(
-      out, ld_out, kp, row_exp, x, nullptr, nullptr, nullptr, 0., nullptr, nrow, N);
+  if (nslice == 6)
+    k_fit_slice<6, false><<<(unsigned)((nrow + 31) / 32), 32 * (N / 16), 0, (cudaStream_t)stream>>>(
+        out, ld_out, kp, row_exp, x, nullptr, nullptr, nullptr, 0., nullptr, nrow, N);
+  else
+    k_fit_slice<4, false><<<(unsigned)((nrow + 31) / 32), 32 * (N / 16), 0, (cudaStream_t)stream>>>(
+        out, ld_out, kp, row_exp, x, nullptr, nullptr, nullptr, 0., nullptr, nrow, N);
   DPB_CUDA(cudaGetLastError());
   note_launches(1);
   return DPB200_OK;
@@ -895,15 +930,19 @@ int dpb200_fit_head_f64(double* e_out, signed char* out, long long ld_out, int k
                         const double* y, const double* w_head, const double* idt, double b_head, long long nrow,
                         int N, int nslice, dpb200_stream_t stream) {
   using namespace dpb200;
-  DPB_REQUIRE(nslice == 6, "fit_head: only 6 operand slices are built");
+  DPB_REQUIRE(nslice == 6 || nslice == 4, "fit_head: built for 6 or 4 operand slices");
   DPB_REQUIRE(nrow >= 0 && N >= 16 && N % 16 == 0 && N <= 512 && kp == N && ld_out >= (long long)nslice * kp &&
                   ld_out % 16 == 0,
               "fit_head: N must be a multiple of 16 up to 512 and kp == N");
   if (nrow == 0) return DPB200_OK;
   DPB_REQUIRE(e_out && out && row_exp && t && y && w_head && ((uintptr_t)out & 15) == 0,
               "fit_head: null or unaligned pointer");
-  k_fit_slice<6, true><<<(unsigned)((nrow + 31) / 32), 32 * (N / 16), 0, (cudaStream_t)stream>>>(
-      out, ld_out, kp, row_exp, t, y, w_head, idt, b_head, e_out, nrow, N);
+  if (nslice == 6)
+    k_fit_slice<6, true><<<(unsigned)((nrow + 31) / 32), 32 * (N / 16), 0, (cudaStream_t)stream>>>(
+        out, ld_out, kp, row_exp, t, y, w_head, idt, b_head, e_out, nrow, N);
+  else
+    k_fit_slice<4, true><<<(unsigned)((nrow + 31) / 32), 32 * (N / 16), 0, (cudaStream_t)stream>>>(
+        out, ld_out, kp, row_exp, t, y, w_head, idt, b_head, e_out, nrow, N);
   DPB_CUDA(cudaGetLastError());
   note_launches(1);
   return DPB200_OK;

@@ -469,6 +469,8 @@ __device__ __forceinline__ void poly_both(const FP (&a)[6], FP x, FP& g, FP& gd)
 //           first, int8 [row][nslice][M*axis] + row_exp[row] (split-integer GEMM on the int8
 //           tensor cores, error-free products, fp64-grade sums);
 //           fp32: TF32 head and tail, float [row][2][M*axis] (3xTF32 GEMM).
+//   mode 3  fp32 only: four int8 digit slices [row][4][M*axis] + row_exp[row] (the fp32 model's operand of the
+//           same int8 tensor-core GEMMs).
 // The first `axis` columns of s*GR are staged in the (idle) per-warp record buffer and read back
 // as broadcasts.
 // ------------------------------------------------------------------------------------------
@@ -507,6 +509,63 @@ __device__ __forceinline__ void desc_store_split(const TabParams<float>& p, cons
     }
   }
 }
+
+// mode 3 (fp32): four balanced base-256 digit slices of the row's 32-bit fixed-point image + row exponent -- the
+// A operand of the int8 tensor-core fitting GEMMs (csrc/fit_tc.cu, NS = 4: 31 fraction bits below the row maximum).
+template <int NC>
+__device__ __forceinline__ void desc_store_split_i8(const TabParams<float>& p, const float (&A)[4][NC], float s2,
+                                                    const float* __restrict__ stage, long long row, int lane) {
+  const int M = p.M;
+  float r2 = 0.f;  // Cauchy-Schwarz: |D[k1][k2]| <= max_k |A[:,k]|^2
+#pragma unroll
+  for (int c = 0; c < NC; ++c) {
+    const float n2 = A[0][c] * A[0][c] + A[1][c] * A[1][c] + A[2][c] * A[2][c] + A[3][c] * A[3][c];
+    r2 = (lane + 32 * c < M && n2 > r2) ? n2 : r2;
+  }
+  r2 *= s2;
+  int e = (int)((__float_as_uint(r2) >> 23) & 0xffu) - 127;
+  e = __reduce_max_sync(kFull, e);
+  int E = e + 2;  // |D| < 2^(E-1)
+  E = E < -90 ? -90 : (E > 100 ? 100 : E);
+  if (lane == 0) p.row_exp[row] = E;
+  const float up = s2 * __uint_as_float((unsigned)(127 + 31 - E) << 23);
+  signed char* __restrict__ base = reinterpret_cast<signed char*>(p.desc) + row * p.desc_ld;
+  const long long K = (long long)M * 16;
+#pragma unroll
+  for (int c = 0; c < NC; ++c) {
+    const int k1 = lane + 32 * c;
+    if (k1 < M) {
+      unsigned u[16];
+#pragma unroll
+      for (int t = 0; t < 16; t += 4) {
+        float v[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+        for (int m = 0; m < 4; ++m) {
+          const float4 b = *reinterpret_cast<const float4*>(stage + m * 16 + t);
+          v[0] += A[m][c] * b.x, v[1] += A[m][c] * b.y, v[2] += A[m][c] * b.z, v[3] += A[m][c] * b.w;
+        }
+#pragma unroll
+        for (int q = 0; q < 4; ++q) u[t + q] = (unsigned)__float2int_rn(v[q] * up) + 0x80808080u;
+      }
+#pragma unroll
+      for (int s = 0; s < 4; ++s) {  // slice s = byte 3-s of the image, top bit flipped = signed digit
+        const unsigned kb = 3u - (unsigned)s;
+        const unsigned sel = kb | ((4u + kb) << 4);
+        unsigned w[4];
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          const unsigned t0 = __byte_perm(u[4 * g], u[4 * g + 1], sel);
+          const unsigned t1 = __byte_perm(u[4 * g + 2], u[4 * g + 3], sel);
+          w[g] = __byte_perm(t0, t1, 0x5410) ^ 0x80808080u;
+        }
+        *reinterpret_cast<uint4*>(base + s * K + (long long)k1 * 16) = make_uint4(w[0], w[1], w[2], w[3]);
+      }
+    }
+  }
+}
+template <int NC>
+__device__ __forceinline__ void desc_store_split_i8(const TabParams<double>&, const double (&)[4][NC], double,
+                                                    const double*, long long, int) {}
 
 template <int NC>
 __device__ __forceinline__ void desc_store_split(const TabParams<double>& p, const double (&A)[4][NC], double s2,
@@ -583,7 +642,9 @@ __device__ __forceinline__ void desc_epilogue(const TabParams<FP>& p, const FP (
     for (int m = 0; m < 4; ++m) stage[m * axis + lane] = acc[m][0];
   }
   __syncwarp();
-  if (p.desc_mode == 2) {
+  if (p.desc_mode == 3) {
+    desc_store_split_i8<NC>(p, acc, s2, stage, row, lane);
+  } else if (p.desc_mode == 2) {
     desc_store_split<NC>(p, acc, s2, stage, row, lane);
   } else {
     FP* __restrict__ d = reinterpret_cast<FP*>(p.desc) + row * p.desc_ld;
@@ -1743,7 +1804,8 @@ int launch_fwd(FP* out, const FP* table, const FP* info, const FP* em_x, long lo
   if constexpr (!GG) if (da) {
     const bool plain = two == nullptr && nnei > 0;
     DPB_REQUIRE(plain, "tabulate+descriptor: plain se_a forward with nnei > 0 only");
-    DPB_REQUIRE(da->desc != nullptr && (da->mode == 1 || da->mode == 2), "tabulate+descriptor: desc is null / bad mode");
+    DPB_REQUIRE(da->desc != nullptr && (da->mode == 1 || da->mode == 2 || (da->mode == 3 && sizeof(FP) == 4)),
+                "tabulate+descriptor: desc is null / bad mode (3 = int8 slices of an fp32 descriptor)");
     DPB_REQUIRE(M <= 128 && da->axis >= 1 && da->axis <= 32 && da->axis <= M,
                 "tabulate+descriptor: needs M <= 128 and axis <= min(32, M)");
     DPB_REQUIRE(aligned16(da->desc), "tabulate+descriptor: desc must be 16-byte aligned");
@@ -1751,6 +1813,10 @@ int launch_fwd(FP* out, const FP* table, const FP* info, const FP* em_x, long lo
       DPB_REQUIRE(da->axis == 16 && da->nslice >= 2 && da->nslice <= 8 && da->row_exp != nullptr &&
                       da->desc_ld % 16 == 0 && da->desc_ld >= (long long)da->nslice * M * 16,
                   "tabulate+descriptor: int8 split needs axis == 16, 2 <= nslice <= 8, row_exp, 16-byte rows");
+    } else if (da->mode == 3) {
+      DPB_REQUIRE(da->axis == 16 && da->nslice == 4 && da->row_exp != nullptr && da->desc_ld % 16 == 0 &&
+                      da->desc_ld >= 4LL * M * 16,
+                  "tabulate+descriptor: fp32 int8 split needs axis == 16, nslice == 4, row_exp, 16-byte rows");
     } else if (da->mode == 2) {
       DPB_REQUIRE(da->axis % 4 == 0 && da->desc_ld % 4 == 0 && da->desc_ld >= 2LL * M * da->axis,
                   "tabulate+descriptor: TF32 split needs axis % 4 == 0 and 16-byte rows of >= 2*M*axis floats");

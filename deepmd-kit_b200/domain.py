@@ -9,9 +9,11 @@ send/recv over the 26 neighbour directions (<= 7 distinct peers on 2x2x2, self-i
 locally), bracketed by the dpb200 pack / unpack-accumulate kernels.  Energy and virial leave as
 one 10-scalar all-reduce.
 
-Atoms are not migrated between bricks here (the benchmark boxes are static); an atom that drifts
-out of its brick by less than the skin is still handled correctly because the ghost shell is
-selected with rcut + skin.
+Atom migration (`migrate_atoms`, `DomainDeepPot.exchange_atoms`): when the list is rebuilt, atoms whose
+wrapped coordinate has left the brick are handed to the rank that owns their new position (LAMMPS
+`Comm::exchange`, which runs before `Comm::borders` on every reneighbouring step; the reference sees its
+result as a changed nlocal / ilist, source/lmp/pair_deepmd.cpp:217-229).  Between rebuilds an atom may sit
+outside its brick by up to skin / 2: the ghost shell is selected with rcut + skin.
 """
 from __future__ import annotations
 
@@ -54,6 +56,92 @@ def coords_to_rank(c: Sequence[int], grid: Sequence[int]) -> int:
     return ((c[0] % gx) * gy + (c[1] % gy)) * gz + (c[2] % gz)
 
 
+def migrate_atoms(coord: torch.Tensor, atype: torch.Tensor, box, grid, rank: int, group=None,
+                  payload: Sequence[torch.Tensor] = ()):
+    """Hand every atom to the rank whose brick contains its periodically wrapped position.
+
+    coord [n, 3], atype [n], payload = per-atom tensors ([n] or [n, k]; ids, velocities, ...) that travel with the
+    atoms.  Returns (coord, atype, payload) of this rank afterwards: the atoms that stayed (original order, wrapped
+    into the box) followed by the arrivals in direction order.  One grouped exchange over the 26 neighbour
+    directions, like the halo; an atom that moved further than the neighbouring brick is an error (the caller
+    rebuilt too rarely).  Device-agnostic torch code: the gloo tests run it on the CPU."""
+    grid = tuple(int(x) for x in grid)
+    world = grid[0] * grid[1] * grid[2]
+    dev, dt = coord.device, coord.dtype
+    c = coord.reshape(-1, 3)
+    n = c.shape[0]
+    b = torch.as_tensor(np.asarray(box, np.float64).reshape(3, 3), device=dev)
+    rec = torch.linalg.inv(b)
+    s = c.to(torch.float64) @ rec
+    wrap = torch.floor(s)
+    s = s - wrap
+    c = (c.to(torch.float64) - wrap @ b).to(dt)
+    me = rank_to_coords(rank, grid)
+    gt = torch.as_tensor(grid, dtype=torch.float64, device=dev)
+    bi = torch.clamp(torch.floor(s * gt).to(torch.int64), min=torch.zeros(3, dtype=torch.int64, device=dev),
+                     max=torch.as_tensor(grid, dtype=torch.int64, device=dev) - 1)
+    delta = bi - torch.as_tensor(me, dtype=torch.int64, device=dev)
+    for d in range(3):  # minimum image on the process grid: -1, 0, +1 (+1 when both are the same peer)
+        gd = grid[d]
+        dd = torch.remainder(delta[:, d], gd)
+        dd = torch.where(dd > gd // 2, dd - gd, dd)
+        if gd == 2:
+            dd = torch.abs(dd)
+        delta[:, d] = dd
+    if n and bool((delta.abs() > 1).any()):
+        raise ValueError(f"rank {rank}: an atom moved past the neighbouring brick between two list rebuilds")
+    cols = [c.to(torch.float64), atype.reshape(-1, 1).to(torch.float64)]
+    shapes = []
+    for q in payload:
+        q2 = q.reshape(n, -1)
+        shapes.append((q.dtype, tuple(q.shape[1:])))
+        cols.append(q2.to(torch.float64))
+    rows = torch.cat(cols, 1).contiguous()
+    width = rows.shape[1]
+    code = (delta[:, 0] + 1) * 9 + (delta[:, 1] + 1) * 3 + (delta[:, 2] + 1)  # 13 = stays
+    send, dests, srcs = [], [], []
+    for (dx, dy, dz) in DIRS:
+        k = (dx + 1) * 9 + (dy + 1) * 3 + (dz + 1)
+        send.append(rows[code == k])
+        dests.append(coords_to_rank((me[0] + dx, me[1] + dy, me[2] + dz), grid))
+        srcs.append(coords_to_rank((me[0] - dx, me[1] - dy, me[2] - dz), grid))
+    keep = rows[code == 13]
+    cnt = torch.tensor([int(x.shape[0]) for x in send], dtype=torch.int64, device=dev)
+    if world > 1:
+        allc = torch.empty(world * len(DIRS), dtype=torch.int64, device=dev)
+        dist.all_gather_into_tensor(allc, cnt, group=group)
+        allc = allc.reshape(world, len(DIRS)).cpu()
+    else:
+        allc = cnt.reshape(1, -1).cpu()
+    parts = [keep]
+    p2p = []
+    for k in range(len(DIRS)):
+        nrecv = int(allc[srcs[k], k])
+        if dests[k] == rank and srcs[k] == rank:  # a periodic self-image: the wrap above already placed the atom
+            parts.append(send[k])
+            continue
+        if send[k].shape[0]:
+            p2p.append(dist.P2POp(dist.isend, send[k].contiguous(), dests[k], group=group))
+        if nrecv:
+            buf = torch.empty((nrecv, width), dtype=torch.float64, device=dev)
+            p2p.append(dist.P2POp(dist.irecv, buf, srcs[k], group=group))
+            parts.append(buf)
+    if p2p:
+        for r in dist.batch_isend_irecv(p2p):
+            r.wait()
+    rows = torch.cat(parts, 0)
+    new_c = rows[:, :3].to(dt).contiguous()
+    new_t = rows[:, 3].round().to(atype.dtype).contiguous()
+    out, col = [], 4
+    for (qdt, tail) in shapes:
+        w = int(np.prod(tail)) if tail else 1
+        q = rows[:, col:col + w]
+        q = q.round().to(qdt) if not qdt.is_floating_point else q.to(qdt)
+        out.append(q.reshape((rows.shape[0],) + tail).contiguous())
+        col += w
+    return new_c, new_t, out
+
+
 class HaloPlan:
     """Send lists per direction, receive segments, peers.  Device-agnostic (torch ops only) so the
     N>1 host logic is testable with the gloo backend on CPU."""
@@ -81,7 +169,7 @@ class HaloPlan:
             out = ((s < torch.as_tensor(lo, device=dev) - tol) | (s >= torch.as_tensor(hi, device=dev) + tol)).any()
             if bool(out):
                 raise ValueError(f"rank {rank}: some atoms lie outside this rank's brick by more than {slack} "
-                                 "(atoms must be handed to the rank that owns them; there is no migration here)")
+                                 "(hand them to their owners first: DomainDeepPot.exchange_atoms)")
         lists, shifts, dests, srcs = [], [], [], []
         for (dx, dy, dz) in DIRS:
             m = torch.ones(c.shape[0], dtype=torch.bool, device=dev)
@@ -177,6 +265,17 @@ class DomainDeepPot(DeepPotB200):
             if ncell % self.grid[d]:
                 raise ValueError(f"ncell = {ncell} is not divisible by the process grid {self.grid}")
         return coord, np.zeros(len(coord), np.int32), np.eye(3) * L
+
+    def exchange_atoms(self, coord, atype, box, payload: Sequence[torch.Tensor] = ()):
+        """migrate_atoms for this rank's brick; the next eval_device rebuilds the halo plan and the list (the local
+        atom set changed).  An MD driver calls this whenever `needs_rebuild(...)` says so, before eval_device."""
+        out = migrate_atoms(coord.reshape(-1, 3), atype, box, self.grid, self.rank, self.group, payload)
+        self.state = None
+        return out
+
+    def needs_rebuild(self, coord, atype, box) -> bool:
+        """True on every rank when any rank's list is stale (collective)."""
+        return self._any_rank_stale(coord, atype, box)
 
     # -- host-side pieces (overridable for CPU tests) -----------------------------------------
     def _pack(self, coord, plan):

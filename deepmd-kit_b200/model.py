@@ -154,9 +154,10 @@ class FittingNet:
         """Weights of all GEMMs of the net (forward and backward) as balanced base-256 int8 digit slices in the B-operand
         layout of dpb200_fit_gemm_i8 ([nslice][N][K padded to 64], K contiguous) + column scales 2^(col_exp-12),
         and the fixed exponents of the hidden activations (|y_l| < sum_k<=l max|idt_k|).  Returns False when the
-        architecture is outside what csrc/fit_tc.cu covers (fp64, first layer without skip connection, equal-width
-        hidden layers)."""
-        if self.dtype != torch.float64:
+        architecture is outside what csrc/fit_tc.cu covers (first layer without skip connection, equal-width hidden
+        layers; 6 slices for an fp64 net, 4 for an fp32 net: 47 / 31 fraction bits per operand -- the fp32 net runs
+        through the same kernels, its intermediates are fp64, and dE/dD leaves the last GEMM as float32)."""
+        if (self.dtype, nslice) not in ((torch.float64, 6), (torch.float32, 4)):
             return False
         dev = self.layers[0][0].device
         widths = [w.shape for w, _, _ in self.layers]
@@ -195,8 +196,10 @@ class FittingNet:
             amp = 1.0 if idt is None else float(idt.abs().max())
             bound = amp if li == 0 else bound + amp
             tc["exp"].append(int(math.floor(math.log2(bound))) + 2)
-        tc["w_head"] = self.head[0][:, 0].contiguous()
+        tc["w_head"] = self.head[0][:, 0].to(torch.float64).contiguous()
         tc["b_head"] = float(self.head[1][0])
+        idt_last = self.layers[-1][2]
+        tc["idt_last"] = None if idt_last is None else idt_last.to(torch.float64).contiguous()
         self.tc = tc
         return True
 
@@ -230,7 +233,7 @@ class FittingNet:
                 a, a_ss, a_rs, a_exp, a_fixed, K = sl, kp_out, ns * kp_out, None, tc["exp"][li], kp_out
         N = self.layers[-1][0].shape[1]
         kp = (N + 15) // 16 * 16
-        e, dz, dz_exp = ops.fit_head(ts[-1], ys[-1], tc["w_head"], self.layers[-1][2], tc["b_head"], n, N, kp, ns)
+        e, dz, dz_exp = ops.fit_head(ts[-1], ys[-1], tc["w_head"], tc["idt_last"], tc["b_head"], n, N, kp, ns)
         g_prev = None
         for li in range(nl - 1, 0, -1):
             w, b, idt = self.layers[li]
@@ -245,9 +248,10 @@ class FittingNet:
             kp = (n_in + 15) // 16 * 16
             dz, dz_exp = ops.fit_slice_rows(dzn, n, n_in, kp, ns)
         bsl, cs, Kp = tc["bw"][0]
-        gd = torch.empty((n, K0), dtype=torch.float64, device=dev)
-        ops.fit_gemm_i8(2, n, K0, kp, dz, kp, ns * kp, dz_exp, 0, bsl, Kp, cs, out0=gd, ld_out=K0, nslice=ns)
-        return e, gd
+        gd = torch.empty((n, K0), dtype=self.dtype, device=dev)
+        ops.fit_gemm_i8(2 if self.dtype == torch.float64 else 3, n, K0, kp, dz, kp, ns * kp, dz_exp, 0, bsl, Kp, cs,
+                        out0=gd, ld_out=K0, nslice=ns)
+        return e.to(self.dtype), gd
 
     def to(self, device, dtype):
         self.layers = [(w.to(device, dtype), b.to(device, dtype), None if i is None else i.to(device, dtype))
@@ -438,12 +442,19 @@ class SeAModel:
                               (w0.shape[0], 2 * w0.shape[0]) and self.device.type == "cuda")
         # fp64: every GEMM of the net on the tcgen05 int8 path (csrc/fit_tc.cu); DPB200_FIT_TC=0 keeps the
         # library GEMMs (cuBLASLt int8 first layer + DGEMM) of round 1 as the comparison path.
+        # fp32: the same kernels with 4 slices (31 fraction bits); the descriptor leaves the table kernel as int8
+        # slices of its 32-bit fixed-point image (mode 3).  Without them: 3xTF32 library GEMMs (mode 2).
         self.use_tc = False
+        self.desc_mode, self.desc_nslice = 2, self.nslice
         if self.use_split:
             for f in self.fit:
                 f.prepare_split(self.nslice)
-            if dtype == torch.float64 and self.nslice == 6 and _os.environ.get("DPB200_FIT_TC", "1") != "0":
-                self.use_tc = all([f.prepare_tc(self.nslice) for f in self.fit])
+            if _os.environ.get("DPB200_FIT_TC", "1") != "0":
+                ns_tc = 6 if dtype == torch.float64 else 4
+                if cfg.axis_neuron == 16 and all([f.prepare_tc(ns_tc) for f in self.fit]):
+                    self.use_tc = True
+                    self.desc_nslice = ns_tc
+                    self.desc_mode = 2 if dtype == torch.float64 else 3
         # Compressed table coefficients (include/dpb200.h DPB200_TAB_COMPRESSED_COEF): the table kernels are bound by
         # the on-chip coefficient stream; for a dp-compress table the high-order terms tolerate fp32 / fp16 storage
         # at the 1e-12 level.  Checked per table here, on the host, once.
@@ -519,7 +530,7 @@ class SeAModel:
         cfg = self.cfg
         F = 8 if self.dtype == torch.float64 else 4
         K = self.M * cfg.axis_neuron
-        desc = (self.nslice * K if self.dtype == torch.float64 else 8 * K) if self.use_split else 0
+        desc = (self.desc_nslice * K if self.desc_mode == 3 or self.dtype == torch.float64 else 8 * K) if self.use_split else 0
         fit = max((sum(int(n) for n in cfg.fitting_neuron) * 3 + K) * F, 0) * min(1.0, self.fit_chunk / 1e6)
         return int(cfg.nnei * (4 + 12 + 3 + 4) * F + cfg.nnei * 4 + 3 * 4 * self.M * F + desc + fit)
 
@@ -542,8 +553,9 @@ class SeAModel:
                                                     cfg.rcut, cfg.rcut_smth, cfg.sec, row_range=(a, b))
             if self.use_split:
                 xyz, desc, row_exp = ops.tabulate_sections_desc(self.tables, self.infos, em, cfg.sec, self.M,
-                                                                cfg.axis_neuron, 1.0 / cfg.nnei, desc_row=inv, mode=2,
-                                                                nslice=self.nslice, pad_rows=32, flags=self.coef_flags)
+                                                                cfg.axis_neuron, 1.0 / cfg.nnei, desc_row=inv,
+                                                                mode=self.desc_mode, nslice=self.desc_nslice, pad_rows=32,
+                                                                flags=self.coef_flags)
                 _, e_c, dy = self.energy_and_dy_split(xyz, desc, row_exp, perm, ranges)
                 del desc
             else:
@@ -572,8 +584,9 @@ class SeAModel:
                 type_inv = torch.empty(nloc, dtype=torch.int32, device=type_perm.device)
                 type_inv[type_perm] = torch.arange(nloc, dtype=torch.int32, device=type_perm.device)
             xyz, desc, row_exp = ops.tabulate_sections_desc(self.tables, self.infos, em, cfg.sec, self.M,
-                                                            cfg.axis_neuron, 1.0 / cfg.nnei, desc_row=type_inv, mode=2,
-                                                            nslice=self.nslice, pad_rows=32, flags=self.coef_flags)
+                                                            cfg.axis_neuron, 1.0 / cfg.nnei, desc_row=type_inv,
+                                                            mode=self.desc_mode, nslice=self.desc_nslice, pad_rows=32,
+                                                            flags=self.coef_flags)
             energy, e_atom, dy = self.energy_and_dy_split(xyz, desc, row_exp, type_perm, type_ranges)
             del desc
         else:

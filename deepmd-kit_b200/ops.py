@@ -659,7 +659,9 @@ def tabulate_sections_desc(tables, infos, em, sec, last_layer_size, axis, scale,
     epilogue (dpb200_tabulate_fusion_se_a_desc).  Returns (out [nloc,4,M], desc, row_exp|None):
       mode 1            desc = D [nloc+pad, M*axis] in em.dtype;
       mode 2, float64   desc = int8 [nloc+pad, nslice*M*axis] balanced base-256 digit slices, row_exp int32 [nloc+pad];
-      mode 2, float32   desc = float32 [nloc+pad, 2*M*axis] = TF32 head | tail.
+      mode 2, float32   desc = float32 [nloc+pad, 2*M*axis] = TF32 head | tail;
+      mode 3, float32   desc = int8 [nloc+pad, 4*M*axis] digit slices of the 32-bit fixed-point image, row_exp int32
+                        (operand of the int8 tensor-core fitting net, nslice = 4).
     Row desc_row[i] (int32; None: i) belongs to atom i; `pad_rows` extra zero rows are appended.
     flags: per-table DPB200_TAB_COMPRESSED_COEF words from `compressed_coef_flags` (None: full fp64 coefficients)."""
     dev = _need_cuda(("em", em), ("desc_row", desc_row))
@@ -675,7 +677,9 @@ def tabulate_sections_desc(tables, infos, em, sec, last_layer_size, axis, scale,
     row_exp = None
     if mode == 1:
         desc = torch.empty((rows, K), dtype=em.dtype, device=dev)
-    elif em.dtype == torch.float64:
+    elif em.dtype == torch.float64 or mode == 3:
+        if mode == 3 and (em.dtype != torch.float32 or int(nslice) != 4):
+            raise ValueError("dpb200: descriptor mode 3 is the float32 form with nslice = 4")
         desc = torch.empty((rows, int(nslice) * K), dtype=torch.int8, device=dev)
         row_exp = torch.empty((rows,), dtype=torch.int32, device=dev)
         if pad_rows:
@@ -783,7 +787,8 @@ def fit_gemm_i8(mode, n, N, K, a_slices, a_slice_stride, a_row_stride, row_exp, 
                 colv, skip=None, t_in=None, out0=None, out1=None, ld_out=0, slices_out=None, ld_slices=0, kp_out=0,
                 out_exp=0, nslice=6):
     """One fitting-net GEMM on the int8 tensor cores (dpb200_fit_gemm_i8_f64, csrc/fit_tc.cu): mode 0 forward layer,
-    1 backward layer, 2 plain product.  colv [N, 4] = {2^(col_exp-12), add, mul, 0} per output column; fp64
+    1 backward layer, 2 plain product, 3 plain product stored as float32 (out0 is a float32 matrix).  nslice 6 (fp64
+    model) or 4 (fp32 model).  colv [N, 4] = {2^(col_exp-12), add, mul, 0} per output column; fp64
     intermediates are in the row-blocked layout of fit_blocked()."""
     dev = _need_cuda(("a_slices", a_slices), ("b_slices", b_slices), ("colv", colv), ("row_exp", row_exp),
                      ("skip", skip), ("t_in", t_in), ("out0", out0), ("out1", out1), ("slices_out", slices_out))

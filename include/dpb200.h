@@ -163,7 +163,9 @@ DPB200_DECL_ENV(f32, float)
    *   desc_mode 0: no descriptor (plain `_ex` forward, but honouring `flags`);                     \
    *   desc_mode 1: FP [M*axis];                                                                    \
    *   desc_mode 2, f64: int8 [nslice][M*axis] balanced base-256 digit slices (most significant first) of     \
-   *     D * 2^-row_exp[row] (needs axis == 16);  f32: float [2][M*axis] = TF32 head | tail.        \
+   *     D * 2^-row_exp[row] (needs axis == 16);  f32: float [2][M*axis] = TF32 head | tail;         \
+   *   desc_mode 3, f32 only: int8 [4][M*axis] digit slices of the 32-bit fixed-point image of       \
+   *     D * 2^-row_exp[row] (axis == 16, nslice == 4): operand of dpb200_fit_gemm_i8 with nslice 4.  \
    * M <= 128, axis <= 32, desc 16-byte aligned.                                                   \
    * flags: DPB200_TAB_COMPRESSED_COEF (f64 only, ignored for f32) = the caller has checked that    \
    * for THIS table a3, a4 may be rounded to fp32, a5 to fp16 and a2 to 36 mantissa bits (true for  \
@@ -362,7 +364,11 @@ int dpb200_split_tf32_f32(float* out, long long ld_out, const float* x, long lon
  *                        [nrow][nslice][kp_out] int8 with the fixed exponent out_exp   (add = bias, mul = idt);
  *                mode 1  g = C + add (+ skip), dz = g*mul*(1 - t_in^2): out0 = g (nullable), out1 = dz
  *                        (add = head weights or 0, mul = idt of the layer below);
- *                mode 2  out0[r*ld_out + c] = C  (row-major).
+ *                mode 2  out0[r*ld_out + c] = C  (row-major);
+ *                mode 3  the same with `out0` pointing to a FLOAT matrix (16-byte aligned rows): dE/dD of an fp32
+ *                        model.
+ *                nslice = 6 (fp64 model: 47 fraction bits per operand) or 4 (fp32 model: 31 bits; the A operand of
+ *                the first layer is then the mode-3 descriptor of dpb200_tabulate_fusion_se_a_desc_f32).
  *  fit_slice_rows : blocked fp64 [nrow][N] -> int8 slices [nrow][nslice][kp] + row_exp (A operand of mode 1 / 2).
  *  fit_head    : e[r] = y[r,:].w_head + b_head and the backward seed dz = w_head*idt*(1 - t^2) as slices.
  *  fit_blocked : row-major <-> blocked conversion (tests, callers that keep row-major activations).

@@ -106,6 +106,27 @@ def main():
     # public host API on every rank
     eh, fh, vh = dp.eval(coord.reshape(1, -1), box.reshape(1, 9), atype)
     assert abs(eh[0, 0] - float(er)) < 1e-10 * abs(float(er))
+    # atom migration: the whole system drifts by more than skin / 2 (atoms cross brick faces and the periodic
+    # boundary), every rank hands its leavers to their new owners, and the decomposed evaluation still equals the
+    # single-GPU one of the same moved system, atom by atom (global ids travel as payload)
+    drift = np.array([3.1, -2.7, 1.3])
+    ids = torch.arange(off[rank], off[rank + 1], dtype=torch.int64, device=dev)
+    moved = c_d + torch.as_tensor(drift, dtype=dtype, device=dev)
+    assert dp.needs_rebuild(moved, t_d, box)
+    c_m, t_m, (ids_m,) = dp.exchange_atoms(moved, t_d, box, payload=(ids,))
+    n_m = torch.tensor([t_m.numel()], dtype=torch.int64, device=dev)
+    dist.all_reduce(n_m)
+    assert int(n_m.item()) == len(gt)
+    em_, fm, vm, _ = dp.eval_device(c_m, t_m, box)
+    er2, fr2, vr2, _ = ref.eval_device(torch.as_tensor(gc + drift).to(dev), torch.as_tensor(gt).to(dev), box)
+    ferr2 = float((fm - fr2[ids_m]).abs().max() / fr2.abs().max())
+    eerr2 = float(abs(em_ - er2) / abs(er2))
+    verr2 = float((vm - vr2).abs().max() / vr2.abs().max())
+    changed = int((ids_m.numel() != ids.numel()) or not torch.equal(ids_m, ids))
+    print(f"[rank {rank}/{world}] after migration: nloc {t_m.numel()} (owner set changed: {changed}) "
+          f"rel.err energy {eerr2:.2e} force {ferr2:.2e} virial {verr2:.2e}", flush=True)
+    assert eerr2 < 1e-10 and ferr2 < 1e-10 and verr2 < 1e-10
+    assert world == 1 or changed
     dist.barrier()
     dist.destroy_process_group()
     if rank == 0:

@@ -102,6 +102,77 @@ def test_halo_plan_gloo(tmp_path, world, grid):
     assert all(os.path.exists(tmp_path / f"ok{r}") for r in range(world))
 
 
+def _migrate_worker(rank, world, port, grid, out_dir):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        g.load_package()
+        from deepmd_kit_b200.domain import HaloPlan, migrate_atoms, rank_to_coords
+
+        rng = np.random.default_rng(7 + rank)
+        Lb = np.array([9.0, 8.0, 7.5])
+        me = np.array(rank_to_coords(rank, grid))
+        box = np.diag(Lb * np.array(grid))
+        nloc = 400 + 11 * rank
+        coord = rng.uniform(0, 1, size=(nloc, 3)) * Lb + me * Lb
+        ids = np.arange(nloc, dtype=np.int64) + 100000 * rank
+        atype = (ids % 3).astype(np.int32)
+        vel = np.stack([ids * 0.5, -ids * 0.25, ids * 1e-3], 1)
+        moved = coord + rng.uniform(-2.5, 2.5, size=coord.shape)  # crosses faces, edges, corners and the periodic wrap
+        c2, t2, (id2, v2) = migrate_atoms(torch.as_tensor(moved), torch.as_tensor(atype), box, grid, rank, None,
+                                          payload=(torch.as_tensor(ids), torch.as_tensor(vel)))
+        c2, t2, id2, v2 = c2.numpy(), t2.numpy(), id2.numpy(), v2.numpy()
+        assert t2.dtype == np.int32 and id2.dtype == np.int64 and c2.shape == (len(id2), 3)
+        lo, hi = me * Lb, (me + 1) * Lb
+        assert np.all((c2 >= lo - 1e-9) & (c2 < hi + 1e-9)), "an atom is outside its new owner's brick"
+        assert np.array_equal(t2, (id2 % 3).astype(np.int32))
+        assert np.allclose(v2, np.stack([id2 * 0.5, -id2 * 0.25, id2 * 1e-3], 1))
+        # nothing lost, nothing duplicated; every atom sits at its wrapped position
+        got = [None] * world
+        dist.all_gather_object(got, (id2, c2))
+        sent = [None] * world
+        dist.all_gather_object(sent, (ids, moved))
+        all_ids = np.concatenate([x[0] for x in got])
+        assert len(all_ids) == len(set(all_ids.tolist())) == sum(len(x[0]) for x in sent)
+        want = {int(i): p for ii, pp in sent for i, p in zip(ii, pp)}
+        Lg = np.diag(box)
+        for i, p in zip(id2, c2):
+            w = want[int(i)] - np.floor(want[int(i)] / Lg) * Lg
+            assert np.allclose(p, w, atol=1e-9)
+        # the halo plan accepts the migrated atoms (it refuses atoms outside the brick)
+        HaloPlan(torch.as_tensor(c2), box, grid, rank, 2.0)
+        # an atom that skipped a whole brick is an error, not a silent misplacement
+        if grid[0] >= 3 and rank == 0:
+            far = coord.copy()
+            far[0, 0] += 2 * Lb[0]
+            with pytest.raises(ValueError):
+                migrate_atoms(torch.as_tensor(far), torch.as_tensor(atype), box, grid, rank, None)
+        open(os.path.join(out_dir, f"ok{rank}"), "w").write("ok")
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world,grid", [(2, (2, 1, 1)), (4, (2, 2, 1))])
+def test_atom_migration_gloo(tmp_path, world, grid):
+    g.build()
+    port = _free_port()
+    mp.spawn(_migrate_worker, args=(world, port, grid, str(tmp_path)), nprocs=world, join=True)
+    assert all(os.path.exists(tmp_path / f"ok{r}") for r in range(world))
+
+
+def test_atom_migration_single_rank_wraps():
+    g.load_package()
+    from deepmd_kit_b200.domain import migrate_atoms
+
+    box = np.diag([5.0, 6.0, 7.0])
+    c = torch.tensor([[5.5, -0.5, 3.0], [1.0, 2.0, 14.5]], dtype=torch.float64)
+    t = torch.tensor([1, 0], dtype=torch.int32)
+    c2, t2, (q,) = migrate_atoms(c, t, box, (1, 1, 1), 0, None, payload=(torch.tensor([7, 8]),))
+    assert torch.allclose(c2, torch.tensor([[0.5, 5.5, 3.0], [1.0, 2.0, 0.5]], dtype=torch.float64))
+    assert t2.tolist() == [1, 0] and q.tolist() == [7, 8]
+
+
 def test_proc_grid():
     g.load_package()
     from deepmd_kit_b200.domain import coords_to_rank, proc_grid, rank_to_coords

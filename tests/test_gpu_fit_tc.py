@@ -56,6 +56,55 @@ def test_fit_gemm_plain_matches_fp64(pkg, n, K, N):
     assert ((out - want).abs() / scale).max().item() < 1e-12
 
 
+@pytest.mark.parametrize("n,K,N", [(130, 64, 80), (300, 1600, 240), (257, 240, 1600), (600, 128, 160)])
+def test_fit_gemm_four_slices(pkg, n, K, N):
+    """nslice = 4 (the fp32 model's operands: 31 fraction bits below 2^E with max in [2^(E-2), 2^(E-1)), orders >= 4
+    dropped: a few 2^-28 per term; measured 2^-26.5): product to 2^-25 of the row x column scale, stored as
+    fp64 (mode 2) and as float32 (mode 3).  Column-tile counts 1, 2 (cluster 1), 3 (no 3-wide cluster for 4 slices)
+    and 20 (cluster 4)."""
+    ops = pkg.ops
+    g = torch.Generator().manual_seed(n + K + N)
+    x = torch.randn(n, K, generator=g, dtype=torch.float64) * torch.exp(2 * torch.randn(n, 1, generator=g, dtype=torch.float64))
+    w = torch.randn(K, N, generator=g, dtype=torch.float64) / K ** 0.5
+    xd = x.to(DEV)
+    xs, ex = ops.split_i8_rows(xd, 4)
+    bsl, colv, Kp = _pack(w, 4)
+    want = xd @ w.to(DEV)
+    scale = xd.abs().amax(1, keepdim=True) * w.to(DEV).abs().amax(0, keepdim=True) * K ** 0.5
+    out = torch.full((n, N), float("nan"), dtype=torch.float64, device=DEV)
+    ops.fit_gemm_i8(2, n, N, K, xs, K, 4 * K, ex, 0, bsl, Kp, colv, out0=out, ld_out=N, nslice=4)
+    assert ((out - want).abs() / scale).max().item() < 2.0 ** -25
+    out32 = torch.full((n, N), float("nan"), dtype=torch.float32, device=DEV)
+    ops.fit_gemm_i8(3, n, N, K, xs, K, 4 * K, ex, 0, bsl, Kp, colv, out0=out32, ld_out=N, nslice=4)
+    assert torch.equal(out32, out.to(torch.float32))
+
+
+@pytest.mark.parametrize("n", [1, 200, 4097])
+def test_fit_net_tc_fp32_model(pkg, n):
+    """An fp32 net through the same kernels with 4 slices: energies and dE/dD (returned as float32) against the
+    fp64 evaluation of the same (float32-valued) weights, 2e-6 of the largest magnitude -- the fp32 model's end-to-end
+    tolerance is 1e-5."""
+    from deepmd_kit_b200.model import FittingNet
+
+    ops = pkg.ops
+    K0 = 1600
+    net = FittingNet(K0, (240, 240, 240), True, 11, torch.float32, DEV)
+    assert net.prepare_tc(4)
+    assert not net.prepare_tc(6)
+    ref = FittingNet(K0, (240, 240, 240), True, 11, torch.float64, DEV)
+    ref.layers = [(w.double(), b.double(), None if i is None else i.double()) for w, b, i in net.layers]
+    ref.head = (net.head[0].double(), net.head[1].double())
+    g = torch.Generator().manual_seed(n)
+    d = (torch.randn(n, K0, generator=g, dtype=torch.float64) * 0.05 *
+         torch.exp(torch.randn(n, 1, generator=g, dtype=torch.float64))).to(DEV)
+    e0, g0 = ref.forward_backward(d)
+    xs, ex = ops.split_i8_rows(d, 4)
+    e1, g1 = net.forward_backward_tc(xs, ex, n)
+    assert e1.dtype == torch.float32 and g1.dtype == torch.float32
+    assert ((e1.double() - e0).abs().max() / e0.abs().max()).item() < 2e-6
+    assert ((g1.double() - g0).abs().max() / g0.abs().max()).item() < 2e-6
+
+
 def test_fit_blocked_roundtrip_and_slices(pkg):
     """Row-blocked layout conversion is exact both ways; fit_slice_rows reproduces the rows to 2^-47 of the row
     maximum with |digit| <= 128 and the documented exponent rule |x| < 2^(E-1)."""
@@ -121,7 +170,8 @@ def test_fit_tc_rejects_unsupported(pkg):
     ops = pkg.ops
     assert not FittingNet(240, (240, 240), True, 1, torch.float64, DEV).prepare_tc(6)   # skip connection on layer 0
     assert not FittingNet(1600, (240, 120), True, 1, torch.float64, DEV).prepare_tc(6)  # unequal hidden widths
-    assert not FittingNet(1600, (240, 240), True, 1, torch.float32, DEV).prepare_tc(6)  # fp64 only
+    assert not FittingNet(1600, (240, 240), True, 1, torch.float32, DEV).prepare_tc(6)  # fp32 nets take 4 slices
+    assert not FittingNet(1600, (240, 240), True, 1, torch.float64, DEV).prepare_tc(4)  # fp64 nets take 6
     x = torch.zeros((4, 6 * 64), dtype=torch.int8, device=DEV)
     ex = torch.zeros(4, dtype=torch.int32, device=DEV)
     b = torch.zeros((6, 24, 64), dtype=torch.int8, device=DEV)

@@ -640,6 +640,23 @@ def test_tabulate_desc_epilogue(ops, dtype):
         assert torch.equal(lo.view(torch.int32) & 0x1FFF, torch.zeros_like(lo, dtype=torch.int32))
         rowmax = want_d.abs().amax(1, keepdim=True)
         assert (((hi + lo) - want_d).abs() / rowmax).max().item() < 2e-6
+        # mode 3: four int8 digit slices of the 32-bit fixed-point image + row exponent (fp32 only)
+        out, d3, ex = ops.tabulate_sections_desc(tables, infos, em, sec, M, axis, 1.0 / nnei, desc_row=perm, mode=3,
+                                                 nslice=4, pad_rows=32)
+        assert torch.equal(out, want_out)
+        assert d3.dtype == torch.int8 and d3.shape == (nloc + 32, 4 * K) and int(d3[nloc:].abs().sum()) == 0
+        sl = d3[perm.long()].reshape(nloc, 4, K).to(torch.float64)
+        assert int(sl.abs().max()) <= 128
+        w = torch.tensor([2.0 ** (-7 - 8 * s) for s in range(4)], dtype=torch.float64, device=DEV)
+        rec = (sl * w[None, :, None]).sum(1) * torch.ldexp(torch.ones((), dtype=torch.float64, device=DEV),
+                                                           ex[perm.long()].to(torch.int32))[:, None]
+        wd = want_d.to(torch.float64)
+        # the image resolves 2^-31 of 2^row_exp; the rest is fp32 rounding of D itself
+        assert ((rec - wd).abs() / rowmax.to(torch.float64)).max().item() < 2e-6
+        assert bool((wd.abs().amax(1) < torch.ldexp(torch.ones(nloc, dtype=torch.float64, device=DEV),
+                                                     ex[perm.long()].to(torch.int32) - 1)).all())
+    with pytest.raises(ValueError):
+        ops.tabulate_sections_desc(tables, infos, em, sec, M, axis, 1.0 / nnei, mode=3, nslice=6)
 
 
 def test_split_i8_gemm_matches_fp64(ops):
