@@ -208,16 +208,18 @@ __device__ __forceinline__ double pow2i(int e) { return __hiloint2double((1023 +
 template <int NS>
 __device__ __forceinline__ void store_slices16(signed char* __restrict__ base, long long slice_stride,
                                                const double (&v)[16], double up) {
-  static_assert(NS <= 8, "the fixed-point image must fit in 64 bits");
+  static_assert(NS <= 6, "the fixed-point image must fit in 48 bits (it is read from the mantissa of a double)");
   unsigned long long bias = 0;
 #pragma unroll
   for (int k = 0; k < NS; ++k) bias = bias * 256ull + 128ull;
+  // one FMA against 2^52 + 2^51 + bias leaves the rounded image in the low mantissa bits (|image| < 2^48): no F2I
+  const double magic = 6755399441055744.0 + (double)bias;
   unsigned lo[16], hi[16];
 #pragma unroll
   for (int j = 0; j < 16; ++j) {
-    const unsigned long long u = (unsigned long long)__double2ll_rn(v[j] * up) + bias;
-    lo[j] = (unsigned)u;
-    hi[j] = (unsigned)(u >> 32);
+    const double f = fma(v[j], up, magic);
+    lo[j] = (unsigned)__double2loint(f);
+    hi[j] = (unsigned)__double2hiint(f);
   }
 #pragma unroll
   for (int s = 0; s < NS; ++s) {

@@ -567,10 +567,76 @@ template <int NC>
 __device__ __forceinline__ void desc_store_split_i8(const TabParams<double>&, const double (&)[4][NC], double,
                                                     const double*, long long, int) {}
 
+// The production slice count (6) with everything known at compile time: the generic version below selects bytes
+// with run-time selectors and costs ~4300 warp instructions per atom, this one ~1000.  The fixed-point image is
+// formed by one FMA against 2^52 + 2^51 + bias (the integer lands in the low mantissa bits, rounded to nearest):
+// no F2I, no 64-bit adds.
+template <int NS, int NC>
+__device__ __forceinline__ void desc_store_split_ns(const TabParams<double>& p, const double (&A)[4][NC], double s2,
+                                                    const double* __restrict__ stage, long long row, int lane) {
+  static_assert(NS >= 5 && NS <= 6, "the image must reach into the high word and fit in 48 bits");
+  const int M = p.M;
+  double r2 = 0.;
+#pragma unroll
+  for (int c = 0; c < NC; ++c) {
+    const double n2 = A[0][c] * A[0][c] + A[1][c] * A[1][c] + A[2][c] * A[2][c] + A[3][c] * A[3][c];
+    r2 = (lane + 32 * c < M && n2 > r2) ? n2 : r2;
+  }
+  r2 *= s2;
+  int e = ((__double2hiint(r2) >> 20) & 0x7ff) - 1023;
+  e = __reduce_max_sync(kFull, e);
+  int E = e + 2;  // |D| < 2^(E-1)
+  E = E < -900 ? -900 : (E > 900 ? 900 : E);
+  if (lane == 0) p.row_exp[row] = E;
+  constexpr int P = 7 + 8 * (NS - 1);
+  const double up = s2 * __hiloint2double((1023 + P - E) << 20, 0);
+  unsigned long long bias = 0;
+#pragma unroll
+  for (int k = 0; k < NS; ++k) bias = bias * 256ull + 128ull;
+  const double magic = 6755399441055744.0 + (double)bias;  // 2^52 + 2^51 + bias, exact
+  signed char* __restrict__ base = reinterpret_cast<signed char*>(p.desc) + row * p.desc_ld;
+  const long long K = (long long)M * 16;
+#pragma unroll
+  for (int c = 0; c < NC; ++c) {
+    const int k1 = lane + 32 * c;
+    if (k1 < M) {
+      signed char* __restrict__ dst = base + (long long)k1 * 16;
+#pragma unroll 1
+      for (int half = 0; half < 2; ++half) {
+        unsigned lo[8], hi[8];
+#pragma unroll
+        for (int t = 0; t < 8; t += 2) {
+          double v0 = 0., v1 = 0.;
+#pragma unroll
+          for (int m = 0; m < 4; ++m) {
+            const double2 b = *reinterpret_cast<const double2*>(stage + m * 16 + half * 8 + t);
+            v0 += A[m][c] * b.x, v1 += A[m][c] * b.y;
+          }
+          const double f0 = fma(v0, up, magic), f1 = fma(v1, up, magic);
+          lo[t] = (unsigned)__double2loint(f0), hi[t] = (unsigned)__double2hiint(f0);
+          lo[t + 1] = (unsigned)__double2loint(f1), hi[t + 1] = (unsigned)__double2hiint(f1);
+        }
+#pragma unroll
+        for (int s = 0; s < NS; ++s) {  // slice s = byte NS-1-s of the image, top bit flipped = signed digit
+          constexpr unsigned kSel[4] = {0x40u, 0x51u, 0x62u, 0x73u};
+          const int kb = NS - 1 - s;
+          const unsigned sel = kSel[kb & 3];
+          const unsigned(&src)[8] = kb < 4 ? lo : hi;
+          const unsigned a0 = __byte_perm(src[0], src[1], sel), a1 = __byte_perm(src[2], src[3], sel);
+          const unsigned a2 = __byte_perm(src[4], src[5], sel), a3 = __byte_perm(src[6], src[7], sel);
+          *reinterpret_cast<uint2*>(dst + s * K + half * 8) =
+              make_uint2(__byte_perm(a0, a1, 0x5410) ^ 0x80808080u, __byte_perm(a2, a3, 0x5410) ^ 0x80808080u);
+        }
+      }
+    }
+  }
+}
+
 template <int NC>
 __device__ __forceinline__ void desc_store_split(const TabParams<double>& p, const double (&A)[4][NC], double s2,
                                                  const double* __restrict__ stage, long long row, int lane) {
   // axis == 16 (checked on the host): one lane owns the 16 contiguous k2 of each of its channels.
+  if (p.nslice == 6) return desc_store_split_ns<6, NC>(p, A, s2, stage, row, lane);
   const int M = p.M, ns = p.nslice;
   // row scale from the Cauchy-Schwarz bound |D[k1][k2]| <= max_k |A[:,k]|^2 (attained on the diagonal)
   double r2 = 0.;
@@ -753,29 +819,37 @@ __global__ void __launch_bounds__(512) k_tab_fwd(const __grid_constant__ TabPara
 
     if (!GG && !TWO && !any_delta) {
       // the common case: nothing to gate, nobody outside [lower, max): 9 FMAs per channel, no branches
+      // Software pipeline: the coefficients of neighbour jj are consumed by the polynomial, THEN the row of
+      // neighbour jj+1 is requested (same registers), and the 16 accumulation FMAs of neighbour jj run while that
+      // fetch is in flight; the row index of jj+1 is read one iteration ahead of its comparison.
+      auto fetch = [&](int row) {
+        cur_row = row;
+        if (CM && sizeof(FP) == 4)
+          fetch_row_c32<NC>(a, hot, p.T, row, r0, p.H, p.M, ob);
+        else if (CM)
+          fetch_row_cmf(a, af, hot, p.T, row, r0, p.H, p.M, ob, p.a5_inv);
+        else
+          fetch_row<FP, NC>(a, hot, p.T, row, r0, p.H, p.M, ob);
+      };
+      if (nproc > 0 && rec[0].idx != cur_row) fetch(rec[0].idx);  // warp-uniform
 #pragma unroll 2
       for (int jj = 0; jj < nproc; ++jj) {
         const Rec<FP>& r = rec[jj];
-        const int row = r.idx;
-        if (row != cur_row) {  // warp-uniform
-          cur_row = row;
-          if (CM && sizeof(FP) == 4)
-            fetch_row_c32<NC>(a, hot, p.T, row, r0, p.H, p.M, ob);
-          else if (CM)
-            fetch_row_cmf(a, af, hot, p.T, row, r0, p.H, p.M, ob, p.a5_inv);
-          else
-            fetch_row<FP, NC>(a, hot, p.T, row, r0, p.H, p.M, ob);
-        }
+        const int row_n = rec[jj + 1 < nproc ? jj + 1 : jj].idx;
         const FP xx = r.xx;
         const float xf = (float)xx;
         const FP e0 = r.e[0], e1 = r.e[1], e2 = r.e[2], e3 = r.e[3];
+        FP g[NC];
+#pragma unroll
+        for (int c = 0; c < NC; ++c)
+          g[c] = (CM && sizeof(FP) == 4) ? poly3(a[c], xx) : (CM ? poly_cm(a[c], af[CM ? c : 0], xx, xf) : poly(a[c], xx));
+        if (row_n != cur_row) fetch(row_n);  // warp-uniform
 #pragma unroll
         for (int c = 0; c < NC; ++c) {
-          const FP g = (CM && sizeof(FP) == 4) ? poly3(a[c], xx) : (CM ? poly_cm(a[c], af[CM ? c : 0], xx, xf) : poly(a[c], xx));
-          acc[0][c] += e0 * g;
-          acc[1][c] += e1 * g;
-          acc[2][c] += e2 * g;
-          acc[3][c] += e3 * g;
+          acc[0][c] += e0 * g[c];
+          acc[1][c] += e1 * g[c];
+          acc[2][c] += e2 * g[c];
+          acc[3][c] += e3 * g[c];
         }
       }
     } else if (!GG && TWO && ring_on && !any_delta) {
@@ -1367,6 +1441,11 @@ __global__ void __launch_bounds__(MAXT) k_tab_grad_mma(const __grid_constant__ T
     if (atom_end && ni < p.nloc) nlast = p.em_x[ni * p.ldx_i + (long long)(p.nnei - 1) * p.ldx_j];
 
     FP* __restrict__ gem = p.dy_dem + i * p.ldem_i;
+    if (j0 == 0 && i + stride < p.nloc && lane * 16 < 4 * M) {
+      // the next atom's dy tile (4*M doubles, staged into shared memory when that atom starts) into L2 now: the
+      // staging stores otherwise wait a full HBM round trip per atom (ncu: 8 % of the kernel's stall samples)
+      asm volatile("prefetch.global.L2 [%0];" ::"l"(p.dy + (i + stride) * 4 * (long long)M + lane * 16));
+    }
     for (int s = 0; s < nproc; s += 8) {
       const int nb = s + q;
       const bool live = nb < nproc;

@@ -634,6 +634,16 @@ def test_tabulate_desc_epilogue(ops, dtype):
         rowmax = want_d.abs().amax(1, keepdim=True)
         err = ((rec - want_d).abs() / rowmax).max().item()
         assert err < 2.0 ** -50, err
+        # the production slice count takes a specialised (compile-time) path: same contract at 47 fraction bits
+        out, d6, ex6 = ops.tabulate_sections_desc(tables, infos, em, sec, M, axis, 1.0 / nnei, desc_row=perm, mode=2,
+                                                  nslice=6, pad_rows=32)
+        assert torch.equal(out, want_out) and torch.equal(ex6, ex)
+        sl = d6[perm.long()].reshape(nloc, 6, K).to(torch.float64)
+        assert int(sl.abs().max()) <= 128
+        rec = (sl * w[None, :6, None]).sum(1) * torch.ldexp(torch.ones((), dtype=torch.float64, device=DEV),
+                                                            ex6[perm.long()].to(torch.int32))[:, None]
+        err = ((rec - want_d).abs() / rowmax).max().item()
+        assert err < 2.0 ** -43, err
     else:
         hi, lo = d2[:, :K], d2[:, K:]
         assert torch.equal(hi.view(torch.int32) & 0x1FFF, torch.zeros_like(hi, dtype=torch.int32))

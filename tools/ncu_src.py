@@ -1,16 +1,15 @@
 """Summarise `ncu --page source --csv` output: opcode mix, stall mix, hottest instructions.
-usage: ncu -i X.ncu-rep --page source --csv --kernel-name regex:K > src.csv; python tools/ncu_src.py src.csv [ntop]"""
+usage: ncu -i X.ncu-rep --page source --csv --kernel-name regex:K > src.csv; python tools/ncu_src.py src.csv [ntop] [launch]"""
 import csv, sys
 from collections import Counter
 rows = list(csv.reader(open(sys.argv[1])))
 ntop = int(sys.argv[2]) if len(sys.argv) > 2 else 20
+which = int(sys.argv[3]) if len(sys.argv) > 3 else 0  # launch index inside the file
+starts = [i for i, r in enumerate(rows) if r and r[0] == "Kernel Name"]
+a = starts[which]; b = starts[which + 1] if which + 1 < len(starts) else len(rows)
+rows = rows[a:b]
 hdr = rows[1]; idx = {n: i for i, n in enumerate(hdr)}
-data = []
-for r in rows[2:]:
-    if r and r[0] == "Kernel Name":
-        break  # first launch only
-    if len(r) >= len(hdr) and r[0] != "Address":
-        data.append(r)
+data = [r for r in rows[2:] if len(r) >= len(hdr) and r[0] != "Address"]
 tot = sum(int(r[idx['# Samples']]) for r in data)
 inst = sum(int(r[idx['Instructions Executed']]) for r in data)
 print('kernel', rows[0][1][:80]); print('samples', tot, 'inst', inst, 'sass lines', len(data))
