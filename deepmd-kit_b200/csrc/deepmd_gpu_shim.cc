@@ -13,7 +13,7 @@
 //  * outputs need not be pre-zeroed;
 //  * errors surface as deepmd::deepmd_exception / deepmd_exception_oom /
 //    deepmd_exception_nlist_capacity (source/lib/include/errors.h:10-35).
-// Scope: the se_a / se_atten path (ndescrpt == 4).  Other descriptors' symbols (se_r, se_t, ...)
+// Scope: the se_a / se_atten path (ndescrpt == 4 hot path; 9 / 16 / 25 through csrc/tabulate_nd.cu).  Other descriptors' symbols (se_r, se_t, ...)
 // are intentionally not provided here.
 #include <cuda_runtime.h>
 
@@ -87,6 +87,9 @@ struct Fn<double> {
   static constexpr auto tab = dpb200_tabulate_fusion_se_a_f64;
   static constexpr auto tab_grad = dpb200_tabulate_fusion_se_a_grad_f64;
   static constexpr auto tab_gg = dpb200_tabulate_fusion_se_a_grad_grad_f64;
+  static constexpr auto tab_nd = dpb200_tabulate_fusion_se_a_nd_f64;
+  static constexpr auto tab_grad_nd = dpb200_tabulate_fusion_se_a_grad_nd_f64;
+  static constexpr auto tab_gg_nd = dpb200_tabulate_fusion_se_a_grad_grad_nd_f64;
   static constexpr auto force = dpb200_prod_force_a_f64;
   static constexpr auto virial = dpb200_prod_virial_a_f64;
   static constexpr auto force_grad = dpb200_prod_force_grad_a_f64;
@@ -102,6 +105,9 @@ struct Fn<float> {
   static constexpr auto tab = dpb200_tabulate_fusion_se_a_f32;
   static constexpr auto tab_grad = dpb200_tabulate_fusion_se_a_grad_f32;
   static constexpr auto tab_gg = dpb200_tabulate_fusion_se_a_grad_grad_f32;
+  static constexpr auto tab_nd = dpb200_tabulate_fusion_se_a_nd_f32;
+  static constexpr auto tab_grad_nd = dpb200_tabulate_fusion_se_a_grad_nd_f32;
+  static constexpr auto tab_gg_nd = dpb200_tabulate_fusion_se_a_grad_grad_nd_f32;
   static constexpr auto force = dpb200_prod_force_a_f32;
   static constexpr auto virial = dpb200_prod_virial_a_f32;
   static constexpr auto force_grad = dpb200_prod_force_grad_a_f32;
@@ -111,9 +117,10 @@ struct Fn<float> {
   static constexpr auto build = dpb200_build_nlist_f32;
 };
 
-void need_ndescrpt4(int ndescrpt) {
-  if (ndescrpt != 4) {
-    throw deepmd::deepmd_exception("dpb200 provides the se_a / se_atten path only (environment basis dimension 4), got " +
+// tabulate.h is_supported_se_a_basis_dimension: 4 (se_a / se_atten hot path), 9, 16, 25 (csrc/tabulate_nd.cu)
+void need_basis_dimension(int ndescrpt) {
+  if (ndescrpt != 4 && ndescrpt != 9 && ndescrpt != 16 && ndescrpt != 25) {
+    throw deepmd::deepmd_exception("The environment basis dimension must be 4, 9, 16 or 25, got " +
                                    std::to_string(ndescrpt));
   }
 }
@@ -160,9 +167,14 @@ DPB_EXPORT void tabulate_fusion_se_a_gpu(FPTYPE* out, const FPTYPE* table, const
                                          const FPTYPE* em_x, const FPTYPE* em, const FPTYPE* two_embed, const int nloc,
                                          const int nnei, const int last_layer_size, const bool is_sorted,
                                          const int ndescrpt) {
-  need_ndescrpt4(ndescrpt);
-  check(Fn<FPTYPE>::tab(out, table, table_info, em_x, em, two_embed, nloc, nnei, last_layer_size, is_sorted, nullptr),
-        "tabulate_fusion_se_a_gpu");
+  need_basis_dimension(ndescrpt);
+  if (ndescrpt != 4)
+    check(Fn<FPTYPE>::tab_nd(out, table, table_info, em_x, em, two_embed, nloc, nnei, last_layer_size, is_sorted,
+                             ndescrpt, nullptr),
+          "tabulate_fusion_se_a_gpu");
+  else
+    check(Fn<FPTYPE>::tab(out, table, table_info, em_x, em, two_embed, nloc, nnei, last_layer_size, is_sorted, nullptr),
+          "tabulate_fusion_se_a_gpu");
   sync_default_stream("tabulate_fusion_se_a_gpu");
 }
 
@@ -172,10 +184,15 @@ DPB_EXPORT void tabulate_fusion_se_a_grad_gpu(FPTYPE* dy_dem_x, FPTYPE* dy_dem, 
                                               const FPTYPE* two_embed, const FPTYPE* dy, const int nloc,
                                               const int nnei, const int last_layer_size, const bool is_sorted,
                                               const int ndescrpt) {
-  need_ndescrpt4(ndescrpt);
-  check(Fn<FPTYPE>::tab_grad(dy_dem_x, dy_dem, dy_dtwo, table, table_info, em_x, em, two_embed, dy, nloc, nnei,
-                             last_layer_size, is_sorted, nullptr),
-        "tabulate_fusion_se_a_grad_gpu");
+  need_basis_dimension(ndescrpt);
+  if (ndescrpt != 4)
+    check(Fn<FPTYPE>::tab_grad_nd(dy_dem_x, dy_dem, dy_dtwo, table, table_info, em_x, em, two_embed, dy, nloc, nnei,
+                                  last_layer_size, is_sorted, ndescrpt, nullptr),
+          "tabulate_fusion_se_a_grad_gpu");
+  else
+    check(Fn<FPTYPE>::tab_grad(dy_dem_x, dy_dem, dy_dtwo, table, table_info, em_x, em, two_embed, dy, nloc, nnei,
+                               last_layer_size, is_sorted, nullptr),
+          "tabulate_fusion_se_a_grad_gpu");
   sync_default_stream("tabulate_fusion_se_a_grad_gpu");
 }
 
@@ -186,10 +203,15 @@ DPB_EXPORT void tabulate_fusion_se_a_grad_grad_gpu(FPTYPE* dz_dy, const FPTYPE* 
                                                    const FPTYPE* dz_dy_dtwo, const int nloc, const int nnei,
                                                    const int last_layer_size, const bool is_sorted,
                                                    const int ndescrpt) {
-  need_ndescrpt4(ndescrpt);
-  check(Fn<FPTYPE>::tab_gg(dz_dy, table, table_info, em_x, em, two_embed, dz_dy_dem_x, dz_dy_dem, dz_dy_dtwo, nloc,
-                           nnei, last_layer_size, is_sorted, nullptr),
-        "tabulate_fusion_se_a_grad_grad_gpu");
+  need_basis_dimension(ndescrpt);
+  if (ndescrpt != 4)
+    check(Fn<FPTYPE>::tab_gg_nd(dz_dy, table, table_info, em_x, em, two_embed, dz_dy_dem_x, dz_dy_dem, dz_dy_dtwo,
+                                nloc, nnei, last_layer_size, is_sorted, ndescrpt, nullptr),
+          "tabulate_fusion_se_a_grad_grad_gpu");
+  else
+    check(Fn<FPTYPE>::tab_gg(dz_dy, table, table_info, em_x, em, two_embed, dz_dy_dem_x, dz_dy_dem, dz_dy_dtwo, nloc,
+                             nnei, last_layer_size, is_sorted, nullptr),
+          "tabulate_fusion_se_a_grad_grad_gpu");
   sync_default_stream("tabulate_fusion_se_a_grad_grad_gpu");
 }
 

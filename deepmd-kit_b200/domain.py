@@ -335,6 +335,7 @@ class DomainDeepPot(DeepPotB200):
             st = self.build_neighbors(coord, atype, box)
         c = coord.reshape(-1, 3)
         ext_c = self.halo_forward(c)
+        self._last_ext_coord = ext_c
         st.ago += 1
         if st.chunks is not None:  # per-atom intermediates exceed the device memory: slabs of centre atoms
             e, f_ext, virial, ex = self.model.evaluate_chunked(ext_c, st.ext_type, st.numneigh, st.rows, None, st.nloc,

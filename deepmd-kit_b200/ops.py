@@ -212,9 +212,8 @@ def _check_tab(table, em_x, em, two_embed):
         raise ValueError("Dim of input should be 3")
     if two_embed is not None and two_embed.dim() != 2:
         raise ValueError("Dim of input should be 2")
-    if em.shape[2] != 4:
-        raise NotImplementedError(
-            f"The environment basis dimension must be 4 for the se_a / se_atten path, got {em.shape[2]}")
+    if em.shape[2] not in (4, 9, 16, 25):  # tabulate.h is_supported_se_a_basis_dimension
+        raise ValueError(f"The environment basis dimension must be 4, 9, 16 or 25, got {em.shape[2]}")
     for name, t in (("em_x", em_x), ("em", em), ("two_embed", two_embed)):
         if t is not None and t.device != table.device:
             raise RuntimeError(f"{name} must be on the same device as table; table is on {table.device} but "
@@ -230,9 +229,13 @@ def tabulate_fusion_se_a(table, table_info, em_x, em, last_layer_size, two_embed
     table, em_x, em = _c(table), _c(em_x, table.dtype), _c(em, table.dtype)
     if two_embed is not None:
         two_embed = _c(two_embed, table.dtype)
-    nloc, nnei = em.shape[0], em.shape[1]
+    nloc, nnei, nd = em.shape[0], em.shape[1], em.shape[2]
     M = int(last_layer_size)
-    out = torch.empty((nloc, 4, M), dtype=table.dtype, device=dev)
+    out = torch.empty((nloc, nd, M), dtype=table.dtype, device=dev)
+    if nd != 4:  # higher angular bases: csrc/tabulate_nd.cu
+        lib().call("tabulate_fusion_se_a_nd_" + s, _p(out), _p(table), C.c_void_p(ti.data_ptr()), _p(em_x), _p(em),
+                   _p(two_embed), nloc, nnei, M, int(bool(is_sorted)), nd, _stream(dev))
+        return out
     lib().call("tabulate_fusion_se_a_" + s, _p(out), _p(table), C.c_void_p(ti.data_ptr()), _p(em_x), _p(em),
                _p(two_embed), nloc, nnei, M, int(bool(is_sorted)), _stream(dev))
     return out
@@ -252,6 +255,11 @@ def tabulate_fusion_se_a_grad(table, table_info, em_x, em, dy, last_layer_size, 
     g_x = torch.zeros_like(em_x) if nnei == 0 else torch.empty_like(em_x)
     g_em = torch.zeros_like(em) if nnei == 0 else torch.empty_like(em)
     g_two = None if two_embed is None else torch.empty_like(two_embed)
+    if em.shape[2] != 4:
+        lib().call("tabulate_fusion_se_a_grad_nd_" + s, _p(g_x), _p(g_em), _p(g_two), _p(table),
+                   C.c_void_p(ti.data_ptr()), _p(em_x), _p(em), _p(two_embed), _p(dy), nloc, nnei, M,
+                   int(bool(is_sorted)), int(em.shape[2]), _stream(dev))
+        return g_x, g_em, g_two
     lib().call("tabulate_fusion_se_a_grad_" + s, _p(g_x), _p(g_em), _p(g_two), _p(table), C.c_void_p(ti.data_ptr()),
                _p(em_x), _p(em), _p(two_embed), _p(dy), nloc, nnei, M, int(bool(is_sorted)), _stream(dev))
     return g_x, g_em, g_two
@@ -310,7 +318,12 @@ def tabulate_fusion_se_a_grad_grad(table, table_info, em_x, em, dz_dy_dem_x, dz_
         dz_dy_dtwo = torch.zeros_like(two_embed) if dz_dy_dtwo is None else _c(dz_dy_dtwo, table.dtype)
     nloc, nnei = em.shape[0], em.shape[1]
     M = int(last_layer_size)
-    out = torch.empty((nloc, 4, M), dtype=table.dtype, device=dev)
+    out = torch.empty((nloc, em.shape[2], M), dtype=table.dtype, device=dev)
+    if em.shape[2] != 4:
+        lib().call("tabulate_fusion_se_a_grad_grad_nd_" + s, _p(out), _p(table), C.c_void_p(ti.data_ptr()), _p(em_x),
+                   _p(em), _p(two_embed), _p(dz_x), _p(dz_em), _p(dz_dy_dtwo if two_embed is not None else None),
+                   nloc, nnei, M, int(bool(is_sorted)), int(em.shape[2]), _stream(dev))
+        return out
     lib().call("tabulate_fusion_se_a_grad_grad_" + s, _p(out), _p(table), C.c_void_p(ti.data_ptr()), _p(em_x), _p(em),
                _p(two_embed), _p(dz_x), _p(dz_em), _p(dz_dy_dtwo if two_embed is not None else None), nloc, nnei, M,
                int(bool(is_sorted)), _stream(dev))

@@ -350,6 +350,36 @@ int dpb200_split_tf32_f32(float* out, long long ld_out, const float* x, long lon
                           int copies, dpb200_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------
+ * tabulate_fusion_se_a for the higher angular bases, ndescrpt = 9 / 16 / 25 (csrc/tabulate_nd.cu).
+ * Replaces deepmd::tabulate_fusion_se_a{,_grad,_grad_grad}_{cpu,gpu} called with ndescrpt != 4
+ * (source/lib/include/tabulate.h:28-72, dispatch source/lib/src/tabulate.cc:456-560; caller
+ * source/op/pt/tabulate_multi_device.cc:101-117, ndescrpt = em.size(2)).  Same argument meaning as the
+ * reference: em [nloc][nnei][ndescrpt], out / dy / dz_dy [nloc][ndescrpt][last_layer_size], two_embed and its
+ * cotangents [nloc][nnei][last_layer_size] or NULL; table_info is a HOST pointer.  ndescrpt == 4 is served by
+ * the entry points above (the hot path); any other value is DPB200_ERR_INVALID as in the reference's
+ * check_se_a_basis_dimension.
+ * ------------------------------------------------------------------------------------- */
+#define DPB200_DECL_TAB_ND(SUF, FP)                                                                               \
+  int dpb200_tabulate_fusion_se_a_nd_##SUF(FP* out, const FP* table, const FP* table_info, const FP* em_x,       \
+                                           const FP* em, const FP* two_embed /*nullable*/, int nloc, int nnei,   \
+                                           int last_layer_size, int is_sorted, int ndescrpt,                     \
+                                           dpb200_stream_t stream);                                              \
+  int dpb200_tabulate_fusion_se_a_grad_nd_##SUF(FP* dy_dem_x, FP* dy_dem, FP* dy_dtwo /*nullable*/,              \
+                                                const FP* table, const FP* table_info, const FP* em_x,           \
+                                                const FP* em, const FP* two_embed /*nullable*/, const FP* dy,    \
+                                                int nloc, int nnei, int last_layer_size, int is_sorted,          \
+                                                int ndescrpt, dpb200_stream_t stream);                           \
+  int dpb200_tabulate_fusion_se_a_grad_grad_nd_##SUF(FP* dz_dy, const FP* table, const FP* table_info,           \
+                                                     const FP* em_x, const FP* em,                               \
+                                                     const FP* two_embed /*nullable*/, const FP* dz_dy_dem_x,    \
+                                                     const FP* dz_dy_dem, const FP* dz_dy_dtwo /*nullable*/,     \
+                                                     int nloc, int nnei, int last_layer_size, int is_sorted,     \
+                                                     int ndescrpt, dpb200_stream_t stream);
+DPB200_DECL_TAB_ND(f64, double)
+DPB200_DECL_TAB_ND(f32, float)
+#undef DPB200_DECL_TAB_ND
+
+/* ---------------------------------------------------------------------------------------
  * Fitting net on the tcgen05 tensor cores (csrc/fit_tc.cu).  Replaces the library GEMMs of the
  * energy fitting net (deepmd/pt/model/network/mlp.py layers: y = tanh(x.W + b) * idt (+ x); reference's fused
  * fp32 analogue source/op/pt/graph_fitting.cu:40-90,230-340) with error-free int8 split products whose order

@@ -170,10 +170,11 @@ class CpuLib:
         em_x = np.ascontiguousarray(em_x, dtype=dt)
         em = np.ascontiguousarray(em, dtype=dt)
         nloc, nnei = em.shape[0], em.shape[1]
+        nd = em.shape[2] if em.ndim == 3 else 4  # NDESCRPT (tabulate.cc:456-497: 4, 9, 16 or 25)
         te = None if two_embed is None else np.ascontiguousarray(two_embed, dtype=dt)
-        out = np.zeros((nloc, 4, M), dt)
-        self._call("tabulate_fusion_se_a_" + s, _p(out), _p(table), _p(info), _p(em_x), _p(em), _p(te),
-                   C.c_int(nloc), C.c_int(nnei), C.c_int(M), C.c_int(int(is_sorted)))
+        out = np.zeros((nloc, nd, M), dt)
+        self._call("tabulate_fusion_se_a_nd_" + s, _p(out), _p(table), _p(info), _p(em_x), _p(em), _p(te),
+                   C.c_int(nloc), C.c_int(nnei), C.c_int(M), C.c_int(int(is_sorted)), C.c_int(nd))
         return out
 
     def tabulate_fusion_se_a_grad(self, table, info, em_x, em, dy, M, two_embed=None, is_sorted=True):
@@ -185,13 +186,14 @@ class CpuLib:
         em = np.ascontiguousarray(em, dtype=dt)
         dy = np.ascontiguousarray(dy, dtype=dt)
         nloc, nnei = em.shape[0], em.shape[1]
+        nd = em.shape[2] if em.ndim == 3 else 4
         te = None if two_embed is None else np.ascontiguousarray(two_embed, dtype=dt)
         g_x = np.zeros((nloc, nnei), dt)
-        g_em = np.zeros((nloc, nnei, 4), dt)
+        g_em = np.zeros((nloc, nnei, nd), dt)
         g_two = np.zeros((nloc, nnei, M), dt) if te is not None else None
-        self._call("tabulate_fusion_se_a_grad_" + s, _p(g_x), _p(g_em), _p(g_two), _p(table), _p(info),
+        self._call("tabulate_fusion_se_a_grad_nd_" + s, _p(g_x), _p(g_em), _p(g_two), _p(table), _p(info),
                    _p(em_x), _p(em), _p(te), _p(dy), C.c_int(nloc), C.c_int(nnei), C.c_int(M),
-                   C.c_int(int(is_sorted)))
+                   C.c_int(int(is_sorted)), C.c_int(nd))
         return g_x, g_em, g_two
 
     def tabulate_fusion_se_a_grad_grad(self, table, info, em_x, em, dz_dem_x, dz_dem, M, two_embed=None,
@@ -205,12 +207,13 @@ class CpuLib:
         dz_dem_x = np.ascontiguousarray(dz_dem_x, dtype=dt)
         dz_dem = np.ascontiguousarray(dz_dem, dtype=dt)
         nloc, nnei = em.shape[0], em.shape[1]
+        nd = em.shape[2] if em.ndim == 3 else 4
         te = None if two_embed is None else np.ascontiguousarray(two_embed, dtype=dt)
         dzt = None if dz_dtwo is None else np.ascontiguousarray(dz_dtwo, dtype=dt)
-        out = np.zeros((nloc, 4, M), dt)
-        self._call("tabulate_fusion_se_a_grad_grad_" + s, _p(out), _p(table), _p(info), _p(em_x), _p(em),
+        out = np.zeros((nloc, nd, M), dt)
+        self._call("tabulate_fusion_se_a_grad_grad_nd_" + s, _p(out), _p(table), _p(info), _p(em_x), _p(em),
                    _p(te), _p(dz_dem_x), _p(dz_dem), _p(dzt), C.c_int(nloc), C.c_int(nnei), C.c_int(M),
-                   C.c_int(int(is_sorted)))
+                   C.c_int(int(is_sorted)), C.c_int(nd))
         return out
 
     # -- a11 / a12 -----------------------------------------------------------------

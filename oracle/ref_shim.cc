@@ -214,6 +214,36 @@ const char* ref_last_error() { return g_err.c_str(); }
                                                      is_sorted != 0);                      \
     });                                                                                    \
   }                                                                                        \
+  int ref_tabulate_fusion_se_a_nd_##SUF(FP* out, const FP* table, const FP* info,          \
+                                        const FP* em_x, const FP* em, const FP* two_embed, \
+                                        int nloc, int nnei, int M, int is_sorted, int nd) {\
+    return guarded([&] {                                                                   \
+      deepmd::tabulate_fusion_se_a_cpu<FP>(out, table, info, em_x, em, two_embed, nloc,    \
+                                           nnei, M, is_sorted != 0, nd);                   \
+    });                                                                                    \
+  }                                                                                        \
+  int ref_tabulate_fusion_se_a_grad_nd_##SUF(FP* dy_dem_x, FP* dy_dem, FP* dy_dtwo,        \
+                                             const FP* table, const FP* info,              \
+                                             const FP* em_x, const FP* em,                 \
+                                             const FP* two_embed, const FP* dy, int nloc,  \
+                                             int nnei, int M, int is_sorted, int nd) {     \
+    return guarded([&] {                                                                   \
+      deepmd::tabulate_fusion_se_a_grad_cpu<FP>(dy_dem_x, dy_dem, dy_dtwo, table, info,    \
+                                                em_x, em, two_embed, dy, nloc, nnei, M,    \
+                                                is_sorted != 0, nd);                       \
+    });                                                                                    \
+  }                                                                                        \
+  int ref_tabulate_fusion_se_a_grad_grad_nd_##SUF(                                         \
+      FP* dz_dy, const FP* table, const FP* info, const FP* em_x, const FP* em,            \
+      const FP* two_embed, const FP* dz_dy_dem_x, const FP* dz_dy_dem,                     \
+      const FP* dz_dy_dtwo, int nloc, int nnei, int M, int is_sorted, int nd) {            \
+    return guarded([&] {                                                                   \
+      deepmd::tabulate_fusion_se_a_grad_grad_cpu<FP>(dz_dy, table, info, em_x, em,         \
+                                                     two_embed, dz_dy_dem_x, dz_dy_dem,    \
+                                                     dz_dy_dtwo, nloc, nnei, M,            \
+                                                     is_sorted != 0, nd);                  \
+    });                                                                                    \
+  }                                                                                        \
   int ref_prod_force_a_##SUF(FP* force, const FP* net_deriv, const FP* in_deriv,           \
                              const int* nlist, int nloc, int nall, int nnei,               \
                              int nframes) {                                                \

@@ -283,6 +283,54 @@ def test_tabulate_atten_vs_oracle(ops, olib, dtype, is_sorted):
     close(N(ggg), wgg, dtype, fac=4)
 
 
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+@pytest.mark.parametrize("nd", [9, 16, 25])
+@pytest.mark.parametrize("two", [False, True])
+@pytest.mark.parametrize("is_sorted", [True, False])
+def test_tabulate_higher_basis_vs_oracle(ops, olib, dtype, nd, two, is_sorted):
+    """ndescrpt = 9 / 16 / 25 (tabulate.cc:456-560; csrc/tabulate_nd.cu): forward, backward and second order against
+    the CPU checkers, with two_embed, padding folds (the fold test reads components 1..3 whatever the basis is), both
+    extrapolation branches, a channel count that is not a multiple of 32."""
+    rng = np.random.default_rng(100 * nd + 7)
+    nloc, nnei, M = 23, 37, 45
+    table, info, em_x, em4 = _random_tab_case(rng, dtype, nloc, nnei, M, unsorted=not is_sorted)
+    em = rng.normal(size=(nloc, nnei, nd)).astype(dtype)
+    em[:, :, :4] = em4
+    pad = em4[:, :, 1:].reshape(nloc, nnei, 3).any(axis=2) == 0  # padded slots keep a zero angular part
+    em[pad, 4:] = 0
+    te = rng.normal(size=(nloc * nnei, M)).astype(dtype) if two else None
+    tt = None if te is None else T(te)
+    want = olib.tabulate_fusion_se_a(table, info, em_x, em, M, two_embed=te, is_sorted=is_sorted)
+    got = ops.tabulate_fusion_se_a(T(table), torch.as_tensor(info), T(em_x), T(em), M, two_embed=tt, is_sorted=is_sorted)
+    assert got.shape == (nloc, nd, M)
+    close(N(got), want, dtype, fac=4)
+    dy = rng.normal(size=(nloc, nd, M)).astype(dtype)
+    wx, wem, wtwo = olib.tabulate_fusion_se_a_grad(table, info, em_x, em, dy, M, two_embed=te, is_sorted=is_sorted)
+    gx, gem, gtwo = ops.tabulate_fusion_se_a_grad(T(table), torch.as_tensor(info), T(em_x), T(em), T(dy), M,
+                                                  two_embed=tt, is_sorted=is_sorted)
+    close(N(gx), wx, dtype, fac=4)
+    close(N(gem), wem, dtype, fac=4)
+    if two:
+        close(N(gtwo), wtwo.reshape(nloc * nnei, M), dtype, fac=4)
+    dzx = rng.normal(size=em_x.shape).astype(dtype)
+    dzem = rng.normal(size=em.shape).astype(dtype)
+    dzt = rng.normal(size=te.shape).astype(dtype) if two else None
+    wgg = olib.tabulate_fusion_se_a_grad_grad(table, info, em_x, em, dzx, dzem, M, two_embed=te, dz_dtwo=dzt,
+                                              is_sorted=is_sorted)
+    ggg = ops.tabulate_fusion_se_a_grad_grad(T(table), torch.as_tensor(info), T(em_x), T(em), T(dzx), T(dzem), M,
+                                             two_embed=tt, dz_dy_dtwo=None if dzt is None else T(dzt),
+                                             is_sorted=is_sorted)
+    close(N(ggg), wgg, dtype, fac=4)
+
+
+def test_tabulate_rejects_other_basis_dimensions(ops):
+    table = torch.zeros(4, 48, dtype=torch.float64, device=DEV)
+    info = torch.tensor([0, 0.2, 0.4, 0.01, 0.1, -1], dtype=torch.float64)
+    with pytest.raises(ValueError):  # tabulate.h is_supported_se_a_basis_dimension: 4, 9, 16, 25
+        ops.tabulate_fusion_se_a(table, info, torch.zeros(6, 1, dtype=torch.float64, device=DEV),
+                                 torch.zeros(2, 3, 5, dtype=torch.float64, device=DEV), 8)
+
+
 def test_tabulate_empty_neighbors(ops):
     """test_tabulate_se_a.cc:761-786: nnei == 0 gives a zero descriptor and empty gradients."""
     table = torch.zeros(4, 48, dtype=torch.float64, device=DEV)

@@ -262,7 +262,9 @@ def test_port_equals_reference_env_mat(port, ref, dtype, jitter, sel):
 @pytest.mark.parametrize("dtype", [np.float64, np.float32])
 @pytest.mark.parametrize("two", [False, True])
 @pytest.mark.parametrize("is_sorted", [True, False])
-def test_port_equals_reference_tabulate(port, ref, dtype, two, is_sorted):
+@pytest.mark.parametrize("nd", [4, 9, 16, 25])
+def test_port_equals_reference_tabulate(port, ref, dtype, two, is_sorted, nd):
+    """nd = NDESCRPT (tabulate.cc:456-560 dispatch: 4 for se_a / se_atten, 9 / 16 / 25 for the higher angular bases)."""
     rng = np.random.default_rng(7)
     nloc, nnei, M = 9, 23, 20
     lower, upper, vmax, s0, s1 = -0.5, 2.0, 10.0, 0.01, 0.1
@@ -271,7 +273,7 @@ def test_port_equals_reference_tabulate(port, ref, dtype, two, is_sorted):
     table = random_table(nspline, M, rng, dtype)
     em_x = rng.uniform(-1.0, 11.0, size=(nloc, nnei)).astype(dtype)  # both extrapolation sides
     em_x[0, :3] = [lower, upper, vmax]  # exact boundaries
-    em = rng.normal(size=(nloc, nnei, 4)).astype(dtype)
+    em = rng.normal(size=(nloc, nnei, nd)).astype(dtype)
     # trailing padding: identical em_x, zero angular part
     for i in range(nloc):
         npad = i % 5
@@ -280,8 +282,9 @@ def test_port_equals_reference_tabulate(port, ref, dtype, two, is_sorted):
             em[i, nnei - npad:, 1:] = 0
             em[i, nnei - npad:, 0] = em[i, nnei - 1, 0]
     te = rng.normal(size=(nloc, nnei, M)).astype(dtype) if two else None
-    dy = rng.normal(size=(nloc, 4, M)).astype(dtype)
+    dy = rng.normal(size=(nloc, nd, M)).astype(dtype)
     a = port.tabulate_fusion_se_a(table, info, em_x, em, M, te, is_sorted)
+    assert a.shape == (nloc, nd, M)
     b = ref.tabulate_fusion_se_a(table, info, em_x, em, M, te, is_sorted)
     assert (a == b).all()
     ga = port.tabulate_fusion_se_a_grad(table, info, em_x, em, dy, M, te, is_sorted)
@@ -289,7 +292,7 @@ def test_port_equals_reference_tabulate(port, ref, dtype, two, is_sorted):
     for x, y in zip(ga, gb):
         assert (x is None and y is None) or (x == y).all()
     dzx = rng.normal(size=(nloc, nnei)).astype(dtype)
-    dze = rng.normal(size=(nloc, nnei, 4)).astype(dtype)
+    dze = rng.normal(size=(nloc, nnei, nd)).astype(dtype)
     dzt = rng.normal(size=(nloc, nnei, M)).astype(dtype) if two else None
     ha = port.tabulate_fusion_se_a_grad_grad(table, info, em_x, em, dzx, dze, M, te, dzt, is_sorted)
     hb = ref.tabulate_fusion_se_a_grad_grad(table, info, em_x, em, dzx, dze, M, te, dzt, is_sorted)
