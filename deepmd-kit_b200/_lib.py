@@ -28,6 +28,8 @@ _SIGS = {
     "tabulate_fusion_se_a_{s}": "pppppp iiii p",
     "tabulate_fusion_se_a_grad_{s}": "ppp pp ppp p iiii p",
     "tabulate_fusion_se_a_grad_grad_{s}": "p pp ppp ppp iiii p",
+    "se_atten_gate_scalars_{s}": "ppp ppp iii ff p",
+    "prod_force_virial_a_pair_{s}": "ppp pppp pp iii p",
     "tabulate_fusion_se_a_nd_{s}": "pppppp iiiii p",
     "tabulate_fusion_se_a_grad_nd_{s}": "ppp pp ppp p iiiii p",
     "tabulate_fusion_se_a_grad_grad_nd_{s}": "p pp ppp ppp iiiii p",

@@ -189,8 +189,8 @@ class SeAttenModel:
                                                 nall, cfg.rcut, cfg.rcut_smth, cfg.sec, f_type=f_type)
         em3 = em.reshape(nloc, nnei, 4)
         if self.use_gate:
-            pair, sw, dsw, r = self.gate_scalars(ext_type, nlist, rij, 0, nloc)
-            pair32 = pair.to(torch.int32)
+            pair32, sw, dswr = ops.se_atten_gate_scalars(nlist, ext_type, rij, nloc, nnei, cfg.ntypes, cfg.rcut_smth,
+                                                         cfg.rcut)
             em_x = em3[:, :, 0].reshape(-1, 1).contiguous()
             xyz = ops.tabulate_fusion_se_atten_gate(self.table, self.info, em_x, em3, self.tt_full, pair32, sw, M)
         else:
@@ -223,12 +223,16 @@ class SeAttenModel:
         # dE/d(sw_ij) = sum_k dE/d(two_embed)_ijk * tt_full[pair]_k ; pair force through the switch:
         # dE/dr_j = q * sw'(r) * (r_j - r_i) / r  (and the opposite on the centre atom)
         if self.use_gate:
-            gx, gem, q = ops.tabulate_fusion_se_atten_gate_grad(self.table, self.info, em_x, em3, self.tt_full, pair32, sw,
-                                                                dy, M)
-            net_deriv = gem.reshape(nloc, nnei, 4)
-            net_deriv[:, :, 0] += gx.reshape(nloc, nnei)
-            coef = torch.where(r > 0, q * dsw / r.clamp_min(1e-30), torch.zeros_like(q))
-            vec = coef.unsqueeze(-1) * rij.reshape(nloc, nnei, 3)  # dE/dr_j of the switch path
+            # the switch-path force -(q * sw'/r) r_ij rides in the force / virial kernel: nothing per pair is
+            # materialised between the table backward and the scatter
+            _, gem, q = ops.tabulate_fusion_se_atten_gate_grad(self.table, self.info, em_x, em3, self.tt_full, pair32, sw,
+                                                               dy, M, fuse_x=True)
+            if mapping is not None:
+                ops.use_nlist_map(nlist, mapping)
+            n_out = nloc if mapping is not None else nall
+            force, virial, av = ops.prod_force_virial_a_pair(gem.reshape(nloc, -1), dv, rij, nlist, q, dswr, nloc, n_out,
+                                                             nnei, atom_virial=atom_virial)
+            return e_atom.sum(), force.reshape(-1, 3), virial, dict(atom_energy=e_atom, atom_virial=av, nlist=nlist)
         else:
             net_deriv = torch.empty((nloc, nnei, 4), dtype=self.dtype, device=em.device)
             vec = torch.empty((nloc, nnei, 3), dtype=self.dtype, device=em.device)

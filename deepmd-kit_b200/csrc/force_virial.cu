@@ -36,6 +36,10 @@ struct FvParams {
   int nloc, nall, nnei;
   long long nrows;    // nframes * nloc
   int center_offset;  // centre atom of row r is r + center_offset (atom-chunked evaluation)
+  // optional central pair force (se_atten switch path): slot (r, s) adds -(pair_q * pair_w) * rij to its neighbour
+  // (and the opposite to the centre atom), with the same virial bookkeeping as the env-mat path
+  const FP* pair_q;  // [nrows][nnei] or null
+  const FP* pair_w;  // [nrows][nnei]
 };
 
 __device__ __forceinline__ void ld2(const double* q, double& a, double& b) {
@@ -108,9 +112,15 @@ __global__ void __launch_bounds__(128) k_force_virial(const __grid_constant__ Fv
       if (lane < nvalid) {
         const typename Vec4<FP>::type g = *reinterpret_cast<const typename Vec4<FP>::type*>(nd + 4 * s);
         const FP* d = st + lane * kStride;
-        const FP f0 = g.x * d[0] + g.y * d[3] + g.z * d[6] + g.w * d[9];
-        const FP f1 = g.x * d[1] + g.y * d[4] + g.z * d[7] + g.w * d[10];
-        const FP f2 = g.x * d[2] + g.y * d[5] + g.z * d[8] + g.w * d[11];
+        FP f0 = g.x * d[0] + g.y * d[3] + g.z * d[6] + g.w * d[9];
+        FP f1 = g.x * d[1] + g.y * d[4] + g.z * d[7] + g.w * d[10];
+        FP f2 = g.x * d[2] + g.y * d[5] + g.z * d[8] + g.w * d[11];
+        FP r0 = (FP)0., r1 = (FP)0., r2 = (FP)0.;
+        if (VIRIAL) r0 = rj[3 * s + 0], r1 = rj[3 * s + 1], r2 = rj[3 * s + 2];
+        if (VIRIAL && p.pair_q) {
+          const FP cf = p.pair_q[row * nnei + s] * p.pair_w[row * nnei + s];
+          f0 -= cf * r0, f1 -= cf * r1, f2 -= cf * r2;
+        }
         c0 += f0, c1 += f1, c2 += f2;
         const int j = nl[s];
         if (j >= 0) {
@@ -120,7 +130,6 @@ __global__ void __launch_bounds__(128) k_force_virial(const __grid_constant__ Fv
             atomic_add(fo + 3 * (long long)j + 2, f2);
           }
           if (VIRIAL) {
-            const FP r0 = rj[3 * s + 0], r1 = rj[3 * s + 1], r2 = rj[3 * s + 2];
             const FP t[9] = {f0 * r0, f0 * r1, f0 * r2, f1 * r0, f1 * r1, f1 * r2, f2 * r0, f2 * r1, f2 * r2};
 #pragma unroll
             for (int q = 0; q < 9; ++q) vs[q] += (double)t[q];
@@ -233,7 +242,8 @@ int launch_fv_grad(bool virial, FP* grad_net, const FP* grad, const FP* in_deriv
 template <typename FP, bool FORCE, bool VIRIAL>
 int launch_fv(FP* force, FP* virial, FP* atom_virial, const FP* net_deriv, const FP* in_deriv,
               const FP* rij, const int* nlist, int nloc, int nall, int nnei, int nframes,
-              cudaStream_t st, int center_offset = 0, int accumulate = 0) {
+              cudaStream_t st, int center_offset = 0, int accumulate = 0, const FP* pair_q = nullptr,
+              const FP* pair_w = nullptr) {
   DPB_REQUIRE(nloc >= 0 && nall >= 0 && nnei >= 0 && nframes >= 1 && center_offset >= 0 &&
                   (long long)center_offset + nloc <= nall,
               "prod_force/virial: need nall >= center_offset + nloc >= 0, nnei >= 0, nframes >= 1");
@@ -266,6 +276,10 @@ int launch_fv(FP* force, FP* virial, FP* atom_virial, const FP* net_deriv, const
   p.nnei = nnei;
   p.nrows = nrows;
   p.center_offset = center_offset;
+  DPB_REQUIRE((pair_q == nullptr) == (pair_w == nullptr) && (!pair_q || VIRIAL),
+              "prod_force_virial_a_pair: pair_q and pair_w come together (fused force + virial entry only)");
+  p.pair_q = pair_q;
+  p.pair_w = pair_w;
   auto kern = k_force_virial<FP, FORCE, VIRIAL>;
   int occ = 0;
   DPB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, 128, 0));
@@ -325,6 +339,22 @@ extern "C" {
   }
 DPB200_DEF_FV(f64, double)
 DPB200_DEF_FV(f32, float)
+
+/* fused force + virial with an additional central pair force -(pair_q * pair_w) * rij per slot (se_atten: pair_q =
+ * dE/d(sw) from the gated table backward, pair_w = sw'(r) / r from dpb200_se_atten_gate_scalars) */
+#define DPB200_DEF_FVP(SUF, FP)                                                                    \
+  int dpb200_prod_force_virial_a_pair_##SUF(FP* force, FP* virial, FP* atom_virial,                \
+                                            const FP* net_deriv, const FP* in_deriv,               \
+                                            const FP* rij, const int* nlist, const FP* pair_q,     \
+                                            const FP* pair_w, int nloc, int nall, int nnei,        \
+                                            dpb200_stream_t stream) {                              \
+    return dpb200::launch_fv<FP, true, true>(force, virial, atom_virial, net_deriv, in_deriv,      \
+                                             rij, nlist, nloc, nall, nnei, 1,                      \
+                                             (cudaStream_t)stream, 0, 0, pair_q, pair_w);          \
+  }
+DPB200_DEF_FVP(f64, double)
+DPB200_DEF_FVP(f32, float)
+#undef DPB200_DEF_FVP
 
 #define DPB200_DEF_FVG(SUF, FP)                                                                    \
   int dpb200_prod_force_grad_a_##SUF(FP* grad_net, const FP* grad, const FP* in_deriv,             \

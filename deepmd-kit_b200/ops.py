@@ -284,8 +284,9 @@ def tabulate_fusion_se_atten_gate(table, table_info, em_x, em, tt_full, pair, sw
 
 
 def tabulate_fusion_se_atten_gate_grad(table, table_info, em_x, em, tt_full, pair, sw, dy, last_layer_size,
-                                       is_sorted=True):
-    """Backward of tabulate_fusion_se_atten_gate: (dy_dem_x [nloc*nnei, 1], dy_dem [nloc, nnei, 4], dy_dsw [nloc, nnei])."""
+                                       is_sorted=True, fuse_x=False):
+    """Backward of tabulate_fusion_se_atten_gate: (dy_dem_x [nloc*nnei, 1], dy_dem [nloc, nnei, 4], dy_dsw [nloc, nnei]).
+    fuse_x: em_x is component 0 of em, its gradient is added into dy_dem[..., 0] and dy_dem_x is returned as None."""
     dev = _need_cuda(("table", table), ("em_x", em_x), ("em", em), ("tt_full", tt_full), ("pair", pair), ("sw", sw),
                      ("dy", dy))
     s = _suffix(table)
@@ -294,7 +295,7 @@ def tabulate_fusion_se_atten_gate_grad(table, table_info, em_x, em, tt_full, pai
     tt_full, pair, sw = _c(tt_full, table.dtype), _c(pair, torch.int32), _c(sw, table.dtype)
     nloc, nnei = em.shape[0], em.shape[1]
     M = int(last_layer_size)
-    g_x = torch.empty_like(em_x)
+    g_x = None if fuse_x else torch.empty_like(em_x)
     g_em = torch.empty_like(em)
     g_sw = torch.empty((nloc, nnei), dtype=table.dtype, device=dev)
     lib().call("tabulate_fusion_se_atten_gate_grad_" + s, _p(g_x), _p(g_em), _p(g_sw), _p(table),
@@ -485,6 +486,37 @@ def prod_force_virial_a(net_deriv, in_deriv, rij, nlist, nloc, nall, nnei, atom_
     lib().call("prod_force_virial_a_" + s, _p(force), _p(virial), _p(av), _p(net_deriv), _p(in_deriv), _p(rij),
                _p(nlist), nloc, nall, nnei, _stream(dev))
     return force, virial, av
+
+
+def prod_force_virial_a_pair(net_deriv, in_deriv, rij, nlist, pair_q, pair_w, nloc, nall, nnei, atom_virial=False):
+    """prod_force_virial_a plus the central pair force -(pair_q * pair_w) * rij of every slot (se_atten switch path;
+    dpb200_prod_force_virial_a_pair): (force[nall*3], virial[9], atom_virial|None)."""
+    dev = _need_cuda(("net_deriv", net_deriv), ("in_deriv", in_deriv), ("rij", rij), ("nlist", nlist),
+                     ("pair_q", pair_q), ("pair_w", pair_w))
+    s = _suffix(net_deriv)
+    dt = net_deriv.dtype
+    net_deriv, in_deriv, rij, nlist = _c(net_deriv), _c(in_deriv, dt), _c(rij, dt), _c(nlist, torch.int32)
+    pair_q, pair_w = _c(pair_q, dt), _c(pair_w, dt)
+    force = torch.empty(nall * 3, dtype=dt, device=dev)
+    virial = torch.empty(9, dtype=dt, device=dev)
+    av = torch.empty(nall * 9, dtype=dt, device=dev) if atom_virial else None
+    lib().call("prod_force_virial_a_pair_" + s, _p(force), _p(virial), _p(av), _p(net_deriv), _p(in_deriv), _p(rij),
+               _p(nlist), _p(pair_q), _p(pair_w), nloc, nall, nnei, _stream(dev))
+    return force, virial, av
+
+
+def se_atten_gate_scalars(nlist, ext_type, rij, nloc, nnei, ntypes, rcut_smth, rcut):
+    """Per (centre, slot) of the formatted list (extended indices): (pair int32 = row of tt_full, sw, sw'(r)/r), all
+    [nloc, nnei] (dpb200_se_atten_gate_scalars; se_atten.py:916-926, 979-983)."""
+    dev = _need_cuda(("nlist", nlist), ("ext_type", ext_type), ("rij", rij))
+    s = _suffix(rij)
+    nlist, ext_type, rij = _c(nlist, torch.int32), _c(ext_type, torch.int32), _c(rij)
+    pair = torch.empty((nloc, nnei), dtype=torch.int32, device=dev)
+    sw = torch.empty((nloc, nnei), dtype=rij.dtype, device=dev)
+    dswr = torch.empty((nloc, nnei), dtype=rij.dtype, device=dev)
+    lib().call("se_atten_gate_scalars_" + s, _p(pair), _p(sw), _p(dswr), _p(nlist), _p(ext_type), _p(rij), int(nloc),
+               int(nnei), int(ntypes), float(rcut_smth), float(rcut), _stream(dev))
+    return pair, sw, dswr
 
 
 def prod_force_grad_a(grad, in_deriv, nlist, nloc, nnei, nframes=1, ngrad=None):

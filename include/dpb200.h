@@ -350,6 +350,29 @@ int dpb200_split_tf32_f32(float* out, long long ld_out, const float* x, long lon
                           int copies, dpb200_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------
+ * se_atten (DPA-1 strip mode, attn_layer 0) glue around the pair-indexed gate (csrc/se_atten.cu,
+ * csrc/force_virial.cu).  Reference algebra: deepmd/pt/model/descriptor/se_atten.py:916-926 (tebd_idx), :979-985
+ * (gg_t = tt_full[tebd_idx] * sw, tabulate_fusion_se_atten); the force through the switch is autograd there.
+ *  se_atten_gate_scalars : per (centre, slot) of the formatted list `nlist` (extended indices, -1 = empty):
+ *      pair = type_i * (ntypes + 1) + type_j (empty slot or negative type -> the padding type `ntypes`),
+ *      sw = spline5 switch of |rij| (switcher.h:61-84; 0 for empty slots), dsw_over_r = sw'(r) / r.
+ *  prod_force_virial_a_pair : dpb200_prod_force_virial_a plus the central pair force
+ *      -(pair_q * pair_w) * rij on the neighbour of every slot (opposite on the centre), included in the virial
+ *      and the atomic virial: pair_q = dE/d(sw) (dpb200_tabulate_fusion_se_atten_gate_grad), pair_w = dsw_over_r.
+ * ------------------------------------------------------------------------------------- */
+#define DPB200_DECL_ATTEN_GLUE(SUF, FP)                                                                          \
+  int dpb200_se_atten_gate_scalars_##SUF(int* pair, FP* sw, FP* dsw_over_r, const int* nlist, const int* type,  \
+                                         const FP* rij, int nloc, int nnei, int ntypes, float rcut_smth,        \
+                                         float rcut, dpb200_stream_t stream);                                   \
+  int dpb200_prod_force_virial_a_pair_##SUF(FP* force, FP* virial, FP* atom_virial /*nullable*/,                \
+                                            const FP* net_deriv, const FP* in_deriv, const FP* rij,             \
+                                            const int* nlist, const FP* pair_q, const FP* pair_w, int nloc,     \
+                                            int nall, int nnei, dpb200_stream_t stream);
+DPB200_DECL_ATTEN_GLUE(f64, double)
+DPB200_DECL_ATTEN_GLUE(f32, float)
+#undef DPB200_DECL_ATTEN_GLUE
+
+/* ---------------------------------------------------------------------------------------
  * tabulate_fusion_se_a for the higher angular bases, ndescrpt = 9 / 16 / 25 (csrc/tabulate_nd.cu).
  * Replaces deepmd::tabulate_fusion_se_a{,_grad,_grad_grad}_{cpu,gpu} called with ndescrpt != 4
  * (source/lib/include/tabulate.h:28-72, dispatch source/lib/src/tabulate.cc:456-560; caller
