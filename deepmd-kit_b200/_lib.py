@@ -33,8 +33,8 @@ _SIGS = {
     "tabulate_fusion_se_a_nd_{s}": "pppppp iiiii p",
     "tabulate_fusion_se_a_grad_nd_{s}": "ppp pp ppp p iiiii p",
     "tabulate_fusion_se_a_grad_grad_nd_{s}": "p pp ppp ppp iiiii p",
-    "tabulate_fusion_se_atten_gate_{s}": "ppppp ppp iiii p",
-    "tabulate_fusion_se_atten_gate_grad_{s}": "ppp pp pp ppp p iiii p",
+    "tabulate_fusion_se_atten_gate_{s}": "ppppp ppp iiiii p",
+    "tabulate_fusion_se_atten_gate_grad_{s}": "ppp pp pp ppp p iiiii p",
     "tabulate_fusion_se_a_ex_{s}": "ppp pli pl p iiiii p",
     "tabulate_fusion_se_a_grad_ex_{s}": "ppp pp pli pl p p iiii p",
     "prod_force_a_{s}": "pppp iiii p",

@@ -144,6 +144,12 @@ class SeAttenModel:
         # default: the pair-indexed gate entry points (dpb200_tabulate_fusion_se_atten_gate*), which form
         # tt_full[pair] * sw inside the kernel; False = the reference-schema op fed with the materialised tensor
         self.use_gate = True
+        # compressed table coefficients in the gated backward (same host-side check as SeAModel; fp64 only here)
+        import os
+
+        self.coef_flags = 0
+        if self.device.type == "cuda" and dtype == torch.float64 and os.environ.get("DPB200_TAB_COMPRESS", "1") != "0":
+            self.coef_flags = int(ops.compressed_coef_flags(self.table64, self.info))
         self.nslice = 6
         self.use_tc = bool(dtype == torch.float64 and self.device.type == "cuda" and self.fit.prepare_tc(self.nslice))
 
@@ -226,7 +232,7 @@ class SeAttenModel:
             # the switch-path force -(q * sw'/r) r_ij rides in the force / virial kernel: nothing per pair is
             # materialised between the table backward and the scatter
             _, gem, q = ops.tabulate_fusion_se_atten_gate_grad(self.table, self.info, em_x, em3, self.tt_full, pair32, sw,
-                                                               dy, M, fuse_x=True)
+                                                               dy, M, fuse_x=True, flags=self.coef_flags)
             if mapping is not None:
                 ops.use_nlist_map(nlist, mapping)
             n_out = nloc if mapping is not None else nall

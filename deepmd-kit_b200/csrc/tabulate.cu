@@ -887,6 +887,48 @@ __global__ void __launch_bounds__(512) k_tab_fwd(const __grid_constant__ TabPara
           acc[3][c] += e3 * g;
         }
       }
+    } else if (!GG && TWO && p.gate_tt != nullptr && !any_delta) {
+      // se_atten with the pair-indexed gate, nobody outside [lower, max): the common case of config 5.  The
+      // neighbour's type-pair row index and switch value ride in its record (`delta` is zero for everybody here and
+      // `mult` is already folded into e[]), so the loop reads them as shared-memory broadcasts; the (ntypes+1)^2-row
+      // pair table stays L1-resident.  Same pipelining as the plain loop above.
+      {
+        const long long gj = i * p.nnei + j0 + lane;
+        FP gsw = (FP)0.;
+        int gpr = 0;
+        if (lane < nproc) gsw = p.gate_sw[gj], gpr = p.gate_pair[gj];
+        rec[lane].delta = gsw;
+        rec[lane].mult = gpr;
+        __syncwarp();
+      }
+      auto fetch = [&](int row) {
+        cur_row = row;
+        fetch_row<FP, NC>(a, hot, p.T, row, r0, p.H, p.M, ob);
+      };
+      if (nproc > 0 && rec[0].idx != cur_row) fetch(rec[0].idx);  // warp-uniform
+#pragma unroll 2
+      for (int jj = 0; jj < nproc; ++jj) {
+        const Rec<FP>& r = rec[jj];
+        const int row_n = rec[jj + 1 < nproc ? jj + 1 : jj].idx;
+        const FP xx = r.xx;
+        const FP gs = r.delta;
+        const FP* __restrict__ trow = p.gate_tt + (long long)r.mult * p.M;
+        const FP e0 = r.e[0], e1 = r.e[1], e2 = r.e[2], e3 = r.e[3];
+        FP g[NC];
+#pragma unroll
+        for (int c = 0; c < NC; ++c) {
+          const FP v = poly(a[c], xx);
+          g[c] = v * (__ldg(trow + kc[c]) * gs) + v;
+        }
+        if (row_n != cur_row) fetch(row_n);  // warp-uniform
+#pragma unroll
+        for (int c = 0; c < NC; ++c) {
+          acc[0][c] += e0 * g[c];
+          acc[1][c] += e1 * g[c];
+          acc[2][c] += e2 * g[c];
+          acc[3][c] += e3 * g[c];
+        }
+      }
     } else {
       if (ring_on) {
         __syncwarp();
@@ -1375,7 +1417,9 @@ __host__ __device__ constexpr int grad_mma_tile_ld(int kt) { return (4 * kt + 11
 // BSM: the B fragments (dy of the current atom) live in a per-warp shared-memory tile instead of 2*KT
 // registers, which lets MAXT / 32 warps (instead of 12) share an SM: the kernel is latency-bound on the
 // coefficient fetches of rows outside the hot window, so warps in flight are what it needs.
-template <int KT, bool BSM, int MAXT, bool CM = false>
+// GATE: se_atten with the pair-indexed gate (two_embed = tt_full[pair] * sw, never materialised): G and G' are
+// scaled by 1 + t, and dE/d(sw) = sum_m e[m] (g tt . dy^T)[m] comes from a third product with A = g * tt.
+template <int KT, bool BSM, int MAXT, bool CM = false, bool GATE = false>
 __global__ void __launch_bounds__(MAXT) k_tab_grad_mma(const __grid_constant__ TabParams<double> p) {
   using FP = double;
   const int lane = threadIdx.x & 31;
@@ -1456,7 +1500,14 @@ __global__ void __launch_bounds__(MAXT) k_tab_grad_mma(const __grid_constant__ T
       const FP dl = r.delta;
       const unsigned rel = (unsigned)(r.idx - r0);
       const bool inwin = rel < (unsigned)p.H;
-      FP c1a = 0., c1b = 0., c2a = 0., c2b = 0.;
+      FP c1a = 0., c1b = 0., c2a = 0., c2b = 0., c3a = 0., c3b = 0.;
+      FP gsw = 0.;
+      const FP* __restrict__ ttrow = nullptr;
+      if (GATE) {
+        const long long gj = i * p.nnei + j0 + (live ? nb : nproc - 1);
+        gsw = p.gate_sw[gj];
+        ttrow = p.gate_tt + (long long)p.gate_pair[gj] * M;
+      }
 #define DPB_GRAD_STEPS(BASE, COMP)                                                            \
   _Pragma("unroll") for (int t = 0; t < KT; ++t) {                                            \
     const unsigned off = (t == KT - 1) ? off_last : (unsigned)t * 64u + off_k;                \
@@ -1493,6 +1544,13 @@ __global__ void __launch_bounds__(MAXT) k_tab_grad_mma(const __grid_constant__ T
     }                                                                                         \
     g += gd * dl; /* dl == 0 inside [lower, max): one FMA instead of a select pair */         \
     const FP bt = BSM ? bsrc[4 * t] : bf[BSM ? 0 : t];                                        \
+    if (GATE) {                                                                               \
+      const FP tt = __ldg(ttrow + (off >> 4)); /* off = 16 * (clamped) channel */              \
+      dmma884(c3a, c3b, g * tt, bt);                                                          \
+      const FP tg = tt * gsw;                                                                 \
+      g = fma(g, tg, g);                                                                      \
+      gd = fma(gd, tg, gd);                                                                   \
+    }                                                                                         \
     dmma884(c1a, c1b, g, bt);                                                                 \
     dmma884(c2a, c2b, gd, bt);                                                                \
   }
@@ -1516,6 +1574,11 @@ __global__ void __launch_bounds__(MAXT) k_tab_grad_mma(const __grid_constant__ T
       const FP ea = r.e[(2 * kk) & 3], eb = r.e[(2 * kk + 1) & 3];  // pre-multiplied by the fold multiplicity
       FP part = kk < 2 ? ea * c2a + eb * c2b : (FP)0.;
       part += __shfl_xor_sync(kFull, part, 1);
+      if (GATE) {
+        FP pq = kk < 2 ? ea * c3a + eb * c3b : (FP)0.;
+        pq += __shfl_xor_sync(kFull, pq, 1);
+        if (live && kk == 0) p.gate_q[i * p.nnei + j0 + nb] = pq;
+      }
       if (live && kk < 2) {
         const FP mult = (FP)r.mult;
         const int j = j0 + nb;
@@ -1537,6 +1600,7 @@ __global__ void __launch_bounds__(MAXT) k_tab_grad_mma(const __grid_constant__ T
         if (!fuse_x) p.dy_dem_x[i * p.ldx_i + (long long)j * p.ldx_j] = (FP)0.;
 #pragma unroll
         for (int m = 0; m < 4; ++m) gem[(long long)j * 4 + m] = (FP)0.;
+        if (GATE) p.gate_q[i * p.nnei + j] = (FP)0.;
       }
     }
     i = ni;
@@ -2063,8 +2127,9 @@ int launch_grad(FP* dy_dem_x, FP* dy_dem, FP* dy_dtwo, const FP* table, const FP
   p.two_ring = ring ? 1 : 0;
   const size_t rec_bytes = (size_t)nw * 32 * sizeof(Rec<FP>) + (ring ? (size_t)nw * kRing * M * sizeof(FP) : 0);
   const int kt = (M + 3) / 4;
-  const bool mma_ok = std::is_same<FP, double>::value && !tw && use_mma_path() &&
-                      (kt == 8 || kt == 16 || kt == 20 || kt == 25 || kt == 32);
+  // the tensor-core backward serves plain se_a and the pair-indexed gate (not a materialised two_embed)
+  const bool mma_ok = std::is_same<FP, double>::value && two == nullptr && use_mma_path() &&
+                      (kt == 8 || kt == 16 || kt == 20 || kt == 25 || kt == 32) && (!ga || grad_variant() == 1);
   const bool cm32 = sizeof(FP) == 4 && !tw && (flags & DPB200_TAB_COMPRESSED_COEF) && fwd_cm_enabled();
   const bool cm = cm32 || (mma_ok && (flags & DPB200_TAB_COMPRESSED_COEF) && grad_variant() == 1);
   p.Mc = M;
@@ -2129,7 +2194,15 @@ int launch_grad(FP* dy_dem_x, FP* dy_dem, FP* dy_dtwo, const FP* table, const FP
       const int gridv = (int)(wantv < cap ? wantv : cap);
 #define DPB_LAUNCH_GRAD_MMA(KT)                                                                 \
   do {                                                                                          \
-    if (cm) {                                                                                   \
+    if (ga && cm) {                                                                             \
+      auto kern = k_tab_grad_mma<KT, true, 512, true, true>;                                    \
+      e1 = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemv); \
+      if (e1 == cudaSuccess) kern<<<gridv, nwv * 32, smemv, st>>>(p);                           \
+    } else if (ga) {                                                                            \
+      auto kern = k_tab_grad_mma<KT, true, 512, false, true>;                                   \
+      e1 = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemv); \
+      if (e1 == cudaSuccess) kern<<<gridv, nwv * 32, smemv, st>>>(p);                           \
+    } else if (cm) {                                                                            \
       auto kern = k_tab_grad_mma<KT, true, 512, true>;                                          \
       e1 = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemv); \
       if (e1 == cudaSuccess) kern<<<gridv, nwv * 32, smemv, st>>>(p);                           \
@@ -2258,22 +2331,22 @@ extern "C" {
   int dpb200_tabulate_fusion_se_atten_gate_##SUF(                                                  \
       FP* out, const FP* table, const FP* table_info, const FP* em_x, const FP* em,                \
       const FP* tt_full, const int* pair, const FP* sw, int nloc, int nnei, int last_layer_size,   \
-      int is_sorted, dpb200_stream_t stream) {                                                     \
+      int is_sorted, int flags, dpb200_stream_t stream) {                                          \
     dpb200::GateArgs<FP> ga = {tt_full, pair, sw, nullptr};                                        \
     return dpb200::launch_fwd<FP, false>(out, table, table_info, em_x, nnei, 1, em,                \
                                          (long long)nnei * 4, nullptr, nullptr, nullptr, nullptr,  \
                                          nloc, nnei, last_layer_size, is_sorted, 0,                \
-                                         (cudaStream_t)stream, nullptr, 0, &ga);                   \
+                                         (cudaStream_t)stream, nullptr, flags, &ga);               \
   }                                                                                                \
   int dpb200_tabulate_fusion_se_atten_gate_grad_##SUF(                                             \
       FP* dy_dem_x, FP* dy_dem, FP* dy_dsw, const FP* table, const FP* table_info,                 \
       const FP* em_x, const FP* em, const FP* tt_full, const int* pair, const FP* sw,              \
-      const FP* dy, int nloc, int nnei, int last_layer_size, int is_sorted,                        \
+      const FP* dy, int nloc, int nnei, int last_layer_size, int is_sorted, int flags,             \
       dpb200_stream_t stream) {                                                                    \
     dpb200::GateArgs<FP> ga = {tt_full, pair, sw, dy_dsw};                                         \
     return dpb200::launch_grad<FP>(dy_dem_x, dy_dem, nullptr, table, table_info, em_x, nnei, 1,    \
                                    em, (long long)nnei * 4, nullptr, dy, nloc, nnei,               \
-                                   last_layer_size, is_sorted, (cudaStream_t)stream, 0, &ga);      \
+                                   last_layer_size, is_sorted, (cudaStream_t)stream, flags, &ga);  \
   }                                                                                                \
   int dpb200_tabulate_fusion_se_a_grad_grad_##SUF(                                                 \
       FP* dz_dy, const FP* table, const FP* table_info, const FP* em_x, const FP* em,              \

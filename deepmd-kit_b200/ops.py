@@ -265,7 +265,8 @@ def tabulate_fusion_se_a_grad(table, table_info, em_x, em, dy, last_layer_size, 
     return g_x, g_em, g_two
 
 
-def tabulate_fusion_se_atten_gate(table, table_info, em_x, em, tt_full, pair, sw, last_layer_size, is_sorted=True):
+def tabulate_fusion_se_atten_gate(table, table_info, em_x, em, tt_full, pair, sw, last_layer_size, is_sorted=True,
+                                  flags=0):
     """tabulate_fusion_se_atten with two_embed = tt_full[pair] * sw formed inside the kernel (never materialised):
     pair int32 [nloc, nnei] rows of tt_full [(ntypes+1)^2, M], sw [nloc, nnei].  Returns [nloc, 4, M]."""
     dev = _need_cuda(("table", table), ("em_x", em_x), ("em", em), ("tt_full", tt_full), ("pair", pair), ("sw", sw))
@@ -279,12 +280,12 @@ def tabulate_fusion_se_atten_gate(table, table_info, em_x, em, tt_full, pair, sw
         raise ValueError("dpb200: gate tensors do not match [nloc, nnei] / M")
     out = torch.empty((nloc, 4, M), dtype=table.dtype, device=dev)
     lib().call("tabulate_fusion_se_atten_gate_" + s, _p(out), _p(table), C.c_void_p(ti.data_ptr()), _p(em_x), _p(em),
-               _p(tt_full), _p(pair), _p(sw), nloc, nnei, M, int(bool(is_sorted)), _stream(dev))
+               _p(tt_full), _p(pair), _p(sw), nloc, nnei, M, int(bool(is_sorted)), int(flags), _stream(dev))
     return out
 
 
 def tabulate_fusion_se_atten_gate_grad(table, table_info, em_x, em, tt_full, pair, sw, dy, last_layer_size,
-                                       is_sorted=True, fuse_x=False):
+                                       is_sorted=True, fuse_x=False, flags=0):
     """Backward of tabulate_fusion_se_atten_gate: (dy_dem_x [nloc*nnei, 1], dy_dem [nloc, nnei, 4], dy_dsw [nloc, nnei]).
     fuse_x: em_x is component 0 of em, its gradient is added into dy_dem[..., 0] and dy_dem_x is returned as None."""
     dev = _need_cuda(("table", table), ("em_x", em_x), ("em", em), ("tt_full", tt_full), ("pair", pair), ("sw", sw),
@@ -300,7 +301,7 @@ def tabulate_fusion_se_atten_gate_grad(table, table_info, em_x, em, tt_full, pai
     g_sw = torch.empty((nloc, nnei), dtype=table.dtype, device=dev)
     lib().call("tabulate_fusion_se_atten_gate_grad_" + s, _p(g_x), _p(g_em), _p(g_sw), _p(table),
                C.c_void_p(ti.data_ptr()), _p(em_x), _p(em), _p(tt_full), _p(pair), _p(sw), _p(dy), nloc, nnei, M,
-               int(bool(is_sorted)), _stream(dev))
+               int(bool(is_sorted)), int(flags), _stream(dev))
     return g_x, g_em, g_sw
 
 

@@ -132,15 +132,18 @@ DPB200_DECL_ENV(f32, float)
    * two_embed[i][j][k] = tt_full[pair[i][j]][k] * sw[i][j]  (deepmd/pt/model/descriptor/se_atten.py:979-985: \
    * gg_t = tt_full[tebd_idx] * sw) is formed inside the kernel; the backward returns                     \
    * dy_dsw[i][j] = sum_k dy_dtwo[i][j][k] * tt_full[pair][k] instead of dy_dtwo.  Same results as the      \
-   * reference-schema entry points above fed with the materialised tensor. */                           \
+   * reference-schema entry points above fed with the materialised tensor.  dy_dem_x may be NULL: em_x is  \
+   * then component 0 of em and its gradient is added into dy_dem[..][0].  flags: 0 or the               \
+   * DPB200_TAB_COMPRESSED_COEF word of dpb200_tabulate_fusion_se_a_desc (caller-validated table).  fp64   \
+   * backward: FP64 tensor cores (three m8n8k4 products per step: G(1+t), G'(1+t), G tt). */             \
   int dpb200_tabulate_fusion_se_atten_gate_##SUF(                                                  \
       FP* out, const FP* table, const FP* table_info, const FP* em_x, const FP* em,                \
       const FP* tt_full, const int* pair, const FP* sw, int nloc, int nnei, int last_layer_size,   \
-      int is_sorted, dpb200_stream_t stream);                                                      \
+      int is_sorted, int flags, dpb200_stream_t stream);                                           \
   int dpb200_tabulate_fusion_se_atten_gate_grad_##SUF(                                             \
-      FP* dy_dem_x, FP* dy_dem, FP* dy_dsw, const FP* table, const FP* table_info,                 \
+      FP* dy_dem_x /*nullable*/, FP* dy_dem, FP* dy_dsw, const FP* table, const FP* table_info,    \
       const FP* em_x, const FP* em, const FP* tt_full, const int* pair, const FP* sw,              \
-      const FP* dy, int nloc, int nnei, int last_layer_size, int is_sorted,                        \
+      const FP* dy, int nloc, int nnei, int last_layer_size, int is_sorted, int flags,             \
       dpb200_stream_t stream);                                                                     \
   int dpb200_tabulate_fusion_se_a_grad_grad_##SUF(                                                 \
       FP* dz_dy, const FP* table, const FP* table_info, const FP* em_x, const FP* em,              \

@@ -96,3 +96,19 @@ def test_gate_op_equals_reference_schema_op(dtype):
     assert ((gx - wx).abs().max() / wx.abs().max()).item() <= tol
     assert ((gem - wem).abs().max() / wem.abs().max()).item() <= tol
     assert ((gq - wq)[:, :100].abs().max() / wq.abs().max()).item() <= 10 * tol
+    # em_x gradient folded into component 0 (dy_dem_x = NULL), with and without the compressed coefficient table
+    want = wem.clone()
+    want[:, :, 0] += wx.reshape(nloc, nnei)
+    flag_sets = [0]
+    if dtype == torch.float64:
+        fl = ops.compressed_coef_flags(m.table64, m.info)
+        assert fl == m.coef_flags and fl != 0
+        flag_sets.append(fl)
+    for fl in flag_sets:
+        none_x, gem2, gq2 = ops.tabulate_fusion_se_atten_gate_grad(m.table, m.info, em_x, em, m.tt_full, pair, sw, dy, M,
+                                                                   fuse_x=True, flags=fl)
+        t2 = tol if fl == 0 else 1e-11
+        assert none_x is None
+        assert ((gem2 - want).abs().max() / want.abs().max()).item() <= t2
+        assert ((gq2 - wq)[:, :100].abs().max() / wq.abs().max()).item() <= 10 * t2
+        assert float(gq2[:, 101:].abs().max()) == 0.0  # behind the folded padding entry
