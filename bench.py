@@ -411,7 +411,8 @@ def per_kernel(args, torch, ops, model, dp, step, L, dev, nloc, esz):
              "normalize_coord", "copy_coord", "build_nlist", "se_a_descriptor", "se_a_descriptor_grad", "halo_pack",
              "halo_unpack_add", "fit_gemm_i8", "fit_head", "fit_slice_rows", "tabulate_fusion_se_a",
              "tabulate_fusion_se_a_grad", "split_i8_rows", "tabulate_fusion_se_atten_gate",
-             "tabulate_fusion_se_atten_gate_grad"]
+             "tabulate_fusion_se_atten_gate_grad", "tabulate_fusion_se_atten_gate_desc", "fit_slice_cols",
+             "se_atten_gate_scalars", "prod_force_virial_a_pair"]
     acc = {}
     orig = {}
 
@@ -498,6 +499,9 @@ def per_kernel(args, torch, ops, model, dp, step, L, dev, nloc, esz):
         alg["tabulate_fusion_se_a_grad"] = ("hbm", 2 * nreal * M * F + 10 * nnei * F + 4 * M * F)
         # pair-indexed gate: no two_embed stream, the op is bound like the plain se_a table kernels
         alg["tabulate_fusion_se_atten_gate"] = ("fp", 20 * npr * M)
+        alg["tabulate_fusion_se_atten_gate_desc"] = ("fp", 20 * npr * M)  # the fused descriptor epilogue is not counted
+        alg["prod_force_virial_a_pair"] = ("hbm", (19 * nnei * F + 4 * nnei) + 2 * nnei * F + 3 * F)
+        alg["se_atten_gate_scalars"] = ("hbm", nnei * (4 + 3 * F) + nnei * (4 + 2 * F))
         alg["tabulate_fusion_se_atten_gate_grad"] = ("fp", 42 * npr * M)
     table = {}
     total = 0.0

@@ -35,6 +35,7 @@ _SIGS = {
     "tabulate_fusion_se_a_grad_grad_nd_{s}": "p pp ppp ppp iiiii p",
     "tabulate_fusion_se_atten_gate_{s}": "ppppp ppp iiiii p",
     "tabulate_fusion_se_atten_gate_grad_{s}": "ppp pp pp ppp p iiiii p",
+    "tabulate_fusion_se_atten_gate_desc_{s}": "ppppp ppp iiii i d p i p l l i p i i p",
     "tabulate_fusion_se_a_ex_{s}": "ppp pli pl p iiiii p",
     "tabulate_fusion_se_a_grad_ex_{s}": "ppp pp pli pl p p iiii p",
     "prod_force_a_{s}": "pppp iiii p",
@@ -71,6 +72,7 @@ _PLAIN_SIGS = {
     "fit_slice_rows_f64": "p l i p p l i i p",
     "fit_head_f64": "p p l i p pppp d l i i p",
     "fit_blocked_f64": "pp l l i i p",
+    "fit_slice_cols_f64": "p l l ii i p p i p l p",
 }
 
 

@@ -152,6 +152,8 @@ class SeAttenModel:
             self.coef_flags = int(ops.compressed_coef_flags(self.table64, self.info))
         self.nslice = 6
         self.use_tc = bool(dtype == torch.float64 and self.device.type == "cuda" and self.fit.prepare_tc(self.nslice))
+        # lower bound of the descriptor rows' exponent so that the appended type embedding fits: |tebd| < 2^(E-1)
+        self.tebd_exp = int(math.floor(math.log2(max(float(self.tebd.abs().max()), 1e-300)))) + 2
 
     def bytes_per_atom(self) -> int:
         """Per-atom intermediates alive across the whole evaluation (two_embed and its gradient are only ever
@@ -194,11 +196,24 @@ class SeAttenModel:
         em, dv, rij, nlist = ops.prod_env_mat_a(ext_coord.reshape(-1), ext_type, numneigh, rows, self.davg, self.dstd, nloc,
                                                 nall, cfg.rcut, cfg.rcut_smth, cfg.sec, f_type=f_type)
         em3 = em.reshape(nloc, nnei, 4)
+        inv = 1.0 / nnei
+        ctype = ext_type[:nloc].to(torch.int64)
+        ctype_e = torch.where(ctype < 0, torch.full_like(ctype, cfg.ntypes), ctype)
+        desc = row_exp = None
         if self.use_gate:
             pair32, sw, dswr = ops.se_atten_gate_scalars(nlist, ext_type, rij, nloc, nnei, cfg.ntypes, cfg.rcut_smth,
                                                          cfg.rcut)
             em_x = em3[:, :, 0].reshape(-1, 1).contiguous()
-            xyz = ops.tabulate_fusion_se_atten_gate(self.table, self.info, em_x, em3, self.tt_full, pair32, sw, M)
+            if self.use_tc:
+                # the warp that finishes an atom writes its descriptor straight as the int8 operand of the first fitting
+                # GEMM; the centre type embedding is appended behind it at the same row exponent
+                xyz, desc, row_exp = ops.tabulate_fusion_se_atten_gate_desc(
+                    self.table, self.info, em_x, em3, self.tt_full, pair32, sw, M, cfg.axis_neuron, inv, self.dim_in,
+                    self.nslice, self.tebd_exp, pad_rows=32)
+                ops.fit_slice_cols(desc, self.dim_in, self.dim_d, self.nslice, row_exp, self.tebd,
+                                   idx=ctype_e.to(torch.int32))
+            else:
+                xyz = ops.tabulate_fusion_se_atten_gate(self.table, self.info, em_x, em3, self.tt_full, pair32, sw, M)
         else:
             xyz = torch.empty((nloc, 4, M), dtype=self.dtype, device=em.device)
             for a in range(0, nloc, self.tab_chunk):
@@ -208,24 +223,28 @@ class SeAttenModel:
                 xyz[a:b] = ops.tabulate_fusion_se_a(self.table, self.info, em_xc, em3[a:b], M, two_embed=two, is_sorted=True)
                 del two
         # descriptor + centre type embedding -> fitting net -> dE/dD
-        inv = 1.0 / nnei
-        ctype = ext_type[:nloc].to(torch.int64)
-        ctype_e = torch.where(ctype < 0, torch.full_like(ctype, cfg.ntypes), ctype)
         e_atom = torch.empty(nloc, dtype=self.dtype, device=em.device)
         dy = torch.empty_like(xyz)
         for c0 in range(0, nloc, self.fit_chunk):
             c1 = min(nloc, c0 + self.fit_chunk)
-            g1 = torch.zeros((c1 - c0, self.dim_in), dtype=self.dtype, device=em.device)
-            g1[:, :self.dim_d] = ops.se_a_descriptor(xyz[c0:c1], cfg.axis_neuron, inv)
-            g1[:, self.dim_d:self.dim_d + cfg.tebd_dim] = self.tebd.index_select(0, ctype_e[c0:c1])
-            if self.use_tc:
-                xs, ex = ops.split_i8_rows(g1, self.nslice)
-                e, gd = self.fit.forward_backward_tc(xs, ex, c1 - c0)
+            if desc is not None:
+                e, gd = self.fit.forward_backward_tc(desc[c0:c1], row_exp[c0:c1], c1 - c0)
             else:
-                e, gd = self.fit.forward_backward(g1)
+                g1 = torch.zeros((c1 - c0, self.dim_in), dtype=self.dtype, device=em.device)
+                g1[:, :self.dim_d] = ops.se_a_descriptor(xyz[c0:c1], cfg.axis_neuron, inv)
+                g1[:, self.dim_d:self.dim_d + cfg.tebd_dim] = self.tebd.index_select(0, ctype_e[c0:c1])
+                if self.use_tc:
+                    xs, ex = ops.split_i8_rows(g1, self.nslice)
+                    e, gd = self.fit.forward_backward_tc(xs, ex, c1 - c0)
+                else:
+                    e, gd = self.fit.forward_backward(g1)
+                del g1
             e_atom[c0:c1] = e + self.bias_atom_e.index_select(0, ctype_e[c0:c1].clamp_max(cfg.ntypes - 1))
-            dy[c0:c1] = ops.se_a_descriptor_grad(gd[:, :self.dim_d].contiguous(), xyz[c0:c1], cfg.axis_neuron, inv)
-            del g1, gd
+            # (the descriptor backward reads the first dim_d columns of the dim_in-wide gradient rows in place)
+            dy[c0:c1] = ops.se_a_descriptor_grad(gd, xyz[c0:c1], cfg.axis_neuron, inv) if gd.shape[1] == self.dim_d \
+                else ops.se_a_descriptor_grad(gd[:, :self.dim_d].contiguous(), xyz[c0:c1], cfg.axis_neuron, inv)
+            del gd
+        del desc
         # dE/d(sw_ij) = sum_k dE/d(two_embed)_ijk * tt_full[pair]_k ; pair force through the switch:
         # dE/dr_j = q * sw'(r) * (r_j - r_i) / r  (and the opposite on the centre atom)
         if self.use_gate:

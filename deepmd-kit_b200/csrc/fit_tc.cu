@@ -695,6 +695,33 @@ __global__ void __launch_bounds__(1024) k_fit_slice(signed char* __restrict__ ou
   store_slices16<NS>(out + r * ld_out + c0, Kp, v, pow2i(7 + 8 * (NS - 1) - E));
 }
 
+// Extra operand columns that are a table look-up per row (se_atten: the centre atom's type embedding behind the
+// descriptor): columns [col0, col0 + width) of every digit slice of row r get the digits of src[idx[r]][c] at the
+// row's exponent row_exp[r] (written earlier by the producer of the other columns, which must have bounded it from
+// below so that these values fit: |v| < 2^(E-1)).
+template <int NS>
+__global__ void k_fit_slice_cols(signed char* __restrict__ out, long long ld_out, long long slice_stride, int col0,
+                                 int width, const int* __restrict__ row_exp, const double* __restrict__ src,
+                                 int src_ld, const int* __restrict__ idx, long long n) {
+  unsigned long long bias = 0;
+#pragma unroll
+  for (int k = 0; k < NS; ++k) bias = bias * 256ull + 128ull;
+  const double magic = 6755399441055744.0 + (double)bias;
+  for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < n * width;
+       e += (long long)gridDim.x * blockDim.x) {
+    const long long r = e / width;
+    const int c = (int)(e - r * width);
+    const int E = row_exp[r];
+    const long long sr = idx ? (long long)idx[r] : r;
+    const double f = fma(src[sr * src_ld + c], pow2i(7 + 8 * (NS - 1) - E), magic);
+    const unsigned long long u =
+        ((unsigned long long)(unsigned)__double2hiint(f) << 32) | (unsigned long long)(unsigned)__double2loint(f);
+    signed char* __restrict__ o = out + r * ld_out + col0 + c;
+#pragma unroll
+    for (int s = 0; s < NS; ++s) o[s * slice_stride] = (signed char)(((u >> (8 * (NS - 1 - s))) & 0xffu) ^ 0x80u);
+  }
+}
+
 // row-major [n][N] (leading dimension ld) <-> blocked layout (tests and the non-tensor-core callers)
 __global__ void k_fit_to_blocked(double* __restrict__ dst, const double* __restrict__ src, long long ld, long long n,
                                  int N, int to_blocked) {
@@ -945,6 +972,30 @@ int dpb200_fit_head_f64(double* e_out, signed char* out, long long ld_out, int k
   else
     k_fit_slice<4, true><<<(unsigned)((nrow + 31) / 32), 32 * (N / 16), 0, (cudaStream_t)stream>>>(
         out, ld_out, kp, row_exp, t, y, w_head, idt, b_head, e_out, nrow, N);
+  DPB_CUDA(cudaGetLastError());
+  note_launches(1);
+  return DPB200_OK;
+}
+
+int dpb200_fit_slice_cols_f64(signed char* out, long long ld_out, long long slice_stride, int col0, int width,
+                              int nslice, const int* row_exp, const double* src, int src_ld, const int* idx,
+                              long long nrow, dpb200_stream_t stream) {
+  using namespace dpb200;
+  DPB_REQUIRE(nslice == 6 || nslice == 4, "fit_slice_cols: built for 6 or 4 operand slices");
+  DPB_REQUIRE(nrow >= 0 && width >= 0 && col0 >= 0 && col0 + width <= slice_stride &&
+                  ld_out >= (long long)nslice * slice_stride && src_ld >= width,
+              "fit_slice_cols: the columns must lie inside one slice of the row");
+  if (nrow == 0 || width == 0) return DPB200_OK;
+  DPB_REQUIRE(out && row_exp && src, "fit_slice_cols: null pointer");
+  long long grid = (nrow * width + 255) / 256;
+  const long long cap = (long long)sm_count() * 16;
+  if (grid > cap) grid = cap;
+  if (nslice == 6)
+    k_fit_slice_cols<6><<<(unsigned)grid, 256, 0, (cudaStream_t)stream>>>(out, ld_out, slice_stride, col0, width, row_exp,
+                                                                          src, src_ld, idx, nrow);
+  else
+    k_fit_slice_cols<4><<<(unsigned)grid, 256, 0, (cudaStream_t)stream>>>(out, ld_out, slice_stride, col0, width, row_exp,
+                                                                          src, src_ld, idx, nrow);
   DPB_CUDA(cudaGetLastError());
   note_launches(1);
   return DPB200_OK;

@@ -87,6 +87,9 @@ struct TabParams {
   int* row_exp;         // mode 2, fp64: binary exponent of the row's fixed-point scale
   FP desc_scale;        // 1/nnei
   int desc_mode, axis, nslice;
+  long long desc_slice_stride;  // mode 2 / 3: elements between two digit slices of a row (>= M*axis; extra columns
+                                // are the caller's: se_atten appends the centre type embedding there)
+  int desc_min_exp;             // mode 2 / 3: lower bound of the row exponent (so that the caller's extra columns fit)
 };
 
 template <typename FP>
@@ -526,11 +529,12 @@ __device__ __forceinline__ void desc_store_split_i8(const TabParams<float>& p, c
   int e = (int)((__float_as_uint(r2) >> 23) & 0xffu) - 127;
   e = __reduce_max_sync(kFull, e);
   int E = e + 2;  // |D| < 2^(E-1)
+  E = E < p.desc_min_exp ? p.desc_min_exp : E;
   E = E < -90 ? -90 : (E > 100 ? 100 : E);
   if (lane == 0) p.row_exp[row] = E;
   const float up = s2 * __uint_as_float((unsigned)(127 + 31 - E) << 23);
   signed char* __restrict__ base = reinterpret_cast<signed char*>(p.desc) + row * p.desc_ld;
-  const long long K = (long long)M * 16;
+  const long long K = p.desc_slice_stride;
 #pragma unroll
   for (int c = 0; c < NC; ++c) {
     const int k1 = lane + 32 * c;
@@ -586,6 +590,7 @@ __device__ __forceinline__ void desc_store_split_ns(const TabParams<double>& p, 
   int e = ((__double2hiint(r2) >> 20) & 0x7ff) - 1023;
   e = __reduce_max_sync(kFull, e);
   int E = e + 2;  // |D| < 2^(E-1)
+  E = E < p.desc_min_exp ? p.desc_min_exp : E;
   E = E < -900 ? -900 : (E > 900 ? 900 : E);
   if (lane == 0) p.row_exp[row] = E;
   constexpr int P = 7 + 8 * (NS - 1);
@@ -595,7 +600,7 @@ __device__ __forceinline__ void desc_store_split_ns(const TabParams<double>& p, 
   for (int k = 0; k < NS; ++k) bias = bias * 256ull + 128ull;
   const double magic = 6755399441055744.0 + (double)bias;  // 2^52 + 2^51 + bias, exact
   signed char* __restrict__ base = reinterpret_cast<signed char*>(p.desc) + row * p.desc_ld;
-  const long long K = (long long)M * 16;
+  const long long K = p.desc_slice_stride;
 #pragma unroll
   for (int c = 0; c < NC; ++c) {
     const int k1 = lane + 32 * c;
@@ -649,6 +654,7 @@ __device__ __forceinline__ void desc_store_split(const TabParams<double>& p, con
   int e = ((__double2hiint(r2) >> 20) & 0x7ff) - 1023;
   e = __reduce_max_sync(kFull, e);
   int E = e + 2;  // |D| < 2^(E-1)
+  E = E < p.desc_min_exp ? p.desc_min_exp : E;
   E = E < -900 ? -900 : (E > 900 ? 900 : E);
   if (lane == 0) p.row_exp[row] = E;
   const int P = 7 + 8 * (ns - 1);  // fixed-point fraction bits
@@ -657,7 +663,7 @@ __device__ __forceinline__ void desc_store_split(const TabParams<double>& p, con
   unsigned long long bias = 0;
   for (int k = 0; k < ns; ++k) bias = bias * 256ull + 128ull;
   signed char* __restrict__ base = reinterpret_cast<signed char*>(p.desc) + row * p.desc_ld;
-  const long long K = (long long)M * 16;
+  const long long K = p.desc_slice_stride;
 #pragma unroll
   for (int c = 0; c < NC; ++c) {  // (unrolled: a runtime channel index would push acc[][] into local memory)
     const int k1 = lane + 32 * c;
@@ -1918,6 +1924,8 @@ struct DescArgs {
   int* row_exp;
   double scale;
   int mode, axis, nslice;
+  long long slice_stride = 0;  // 0: M * axis
+  int min_exp = -100000;
 };
 
 template <typename FP>
@@ -1946,7 +1954,7 @@ int launch_fwd(FP* out, const FP* table, const FP* info, const FP* em_x, long lo
   }
   if constexpr (!GG) if (da) {
     const bool plain = two == nullptr && nnei > 0;
-    DPB_REQUIRE(plain, "tabulate+descriptor: plain se_a forward with nnei > 0 only");
+    DPB_REQUIRE(plain, "tabulate+descriptor: se_a or pair-gated se_atten forward (no materialised two_embed), nnei > 0");
     DPB_REQUIRE(da->desc != nullptr && (da->mode == 1 || da->mode == 2 || (da->mode == 3 && sizeof(FP) == 4)),
                 "tabulate+descriptor: desc is null / bad mode (3 = int8 slices of an fp32 descriptor)");
     DPB_REQUIRE(M <= 128 && da->axis >= 1 && da->axis <= 32 && da->axis <= M,
@@ -1991,6 +1999,12 @@ int launch_fwd(FP* out, const FP* table, const FP* info, const FP* em_x, long lo
     p.desc_mode = da->mode;
     p.axis = da->axis;
     p.nslice = da->nslice;
+    p.desc_slice_stride = da->slice_stride > 0 ? da->slice_stride : (long long)M * da->axis;
+    p.desc_min_exp = da->min_exp;
+    DPB_REQUIRE(p.desc_slice_stride >= (long long)M * da->axis && p.desc_slice_stride % 16 == 0 &&
+                    (!((da->mode == 2 && sizeof(FP) == 8) || da->mode == 3) ||
+                     da->desc_ld >= da->nslice * p.desc_slice_stride),
+                "tabulate+descriptor: slice stride must be a multiple of 16, >= M*axis, and nslice strides fit a row");
   }
   if (GG) {
     DPB_REQUIRE(dz_x != nullptr && dz_em != nullptr, "tabulate grad_grad: dz_dy_dem_x / dz_dy_dem are null");
@@ -2063,7 +2077,11 @@ int launch_fwd(FP* out, const FP* table, const FP* info, const FP* em_x, long lo
   }
 #define DPB_LAUNCH_FWD(NC)                                                                      \
   do {                                                                                          \
-    if (da && cm) {                                                                             \
+    if (da && ga) {                                                                             \
+      auto kern = k_tab_fwd<FP, NC, true, false, true>;                                         \
+      e1 = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);  \
+      if (e1 == cudaSuccess) kern<<<grid, nw * 32, smem, st>>>(p);                              \
+    } else if (da && cm) {                                                                      \
       auto kern = k_tab_fwd<FP, NC, false, false, true, true>;                                  \
       e1 = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);  \
       if (e1 == cudaSuccess) kern<<<grid, nw * 32, smem, st>>>(p);                              \
@@ -2337,6 +2355,21 @@ extern "C" {
                                          (long long)nnei * 4, nullptr, nullptr, nullptr, nullptr,  \
                                          nloc, nnei, last_layer_size, is_sorted, 0,                \
                                          (cudaStream_t)stream, nullptr, flags, &ga);               \
+  }                                                                                                \
+  int dpb200_tabulate_fusion_se_atten_gate_desc_##SUF(                                             \
+      FP* out, const FP* table, const FP* table_info, const FP* em_x, const FP* em,                \
+      const FP* tt_full, const int* pair, const FP* sw, int nloc, int nnei, int last_layer_size,   \
+      int is_sorted, int axis, double scale, const int* desc_row, int desc_mode, void* desc,       \
+      long long desc_ld, long long slice_stride, int nslice, int* row_exp, int min_row_exp,        \
+      int flags, dpb200_stream_t stream) {                                                         \
+    dpb200::GateArgs<FP> ga = {tt_full, pair, sw, nullptr};                                        \
+    dpb200::DescArgs da = {desc, desc_ld, desc_row, row_exp, scale, desc_mode, axis, nslice,       \
+                           slice_stride, min_row_exp};                                             \
+    return dpb200::launch_fwd<FP, false>(out, table, table_info, em_x, nnei, 1, em,                \
+                                         (long long)nnei * 4, nullptr, nullptr, nullptr, nullptr,  \
+                                         nloc, nnei, last_layer_size, is_sorted, 0,                \
+                                         (cudaStream_t)stream, desc_mode == 0 ? nullptr : &da,     \
+                                         flags, &ga);                                              \
   }                                                                                                \
   int dpb200_tabulate_fusion_se_atten_gate_grad_##SUF(                                             \
       FP* dy_dem_x, FP* dy_dem, FP* dy_dsw, const FP* table, const FP* table_info,                 \

@@ -284,6 +284,46 @@ def tabulate_fusion_se_atten_gate(table, table_info, em_x, em, tt_full, pair, sw
     return out
 
 
+def tabulate_fusion_se_atten_gate_desc(table, table_info, em_x, em, tt_full, pair, sw, last_layer_size, axis, scale,
+                                       dim_in, nslice, min_row_exp, pad_rows=0, desc_row=None, is_sorted=True, flags=0):
+    """tabulate_fusion_se_atten_gate with the descriptor epilogue (fp64): returns (out [nloc, 4, M], desc int8
+    [nloc+pad, nslice*dim_in] whose first M*axis columns of every slice hold D = (scale out)^T (scale out)[:, :axis]
+    (the remaining dim_in - M*axis columns are zero, for the caller's own operand columns: fit_slice_cols), row_exp
+    int32 [nloc+pad] >= min_row_exp)."""
+    dev = _need_cuda(("table", table), ("em_x", em_x), ("em", em), ("tt_full", tt_full), ("pair", pair), ("sw", sw))
+    if table.dtype != torch.float64:
+        raise ValueError("dpb200: the gated descriptor epilogue is the fp64 form")
+    s = _suffix(table)
+    ti = _info_host(table_info, table.dtype)
+    table, em_x, em = _c(table), _c(em_x, table.dtype), _c(em, table.dtype)
+    tt_full, pair, sw = _c(tt_full, table.dtype), _c(pair, torch.int32), _c(sw, table.dtype)
+    nloc, nnei = em.shape[0], em.shape[1]
+    M = int(last_layer_size)
+    out = torch.empty((nloc, 4, M), dtype=table.dtype, device=dev)
+    rows = nloc + int(pad_rows)
+    desc = torch.zeros((rows, int(nslice) * int(dim_in)), dtype=torch.int8, device=dev)
+    row_exp = torch.zeros((rows,), dtype=torch.int32, device=dev)
+    if desc_row is not None:
+        desc_row = _c(desc_row, torch.int32)
+    lib().call("tabulate_fusion_se_atten_gate_desc_" + s, _p(out), _p(table), C.c_void_p(ti.data_ptr()), _p(em_x), _p(em),
+               _p(tt_full), _p(pair), _p(sw), nloc, nnei, M, int(bool(is_sorted)), int(axis), float(scale), _p(desc_row),
+               2, _p(desc), int(desc.shape[1]), int(dim_in), int(nslice), _p(row_exp), int(min_row_exp), int(flags),
+               _stream(dev))
+    return out, desc, row_exp
+
+
+def fit_slice_cols(desc, slice_stride, col0, nslice, row_exp, src, idx=None):
+    """Columns [col0, col0 + src.shape[1]) of every digit slice of desc[r] := digits of src[idx[r]] at row_exp[r]
+    (dpb200_fit_slice_cols_f64)."""
+    dev = _need_cuda(("desc", desc), ("row_exp", row_exp), ("src", src), ("idx", idx))
+    src = _c(src, torch.float64)
+    n = int(row_exp.numel()) if idx is None else int(idx.numel())
+    if idx is not None:
+        idx = _c(idx, torch.int32)
+    lib().call("fit_slice_cols_f64", _p(desc), int(desc.stride(0)), int(slice_stride), int(col0), int(src.shape[1]),
+               int(nslice), _p(row_exp), _p(src), int(src.stride(0)), _p(idx), n, _stream(dev))
+
+
 def tabulate_fusion_se_atten_gate_grad(table, table_info, em_x, em, tt_full, pair, sw, dy, last_layer_size,
                                        is_sorted=True, fuse_x=False, flags=0):
     """Backward of tabulate_fusion_se_atten_gate: (dy_dem_x [nloc*nnei, 1], dy_dem [nloc, nnei, 4], dy_dsw [nloc, nnei]).

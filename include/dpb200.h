@@ -140,6 +140,15 @@ DPB200_DECL_ENV(f32, float)
       FP* out, const FP* table, const FP* table_info, const FP* em_x, const FP* em,                \
       const FP* tt_full, const int* pair, const FP* sw, int nloc, int nnei, int last_layer_size,   \
       int is_sorted, int flags, dpb200_stream_t stream);                                           \
+  /* the gated forward with the descriptor epilogue of dpb200_tabulate_fusion_se_a_desc (same desc_mode values);  \
+   * slice_stride (0: M*axis) = elements between two digit slices of a row, min_row_exp = lower bound of the    \
+   * row exponent: the caller appends its own columns (centre type embedding) with dpb200_fit_slice_cols. */     \
+  int dpb200_tabulate_fusion_se_atten_gate_desc_##SUF(                                             \
+      FP* out, const FP* table, const FP* table_info, const FP* em_x, const FP* em,                \
+      const FP* tt_full, const int* pair, const FP* sw, int nloc, int nnei, int last_layer_size,   \
+      int is_sorted, int axis, double scale, const int* desc_row /*nullable*/, int desc_mode,      \
+      void* desc, long long desc_ld, long long slice_stride, int nslice, int* row_exp,             \
+      int min_row_exp, int flags, dpb200_stream_t stream);                                         \
   int dpb200_tabulate_fusion_se_atten_gate_grad_##SUF(                                             \
       FP* dy_dem_x /*nullable*/, FP* dy_dem, FP* dy_dsw, const FP* table, const FP* table_info,    \
       const FP* em_x, const FP* em, const FP* tt_full, const int* pair, const FP* sw,              \
@@ -429,6 +438,12 @@ DPB200_DECL_TAB_ND(f32, float)
  *  fit_head    : e[r] = y[r,:].w_head + b_head and the backward seed dz = w_head*idt*(1 - t^2) as slices.
  *  fit_blocked : row-major <-> blocked conversion (tests, callers that keep row-major activations).
  * ------------------------------------------------------------------------------------- */
+/* columns [col0, col0 + width) of every digit slice of row r := digits of src[idx[r] (NULL: r)][c] at the exponent
+ * row_exp[r] already chosen by the producer of the other columns (se_atten: the centre type embedding appended to
+ * the descriptor written by dpb200_tabulate_fusion_se_atten_gate_desc with min_row_exp bounding these values). */
+int dpb200_fit_slice_cols_f64(signed char* out, long long ld_out, long long slice_stride, int col0, int width,
+                              int nslice, const int* row_exp, const double* src, int src_ld,
+                              const int* idx /*nullable*/, long long nrow, dpb200_stream_t stream);
 int dpb200_fit_gemm_i8_f64(int mode, long long nrow, int N, int K, int nslice, const signed char* a_slices,
                            long long a_slice_stride, long long a_row_stride, const int* row_exp /*nullable*/,
                            int row_exp_fixed, const signed char* b_slices, int b_k_stride, const double* colv,
