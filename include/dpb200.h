@@ -134,13 +134,13 @@ DPB200_DECL_ENV(f32, float)
    * dy_dsw[i][j] = sum_k dy_dtwo[i][j][k] * tt_full[pair][k] instead of dy_dtwo.  Same results as the      \
    * reference-schema entry points above fed with the materialised tensor.  dy_dem_x may be NULL: em_x is  \
    * then component 0 of em and its gradient is added into dy_dem[..][0].  flags: 0 or the               \
-   * DPB200_TAB_COMPRESSED_COEF word of dpb200_tabulate_fusion_se_a_desc (caller-validated table).  fp64   \
+   * DPB200_TAB_COMPRESSED_COEF word of the se_a_desc entry point below (caller-validated table).  fp64  \
    * backward: FP64 tensor cores (three m8n8k4 products per step: G(1+t), G'(1+t), G tt). */             \
   int dpb200_tabulate_fusion_se_atten_gate_##SUF(                                                  \
       FP* out, const FP* table, const FP* table_info, const FP* em_x, const FP* em,                \
       const FP* tt_full, const int* pair, const FP* sw, int nloc, int nnei, int last_layer_size,   \
       int is_sorted, int flags, dpb200_stream_t stream);                                           \
-  /* the gated forward with the descriptor epilogue of dpb200_tabulate_fusion_se_a_desc (same desc_mode values);  \
+  /* the gated forward with the descriptor epilogue of the se_a_desc entry point (same desc_mode values);        \
    * slice_stride (0: M*axis) = elements between two digit slices of a row, min_row_exp = lower bound of the    \
    * row exponent: the caller appends its own columns (centre type embedding) with dpb200_fit_slice_cols. */     \
   int dpb200_tabulate_fusion_se_atten_gate_desc_##SUF(                                             \
