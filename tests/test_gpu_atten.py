@@ -112,3 +112,97 @@ def test_gate_op_equals_reference_schema_op(dtype):
         assert ((gem2 - want).abs().max() / want.abs().max()).item() <= t2
         assert ((gq2 - wq)[:, :100].abs().max() / wq.abs().max()).item() <= 10 * t2
         assert float(gq2[:, 101:].abs().max()) == 0.0  # behind the folded padding entry
+
+
+@pytest.mark.parametrize("dtype", [torch.float64, torch.float32])
+def test_gate_scalars_and_pair_force_match_torch(dtype):
+    """dpb200_se_atten_gate_scalars against the torch expressions of SeAttenModel.gate_scalars (se_atten.py:916-926,
+    switcher.h:61-84), and dpb200_prod_force_virial_a_pair against prod_force_virial_a + the explicit scatter of
+    -(q w) r_ij (force on the neighbour, opposite on the centre, virial and atomic virial)."""
+    pkg = g.load_package()
+    ops = pkg.ops
+    from deepmd_kit_b200.atten import SeAttenConfig, SeAttenModel, switch_and_derivative
+
+    dev = "cuda:0"
+    torch.manual_seed(11)
+    cfg = SeAttenConfig()
+    nloc, nall, nnei, nt = 257, 400, cfg.nnei, cfg.ntypes
+    nlist = torch.randint(0, nall, (nloc, nnei), dtype=torch.int32, device=dev)
+    nlist[:, 90:] = -1
+    nlist[5] = -1
+    ext_type = torch.randint(0, nt, (nall,), dtype=torch.int32, device=dev)
+    ext_type[7] = -1  # virtual atom: padding type
+    rij = torch.randn(nloc, nnei, 3, dtype=dtype, device=dev) * 2.5
+    rij[3, 0] = 0.0   # r = 0: inside rcut_smth, no switch force
+    rij[4, 1] = torch.tensor([cfg.rcut + 1.0, 0.0, 0.0], dtype=dtype, device=dev)  # beyond rcut
+    pair, sw, dswr = ops.se_atten_gate_scalars(nlist, ext_type, rij.reshape(nloc, -1), nloc, nnei, nt, cfg.rcut_smth, cfg.rcut)
+    m = SeAttenModel.__new__(SeAttenModel)
+    m.cfg = cfg
+    wpair, wsw, wdsw, wr = SeAttenModel.gate_scalars(m, ext_type, nlist, rij.reshape(nloc, -1), 0, nloc)
+    assert torch.equal(pair.long(), wpair)
+    tol = 1e-13 if dtype == torch.float64 else 2e-6
+    assert (sw - wsw).abs().max().item() <= tol
+    wdswr = torch.where((wr > 0) & (nlist >= 0), wdsw / wr.clamp_min(1e-30), torch.zeros_like(wr))
+    assert (dswr - wdswr).abs().max().item() <= tol * max(1.0, wdswr.abs().max().item())
+    # pair force
+    nd = torch.randn(nloc, nnei * 4, dtype=dtype, device=dev)
+    dv = torch.randn(nloc, nnei * 12, dtype=dtype, device=dev)
+    q = torch.randn(nloc, nnei, dtype=dtype, device=dev)
+    f0, v0, a0 = ops.prod_force_virial_a(nd, dv, rij.reshape(nloc, -1), nlist, nloc, nall, nnei, atom_virial=True)
+    f1, v1, a1 = ops.prod_force_virial_a_pair(nd, dv, rij.reshape(nloc, -1), nlist, q, dswr, nloc, nall, nnei,
+                                              atom_virial=True)
+    vec = (q * dswr).unsqueeze(-1) * rij  # dE/dr_j of the switch path
+    vec = torch.where((nlist >= 0).unsqueeze(-1), vec, torch.zeros_like(vec))
+    idx = nlist.clamp_min(0).long().reshape(-1)
+    want_f = f0.reshape(-1, 3).clone()
+    want_f.index_add_(0, idx, -vec.reshape(-1, 3))
+    want_f[:nloc] += vec.sum(1)
+    want_v = v0 - torch.einsum("pi,pj->ij", vec.reshape(-1, 3), rij.reshape(-1, 3)).reshape(9)
+    want_a = a0.reshape(-1, 9).clone()
+    want_a.index_add_(0, idx, -(vec.reshape(-1, 3, 1) * rij.reshape(-1, 1, 3)).reshape(-1, 9))
+    ftol = 1e-12 if dtype == torch.float64 else 3e-5
+    assert ((f1.reshape(-1, 3) - want_f).abs().max() / want_f.abs().max()).item() <= ftol
+    assert ((v1 - want_v).abs().max() / want_v.abs().max()).item() <= ftol
+    assert ((a1.reshape(-1, 9) - want_a).abs().max() / want_a.abs().max()).item() <= ftol
+
+
+def test_gate_desc_epilogue_and_slice_cols():
+    """The gated forward with the descriptor epilogue: same table output as the plain gated forward; the int8 operand
+    rows reproduce [D | tebd(centre) | 0] to 2^-44 of 2^row_exp with row_exp >= the requested lower bound."""
+    pkg = g.load_package()
+    ops = pkg.ops
+    from deepmd_kit_b200.atten import SeAttenConfig, SeAttenModel
+
+    dev = "cuda:0"
+    torch.manual_seed(5)
+    dtype = torch.float64
+    m = SeAttenModel(SeAttenConfig(), dtype, dev)
+    cfg = m.cfg
+    nloc, nnei, M = 130, cfg.nnei, m.M
+    em = torch.randn(nloc, nnei, 4, dtype=dtype, device=dev) * 0.3
+    em[:, :, 0] = torch.sort(torch.rand(nloc, nnei, dtype=dtype, device=dev) * 5 - 0.3, dim=1, descending=True)[0]
+    em[:, 100:, :] = torch.tensor([-0.36, 0.0, 0.0, 0.0], dtype=dtype, device=dev)
+    em[9] *= 1e-6  # a tiny row: its exponent is set by the lower bound
+    em_x = em[:, :, 0].reshape(-1, 1).contiguous()
+    pair = torch.randint(0, 9, (nloc, nnei), dtype=torch.int32, device=dev)
+    sw = torch.rand(nloc, nnei, dtype=dtype, device=dev)
+    sw[:, 100:] = 0
+    want = ops.tabulate_fusion_se_atten_gate(m.table, m.info, em_x, em, m.tt_full, pair, sw, M)
+    inv = 1.0 / nnei
+    out, desc, ex = ops.tabulate_fusion_se_atten_gate_desc(m.table, m.info, em_x, em, m.tt_full, pair, sw, M,
+                                                           cfg.axis_neuron, inv, m.dim_in, 6, m.tebd_exp, pad_rows=32)
+    assert torch.equal(out, want)
+    assert desc.shape == (nloc + 32, 6 * m.dim_in) and int(desc[nloc:].abs().sum()) == 0
+    assert int(ex[:nloc].min()) >= m.tebd_exp
+    ctype = torch.randint(0, cfg.ntypes + 1, (nloc,), dtype=torch.int32, device=dev)
+    ops.fit_slice_cols(desc, m.dim_in, m.dim_d, 6, ex, m.tebd, idx=ctype)
+    sl = desc[:nloc].reshape(nloc, 6, m.dim_in).to(torch.float64)
+    assert int(sl.abs().max()) <= 128
+    w = torch.tensor([2.0 ** (-7 - 8 * s) for s in range(6)], dtype=torch.float64, device=dev)
+    scale = torch.ldexp(torch.ones(nloc, dtype=torch.float64, device=dev), ex[:nloc])
+    rec = (sl * w[None, :, None]).sum(1) * scale[:, None]
+    d = ops.se_a_descriptor(want, cfg.axis_neuron, inv)
+    full = torch.zeros(nloc, m.dim_in, dtype=torch.float64, device=dev)
+    full[:, :m.dim_d] = d
+    full[:, m.dim_d:m.dim_d + cfg.tebd_dim] = m.tebd[ctype.long()]
+    assert ((rec - full).abs() / scale[:, None]).max().item() <= 2.0 ** -44
