@@ -209,11 +209,12 @@ class SeAttenModel:
                 # GEMM; the centre type embedding is appended behind it at the same row exponent
                 xyz, desc, row_exp = ops.tabulate_fusion_se_atten_gate_desc(
                     self.table, self.info, em_x, em3, self.tt_full, pair32, sw, M, cfg.axis_neuron, inv, self.dim_in,
-                    self.nslice, self.tebd_exp, pad_rows=32)
+                    self.nslice, self.tebd_exp, pad_rows=32, flags=self.coef_flags)
                 ops.fit_slice_cols(desc, self.dim_in, self.dim_d, self.nslice, row_exp, self.tebd,
                                    idx=ctype_e.to(torch.int32))
             else:
-                xyz = ops.tabulate_fusion_se_atten_gate(self.table, self.info, em_x, em3, self.tt_full, pair32, sw, M)
+                xyz = ops.tabulate_fusion_se_atten_gate(self.table, self.info, em_x, em3, self.tt_full, pair32, sw, M,
+                                                        flags=self.coef_flags)
         else:
             xyz = torch.empty((nloc, 4, M), dtype=self.dtype, device=em.device)
             for a in range(0, nloc, self.tab_chunk):
@@ -228,7 +229,7 @@ class SeAttenModel:
         for c0 in range(0, nloc, self.fit_chunk):
             c1 = min(nloc, c0 + self.fit_chunk)
             if desc is not None:
-                e, gd = self.fit.forward_backward_tc(desc[c0:c1], row_exp[c0:c1], c1 - c0)
+                e, gd = self.fit.forward_backward_tc(desc[c0:c1], row_exp[c0:c1], c1 - c0, grad_cols=self.dim_d)
             else:
                 g1 = torch.zeros((c1 - c0, self.dim_in), dtype=self.dtype, device=em.device)
                 g1[:, :self.dim_d] = ops.se_a_descriptor(xyz[c0:c1], cfg.axis_neuron, inv)

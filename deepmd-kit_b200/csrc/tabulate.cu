@@ -909,7 +909,12 @@ __global__ void __launch_bounds__(512) k_tab_fwd(const __grid_constant__ TabPara
       }
       auto fetch = [&](int row) {
         cur_row = row;
-        fetch_row<FP, NC>(a, hot, p.T, row, r0, p.H, p.M, ob);
+        if (CM && sizeof(FP) == 4)
+          fetch_row_c32<NC>(a, hot, p.T, row, r0, p.H, p.M, ob);
+        else if (CM)
+          fetch_row_cmf(a, af, hot, p.T, row, r0, p.H, p.M, ob, p.a5_inv);
+        else
+          fetch_row<FP, NC>(a, hot, p.T, row, r0, p.H, p.M, ob);
       };
       if (nproc > 0 && rec[0].idx != cur_row) fetch(rec[0].idx);  // warp-uniform
 #pragma unroll 2
@@ -917,13 +922,14 @@ __global__ void __launch_bounds__(512) k_tab_fwd(const __grid_constant__ TabPara
         const Rec<FP>& r = rec[jj];
         const int row_n = rec[jj + 1 < nproc ? jj + 1 : jj].idx;
         const FP xx = r.xx;
+        const float xf = (float)xx;
         const FP gs = r.delta;
         const FP* __restrict__ trow = p.gate_tt + (long long)r.mult * p.M;
         const FP e0 = r.e[0], e1 = r.e[1], e2 = r.e[2], e3 = r.e[3];
         FP g[NC];
 #pragma unroll
         for (int c = 0; c < NC; ++c) {
-          const FP v = poly(a[c], xx);
+          const FP v = (CM && sizeof(FP) == 4) ? poly3(a[c], xx) : (CM ? poly_cm(a[c], af[CM ? c : 0], xx, xf) : poly(a[c], xx));
           g[c] = v * (__ldg(trow + kc[c]) * gs) + v;
         }
         if (row_n != cur_row) fetch(row_n);  // warp-uniform
@@ -1947,6 +1953,8 @@ int launch_fwd(FP* out, const FP* table, const FP* info, const FP* em_x, long lo
   DPB_REQUIRE(!ga || (!GG && two == nullptr && ga->tt && ga->pair && ga->sw), "tabulate gate: bad arguments");
   // compressed coefficients in the SIMT forward: a3..a5 stay fp32 in the row cache and the top two Horner steps
   // run on the FP32 pipe (widening them to fp64 at fetch time instead was measured 8 % SLOWER than the full table)
+  // (not with the pair-indexed gate: the gated loop with fp32 coefficient registers measured 17.1 -> 21.4 ms at
+  //  526 848 atoms -- the extra live values push the kernel over its register budget)
   const bool cm = (flags & DPB200_TAB_COMPRESSED_COEF) && !GG && two == nullptr && !ga && !use_mma_fwd() && fwd_cm_enabled();
   if (GG && da) {
     set_error("tabulate+descriptor: plain se_a forward only");

@@ -204,10 +204,12 @@ class FittingNet:
         return True
 
     @torch.no_grad()
-    def forward_backward_tc(self, xs: torch.Tensor, row_exp: torch.Tensor, n: int):
+    def forward_backward_tc(self, xs: torch.Tensor, row_exp: torch.Tensor, n: int, grad_cols: Optional[int] = None):
         """forward_backward on the pre-split descriptor rows with every GEMM on the int8 tensor cores
         (csrc/fit_tc.cu): per layer ONE kernel does the split product, the recombination and the layer's
-        elementwise chain; the activations travel between layers as int8 slices.  Returns (e [n], dE/dD [n, K0])."""
+        elementwise chain; the activations travel between layers as int8 slices.  Returns (e [n], dE/dD [n, K0]);
+        grad_cols (a multiple of 16): only the first grad_cols input columns of the gradient are formed (se_atten: the
+        descriptor part of [D | type embedding])."""
         tc = self.tc
         ns = tc["nslice"]
         dev = xs.device
@@ -248,9 +250,15 @@ class FittingNet:
             kp = (n_in + 15) // 16 * 16
             dz, dz_exp = ops.fit_slice_rows(dzn, n, n_in, kp, ns)
         bsl, cs, Kp = tc["bw"][0]
-        gd = torch.empty((n, K0), dtype=self.dtype, device=dev)
-        ops.fit_gemm_i8(2 if self.dtype == torch.float64 else 3, n, K0, kp, dz, kp, ns * kp, dz_exp, 0, bsl, Kp, cs,
-                        out0=gd, ld_out=K0, nslice=ns)
+        ng = K0 if grad_cols is None else int(grad_cols)
+        if ng != K0:  # the weight rows of the wanted input columns as their own operand (slice stride = ng rows)
+            key = ("bw0", ng)
+            if key not in tc:
+                tc[key] = (bsl[:, :ng, :].contiguous(), cs[:ng].contiguous(), Kp)
+            bsl, cs, Kp = tc[key]
+        gd = torch.empty((n, ng), dtype=self.dtype, device=dev)
+        ops.fit_gemm_i8(2 if self.dtype == torch.float64 else 3, n, ng, kp, dz, kp, ns * kp, dz_exp, 0, bsl, Kp, cs,
+                        out0=gd, ld_out=ng, nslice=ns)
         return e.to(self.dtype), gd
 
     def to(self, device, dtype):

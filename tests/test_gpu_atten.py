@@ -109,6 +109,8 @@ def test_gate_op_equals_reference_schema_op(dtype):
                                                                    fuse_x=True, flags=fl)
         t2 = tol if fl == 0 else 1e-11
         assert none_x is None
+        a2 = ops.tabulate_fusion_se_atten_gate(m.table, m.info, em_x, em, m.tt_full, pair, sw, M, flags=fl)
+        assert ((a2 - b).abs().max() / b.abs().max()).item() <= t2
         assert ((gem2 - want).abs().max() / want.abs().max()).item() <= t2
         assert ((gq2 - wq)[:, :100].abs().max() / wq.abs().max()).item() <= 10 * t2
         assert float(gq2[:, 101:].abs().max()) == 0.0  # behind the folded padding entry
@@ -192,6 +194,11 @@ def test_gate_desc_epilogue_and_slice_cols():
     out, desc, ex = ops.tabulate_fusion_se_atten_gate_desc(m.table, m.info, em_x, em, m.tt_full, pair, sw, M,
                                                            cfg.axis_neuron, inv, m.dim_in, 6, m.tebd_exp, pad_rows=32)
     assert torch.equal(out, want)
+    out_c, desc_c, ex_c = ops.tabulate_fusion_se_atten_gate_desc(m.table, m.info, em_x, em, m.tt_full, pair, sw, M,
+                                                                 cfg.axis_neuron, inv, m.dim_in, 6, m.tebd_exp,
+                                                                 pad_rows=32, flags=m.coef_flags)
+    assert m.coef_flags != 0 and ((out_c - want).abs().max() / want.abs().max()).item() <= 1e-11  # (flag ignored)
+    assert (ex_c - ex).abs().max().item() <= 1
     assert desc.shape == (nloc + 32, 6 * m.dim_in) and int(desc[nloc:].abs().sum()) == 0
     assert int(ex[:nloc].min()) >= m.tebd_exp
     ctype = torch.randint(0, cfg.ntypes + 1, (nloc,), dtype=torch.int32, device=dev)
