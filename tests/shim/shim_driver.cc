@@ -162,8 +162,60 @@ static int nlist_mode(const char* in, const char* out) {
   return 0;
 }
 
+// Third mode (`shim_driver tabnd in out`): tabulate_fusion_se_a{,_grad,_grad_grad}_gpu with ndescrpt = 9 / 16 / 25
+// through the reference's own C++ signatures (source/lib/include/tabulate.h:175-218, the trailing `ndescrpt`).
+static int tabnd_mode(const char* in, const char* out) {
+  FILE* fi = fopen(in, "rb");
+  FILE* fo = fopen(out, "wb");
+  if (!fi || !fo) return 1;
+  auto hd = rd<int>(fi, 6);  // nloc nnei M nd nspline is_sorted
+  const int nloc = hd[0], nnei = hd[1], M = hd[2], nd = hd[3], nspline = hd[4];
+  const bool is_sorted = hd[5] != 0;
+  auto table = rd<double>(fi, (size_t)nspline * M * 6);
+  auto info = rd<double>(fi, 6);
+  auto em_x = rd<double>(fi, (size_t)nloc * nnei);
+  auto em = rd<double>(fi, (size_t)nloc * nnei * nd);
+  auto dy = rd<double>(fi, (size_t)nloc * nd * M);
+  auto dzx = rd<double>(fi, (size_t)nloc * nnei);
+  auto dzem = rd<double>(fi, (size_t)nloc * nnei * nd);
+  double *d_table = up(table), *d_x = up(em_x), *d_em = up(em), *d_dy = up(dy), *d_dzx = up(dzx), *d_dzem = up(dzem);
+  double *desc, *gx, *gem, *gg;
+  CK(cudaMalloc((void**)&desc, sizeof(double) * nloc * nd * M));
+  CK(cudaMalloc((void**)&gx, sizeof(double) * nloc * nnei));
+  CK(cudaMalloc((void**)&gem, sizeof(double) * nloc * nnei * nd));
+  CK(cudaMalloc((void**)&gg, sizeof(double) * nloc * nd * M));
+  try {
+    deepmd::tabulate_fusion_se_a_gpu<double>(desc, d_table, info.data(), d_x, d_em, nullptr, nloc, nnei, M, is_sorted, nd);
+    deepmd::tabulate_fusion_se_a_grad_gpu<double>(gx, gem, nullptr, d_table, info.data(), d_x, d_em, nullptr, d_dy, nloc,
+                                                  nnei, M, is_sorted, nd);
+    deepmd::tabulate_fusion_se_a_grad_grad_gpu<double>(gg, d_table, info.data(), d_x, d_em, nullptr, d_dzx, d_dzem,
+                                                       nullptr, nloc, nnei, M, is_sorted, nd);
+    bool refused = false;
+    try {  // 5 is not a supported basis dimension
+      deepmd::tabulate_fusion_se_a_gpu<double>(desc, d_table, info.data(), d_x, d_em, nullptr, 0, nnei, M, is_sorted, 5);
+    } catch (const std::exception&) {
+      refused = true;
+    }
+    if (!refused) {
+      fprintf(stderr, "ndescrpt = 5 was not refused\n");
+      return 5;
+    }
+  } catch (const std::exception& e) {
+    fprintf(stderr, "exception: %s\n", e.what());
+    return 4;
+  }
+  down(fo, desc, (size_t)nloc * nd * M);
+  down(fo, gx, (size_t)nloc * nnei);
+  down(fo, gem, (size_t)nloc * nnei * nd);
+  down(fo, gg, (size_t)nloc * nd * M);
+  fclose(fo);
+  printf("SHIM_DRIVER_OK\n");
+  return 0;
+}
+
 int main(int argc, char** argv) {
   if (argc >= 4 && std::string(argv[1]) == "nlist") return nlist_mode(argv[2], argv[3]);
+  if (argc >= 4 && std::string(argv[1]) == "tabnd") return tabnd_mode(argv[2], argv[3]);
   if (argc < 3) return 1;
   FILE* fi = fopen(argv[1], "rb");
   FILE* fo = fopen(argv[2], "wb");

@@ -106,6 +106,52 @@ def test_shim_driver_matches_oracle(olib, tmp_path):
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("nd", [9, 16, 25])
+def test_shim_tabulate_higher_basis(olib, tmp_path, nd):
+    """deepmd::tabulate_fusion_se_a{,_grad,_grad_grad}_gpu with the trailing ndescrpt argument (tabulate.h:175-218),
+    called from C++ exactly as source/op/pt/tabulate_multi_device.cc:101-117 does with ndescrpt = em.size(2); an
+    unsupported basis dimension must throw as the reference's check_se_a_basis_dimension does."""
+    if not os.path.exists(DRIVER):
+        pytest.skip("tests/shim/_build/shim_driver not built (needs the reference headers)")
+    rng = np.random.default_rng(40 + nd)
+    nloc, nnei, M = 17, 29, 40
+    info = np.array([-0.4, 2.0, 6.0, 0.05, 0.5, -1.0])
+    nspline = int((info[1] - info[0]) / info[3]) + int((info[2] - info[1]) / info[4]) + 1
+    table = random_table(nspline, M, rng)
+    em_x = np.sort(rng.uniform(-0.8, 7.5, size=(nloc, nnei)), axis=1)[:, ::-1].copy()
+    em = rng.normal(size=(nloc, nnei, nd))
+    for i in range(nloc):  # trailing padding: constant em_x, zero angular part
+        k = int(rng.integers(0, 6))
+        if k:
+            em_x[i, nnei - k:] = -0.37
+            em[i, nnei - k:, 1:] = 0
+    em[:, :, 0] = em_x
+    dy = rng.normal(size=(nloc, nd, M))
+    dzx = rng.normal(size=(nloc, nnei))
+    dzem = rng.normal(size=(nloc, nnei, nd))
+    fin, fout = tmp_path / "in.bin", tmp_path / "out.bin"
+    with open(fin, "wb") as f:
+        np.array([nloc, nnei, M, nd, nspline, 1], np.int32).tofile(f)
+        for a in (table, info, em_x, em, dy, dzx, dzem):
+            np.ascontiguousarray(a, dtype=np.float64).tofile(f)
+    r = subprocess.run([DRIVER, "tabnd", str(fin), str(fout)], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0 and "SHIM_DRIVER_OK" in r.stdout, r.stderr[-2000:]
+    raw = np.fromfile(fout, dtype=np.float64)
+    n1, n2, n3 = nloc * nd * M, nloc * nnei, nloc * nnei * nd
+    desc, gx, gem, gg = raw[:n1], raw[n1:n1 + n2], raw[n1 + n2:n1 + n2 + n3], raw[n1 + n2 + n3:]
+    ex = em_x.reshape(-1, 1)
+
+    def close(a, b, tol=1e-10):
+        b = np.asarray(b).reshape(-1)
+        assert a.shape == b.shape and np.abs(a - b).max() <= tol * max(np.abs(b).max(), 1e-300)
+
+    close(desc, olib.tabulate_fusion_se_a(table, info, ex, em, M))
+    wx, wem, _ = olib.tabulate_fusion_se_a_grad(table, info, ex, em, dy, M)
+    close(gx, wx)
+    close(gem, wem)
+    close(gg, olib.tabulate_fusion_se_a_grad_grad(table, info, ex, em, dzx.reshape(-1, 1), dzem, M))
+
+
 def test_shim_neighbour_front_end(olib, tmp_path):
     """normalize_coord_gpu / copy_coord_gpu / build_nlist_gpu driven as _norm_copy_coord_gpu and _build_nlist_gpu of
     source/op/tf/prod_env_mat_multi_device.cc:2399-2600 drive them: Region and cell_info in DEVICE memory, rows
