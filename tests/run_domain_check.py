@@ -75,7 +75,12 @@ def main():
 
     ncopy = int(os.environ.get("DPB_NCOPY", "2"))
     dtype = torch.float64
-    model = SeAModel(SeAConfig(), dtype, dev)
+    if os.environ.get("DPB_MODEL", "se_a") == "se_atten":  # config 5: DPA-1 strip mode with the pair-indexed gate
+        from deepmd_kit_b200.atten import SeAttenConfig, SeAttenModel
+
+        model = SeAttenModel(SeAttenConfig(), dtype, dev)
+    else:
+        model = SeAModel(SeAConfig(), dtype, dev)
     grid = proc_grid(world)
     dp = DomainDeepPot(model, grid, skin=2.0, nlist_every=10)
     coord, atype, box = dp.make_local_water(g.water_box, ncopy, 0.01)

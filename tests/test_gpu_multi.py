@@ -20,16 +20,21 @@ def _free_port():
 
 
 @pytest.mark.parametrize("world", [2, 4, 8])
-def test_domain_decomposition_matches_single_gpu(world):
+@pytest.mark.parametrize("model", ["se_a", "se_atten"])
+def test_domain_decomposition_matches_single_gpu(world, model):
     if torch.cuda.device_count() < world:
         pytest.skip(f"needs {world} GPUs")
+    if model == "se_atten" and world == 4:
+        pytest.skip("se_atten is checked at 2 and 8 ranks")
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}",
            "--master-addr", "127.0.0.1", "--master-port", str(_free_port()),
            os.path.join(ROOT, "tests", "run_domain_check.py")]
-    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=ROOT)
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=ROOT,
+                       env=dict(os.environ, DPB_MODEL=model))
     sys.stdout.write(r.stdout[-3000:])
     sys.stderr.write(r.stderr[-3000:])
     os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
-    with open(os.path.join(ROOT, "gpurun_out", f"domain_check_{world}.log"), "w") as f:
+    tag = "" if model == "se_a" else "_" + model
+    with open(os.path.join(ROOT, "gpurun_out", f"domain_check{tag}_{world}.log"), "w") as f:
         f.write(r.stdout + "\n=== stderr ===\n" + r.stderr)
     assert r.returncode == 0 and "DOMAIN_CHECK_OK" in r.stdout
