@@ -150,8 +150,8 @@ class SeAttenModel:
         self.coef_flags = 0
         if self.device.type == "cuda" and dtype == torch.float64 and os.environ.get("DPB200_TAB_COMPRESS", "1") != "0":
             self.coef_flags = int(ops.compressed_coef_flags(self.table64, self.info))
-        self.nslice = 6
-        self.use_tc = bool(dtype == torch.float64 and self.device.type == "cuda" and self.fit.prepare_tc(self.nslice))
+        self.nslice = 6 if dtype == torch.float64 else 4  # int8 digit slices of the fitting-net operands
+        self.use_tc = bool(self.device.type == "cuda" and self.fit.prepare_tc(self.nslice))
         # lower bound of the descriptor rows' exponent so that the appended type embedding fits: |tebd| < 2^(E-1)
         self.tebd_exp = int(math.floor(math.log2(max(float(self.tebd.abs().max()), 1e-300)))) + 2
 
@@ -204,7 +204,7 @@ class SeAttenModel:
             pair32, sw, dswr = ops.se_atten_gate_scalars(nlist, ext_type, rij, nloc, nnei, cfg.ntypes, cfg.rcut_smth,
                                                          cfg.rcut)
             em_x = em3[:, :, 0].reshape(-1, 1).contiguous()
-            if self.use_tc:
+            if self.use_tc and self.dtype == torch.float64:
                 # the warp that finishes an atom writes its descriptor straight as the int8 operand of the first fitting
                 # GEMM; the centre type embedding is appended behind it at the same row exponent
                 xyz, desc, row_exp = ops.tabulate_fusion_se_atten_gate_desc(
@@ -235,8 +235,8 @@ class SeAttenModel:
                 g1[:, :self.dim_d] = ops.se_a_descriptor(xyz[c0:c1], cfg.axis_neuron, inv)
                 g1[:, self.dim_d:self.dim_d + cfg.tebd_dim] = self.tebd.index_select(0, ctype_e[c0:c1])
                 if self.use_tc:
-                    xs, ex = ops.split_i8_rows(g1, self.nslice)
-                    e, gd = self.fit.forward_backward_tc(xs, ex, c1 - c0)
+                    xs, ex = ops.split_i8_rows(g1.to(torch.float64), self.nslice)
+                    e, gd = self.fit.forward_backward_tc(xs, ex, c1 - c0, grad_cols=self.dim_d)
                 else:
                     e, gd = self.fit.forward_backward(g1)
                 del g1

@@ -48,6 +48,29 @@ def test_se_atten_e2e_matches_cpu_pipeline(ncopy, jitter, use_gate):
     assert rel(f2[0], f[0]) <= 1e-12
 
 
+def test_se_atten_e2e_fp32_against_fp64_checker():
+    """fp32 model (fitting net on the four-slice int8 tensor-core kernels).  The fp32 CPU pipeline is NOT a usable
+    yardstick here: it differs from its own fp64 evaluation by 1.8e-4 on the forces (single-precision cancellation in
+    the autograd switch path and in prod_force), ten times more than the GPU path does.  So the fp32 GPU result is held
+    against the fp64 checker at single-precision level: measured 1.8e-5 (force), 1e-6 (virial), < 1e-7 (energy)."""
+    g.load_package()
+    from deepmd_kit_b200.atten import SeAttenConfig, SeAttenModel
+    from deepmd_kit_b200.model import DeepPotB200
+
+    cfg = SeAttenConfig()
+    coord, atype, box = g.water_box(2, 0.01)
+    model = SeAttenModel(cfg, torch.float32, "cuda:0")
+    assert model.use_tc and model.nslice == 4
+    dp = DeepPotB200(model, skin=2.0)
+    e, f, v = dp.eval(coord.reshape(1, -1), box.reshape(1, 9), atype)
+    lib = ocpu.CpuLib("reference" if ocpu.available("reference") else "port")
+    lists = pipeline.build_lists(lib, coord, atype, box, cfg.rcut + 2.0)
+    we, wf, wv, ex = pipeline_atten.evaluate(lib, SeAttenModel(cfg, torch.float64, "cpu"), lists)
+    assert abs(e[0, 0] - we) <= 1e-6 * abs(we)
+    assert rel(f[0], wf) <= 5e-5
+    assert rel(v[0], wv) <= 1e-5
+
+
 def test_se_atten_force_is_energy_gradient():
     g.load_package()
     from deepmd_kit_b200.atten import SeAttenConfig, SeAttenModel
