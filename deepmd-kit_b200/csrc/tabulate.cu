@@ -763,8 +763,16 @@ extern __shared__ __align__(16) unsigned char tab_smem[];
 // grid (x: persistent over atoms, y: block of 32*NC channels); block = nw warps.
 // smem: hot[H][3][M] pairs | Rec[nw][32] | RecGG[nw][32] (GG only)
 // ------------------------------------------------------------------------------------------
+// Threads per CTA: the fp64 kernels with the descriptor epilogue run 12 warps with up to 168 registers (no spills;
+// measured 6.28 -> 6.11 ms at 332 k atoms), everything else 16 warps at 128 registers (12 warps cost the plain fp64
+// and the fp32 forward 8-10 %).
+template <typename FP, bool DESC>
+constexpr int fwd_threads() {
+  return (sizeof(FP) == 8 && DESC) ? 384 : 512;
+}
+
 template <typename FP, int NC, bool TWO, bool GG, bool DESC = false, bool CM = false>
-__global__ void __launch_bounds__(512) k_tab_fwd(const __grid_constant__ TabParams<FP> p) {
+__global__ void __launch_bounds__(fwd_threads<FP, DESC>()) k_tab_fwd(const __grid_constant__ TabParams<FP> p) {
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
   const int nw = blockDim.x >> 5;
@@ -2020,7 +2028,7 @@ int launch_fwd(FP* out, const FP* table, const FP* info, const FP* em_x, long lo
     DPB_REQUIRE(two == nullptr || dz_two != nullptr, "tabulate grad_grad: dz_dy_dtwo is null");
   }
   const int nc = M <= 32 ? 1 : (M <= 64 ? 2 : 4);
-  const int nw = 16;
+  const int nw = (da ? fwd_threads<FP, true>() : fwd_threads<FP, false>()) / 32;
   // se_atten: per-warp cp.async ring for two_embed rows (needs 16-byte aligned rows)
   const bool ring = !GG && two != nullptr && ((size_t)M * sizeof(FP)) % 16 == 0 && aligned16(two) && M <= 128;
   p.two_ring = ring ? 1 : 0;
