@@ -43,6 +43,10 @@ constexpr int kTileM = 128;
 constexpr int kChunkK = 64;   // bytes of K per operand unit = one SWIZZLE_64B row
 constexpr int kStages = 5;    // operand ring of HALF chunks: slices [0, NS/2) or [NS/2, NS) of one K-chunk
 constexpr int kEpiWarps = 20; // 5 column groups of 16 x 4 TMEM lane quadrants
+#ifndef DPB_EPI_BATCH
+#define DPB_EPI_BATCH 8
+#endif
+constexpr int kEpiBatch = DPB_EPI_BATCH;  // columns whose fp64 inputs are fetched together in the epilogue
 constexpr int kThreads = 32 * (2 + kEpiWarps);
 
 enum { EPI_FWD = 0, EPI_BWD = 1, EPI_PLAIN = 2 };
@@ -551,12 +555,12 @@ __global__ void __launch_bounds__(kThreads, 1)
         double* __restrict__ o0 = p.out0 + boff;
         double* __restrict__ o1 = p.out1 + boff;
 #pragma unroll
-        for (int h = 0; h < 16; h += 8) {
-          double xin[8];
+        for (int h = 0; h < 16; h += kEpiBatch) {
+          double xin[kEpiBatch];
 #pragma unroll
-          for (int j = 0; j < 8; ++j) xin[j] = sk ? __ldcs(sk + (h + j) * kTileM) : 0.;
+          for (int j = 0; j < kEpiBatch; ++j) xin[j] = sk ? __ldcs(sk + (h + j) * kTileM) : 0.;
 #pragma unroll
-          for (int j = 0; j < 8; ++j) {
+          for (int j = 0; j < kEpiBatch; ++j) {
             const double2 c01 = *reinterpret_cast<const double2*>(cvs + 4 * (h + j));
             const double2 c23 = *reinterpret_cast<const double2*>(cvs + 4 * (h + j) + 2);
             const double4 c4 = make_double4(c01.x, c01.y, c23.x, c23.y);
@@ -577,15 +581,15 @@ __global__ void __launch_bounds__(kThreads, 1)
         double* __restrict__ o0 = p.out0 ? p.out0 + boff : nullptr;
         double* __restrict__ o1 = p.out1 + boff;
 #pragma unroll
-        for (int h = 0; h < 16; h += 8) {
-          double xin[8], tin[8];
+        for (int h = 0; h < 16; h += kEpiBatch) {
+          double xin[kEpiBatch], tin[kEpiBatch];
 #pragma unroll
-          for (int j = 0; j < 8; ++j) {
+          for (int j = 0; j < kEpiBatch; ++j) {
             xin[j] = sk ? __ldcs(sk + (h + j) * kTileM) : 0.;
             tin[j] = __ldcs(ti + (h + j) * kTileM);
           }
 #pragma unroll
-          for (int j = 0; j < 8; ++j) {
+          for (int j = 0; j < kEpiBatch; ++j) {
             const double2 c01 = *reinterpret_cast<const double2*>(cvs + 4 * (h + j));
             const double2 c23 = *reinterpret_cast<const double2*>(cvs + 4 * (h + j) + 2);
             const double4 c4 = make_double4(c01.x, c01.y, c23.x, c23.y);
