@@ -1439,7 +1439,10 @@ __host__ __device__ constexpr int grad_mma_tile_ld(int kt) { return (4 * kt + 11
 // coefficient fetches of rows outside the hot window, so warps in flight are what it needs.
 // GATE: se_atten with the pair-indexed gate (two_embed = tt_full[pair] * sw, never materialised): G and G' are
 // scaled by 1 + t, and dE/d(sw) = sum_m e[m] (g tt . dy^T)[m] comes from a third product with A = g * tt.
-template <int KT, bool BSM, int MAXT, bool CM = false, bool GATE = false>
+// KR (BSM only): the B fragments of the first KR channel steps are copied from the shared-memory tile into registers
+// once per atom (the kernel has register headroom at 16 warps, and every B load is a wavefront of the L1/shared pipe
+// that bounds it).
+template <int KT, bool BSM, int MAXT, bool CM = false, bool GATE = false, int KR = 0>
 __global__ void __launch_bounds__(MAXT) k_tab_grad_mma(const __grid_constant__ TabParams<double> p) {
   using FP = double;
   const int lane = threadIdx.x & 31;
@@ -1470,7 +1473,7 @@ __global__ void __launch_bounds__(MAXT) k_tab_grad_mma(const __grid_constant__ T
   Pre<FP, false> pre;
   load_pre(pre, p, i, 0, lane);
   FP last = i < p.nloc ? p.em_x[i * p.ldx_i + (long long)(p.nnei - 1) * p.ldx_j] : (FP)0.;
-  FP bf[BSM ? 1 : KT];  // B fragments: dy[m = q][channel 4t + kk] (q < 4), constant per atom
+  FP bf[BSM ? (KR > 0 ? KR : 1) : KT];  // B fragments: dy[m = q][channel 4t + kk] (q < 4), constant per atom
   const FP* bsrc = dyt + (q & 3) * MP + kk;
   if (BSM) {
     for (int e = lane; e < 4 * MP; e += 32) dyt[e] = (FP)0.;
@@ -1487,6 +1490,10 @@ __global__ void __launch_bounds__(MAXT) k_tab_grad_mma(const __grid_constant__ T
           dyt[m * MP + (e - m * M)] = dyi[e];
         }
         __syncwarp();
+        if (KR > 0) {
+#pragma unroll
+          for (int t = 0; t < (KR < KT ? KR : KT); ++t) bf[t] = bsrc[4 * t];
+        }
       } else {
 #pragma unroll
         for (int t = 0; t < KT; ++t) {
@@ -1563,7 +1570,7 @@ __global__ void __launch_bounds__(MAXT) k_tab_grad_mma(const __grid_constant__ T
       gd = b1 + d2 * xx;                                                                      \
     }                                                                                         \
     g += gd * dl; /* dl == 0 inside [lower, max): one FMA instead of a select pair */         \
-    const FP bt = BSM ? bsrc[4 * t] : bf[BSM ? 0 : t];                                        \
+    const FP bt = BSM ? (t < KR ? bf[t < KR ? t : 0] : bsrc[4 * t]) : bf[BSM ? 0 : t];        \
     if (GATE) {                                                                               \
       const FP tt = __ldg(ttrow + (off >> 4)); /* off = 16 * (clamped) channel */              \
       dmma884(c3a, c3b, g * tt, bt);                                                          \
@@ -1771,6 +1778,14 @@ inline int grad_hot_pad() {
   static const int v = [] {
     const char* e = getenv("DPB200_TAB_GRAD_PAD");
     return e ? atoi(e) : 64;
+  }();
+  return v;
+}
+
+inline int grad_breg() {
+  static const int v = [] {
+    const char* e = getenv("DPB200_GRAD_BREG");  // 0: all B fragments from shared memory (comparison runs)
+    return e ? atoi(e) : 1;
   }();
   return v;
 }
@@ -2234,6 +2249,10 @@ int launch_grad(FP* dy_dem_x, FP* dy_dem, FP* dy_dtwo, const FP* table, const FP
       if (e1 == cudaSuccess) kern<<<gridv, nwv * 32, smemv, st>>>(p);                           \
     } else if (ga) {                                                                            \
       auto kern = k_tab_grad_mma<KT, true, 512, false, true>;                                   \
+      e1 = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemv); \
+      if (e1 == cudaSuccess) kern<<<gridv, nwv * 32, smemv, st>>>(p);                           \
+    } else if (cm && grad_breg() > 0) {                                                         \
+      auto kern = k_tab_grad_mma<KT, true, 512, true, false, 12>;                               \
       e1 = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemv); \
       if (e1 == cudaSuccess) kern<<<gridv, nwv * 32, smemv, st>>>(p);                           \
     } else if (cm) {                                                                            \
