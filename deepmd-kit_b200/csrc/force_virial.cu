@@ -82,7 +82,7 @@ __device__ __forceinline__ void stage_deriv(float* __restrict__ s, const float* 
   }
 }
 
-template <typename FP, bool FORCE, bool VIRIAL>
+template <typename FP, bool FORCE, bool VIRIAL, bool PAIR = false>
 __global__ void __launch_bounds__(128) k_force_virial(const __grid_constant__ FvParams<FP> p) {
   __shared__ FP stage_all[4][32 * kStride];
   __shared__ double vred[4][9];
@@ -116,8 +116,8 @@ __global__ void __launch_bounds__(128) k_force_virial(const __grid_constant__ Fv
         FP f1 = g.x * d[1] + g.y * d[4] + g.z * d[7] + g.w * d[10];
         FP f2 = g.x * d[2] + g.y * d[5] + g.z * d[8] + g.w * d[11];
         FP r0 = (FP)0., r1 = (FP)0., r2 = (FP)0.;
-        if (VIRIAL) r0 = rj[3 * s + 0], r1 = rj[3 * s + 1], r2 = rj[3 * s + 2];
-        if (VIRIAL && p.pair_q) {
+        if (PAIR) {  // (compiled out of the plain kernels: loading rij ahead of the list test costs them 10 %)
+          r0 = rj[3 * s + 0], r1 = rj[3 * s + 1], r2 = rj[3 * s + 2];
           const FP cf = p.pair_q[row * nnei + s] * p.pair_w[row * nnei + s];
           f0 -= cf * r0, f1 -= cf * r1, f2 -= cf * r2;
         }
@@ -130,6 +130,7 @@ __global__ void __launch_bounds__(128) k_force_virial(const __grid_constant__ Fv
             atomic_add(fo + 3 * (long long)j + 2, f2);
           }
           if (VIRIAL) {
+            if (!PAIR) r0 = rj[3 * s + 0], r1 = rj[3 * s + 1], r2 = rj[3 * s + 2];
             const FP t[9] = {f0 * r0, f0 * r1, f0 * r2, f1 * r0, f1 * r1, f1 * r2, f2 * r0, f2 * r1, f2 * r2};
 #pragma unroll
             for (int q = 0; q < 9; ++q) vs[q] += (double)t[q];
@@ -280,11 +281,22 @@ int launch_fv(FP* force, FP* virial, FP* atom_virial, const FP* net_deriv, const
               "prod_force_virial_a_pair: pair_q and pair_w come together (fused force + virial entry only)");
   p.pair_q = pair_q;
   p.pair_w = pair_w;
-  auto kern = k_force_virial<FP, FORCE, VIRIAL>;
   int occ = 0;
+  long long want = (nrows + 3) / 4;
+  if constexpr (FORCE && VIRIAL) {
+    if (pair_q) {
+      auto kern = k_force_virial<FP, true, true, true>;
+      DPB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, 128, 0));
+      long long cap = (long long)sm_count() * (occ < 1 ? 1 : occ);
+      kern<<<(int)(want < cap ? want : cap), 128, 0, st>>>(p);
+      DPB_CUDA(cudaGetLastError());
+      note_launches(1);
+      return DPB200_OK;
+    }
+  }
+  auto kern = k_force_virial<FP, FORCE, VIRIAL>;
   DPB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, 128, 0));
   if (occ < 1) occ = 1;
-  long long want = (nrows + 3) / 4;
   long long cap = (long long)sm_count() * occ;
   const int grid = (int)(want < cap ? want : cap);
   kern<<<grid, 128, 0, st>>>(p);
