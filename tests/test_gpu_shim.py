@@ -152,6 +152,7 @@ def test_shim_tabulate_higher_basis(olib, tmp_path, nd):
     close(gg, olib.tabulate_fusion_se_a_grad_grad(table, info, ex, em, dzx.reshape(-1, 1), dzem, M))
 
 
+@pytest.mark.gpu
 def test_shim_neighbour_front_end(olib, tmp_path):
     """normalize_coord_gpu / copy_coord_gpu / build_nlist_gpu driven as _norm_copy_coord_gpu and _build_nlist_gpu of
     source/op/tf/prod_env_mat_multi_device.cc:2399-2600 drive them: Region and cell_info in DEVICE memory, rows
