@@ -17,7 +17,13 @@ ncopy = int(os.environ.get("NCOPY", "8"))
 dtype = torch.float64 if os.environ.get("DTYPE", "f64") == "f64" else torch.float32
 dev = torch.device("cuda:0")
 coord, atype, box = g.water_box(ncopy, 0.01)
-dp = DeepPotB200(SeAModel(SeAConfig(), dtype, dev), skin=2.0, nlist_every=10, use_graph=False)
+if os.environ.get("MODEL", "se_a") == "se_atten":  # config 5 model (ncu summary of the gated kernels)
+    from deepmd_kit_b200.atten import SeAttenConfig, SeAttenModel  # noqa: E402
+
+    model = SeAttenModel(SeAttenConfig(), dtype, dev)
+else:
+    model = SeAModel(SeAConfig(), dtype, dev)
+dp = DeepPotB200(model, skin=2.0, nlist_every=10, use_graph=False)
 c = torch.as_tensor(coord.astype(np.float64 if dtype == torch.float64 else np.float32)).to(dev)
 t = torch.as_tensor(atype).to(dev)
 for _ in range(3):
