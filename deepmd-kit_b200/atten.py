@@ -21,7 +21,7 @@ from __future__ import annotations
 
 import math
 from dataclasses import dataclass
-from typing import Sequence
+from typing import Optional, Sequence
 
 import numpy as np
 import torch
@@ -99,7 +99,10 @@ class SeAttenModel:
     """Random-init compressed se_atten_v2 model (weights of the named architecture; geometric table through the
     restated `dp compress`, type-pair table through the strip net)."""
 
-    def __init__(self, cfg: SeAttenConfig, dtype=torch.float64, device="cuda"):
+    def __init__(self, cfg: SeAttenConfig, dtype=torch.float64, device="cuda", weights: Optional[dict] = None):
+        """weights (optional; tests/golden/dpa1_strip.json "weights", taken from the reference's DescrptDPA1):
+        embed / strip = [{w, b, resnet}] of the geometric net and of the two-side strip net, tebd = the type-embedding
+        table [(ntypes + 1), tebd_dim] with the zero padding row last.  Without it: random init of the same shapes."""
         self.cfg = cfg
         self.dtype = dtype
         self.device = torch.device(device)
@@ -114,6 +117,9 @@ class SeAttenModel:
         self.dstd = torch.as_tensor(dstd.reshape(nt, -1), dtype=dtype, device=self.device)
         # one type-agnostic geometric embedding net -> one table over the range of all centre types
         self.embed = EmbeddingNet(cfg.neuron, cfg.seed)
+        if weights is not None:
+            self.embed.weights = [torch.as_tensor(np.asarray(l["w"], np.float64)) for l in weights["embed"]]
+            self.embed.biases = [torch.as_tensor(np.asarray(l["b"], np.float64)) for l in weights["embed"]]
         lower, upper = env_mat_range(davg[:, 0, :], dstd[:, 0, :], cfg.min_nbor_dist, cfg.rcut_smth, cfg.rcut)
         ll, uu = float(lower.min()), float(upper.max())
         self.table64 = build_table(self.embed, ll, uu, cfg.stride0, cfg.stride1, cfg.extrapolate)
@@ -126,6 +132,10 @@ class SeAttenModel:
         tebd = torch.zeros(nt + 1, cfg.tebd_dim, dtype=torch.float64)
         tebd[:nt] = torch.empty(nt, cfg.tebd_dim, dtype=torch.float64).normal_(0.0, 1.0, generator=g)
         ws, bs = _mlp_init([2 * cfg.tebd_dim] + list(cfg.neuron), cfg.seed + 13)
+        if weights is not None:
+            tebd = torch.as_tensor(np.asarray(weights["tebd"], np.float64)).reshape(nt + 1, cfg.tebd_dim)
+            ws = [torch.as_tensor(np.asarray(l["w"], np.float64)) for l in weights["strip"]]
+            bs = [torch.as_tensor(np.asarray(l["b"], np.float64)) for l in weights["strip"]]
         nei = tebd.view(1, nt + 1, -1).expand(nt + 1, nt + 1, -1)
         cen = tebd.view(nt + 1, 1, -1).expand(nt + 1, nt + 1, -1)
         tt = _mlp_tanh_resnet(torch.cat([nei, cen], -1).reshape(-1, 2 * cfg.tebd_dim), ws, bs)

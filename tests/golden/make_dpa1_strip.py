@@ -1,0 +1,98 @@
+"""Golden vectors for the se_atten (DPA-1 strip / smooth, attn_layer 0) MODEL composition, produced by the reference's
+own NumPy backend (deepmd/dpmodel/descriptor/dpa1.py: DescrptDPA1.call), run HERE where /root/reference exists:
+
+    python tests/golden/make_dpa1_strip.py
+
+The reference package is imported from the read-only tree.  Four things it imports at module level are absent from
+this image (no network): `array_api_compat`, `h5py`, `wcmatch`, `lmdb`, and the compiled `deepmd.lib` package.  None of
+them takes part in a CPU evaluation of the descriptor; tests/golden/_ref_shims holds import stand-ins (NumPy >= 2
+provides the array-API functions the backend calls).  Nothing of the reference is copied: the script builds the model
+of examples/water/se_atten_compressible/input.json (se_atten_v2 = strip + smooth type embedding; sel 120, rcut 6.0 /
+0.5, neuron [25, 50, 100], axis 16, tebd_dim 8, two-side) with the reference's default initialisation (seed 1), gives it
+the env-mat statistics of deepmd_kit_b200.atten.SeAttenConfig, evaluates the 192-atom water frame and writes
+tests/golden/dpa1_strip.json:
+  weights   : davg / dstd, geometric embedding net, two-side strip net, type-embedding table (padding row last)
+  expected  : descriptor rows [D (100 x 16) | tebd(centre)] of eight atoms, sum and sum of squares of all rows,
+              per-atom neighbour counts
+"""
+import json
+import os
+import sys
+import types
+
+import numpy as np
+
+REF = os.environ.get("DEEPMD_SOURCE_DIR", "/root/reference")
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+
+
+def import_reference():
+    sys.path.insert(0, os.path.join(HERE, "_ref_shims"))
+    sys.path.insert(0, REF)
+    import deepmd
+
+    lib = types.ModuleType("deepmd.lib")
+    lib.__path__ = [os.path.join(HERE, "_ref_shims", "dplib")]
+    sys.modules["deepmd.lib"] = lib
+    deepmd.lib = lib
+    from deepmd.dpmodel.descriptor.dpa1 import DescrptDPA1
+    from deepmd.dpmodel.utils.nlist import extend_input_and_build_neighbor_list
+
+    return DescrptDPA1, extend_input_and_build_neighbor_list
+
+
+def net_weights(net):
+    out = []
+    for layer in net.layers:
+        assert layer.idt is None and layer.activation_function == "tanh"
+        out.append(dict(w=np.asarray(layer.w).tolist(), b=np.asarray(layer.b).tolist(), resnet=bool(layer.resnet)))
+    return out
+
+
+def main():
+    DescrptDPA1, build = import_reference()
+    sys.path.insert(0, ROOT)
+    import __graft_entry__ as g
+
+    coord, atype, box = g.water_box(1, 0.0)
+    # statistics as in deepmd_kit_b200.atten.SeAttenConfig.stats (type 0 / 1: davg0, dstd radial, dstd angular)
+    stats = ((0.05033, 0.13984, 0.08580), (0.04810, 0.12388, 0.07672))
+    rcut, rcut_smth, sel, ntypes, tebd_dim = 6.0, 0.5, 120, 2, 8
+    dp = DescrptDPA1(rcut=rcut, rcut_smth=rcut_smth, sel=sel, ntypes=ntypes, neuron=[25, 50, 100], axis_neuron=16,
+                     tebd_dim=tebd_dim, tebd_input_mode="strip", attn_layer=0, smooth_type_embedding=True,
+                     type_one_side=False, concat_output_tebd=True, seed=1, precision="float64")
+    blk = dp.se_atten
+    davg = np.zeros((ntypes, sel, 4))
+    dstd = np.ones((ntypes, sel, 4))
+    for t, (a0, s0, s1) in enumerate(stats):
+        davg[t, :, 0] = a0
+        dstd[t, :, 0] = s0
+        dstd[t, :, 1:] = s1
+    blk.mean[...] = davg
+    blk.stddev[...] = dstd
+    c = coord.reshape(1, -1, 3)
+    ext_c, ext_t, mapping, nlist = build(c, atype.reshape(1, -1).astype(np.int64), rcut, [sel], mixed_types=True,
+                                        box=box.reshape(1, 3, 3))
+    out = dp.call(ext_c, ext_t, nlist, mapping)
+    desc = np.asarray(out[0])[0]  # [nloc, 100*16 + 8]
+    assert desc.shape == (len(atype), 1608)
+    tebd = np.asarray(dp.type_embedding.call())  # [ntypes + 1, tebd_dim], padding row last
+    rows = [0, 1, 2, 63, 64, 65, 100, 191]
+    data = dict(
+        config=dict(rcut=rcut, rcut_smth=rcut_smth, sel=sel, ntypes=ntypes, neuron=[25, 50, 100], axis_neuron=16,
+                    tebd_dim=tebd_dim, stats=stats),
+        weights=dict(embed=net_weights(blk.embeddings[0]), strip=net_weights(blk.embeddings_strip[0]),
+                     tebd=tebd.tolist()),
+        expected=dict(rows=rows, descriptor=desc[rows].tolist(), total=float(desc.sum()),
+                      total_sq=float((desc * desc).sum()),
+                      numneigh=(np.asarray(nlist)[0] >= 0).sum(1).tolist()),
+    )
+    path = os.path.join(HERE, "dpa1_strip.json")
+    with open(path, "w") as f:
+        json.dump(data, f)
+    print("wrote", path, os.path.getsize(path), "bytes; |D| max", float(np.abs(desc).max()))
+
+
+if __name__ == "__main__":
+    main()

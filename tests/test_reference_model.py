@@ -68,3 +68,83 @@ def test_reference_model_on_the_gpu(data):
         assert rel(ae[0], c["atomic_energy"]) <= 1e-10
         assert rel(f[0], c["force"]) <= 1e-10
         assert rel(v[0], c["virial"]) <= 1e-10
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# se_atten (DPA-1 strip / smooth, attn_layer 0): descriptor rows produced by the reference's own NumPy backend
+# (deepmd/dpmodel/descriptor/dpa1.py DescrptDPA1.call; fixture tests/golden/dpa1_strip.json written by
+# tests/golden/make_dpa1_strip.py).  Pins the MODEL composition -- one type-agnostic section with per-type statistics,
+# tebd_idx = centre * (ntypes + 1) + neighbour, strip net on [tebd(neighbour), tebd(centre)], gate
+# gg_s * (1 + gg_t * sw), /nnei, GR^T GR[:, :axis], centre type embedding appended -- to the reference itself.  The
+# reference evaluates the embedding net exactly; here it is tabulated (stride 0.01 quintic): measured 3.4e-15 (CPU).
+# ---------------------------------------------------------------------------------------------------------------
+@pytest.fixture(scope="module")
+def dpa1():
+    with open(os.path.join(ROOT, "tests", "golden", "dpa1_strip.json")) as f:
+        return json.load(f)
+
+
+def _atten_model(dpa1, device):
+    from deepmd_kit_b200.atten import SeAttenConfig, SeAttenModel
+
+    c = dpa1["config"]
+    cfg = SeAttenConfig(ntypes=c["ntypes"], nsel=c["sel"], rcut=c["rcut"], rcut_smth=c["rcut_smth"],
+                        neuron=tuple(c["neuron"]), axis_neuron=c["axis_neuron"], tebd_dim=c["tebd_dim"],
+                        stats=tuple(tuple(s) for s in c["stats"]))
+    return SeAttenModel(cfg, torch.float64, device, weights=dpa1["weights"])
+
+
+def _descriptor_rows(model, xyz, ctype):
+    """[D | tebd(centre)] from the gated table output xyz [nloc, 4, M] (what the fitting net is fed with)."""
+    cfg = model.cfg
+    xs = xyz / cfg.nnei
+    d = torch.matmul(xs.permute(0, 2, 1), xs[:, :, :cfg.axis_neuron]).reshape(xyz.shape[0], -1)
+    return torch.cat([d, model.tebd.to(d.device)[ctype]], 1)
+
+
+def test_se_atten_composition_matches_reference_backend_cpu(dpa1):
+    g.load_package()
+    model = _atten_model(dpa1, "cpu")
+    from oracle import pipeline_atten
+
+    coord, atype, box = g.water_box(1, 0.0)
+    lib = ocpu.CpuLib("reference" if ocpu.available("reference") else "port")
+    lists = pipeline.build_lists(lib, coord, atype, box, model.cfg.rcut + 2.0)
+    _, _, _, ex = pipeline_atten.evaluate(lib, model, lists)
+    exp = dpa1["expected"]
+    assert ((ex["nlist"] >= 0).sum(1) == np.array(exp["numneigh"])).all()
+    got = _descriptor_rows(model, torch.as_tensor(ex["xyz"]), torch.as_tensor(atype.astype(np.int64))).numpy()
+    want = np.array(exp["descriptor"])
+    assert got.shape[1] == want.shape[1] == 1608
+    assert rel(got[exp["rows"]], want) <= 1e-12  # measured 3.4e-15
+    assert abs(got.sum() - exp["total"]) <= 1e-12 * abs(exp["total"])
+    assert abs((got * got).sum() - exp["total_sq"]) <= 1e-12 * exp["total_sq"]
+
+
+@pytest.mark.gpu
+def test_se_atten_composition_matches_reference_backend_gpu(dpa1):
+    """The product kernels (env-mat, gate scalars, gated table forward) on the same weights."""
+    pkg = g.load_package()
+    ops = pkg.ops
+    from deepmd_kit_b200.model import DeepPotB200
+
+    model = _atten_model(dpa1, "cuda:0")
+    cfg = model.cfg
+    coord, atype, box = g.water_box(1, 0.0)
+    dp = DeepPotB200(model, skin=2.0, use_graph=False)
+    c = torch.as_tensor(coord).to("cuda:0")
+    t = torch.as_tensor(atype).to("cuda:0")
+    st = dp.build_neighbors(c, t, box)
+    ext_c = (c.reshape(-1, 3).index_select(0, st.map64) + st.shift).contiguous()
+    nloc, nall, nnei = st.nloc, int(st.ext_type.numel()), cfg.nnei
+    em, dv, rij, nlist = ops.prod_env_mat_a(ext_c.reshape(-1), st.ext_type, st.numneigh, st.rows, model.davg, model.dstd,
+                                            nloc, nall, cfg.rcut, cfg.rcut_smth, cfg.sec,
+                                            f_type=torch.zeros_like(st.ext_type))
+    pair, sw, _ = ops.se_atten_gate_scalars(nlist, st.ext_type, rij, nloc, nnei, cfg.ntypes, cfg.rcut_smth, cfg.rcut)
+    em3 = em.reshape(nloc, nnei, 4)
+    em_x = em3[:, :, 0].reshape(-1, 1).contiguous()
+    xyz = ops.tabulate_fusion_se_atten_gate(model.table, model.info, em_x, em3, model.tt_full, pair, sw, model.M)
+    got = _descriptor_rows(model, xyz, t.long()).cpu().numpy()
+    exp = dpa1["expected"]
+    assert rel(got[exp["rows"]], np.array(exp["descriptor"])) <= 1e-10
+    assert abs(got.sum() - exp["total"]) <= 1e-10 * abs(exp["total"])
