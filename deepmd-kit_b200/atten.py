@@ -147,6 +147,23 @@ class SeAttenModel:
         self.dim_in = (self.dim_d + cfg.tebd_dim + 15) // 16 * 16
         self.fit = FittingNet(self.dim_in, cfg.fitting_neuron, cfg.fitting_resnet_dt, cfg.seed + 101, dtype, self.device)
         self.bias_atom_e = torch.zeros(nt, dtype=dtype, device=self.device)
+        if weights is not None and "fit" in weights:
+            # the reference's fitting net (deepmd/dpmodel/fitting: one net for all types, input [D | tebd(centre)]);
+            # the first weight matrix gets zero rows for the padded input columns
+            layers = []
+            for li, l in enumerate(weights["fit"]["layers"]):
+                w = torch.as_tensor(np.asarray(l["w"], np.float64))
+                if li == 0 and w.shape[0] < self.dim_in:
+                    w = torch.cat([w, torch.zeros(self.dim_in - w.shape[0], w.shape[1], dtype=torch.float64)], 0)
+                b = torch.as_tensor(np.asarray(l["b"], np.float64))
+                idt = None if l.get("idt") is None else torch.as_tensor(np.asarray(l["idt"], np.float64))
+                layers.append((w.to(self.device, dtype).contiguous(), b.to(self.device, dtype),
+                               None if idt is None else idt.to(self.device, dtype)))
+            self.fit.layers = layers
+            hw = torch.as_tensor(np.asarray(weights["fit"]["head"]["w"], np.float64)).reshape(-1, 1)
+            hb = torch.as_tensor(np.asarray(weights["fit"]["head"]["b"], np.float64)).reshape(1)
+            self.fit.head = (hw.to(self.device, dtype), hb.to(self.device, dtype))
+            self.bias_atom_e = torch.as_tensor(np.asarray(weights["bias_atom_e"], np.float64)).to(self.device, dtype)
         self.fit_chunk = 1 << 17
         # two_embed [atoms * nnei, M] is 96 KB per atom in fp64 (50 GB for the 526 848-atom box): the gated table
         # operator runs over slabs of this many centre atoms, the gate being recomputed for the backward

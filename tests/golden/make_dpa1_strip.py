@@ -13,7 +13,10 @@ the env-mat statistics of deepmd_kit_b200.atten.SeAttenConfig, evaluates the 192
 tests/golden/dpa1_strip.json:
   weights   : davg / dstd, geometric embedding net, two-side strip net, type-embedding table (padding row last)
   expected  : descriptor rows [D (100 x 16) | tebd(centre)] of eight atoms, sum and sum of squares of all rows,
-              per-atom neighbour counts
+              per-atom neighbour counts, and the atomic energies of the reference's EnergyFittingNet
+              (deepmd/dpmodel/fitting/ener_fitting.py; mixed types, resnet_dt, a REDUCED width [16, 16, 16] so that
+              the fixture stays small -- the conventions it pins do not depend on the width -- and a non-zero
+              bias_atom_e) on that descriptor
 """
 import json
 import os
@@ -37,9 +40,10 @@ def import_reference():
     sys.modules["deepmd.lib"] = lib
     deepmd.lib = lib
     from deepmd.dpmodel.descriptor.dpa1 import DescrptDPA1
+    from deepmd.dpmodel.fitting.ener_fitting import EnergyFittingNet
     from deepmd.dpmodel.utils.nlist import extend_input_and_build_neighbor_list
 
-    return DescrptDPA1, extend_input_and_build_neighbor_list
+    return DescrptDPA1, extend_input_and_build_neighbor_list, EnergyFittingNet
 
 
 def net_weights(net):
@@ -51,7 +55,7 @@ def net_weights(net):
 
 
 def main():
-    DescrptDPA1, build = import_reference()
+    DescrptDPA1, build, EnergyFittingNet = import_reference()
     sys.path.insert(0, ROOT)
     import __graft_entry__ as g
 
@@ -78,15 +82,28 @@ def main():
     desc = np.asarray(out[0])[0]  # [nloc, 100*16 + 8]
     assert desc.shape == (len(atype), 1608)
     tebd = np.asarray(dp.type_embedding.call())  # [ntypes + 1, tebd_dim], padding row last
+    fit_neuron = [16, 16, 16]
+    fit = EnergyFittingNet(ntypes=ntypes, dim_descrpt=desc.shape[1], neuron=fit_neuron, resnet_dt=True, mixed_types=True,
+                           seed=1, precision="float64")
+    fit.bias_atom_e[...] = np.array([[-1.5], [0.7]])
+    e_atom = np.asarray(fit.call(desc[None], atype.reshape(1, -1).astype(np.int64))["energy"]).reshape(-1)
+    net = fit.nets[()]
+    layers = [dict(w=np.asarray(l.w).tolist(), b=np.asarray(l.b).tolist(),
+                   idt=None if l.idt is None else np.asarray(l.idt).tolist()) for l in net.layers[:-1]]
+    head = net.layers[-1]
+    assert head.activation_function == "none" and head.idt is None and not head.resnet
     rows = [0, 1, 2, 63, 64, 65, 100, 191]
     data = dict(
         config=dict(rcut=rcut, rcut_smth=rcut_smth, sel=sel, ntypes=ntypes, neuron=[25, 50, 100], axis_neuron=16,
-                    tebd_dim=tebd_dim, stats=stats),
+                    tebd_dim=tebd_dim, stats=stats, fitting_neuron=fit_neuron, fitting_resnet_dt=True),
         weights=dict(embed=net_weights(blk.embeddings[0]), strip=net_weights(blk.embeddings_strip[0]),
-                     tebd=tebd.tolist()),
+                     tebd=tebd.tolist(),
+                     fit=dict(layers=layers, head=dict(w=np.asarray(head.w).tolist(), b=np.asarray(head.b).tolist())),
+                     bias_atom_e=np.asarray(fit.bias_atom_e).reshape(-1).tolist()),
         expected=dict(rows=rows, descriptor=desc[rows].tolist(), total=float(desc.sum()),
                       total_sq=float((desc * desc).sum()),
-                      numneigh=(np.asarray(nlist)[0] >= 0).sum(1).tolist()),
+                      numneigh=(np.asarray(nlist)[0] >= 0).sum(1).tolist(),
+                      atomic_energy=e_atom.tolist(), energy=float(e_atom.sum())),
     )
     path = os.path.join(HERE, "dpa1_strip.json")
     with open(path, "w") as f:

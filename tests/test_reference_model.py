@@ -90,7 +90,8 @@ def _atten_model(dpa1, device):
     c = dpa1["config"]
     cfg = SeAttenConfig(ntypes=c["ntypes"], nsel=c["sel"], rcut=c["rcut"], rcut_smth=c["rcut_smth"],
                         neuron=tuple(c["neuron"]), axis_neuron=c["axis_neuron"], tebd_dim=c["tebd_dim"],
-                        stats=tuple(tuple(s) for s in c["stats"]))
+                        stats=tuple(tuple(s) for s in c["stats"]), fitting_neuron=tuple(c["fitting_neuron"]),
+                        fitting_resnet_dt=bool(c["fitting_resnet_dt"]))
     return SeAttenModel(cfg, torch.float64, device, weights=dpa1["weights"])
 
 
@@ -110,7 +111,7 @@ def test_se_atten_composition_matches_reference_backend_cpu(dpa1):
     coord, atype, box = g.water_box(1, 0.0)
     lib = ocpu.CpuLib("reference" if ocpu.available("reference") else "port")
     lists = pipeline.build_lists(lib, coord, atype, box, model.cfg.rcut + 2.0)
-    _, _, _, ex = pipeline_atten.evaluate(lib, model, lists)
+    e, _, _, ex = pipeline_atten.evaluate(lib, model, lists)
     exp = dpa1["expected"]
     assert ((ex["nlist"] >= 0).sum(1) == np.array(exp["numneigh"])).all()
     got = _descriptor_rows(model, torch.as_tensor(ex["xyz"]), torch.as_tensor(atype.astype(np.int64))).numpy()
@@ -119,6 +120,9 @@ def test_se_atten_composition_matches_reference_backend_cpu(dpa1):
     assert rel(got[exp["rows"]], want) <= 1e-12  # measured 3.4e-15
     assert abs(got.sum() - exp["total"]) <= 1e-12 * abs(exp["total"])
     assert abs((got * got).sum() - exp["total_sq"]) <= 1e-12 * exp["total_sq"]
+    # ... and the energies of the reference's EnergyFittingNet on top (mixed types, resnet_dt / idt, bias_atom_e)
+    assert rel(ex["atom_energy"], exp["atomic_energy"]) <= 1e-12
+    assert abs(e - exp["energy"]) <= 1e-12 * abs(exp["energy"])
 
 
 @pytest.mark.gpu
@@ -148,3 +152,9 @@ def test_se_atten_composition_matches_reference_backend_gpu(dpa1):
     exp = dpa1["expected"]
     assert rel(got[exp["rows"]], np.array(exp["descriptor"])) <= 1e-10
     assert abs(got.sum() - exp["total"]) <= 1e-10 * abs(exp["total"])
+    # the whole model through the public API (fitting net on the tcgen05 kernels): the reference's energies
+    assert model.use_tc
+    eg, fg, vg, ae, _ = DeepPotB200(model, skin=2.0).eval(coord.reshape(1, -1), box.reshape(1, 9), atype, atomic=True)
+    assert rel(ae[0].reshape(-1), exp["atomic_energy"]) <= 1e-10
+    assert abs(eg[0, 0] - exp["energy"]) <= 1e-10 * abs(exp["energy"])
+    assert np.abs(fg[0].sum(0)).max() <= 1e-9 * np.abs(fg[0]).max()  # no net force
