@@ -76,11 +76,18 @@ def spline5_switch(r: float, rmin: float, rmax: float) -> float:
 
 
 def env_mat_range(davg: np.ndarray, dstd: np.ndarray, min_nbor_dist: float, rcut_smth: float, rcut: float):
-    """tabulate.py:468-486: per centre type floor(-davg/dstd), ceil((sw/rmin - davg)/dstd)."""
+    """deepmd/utils/tabulate.py:468-486 + :94-96.  davg / dstd: the statistics of neighbour SLOT 0, [ntypes, 4] (the
+    reference indexes `davg[:, 0]` on its [ntypes, nnei, 4] arrays, i.e. all four components of the first slot): per
+    centre type floor(-davg/dstd) and ceil((sw/rmin - davg)/dstd) element-wise, then the minimum / maximum over the
+    components.  With the usual statistics (davg = 0, smaller dstd on the angular components) the ANGULAR components
+    set the upper boundary -- checked against the table the reference's own `enable_compression` builds
+    (tests/golden/dpa1_strip.json: lower -1, upper 15 for the water statistics)."""
+    davg = np.asarray(davg, np.float64).reshape(len(davg), -1)
+    dstd = np.asarray(dstd, np.float64).reshape(len(dstd), -1)
     sw = spline5_switch(min_nbor_dist, rcut_smth, rcut)
-    lower = -davg[:, 0] / dstd[:, 0]
-    upper = ((1.0 / min_nbor_dist) * sw - davg[:, 0]) / dstd[:, 0]
-    return np.floor(lower), np.ceil(upper)
+    lower = np.floor(-davg / dstd)
+    upper = np.ceil(((1.0 / min_nbor_dist) * sw - davg) / dstd)
+    return lower.min(axis=1), upper.max(axis=1)
 
 
 def build_table(net: EmbeddingNet, lower: float, upper: float, stride0: float, stride1: float, extrapolate: float,

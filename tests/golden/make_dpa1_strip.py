@@ -105,6 +105,25 @@ def main():
                       numneigh=(np.asarray(nlist)[0] >= 0).sum(1).tolist(),
                       atomic_energy=e_atom.tolist(), energy=float(e_atom.sum())),
     )
+    # `dp compress` by the reference itself (deepmd/utils/tabulate.py + tabulate_math.py through
+    # DescrptDPA1.enable_compression): table_info and the tabulated quintics.  The high-order coefficients come from
+    # differences divided by stride^3..5 and carry amplified rounding noise (two builds of the reference differ in
+    # a5 at the 1e-5 level), so the fixture stores what the table MEANS: the quintic evaluated at three points of
+    # every row, summed over channels (per row) and over rows (per channel).
+    dp.enable_compression(0.9, 5, 0.01, 0.1, -1)
+    info = np.asarray(blk.compress_info[0], np.float64)
+    tab = np.asarray(blk.compress_data[0], np.float64)
+    nrow = tab.shape[0]
+    first = int((info[1] - info[0]) / info[3])
+    h = np.where(np.arange(nrow) < first, info[3], info[4])[:, None]
+    a = tab.reshape(nrow, -1, 6)
+    sums = []
+    for frac in (0.0, 0.5, 0.999):
+        x = frac * h
+        v = a[:, :, 0] + (a[:, :, 1] + (a[:, :, 2] + (a[:, :, 3] + (a[:, :, 4] + a[:, :, 5] * x) * x) * x) * x) * x
+        sums.append(dict(frac=frac, per_row=v.sum(1).tolist(), per_channel=v.sum(0).tolist()))
+    data["compress"] = dict(min_nbor_dist=0.9, table_info=info.tolist(), nrow=int(nrow), sums=sums,
+                            tt_full=np.asarray(blk.type_embd_data).tolist())
     path = os.path.join(HERE, "dpa1_strip.json")
     with open(path, "w") as f:
         json.dump(data, f)

@@ -158,3 +158,27 @@ def test_se_atten_composition_matches_reference_backend_gpu(dpa1):
     assert rel(ae[0].reshape(-1), exp["atomic_energy"]) <= 1e-10
     assert abs(eg[0, 0] - exp["energy"]) <= 1e-10 * abs(exp["energy"])
     assert np.abs(fg[0].sum(0)).max() <= 1e-9 * np.abs(fg[0]).max()  # no net force
+
+
+def test_dp_compress_restatement_matches_reference_table(dpa1):
+    """compress.py against the table the reference's own DescrptDPA1.enable_compression builds for the same embedding
+    net and statistics: identical table_info / row count (the upper boundary comes from the angular components of slot
+    0: 15, not 9), the tabulated quintics equal where it matters (values at three points of every row, summed per row
+    and per channel: 1e-12), and the type-pair table of the strip net (tt_full) element-wise."""
+    g.load_package()
+    model = _atten_model(dpa1, "cpu")
+    cz = dpa1["compress"]
+    assert model.cfg.min_nbor_dist == cz["min_nbor_dist"]
+    info = model.info.numpy()
+    assert np.array_equal(info, np.array(cz["table_info"]))
+    tab = model.table64.numpy()
+    assert tab.shape[0] == cz["nrow"]
+    first = int((info[1] - info[0]) / info[3])
+    h = np.where(np.arange(tab.shape[0]) < first, info[3], info[4])[:, None]
+    a = tab.reshape(tab.shape[0], -1, 6)
+    for srec in cz["sums"]:
+        x = srec["frac"] * h
+        v = a[:, :, 0] + (a[:, :, 1] + (a[:, :, 2] + (a[:, :, 3] + (a[:, :, 4] + a[:, :, 5] * x) * x) * x) * x) * x
+        assert rel(v.sum(1), srec["per_row"]) <= 1e-12
+        assert rel(v.sum(0), srec["per_channel"]) <= 1e-12
+    assert rel(model.tt_full.numpy(), cz["tt_full"]) <= 1e-14
