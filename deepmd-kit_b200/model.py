@@ -428,7 +428,7 @@ class SeAModel:
         dim_d = self.M * cfg.axis_neuron
         self.fit = [FittingNet(dim_d, cfg.fitting_neuron, cfg.fitting_resnet_dt, cfg.seed + 101 * t, dtype, self.device)
                     for t in range(cfg.ntypes)]
-        if weights is not None:
+        if weights is not None and weights.get("fit") is not None:  # (descriptor-only weight sets keep the random fit)
             for f, fw in zip(self.fit, weights["fit"]):
                 f.layers = [(torch.as_tensor(np.asarray(w, np.float64)).to(self.device, dtype),
                              torch.as_tensor(np.asarray(b, np.float64)).reshape(-1).to(self.device, dtype),

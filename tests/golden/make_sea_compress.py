@@ -1,0 +1,68 @@
+"""`dp compress` of a se_e2_a descriptor by the reference's own NumPy backend (deepmd/dpmodel/descriptor/se_e2_a.py:
+DescrptSeA.enable_compression -> deepmd/utils/tabulate.py + tabulate_math.py), run HERE where /root/reference exists:
+
+    python tests/golden/make_sea_compress.py
+
+Benchmark configuration (examples/water/se_e2_a: rcut 6.0 / 0.5, sel [46, 92], neuron [25, 50, 100], type_one_side,
+default initialisation with seed 1) with the env-mat statistics of deepmd_kit_b200.model.WATER_STATS.  Writes
+tests/golden/sea_compress.json: the embedding-net weights per NEIGHBOUR type (the table of net `filter_-1_net_<t>`),
+table_info and row count of every table, and the tabulated quintics evaluated at three points of every row, summed
+over rows (per channel) -- see make_dpa1_strip.py for why values and not coefficients.  Import stand-ins:
+tests/golden/_ref_shims (same as make_dpa1_strip.py)."""
+import json
+import os
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, HERE)
+from make_dpa1_strip import REF  # noqa: E402,F401
+import make_dpa1_strip as base  # noqa: E402
+
+
+def main():
+    base.import_reference()
+    from deepmd.dpmodel.descriptor.se_e2_a import DescrptSeA
+
+    stats = ((0.05033, 0.13984, 0.08580), (0.04810, 0.12388, 0.07672))
+    sel = [46, 92]
+    dp = DescrptSeA(rcut=6.0, rcut_smth=0.5, sel=sel, neuron=[25, 50, 100], axis_neuron=16, type_one_side=True, seed=1,
+                    precision="float64")
+    for t, (a0, s0, s1) in enumerate(stats):
+        dp.davg[t, :, 0] = a0
+        dp.davg[t, :, 1:] = 0.0
+        dp.dstd[t, :, 0] = s0
+        dp.dstd[t, :, 1:] = s1
+    embed = []
+    for t in range(len(sel)):
+        net = dp.embeddings[(t,)]
+        for layer in net.layers:
+            assert layer.idt is None and layer.activation_function == "tanh"
+        embed.append([[np.asarray(l.w).tolist() for l in net.layers], [np.asarray(l.b).tolist() for l in net.layers]])
+    dp.enable_compression(0.9, 5, 0.01, 0.1, -1)
+    tables = []
+    for t in range(len(sel)):
+        info = np.asarray(dp.compress_info[t], np.float64)
+        tab = np.asarray(dp.compress_data[t], np.float64)
+        nrow = tab.shape[0]
+        first = int((info[1] - info[0]) / info[3])
+        h = np.where(np.arange(nrow) < first, info[3], info[4])[:, None]
+        a = tab.reshape(nrow, -1, 6)
+        sums = []
+        for frac in (0.0, 0.5, 0.999):
+            x = frac * h
+            v = a[:, :, 0] + (a[:, :, 1] + (a[:, :, 2] + (a[:, :, 3] + (a[:, :, 4] + a[:, :, 5] * x) * x) * x) * x) * x
+            sums.append(dict(frac=frac, per_channel=v.sum(0).tolist(), total=float(v.sum())))
+        tables.append(dict(table_info=info.tolist(), nrow=int(nrow), sums=sums))
+    data = dict(config=dict(rcut=6.0, rcut_smth=0.5, sel=sel, neuron=[25, 50, 100], axis_neuron=16, stats=stats,
+                            min_nbor_dist=0.9),
+                embed=embed, tables=tables)
+    path = os.path.join(HERE, "sea_compress.json")
+    with open(path, "w") as f:
+        json.dump(data, f)
+    print("wrote", path, os.path.getsize(path), "bytes")
+
+
+if __name__ == "__main__":
+    main()

@@ -182,3 +182,36 @@ def test_dp_compress_restatement_matches_reference_table(dpa1):
         assert rel(v.sum(1), srec["per_row"]) <= 1e-12
         assert rel(v.sum(0), srec["per_channel"]) <= 1e-12
     assert rel(model.tt_full.numpy(), cz["tt_full"]) <= 1e-14
+
+
+def test_se_a_compress_restatement_matches_reference_tables():
+    """compress_se_a (type_one_side: one table per NEIGHBOUR type, range over all centre types with sel > 0) on the
+    benchmark configuration against the reference's own DescrptSeA.enable_compression for the same embedding nets
+    (fixture tests/golden/sea_compress.json, written by tests/golden/make_sea_compress.py)."""
+    g.load_package()
+    from deepmd_kit_b200.model import SeAConfig, SeAModel
+
+    with open(os.path.join(ROOT, "tests", "golden", "sea_compress.json")) as f:
+        d = json.load(f)
+    c = d["config"]
+    cfg = SeAConfig(ntypes=len(c["sel"]), sel=tuple(c["sel"]), rcut=c["rcut"], rcut_smth=c["rcut_smth"],
+                    neuron=tuple(c["neuron"]), axis_neuron=c["axis_neuron"], min_nbor_dist=c["min_nbor_dist"])
+    nnei = sum(c["sel"])
+    davg = np.zeros((cfg.ntypes, nnei, 4))
+    dstd = np.ones((cfg.ntypes, nnei, 4))
+    for t, (a0, s0, s1) in enumerate(c["stats"]):
+        davg[t, :, 0], dstd[t, :, 0], dstd[t, :, 1:] = a0, s0, s1
+    model = SeAModel(cfg, torch.float64, "cpu", weights=dict(davg=davg, dstd=dstd, embed=d["embed"]))
+    for t, want in enumerate(d["tables"]):
+        info = model.infos[t].numpy()
+        assert np.array_equal(info, np.array(want["table_info"]))
+        tab = model.tables64[t].numpy()
+        assert tab.shape[0] == want["nrow"]
+        first = int((info[1] - info[0]) / info[3])
+        h = np.where(np.arange(tab.shape[0]) < first, info[3], info[4])[:, None]
+        a = tab.reshape(tab.shape[0], -1, 6)
+        for srec in want["sums"]:
+            x = srec["frac"] * h
+            v = a[:, :, 0] + (a[:, :, 1] + (a[:, :, 2] + (a[:, :, 3] + (a[:, :, 4] + a[:, :, 5] * x) * x) * x) * x) * x
+            assert rel(v.sum(0), srec["per_channel"]) <= 1e-12
+            assert abs(v.sum() - srec["total"]) <= 1e-12 * abs(srec["total"])
