@@ -6,8 +6,8 @@ DescrptSeA.enable_compression -> deepmd/utils/tabulate.py + tabulate_math.py), r
 Benchmark configuration (examples/water/se_e2_a: rcut 6.0 / 0.5, sel [46, 92], neuron [25, 50, 100], type_one_side,
 default initialisation with seed 1) with the env-mat statistics of deepmd_kit_b200.model.WATER_STATS.  Writes
 tests/golden/sea_compress.json: the embedding-net weights per NEIGHBOUR type (the table of net `filter_-1_net_<t>`),
-table_info and row count of every table, and the tabulated quintics evaluated at three points of every row, summed
-over rows (per channel) -- see make_dpa1_strip.py for why values and not coefficients.  Import stand-ins:
+table_info and row count of every table, the tabulated quintics evaluated at three points of every row, summed
+over rows (per channel), and rows of the UNCOMPRESSED descriptor of the 192-atom water frame (DescrptSeA.call) -- see make_dpa1_strip.py for why values and not coefficients.  Import stand-ins:
 tests/golden/_ref_shims (same as make_dpa1_strip.py)."""
 import json
 import os
@@ -40,6 +40,20 @@ def main():
         for layer in net.layers:
             assert layer.idt is None and layer.activation_function == "tanh"
         embed.append([[np.asarray(l.w).tolist() for l in net.layers], [np.asarray(l.b).tolist() for l in net.layers]])
+    # the UNCOMPRESSED descriptor of the 192-atom water frame (DescrptSeA.call: exact embedding nets)
+    from deepmd.dpmodel.utils.nlist import extend_input_and_build_neighbor_list
+
+    sys.path.insert(0, base.ROOT)
+    import __graft_entry__ as g
+
+    coord, atype, box = g.water_box(1, 0.0)
+    ext_c, ext_t, mapping, nlist = extend_input_and_build_neighbor_list(
+        coord.reshape(1, -1, 3), atype.reshape(1, -1).astype(np.int64), 6.0, sel, mixed_types=False, box=box.reshape(1, 3, 3))
+    desc = np.asarray(dp.call(ext_c, ext_t, nlist, mapping)[0])[0]
+    assert desc.shape == (len(atype), 1600)
+    rows = [0, 1, 63, 64, 130, 191]
+    descriptor = dict(rows=rows, values=desc[rows].tolist(), total=float(desc.sum()), total_sq=float((desc * desc).sum()),
+                      numneigh=(np.asarray(nlist)[0] >= 0).sum(1).tolist())
     dp.enable_compression(0.9, 5, 0.01, 0.1, -1)
     tables = []
     for t in range(len(sel)):
@@ -57,7 +71,7 @@ def main():
         tables.append(dict(table_info=info.tolist(), nrow=int(nrow), sums=sums))
     data = dict(config=dict(rcut=6.0, rcut_smth=0.5, sel=sel, neuron=[25, 50, 100], axis_neuron=16, stats=stats,
                             min_nbor_dist=0.9),
-                embed=embed, tables=tables)
+                embed=embed, tables=tables, descriptor=descriptor)
     path = os.path.join(HERE, "sea_compress.json")
     with open(path, "w") as f:
         json.dump(data, f)

@@ -215,3 +215,33 @@ def test_se_a_compress_restatement_matches_reference_tables():
             v = a[:, :, 0] + (a[:, :, 1] + (a[:, :, 2] + (a[:, :, 3] + (a[:, :, 4] + a[:, :, 5] * x) * x) * x) * x) * x
             assert rel(v.sum(0), srec["per_channel"]) <= 1e-12
             assert abs(v.sum() - srec["total"]) <= 1e-12 * abs(srec["total"])
+
+
+def test_se_a_descriptor_matches_reference_backend():
+    """Benchmark-size se_e2_a (type_one_side, sel [46, 92], M 100, axis 16): the compressed descriptor through the CPU
+    checker pipeline against the reference's UNCOMPRESSED DescrptSeA.call on the 192-atom water frame."""
+    g.load_package()
+    from deepmd_kit_b200.model import SeAConfig, SeAModel
+
+    with open(os.path.join(ROOT, "tests", "golden", "sea_compress.json")) as f:
+        d = json.load(f)
+    c = d["config"]
+    cfg = SeAConfig(ntypes=len(c["sel"]), sel=tuple(c["sel"]), rcut=c["rcut"], rcut_smth=c["rcut_smth"],
+                    neuron=tuple(c["neuron"]), axis_neuron=c["axis_neuron"], min_nbor_dist=c["min_nbor_dist"])
+    nnei = sum(c["sel"])
+    davg = np.zeros((cfg.ntypes, nnei, 4))
+    dstd = np.ones((cfg.ntypes, nnei, 4))
+    for t, (a0, s0, s1) in enumerate(c["stats"]):
+        davg[t, :, 0], dstd[t, :, 0], dstd[t, :, 1:] = a0, s0, s1
+    model = SeAModel(cfg, torch.float64, "cpu", weights=dict(davg=davg, dstd=dstd, embed=d["embed"]))
+    coord, atype, box = g.water_box(1, 0.0)
+    lib = ocpu.CpuLib("reference" if ocpu.available("reference") else "port")
+    lists = pipeline.build_lists(lib, coord, atype, box, cfg.rcut + 2.0)
+    _, _, _, ex = pipeline.evaluate(lib, model, lists)
+    exp = d["descriptor"]
+    assert ((ex["nlist"] >= 0).sum(1) == np.array(exp["numneigh"])).all()
+    xs = torch.as_tensor(ex["xyz"]) / cfg.nnei
+    got = torch.matmul(xs.permute(0, 2, 1), xs[:, :, :cfg.axis_neuron]).reshape(len(atype), -1).numpy()
+    assert rel(got[exp["rows"]], exp["values"]) <= 1e-12
+    assert abs(got.sum() - exp["total"]) <= 1e-12 * abs(exp["total"])
+    assert abs((got * got).sum() - exp["total_sq"]) <= 1e-12 * exp["total_sq"]
