@@ -46,6 +46,31 @@ def import_reference():
     return DescrptDPA1, extend_input_and_build_neighbor_list, EnergyFittingNet
 
 
+def pt_energy_force_virial(dp_descriptor, dp_fitting, coord, atype, box, e_atom_numpy):
+    """deepmd.pt EnergyModel with the given (NumPy-backend) descriptor and fitting net: E, F = -dE/dr, virial."""
+    import torch
+    from deepmd.pt.model.descriptor.base_descriptor import BaseDescriptor
+    from deepmd.pt.model.model import get_model
+    from deepmd.pt.model.task.base_fitting import BaseFitting
+
+    d_ser, f_ser = dp_descriptor.serialize(), dp_fitting.serialize()
+    params = {"type_map": ["O", "H"],
+              "descriptor": {"type": "se_e2_a", "sel": [4, 4], "rcut": 6.0, "rcut_smth": 0.5, "neuron": [2, 4], "axis_neuron": 2},
+              "fitting_net": {"neuron": [4], "resnet_dt": True}}
+    model = get_model(params).to("cpu")  # a shell; descriptor and fitting net are replaced below
+    model.atomic_model.descriptor = BaseDescriptor.deserialize(d_ser).to("cpu")
+    model.atomic_model.fitting_net = BaseFitting.deserialize(f_ser).to("cpu")
+    model.atomic_model.rcut = dp_descriptor.get_rcut()
+    model.atomic_model.sel = dp_descriptor.get_sel()
+    c = torch.tensor(coord.reshape(1, -1), dtype=torch.float64, requires_grad=True)
+    out = model(c, torch.tensor(atype.reshape(1, -1), dtype=torch.int64), box=torch.tensor(box.reshape(1, 9)))
+    ea = out["atom_energy"].detach().numpy().reshape(-1)
+    assert np.abs(ea - e_atom_numpy).max() <= 1e-12 * np.abs(e_atom_numpy).max(), "PyTorch and NumPy backends disagree"
+    return dict(pt_energy=float(out["energy"].detach().numpy().reshape(-1)[0]),
+                pt_force=out["force"].detach().numpy().reshape(-1, 3).tolist(),
+                pt_virial=out["virial"].detach().numpy().reshape(9).tolist())
+
+
 def net_weights(net):
     out = []
     for layer in net.layers:
@@ -105,6 +130,9 @@ def main():
                       numneigh=(np.asarray(nlist)[0] >= 0).sum(1).tolist(),
                       atomic_energy=e_atom.tolist(), energy=float(e_atom.sum())),
     )
+    # Energy, forces and virial of the whole model from the reference's PyTorch backend (autograd): the NumPy objects
+    # above are handed over through the reference's own cross-backend serialisation.
+    data["expected"].update(pt_energy_force_virial(dp, fit, coord, atype, box, e_atom))
     # `dp compress` by the reference itself (deepmd/utils/tabulate.py + tabulate_math.py through
     # DescrptDPA1.enable_compression): table_info and the tabulated quintics.  The high-order coefficients come from
     # differences divided by stride^3..5 and carry amplified rounding noise (two builds of the reference differ in

@@ -111,7 +111,7 @@ def test_se_atten_composition_matches_reference_backend_cpu(dpa1):
     coord, atype, box = g.water_box(1, 0.0)
     lib = ocpu.CpuLib("reference" if ocpu.available("reference") else "port")
     lists = pipeline.build_lists(lib, coord, atype, box, model.cfg.rcut + 2.0)
-    e, _, _, ex = pipeline_atten.evaluate(lib, model, lists)
+    e, f_cpu, v_cpu, ex = pipeline_atten.evaluate(lib, model, lists)
     exp = dpa1["expected"]
     assert ((ex["nlist"] >= 0).sum(1) == np.array(exp["numneigh"])).all()
     got = _descriptor_rows(model, torch.as_tensor(ex["xyz"]), torch.as_tensor(atype.astype(np.int64))).numpy()
@@ -123,6 +123,10 @@ def test_se_atten_composition_matches_reference_backend_cpu(dpa1):
     # ... and the energies of the reference's EnergyFittingNet on top (mixed types, resnet_dt / idt, bias_atom_e)
     assert rel(ex["atom_energy"], exp["atomic_energy"]) <= 1e-12
     assert abs(e - exp["energy"]) <= 1e-12 * abs(exp["energy"])
+    # ... and energy / forces / virial of the reference's PyTorch backend (autograd through the uncompressed model)
+    assert abs(e - exp["pt_energy"]) <= 1e-12 * abs(exp["pt_energy"])
+    assert rel(f_cpu, exp["pt_force"]) <= 1e-10
+    assert rel(v_cpu, exp["pt_virial"]) <= 1e-10
 
 
 @pytest.mark.gpu
@@ -158,6 +162,8 @@ def test_se_atten_composition_matches_reference_backend_gpu(dpa1):
     assert rel(ae[0].reshape(-1), exp["atomic_energy"]) <= 1e-10
     assert abs(eg[0, 0] - exp["energy"]) <= 1e-10 * abs(exp["energy"])
     assert np.abs(fg[0].sum(0)).max() <= 1e-9 * np.abs(fg[0]).max()  # no net force
+    assert rel(fg[0], exp["pt_force"]) <= 1e-10   # the reference's own autograd forces and virial
+    assert rel(vg[0], exp["pt_virial"]) <= 1e-10
 
 
 def test_dp_compress_restatement_matches_reference_table(dpa1):
