@@ -21,6 +21,27 @@ from make_dpa1_strip import REF  # noqa: E402,F401
 import make_dpa1_strip as base  # noqa: E402
 
 
+FIT_NEURON = (16, 16, 16)
+BIAS_ATOM_E = (-1.5, 0.7)
+
+
+def fit_weights(t, dim_in, neuron=FIT_NEURON):
+    """Closed-form weights of the fitting net of centre type t: [(w, b, idt | None)] per hidden layer and (w, b) of
+    the head.  Used by this generator AND by tests/test_reference_model.py, so the fixture does not carry them."""
+    layers = []
+    n_in = dim_in
+    for k, n_out in enumerate(neuron):
+        i = np.arange(n_in, dtype=np.float64)[:, None]
+        j = np.arange(n_out, dtype=np.float64)[None, :]
+        w = np.sin(0.37 * i + 1.3 * j + 0.71 * t + k) / np.sqrt(n_in + n_out)
+        b = 0.1 * np.cos(j[0] + t + k)
+        idt = (0.1 + 0.01 * np.sin(j[0] + k)) if n_in == n_out else None
+        layers.append((w, b, idt))
+        n_in = n_out
+    i = np.arange(n_in, dtype=np.float64)[:, None]
+    return layers, (0.3 * np.cos(0.9 * i + t), np.array([0.05 * t]))
+
+
 def main():
     base.import_reference()
     from deepmd.dpmodel.descriptor.se_e2_a import DescrptSeA
@@ -54,6 +75,27 @@ def main():
     rows = [0, 1, 63, 64, 130, 191]
     descriptor = dict(rows=rows, values=desc[rows].tolist(), total=float(desc.sum()), total_sq=float((desc * desc).sum()),
                       numneigh=(np.asarray(nlist)[0] >= 0).sum(1).tolist())
+    # whole model: per-type energy fitting nets with CLOSED-FORM weights (fit_weights below: the test rebuilds them, the
+    # fixture need not store them), energy / forces / virial from the reference's PyTorch backend (autograd)
+    from deepmd.dpmodel.fitting.ener_fitting import EnergyFittingNet
+
+    fit = EnergyFittingNet(ntypes=len(sel), dim_descrpt=1600, neuron=list(FIT_NEURON), resnet_dt=True, mixed_types=False,
+                           seed=1, precision="float64")
+    fit.bias_atom_e[...] = np.array(BIAS_ATOM_E).reshape(-1, 1)
+    for t in range(len(sel)):
+        net = fit.nets[(t,)]
+        layers, head = fit_weights(t, 1600)
+        for layer, (w, b, idt) in zip(net.layers[:-1], layers):
+            assert layer.w.shape == w.shape and (layer.idt is None) == (idt is None)
+            layer.w[...] = w
+            layer.b[...] = b
+            if idt is not None:
+                layer.idt[...] = idt
+        net.layers[-1].w[...] = head[0]
+        net.layers[-1].b[...] = head[1]
+    e_atom = np.asarray(fit.call(desc[None], atype.reshape(1, -1).astype(np.int64))["energy"]).reshape(-1)
+    efv = base.pt_energy_force_virial(dp, fit, coord, atype, box, e_atom)
+    descriptor.update(atomic_energy=e_atom.tolist(), energy=float(e_atom.sum()), **efv)
     dp.enable_compression(0.9, 5, 0.01, 0.1, -1)
     tables = []
     for t in range(len(sel)):

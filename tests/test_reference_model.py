@@ -251,3 +251,67 @@ def test_se_a_descriptor_matches_reference_backend():
     assert rel(got[exp["rows"]], exp["values"]) <= 1e-12
     assert abs(got.sum() - exp["total"]) <= 1e-12 * abs(exp["total"])
     assert abs((got * got).sum() - exp["total_sq"]) <= 1e-12 * exp["total_sq"]
+
+
+def _sea_benchmark_model(device):
+    """Benchmark-size se_e2_a model with the fixture's embedding nets and the closed-form fitting nets of
+    tests/golden/make_sea_compress.py (fit_weights is imported from the generator: the fixture does not store them)."""
+    import importlib.util
+
+    from deepmd_kit_b200.model import SeAConfig, SeAModel
+
+    spec = importlib.util.spec_from_file_location("_make_sea_compress", os.path.join(ROOT, "tests", "golden",
+                                                                                      "make_sea_compress.py"))
+    with open(os.path.join(ROOT, "tests", "golden", "sea_compress.json")) as f:
+        d = json.load(f)
+    # only fit_weights / constants are needed: parse them without executing the generator's reference imports
+    src = open(spec.origin).read()
+    ns = {"np": np}
+    start = src.index("FIT_NEURON = ")
+    exec(src[start:src.index("def main():")], ns)
+    c = d["config"]
+    cfg = SeAConfig(ntypes=len(c["sel"]), sel=tuple(c["sel"]), rcut=c["rcut"], rcut_smth=c["rcut_smth"],
+                    neuron=tuple(c["neuron"]), axis_neuron=c["axis_neuron"], min_nbor_dist=c["min_nbor_dist"],
+                    fitting_neuron=tuple(ns["FIT_NEURON"]), fitting_resnet_dt=True)
+    nnei = sum(c["sel"])
+    davg = np.zeros((cfg.ntypes, nnei, 4))
+    dstd = np.ones((cfg.ntypes, nnei, 4))
+    for t, (a0, s0, s1) in enumerate(c["stats"]):
+        davg[t, :, 0], dstd[t, :, 0], dstd[t, :, 1:] = a0, s0, s1
+    fits = []
+    for t in range(cfg.ntypes):
+        layers, head = ns["fit_weights"](t, 1600)
+        fits.append(dict(layers=[[w, b, idt] for w, b, idt in layers], head=[head[0], head[1]]))
+    model = SeAModel(cfg, torch.float64, device, weights=dict(davg=davg, dstd=dstd, embed=d["embed"], fit=fits,
+                                                             bias_atom_e=list(ns["BIAS_ATOM_E"])))
+    return model, d["descriptor"]
+
+
+def test_se_a_benchmark_model_matches_reference_pytorch_backend_cpu():
+    """Energy, forces and virial of the reference's PyTorch backend (autograd, UNCOMPRESSED benchmark-size se_e2_a +
+    per-type fitting nets) on the 192-atom water frame, reproduced by the compressed CPU checker pipeline."""
+    g.load_package()
+    model, exp = _sea_benchmark_model("cpu")
+    coord, atype, box = g.water_box(1, 0.0)
+    lib = ocpu.CpuLib("reference" if ocpu.available("reference") else "port")
+    lists = pipeline.build_lists(lib, coord, atype, box, model.cfg.rcut + 2.0)
+    e, f, v, ex = pipeline.evaluate(lib, model, lists)
+    assert rel(ex["atom_energy"], exp["atomic_energy"]) <= 1e-12
+    assert abs(e - exp["pt_energy"]) <= 1e-12 * abs(exp["pt_energy"])
+    assert rel(f, exp["pt_force"]) <= 1e-10
+    assert rel(v, exp["pt_virial"]) <= 1e-10
+
+
+@pytest.mark.gpu
+def test_se_a_benchmark_model_matches_reference_pytorch_backend_gpu():
+    g.load_package()
+    from deepmd_kit_b200.model import DeepPotB200
+
+    model, exp = _sea_benchmark_model("cuda:0")
+    assert model.use_tc
+    coord, atype, box = g.water_box(1, 0.0)
+    e, f, v, ae, _ = DeepPotB200(model, skin=2.0).eval(coord.reshape(1, -1), box.reshape(1, 9), atype, atomic=True)
+    assert rel(ae[0].reshape(-1), exp["atomic_energy"]) <= 1e-10
+    assert abs(e[0, 0] - exp["pt_energy"]) <= 1e-10 * abs(exp["pt_energy"])
+    assert rel(f[0], exp["pt_force"]) <= 1e-10
+    assert rel(v[0], exp["pt_virial"]) <= 1e-10
