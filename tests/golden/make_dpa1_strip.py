@@ -46,7 +46,7 @@ def import_reference():
     return DescrptDPA1, extend_input_and_build_neighbor_list, EnergyFittingNet
 
 
-def pt_energy_force_virial(dp_descriptor, dp_fitting, coord, atype, box, e_atom_numpy):
+def pt_energy_force_virial(dp_descriptor, dp_fitting, coord, atype, box, e_atom_numpy, type_map=("O", "H")):
     """deepmd.pt EnergyModel with the given (NumPy-backend) descriptor and fitting net: E, F = -dE/dr, virial."""
     import torch
     from deepmd.pt.model.descriptor.base_descriptor import BaseDescriptor
@@ -54,8 +54,9 @@ def pt_energy_force_virial(dp_descriptor, dp_fitting, coord, atype, box, e_atom_
     from deepmd.pt.model.task.base_fitting import BaseFitting
 
     d_ser, f_ser = dp_descriptor.serialize(), dp_fitting.serialize()
-    params = {"type_map": ["O", "H"],
-              "descriptor": {"type": "se_e2_a", "sel": [4, 4], "rcut": 6.0, "rcut_smth": 0.5, "neuron": [2, 4], "axis_neuron": 2},
+    params = {"type_map": list(type_map),
+              "descriptor": {"type": "se_e2_a", "sel": [4] * len(type_map), "rcut": 6.0, "rcut_smth": 0.5, "neuron": [2, 4],
+                             "axis_neuron": 2},
               "fitting_net": {"neuron": [4], "resnet_dt": True}}
     model = get_model(params).to("cpu")  # a shell; descriptor and fitting net are replaced below
     model.atomic_model.descriptor = BaseDescriptor.deserialize(d_ser).to("cpu")

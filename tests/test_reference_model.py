@@ -315,3 +315,62 @@ def test_se_a_benchmark_model_matches_reference_pytorch_backend_gpu():
     assert abs(e[0, 0] - exp["pt_energy"]) <= 1e-10 * abs(exp["pt_energy"])
     assert rel(f[0], exp["pt_force"]) <= 1e-10
     assert rel(v[0], exp["pt_virial"]) <= 1e-10
+
+
+def _copper_model(device):
+    import importlib.util  # noqa: F401
+
+    from deepmd_kit_b200.model import SeAConfig, SeAModel
+
+    with open(os.path.join(ROOT, "tests", "golden", "copper_pt.json")) as f:
+        d = json.load(f)
+    src = open(os.path.join(ROOT, "tests", "golden", "make_sea_compress.py")).read()
+    ns = {"np": np}
+    exec(src[src.index("FIT_NEURON = "):src.index("def main():")], ns)
+    c = d["config"]
+    cfg = SeAConfig(ntypes=1, sel=tuple(c["sel"]), rcut=c["rcut"], rcut_smth=c["rcut_smth"], neuron=tuple(c["neuron"]),
+                    axis_neuron=c["axis_neuron"], min_nbor_dist=c["min_nbor_dist"], stats=[tuple(c["stats"][0])],
+                    fitting_neuron=tuple(ns["FIT_NEURON"]), fitting_resnet_dt=True)
+    nnei = sum(c["sel"])
+    a0, s0, s1 = c["stats"][0]
+    davg = np.zeros((1, nnei, 4))
+    dstd = np.ones((1, nnei, 4))
+    davg[0, :, 0], dstd[0, :, 0], dstd[0, :, 1:] = a0, s0, s1
+    layers, head = ns["fit_weights"](0, 1600)
+    fits = [dict(layers=[[w, b, idt] for w, b, idt in layers], head=[head[0], head[1]])]
+    model = SeAModel(cfg, torch.float64, device, weights=dict(davg=davg, dstd=dstd, embed=d["embed"], fit=fits,
+                                                             bias_atom_e=[ns["BIAS_ATOM_E"][0]]))
+    return model, d
+
+
+def test_copper_model_matches_reference_pytorch_backend_cpu():
+    """BASELINE config 3 model (one type, sel 512, rcut 8) on a 500-atom FCC box: forces of a near-perfect lattice are
+    sums with ~1000-fold cancellation (max |F| = 1.4e-4 against per-neighbour terms of 1e-1).  Reference = its PyTorch
+    backend (autograd, uncompressed)."""
+    g.load_package()
+    model, d = _copper_model("cpu")
+    exp, c = d["expected"], d["config"]
+    coord, atype, box = g.copper_box(c["ncell"], c["jitter"])
+    lib = ocpu.CpuLib("reference" if ocpu.available("reference") else "port")
+    lists = pipeline.build_lists(lib, coord, atype, box, model.cfg.rcut + 2.0)
+    e, f, v, ex = pipeline.evaluate(lib, model, lists)
+    assert ((ex["nlist"] >= 0).sum(1) == np.array(exp["numneigh"])).all()
+    assert rel(ex["atom_energy"], exp["atomic_energy"]) <= 1e-12
+    assert abs(e - exp["pt_energy"]) <= 1e-12 * abs(exp["pt_energy"])
+    assert rel(f, exp["pt_force"]) <= 1e-10
+    assert rel(v, exp["pt_virial"]) <= 1e-10
+
+
+@pytest.mark.gpu
+def test_copper_model_matches_reference_pytorch_backend_gpu():
+    g.load_package()
+    from deepmd_kit_b200.model import DeepPotB200
+
+    model, d = _copper_model("cuda:0")
+    exp, c = d["expected"], d["config"]
+    coord, atype, box = g.copper_box(c["ncell"], c["jitter"])
+    e, f, v, ae, _ = DeepPotB200(model, skin=2.0).eval(coord.reshape(1, -1), box.reshape(1, 9), atype, atomic=True)
+    assert rel(ae[0].reshape(-1), exp["atomic_energy"]) <= 1e-10
+    assert abs(e[0, 0] - exp["pt_energy"]) <= 1e-10 * abs(exp["pt_energy"])
+    assert rel(f[0], exp["pt_force"]) <= 1e-10
+    assert rel(v[0], exp["pt_virial"]) <= 1e-10
