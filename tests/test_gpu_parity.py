@@ -542,8 +542,8 @@ def test_copy_coord_golden(ops):
 
 @pytest.mark.parametrize("dtype", [np.float64, np.float32])
 def test_op_prod_env_mat_a_modes(ops, olib, dtype):
-    """torch.ops.deepmd.prod_env_mat_a with the mesh encodings: PBC self-built list
-    (len 6) and pointer-free inline list (len > 16), against the oracle pipeline."""
+    """torch.ops.deepmd.prod_env_mat_a with ALL mesh encodings: PBC self-built list (len 6), pointer-free
+    inline list (len > 16), raw host pointers (len 16, the LAMMPS hand-off) and no PBC (len 0), against the oracle."""
     coord, atype, box = water_like_box(ncopy=2, seed=12, jitter=0.1, dtype=dtype)
     nloc = len(atype)
     sec = [0, 46, 138]
@@ -580,6 +580,34 @@ def test_op_prod_env_mat_a_modes(ops, olib, dtype):
     close(N(em2), w[0], dtype)
     close(N(dv2), w[1], dtype)
     close(N(rij2), w[2], dtype)
+    # length 16: the LAMMPS hand-off, raw HOST pointers to ilist / numneigh / firstneigh packed as int32 pairs
+    # (source/op/tf/prod_env_mat_multi_device.cc:529-552: mesh[1] = inum, mesh[4..5], [8..9], [12..13] = pointers)
+    import ctypes as C
+
+    ilist_h = np.arange(nloc, dtype=np.int32)
+    nn_h = np.ascontiguousarray(nn, dtype=np.int32)
+    rows_h = [np.ascontiguousarray(neigh[off[i]:off[i + 1]], dtype=np.int32) for i in range(nloc)]
+    first_h = (C.POINTER(C.c_int) * nloc)(*[r.ctypes.data_as(C.POINTER(C.c_int)) for r in rows_h])
+    mesh16 = np.zeros(16, np.int32)
+    mesh16[1] = nloc
+    for k, ptr in ((4, ilist_h.ctypes.data), (8, nn_h.ctypes.data), (12, C.addressof(first_h))):
+        mesh16[k:k + 2] = np.frombuffer(np.uint64(ptr).tobytes(), dtype=np.int32)
+    em3, dv3, rij3, nl3 = torch.ops.deepmd.prod_env_mat_a(T(ext_c).reshape(1, -1), T(ext_t).reshape(1, -1), nat2,
+                                                          T(box).reshape(1, 9), torch.from_numpy(mesh16), T(avg), T(std),
+                                                          0.0, 6.0, 0.5, [46, 92], [0, 0])
+    assert np.array_equal(N(nl3).reshape(nloc, -1), w[3])
+    assert torch.equal(em3, em2) and torch.equal(dv3, dv2) and torch.equal(rij3, rij2)
+    # length 0: no PBC, the op builds the list over the atoms it is given (an isolated cluster)
+    wn, wrows = olib.build_nlist(coord, nloc, 6.0)
+    woff, wneigh = ocpu.dense_to_csr(wrows, wn)
+    w0 = olib.prod_env_mat_a(coord, atype, woff, wneigh, avg, std, nloc, 6.0, 0.5, sec)
+    em0, dv0, rij0, nl0 = torch.ops.deepmd.prod_env_mat_a(T(coord).reshape(1, -1), T(atype).reshape(1, -1), nat,
+                                                          T(box).reshape(1, 9), torch.zeros(0, dtype=torch.int32), T(avg),
+                                                          T(std), 0.0, 6.0, 0.5, [46, 92], [0, 0])
+    assert np.array_equal(N(nl0).reshape(nloc, -1), w0[3])
+    close(N(em0), w0[0], dtype)
+    close(N(dv0), w0[1], dtype)
+    close(N(rij0), w0[2], dtype)
 
 
 # ------------------------------------------------------------------ descriptor contraction ----
