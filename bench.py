@@ -39,7 +39,7 @@ def parse():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--dtype", default="f64", choices=["f64", "f32"])
-    ap.add_argument("--workload", default="water", choices=["water", "copper", "se_atten"],
+    ap.add_argument("--workload", default="water", choices=["water", "copper", "se_atten", "dpa1_attn"],
                     help="water: BASELINE config 2 (the metric's configuration); copper: config 3 (FCC, sel 512, rcut 8; "
                          "--ncopy = conventional cells per axis, 100 = 4 M atoms; 1 GPU only, evaluated in atom slabs); "
                          "se_atten: config 5 (DPA-1 se_atten_v2 strip / smooth, attn_layer 0, sel 120; --ncopy 14 = 526 848 atoms)")
@@ -250,9 +250,13 @@ def run_ours(args):
         from deepmd_kit_b200.atten import SeAttenConfig, SeAttenModel
 
         cfg = SeAttenConfig()
+    elif args.workload == "dpa1_attn":  # DPA-1 with its attention layers: not compressible upstream
+        from deepmd_kit_b200.atten import SeAttenConfig, SeAttenModel
+
+        cfg = SeAttenConfig(attn_layer=2)
     else:
         cfg = SeAConfig()
-    model = SeAttenModel(cfg, dtype, dev) if args.workload == "se_atten" else SeAModel(cfg, dtype, dev)
+    model = SeAttenModel(cfg, dtype, dev) if args.workload in ("se_atten", "dpa1_attn") else SeAModel(cfg, dtype, dev)
     esz = 8 if args.dtype == "f64" else 4
 
     if world == 1:
@@ -375,6 +379,10 @@ def run_ours(args):
                 (f"DPA-1 se_atten_v2 (strip, smooth, attn_layer 0, sel 120) compressed water, {natoms_total}-atom box "
                  f"({args.ncopy}^3 replicas of the 192-atom frame per GPU, jitter {args.jitter} A), {args.dtype}, {world}xB200")
                 if args.workload == "se_atten" else
+                (f"DPA-1 se_atten_v2 with attention (strip, smooth, attn_layer 2, attn 128, dotr, sel 120; tabulated "
+                 f"embedding + attention layers) water, {natoms_total}-atom box ({args.ncopy}^3 replicas of the 192-atom "
+                 f"frame per GPU, jitter {args.jitter} A), {args.dtype}, {world}xB200")
+                if args.workload == "dpa1_attn" else
                 (f"se_e2_a compressed copper FCC, {natoms_total} atoms ({args.ncopy}^3 cells, a0 3.615 A, jitter 0.05 A), "
                  f"{args.dtype}, {world}xB200, evaluated in "
                  f"{1 if dp.state.chunks is None else len(dp.state.chunks)} atom slab(s) per GPU"),
@@ -412,7 +420,9 @@ def per_kernel(args, torch, ops, model, dp, step, L, dev, nloc, esz):
              "halo_unpack_add", "fit_gemm_i8", "fit_head", "fit_slice_rows", "tabulate_fusion_se_a",
              "tabulate_fusion_se_a_grad", "split_i8_rows", "tabulate_fusion_se_atten_gate",
              "tabulate_fusion_se_atten_gate_grad", "tabulate_fusion_se_atten_gate_desc", "fit_slice_cols",
-             "se_atten_gate_scalars", "prod_force_virial_a_pair"]
+             "se_atten_gate_scalars", "prod_force_virial_a_pair", "se_atten_embed", "se_atten_embed_grad",
+             "se_atten_rhat", "se_atten_rhat_grad", "attn_qkv_normalize", "attn_qkv_normalize_grad", "attn_weights",
+             "attn_weights_grad", "attn_residual_layernorm", "attn_residual_layernorm_grad"]
     acc = {}
     orig = {}
 
@@ -436,7 +446,15 @@ def per_kernel(args, torch, ops, model, dp, step, L, dev, nloc, esz):
         orig_fit_split = model.energy_and_dy_split
         model.energy_and_dy = wrap(umbrella, orig_fit)
         model.energy_and_dy_split = wrap(umbrella, orig_fit_split)
-    nsteps = 10
+    # attention model: the dense products of the layers run on the library; one row for all of them
+    from deepmd_kit_b200 import atten as atten_mod
+
+    gemm_row = "attn_library_gemm (cuBLAS fp64 / fp32 through torch: in_proj, q k^T, A v, out_proj and transposes)"
+    gemm_orig = {n: getattr(atten_mod, n) for n in ("_addmm", "_bmm", "_mm")}
+    if args.workload == "dpa1_attn":
+        for n, fn in gemm_orig.items():
+            setattr(atten_mod, n, wrap(gemm_row, fn))
+    nsteps = 10 if args.workload != "dpa1_attn" else 3
     graph_mode = getattr(dp, "use_graph", False)
     dp.use_graph = False  # the instrumented pass needs real launches (events cannot be timed inside a graph)
     try:
@@ -450,6 +468,8 @@ def per_kernel(args, torch, ops, model, dp, step, L, dev, nloc, esz):
     finally:
         for n in names:
             setattr(ops, n, orig[n])
+        for n, fn in gemm_orig.items():
+            setattr(atten_mod, n, fn)
         if has_fit:
             model.energy_and_dy = orig_fit
             model.energy_and_dy_split = orig_fit_split
@@ -503,6 +523,20 @@ def per_kernel(args, torch, ops, model, dp, step, L, dev, nloc, esz):
         alg["prod_force_virial_a_pair"] = ("hbm", (19 * nnei * F + 4 * nnei) + 2 * nnei * F + 3 * F)
         alg["se_atten_gate_scalars"] = ("hbm", nnei * (4 + 3 * F) + nnei * (4 + 2 * F))
         alg["tabulate_fusion_se_atten_gate_grad"] = ("fp", 42 * npr * M)
+    if args.workload == "dpa1_attn":
+        nl_, h_ = cfg.attn_layer, cfg.attn
+        alg["se_atten_embed"] = ("hbm", 3 * nnei * M * F + nnei * (2 * F + 4))
+        alg["se_atten_embed_grad"] = ("hbm", 3 * nnei * M * F + nnei * (4 * F + 4))
+        alg["attn_qkv_normalize"] = ("hbm", nl_ * 2 * nnei * 3 * h_ * F)
+        alg["attn_qkv_normalize_grad"] = ("hbm", nl_ * 3 * nnei * 3 * h_ * F)
+        alg["attn_weights"] = ("hbm", nl_ * 3 * nnei * nnei * F)
+        alg["attn_weights_grad"] = ("hbm", nl_ * 4 * nnei * nnei * F)
+        alg["attn_residual_layernorm"] = ("hbm", nl_ * 4 * nnei * M * F)
+        alg["attn_residual_layernorm_grad"] = ("hbm", nl_ * 3 * nnei * M * F)
+        alg["prod_force_virial_a_pair"] = ("hbm", (19 * nnei * F + 4 * nnei) + 2 * nnei * F + 3 * F)
+        alg["se_atten_gate_scalars"] = ("hbm", nnei * (4 + 3 * F) + nnei * (4 + 2 * F))
+        # forward products of a layer; the backward has two products per forward one
+        alg[gemm_row] = ("fp", nl_ * 3 * 2.0 * nnei * (M * 3 * h_ + 2 * nnei * h_ + h_ * M))
     table = {}
     total = 0.0
     for n, evs in acc.items():
@@ -510,7 +544,7 @@ def per_kernel(args, torch, ops, model, dp, step, L, dev, nloc, esz):
         med = times[len(times) // 2]
         # median call x calls per step (robust against allocator hiccups); kernels with several call shapes per
         # step (the six GEMMs of the fitting net) are summed instead
-        ms = sum(times) / nsteps if n.startswith("fit_") else med * len(evs) / nsteps
+        ms = sum(times) / nsteps if n.startswith(("fit_", "attn_library")) else med * len(evs) / nsteps
         table[n] = {"ms_per_step": ms, "calls_per_step": len(evs) / nsteps, "ms_min_call": times[0],
                     "ms_max_call": times[-1]}
         if n == umbrella:
@@ -543,7 +577,7 @@ def per_kernel(args, torch, ops, model, dp, step, L, dev, nloc, esz):
         for n, row in table.items():
             if n in limiter:
                 row["ncu_limiter"] = limiter[n]
-    ours = {n: r for n, r in table.items() if "bound" in r}
+    ours = {n: r for n, r in table.items() if "bound" in r and not n.startswith("attn_library")}  # (library row: reported, not ours)
     top = max(ours, key=lambda n: ours[n]["ms_per_step"]) if ours else None
     roofline = None
     if top:

@@ -57,6 +57,16 @@ _SIGS = {
     "mlp_tanh_bwd_split_{s}": "pp l pp l i p p",
     "tabulate_fusion_se_a_desc_{s}": "ppp pli pl iiiii i d p i p l i p i p",
     "tabulate_fusion_se_a_grad_fx_{s}": "pp pp pli pl p iiii i p",
+    "se_atten_embed_{s}": "ppp pp p l pp p l i p",
+    "se_atten_embed_grad_{s}": "p l p ppp pp p l i p",
+    "se_atten_rhat_{s}": "ppp l p",
+    "se_atten_rhat_grad_{s}": "pppp l p",
+    "attn_qkv_normalize_{s}": "pp l i d i p",
+    "attn_qkv_normalize_grad_{s}": "ppp l i d i p",
+    "attn_weights_{s}": "pp ppp l i d i p",
+    "attn_weights_grad_{s}": "ppp pp ppp l i d i p",
+    "attn_residual_layernorm_{s}": "ppp ppp l i d p",
+    "attn_residual_layernorm_grad_{s}": "p pppp l i p",
     "halo_pack_{s}": "pppp i p",
     "halo_unpack_add_{s}": "ppp i p",
 }

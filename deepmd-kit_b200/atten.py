@@ -49,6 +49,16 @@ class SeAttenConfig:
     stride1: float = 0.1
     extrapolate: float = 5.0
     min_nbor_dist: float = 0.9
+    # neighbour-gated self-attention on the per-neighbour embedding (DPA-1 proper; 0 = the compressible model).
+    # Reference defaults of deepmd/pt/model/descriptor/dpa1.py: attn 128, attn_dotr, normalised q / k / v, one head,
+    # scaling (attn * scaling_factor)^-1/2, smooth shift 20, layer-norm eps 1e-5.
+    attn_layer: int = 0
+    attn: int = 128
+    attn_dotr: bool = True
+    attn_normalize: bool = True
+    scaling_factor: float = 1.0
+    ln_eps: float = 1e-5
+    attnw_shift: float = 20.0
 
     @property
     def sel(self):
@@ -93,6 +103,20 @@ def switch_and_derivative(r: torch.Tensor, rmin: float, rmax: float):
     sw = torch.where(r < rmin, torch.ones_like(sw), torch.where(inside, sw, torch.zeros_like(sw)))
     dsw = torch.where(inside, dsw, torch.zeros_like(dsw))
     return sw, dsw
+
+
+# The dense products of the attention layers go to the library (cuBLAS through torch): plain GEMMs.  They are module
+# level names so that bench.py can time them as one row ("attn_library_gemm") next to the dpb200 stage kernels.
+def _addmm(bias, a, b):
+    return torch.addmm(bias, a, b)
+
+
+def _bmm(a, b):
+    return torch.bmm(a, b)
+
+
+def _mm(a, b):
+    return torch.mm(a, b)
 
 
 class SeAttenModel:
@@ -177,6 +201,24 @@ class SeAttenModel:
         self.coef_flags = 0
         if self.device.type == "cuda" and dtype == torch.float64 and os.environ.get("DPB200_TAB_COMPRESS", "1") != "0":
             self.coef_flags = int(ops.compressed_coef_flags(self.table64, self.info))
+        # attention layers: in_proj [M, 3 attn] + bias, out_proj [attn, M] + bias, layer norm scale / shift [M]
+        # (weights["attn"] = [{in_w, in_b, out_w, out_b, ln_w, ln_b}] from the reference's NeighborGatedAttention)
+        self.attn_layers = []
+        self.attn_scaling = float((cfg.attn * cfg.scaling_factor) ** -0.5)
+        self.attn_chunk = 4096  # centre atoms per slab: ~2 MB of saved activations per atom and layer pair in fp64
+        for li in range(cfg.attn_layer):
+            if weights is not None and "attn" in weights:
+                lay = {k: torch.as_tensor(np.asarray(v, np.float64)) for k, v in weights["attn"][li].items()}
+            else:
+                ws_, bs_ = _mlp_init([self.M, 3 * cfg.attn], cfg.seed + 31 + 2 * li)
+                wo_, bo_ = _mlp_init([cfg.attn, self.M], cfg.seed + 32 + 2 * li)
+                lay = dict(in_w=ws_[0], in_b=bs_[0], out_w=wo_[0], out_b=bo_[0],
+                           ln_w=torch.ones(self.M, dtype=torch.float64), ln_b=torch.zeros(self.M, dtype=torch.float64))
+            assert lay["in_w"].shape == (self.M, 3 * cfg.attn) and lay["out_w"].shape == (cfg.attn, self.M)
+            lay = {k: v.to(self.device, dtype).contiguous() for k, v in lay.items()}
+            lay["in_wt"] = lay["in_w"].t().contiguous()
+            lay["out_wt"] = lay["out_w"].t().contiguous()
+            self.attn_layers.append(lay)
         self.nslice = 6 if dtype == torch.float64 else 4  # int8 digit slices of the fitting-net operands
         self.use_tc = bool(self.device.type == "cuda" and self.fit.prepare_tc(self.nslice))
         # lower bound of the descriptor rows' exponent so that the appended type embedding fits: |tebd| < 2^(E-1)
@@ -217,6 +259,8 @@ class SeAttenModel:
                  atom_virial=False, fused=True, type_inv=None):
         """One force evaluation on an extended system: (E, force[n_out, 3], virial[9], extras)."""
         cfg = self.cfg
+        if cfg.attn_layer > 0:
+            return self._evaluate_attn(ext_coord, ext_type, numneigh, rows, mapping, nloc, atom_virial)
         nall = ext_type.numel()
         nnei, M = cfg.nnei, self.M
         f_type = torch.zeros_like(ext_type)  # one section: the list is ordered by distance only
@@ -323,3 +367,108 @@ class SeAttenModel:
                 av.index_add_(0, idx[a * nnei:b * nnei], w.reshape(-1, 9))
             av = av.reshape(-1)
         return e_atom.sum(), force, virial, dict(atom_energy=e_atom, atom_virial=av, nlist=nlist)
+
+    # ---------------------------------------------------------------------------------------- attention layers
+    def attention_forward(self, x, sw, rhat, keep=True):
+        """NeighborGatedAttention (se_atten.py:1058-1447) on x [B, nnei, M]: per layer in_proj -> normalised q, k, v
+        -> gated softmax weights -> A v -> out_proj -> residual + layer norm.  Dense products on the library, the stages
+        between them in csrc/attn_layers.cu.  Returns (x_out, saved activations for attention_backward)."""
+        cfg = self.cfg
+        B, n, M = x.shape
+        h = cfg.attn
+        saved = []
+        for lay in self.attn_layers:
+            qkv = _addmm(lay["in_b"], x.view(-1, M), lay["in_w"])
+            inv = ops.attn_qkv_normalize(qkv, h, self.attn_scaling, cfg.attn_normalize)
+            q3 = qkv.view(B, n, 3 * h)
+            S = _bmm(q3[:, :, :h], q3[:, :, h:2 * h].transpose(1, 2))
+            P, A = ops.attn_weights(S, sw, rhat, cfg.attnw_shift, cfg.attn_dotr)
+            O = _bmm(A, q3[:, :, 2 * h:])
+            Y = _addmm(lay["out_b"], O.view(-1, h), lay["out_w"])
+            del O
+            xn, zhat, rstd = ops.attn_residual_layernorm(x.view(-1, M), Y, lay["ln_w"], lay["ln_b"], cfg.ln_eps)
+            if keep:
+                saved.append((qkv, inv, S, P, A, zhat, rstd))
+            x = xn.view(B, n, M)
+        return x, saved
+
+    def attention_backward(self, dx, saved, sw, rhat, d_sw, d_rhat):
+        """Transpose of attention_forward: dE/d(x_out) [B, nnei, M] -> dE/d(x_in); dE/d(sw) and dE/d(rhat) of all
+        layers are accumulated into d_sw / d_rhat."""
+        cfg = self.cfg
+        B, n, M = dx.shape
+        h = cfg.attn
+        for lay in reversed(self.attn_layers):
+            qkv, inv, S, P, A, zhat, rstd = saved.pop()
+            q3 = qkv.view(B, n, 3 * h)
+            dz = ops.attn_residual_layernorm_grad(dx.reshape(-1, M), zhat, rstd, lay["ln_w"])  # = dY and the skip
+            dO = _mm(dz, lay["out_wt"]).view(B, n, h)
+            dqkv = torch.empty((B, n, 3 * h), dtype=dx.dtype, device=dx.device)
+            dA = _bmm(dO, q3[:, :, 2 * h:].transpose(1, 2))
+            dqkv[:, :, 2 * h:] = _bmm(A.transpose(1, 2), dO)
+            del dO, A
+            dS = ops.attn_weights_grad(dA, P, S, sw, rhat, d_sw, d_rhat, cfg.attnw_shift, cfg.attn_dotr)
+            dqkv[:, :, :h] = _bmm(dS, q3[:, :, h:2 * h])
+            dqkv[:, :, h:2 * h] = _bmm(dS.transpose(1, 2), q3[:, :, :h])
+            del dS, dA, P, S
+            ops.attn_qkv_normalize_grad(dqkv, qkv, inv, h, self.attn_scaling, cfg.attn_normalize)
+            dx = _addmm(dz, dqkv.view(-1, 3 * h), lay["in_wt"]).view(B, n, M)
+            del dqkv, qkv, dz
+        return dx
+
+    def _evaluate_attn(self, ext_coord, ext_type, numneigh, rows, mapping, nloc, atom_virial=False):
+        """attn_layer > 0: the per-neighbour embedding is materialised slab by slab (attn_chunk centre atoms): table ->
+        g2 -> attention layers -> moment -> descriptor -> fitting net -> and all the way back inside the slab, so
+        that only net_deriv [nloc, nnei, 4] and dE/d(sw) [nloc, nnei] outlive it."""
+        cfg = self.cfg
+        nall = ext_type.numel()
+        nnei, M = cfg.nnei, self.M
+        f_type = torch.zeros_like(ext_type)
+        em, dv, rij, nlist = ops.prod_env_mat_a(ext_coord.reshape(-1), ext_type, numneigh, rows, self.davg, self.dstd, nloc,
+                                                nall, cfg.rcut, cfg.rcut_smth, cfg.sec, f_type=f_type)
+        em3 = em.reshape(nloc, nnei, 4)
+        inv = 1.0 / nnei
+        ctype = ext_type[:nloc].to(torch.int64)
+        ctype_e = torch.where(ctype < 0, torch.full_like(ctype, cfg.ntypes), ctype)
+        pair32, sw, dswr = ops.se_atten_gate_scalars(nlist, ext_type, rij, nloc, nnei, cfg.ntypes, cfg.rcut_smth, cfg.rcut)
+        e_atom = torch.empty(nloc, dtype=self.dtype, device=em.device)
+        net_deriv = torch.empty((nloc, nnei, 4), dtype=self.dtype, device=em.device)
+        q_sw = torch.zeros((nloc, nnei), dtype=self.dtype, device=em.device)
+        for a in range(0, nloc, self.attn_chunk):
+            b = min(nloc, a + self.attn_chunk)
+            em_c, sw_c, pair_c = em3[a:b], sw[a:b], pair32[a:b]
+            x0, gs, dgs = ops.se_atten_embed(self.table, self.info, em_c, self.tt_full, pair_c, sw_c, M)
+            rhat, rinv = ops.se_atten_rhat(em_c)
+            x, saved = self.attention_forward(x0, sw_c, rhat)
+            del x0
+            xyz = _bmm(em_c.transpose(1, 2), x)  # [B, 4, M], the unscaled moment (se_atten.py:1012)
+            g1 = torch.zeros((b - a, self.dim_in), dtype=self.dtype, device=em.device)
+            g1[:, :self.dim_d] = ops.se_a_descriptor(xyz, cfg.axis_neuron, inv)
+            g1[:, self.dim_d:self.dim_d + cfg.tebd_dim] = self.tebd.index_select(0, ctype_e[a:b])
+            if self.use_tc:
+                xs, ex = ops.split_i8_rows(g1.to(torch.float64), self.nslice)
+                e, gd = self.fit.forward_backward_tc(xs, ex, b - a, grad_cols=self.dim_d)
+                del xs
+            else:
+                e, gd = self.fit.forward_backward(g1)
+            del g1
+            e_atom[a:b] = e + self.bias_atom_e.index_select(0, ctype_e[a:b].clamp_max(cfg.ntypes - 1))
+            dy = ops.se_a_descriptor_grad(gd, xyz, cfg.axis_neuron, inv) if gd.shape[1] == self.dim_d \
+                else ops.se_a_descriptor_grad(gd[:, :self.dim_d].contiguous(), xyz, cfg.axis_neuron, inv)
+            dy = dy.to(self.dtype)
+            del gd
+            d_em = _bmm(x, dy.transpose(1, 2)).contiguous()  # through the moment's em factor
+            dx = _bmm(em_c, dy)
+            del x, dy
+            d_rhat = torch.zeros((b - a, nnei, 3), dtype=self.dtype, device=em.device)
+            dx = self.attention_backward(dx, saved, sw_c, rhat, q_sw[a:b], d_rhat)
+            ops.se_atten_embed_grad(d_em, q_sw[a:b], dx, gs, dgs, self.tt_full, pair_c, sw_c)
+            ops.se_atten_rhat_grad(d_em, d_rhat, rhat, rinv)
+            net_deriv[a:b] = d_em
+            del dx, gs, dgs, d_em, d_rhat
+        if mapping is not None:
+            ops.use_nlist_map(nlist, mapping)
+        n_out = nloc if mapping is not None else nall
+        force, virial, av = ops.prod_force_virial_a_pair(net_deriv.reshape(nloc, -1), dv, rij, nlist, q_sw, dswr, nloc,
+                                                         n_out, nnei, atom_virial=atom_virial)
+        return e_atom.sum(), force.reshape(-1, 3), virial, dict(atom_energy=e_atom, atom_virial=av, nlist=nlist)

@@ -560,6 +560,117 @@ def se_atten_gate_scalars(nlist, ext_type, rij, nloc, nnei, ntypes, rcut_smth, r
     return pair, sw, dswr
 
 
+# ---- DPA-1 attention layers (csrc/attn_layers.cu): the stages between the dense products of a layer ------------
+def se_atten_embed(table, table_info, em, tt_full, pair, sw, last_layer_size):
+    """em [natoms, nnei, 4] -> (x0, g_s, g_s') [natoms, nnei, M]: the tabulated geometric embedding of every neighbour
+    and x0 = g_s (1 + tt_full[pair] sw) (se_atten.py:979-1003)."""
+    dev = _need_cuda(("table", table), ("em", em), ("tt_full", tt_full), ("pair", pair), ("sw", sw))
+    s = _suffix(em)
+    table, em, tt_full, pair, sw = _c(table, em.dtype), _c(em), _c(tt_full, em.dtype), _c(pair, torch.int32), _c(sw, em.dtype)
+    info = _info_host(table_info, em.dtype)
+    n, nnei = em.shape[0], em.shape[1]
+    M = int(last_layer_size)
+    x0 = torch.empty((n, nnei, M), dtype=em.dtype, device=dev)
+    gs, dgs = torch.empty_like(x0), torch.empty_like(x0)
+    lib().call("se_atten_embed_" + s, _p(x0), _p(gs), _p(dgs), _p(table), info.data_ptr(), _p(em), 4, _p(tt_full),
+               _p(pair), _p(sw), n * nnei, M, _stream(dev))
+    return x0, gs, dgs
+
+
+def se_atten_embed_grad(d_em, d_sw, dx0, gs, dgs, tt_full, pair, sw):
+    """Accumulates dE/ds into d_em[:, :, 0] and dE/d(sw) into d_sw (both in place)."""
+    dev = _need_cuda(("d_em", d_em), ("dx0", dx0))
+    s = _suffix(dx0)
+    assert d_em.is_contiguous() and d_sw.is_contiguous()
+    n, nnei, M = dx0.shape
+    lib().call("se_atten_embed_grad_" + s, _p(d_em), 4, _p(d_sw), _p(_c(dx0)), _p(gs), _p(dgs), _p(_c(tt_full, dx0.dtype)),
+               _p(_c(pair, torch.int32)), _p(_c(sw, dx0.dtype)), n * nnei, M, _stream(dev))
+
+
+def se_atten_rhat(em):
+    """em [natoms, nnei, 4] -> (rhat [natoms, nnei, 3] = normalize(em[..., 1:4]), rinv [natoms, nnei])."""
+    dev = _need_cuda(("em", em))
+    s = _suffix(em)
+    em = _c(em)
+    n, nnei = em.shape[0], em.shape[1]
+    rhat = torch.empty((n, nnei, 3), dtype=em.dtype, device=dev)
+    rinv = torch.empty((n, nnei), dtype=em.dtype, device=dev)
+    lib().call("se_atten_rhat_" + s, _p(rhat), _p(rinv), _p(em), n * nnei, _stream(dev))
+    return rhat, rinv
+
+
+def se_atten_rhat_grad(d_em, d_rhat, rhat, rinv):
+    """d_em[..., 1:4] += d normalize / d em applied to d_rhat (in place)."""
+    dev = _need_cuda(("d_em", d_em), ("d_rhat", d_rhat))
+    assert d_em.is_contiguous()
+    lib().call("se_atten_rhat_grad_" + _suffix(d_em), _p(d_em), _p(_c(d_rhat)), _p(rhat), _p(rinv), rinv.numel(),
+               _stream(dev))
+
+
+def attn_qkv_normalize(qkv, hidden, q_scale, normalize=True):
+    """qkv [rows, 3 * hidden] in place -> inv_norm [rows, 3] (se_atten.py:1368-1373)."""
+    dev = _need_cuda(("qkv", qkv))
+    assert qkv.is_contiguous()
+    rows = qkv.numel() // (3 * hidden)
+    inv = torch.empty((rows, 3), dtype=qkv.dtype, device=dev)
+    lib().call("attn_qkv_normalize_" + _suffix(qkv), _p(qkv), _p(inv), rows, int(hidden), float(q_scale),
+               int(bool(normalize)), _stream(dev))
+    return inv
+
+
+def attn_qkv_normalize_grad(d_qkv, qkv_hat, inv, hidden, q_scale, normalize=True):
+    dev = _need_cuda(("d_qkv", d_qkv), ("qkv_hat", qkv_hat))
+    assert d_qkv.is_contiguous() and qkv_hat.is_contiguous()
+    rows = d_qkv.numel() // (3 * hidden)
+    lib().call("attn_qkv_normalize_grad_" + _suffix(d_qkv), _p(d_qkv), _p(qkv_hat), _p(inv), rows, int(hidden),
+               float(q_scale), int(bool(normalize)), _stream(dev))
+
+
+def attn_weights(S, sw, rhat, shift=20.0, dotr=True):
+    """S [natoms, nnei, nnei] -> (P, A): gated softmax and the attention weights (se_atten.py:1386-1416)."""
+    dev = _need_cuda(("S", S), ("sw", sw), ("rhat", rhat))
+    S = _c(S)
+    natoms, n = S.shape[0], S.shape[1]
+    P, A = torch.empty_like(S), torch.empty_like(S)
+    lib().call("attn_weights_" + _suffix(S), _p(P), _p(A), _p(S), _p(_c(sw, S.dtype)), _p(_c(rhat, S.dtype)), natoms, n,
+               float(shift), int(bool(dotr)), _stream(dev))
+    return P, A
+
+
+def attn_weights_grad(dA, P, S, sw, rhat, d_sw, d_rhat, shift=20.0, dotr=True):
+    """dA -> dS, written over dA; accumulates into d_sw [natoms, nnei] and d_rhat [natoms, nnei, 3]."""
+    dev = _need_cuda(("dA", dA), ("P", P), ("S", S))
+    assert dA.is_contiguous() and d_sw.is_contiguous() and d_rhat.is_contiguous()
+    natoms, n = S.shape[0], S.shape[1]
+    lib().call("attn_weights_grad_" + _suffix(S), _p(dA), _p(d_sw), _p(d_rhat), _p(dA), _p(P), _p(S), _p(_c(sw, S.dtype)),
+               _p(_c(rhat, S.dtype)), natoms, n, float(shift), int(bool(dotr)), _stream(dev))
+    return dA
+
+
+def attn_residual_layernorm(x, y, gamma, beta, eps):
+    """LayerNorm(x + y) * gamma + beta over the last axis; y is overwritten with the normalised rows.
+    Returns (out, zhat (= y's storage), rstd)."""
+    dev = _need_cuda(("x", x), ("y", y))
+    assert x.is_contiguous() and y.is_contiguous()
+    C_ = x.shape[-1]
+    rows = x.numel() // C_
+    out = torch.empty_like(x)
+    rstd = torch.empty(rows, dtype=x.dtype, device=dev)
+    lib().call("attn_residual_layernorm_" + _suffix(x), _p(out), _p(y), _p(rstd), _p(x), _p(_c(gamma, x.dtype)),
+               _p(_c(beta, x.dtype)), rows, C_, float(eps), _stream(dev))
+    return out, y, rstd
+
+
+def attn_residual_layernorm_grad(dout, zhat, rstd, gamma):
+    dev = _need_cuda(("dout", dout), ("zhat", zhat))
+    dout = _c(dout)
+    C_ = dout.shape[-1]
+    dz = torch.empty_like(dout)
+    lib().call("attn_residual_layernorm_grad_" + _suffix(dout), _p(dz), _p(dout), _p(zhat), _p(rstd),
+               _p(_c(gamma, dout.dtype)), rstd.numel(), C_, _stream(dev))
+    return dz
+
+
 def prod_force_grad_a(grad, in_deriv, nlist, nloc, nnei, nframes=1, ngrad=None):
     """deepmd::prod_force_grad_a_gpu (source/lib/include/prod_force_grad.h:26-33): gradient of prod_force_a with
     respect to net_deriv, grad [nframes, ngrad*3] -> grad_net [nframes*nloc, nnei*4].  ngrad (default nloc, the

@@ -385,6 +385,56 @@ DPB200_DECL_ATTEN_GLUE(f32, float)
 #undef DPB200_DECL_ATTEN_GLUE
 
 /* ---------------------------------------------------------------------------------------
+ * DPA-1 attention layers, attn_layer > 0 (csrc/attn_layers.cu).  Replaces what the reference runs
+ * as torch modules + autograd: deepmd/pt/model/descriptor/se_atten.py:977-1012 (strip-mode g2 = g_s (1 + gg_t sw),
+ * input_r) and :1058-1447 (NeighborGatedAttention / NeighborGatedAttentionLayer / GatedAttentionLayer).  The dense
+ * products of a layer are plain GEMMs issued by the caller; these entry points are the stages between them, forward
+ * and backward.  All tensors are row-major device arrays; `rows` = atoms * nnei.
+ *  embed      : g_s, g_s' [rows, M] from the `dp compress` table at s = em_x[row * em_x_stride] (table_info is a
+ *               HOST pointer, 6 numbers) and x0 = g_s (1 + tt_full[pair] sw).
+ *  embed_grad : d_em_x[row * stride] += sum_c dx0 (1 + tt sw) g_s';  d_sw[row] += sum_c dx0 g_s tt.
+ *  rhat       : rhat [rows, 3] = normalize(em[row, 1:4]) (eps 1e-12), rinv [rows] = 1 / norm (negative when clamped).
+ *  rhat_grad  : d_em[row, 1:4] += (d_rhat - rhat (rhat . d_rhat)) * rinv.
+ *  qkv_normalize      : qkv [rows, 3, hidden] in place: each of q, k, v <- x / max(|x|, 1e-12) (skipped when
+ *               normalize = 0), q additionally * q_scale; inv_norm [rows, 3].
+ *  qkv_normalize_grad : d_qkv in place from the stored (normalised, q-scaled) qkv_hat and inv_norm.
+ *  weights    : S [natoms, nnei, nnei] = q k^T ->  T = (S + shift) sw_i sw_j - shift, P = softmax_j T,
+ *               A = P sw_i sw_j (rhat_i . rhat_j if dotr).
+ *  weights_grad : dS (may alias dA) from dA; d_sw [natoms, nnei] and d_rhat [natoms, nnei, 3] are ACCUMULATED into.
+ *  residual_layernorm : z = x + y; zhat = (z - mean) / sqrt(var + eps) (biased variance) overwrites y;
+ *               out = zhat gamma + beta; rstd [rows].
+ *  residual_layernorm_grad : dz = rstd (g - mean g - zhat mean(g zhat)), g = dout gamma.
+ * ------------------------------------------------------------------------------------- */
+#define DPB200_DECL_ATTN(SUF, FP)                                                                                  \
+  int dpb200_se_atten_embed_##SUF(FP* x0, FP* gs, FP* dgs, const FP* table, const FP* table_info, const FP* em_x,  \
+                                  long long em_x_stride, const FP* tt_full, const int* pair, const FP* sw,         \
+                                  long long rows, int last_layer_size, dpb200_stream_t stream);                    \
+  int dpb200_se_atten_embed_grad_##SUF(FP* d_em_x, long long d_em_x_stride, FP* d_sw, const FP* dx0, const FP* gs, \
+                                       const FP* dgs, const FP* tt_full, const int* pair, const FP* sw,            \
+                                       long long rows, int last_layer_size, dpb200_stream_t stream);               \
+  int dpb200_se_atten_rhat_##SUF(FP* rhat, FP* rinv, const FP* em, long long rows, dpb200_stream_t stream);        \
+  int dpb200_se_atten_rhat_grad_##SUF(FP* d_em, const FP* d_rhat, const FP* rhat, const FP* rinv, long long rows,  \
+                                      dpb200_stream_t stream);                                                     \
+  int dpb200_attn_qkv_normalize_##SUF(FP* qkv, FP* inv_norm, long long rows, int hidden, double q_scale,           \
+                                      int normalize, dpb200_stream_t stream);                                      \
+  int dpb200_attn_qkv_normalize_grad_##SUF(FP* d_qkv, const FP* qkv_hat, const FP* inv_norm, long long rows,       \
+                                           int hidden, double q_scale, int normalize, dpb200_stream_t stream);     \
+  int dpb200_attn_weights_##SUF(FP* P, FP* A, const FP* S, const FP* sw, const FP* rhat, long long natoms,         \
+                                int nnei, double shift, int dotr, dpb200_stream_t stream);                         \
+  int dpb200_attn_weights_grad_##SUF(FP* dS, FP* d_sw, FP* d_rhat, const FP* dA, const FP* P, const FP* S,         \
+                                     const FP* sw, const FP* rhat, long long natoms, int nnei, double shift,       \
+                                     int dotr, dpb200_stream_t stream);                                            \
+  int dpb200_attn_residual_layernorm_##SUF(FP* out, FP* y_zhat, FP* rstd, const FP* x, const FP* gamma,            \
+                                           const FP* beta, long long rows, int width, double eps,                  \
+                                           dpb200_stream_t stream);                                                \
+  int dpb200_attn_residual_layernorm_grad_##SUF(FP* dz, const FP* dout, const FP* zhat, const FP* rstd,            \
+                                                const FP* gamma, long long rows, int width,                        \
+                                                dpb200_stream_t stream);
+DPB200_DECL_ATTN(f64, double)
+DPB200_DECL_ATTN(f32, float)
+#undef DPB200_DECL_ATTN
+
+/* ---------------------------------------------------------------------------------------
  * tabulate_fusion_se_a for the higher angular bases, ndescrpt = 9 / 16 / 25 (csrc/tabulate_nd.cu).
  * Replaces deepmd::tabulate_fusion_se_a{,_grad,_grad_grad}_{cpu,gpu} called with ndescrpt != 4
  * (source/lib/include/tabulate.h:28-72, dispatch source/lib/src/tabulate.cc:456-560; caller
