@@ -395,6 +395,8 @@ def run_ours(args):
                 "atom_virial": bool(args.atom_virial),
                 "l2_policy": "per-step working set (tens of GB of env-mat intermediates) is far larger than the 126 MB L2",
                 "energy": energy,
+                **({"attn_slots_evaluated_per_atom": float(np.mean(model.last_n_eff))}
+                   if getattr(model, "last_n_eff", None) else {}),
             },
             "clocks": clocks, "gpu_launches": int(launches), "step_ms": step_ms,
         }
@@ -525,18 +527,20 @@ def per_kernel(args, torch, ops, model, dp, step, L, dev, nloc, esz):
         alg["tabulate_fusion_se_atten_gate_grad"] = ("fp", 42 * npr * M)
     if args.workload == "dpa1_attn":
         nl_, h_ = cfg.attn_layer, cfg.attn
-        alg["se_atten_embed"] = ("hbm", 3 * nnei * M * F + nnei * (2 * F + 4))
-        alg["se_atten_embed_grad"] = ("hbm", 3 * nnei * M * F + nnei * (4 * F + 4))
-        alg["attn_qkv_normalize"] = ("hbm", nl_ * 2 * nnei * 3 * h_ * F)
-        alg["attn_qkv_normalize_grad"] = ("hbm", nl_ * 3 * nnei * 3 * h_ * F)
-        alg["attn_weights"] = ("hbm", nl_ * 3 * nnei * nnei * F)
-        alg["attn_weights_grad"] = ("hbm", nl_ * 4 * nnei * nnei * F)
-        alg["attn_residual_layernorm"] = ("hbm", nl_ * 4 * nnei * M * F)
-        alg["attn_residual_layernorm_grad"] = ("hbm", nl_ * 3 * nnei * M * F)
+        # slots actually evaluated per atom: trailing empty slots of a slab are folded into one (atten.py attn_compact)
+        ne_ = float(np.mean(getattr(model, "last_n_eff", [nnei]) or [nnei]))
+        alg["se_atten_embed"] = ("hbm", 3 * ne_ * M * F + ne_ * (2 * F + 4))
+        alg["se_atten_embed_grad"] = ("hbm", 3 * ne_ * M * F + ne_ * (4 * F + 4))
+        alg["attn_qkv_normalize"] = ("hbm", nl_ * 2 * ne_ * 3 * h_ * F)
+        alg["attn_qkv_normalize_grad"] = ("hbm", nl_ * 3 * ne_ * 3 * h_ * F)
+        alg["attn_weights"] = ("hbm", nl_ * 3 * ne_ * ne_ * F)
+        alg["attn_weights_grad"] = ("hbm", nl_ * 4 * ne_ * ne_ * F)
+        alg["attn_residual_layernorm"] = ("hbm", nl_ * 4 * ne_ * M * F)
+        alg["attn_residual_layernorm_grad"] = ("hbm", nl_ * 3 * ne_ * M * F)
         alg["prod_force_virial_a_pair"] = ("hbm", (19 * nnei * F + 4 * nnei) + 2 * nnei * F + 3 * F)
         alg["se_atten_gate_scalars"] = ("hbm", nnei * (4 + 3 * F) + nnei * (4 + 2 * F))
         # forward products of a layer; the backward has two products per forward one
-        alg[gemm_row] = ("fp", nl_ * 3 * 2.0 * nnei * (M * 3 * h_ + 2 * nnei * h_ + h_ * M))
+        alg[gemm_row] = ("fp", nl_ * 3 * 2.0 * ne_ * (M * 3 * h_ + 2 * ne_ * h_ + h_ * M))
     table = {}
     total = 0.0
     for n, evs in acc.items():

@@ -63,7 +63,7 @@ _SIGS = {
     "se_atten_rhat_grad_{s}": "pppp l p",
     "attn_qkv_normalize_{s}": "pp l i d i p",
     "attn_qkv_normalize_grad_{s}": "ppp l i d i p",
-    "attn_weights_{s}": "pp ppp l i d i p",
+    "attn_weights_{s}": "pp ppp l ii d i p",
     "attn_weights_grad_{s}": "ppp pp ppp l i d i p",
     "attn_residual_layernorm_{s}": "ppp ppp l i d p",
     "attn_residual_layernorm_grad_{s}": "p pppp l i p",

@@ -206,6 +206,13 @@ class SeAttenModel:
         self.attn_layers = []
         self.attn_scaling = float((cfg.attn * cfg.scaling_factor) ** -0.5)
         self.attn_chunk = 4096  # centre atoms per slab: ~2 MB of saved activations per atom and layer pair in fp64
+        # Empty neighbour slots trail the formatted list and are all alike (s = -davg / dstd, sw = 0, rhat = 0): a slab
+        # is evaluated on its first n_eff slots, n_eff = the slab's largest neighbour count + 1 (rounded up to 8), the
+        # last of which stands for every omitted empty slot -- (nnei - n_eff + 1)-fold in the moment, and through
+        # `nnei_full` in the softmax denominators.  The slot count follows the step's neighbour counts (one host read
+        # per slab), so the step is not replayed from a CUDA graph.
+        self.attn_compact = True
+        self.graph_safe = cfg.attn_layer == 0
         for li in range(cfg.attn_layer):
             if weights is not None and "attn" in weights:
                 lay = {k: torch.as_tensor(np.asarray(v, np.float64)) for k, v in weights["attn"][li].items()}
@@ -369,7 +376,7 @@ class SeAttenModel:
         return e_atom.sum(), force, virial, dict(atom_energy=e_atom, atom_virial=av, nlist=nlist)
 
     # ---------------------------------------------------------------------------------------- attention layers
-    def attention_forward(self, x, sw, rhat, keep=True):
+    def attention_forward(self, x, sw, rhat, keep=True, nnei_full=None):
         """NeighborGatedAttention (se_atten.py:1058-1447) on x [B, nnei, M]: per layer in_proj -> normalised q, k, v
         -> gated softmax weights -> A v -> out_proj -> residual + layer norm.  Dense products on the library, the stages
         between them in csrc/attn_layers.cu.  Returns (x_out, saved activations for attention_backward)."""
@@ -382,7 +389,7 @@ class SeAttenModel:
             inv = ops.attn_qkv_normalize(qkv, h, self.attn_scaling, cfg.attn_normalize)
             q3 = qkv.view(B, n, 3 * h)
             S = _bmm(q3[:, :, :h], q3[:, :, h:2 * h].transpose(1, 2))
-            P, A = ops.attn_weights(S, sw, rhat, cfg.attnw_shift, cfg.attn_dotr)
+            P, A = ops.attn_weights(S, sw, rhat, cfg.attnw_shift, cfg.attn_dotr, nnei_full=nnei_full)
             O = _bmm(A, q3[:, :, 2 * h:])
             Y = _addmm(lay["out_b"], O.view(-1, h), lay["out_w"])
             del O
@@ -436,12 +443,26 @@ class SeAttenModel:
         q_sw = torch.zeros((nloc, nnei), dtype=self.dtype, device=em.device)
         for a in range(0, nloc, self.attn_chunk):
             b = min(nloc, a + self.attn_chunk)
-            em_c, sw_c, pair_c = em3[a:b], sw[a:b], pair32[a:b]
+            n_eff = nnei
+            if a == 0:
+                self.last_n_eff = []  # slots evaluated per slab (bench.py sizes the rooflines with it)
+            if self.attn_compact:
+                most = int((nlist[a:b] >= 0).sum(1).max().item())
+                n_eff = min(nnei, (most + 1 + 7) // 8 * 8)
+            self.last_n_eff.append(n_eff)
+            if n_eff < nnei:
+                em_c, sw_c, pair_c = em3[a:b, :n_eff].contiguous(), sw[a:b, :n_eff].contiguous(), \
+                    pair32[a:b, :n_eff].contiguous()
+                em_w = em_c.clone()
+                em_w[:, -1, :] *= float(nnei - n_eff + 1)  # the kept empty slot stands for all of them in the moment
+            else:
+                em_c, sw_c, pair_c = em3[a:b], sw[a:b], pair32[a:b]
+                em_w = em_c
             x0, gs, dgs = ops.se_atten_embed(self.table, self.info, em_c, self.tt_full, pair_c, sw_c, M)
             rhat, rinv = ops.se_atten_rhat(em_c)
-            x, saved = self.attention_forward(x0, sw_c, rhat)
+            x, saved = self.attention_forward(x0, sw_c, rhat, nnei_full=nnei)
             del x0
-            xyz = _bmm(em_c.transpose(1, 2), x)  # [B, 4, M], the unscaled moment (se_atten.py:1012)
+            xyz = _bmm(em_w.transpose(1, 2), x)  # [B, 4, M], the unscaled moment (se_atten.py:1012)
             g1 = torch.zeros((b - a, self.dim_in), dtype=self.dtype, device=em.device)
             g1[:, :self.dim_d] = ops.se_a_descriptor(xyz, cfg.axis_neuron, inv)
             g1[:, self.dim_d:self.dim_d + cfg.tebd_dim] = self.tebd.index_select(0, ctype_e[a:b])
@@ -458,14 +479,20 @@ class SeAttenModel:
             dy = dy.to(self.dtype)
             del gd
             d_em = _bmm(x, dy.transpose(1, 2)).contiguous()  # through the moment's em factor
-            dx = _bmm(em_c, dy)
+            dx = _bmm(em_w, dy)
             del x, dy
-            d_rhat = torch.zeros((b - a, nnei, 3), dtype=self.dtype, device=em.device)
-            dx = self.attention_backward(dx, saved, sw_c, rhat, q_sw[a:b], d_rhat)
-            ops.se_atten_embed_grad(d_em, q_sw[a:b], dx, gs, dgs, self.tt_full, pair_c, sw_c)
+            d_rhat = torch.zeros((b - a, n_eff, 3), dtype=self.dtype, device=em.device)
+            d_sw = q_sw[a:b] if n_eff == nnei else torch.zeros((b - a, n_eff), dtype=self.dtype, device=em.device)
+            dx = self.attention_backward(dx, saved, sw_c, rhat, d_sw, d_rhat)
+            ops.se_atten_embed_grad(d_em, d_sw, dx, gs, dgs, self.tt_full, pair_c, sw_c)
             ops.se_atten_rhat_grad(d_em, d_rhat, rhat, rinv)
-            net_deriv[a:b] = d_em
-            del dx, gs, dgs, d_em, d_rhat
+            if n_eff == nnei:
+                net_deriv[a:b] = d_em
+            else:  # (the omitted slots are empty: their environment derivative is zero whatever stands here)
+                net_deriv[a:b, :n_eff] = d_em
+                net_deriv[a:b, n_eff:] = 0
+                q_sw[a:b, :n_eff] = d_sw
+            del dx, gs, dgs, d_em, d_rhat, d_sw
         if mapping is not None:
             ops.use_nlist_map(nlist, mapping)
         n_out = nloc if mapping is not None else nall

@@ -202,13 +202,18 @@ __global__ void __launch_bounds__(256) k_qkv_norm(FP* __restrict__ qkv, FP* __re
 }
 
 // ------------------------------------------------------------------------------------------ weights
-constexpr int kMaxJ = 8;  // neighbours per lane: nnei <= 256
+// Lanes over the neighbours j, NJ per lane (NJ = 4 serves nnei <= 128, NJ = 8 nnei <= 256).
+//
+// Slabs with trailing empty slots may be evaluated on the first n < n_full slots only (the host keeps one empty slot
+// as the representative of all of them): an empty column has T = -shift whatever S is, so the n_full - n omitted ones
+// add (n_full - n) exp(-shift) to every softmax denominator and nothing else.
+constexpr int kMaxJ = 8;
 
 // one warp per (atom, i)
-template <typename FP>
+template <typename FP, int NJ>
 __global__ void __launch_bounds__(256) k_attn_weights(FP* __restrict__ P, FP* __restrict__ A, const FP* __restrict__ S,
                                                       const FP* __restrict__ sw, const FP* __restrict__ rhat,
-                                                      long long natoms, int n, FP shift, int dotr) {
+                                                      long long natoms, int n, int n_full, FP shift, int dotr) {
   const int lane = threadIdx.x & 31;
   const long long wpg = (long long)gridDim.x * (blockDim.x >> 5);
   for (long long u = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); u < natoms * n; u += wpg) {
@@ -218,13 +223,14 @@ __global__ void __launch_bounds__(256) k_attn_weights(FP* __restrict__ P, FP* __
     const FP swi = sw[u];
     const FP rx = rhat[3 * u], ry = rhat[3 * u + 1], rz = rhat[3 * u + 2];
     const FP* __restrict__ srow = S + u * n;
-    FP t[kMaxJ];
-    FP mx = -INFINITY;
+    FP t[NJ], w[NJ];
+    FP mx = n_full > n ? -shift : -INFINITY;
 #pragma unroll
-    for (int k = 0; k < kMaxJ; ++k) {
+    for (int k = 0; k < NJ; ++k) {
       const int j = lane + 32 * k;
       if (j < n) {
-        t[k] = (srow[j] + shift) * swi * swa[j] - shift;
+        w[k] = swi * swa[j];
+        t[k] = (srow[j] + shift) * w[k] - shift;
         mx = fmax(mx, t[k]);
       }
     }
@@ -232,31 +238,35 @@ __global__ void __launch_bounds__(256) k_attn_weights(FP* __restrict__ P, FP* __
     for (int o = 16; o > 0; o >>= 1) mx = fmax(mx, __shfl_xor_sync(kFull, mx, o));
     FP sum = (FP)0.;
 #pragma unroll
-    for (int k = 0; k < kMaxJ; ++k) {
+    for (int k = 0; k < NJ; ++k) {
       const int j = lane + 32 * k;
       if (j < n) {
         t[k] = exp(t[k] - mx);
         sum += t[k];
       }
     }
-    const FP rs = (FP)1. / warp_sum(sum);
+    sum = warp_sum(sum);
+    if (n_full > n) sum += (FP)(n_full - n) * exp(-shift - mx);
+    const FP rs = (FP)1. / sum;
 #pragma unroll
-    for (int k = 0; k < kMaxJ; ++k) {
+    for (int k = 0; k < NJ; ++k) {
       const int j = lane + 32 * k;
       if (j < n) {
         const FP pj = t[k] * rs;
-        FP w = swi * swa[j];
-        if (dotr) w *= rx * ra[3 * j] + ry * ra[3 * j + 1] + rz * ra[3 * j + 2];
-        P[u * n + j] = pj;
-        A[u * n + j] = pj * w;
+        FP ww = w[k];
+        if (dotr) ww *= rx * ra[3 * j] + ry * ra[3 * j + 1] + rz * ra[3 * j + 2];
+        st_cs(P + u * n + j, pj);
+        A[u * n + j] = pj * ww;
       }
     }
   }
 }
 
-// one CTA per atom; dS may alias dA.  d_sw [natoms][n] and d_rhat [natoms][n][3] are accumulated into.
-template <typename FP>
-__global__ void __launch_bounds__(256) k_attn_weights_grad(FP* __restrict__ dS, FP* __restrict__ d_sw,
+// one CTA per atom, one warp per row i; dS may alias dA.  Column sums (the j side of d sw_i sw_j and d rhat_i . rhat_j)
+// stay in registers over the rows of a warp and meet the row sums in shared memory once per warp.
+// d_sw [natoms][n] and d_rhat [natoms][n][3] are accumulated into.
+template <typename FP, int NJ>
+__global__ void __launch_bounds__(128, NJ == 4 ? 3 : 1) k_attn_weights_grad(FP* __restrict__ dS, FP* __restrict__ d_sw,
                                                            FP* __restrict__ d_rhat, const FP* __restrict__ dA,
                                                            const FP* __restrict__ P, const FP* __restrict__ S,
                                                            const FP* __restrict__ sw, const FP* __restrict__ rhat,
@@ -264,7 +274,7 @@ __global__ void __launch_bounds__(256) k_attn_weights_grad(FP* __restrict__ dS, 
   extern __shared__ __align__(16) unsigned char smem_raw[];
   FP* s_sw = reinterpret_cast<FP*>(smem_raw);  // [n]
   FP* s_r = s_sw + n;                          // [n][3]
-  FP* c_sw = s_r + 3 * n;                      // [n]  column + row accumulators
+  FP* c_sw = s_r + 3 * n;                      // [n]     accumulators of this atom
   FP* c_r = c_sw + n;                          // [n][3]
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
   for (long long atom = blockIdx.x; atom < natoms; atom += gridDim.x) {
@@ -278,45 +288,59 @@ __global__ void __launch_bounds__(256) k_attn_weights_grad(FP* __restrict__ dS, 
       c_r[j] = (FP)0.;
     }
     __syncthreads();
+    FP csw[NJ], crx[NJ], cry[NJ], crz[NJ], swj[NJ], rjx[NJ], rjy[NJ], rjz[NJ];
+#pragma unroll
+    for (int k = 0; k < NJ; ++k) {
+      const int j = lane + 32 * k;
+      const bool in = j < n;
+      csw[k] = crx[k] = cry[k] = crz[k] = (FP)0.;
+      swj[k] = in ? s_sw[j] : (FP)0.;
+      rjx[k] = in ? s_r[3 * j] : (FP)0.;
+      rjy[k] = in ? s_r[3 * j + 1] : (FP)0.;
+      rjz[k] = in ? s_r[3 * j + 2] : (FP)0.;
+    }
     for (int i = warp; i < n; i += nwarp) {
       const long long u = atom * n + i;
       const FP swi = s_sw[i];
       const FP rx = s_r[3 * i], ry = s_r[3 * i + 1], rz = s_r[3 * i + 2];
-      FP da[kMaxJ], pp[kMaxJ], ww[kMaxJ], rr[kMaxJ];
-      FP dot = (FP)0.;
+      FP da[NJ], pp[NJ], ss[NJ];
 #pragma unroll
-      for (int k = 0; k < kMaxJ; ++k) {
+      for (int k = 0; k < NJ; ++k) {
         const int j = lane + 32 * k;
         if (j < n) {
-          da[k] = dA[u * n + j];
-          pp[k] = P[u * n + j];
-          ww[k] = swi * s_sw[j];
-          rr[k] = dotr ? rx * s_r[3 * j] + ry * s_r[3 * j + 1] + rz * s_r[3 * j + 2] : (FP)1.;
-          dot += da[k] * ww[k] * rr[k] * pp[k];  // sum_j dP_ij P_ij
+          da[k] = __ldcs(dA + u * n + j);
+          pp[k] = __ldcs(P + u * n + j);
+          ss[k] = __ldcs(S + u * n + j);
+        } else {
+          da[k] = pp[k] = ss[k] = (FP)0.;
         }
+      }
+      FP dot = (FP)0.;
+#pragma unroll
+      for (int k = 0; k < NJ; ++k) {
+        const FP rr = dotr ? rx * rjx[k] + ry * rjy[k] + rz * rjz[k] : (FP)1.;
+        dot += da[k] * swi * swj[k] * rr * pp[k];  // sum_j dP_ij P_ij
       }
       dot = warp_sum(dot);
       FP row_sw = (FP)0., row_rx = (FP)0., row_ry = (FP)0., row_rz = (FP)0.;
 #pragma unroll
-      for (int k = 0; k < kMaxJ; ++k) {
+      for (int k = 0; k < NJ; ++k) {
         const int j = lane + 32 * k;
-        if (j < n) {
-          const FP dP = da[k] * ww[k] * rr[k];
-          const FP dT = pp[k] * (dP - dot);
-          const FP sij = S[u * n + j];
-          const FP dw = da[k] * pp[k] * rr[k] + dT * (sij + shift);  // d/d(sw_i sw_j)
-          dS[u * n + j] = dT * ww[k];
-          row_sw += dw * s_sw[j];
-          atomicAdd(&c_sw[j], dw * swi);
-          if (dotr) {
-            const FP dR = da[k] * pp[k] * ww[k];
-            row_rx += dR * s_r[3 * j];
-            row_ry += dR * s_r[3 * j + 1];
-            row_rz += dR * s_r[3 * j + 2];
-            atomicAdd(&c_r[3 * j], dR * rx);
-            atomicAdd(&c_r[3 * j + 1], dR * ry);
-            atomicAdd(&c_r[3 * j + 2], dR * rz);
-          }
+        const FP ww = swi * swj[k];
+        const FP rr = dotr ? rx * rjx[k] + ry * rjy[k] + rz * rjz[k] : (FP)1.;
+        const FP dT = pp[k] * (da[k] * ww * rr - dot);
+        const FP dw = da[k] * pp[k] * rr + dT * (ss[k] + shift);  // d / d(sw_i sw_j)
+        if (j < n) dS[u * n + j] = dT * ww;
+        row_sw += dw * swj[k];
+        csw[k] += dw * swi;
+        if (dotr) {
+          const FP dR = da[k] * pp[k] * ww;
+          row_rx += dR * rjx[k];
+          row_ry += dR * rjy[k];
+          row_rz += dR * rjz[k];
+          crx[k] += dR * rx;
+          cry[k] += dR * ry;
+          crz[k] += dR * rz;
         }
       }
       row_sw = warp_sum(row_sw);
@@ -331,6 +355,18 @@ __global__ void __launch_bounds__(256) k_attn_weights_grad(FP* __restrict__ dS, 
           atomicAdd(&c_r[3 * i], row_rx);
           atomicAdd(&c_r[3 * i + 1], row_ry);
           atomicAdd(&c_r[3 * i + 2], row_rz);
+        }
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < NJ; ++k) {
+      const int j = lane + 32 * k;
+      if (j < n) {
+        atomicAdd(&c_sw[j], csw[k]);
+        if (dotr) {
+          atomicAdd(&c_r[3 * j], crx[k]);
+          atomicAdd(&c_r[3 * j + 1], cry[k]);
+          atomicAdd(&c_r[3 * j + 2], crz[k]);
         }
       }
     }
@@ -466,12 +502,16 @@ int launch_qkv_norm(FP* qkv, FP* inv, const FP* yhat, long long rows, int h, dou
 }
 
 template <typename FP>
-int launch_weights(FP* P, FP* A, const FP* S, const FP* sw, const FP* rhat, long long natoms, int n, double shift,
-                   int dotr, cudaStream_t st) {
-  DPB_REQUIRE(natoms >= 0 && n >= 1 && n <= 32 * kMaxJ, "attn_weights: nnei must be in 1..256");
+int launch_weights(FP* P, FP* A, const FP* S, const FP* sw, const FP* rhat, long long natoms, int n, int n_full,
+                   double shift, int dotr, cudaStream_t st) {
+  DPB_REQUIRE(natoms >= 0 && n >= 1 && n <= 32 * kMaxJ && n_full >= n, "attn_weights: nnei must be in 1..256, nnei_full >= nnei");
   if (natoms == 0) return DPB200_OK;
   DPB_REQUIRE(P && A && S && sw && rhat, "attn_weights: null pointer");
-  k_attn_weights<FP><<<warp_grid(natoms * n, 8), 256, 0, st>>>(P, A, S, sw, rhat, natoms, n, (FP)shift, dotr);
+  const unsigned grid = warp_grid(natoms * n, 8);
+  if (n <= 128)
+    k_attn_weights<FP, 4><<<grid, 256, 0, st>>>(P, A, S, sw, rhat, natoms, n, n_full, (FP)shift, dotr);
+  else
+    k_attn_weights<FP, 8><<<grid, 256, 0, st>>>(P, A, S, sw, rhat, natoms, n, n_full, (FP)shift, dotr);
   DPB_CUDA(cudaGetLastError());
   note_launches(1);
   return DPB200_OK;
@@ -484,11 +524,15 @@ int launch_weights_grad(FP* dS, FP* d_sw, FP* d_rhat, const FP* dA, const FP* P,
   if (natoms == 0) return DPB200_OK;
   DPB_REQUIRE(dS && d_sw && d_rhat && dA && P && S && sw && rhat, "attn_weights_grad: null pointer");
   long long grid = natoms;
-  const long long cap = (long long)sm_count() * 8;
+  const long long cap = (long long)sm_count() * 12;
   if (grid > cap) grid = cap;
   const size_t smem = sizeof(FP) * 8 * (size_t)n;
-  k_attn_weights_grad<FP><<<(unsigned)grid, 256, smem, st>>>(dS, d_sw, d_rhat, dA, P, S, sw, rhat, natoms, n,
-                                                             (FP)shift, dotr);
+  if (n <= 128)
+    k_attn_weights_grad<FP, 4><<<(unsigned)grid, 128, smem, st>>>(dS, d_sw, d_rhat, dA, P, S, sw, rhat, natoms, n,
+                                                                  (FP)shift, dotr);
+  else
+    k_attn_weights_grad<FP, 8><<<(unsigned)grid, 128, smem, st>>>(dS, d_sw, d_rhat, dA, P, S, sw, rhat, natoms, n,
+                                                                  (FP)shift, dotr);
   DPB_CUDA(cudaGetLastError());
   note_launches(1);
   return DPB200_OK;
@@ -554,8 +598,9 @@ extern "C" {
                                              normalize, (cudaStream_t)stream);                                      \
   }                                                                                                                 \
   int dpb200_attn_weights_##SUF(FP* P, FP* A, const FP* S, const FP* sw, const FP* rhat, long long natoms,          \
-                                int nnei, double shift, int dotr, dpb200_stream_t stream) {                         \
-    return dpb200::launch_weights<FP>(P, A, S, sw, rhat, natoms, nnei, shift, dotr, (cudaStream_t)stream);          \
+                                int nnei, int nnei_full, double shift, int dotr, dpb200_stream_t stream) {          \
+    return dpb200::launch_weights<FP>(P, A, S, sw, rhat, natoms, nnei, nnei_full, shift, dotr,                      \
+                                      (cudaStream_t)stream);                                                        \
   }                                                                                                                 \
   int dpb200_attn_weights_grad_##SUF(FP* dS, FP* d_sw, FP* d_rhat, const FP* dA, const FP* P, const FP* S,          \
                                      const FP* sw, const FP* rhat, long long natoms, int nnei, double shift,        \

@@ -776,7 +776,8 @@ class DeepPotB200:
         if self._list_is_stale(coord, atype, box):
             st = self.build_neighbors(coord, atype, box)
         st.ago += 1
-        if not self.use_graph:
+        if not self.use_graph or not getattr(self.model, "graph_safe", True):
+            # (a model whose launch shapes follow the neighbour counts of the step cannot be replayed from a graph)
             return self._step(coord, atom_virial, fused)
         key = (st.nloc, int(st.ext_type.numel()), int(st.rows.shape[1]), st.rows.data_ptr(), st.ext_type.data_ptr(),
                bool(atom_virial), bool(fused), coord.dtype, st.type_perm.data_ptr(),

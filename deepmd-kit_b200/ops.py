@@ -626,14 +626,15 @@ def attn_qkv_normalize_grad(d_qkv, qkv_hat, inv, hidden, q_scale, normalize=True
                float(q_scale), int(bool(normalize)), _stream(dev))
 
 
-def attn_weights(S, sw, rhat, shift=20.0, dotr=True):
-    """S [natoms, nnei, nnei] -> (P, A): gated softmax and the attention weights (se_atten.py:1386-1416)."""
+def attn_weights(S, sw, rhat, shift=20.0, dotr=True, nnei_full=None):
+    """S [natoms, nnei, nnei] -> (P, A): gated softmax and the attention weights (se_atten.py:1386-1416).
+    nnei_full > nnei: the slab holds only the first nnei slots, the omitted ones are empty (trailing padding)."""
     dev = _need_cuda(("S", S), ("sw", sw), ("rhat", rhat))
     S = _c(S)
     natoms, n = S.shape[0], S.shape[1]
     P, A = torch.empty_like(S), torch.empty_like(S)
     lib().call("attn_weights_" + _suffix(S), _p(P), _p(A), _p(S), _p(_c(sw, S.dtype)), _p(_c(rhat, S.dtype)), natoms, n,
-               float(shift), int(bool(dotr)), _stream(dev))
+               int(n if nnei_full is None else nnei_full), float(shift), int(bool(dotr)), _stream(dev))
     return P, A
 
 

@@ -399,7 +399,9 @@ DPB200_DECL_ATTEN_GLUE(f32, float)
  *               normalize = 0), q additionally * q_scale; inv_norm [rows, 3].
  *  qkv_normalize_grad : d_qkv in place from the stored (normalised, q-scaled) qkv_hat and inv_norm.
  *  weights    : S [natoms, nnei, nnei] = q k^T ->  T = (S + shift) sw_i sw_j - shift, P = softmax_j T,
- *               A = P sw_i sw_j (rhat_i . rhat_j if dotr).
+ *               A = P sw_i sw_j (rhat_i . rhat_j if dotr).  nnei_full >= nnei: the slab was cut to its first nnei
+ *               slots and the nnei_full - nnei omitted (empty, trailing) slots are accounted for in the softmax
+ *               denominators, each with exp(-shift).
  *  weights_grad : dS (may alias dA) from dA; d_sw [natoms, nnei] and d_rhat [natoms, nnei, 3] are ACCUMULATED into.
  *  residual_layernorm : z = x + y; zhat = (z - mean) / sqrt(var + eps) (biased variance) overwrites y;
  *               out = zhat gamma + beta; rstd [rows].
@@ -420,7 +422,7 @@ DPB200_DECL_ATTEN_GLUE(f32, float)
   int dpb200_attn_qkv_normalize_grad_##SUF(FP* d_qkv, const FP* qkv_hat, const FP* inv_norm, long long rows,       \
                                            int hidden, double q_scale, int normalize, dpb200_stream_t stream);     \
   int dpb200_attn_weights_##SUF(FP* P, FP* A, const FP* S, const FP* sw, const FP* rhat, long long natoms,         \
-                                int nnei, double shift, int dotr, dpb200_stream_t stream);                         \
+                                int nnei, int nnei_full, double shift, int dotr, dpb200_stream_t stream);          \
   int dpb200_attn_weights_grad_##SUF(FP* dS, FP* d_sw, FP* d_rhat, const FP* dA, const FP* P, const FP* S,         \
                                      const FP* sw, const FP* rhat, long long natoms, int nnei, double shift,       \
                                      int dotr, dpb200_stream_t stream);                                            \

@@ -79,6 +79,10 @@ def main():
         from deepmd_kit_b200.atten import SeAttenConfig, SeAttenModel
 
         model = SeAttenModel(SeAttenConfig(), dtype, dev)
+    elif os.environ.get("DPB_MODEL") == "dpa1_attn":  # DPA-1 with two attention layers (slab-wise, no CUDA graph)
+        from deepmd_kit_b200.atten import SeAttenConfig, SeAttenModel
+
+        model = SeAttenModel(SeAttenConfig(attn_layer=2), dtype, dev)
     else:
         model = SeAModel(SeAConfig(), dtype, dev)
     grid = proc_grid(world)

@@ -105,6 +105,14 @@ def test_product_matches_reference_backends_gpu(gold):
     e2, f2, v2, _ = dp.eval_device(torch.as_tensor(coord).cuda(), torch.as_tensor(atype).cuda(), box)
     assert abs(float(e2) - float(e)) <= 1e-12 * abs(float(e))
     assert rel(f2.cpu().numpy(), f.cpu().numpy()) <= 1e-11
+    # ... and so does the evaluation on all nnei slots (default: the trailing empty slots of a slab are folded into one)
+    assert model.attn_compact
+    model.attn_compact = False
+    e3, f3, v3, _ = dp.eval_device(torch.as_tensor(coord).cuda(), torch.as_tensor(atype).cuda(), box)
+    assert abs(float(e3) - float(e)) <= 1e-12 * abs(float(e))
+    assert rel(f3.cpu().numpy(), f.cpu().numpy()) <= 1e-11
+    assert rel(v3.cpu().numpy(), v.cpu().numpy()) <= 1e-11
+    assert rel(f3.cpu().numpy(), gold["x_pt_force"]) <= 1e-10
     assert lib().launch_count() > n0
 
 

@@ -7,7 +7,11 @@ import json
 import subprocess
 import sys
 
-OPS = [("k_env_mat_a", "prod_env_mat_a"), ("k_tab_fwd", "tabulate_sections_desc"), ("k_tab_grad", "tabulate_sections_grad"),
+OPS = [("k_embed_grad", "se_atten_embed_grad"), ("k_embed", "se_atten_embed"), ("k_qkv_norm", "attn_qkv_normalize (+grad)"),
+       ("k_attn_weights_grad", "attn_weights_grad"), ("k_attn_weights", "attn_weights"),
+       ("k_res_ln_grad", "attn_residual_layernorm_grad"), ("k_res_ln", "attn_residual_layernorm"),
+       ("k_rhat", "se_atten_rhat (+grad)"), ("gemm", "library GEMM (cuBLAS)"), ("k_gate_scalars", "se_atten_gate_scalars"),
+       ("k_env_mat_a", "prod_env_mat_a"), ("k_tab_fwd", "tabulate_sections_desc"), ("k_tab_grad", "tabulate_sections_grad"),
        ("k_desc_bwd", "se_a_descriptor_grad"), ("k_fit_gemm", "fit_gemm_i8"), ("k_fit_slice<(int)6, (bool)1>", "fit_head"),
        ("k_fit_slice<(int)6, (bool)0>", "fit_slice_rows"), ("k_force_virial", "prod_force_virial_a"),
        ("k_split", "split glue"), ("k_mlp", "mlp glue")]

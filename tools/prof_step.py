@@ -21,6 +21,10 @@ if os.environ.get("MODEL", "se_a") == "se_atten":  # config 5 model (ncu summary
     from deepmd_kit_b200.atten import SeAttenConfig, SeAttenModel  # noqa: E402
 
     model = SeAttenModel(SeAttenConfig(), dtype, dev)
+elif os.environ.get("MODEL") == "dpa1_attn":  # DPA-1 with two attention layers
+    from deepmd_kit_b200.atten import SeAttenConfig, SeAttenModel  # noqa: E402
+
+    model = SeAttenModel(SeAttenConfig(attn_layer=2), dtype, dev)
 else:
     model = SeAModel(SeAConfig(), dtype, dev)
 dp = DeepPotB200(model, skin=2.0, nlist_every=10, use_graph=False)
