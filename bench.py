@@ -175,9 +175,74 @@ def cpu_pipeline_timing(args, steps, warmup, seconds=None):
                        f"raw list (cell list, {t_build * 1e3:.0f} ms) excluded, {args.dtype}")
 
 
+def cpu_attn_timing(args, steps, warmup, seconds=None):
+    """DPA-1 with attention layers on the host cores: the reference's CPU env-mat / force / virial ops + a plain torch
+    restatement of its dense uncompressed path (embedding MLP, attention layers, autograd) = oracle.pipeline_atten
+    .evaluate_layers, on a bounded sample (the reference cannot compress this model, so this IS its algorithm)."""
+    import torch
+
+    import __graft_entry__ as g
+    from oracle import cpu as ocpu
+    from oracle import pipeline, pipeline_atten
+    from oracle.refmodel import RefAttnModel
+
+    kind = "reference" if ocpu.available("reference") else "port"
+    lib = ocpu.CpuLib(kind)
+    ncores = os.cpu_count() or 1
+    try:
+        import ctypes
+
+        ctypes.CDLL("libgomp.so.1").omp_set_num_threads(ncores)
+    except OSError:
+        pass
+    torch.set_num_threads(ncores)
+    model = RefAttnModel(torch.float64)
+    ncopy = min(args.cpu_ncopy, 2)
+    coord, atype, box = g.water_box(ncopy, args.jitter)
+    nat = len(atype)
+    lists = pipeline.build_lists(ocpu.CpuLib("port"), coord, atype, box, model.cfg.rcut + 2.0)
+    for _ in range(warmup):
+        pipeline_atten.evaluate_layers(lib, model, lists)
+    t0 = time.perf_counter()
+    n = 0
+    while n < steps:
+        pipeline_atten.evaluate_layers(lib, model, lists)
+        n += 1
+        if seconds is not None and time.perf_counter() - t0 > seconds and n >= 2:
+            break
+    dt = (time.perf_counter() - t0) / n
+    return dict(us_per_step_atom=dt * 1e6 / nat, ms_per_step=dt * 1e3, steps=n, natoms=nat,
+                kind=kind + " CPU ops + torch-CPU restatement of the dense attention path (autograd)", cores=ncores,
+                stages_us_per_atom={},
+                sample=f"{nat}-atom water box ({ncopy}^3 replicas of the 192-atom frame), {n} steps, raw list excluded, f64")
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
+        return
+    if args.workload == "dpa1_attn":
+        r = cpu_attn_timing(args, args.steps, args.warmup)
+        nat = 192 * args.ncopy ** 3 * args.gpus
+        line = {
+            "impl": "reference", "metric": METRIC, "value": r["us_per_step_atom"], "unit": UNIT, "n_gpus": args.gpus,
+            "steps": r["steps"], "warmup": args.warmup, "ms_per_step": r["ms_per_step"], "higher_is_better": False,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": (f"DPA-1 se_atten_v2 with attention (strip, smooth, attn_layer 2, attn 128, dotr, sel "
+                                    f"120; tabulated embedding + attention layers) water, {nat}-atom box ({args.ncopy}^3 "
+                                    f"replicas of the 192-atom frame per GPU, jitter {args.jitter} A), f64, "
+                                    f"{args.gpus}xB200"),
+                       "natoms": nat, "rcut": 6.0, "rcut_smth": 0.5, "sel": [120], "neuron": [25, 50, 100],
+                       "axis_neuron": 16, "fitting_neuron": [240, 240, 240], "bench_workload": "dpa1_attn",
+                       "reference_implementation": "uncompressed dense path (the reference cannot compress a model "
+                                                   "with attention layers) on all host cores; bounded sample",
+                       "sample_natoms": r["natoms"]},
+            "cpu_baseline": {"value": r["us_per_step_atom"], "unit": UNIT, "cores": r["cores"], "kind": r["kind"],
+                             "sample": r["sample"]},
+            "e2e": {"value": r["us_per_step_atom"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "product_native_loaded": _maps_contain("libdpb200"),
+        }
+        _emit(json.dumps(line))
         return
     r = cpu_pipeline_timing(args, args.steps, args.warmup)
     line = {
@@ -358,9 +423,10 @@ def run_ours(args):
     kernels, roofline = per_kernel(args, torch, ops, model, dp, step, L, dev, len(atype), esz)
 
     cpu_base = None
-    if rank == 0 and world == 1 and not args.no_cpu_baseline and args.workload == "water":
+    if rank == 0 and world == 1 and not args.no_cpu_baseline and args.workload in ("water", "dpa1_attn"):
         try:
-            r = cpu_pipeline_timing(args, 10 ** 6, 1, seconds=args.cpu_seconds)
+            r = (cpu_pipeline_timing if args.workload == "water" else cpu_attn_timing)(args, 10 ** 6, 1,
+                                                                                     seconds=args.cpu_seconds)
             cpu_base = {"value": r["us_per_step_atom"], "unit": UNIT, "cores": r["cores"], "kind": r["kind"],
                         "sample": r["sample"], "stages_us_per_atom": r["stages_us_per_atom"]}
         except Exception as e:  # the checker libraries are test infrastructure; report, do not hide

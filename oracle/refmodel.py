@@ -82,3 +82,48 @@ class RefWaterModel:
         self.M = 100
         self.fit = [RefFittingNet(1600, self.cfg.fitting_neuron, True, seed + 101 * t, dtype) for t in range(2)]
         self.bias_atom_e = torch.zeros(2, dtype=dtype)
+
+
+class RefAttnModel:
+    """DPA-1 se_atten_v2 WITH attention layers (strip, smooth, attn_layer 2, attn 128, dotr, sel 120; the architecture
+    of deepmd_kit_b200.atten.SeAttenConfig(attn_layer=2)), random-init: what oracle.pipeline_atten.evaluate_layers
+    needs.  Used by the CPU timing legs of bench.py (`--workload dpa1_attn`): the arithmetic does not depend on the
+    weight values, so this model has its own seeds (it is NOT weight-identical to the product's random model; parity
+    for this path is pinned by tests/golden/dpa1_attn.npz instead)."""
+
+    def __init__(self, dtype=torch.float64, seed=1, attn_layer=2):
+        cz = _compress_module()
+        nnei, M, tebd_dim, attn, nt = 120, 100, 8, 128, 2
+        self.cfg = SimpleNamespace(ntypes=nt, nsel=nnei, sel=(nnei,), sec=[0, nnei], nnei=nnei, rcut=6.0, rcut_smth=0.5,
+                                   neuron=(25, 50, 100), axis_neuron=16, tebd_dim=tebd_dim, fitting_neuron=(240, 240, 240),
+                                   fitting_resnet_dt=True, seed=seed, attn_layer=attn_layer, attn=attn, attn_dotr=True,
+                                   attn_normalize=True, scaling_factor=1.0, ln_eps=1e-5, attnw_shift=20.0)
+        self.dtype = dtype
+        self.M = M
+        davg = np.zeros((nt, nnei, 4))
+        dstd = np.ones((nt, nnei, 4))
+        for t, (a0, s0, s1) in enumerate(WATER_STATS):
+            davg[t, :, 0] = a0
+            dstd[t, :, 0] = s0
+            dstd[t, :, 1:] = s1
+        self.davg = torch.as_tensor(davg.reshape(nt, -1), dtype=dtype)
+        self.dstd = torch.as_tensor(dstd.reshape(nt, -1), dtype=dtype)
+        self.embed = cz.EmbeddingNet(self.cfg.neuron, seed)
+        g = torch.Generator().manual_seed(seed + 7)
+
+        def normal(*shape, std=1.0):
+            return torch.empty(*shape, dtype=torch.float64).normal_(0.0, std, generator=g)
+
+        self.tebd = torch.zeros(nt + 1, tebd_dim, dtype=torch.float64)
+        self.tebd[:nt] = normal(nt, tebd_dim)
+        self.tt_full = 0.1 * normal((nt + 1) ** 2, M)  # the strip net's output table (values irrelevant for timing)
+        self.attn_scaling = float(attn ** -0.5)
+        self.attn_layers = []
+        for _ in range(attn_layer):
+            self.attn_layers.append(dict(in_w=normal(M, 3 * attn, std=1.0 / math.sqrt(M + 3 * attn)), in_b=normal(3 * attn),
+                                         out_w=normal(attn, M, std=1.0 / math.sqrt(attn + M)), out_b=normal(M),
+                                         ln_w=torch.ones(M, dtype=torch.float64), ln_b=torch.zeros(M, dtype=torch.float64)))
+        self.dim_d = M * self.cfg.axis_neuron
+        self.dim_in = (self.dim_d + tebd_dim + 15) // 16 * 16
+        self.fit = RefFittingNet(self.dim_in, self.cfg.fitting_neuron, True, seed + 101, torch.float64)
+        self.bias_atom_e = torch.zeros(nt, dtype=torch.float64)
