@@ -231,6 +231,26 @@ def test_bench_reference_arm_contract():
     assert d["config"]["natoms"] == 1536000 and "workload" in d["config"]
 
 
+def test_bench_reference_arm_attention_workload():
+    """`bench.py --impl reference --workload dpa1_attn`: the dense CPU path of DPA-1 with attention layers (checker +
+    oracle/refmodel.RefAttnModel, no product native code) prints the same contract line."""
+    import json
+    import subprocess
+    import sys
+
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--workload", "dpa1_attn",
+                        "--steps", "1", "--warmup", "0", "--cpu-ncopy", "1", "--ncopy", "6"], capture_output=True, text=True,
+                       timeout=600, cwd=ROOT)
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [ln for ln in r.stdout.splitlines() if ln.strip()]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["unit"] == "us/step/atom" and d["higher_is_better"] is False
+    assert d["value"] > 0 and d["cpu_baseline"]["value"] == d["value"] and d["cpu_baseline"]["cores"] >= 1
+    assert d["config"]["natoms"] == 192 * 6 ** 3 and d["config"]["sample_natoms"] == 192
+    assert d["config"]["bench_workload"] == "dpa1_attn" and d["product_native_loaded"] is False
+
+
 def test_reference_arm_model_equals_product_model(pkg):
     """bench.py --impl reference builds its model data without importing the product (oracle/refmodel.py): weights,
     statistics and tables must be bit-identical to the product's SeAModel, or the two arms would time different work."""
