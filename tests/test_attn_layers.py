@@ -117,6 +117,25 @@ def test_product_matches_reference_backends_gpu(gold):
 
 
 @pytest.mark.gpu
+def test_product_fp32_model_gpu(gold):
+    """The float32 model with attention layers end to end (fp32 table, stage kernels, library SGEMMs, four-slice
+    fitting net) against the reference's fp64 PyTorch-backend values: single-precision agreement."""
+    g.load_package()
+    from deepmd_kit_b200.model import DeepPotB200
+
+    model = _model(gold, "cuda", torch.float32)
+    coord, atype, box = g.water_box(1, 0.0)
+    dp = DeepPotB200(model, skin=2.0)
+    e, f, v, ex = dp.eval_device(torch.as_tensor(coord.astype(np.float32)).cuda(), torch.as_tensor(atype).cuda(), box)
+    assert f.dtype == torch.float32
+    ee = abs(float(e) - float(gold["x_pt_energy"])) / abs(float(gold["x_pt_energy"]))
+    fe = rel(f.double().cpu().numpy(), gold["x_pt_force"])
+    ve = rel(v.double().cpu().numpy(), gold["x_pt_virial"])
+    print(f"fp32 attention model vs fp64 reference: energy {ee:.2e} force {fe:.2e} virial {ve:.2e}")
+    assert ee <= 1e-6 and fe <= 1e-5 and ve <= 1e-5  # measured on B200: 5.9e-08, 2.5e-06, 4.0e-06
+
+
+@pytest.mark.gpu
 def test_attention_g2_matches_reference_gpu(gold):
     """The attention output g2 of two atoms (forward only) against the reference's NumPy backend."""
     g.load_package()
