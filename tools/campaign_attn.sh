@@ -1,5 +1,6 @@
 #!/bin/bash
-# DPA-1 attention-layer measurement set on one GPU (outputs under gpurun_out/, copied to profiles/ afterwards)
+# DPA-1 attention-layer measurement set on one GPU (outputs under gpurun_out/, copied to profiles/ afterwards).
+# NOTE: the `ncu --set full` pass over a whole step replays ~600 launches ~40 times each: ~15 minutes of box time.
 mkdir -p gpurun_out
 python -m pytest tests/test_attn_layers.py -q -m gpu > gpurun_out/r02_pytest_attn.log 2>&1; tail -2 gpurun_out/r02_pytest_attn.log
 timeout 400 compute-sanitizer --tool memcheck --error-exitcode 9 python -m pytest tests/test_attn_layers.py -q -m gpu -k "autograd or embed" > gpurun_out/r02_memcheck_attn.log 2>&1; echo "memcheck rc $?"; tail -4 gpurun_out/r02_memcheck_attn.log
