@@ -457,7 +457,7 @@ def run_ours(args):
                 "bench_workload": args.workload,
                 "table": "dp-compress restatement, stride 0.01/0.1, extrapolate 5, random-init weights (seed 1)",
                 "skin": 2.0, "nlist_every": 10, "parallelism": parallelism,
-                "cuda_graph": bool(getattr(dp, "use_graph", False)),
+                "cuda_graph": bool(getattr(dp, "use_graph", False) and getattr(model, "graph_safe", True)),
                 "atom_virial": bool(args.atom_virial),
                 "l2_policy": "per-step working set (tens of GB of env-mat intermediates) is far larger than the 126 MB L2",
                 "energy": energy,
